@@ -1,0 +1,40 @@
+// Host-side description of one conv-family contraction and its launcher (see conv_umma.cuh).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace gct2 {
+
+struct ConvArgs {
+  int mode;                      // MODE_S / MODE_P / MODE_W
+  int B, Hlo, Wlo;               // lo-res spatial extent; the hi-res side is (2*Hlo, 2*Wlo)
+  const __nv_bfloat16* hi;       // hi-res operand (S: A gather; W: G), base already offset to its first channel
+  int ldHi, Chi;                 // pixel stride (elements) and number of channels used
+  const __nv_bfloat16* lo;       // lo-res operand (P: A; W: P)
+  int ldLo, Clo;
+  const __nv_bfloat16* w;        // S/P: bf16 kernel, flat [16][R][Cc] in the Keras layout (HWIO or HWOI)
+  int R, Cc;
+  // epilogue (S/P)
+  int epi;                       // EPI_BIAS_RELU or EPI_DGRAD
+  __nv_bfloat16* out;
+  int ldo;
+  const float* bias;
+  const __nv_bfloat16* act;
+  int ldact, maskN, addOld;
+  float* ws;                     // fp32 split-K workspace (zero on entry, left zero on exit)
+  size_t wsBytes;
+  // W
+  float* dw;                     // fp32 [16][Chi][Clo]
+  // tuning overrides (0 = heuristic)
+  int forceBN, forceSplits;
+};
+
+int conv_init(int device);                       // once per process/device
+int conv_launch(const ConvArgs& a, cudaStream_t stream);
+void conv_set_debug(int key, int value);         // test hook: 0 = MN-major LBO, 1 = MN-major SBO, 2 = verbose
+const char* last_error();
+void set_error(const char* fmt, ...);
+
+}  // namespace gct2

@@ -1,0 +1,384 @@
+// Launcher for the tcgen05 conv family: builds TMA tensor maps, picks the tile shape / split-K factor,
+// and launches conv_umma_kernel (+ the split-K finishing pass).  See conv_umma.cuh for the data flow.
+#include "conv_umma.cuh"
+#include "conv_host.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+namespace gct2 {
+
+// ------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+const char* last_error() { return g_err; }
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------ globals
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static int g_num_sms = 148;
+static int g_mn_lbo = 8192, g_mn_sbo = 1024, g_verbose = 0;
+static bool g_inited = false;
+
+void conv_set_debug(int key, int value) {
+  if (key == 0) g_mn_lbo = value;
+  if (key == 1) g_mn_sbo = value;
+  if (key == 2) g_verbose = value;
+}
+
+template <int MODE, int BN>
+static int set_attr() {
+  cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       227 * 1024);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(conv_umma_kernel<%d,%d>): %s", MODE, BN, cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+int conv_init(int device) {
+  if (g_inited) return 0;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    set_error("cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    return 1;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  if (prop.major != 10) {
+    set_error("gct2 requires an sm_100a device (B200); found sm_%d%d", prop.major, prop.minor);
+    return 1;
+  }
+  g_num_sms = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  int rc = 0;
+  rc |= set_attr<MODE_S, 64>() | set_attr<MODE_S, 128>() | set_attr<MODE_S, 256>();
+  rc |= set_attr<MODE_P, 64>() | set_attr<MODE_P, 128>() | set_attr<MODE_P, 256>();
+  rc |= set_attr<MODE_W, 64>() | set_attr<MODE_W, 128>() | set_attr<MODE_W, 256>();
+  if (rc) return 1;
+  g_inited = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ tensor maps
+static int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                  const cuuint32_t* box) {
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u]", (int)r,
+              rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+              (unsigned long long)(rank > 4 ? dims[4] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0,
+              rank > 3 ? box[3] : 0, rank > 4 ? box[4] : 0);
+    return 1;
+  }
+  return 0;
+}
+
+// hi-res NHWC tensor viewed as (px*ld + c, W/2, py, H/2, B): one box = one filter tap of a pixel tile.
+static int map_hi5(CUtensorMap* m, const __nv_bfloat16* p, int ld, int C, int B, int Hhi, int Whi, int Wt, int Ht,
+                   int Nb) {
+  cuuint64_t dims[5] = {(cuuint64_t)(ld + C), (cuuint64_t)(Whi / 2), 2, (cuuint64_t)(Hhi / 2), (cuuint64_t)B};
+  cuuint64_t st[4] = {(cuuint64_t)2 * ld * 2, (cuuint64_t)Whi * ld * 2, (cuuint64_t)2 * Whi * ld * 2,
+                      (cuuint64_t)Hhi * Whi * ld * 2};
+  cuuint32_t box[5] = {64, (cuuint32_t)Wt, 1, (cuuint32_t)Ht, (cuuint32_t)Nb};
+  return encode(m, p, 5, dims, st, box);
+}
+// lo-res NHWC tensor (C, W, H, B).
+static int map_lo4(CUtensorMap* m, const __nv_bfloat16* p, int ld, int C, int B, int H, int W, int Wt, int Ht,
+                   int Nb) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t st[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)Wt, (cuuint32_t)Ht, (cuuint32_t)Nb};
+  return encode(m, p, 4, dims, st, box);
+}
+// kernel [16][R][Cc] viewed as (Cc, R, 16).
+static int map_w3(CUtensorMap* m, const __nv_bfloat16* p, int R, int Cc, int boxRows) {
+  cuuint64_t dims[3] = {(cuuint64_t)Cc, (cuuint64_t)R, 16};
+  cuuint64_t st[2] = {(cuuint64_t)Cc * 2, (cuuint64_t)R * Cc * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)boxRows, 1};
+  return encode(m, p, 3, dims, st, box);
+}
+
+// ------------------------------------------------------------------------------------ split-K finish
+// ws fp32 [pixels][N] -> bf16 out with the real epilogue; re-zeroes ws for its next user.
+__global__ void splitk_finish_kernel(float* __restrict__ ws, int N, long long pixels, int epi,
+                                     __nv_bfloat16* __restrict__ out, int ldo, const float* __restrict__ bias,
+                                     const __nv_bfloat16* __restrict__ act, int ldact, int maskN, int addOld) {
+  const int vecPerRow = N / 4;
+  const long long total = pixels * vecPerRow;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / vecPerRow;
+    const int n = (int)(i % vecPerRow) * 4;
+    float4* wp = reinterpret_cast<float4*>(ws + pix * N + n);
+    float4 v = *wp;
+    *wp = make_float4(0.f, 0.f, 0.f, 0.f);
+    __nv_bfloat16* o = out + pix * ldo + n;
+    if (epi == EPI_BIAS_RELU) {
+      const float4 b = *reinterpret_cast<const float4*>(bias + n);
+      v.x = fmaxf(v.x + b.x, 0.f);
+      v.y = fmaxf(v.y + b.y, 0.f);
+      v.z = fmaxf(v.z + b.z, 0.f);
+      v.w = fmaxf(v.w + b.w, 0.f);
+    } else {
+      if (addOld) {
+        const uint2 old = *reinterpret_cast<const uint2*>(o);
+        v.x += bf16_lo(old.x);
+        v.y += bf16_hi(old.x);
+        v.z += bf16_lo(old.y);
+        v.w += bf16_hi(old.y);
+      }
+      if (n < maskN) {
+        const uint2 a = *reinterpret_cast<const uint2*>(act + pix * ldact + n);
+        v.x = bf16_lo(a.x) > 0.f ? v.x : 0.f;
+        v.y = bf16_hi(a.x) > 0.f ? v.y : 0.f;
+        v.z = bf16_lo(a.y) > 0.f ? v.z : 0.f;
+        v.w = bf16_hi(a.y) > 0.f ? v.w : 0.f;
+      }
+    }
+    uint2 r;
+    r.x = pack_bf16x2(v.x, v.y);
+    r.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(o) = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------ heuristics
+static int stages_for(int BN) { return BN == 256 ? 4 : (BN == 128 ? 5 : 4); }
+static int occupancy_for(int BN) { return BN == 64 ? 2 : 1; }
+static size_t smem_for(int BN) { return (size_t)stages_for(BN) * (16384 + BN * 128) + 1024 + 256; }
+
+struct Choice {
+  int BN, splits;
+};
+
+static Choice choose(int baseItemsPerN /* items excluding the N split */, int N, int kTotal, bool isW,
+                     int forceBN, int forceSplits) {
+  Choice best{0, 1};
+  double bestCost = 1e30;
+  const int bns[3] = {256, 128, 64};
+  for (int bi = 0; bi < 3; ++bi) {
+    const int BN = bns[bi];
+    if (N % BN) continue;
+    if (forceBN && BN != forceBN) continue;
+    const double tk = BN == 256 ? 1024.0 : (BN == 128 ? 700.0 : 520.0);
+    for (int splits = 1; splits <= 64; splits *= 2) {
+      if (kTotal % splits) break;
+      if (forceSplits && splits != forceSplits) continue;
+      const int kIters = kTotal / splits;
+      const long long items = (long long)baseItemsPerN * (N / BN) * splits;
+      const long long rounds = (items + g_num_sms - 1) / g_num_sms;
+      double epi = 6.0 * BN;
+      if (splits > 1) epi = isW ? 12.0 * BN : 14.0 * BN;
+      double cost = rounds * (1800.0 + kIters * tk + epi);
+      if (splits > 1) cost += isW ? 2500.0 : 6000.0;  // memset / finishing pass
+      if (cost < bestCost) {
+        bestCost = cost;
+        best = Choice{BN, splits};
+      }
+    }
+  }
+  return best;
+}
+
+template <int MODE>
+static cudaError_t launch_bn(int BN, int grid, size_t smem, cudaStream_t st, const CUtensorMap& a,
+                             const CUtensorMap& b, const ConvParams& p) {
+  switch (BN) {
+    case 64: conv_umma_kernel<MODE, 64><<<grid, 192, smem, st>>>(a, b, p); break;
+    case 128: conv_umma_kernel<MODE, 128><<<grid, 192, smem, st>>>(a, b, p); break;
+    default: conv_umma_kernel<MODE, 256><<<grid, 192, smem, st>>>(a, b, p); break;
+  }
+  return cudaGetLastError();
+}
+
+static void pixel_tile(int rows, int H, int W, int* Wt, int* Ht, int* Nb) {
+  int wt = W < 16 ? W : 16;
+  if (rows == 64 && wt > 8) wt = 8;
+  int ht = rows / wt;
+  if (ht > H) ht = H;
+  *Wt = wt;
+  *Ht = ht;
+  *Nb = rows / (wt * ht);
+}
+
+int conv_launch(const ConvArgs& a, cudaStream_t stream) {
+  if (!g_inited) {
+    set_error("gct2_init was not called");
+    return 1;
+  }
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  CUtensorMap mapA, mapB;
+  p.B = a.B;
+  p.Hlo = a.Hlo;
+  p.Wlo = a.Wlo;
+  p.mnLbo = g_mn_lbo;
+  p.mnSbo = g_mn_sbo;
+  const int rows = a.mode == MODE_W ? 64 : 128;
+  pixel_tile(rows, a.Hlo, a.Wlo, &p.Wt, &p.Ht, &p.Nb);
+  if (a.Wlo % p.Wt || a.Hlo % p.Ht || p.Wt * p.Ht * p.Nb != rows) {
+    set_error("unsupported spatial extent %dx%d (tile %dx%dx%d)", a.Hlo, a.Wlo, p.Nb, p.Ht, p.Wt);
+    return 1;
+  }
+  p.tilesX = a.Wlo / p.Wt;
+  p.tilesY = a.Hlo / p.Ht;
+  const int tilesB = (a.B + p.Nb - 1) / p.Nb;
+  const int pixTiles = p.tilesX * p.tilesY * tilesB;
+  int BN = 0;
+
+  if (a.mode == MODE_S || a.mode == MODE_P) {
+    const int Ck = a.mode == MODE_S ? a.Chi : a.Clo;
+    const int N = a.mode == MODE_S ? a.Cc : a.R;
+    const int wk = a.mode == MODE_S ? a.R : a.Cc;
+    if (Ck % 64 || N % 64 || wk != Ck) {
+      set_error("conv: channel counts must be multiples of 64 and match the kernel (Ck=%d N=%d kernel %dx%d)", Ck, N,
+                a.R, a.Cc);
+      return 1;
+    }
+    const int taps = a.mode == MODE_S ? 16 : 4;
+    const int phases = a.mode == MODE_S ? 1 : 4;
+    p.kcPer = Ck / 64;
+    const int kTotal = taps * p.kcPer;
+    Choice c = choose(pixTiles * phases, N, kTotal, false, a.forceBN, a.forceSplits);
+    if (c.BN == 0) {
+      set_error("conv: no tile shape for N=%d", N);
+      return 1;
+    }
+    BN = c.BN;
+    p.mTiles = pixTiles;
+    p.nTiles = N / BN;
+    p.splits = c.splits;
+    p.kIters = kTotal / c.splits;
+    p.numItems = pixTiles * p.nTiles * phases * c.splits;
+    p.N = N;
+    p.Hout = a.mode == MODE_S ? a.Hlo : 2 * a.Hlo;
+    p.Wout = a.mode == MODE_S ? a.Wlo : 2 * a.Wlo;
+    p.out = a.out;
+    p.ldo = a.ldo;
+    p.bias = a.bias;
+    p.act = a.act;
+    p.ldact = a.ldact;
+    p.maskN = a.maskN;
+    p.addOld = a.addOld;
+    p.epi = a.epi;
+    if (c.splits > 1) {
+      const size_t need = (size_t)a.B * p.Hout * p.Wout * N * sizeof(float);
+      if (a.ws == nullptr || a.wsBytes < need) {
+        set_error("conv: split-K workspace too small (%zu < %zu bytes)", a.wsBytes, need);
+        return 1;
+      }
+      p.epi = EPI_WS_ATOMIC;
+      p.ws = a.ws;
+    }
+    if (a.mode == MODE_S) {
+      p.ldG = a.ldHi;
+      if (map_hi5(&mapA, a.hi, a.ldHi, a.Chi, a.B, 2 * a.Hlo, 2 * a.Wlo, p.Wt, p.Ht, p.Nb)) return 1;
+      if (map_w3(&mapB, a.w, a.R, a.Cc, 64)) return 1;
+    } else {
+      if (map_lo4(&mapA, a.lo, a.ldLo, a.Clo, a.B, a.Hlo, a.Wlo, p.Wt, p.Ht, p.Nb)) return 1;
+      if (map_w3(&mapB, a.w, a.R, a.Cc, BN)) return 1;
+    }
+  } else {
+    // wgrad: dw[tap][Chi][Clo]; the M side must be a multiple of 128
+    p.gIsA = (a.Chi % 128 == 0) ? 1 : 0;
+    const int Mch = p.gIsA ? a.Chi : a.Clo;
+    const int Nch = p.gIsA ? a.Clo : a.Chi;
+    if (Mch % 128 || Nch % 64) {
+      set_error("wgrad: unsupported channel counts (%d, %d)", a.Chi, a.Clo);
+      return 1;
+    }
+    const int chunks = pixTiles;
+    Choice c = choose(16 * (Mch / 128), Nch, chunks, true, a.forceBN, a.forceSplits);
+    if (c.BN == 0) {
+      set_error("wgrad: no tile shape for N=%d", Nch);
+      return 1;
+    }
+    BN = c.BN;
+    p.mTiles = Mch / 128;
+    p.nTiles = Nch / BN;
+    p.splits = c.splits;
+    p.kIters = chunks / c.splits;
+    p.numItems = 16 * p.mTiles * p.nTiles * c.splits;
+    p.N = Nch;
+    p.ldG = a.ldHi;
+    p.epi = EPI_WGRAD;
+    p.dw = a.dw;
+    p.tapStride = (long long)a.Chi * a.Clo;
+    p.rowStride = p.gIsA ? a.Clo : 1;
+    p.colStride = p.gIsA ? 1 : a.Clo;
+    p.atomic = c.splits > 1;
+    CUtensorMap mg, mp;
+    if (map_hi5(&mg, a.hi, a.ldHi, a.Chi, a.B, 2 * a.Hlo, 2 * a.Wlo, p.Wt, p.Ht, p.Nb)) return 1;
+    if (map_lo4(&mp, a.lo, a.ldLo, a.Clo, a.B, a.Hlo, a.Wlo, p.Wt, p.Ht, p.Nb)) return 1;
+    mapA = p.gIsA ? mg : mp;
+    mapB = p.gIsA ? mp : mg;
+    if (p.atomic) {
+      cudaError_t e = cudaMemsetAsync(a.dw, 0, (size_t)16 * a.Chi * a.Clo * sizeof(float), stream);
+      if (e != cudaSuccess) {
+        set_error("wgrad memset: %s", cudaGetErrorString(e));
+        return 1;
+      }
+    }
+  }
+
+  p.stages = stages_for(BN);
+  const size_t smem = smem_for(BN);
+  int grid = g_num_sms * occupancy_for(BN);
+  if (grid > p.numItems) grid = p.numItems;
+  if (g_verbose)
+    fprintf(stderr,
+            "gct2 conv mode %d B %d lo %dx%d tile %dx%dx%d BN %d splits %d kIters %d items %d grid %d stages %d smem %zu\n",
+            a.mode, a.B, a.Hlo, a.Wlo, p.Nb, p.Ht, p.Wt, BN, p.splits, p.kIters, p.numItems, grid, p.stages, smem);
+  cudaError_t e;
+  if (a.mode == MODE_S)
+    e = launch_bn<MODE_S>(BN, grid, smem, stream, mapA, mapB, p);
+  else if (a.mode == MODE_P)
+    e = launch_bn<MODE_P>(BN, grid, smem, stream, mapA, mapB, p);
+  else
+    e = launch_bn<MODE_W>(BN, grid, smem, stream, mapA, mapB, p);
+  if (e != cudaSuccess) {
+    set_error("conv_umma_kernel launch: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  if (a.mode != MODE_W && p.splits > 1) {
+    const long long pixels = (long long)a.B * p.Hout * p.Wout;
+    const long long total = pixels * (p.N / 4);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > g_num_sms * 8) blocks = g_num_sms * 8;
+    splitk_finish_kernel<<<blocks, 256, 0, stream>>>(a.ws, p.N, pixels, a.epi, a.out, a.ldo, a.bias, a.act, a.ldact,
+                                                     a.maskN, a.addOld);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      set_error("splitk_finish_kernel launch: %s", cudaGetErrorString(e));
+      return 1;
+    }
+  }
+  return 0;
+}
+
+}  // namespace gct2

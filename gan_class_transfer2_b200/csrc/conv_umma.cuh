@@ -1,0 +1,361 @@
+// Implicit-GEMM 4x4 / stride-2 convolution family on tcgen05 + TMEM, operands staged by TMA.
+//
+// One persistent, warp-specialised kernel template serves all 24 tensor-core contractions of the
+// reference's U-Net step (reference: train.py:145-169 DownShuffle/UpShuffle; the backward passes are
+// implicit in Keras' train_step, SURVEY.md 8(a) rows a2,a3,a8).  Three index maps ("modes"):
+//
+//   MODE_S  strided form     out_lo[pix, n] = sum_{tap(16), k} G_hi[pix @ tap, k] * Wt[tap][k][n]
+//           DownShuffle fprop (G = x, Wt = HWIO kernel) and UpShuffle dgrad (G = dy, Wt = HWOI kernel).
+//           A: K-major im2col tile (5-D TMA box on the parity-split hi-res tensor), B: MN-major weights.
+//   MODE_P  phase form       out_hi[2m+py, 2n+px, n] = sum_{tap(2x2), k} X_lo[(m,n)+d(tap,phase), k] * Wt[tap][n][k]
+//           UpShuffle fprop (Wt = HWOI kernel) and DownShuffle dgrad (Wt = HWIO kernel).
+//           A: K-major shifted tile (4-D TMA box, zero fill at the border), B: K-major weights.
+//   MODE_W  weight gradient  dW[tap][g][p] = sum_pix G_hi[pix @ tap, g] * P_lo[pix, p]
+//           both operands MN-major (pixels are the contraction dim and are the slow smem axis).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue
+// (TMEM -> registers -> global).  Accumulators are double-buffered in TMEM (2 x BN columns) so the
+// epilogue of tile i overlaps the main loop of tile i+1.
+#pragma once
+#include <cuda_bf16.h>
+#include "ptx.cuh"
+
+namespace gct2 {
+
+enum : int { MODE_S = 0, MODE_P = 1, MODE_W = 2 };
+enum : int { EPI_BIAS_RELU = 0, EPI_DGRAD = 1, EPI_WS_ATOMIC = 2, EPI_WGRAD = 3 };
+
+struct ConvParams {
+  int B, Hlo, Wlo;             // lo-res spatial extent (hi-res = 2x)
+  int Wt, Ht, Nb;              // pixel-tile geometry; rows = Nb*Ht*Wt (128 for S/P, 64 for W)
+  int tilesX, tilesY;          // pixel tiles along W and H (batch tiles = mTiles / (tilesX*tilesY))
+  int mTiles;                  // S/P: pixel tiles; W: (M-side channels)/128
+  int nTiles;                  // N / BN
+  int splits;                  // split-K factor
+  int kIters;                  // k-iterations per work item
+  int kcPer;                   // S/P: 64-channel chunks per tap
+  int numItems;                // total work items
+  int stages;                  // smem pipeline depth
+  int ldG;                     // S / W(G operand): pixel stride (elements) of the gathered hi-res tensor
+  int gIsA;                    // W: 1 when the gathered operand supplies the M side
+  int mnLbo, mnSbo;            // MN-major descriptor offsets (bytes)
+  // epilogue
+  int epi;
+  int N;                       // total output columns (S/P) ; W: N-side channels
+  int Hout, Wout;              // output spatial extent (S: lo-res, P: hi-res)
+  __nv_bfloat16* out;          // bf16 output (pixel stride ldo)
+  int ldo;
+  const float* bias;
+  const __nv_bfloat16* act;    // EPI_DGRAD: saved post-ReLU activation co-located with out (pixel stride ldact)
+  int ldact;
+  int maskN;                   // EPI_DGRAD: columns [0,maskN) are ReLU-masked
+  int addOld;                  // EPI_DGRAD: add the value already stored in out (skip-path gradient)
+  float* ws;                   // EPI_WS_ATOMIC: fp32 [outPixels][N]
+  float* dw;                   // EPI_WGRAD: fp32 [16][...]
+  long long tapStride;
+  int rowStride, colStride;    // element strides of the (M-row, N-col) accumulator tile inside one tap
+  int atomic;                  // EPI_WGRAD: accumulate with red.add (split-K) instead of store
+};
+
+struct WorkItem {
+  int mt, nt, ph, split;       // ph: phase (P) or tap (W)
+};
+
+template <int MODE>
+__device__ __forceinline__ WorkItem decode_item(const ConvParams& p, int item) {
+  WorkItem w;
+  w.mt = item % p.mTiles;
+  int r = item / p.mTiles;
+  if (MODE == MODE_W) {
+    w.nt = r % p.nTiles;
+    r /= p.nTiles;
+    w.split = r % p.splits;
+    w.ph = r / p.splits;
+  } else {
+    w.split = r % p.splits;
+    r /= p.splits;
+    w.nt = r % p.nTiles;
+    w.ph = r / p.nTiles;
+  }
+  return w;
+}
+
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+
+template <int MODE, int BN>
+__global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                        const __grid_constant__ CUtensorMap mapB,
+                                                        const ConvParams p) {
+  constexpr int A_BYTES = 128 * 128;  // 128 rows x 64 bf16 (S/P) or 2 blocks of 64 pixels x 64 channels (W)
+  constexpr int B_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int BLK = 64 * 128;       // one 64x64 bf16 block = one TMA box of an MN-major operand
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int S = p.stages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * STAGE_BYTES);
+  uint64_t* empty = full + S;
+  uint64_t* tfull = empty + S;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tilesXY = p.tilesX * p.tilesY;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int item = blockIdx.x; item < p.numItems; item += gridDim.x) {
+        const WorkItem w = decode_item<MODE>(p, item);
+        int x0 = 0, y0 = 0, b0 = 0;
+        if (MODE != MODE_W) {
+          x0 = (w.mt % p.tilesX) * p.Wt;
+          y0 = ((w.mt / p.tilesX) % p.tilesY) * p.Ht;
+          b0 = (w.mt / tilesXY) * p.Nb;
+        }
+        for (int it = 0; it < p.kIters; ++it) {
+          const int kit = w.split * p.kIters + it;
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          if (MODE == MODE_S) {
+            const int tap = kit / p.kcPer, kc = kit % p.kcPer;
+            const int ky = tap >> 2, kx = tap & 3;
+            const int py = (ky + 1) & 1, px = (kx + 1) & 1;
+            const int hy = ((ky + 1) >> 1) - 1, hx = ((kx + 1) >> 1) - 1;
+            tma_load_5d(sa, &mapA, &full[stage], px * p.ldG + kc * 64, x0 + hx, py, y0 + hy, b0);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_3d(sb + j * BLK, &mapB, &full[stage], w.nt * BN + j * 64, kc * 64, tap);
+          } else if (MODE == MODE_P) {
+            const int t4 = kit / p.kcPer, kc = kit % p.kcPer;
+            const int ty = t4 >> 1, tx = t4 & 1;
+            const int py = w.ph >> 1, px = w.ph & 1;
+            const int ky = (1 - py) + 2 * ty, kx = (1 - px) + 2 * tx;
+            tma_load_4d(sa, &mapA, &full[stage], kc * 64, x0 + (px - tx), y0 + (py - ty), b0);
+            tma_load_3d(sb, &mapB, &full[stage], kc * 64, w.nt * BN, ky * 4 + kx);
+          } else {
+            // pixel chunk -> (batch tile, y tile, x tile)
+            const int cx = (kit % p.tilesX) * p.Wt;
+            const int cy = ((kit / p.tilesX) % p.tilesY) * p.Ht;
+            const int cb = (kit / tilesXY) * p.Nb;
+            const int ky = w.ph >> 2, kx = w.ph & 3;
+            const int py = (ky + 1) & 1, px = (kx + 1) & 1;
+            const int hy = ((ky + 1) >> 1) - 1, hx = ((kx + 1) >> 1) - 1;
+            if (p.gIsA) {
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                tma_load_5d(sa + j * BLK, &mapA, &full[stage], px * p.ldG + w.mt * 128 + j * 64, cx + hx, py,
+                            cy + hy, cb);
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_4d(sb + j * BLK, &mapB, &full[stage], w.nt * BN + j * 64, cx, cy, cb);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                tma_load_4d(sa + j * BLK, &mapA, &full[stage], w.mt * 128 + j * 64, cx, cy, cb);
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_5d(sb + j * BLK, &mapB, &full[stage], px * p.ldG + w.nt * BN + j * 64, cx + hx, py,
+                            cy + hy, cb);
+            }
+          }
+          if (++stage == (uint32_t)S) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr int A_MN = (MODE == MODE_W) ? 1 : 0;
+      constexpr int B_MN = (MODE == MODE_P) ? 0 : 1;
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, A_MN, B_MN);
+      const uint32_t a_lbo = A_MN ? (uint32_t)p.mnLbo : 16u, a_sbo = A_MN ? (uint32_t)p.mnSbo : 1024u;
+      const uint32_t b_lbo = B_MN ? (uint32_t)p.mnLbo : 16u, b_sbo = B_MN ? (uint32_t)p.mnSbo : 1024u;
+      constexpr uint32_t a_kstep = A_MN ? 2048u : 32u;  // bytes per UMMA_K = 16 along K
+      constexpr uint32_t b_kstep = B_MN ? 2048u : 32u;
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int item = blockIdx.x; item < p.numItems; item += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int it = 0; it < p.kIters; ++it) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo);
+            const uint64_t db = make_smem_desc(sb + k * b_kstep, b_lbo, b_sbo);
+            umma_bf16(d_tmem, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == (uint32_t)S) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int item = blockIdx.x; item < p.numItems; item += gridDim.x) {
+      const WorkItem w = decode_item<MODE>(p, item);
+      const int n0 = w.nt * BN;
+      // row -> output location
+      bool valid = true;
+      long long pix = 0;
+      if (MODE != MODE_W) {
+        const int xl = r % p.Wt, yl = (r / p.Wt) % p.Ht, bl = r / (p.Wt * p.Ht);
+        const int x = (w.mt % p.tilesX) * p.Wt + xl;
+        const int y = ((w.mt / p.tilesX) % p.tilesY) * p.Ht + yl;
+        const int b = (w.mt / tilesXY) * p.Nb + bl;
+        valid = b < p.B;
+        int oy = y, ox = x;
+        if (MODE == MODE_P) {
+          oy = 2 * y + (w.ph >> 1);
+          ox = 2 * x + (w.ph & 1);
+        }
+        pix = ((long long)b * p.Hout + oy) * p.Wout + ox;
+      }
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + c0, v);
+        tmem_ld_wait();
+        const int n = n0 + c0;
+        if (p.epi == EPI_BIAS_RELU) {
+          if (valid) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
+            uint4* dst = reinterpret_cast<uint4*>(p.out + pix * p.ldo + n);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float4 b0 = __ldg(bp + 2 * g), b1 = __ldg(bp + 2 * g + 1);
+              uint4 o;
+              o.x = pack_bf16x2(fmaxf(__uint_as_float(v[8 * g + 0]) + b0.x, 0.f),
+                                fmaxf(__uint_as_float(v[8 * g + 1]) + b0.y, 0.f));
+              o.y = pack_bf16x2(fmaxf(__uint_as_float(v[8 * g + 2]) + b0.z, 0.f),
+                                fmaxf(__uint_as_float(v[8 * g + 3]) + b0.w, 0.f));
+              o.z = pack_bf16x2(fmaxf(__uint_as_float(v[8 * g + 4]) + b1.x, 0.f),
+                                fmaxf(__uint_as_float(v[8 * g + 5]) + b1.y, 0.f));
+              o.w = pack_bf16x2(fmaxf(__uint_as_float(v[8 * g + 6]) + b1.z, 0.f),
+                                fmaxf(__uint_as_float(v[8 * g + 7]) + b1.w, 0.f));
+              dst[g] = o;
+            }
+          }
+        } else if (p.epi == EPI_DGRAD) {
+          if (valid) {
+            uint4* dst = reinterpret_cast<uint4*>(p.out + pix * p.ldo + n);
+            const uint4* ap = reinterpret_cast<const uint4*>(p.act + pix * p.ldact + n);
+            const bool masked = n < p.maskN;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[8 * g + j]);
+              if (p.addOld) {
+                const uint4 o = dst[g];
+                f[0] += bf16_lo(o.x); f[1] += bf16_hi(o.x); f[2] += bf16_lo(o.y); f[3] += bf16_hi(o.y);
+                f[4] += bf16_lo(o.z); f[5] += bf16_hi(o.z); f[6] += bf16_lo(o.w); f[7] += bf16_hi(o.w);
+              }
+              if (masked) {
+                const uint4 a = __ldg(ap + g);
+                f[0] = bf16_lo(a.x) > 0.f ? f[0] : 0.f; f[1] = bf16_hi(a.x) > 0.f ? f[1] : 0.f;
+                f[2] = bf16_lo(a.y) > 0.f ? f[2] : 0.f; f[3] = bf16_hi(a.y) > 0.f ? f[3] : 0.f;
+                f[4] = bf16_lo(a.z) > 0.f ? f[4] : 0.f; f[5] = bf16_hi(a.z) > 0.f ? f[5] : 0.f;
+                f[6] = bf16_lo(a.w) > 0.f ? f[6] : 0.f; f[7] = bf16_hi(a.w) > 0.f ? f[7] : 0.f;
+              }
+              uint4 o;
+              o.x = pack_bf16x2(f[0], f[1]);
+              o.y = pack_bf16x2(f[2], f[3]);
+              o.z = pack_bf16x2(f[4], f[5]);
+              o.w = pack_bf16x2(f[6], f[7]);
+              dst[g] = o;
+            }
+          }
+        } else if (p.epi == EPI_WS_ATOMIC) {
+          if (valid) {
+            float* dst = p.ws + pix * p.N + n;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) red_add_f32(dst + j, __uint_as_float(v[j]));
+          }
+        } else {  // EPI_WGRAD: row = M-side channel, columns = N-side channels
+          float* base = p.dw + (long long)w.ph * p.tapStride + (long long)(w.mt * 128 + r) * p.rowStride +
+                        (long long)n * p.colStride;
+          if (p.atomic) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) red_add_f32(base + (long long)j * p.colStride, __uint_as_float(v[j]));
+          } else if (p.colStride == 1) {
+            float4* d4 = reinterpret_cast<float4*>(base);
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              d4[g] = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
+                                  __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) base[(long long)j * p.colStride] = __uint_as_float(v[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace gct2

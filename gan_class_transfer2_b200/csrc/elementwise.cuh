@@ -1,0 +1,24 @@
+// Internal declarations of the HBM-bound kernels' launchers (definitions in elementwise.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace gct2 {
+
+void elementwise_set_sms(int n);
+int noise_images(const float* x, const float* eps, const int* t_int, float* noised, int B, int elemsPerImage,
+                 int steps, cudaStream_t st);
+int conv4s2_c3_fprop(const float* x, const float* w, const float* bias, __nv_bfloat16* y, int ldy, int B, int H,
+                     int W, int Cout, cudaStream_t st);
+int conv4s2_c3_wgrad(const float* x, const __nv_bfloat16* dz, int lddz, float* dw, float* db, int B, int H, int W,
+                     int Cout, cudaStream_t st);
+int dense_mse(const __nv_bfloat16* u0, int ldu, const float* noised, const float* x, const float* wd,
+              const float* bd, float* pred, float* loss, __nv_bfloat16* du0, int lddu, float* dwd, float* dbd,
+              long long pixels, int Cu, float invN, int backward, cudaStream_t st);
+int bias_grad(const __nv_bfloat16* dz, int ld, long long rows, int C, float* db, cudaStream_t st);
+int adam_keras(float* w, float* m, float* v, const float* g, __nv_bfloat16* w_bf16, long long n,
+               long long* iterations, float* hyper, float base_lr, int warmup_steps, float beta1, float beta2,
+               float eps, float grad_scale, cudaStream_t st);
+int cast_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t st);
+
+}  // namespace gct2

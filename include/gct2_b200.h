@@ -1,0 +1,112 @@
+/* gct2_b200.h -- C ABI of the B200-native training-step kernels for relgukxilef/GAN-Class-Transfer2.
+ *
+ * The reference (train.py, TensorFlow/Keras) has no FFI of its own: every op below replaces the TensorFlow
+ * library op that one line of train.py expands to.  Each entry point names that line.  A maintainer binds
+ * these with ctypes; the in-repo binding is gan_class_transfer2_b200/_lib.py.
+ *
+ * Conventions
+ *   - all tensor pointers are DEVICE pointers owned by the caller; nothing is allocated or freed here;
+ *   - activations are NHWC bf16 (uint16_t storage), addressed as base + pixel*ld + channel, where `ld` is the
+ *     pixel stride in elements: producers write straight into channel slices of the U-Net's concat buffers
+ *     (train.py:113-119 tf.concat is never materialised as a copy);
+ *   - kernels ("w") are in the Keras variable layouts: Conv2D [4,4,Cin,Cout], Conv2DTranspose [4,4,Cout,Cin];
+ *     the tensor-core ops take the bf16 shadow copy maintained by gct2_adam_keras / gct2_cast_bf16;
+ *   - gradients, Adam state and master weights are fp32;
+ *   - `stream` is a cudaStream_t (CUstream) passed as void*; every call only enqueues work on it (no host
+ *     synchronisation), so a whole step can be captured into a CUDA graph;
+ *   - return value 0 = success; otherwise gct2_last_error() describes the failure (thread-local string);
+ *   - channel counts of tensor-core ops must be multiples of 64; spatial extents powers of two >= 4.
+ */
+#ifndef GCT2_B200_H
+#define GCT2_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCT2_ABI_VERSION 1
+
+int gct2_abi_version(void);
+const char* gct2_last_error(void);
+/* Selects the device, resolves the driver entry points, raises the kernels' shared-memory limits.
+ * Fails (non-zero) when the device is not sm_100. */
+int gct2_init(int device);
+int gct2_num_sms(void);
+/* Test hook (not part of the drop-in surface): key 0/1 override the MN-major UMMA descriptor LBO/SBO bytes,
+ * key 2 = verbose plan logging, key 3 = force N tile, key 4 = force split-K. */
+void gct2_debug_set(int key, int value);
+
+/* train.py:224-234 + :85-93 -- Trainer.call noising with alpha_dash:
+ *   noised = x*sqrt(abar(t)) + eps*sqrt(1-abar(t)), abar(t) = (1 - t/(steps+1))^2 * 0.25.
+ * x, eps, noised: fp32 [B, elems_per_image]; t_int: int32 [B]. RNG (t_int, eps) is an input. */
+int gct2_noise_images(const float* x, const float* eps, const int32_t* t_int, float* noised, int B,
+                      int elems_per_image, int steps, void* stream);
+
+/* train.py:158-169 DownShuffle on the 3-channel image (down0): relu(conv2d(x, w[4,4,3,Cout], s=2, SAME) + b).
+ * x fp32 [B,H,W,3]; w, bias fp32; y bf16 [B,H/2,W/2,Cout] with pixel stride ldy. CUDA-core direct conv. */
+int gct2_conv4s2_c3_fprop(const float* x, const float* w, const float* bias, uint16_t* y, int ldy, int B, int H,
+                          int W, int Cout, void* stream);
+/* Backward of the above w.r.t. kernel and bias (Keras train_step, implicit at train.py:516):
+ * dz bf16 [B,H/2,W/2,Cout] (already ReLU-masked); dw fp32 [4,4,3,Cout]; db fp32 [Cout]. Overwrites dw, db. */
+int gct2_conv4s2_c3_wgrad(const float* x, const uint16_t* dz, int lddz, float* dw, float* db, int B, int H, int W,
+                          int Cout, void* stream);
+
+/* train.py:158-169 DownShuffle forward (Cin % 64 == 0): y = relu(conv2d(x, w[4,4,Cin,Cout], s=2, SAME) + b).
+ * x bf16 [B,H,W,Cin] stride ldx; y bf16 [B,H/2,W/2,Cout] stride ldy. tcgen05 implicit GEMM (strided form).
+ * ws: fp32 split-K workspace of >= B*(H/2)*(W/2)*Cout floats, zero on entry, returned zeroed. */
+int gct2_conv4s2_fprop(const uint16_t* x, int ldx, const uint16_t* w, const float* bias, uint16_t* y, int ldy,
+                       int B, int H, int W, int Cin, int Cout, float* ws, size_t ws_bytes, void* stream);
+/* Backward-data of DownShuffle: dx[b,iy,ix,ci] (+)= sum dy[b,oy,ox,co]*w[ky,kx,ci,co], then ReLU-masked by the
+ * producer's saved output: dx = (acc + (add_old ? dx : 0)) * (act > 0).  dy bf16 [B,H/2,W/2,Cout]; dx, act bf16
+ * [B,H,W,Cin].  tcgen05 implicit GEMM (phase form).  ws >= B*H*W*Cin floats. */
+int gct2_conv4s2_dgrad(const uint16_t* dy, int lddy, const uint16_t* w, uint16_t* dx, int lddx,
+                       const uint16_t* act, int ldact, int add_old, int B, int H, int W, int Cin, int Cout,
+                       float* ws, size_t ws_bytes, void* stream);
+/* Backward-filter of DownShuffle: dw[ky,kx,ci,co] = sum x[b,2oy-1+ky,2ox-1+kx,ci]*dy[b,oy,ox,co]; fp32, overwritten. */
+int gct2_conv4s2_wgrad(const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, int B, int H, int W,
+                       int Cin, int Cout, void* stream);
+
+/* train.py:145-156 UpShuffle forward: y = relu(conv2d_transpose(x, w[4,4,Cout,Cin], s=2, SAME) + b).
+ * x bf16 [B,H,W,Cin] stride ldx; y bf16 [B,2H,2W,Cout] stride ldy (phase form). ws >= B*2H*2W*Cout floats. */
+int gct2_convT4s2_fprop(const uint16_t* x, int ldx, const uint16_t* w, const float* bias, uint16_t* y, int ldy,
+                        int B, int H, int W, int Cin, int Cout, float* ws, size_t ws_bytes, void* stream);
+/* Backward-data of UpShuffle: dx[b,iy,ix,ci] = sum dy[b,2iy-1+ky,2ix-1+kx,co]*w[ky,kx,co,ci]; channels
+ * [0,mask_channels) are ReLU-masked by act (the saved activation co-located with dx), the rest stored raw
+ * (they are the skip-path gradient, consumed by gct2_conv4s2_dgrad(add_old=1)).  Strided form.
+ * dy bf16 [B,2H,2W,Cout]; dx, act bf16 [B,H,W,Cin]. ws >= B*H*W*Cin floats. */
+int gct2_convT4s2_dgrad(const uint16_t* dy, int lddy, const uint16_t* w, uint16_t* dx, int lddx,
+                        const uint16_t* act, int ldact, int mask_channels, int B, int H, int W, int Cin, int Cout,
+                        float* ws, size_t ws_bytes, void* stream);
+/* Backward-filter of UpShuffle: dw[ky,kx,co,ci] = sum dy[b,2iy-1+ky,2ix-1+kx,co]*x[b,iy,ix,ci]; fp32, overwritten. */
+int gct2_convT4s2_wgrad(const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, int B, int H, int W,
+                        int Cin, int Cout, void* stream);
+
+/* BiasAddGrad of every conv layer: db[c] = sum over rows of dz[row*ld + c]; dz bf16, db fp32 (overwritten). */
+int gct2_bias_grad(const uint16_t* dz, int ld, long long rows, int C, float* db, void* stream);
+
+/* train.py:198-202 Dense(3) on concat([up0_out(64), noised(3)]) fused with train.py:262-272 MSE and their
+ * backward.  u0 bf16 [pixels,64] stride ldu; noised, x fp32 [pixels,3]; wd fp32 [67,3]; bd fp32 [3].
+ * pred (nullable) fp32 [pixels,3]; loss: one fp32, overwritten with sum((pred-x)^2)*inv_n; inv_n = 1/(global
+ * element count) so data-parallel ranks produce partial means.  When backward != 0 also writes
+ * du0 = (u0>0) * (dpred . wd^T) (bf16, stride lddu), dwd fp32 [67,3], dbd fp32 [3], dpred = 2(pred-x)*inv_n. */
+int gct2_dense_mse(const uint16_t* u0, int ldu, const float* noised, const float* x, const float* wd,
+                   const float* bd, float* pred, float* loss, uint16_t* du0, int lddu, float* dwd, float* dbd,
+                   long long pixels, int Cu, float inv_n, int backward, void* stream);
+
+/* train.py:50-65,75 -- tf.keras.optimizers.Adam(WarmUp(base_lr, warmup_steps)), Keras formula (epsilon added to
+ * the un-bias-corrected sqrt(v)).  All n parameters live in flat fp32 buffers; w_bf16 receives the shadow copy.
+ * iterations: device int64 (0-based step count, incremented here); hyper: device float[2] scratch
+ * (alpha, lr of this step).  g is multiplied by grad_scale first (1 for summed data-parallel gradients). */
+int gct2_adam_keras(float* w, float* m, float* v, const float* g, uint16_t* w_bf16, long long n,
+                    long long* iterations, float* hyper, float base_lr, int warmup_steps, float beta1, float beta2,
+                    float eps, float grad_scale, void* stream);
+/* fp32 -> bf16 (round to nearest even); builds the first shadow copy of the weights. */
+int gct2_cast_bf16(const float* src, uint16_t* dst, long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCT2_B200_H */

@@ -1,0 +1,302 @@
+"""CPU oracle: an fp32 PyTorch-CPU restatement of the training step of the reference's train.py.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product path (gan_class_transfer2_b200/) imports this module;
+only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may.
+
+PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures, TensorFlow is
+not installable in this environment, and train.py cannot even be imported without a GPU and the author's
+dataset (train.py:40,305,315).  This restatement therefore follows the TensorFlow/Keras semantics documented
+in SURVEY.md Appendix A and is pinned only by its own self-consistency tests (tests/test_oracle.py): parameter
+count 41 691 660, shape walk, conv-transpose == autograd-dgrad of the SAME-padded strided conv, the 4-phase
+identity, Dense == 1x1 conv, a finite-difference gradient check and an Adam closed-form known answer.
+
+What follows what (reference = /root/reference/train.py):
+  Config            :17-36   module-level hyper-parameters
+  alpha_dash        :85-93
+  WarmUp            :50-65   ; keras_adam_update: tf.keras.optimizers.Adam defaults (:75), Keras formula
+  variable_specs    :175-204 construction recursion (Denoiser.__init__) + Keras variable layouts/order
+  glorot_init       :134,149,162 (explicit glorot_uniform) and the Keras Dense default
+  denoiser_forward  :97-121 (concat branch), :123-143 (block_depth=0 -> identity), :145-169, :206-215
+  trainer_loss      :223-236,243-244,262-263,272 (RNG t_int/eps are *inputs*: TF never seeds them)
+  identity          :171-173
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+
+@dataclasses.dataclass(frozen=True)
+class Config:
+    """train.py:17-36 defaults."""
+    size: int = 256
+    pixel_size: int = 128
+    max_size: int = 512
+    block_depth: int = 0
+    octaves: int = 6
+    batch_size: int = 1
+    steps: int = 200
+    warm_up: int = 2000
+    base_lr: float = 2e-5
+    beta1: float = 0.9
+    beta2: float = 0.999
+    epsilon: float = 1e-7
+
+    def down_filters(self, i: int) -> int:  # train.py:181
+        return min(self.pixel_size * 2 ** i, self.max_size)
+
+    def up_filters(self, i: int) -> int:  # train.py:188
+        return min(self.pixel_size * 2 ** i // 2, self.max_size)
+
+
+DEFAULT = Config()
+#: shrunken config used by the fast tests (keeps a 4x4 bottleneck like the reference's comment at train.py:21)
+TINY = Config(size=64, pixel_size=128, max_size=256, octaves=4)
+
+
+def alpha_dash(t, steps: int = 200):
+    """train.py:85-93: (1 - t/(steps+1))**2 * 0.25 ; works on tensors and Python numbers."""
+    t = t / (steps + 1)
+    return (1 - t) ** 2 * 0.25
+
+
+class WarmUp:
+    """train.py:50-65. `step` is the 0-based optimizer iteration."""
+
+    def __init__(self, base: float, warmup_steps: int):
+        self.base = base
+        self.warmup_steps = warmup_steps
+
+    def __call__(self, step: int) -> float:
+        if step < self.warmup_steps:
+            return float(torch.tensor(self.base, dtype=torch.float32) * torch.tensor(float(step + 1), dtype=torch.float32)
+                         / (self.warmup_steps + 1))
+        return self.base
+
+
+# --------------------------------------------------------------------------------------------- variables
+def variable_specs(cfg: Config = DEFAULT) -> List[Tuple[str, Tuple[int, ...]]]:
+    """Keras variable order and layouts: down0..down{n-1}, up{n-1}..up0, dense; kernel then bias.
+
+    Conv2D.kernel [4,4,Cin,Cout]; Conv2DTranspose.kernel [4,4,Cout,Cin]; Dense.kernel [Cin,3].
+    """
+    specs: List[Tuple[str, Tuple[int, ...]]] = []
+    cin = 3
+    skip_c = []  # channels of the tensor entering Residual_i (the skip)
+    for i in range(cfg.octaves):
+        co = cfg.down_filters(i)
+        specs.append((f"down{i}/kernel", (4, 4, cin, co)))
+        specs.append((f"down{i}/bias", (co,)))
+        skip_c.append(cin)
+        cin = co
+    # innermost: up_{n-1} consumes down_{n-1}'s output; up_i (i < n-1) consumes concat[up_{i+1}, down_i]
+    for i in reversed(range(cfg.octaves)):
+        if i == cfg.octaves - 1:
+            ci = cfg.down_filters(i)
+        else:
+            ci = cfg.up_filters(i + 1) + cfg.down_filters(i)
+        co = cfg.up_filters(i)
+        specs.append((f"up{i}/kernel", (4, 4, co, ci)))
+        specs.append((f"up{i}/bias", (co,)))
+    specs.append(("dense/kernel", (cfg.up_filters(0) + 3, 3)))
+    specs.append(("dense/bias", (3,)))
+    return specs
+
+
+def param_count(cfg: Config = DEFAULT) -> int:
+    return sum(math.prod(s) for _, s in variable_specs(cfg))
+
+
+def glorot_init(cfg: Config = DEFAULT, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """glorot_uniform kernels (limit sqrt(6/(fan_in+fan_out)), fans = receptive field x last two dims), zero biases."""
+    g = torch.Generator().manual_seed(seed)
+    out: Dict[str, torch.Tensor] = {}
+    for name, shape in variable_specs(cfg):
+        if name.endswith("bias"):
+            out[name] = torch.zeros(shape, dtype=torch.float32)
+            continue
+        rf = math.prod(shape[:-2]) if len(shape) > 2 else 1
+        fan_a, fan_b = shape[-2] * rf, shape[-1] * rf
+        limit = math.sqrt(6.0 / (fan_a + fan_b))
+        out[name] = (torch.rand(shape, generator=g, dtype=torch.float32) * 2 - 1) * limit
+    return out
+
+
+def synthetic_batch(cfg: Config, batch: int, seed: int = 1):
+    """x = k/128 - 1 with k ~ U{0..255} (decode_file's value grid, train.py:292),
+    t_int ~ U{1..steps} (train.py:224-226), eps ~ N(0,1) (train.py:227)."""
+    g = torch.Generator().manual_seed(seed)
+    k = torch.randint(0, 256, (batch, cfg.size, cfg.size, 3), generator=g)
+    x = k.to(torch.float32) / 128 - 1
+    t_int = torch.randint(1, cfg.steps + 1, (batch,), generator=g, dtype=torch.int32)
+    eps = torch.randn((batch, cfg.size, cfg.size, 3), generator=g, dtype=torch.float32)
+    return x, t_int, eps
+
+
+# --------------------------------------------------------------------------------------------- layers
+def _nchw(x):
+    return x.permute(0, 3, 1, 2)
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1)
+
+
+def down_shuffle(x_nhwc, kernel_hwio, bias):
+    """train.py:158-169: relu(Conv2D(filters, 4, 2, 'same')(x)); SAME for k4/s2/even N is pad (1,1)."""
+    w = kernel_hwio.permute(3, 2, 0, 1)  # -> [Cout, Cin, kh, kw]
+    return _nhwc(F.relu(F.conv2d(_nchw(x_nhwc), w, bias, stride=2, padding=1)))
+
+
+def up_shuffle(x_nhwc, kernel_hwoi, bias):
+    """train.py:145-156: relu(Conv2DTranspose(filters, 4, 2, 'same')(x)) == conv_transpose2d(k4,s2,p1), no flip
+    (SURVEY A.2): out[2*iy-1+ky] += x[iy] * w[ky]."""
+    w = kernel_hwoi.permute(3, 2, 0, 1)  # [4,4,Cout,Cin] -> [Cin, Cout, kh, kw]
+    return _nhwc(F.relu(F.conv_transpose2d(_nchw(x_nhwc), w, bias, stride=2, padding=1)))
+
+
+def dense(x_nhwc, kernel, bias):
+    """train.py:198-202: Keras Dense contracts the last axis only; no activation."""
+    return x_nhwc @ kernel + bias
+
+
+def denoiser_forward(weights: Dict[str, torch.Tensor], x_nhwc: torch.Tensor, cfg: Config = DEFAULT,
+                     taps: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+    """Denoiser.call (train.py:206-215): `t` is ignored by the reference; Block is identity at block_depth=0.
+
+    Residual_i(h) = concat([Up_i(Residual_{i+1}(Down_i(h))), h], -1) with the module output FIRST (train.py:113-119).
+    `taps`, when given, collects every layer output (post-ReLU) by name.
+    """
+
+    def residual(i: int, h):
+        d = down_shuffle(h, weights[f"down{i}/kernel"], weights[f"down{i}/bias"])
+        if taps is not None:
+            taps[f"down{i}"] = d
+        inner = residual(i + 1, d) if i + 1 < cfg.octaves else d
+        u = up_shuffle(inner, weights[f"up{i}/kernel"], weights[f"up{i}/bias"])
+        if taps is not None:
+            taps[f"up{i}"] = u
+        return torch.cat([u, h], dim=-1)
+
+    cat0 = residual(0, x_nhwc)
+    pred = dense(cat0, weights["dense/kernel"], weights["dense/bias"])
+    if taps is not None:
+        taps["pred"] = pred
+    return pred
+
+
+def noise_images(x, t_int, eps, cfg: Config = DEFAULT):
+    """train.py:224-234. x [B,H,W,3] fp32, t_int [B] int32, eps like x."""
+    t = t_int.to(x.dtype)[:, None, None, None]
+    a = alpha_dash(t, cfg.steps)
+    return x * a ** 0.5 + eps * (1 - a) ** 0.5
+
+
+def trainer_loss(weights, x, t_int, eps, cfg: Config = DEFAULT, taps=None, global_elems: Optional[int] = None):
+    """Trainer.call with predict_x=True (train.py:223-236,243-244,262-263,272) -> scalar mean squared error.
+
+    global_elems overrides the mean's denominator (data-parallel shards of one global batch)."""
+    noised = noise_images(x, t_int, eps, cfg)
+    if taps is not None:
+        taps["noised"] = noised
+    pred = denoiser_forward(weights, noised, cfg, taps)
+    sq = (x.to(torch.float32) - pred.to(torch.float32)) ** 2
+    if global_elems is None:
+        return sq.mean()
+    return sq.sum() / global_elems
+
+
+def identity(y_true, y_pred):
+    """train.py:171-173."""
+    return torch.mean(y_pred)
+
+
+def loss_and_grads(weights, x, t_int, eps, cfg: Config = DEFAULT, want_taps: bool = False,
+                   global_elems: Optional[int] = None):
+    """One forward+backward (what Keras train_step's GradientTape does, train.py:516): returns
+    (loss, {name: grad}, taps) where taps also carries d(loss)/d(layer output) under 'd<name>' when requested."""
+    ws = {k: v.detach().clone().requires_grad_(True) for k, v in weights.items()}
+    taps: Optional[Dict[str, torch.Tensor]] = {} if want_taps else None
+    loss = identity(None, trainer_loss(ws, x, t_int, eps, cfg, taps, global_elems))
+    if want_taps:
+        for v in taps.values():
+            if v.requires_grad:
+                v.retain_grad()
+    loss.backward()
+    grads = {k: v.grad.detach() for k, v in ws.items()}
+    out_taps: Dict[str, torch.Tensor] = {}
+    if want_taps:
+        for k, v in taps.items():
+            out_taps[k] = v.detach()
+            if v.grad is not None:
+                out_taps["d" + k] = v.grad.detach()
+    return loss.detach(), grads, out_taps
+
+
+# --------------------------------------------------------------------------------------------- optimizer
+def keras_adam_update(w, m, v, g, iteration: int, cfg: Config = DEFAULT):
+    """tf.keras.optimizers.Adam (OptimizerV2) dense update, SURVEY.md A.6, in place on fp32 tensors.
+
+    t = iteration+1; lr = WarmUp(iteration); alpha = lr*sqrt(1-b2^t)/(1-b1^t);
+    m += (g-m)(1-b1); v += (g^2-v)(1-b2); w -= alpha*m/(sqrt(v)+eps)   (epsilon on the un-corrected sqrt(v))."""
+    lr = WarmUp(cfg.base_lr, cfg.warm_up)(iteration)
+    t = float(iteration + 1)
+    b1p = torch.tensor(cfg.beta1, dtype=torch.float32) ** t
+    b2p = torch.tensor(cfg.beta2, dtype=torch.float32) ** t
+    alpha = (torch.tensor(lr, dtype=torch.float32) * torch.sqrt(1 - b2p) / (1 - b1p)).item()
+    m.add_((g - m) * (1 - cfg.beta1))
+    v.add_((g * g - v) * (1 - cfg.beta2))
+    w.sub_(alpha * m / (torch.sqrt(v) + cfg.epsilon))
+    return alpha
+
+
+class OracleTrainer:
+    """Stateful restatement of `trainer.fit`'s per-step work (train.py:511-523): loss, grads, Adam."""
+
+    def __init__(self, cfg: Config = DEFAULT, weights: Optional[Dict[str, torch.Tensor]] = None, seed: int = 0):
+        self.cfg = cfg
+        self.weights = {k: v.clone() for k, v in (weights or glorot_init(cfg, seed)).items()}
+        self.m = {k: torch.zeros_like(v) for k, v in self.weights.items()}
+        self.v = {k: torch.zeros_like(v) for k, v in self.weights.items()}
+        self.iterations = 0
+
+    def train_step(self, x, t_int, eps) -> float:
+        loss, grads, _ = loss_and_grads(self.weights, x, t_int, eps, self.cfg)
+        for k in self.weights:
+            keras_adam_update(self.weights[k], self.m[k], self.v[k], grads[k], self.iterations, self.cfg)
+        self.iterations += 1
+        return float(loss)
+
+
+# --------------------------------------------------------------------------------------------- bf16 emulation
+def bf16_round(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def flops_per_image(cfg: Config = DEFAULT) -> Dict[str, float]:
+    """FLOP convention of SURVEY.md 8(a): conv 2*Ho*Wo*16*Cin*Cout, convT 2*Hin*Win*16*Cin*Cout, dense 2*H*W*Cin*Cout."""
+    fwd = 0.0
+    down0 = 0.0
+    h = cfg.size
+    for name, shape in variable_specs(cfg):
+        if not name.endswith("kernel"):
+            continue
+        if name.startswith("down"):
+            i = int(name[4:name.index("/")])
+            ho = cfg.size // 2 ** (i + 1)
+            f = 2.0 * ho * ho * 16 * shape[2] * shape[3]
+            if i == 0:
+                down0 = f
+        elif name.startswith("up"):
+            i = int(name[2:name.index("/")])
+            hin = cfg.size // 2 ** (i + 1)
+            f = 2.0 * hin * hin * 16 * shape[2] * shape[3]
+        else:
+            f = 2.0 * h * h * shape[0] * shape[1]
+        fwd += f
+    bwd = 2 * fwd - down0
+    return {"fwd": fwd, "bwd": bwd, "step": fwd + bwd}
