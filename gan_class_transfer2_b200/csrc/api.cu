@@ -58,6 +58,7 @@ int gct2_init(int device) {
   return 0;
 }
 int gct2_num_sms(void) { return g_sms; }
+long long gct2_launch_count(void) { return launch_count(); }
 
 void gct2_debug_set(int key, int value) {
   if (key == 3)

@@ -35,6 +35,8 @@ int conv_init(int device);                       // once per process/device
 int conv_launch(const ConvArgs& a, cudaStream_t stream);
 void conv_set_debug(int key, int value);         // test hook: 0 = MN-major LBO, 1 = MN-major SBO, 2 = verbose
 const char* last_error();
+void count_launch(int n = 1);                   // kernels/memsets enqueued by this library (gct2_launch_count)
+long long launch_count();
 void set_error(const char* fmt, ...);
 
 }  // namespace gct2

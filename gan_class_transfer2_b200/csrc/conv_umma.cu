@@ -19,6 +19,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static long long g_launches = 0;
+void count_launch(int n) { g_launches += n; }
+long long launch_count() { return g_launches; }
+
 // ------------------------------------------------------------------------------------ globals
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -339,6 +343,7 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     mapB = p.gIsA ? mp : mg;
     if (p.atomic) {
       cudaError_t e = cudaMemsetAsync(a.dw, 0, (size_t)16 * a.Chi * a.Clo * sizeof(float), stream);
+      count_launch();
       if (e != cudaSuccess) {
         set_error("wgrad memset: %s", cudaGetErrorString(e));
         return 1;
@@ -365,6 +370,7 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     set_error("conv_umma_kernel launch: %s", cudaGetErrorString(e));
     return 1;
   }
+  count_launch();
   if (a.mode != MODE_W && p.splits > 1) {
     const long long pixels = (long long)a.B * p.Hout * p.Wout;
     const long long total = pixels * (p.N / 4);
@@ -377,6 +383,7 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
       set_error("splitk_finish_kernel launch: %s", cudaGetErrorString(e));
       return 1;
     }
+    count_launch();
   }
   return 0;
 }

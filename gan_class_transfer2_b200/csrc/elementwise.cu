@@ -22,6 +22,7 @@ void elementwise_set_sms(int n) { g_ew_sms = n; }
       set_error("%s launch: %s", name, cudaGetErrorString(e__));      \
       return 1;                                                       \
     }                                                                 \
+    count_launch();                                                   \
   } while (0)
 
 __device__ __forceinline__ float warp_sum(float v) {

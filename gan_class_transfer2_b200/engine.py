@@ -1,0 +1,369 @@
+"""Step engine: owns the HBM-resident state of the reference's training step and sequences the kernels.
+
+What it replaces: everything Keras does for ``trainer.fit`` per step in the reference (train.py:516-523) --
+``Trainer.call`` (:223-272), ``Denoiser.call`` (:206-215), the GradientTape backward and ``Adam.apply_gradients``
+(:75) -- as one fixed launch sequence over pre-allocated buffers, optionally captured into a CUDA graph.
+
+Data layout in HBM (B = per-GPU batch, S = size, n = octaves; all activations NHWC bf16):
+  noised            fp32 [B,S,S,3]                        train.py:231-234
+  cat[j], j=1..n-1  bf16 [B,S/2^j,S/2^j, up_c[j]+down_c[j-1]]   the tf.concat of Residual (train.py:113-119) is never
+                    materialised: up_j writes channels [0,up_c[j]), down_{j-1} writes the rest
+  bot               bf16 [B,S/2^n,S/2^n,down_c[n-1]]      bottleneck (down_{n-1} output)
+  u0                bf16 [B,S,S,up_c[0]]                  up_0 output; Dense(3) reads u0 and noised separately
+  gcat[j], gbot, gu0   same shapes: gradients w.r.t. the *pre-activation* of the producing layer (ReLU mask applied)
+  w, m, v, g        fp32 flat [P] in Keras variable order (down0..down{n-1}, up{n-1}..up0, dense; kernel, bias)
+  w16               bf16 flat [P] shadow copy read by the tensor-core kernels (rewritten by the Adam kernel)
+Backward walks the flat gradient buffer from its end to its start (dense, up0..up{n-1}, down{n-1}..down0), so the
+data-parallel buckets are contiguous tail-to-head ranges that become ready in order.
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+
+
+@dataclasses.dataclass(frozen=True)
+class NetConfig:
+    """Hyper-parameters of train.py:17-36 that shape the network and the optimiser."""
+    size: int = 256
+    pixel_size: int = 128
+    max_size: int = 512
+    octaves: int = 6
+    steps: int = 200
+    warm_up: int = 2000
+    base_lr: float = 2e-5
+    beta1: float = 0.9
+    beta2: float = 0.999
+    epsilon: float = 1e-7
+
+    def down_c(self, i: int) -> int:  # train.py:181
+        return min(self.pixel_size * 2 ** i, self.max_size)
+
+    def up_c(self, i: int) -> int:  # train.py:188
+        return min(self.pixel_size * 2 ** i // 2, self.max_size)
+
+    def up_in(self, i: int) -> int:
+        return self.down_c(i) if i == self.octaves - 1 else self.up_c(i + 1) + self.down_c(i)
+
+    def validate(self) -> None:
+        n = self.octaves
+        if n < 1 or self.size % (2 ** n) or (self.size >> n) < 4:
+            raise ValueError(f"size {self.size} must be a multiple of 2^octaves with a bottleneck of at least 4x4")
+        if self.size & (self.size - 1):
+            raise ValueError("size must be a power of two")
+        for i in range(n):
+            if self.down_c(i) % 64 or self.up_c(i) % 64:
+                raise ValueError("channel counts must be multiples of 64 (tensor-core tile granularity)")
+        if self.down_c(0) % 128:
+            raise ValueError("down0 filters must be a multiple of 128")
+        if self.up_c(0) not in (64, 128):
+            raise ValueError("the fused Dense(3)+MSE kernel supports 64 or 128 up0 channels")
+
+
+def variable_specs(cfg: NetConfig) -> List[Tuple[str, Tuple[int, ...]]]:
+    """Keras variable order and layouts of trainer.trainable_variables (train.py:175-204)."""
+    specs: List[Tuple[str, Tuple[int, ...]]] = []
+    cin = 3
+    for i in range(cfg.octaves):
+        specs += [(f"down{i}/kernel", (4, 4, cin, cfg.down_c(i))), (f"down{i}/bias", (cfg.down_c(i),))]
+        cin = cfg.down_c(i)
+    for i in reversed(range(cfg.octaves)):
+        specs += [(f"up{i}/kernel", (4, 4, cfg.up_c(i), cfg.up_in(i))), (f"up{i}/bias", (cfg.up_c(i),))]
+    specs += [("dense/kernel", (cfg.up_c(0) + 3, 3)), ("dense/bias", (3,))]
+    return specs
+
+
+def glorot_uniform(shape, generator) -> torch.Tensor:
+    """Keras glorot_uniform (train.py:134,149,162; Dense default): U(+-sqrt(6/(fan_in+fan_out)))."""
+    rf = math.prod(shape[:-2]) if len(shape) > 2 else 1
+    limit = math.sqrt(6.0 / (shape[-2] * rf + shape[-1] * rf))
+    return (torch.rand(shape, generator=generator, dtype=torch.float32) * 2 - 1) * limit
+
+
+class DataParallel:
+    """Data-parallel context: the batch shards over ranks, gradient buckets are summed with NCCL."""
+
+    def __init__(self, group=None, bucket_bytes: int = 48 << 20, overlap: bool = True):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.bucket_bytes = bucket_bytes
+        self.overlap = overlap
+
+
+class UNetEngine:
+    def __init__(self, cfg: NetConfig, batch: int, device=None, dp: Optional[DataParallel] = None,
+                 use_graph: bool = False):
+        cfg.validate()
+        self.cfg = cfg
+        self.B = batch
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.dp = dp
+        self.use_graph = use_graph
+        self._graph = None
+        self._graph_launches = 0
+        dev, n, S, B = self.device, cfg.octaves, cfg.size, batch
+        from . import _lib
+        _lib.init(self.device.index or 0)
+
+        # ---- parameters, flat in Keras order
+        self.specs = variable_specs(cfg)
+        self.offsets: Dict[str, Tuple[int, int]] = {}
+        off = 0
+        for name, shape in self.specs:
+            cnt = math.prod(shape)
+            self.offsets[name] = (off, cnt)
+            off += cnt
+        self.P = off
+        if self.P % 4:
+            raise ValueError("parameter count must be a multiple of 4")
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.w = torch.zeros(self.P, **f32)
+        self.m = torch.zeros(self.P, **f32)
+        self.v = torch.zeros(self.P, **f32)
+        self.g = torch.zeros(self.P, **f32)
+        self.w16 = torch.zeros(self.P, dtype=torch.bfloat16, device=dev)
+        self.iterations = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.hyper = torch.zeros(2, **f32)
+
+        # ---- activations and their gradients
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        self.x = torch.zeros(B, S, S, 3, **f32)
+        self.eps = torch.zeros(B, S, S, 3, **f32)
+        self.t_int = torch.ones(B, dtype=torch.int32, device=dev)
+        self.noised = torch.zeros(B, S, S, 3, **f32)
+        self.pred = torch.zeros(B, S, S, 3, **f32)
+        self.loss = torch.zeros(1, **f32)
+        self.cat: Dict[int, torch.Tensor] = {}
+        self.gcat: Dict[int, torch.Tensor] = {}
+        for j in range(1, n):
+            shape = (B, S >> j, S >> j, cfg.up_c(j) + cfg.down_c(j - 1))
+            self.cat[j] = torch.zeros(shape, **bf)
+            self.gcat[j] = torch.zeros(shape, **bf)
+        self.bot = torch.zeros(B, S >> n, S >> n, cfg.down_c(n - 1), **bf)
+        self.gbot = torch.zeros_like(self.bot)
+        self.u0 = torch.zeros(B, S, S, cfg.up_c(0), **bf)
+        self.gu0 = torch.zeros_like(self.u0)
+        biggest = max([self.u0.numel(), self.bot.numel()] + [c.numel() for c in self.cat.values()])
+        self.ws = ops.Workspace(4 * biggest, dev)
+        self.global_batch = B * (dp.world if dp else 1)
+        self._buckets = self._make_buckets() if dp else []
+
+    # ------------------------------------------------------------------------------------------ parameter access
+    def view(self, buf: torch.Tensor, name: str) -> torch.Tensor:
+        off, cnt = self.offsets[name]
+        return buf[off:off + cnt].view(dict(self.specs)[name])
+
+    def load_weights(self, weights: Dict[str, torch.Tensor], reset_optimizer: bool = True) -> None:
+        for name, shape in self.specs:
+            t = weights[name]
+            if tuple(t.shape) != tuple(shape):
+                raise ValueError(f"{name}: expected shape {shape}, got {tuple(t.shape)}")
+            self.view(self.w, name).copy_(t.to(torch.float32))
+        ops.cast_bf16(self.w, self.w16)
+        if reset_optimizer:
+            self.m.zero_()
+            self.v.zero_()
+            self.iterations.zero_()
+        self._graph = None
+
+    def init_glorot(self, seed: int = 0) -> None:
+        gen = torch.Generator().manual_seed(seed)
+        self.load_weights({name: torch.zeros(shape) if name.endswith("bias") else glorot_uniform(shape, gen)
+                           for name, shape in self.specs})
+
+    def weights(self) -> Dict[str, torch.Tensor]:
+        return {name: self.view(self.w, name).detach().clone() for name, _ in self.specs}
+
+    def grads(self) -> Dict[str, torch.Tensor]:
+        return {name: self.view(self.g, name).detach().clone() for name, _ in self.specs}
+
+    # ------------------------------------------------------------------------------------------ buffer wiring
+    def down_in(self, i: int) -> torch.Tensor:
+        """Input of DownShuffle i (i >= 1): the skip slice of cat[i] (= down_{i-1}'s output)."""
+        return self.cat[i][..., self.cfg.up_c(i):]
+
+    def down_out(self, i: int) -> torch.Tensor:
+        return self.bot if i == self.cfg.octaves - 1 else self.cat[i + 1][..., self.cfg.up_c(i + 1):]
+
+    def gdown_out(self, i: int) -> torch.Tensor:
+        return self.gbot if i == self.cfg.octaves - 1 else self.gcat[i + 1][..., self.cfg.up_c(i + 1):]
+
+    def up_in_buf(self, i: int) -> torch.Tensor:
+        return self.bot if i == self.cfg.octaves - 1 else self.cat[i + 1]
+
+    def gup_in_buf(self, i: int) -> torch.Tensor:
+        return self.gbot if i == self.cfg.octaves - 1 else self.gcat[i + 1]
+
+    def up_out(self, i: int) -> torch.Tensor:
+        return self.u0 if i == 0 else self.cat[i][..., :self.cfg.up_c(i)]
+
+    def gup_out(self, i: int) -> torch.Tensor:
+        return self.gu0 if i == 0 else self.gcat[i][..., :self.cfg.up_c(i)]
+
+    # ------------------------------------------------------------------------------------------ forward / backward
+    def _forward(self, want_pred: bool, backward: bool, inv_n: float) -> None:
+        cfg, n = self.cfg, self.cfg.octaves
+        ops.conv4s2_c3_fprop(self.noised, self.view(self.w, "down0/kernel"), self.view(self.w, "down0/bias"),
+                             self.down_out(0))
+        for i in range(1, n):
+            ops.conv4s2_fprop(self.down_in(i), self.view(self.w16, f"down{i}/kernel"),
+                              self.view(self.w, f"down{i}/bias"), self.down_out(i), self.ws)
+        for i in reversed(range(n)):
+            ops.convT4s2_fprop(self.up_in_buf(i), self.view(self.w16, f"up{i}/kernel"),
+                               self.view(self.w, f"up{i}/bias"), self.up_out(i), self.ws)
+        ops.dense_mse(self.u0, self.noised, self.x, self.view(self.w, "dense/kernel"), self.view(self.w, "dense/bias"),
+                      self.loss, inv_n, pred=self.pred if want_pred else None,
+                      du0=self.gu0 if backward else None, dwd=self.view(self.g, "dense/kernel") if backward else None,
+                      dbd=self.view(self.g, "dense/bias") if backward else None)
+
+    def _backward(self) -> None:
+        cfg, n = self.cfg, self.cfg.octaves
+        self._bucket_ready("dense/kernel")
+        for i in range(n):  # up0 .. up{n-1}
+            dz = self.gup_out(i)
+            ops.convT4s2_wgrad(self.up_in_buf(i), dz, self.view(self.g, f"up{i}/kernel"))
+            ops.bias_grad(dz, self.view(self.g, f"up{i}/bias"))
+            self._bucket_ready(f"up{i}/kernel")
+            mask = cfg.down_c(i) if i == n - 1 else cfg.up_c(i + 1)
+            ops.convT4s2_dgrad(dz, self.view(self.w16, f"up{i}/kernel"), self.gup_in_buf(i), self.up_in_buf(i), mask,
+                               self.ws)
+        for i in reversed(range(1, n)):  # down{n-1} .. down1
+            dz = self.gdown_out(i)
+            ops.conv4s2_wgrad(self.down_in(i), dz, self.view(self.g, f"down{i}/kernel"))
+            ops.bias_grad(dz, self.view(self.g, f"down{i}/bias"))
+            self._bucket_ready(f"down{i}/kernel")
+            # total gradient of down_{i-1}'s output = skip-path part (already stored raw by up_{i-1}'s dgrad) + this
+            ops.conv4s2_dgrad(dz, self.view(self.w16, f"down{i}/kernel"), self.gcat[i][..., cfg.up_c(i):],
+                              self.down_in(i), True, self.ws)
+        ops.conv4s2_c3_wgrad(self.noised, self.gdown_out(0), self.view(self.g, "down0/kernel"),
+                             self.view(self.g, "down0/bias"))
+        self._bucket_ready("down0/kernel")
+
+    # ------------------------------------------------------------------------------------------ data parallel
+    def _make_buckets(self) -> List[Tuple[int, int, str]]:
+        """Contiguous [start, end) ranges of the flat gradient buffer, tail to head, each closed by the layer whose
+        weight gradient completes it."""
+        order = ["dense"] + [f"up{i}" for i in range(self.cfg.octaves)] + \
+                [f"down{i}" for i in reversed(range(self.cfg.octaves))]
+        buckets: List[Tuple[int, int, str]] = []
+        end = self.P
+        cur_end = end
+        for layer in order:
+            start = self.offsets[f"{layer}/kernel"][0]
+            if (cur_end - start) * 4 >= self.dp.bucket_bytes or layer == order[-1]:
+                buckets.append((start, cur_end, f"{layer}/kernel"))
+                cur_end = start
+        return buckets
+
+    def _bucket_ready(self, name: str) -> None:
+        if not self.dp or self.dp.world == 1:
+            return
+        for start, end, trigger in self._buckets:
+            if trigger == name:
+                if self.dp.overlap:
+                    self._pending.append(self.dp.dist.all_reduce(self.g[start:end], group=self.dp.group, async_op=True))
+                else:
+                    self._deferred.append((start, end))
+
+    def _finish_allreduce(self) -> None:
+        if not self.dp or self.dp.world == 1:
+            return
+        for start, end in self._deferred:
+            self.dp.dist.all_reduce(self.g[start:end], group=self.dp.group)
+        for work in self._pending:
+            work.wait()
+        self.dp.dist.all_reduce(self.loss, group=self.dp.group)
+
+    # ------------------------------------------------------------------------------------------ public steps
+    def _step_body(self) -> None:
+        cfg = self.cfg
+        self._pending, self._deferred = [], []
+        inv_n = 1.0 / (self.global_batch * cfg.size * cfg.size * 3)
+        ops.noise_images(self.x, self.eps, self.t_int, self.noised, cfg.steps)
+        self._forward(want_pred=False, backward=True, inv_n=inv_n)
+        self._backward()
+        self._finish_allreduce()
+        ops.adam_keras(self.w, self.m, self.v, self.g, self.w16, self.iterations, self.hyper, cfg.base_lr, cfg.warm_up,
+                       cfg.beta1, cfg.beta2, cfg.epsilon, 1.0)
+
+    def set_batch(self, x: torch.Tensor, t_int: Optional[torch.Tensor] = None,
+                  eps: Optional[torch.Tensor] = None) -> None:
+        """Stages one batch into the engine's input buffers (host tensors are copied asynchronously).  t_int / eps
+        default to fresh device-side draws: U{1..steps} and N(0,1) as in train.py:224-227."""
+        self.x.copy_(x, non_blocking=True)
+        if t_int is None:
+            self.t_int.random_(1, self.cfg.steps + 1)
+        else:
+            self.t_int.copy_(t_int, non_blocking=True)
+        if eps is None:
+            self.eps.normal_()
+        else:
+            self.eps.copy_(eps, non_blocking=True)
+
+    def train_step(self, x: torch.Tensor, t_int: Optional[torch.Tensor] = None,
+                   eps: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One training step on the batch x [B,S,S,3] fp32 (host or device).  Returns the device scalar loss
+        (global mean over all ranks).  Everything is enqueued on the current stream; nothing synchronises."""
+        self.set_batch(x, t_int, eps)
+        self.run_step()
+        return self.loss
+
+    def run_step(self) -> None:
+        """The step on whatever set_batch staged (the part bench.py times as `value`)."""
+        if not self.use_graph:
+            self._step_body()
+            return
+        if self._graph is None:
+            # warm up once eagerly on a side stream (lazy inits must not happen under capture), then capture
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                saved = (self.w.clone(), self.m.clone(), self.v.clone(), self.w16.clone(), self.iterations.clone())
+                self._step_body()
+                for dst, src in zip((self.w, self.m, self.v, self.w16, self.iterations), saved):
+                    dst.copy_(src)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            before = ops.launch_count()
+            with torch.cuda.graph(graph):
+                self._step_body()
+            self._graph_launches = ops.launch_count() - before
+            self._graph = graph
+        self._graph.replay()
+
+    def launches_per_step(self) -> int:
+        """Kernels of ours one step enqueues (counted inside the C library; graph replays re-issue the same nodes)."""
+        if self.use_graph and self._graph is not None:
+            return self._graph_launches
+        before = ops.launch_count()
+        saved = (self.w.clone(), self.m.clone(), self.v.clone(), self.w16.clone(), self.iterations.clone())
+        self._step_body()
+        for dst, src in zip((self.w, self.m, self.v, self.w16, self.iterations), saved):
+            dst.copy_(src)
+        return ops.launch_count() - before
+
+    def loss_and_grads(self, x, t_int, eps) -> torch.Tensor:
+        """Forward + backward without the optimiser update (parity tests compare self.g with the oracle)."""
+        self.set_batch(x, t_int, eps)
+        self._pending, self._deferred = [], []
+        inv_n = 1.0 / (self.global_batch * self.cfg.size * self.cfg.size * 3)
+        ops.noise_images(self.x, self.eps, self.t_int, self.noised, self.cfg.steps)
+        self._forward(want_pred=True, backward=True, inv_n=inv_n)
+        self._backward()
+        self._finish_allreduce()
+        return self.loss
+
+    def denoise(self, noised: torch.Tensor) -> torch.Tensor:
+        """Denoiser.call (train.py:206-215): forward only on an already-noised image; returns the fp32 prediction."""
+        self.noised.copy_(noised, non_blocking=True)
+        self.x.copy_(self.noised)
+        self._forward(want_pred=True, backward=False, inv_n=1.0)
+        return self.pred

@@ -1,0 +1,163 @@
+"""Tensor-level wrappers over the C ABI (include/gct2_b200.h).
+
+Each function takes torch CUDA tensors (used only as device-memory handles), derives the pixel strides the
+kernels need from the tensors' own strides -- so a channel slice ``cat[..., a:b]`` of a concat buffer is
+passed as-is and the reference's ``tf.concat`` (train.py:113-119) never becomes a copy -- and enqueues the
+kernel on the current CUDA stream.  There is no fallback: a missing library or a non-sm_100 device raises.
+
+Activation tensors are NHWC bf16; kernels are in the Keras layouts (Conv2D [4,4,Cin,Cout], Conv2DTranspose
+[4,4,Cout,Cin]) as bf16 shadow copies; gradients and optimizer state are fp32.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import check, current_stream, ptr
+
+
+def launch_count() -> int:
+    """Kernels this library has enqueued so far in this process (counted inside the C library)."""
+    return int(_lib.load().gct2_launch_count())
+
+
+def _lib_for(t: torch.Tensor):
+    if not t.is_cuda:
+        raise _lib.Gct2Error("gct2 ops need CUDA tensors: there is no CPU path")
+    return _lib.init(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+def _nhwc(t: torch.Tensor, dtype) -> int:
+    """Checks a [B,H,W,C] (possibly channel-sliced) view and returns its pixel stride in elements."""
+    if t.dtype != dtype or t.dim() != 4 or t.stride(3) != 1:
+        raise _lib.Gct2Error(f"expected an NHWC {dtype} tensor with unit channel stride, got {t.dtype} {tuple(t.shape)} "
+                             f"strides {t.stride()}")
+    ld = t.stride(2)
+    if t.stride(1) != ld * t.shape[2] or (t.shape[0] > 1 and t.stride(0) != ld * t.shape[1] * t.shape[2]):
+        raise _lib.Gct2Error(f"tensor is not a channel slice of a dense NHWC buffer: strides {t.stride()}")
+    return ld
+
+
+class Workspace:
+    """fp32 split-K scratch shared by all conv calls on one stream (zero on entry, returned zeroed)."""
+
+    def __init__(self, nbytes: int, device):
+        self.buf = torch.zeros(max(nbytes, 16) // 4, dtype=torch.float32, device=device)
+
+    @property
+    def nbytes(self) -> int:
+        return self.buf.numel() * 4
+
+
+def noise_images(x, eps, t_int, out, steps: int = 200):
+    """train.py:224-234: out = x*sqrt(abar(t)) + eps*sqrt(1-abar(t)); x, eps, out fp32 [B,H,W,3]; t_int int32 [B]."""
+    lib = _lib_for(x)
+    B = x.shape[0]
+    check(lib.gct2_noise_images(ptr(x), ptr(eps), ptr(t_int), ptr(out), B, x.numel() // B, steps, current_stream()))
+    return out
+
+
+def conv4s2_c3_fprop(x, w, bias, y):
+    """DownShuffle on the fp32 3-channel image (train.py:158-169, down0). w fp32 [4,4,3,Cout]."""
+    lib = _lib_for(x)
+    B, H, W, _ = x.shape
+    check(lib.gct2_conv4s2_c3_fprop(ptr(x), ptr(w), ptr(bias), ptr(y), _nhwc(y, torch.bfloat16), B, H, W, y.shape[3],
+                                    current_stream()))
+    return y
+
+
+def conv4s2_c3_wgrad(x, dz, dw, db):
+    lib = _lib_for(x)
+    B, H, W, _ = x.shape
+    check(lib.gct2_conv4s2_c3_wgrad(ptr(x), ptr(dz), _nhwc(dz, torch.bfloat16), ptr(dw), ptr(db), B, H, W, dz.shape[3],
+                                    current_stream()))
+
+
+def conv4s2_fprop(x, w, bias, y, ws: Workspace):
+    """DownShuffle forward (train.py:158-169): y = relu(conv2d(x, w, s=2, SAME) + b).  w bf16 [4,4,Cin,Cout]."""
+    lib = _lib_for(x)
+    B, H, W, Cin = x.shape
+    check(lib.gct2_conv4s2_fprop(ptr(x), _nhwc(x, torch.bfloat16), ptr(w), ptr(bias), ptr(y), _nhwc(y, torch.bfloat16),
+                                 B, H, W, Cin, y.shape[3], ptr(ws.buf), ws.nbytes, current_stream()))
+    return y
+
+
+def conv4s2_dgrad(dy, w, dx, act, add_old: bool, ws: Workspace):
+    """Backward-data of DownShuffle, fused with the ReLU mask of the layer that produced the input and the add of
+    the skip-path gradient already sitting in dx."""
+    lib = _lib_for(dy)
+    B, H, W, Cin = dx.shape
+    check(lib.gct2_conv4s2_dgrad(ptr(dy), _nhwc(dy, torch.bfloat16), ptr(w), ptr(dx), _nhwc(dx, torch.bfloat16),
+                                 ptr(act), _nhwc(act, torch.bfloat16), int(add_old), B, H, W, Cin, dy.shape[3],
+                                 ptr(ws.buf), ws.nbytes, current_stream()))
+    return dx
+
+
+def conv4s2_wgrad(x, dy, dw):
+    lib = _lib_for(x)
+    B, H, W, Cin = x.shape
+    check(lib.gct2_conv4s2_wgrad(ptr(x), _nhwc(x, torch.bfloat16), ptr(dy), _nhwc(dy, torch.bfloat16), ptr(dw), B, H, W,
+                                 Cin, dy.shape[3], current_stream()))
+    return dw
+
+
+def convT4s2_fprop(x, w, bias, y, ws: Workspace):
+    """UpShuffle forward (train.py:145-156): y = relu(conv2d_transpose(x, w, s=2, SAME) + b). w bf16 [4,4,Cout,Cin]."""
+    lib = _lib_for(x)
+    B, H, W, Cin = x.shape
+    check(lib.gct2_convT4s2_fprop(ptr(x), _nhwc(x, torch.bfloat16), ptr(w), ptr(bias), ptr(y),
+                                  _nhwc(y, torch.bfloat16), B, H, W, Cin, y.shape[3], ptr(ws.buf), ws.nbytes,
+                                  current_stream()))
+    return y
+
+
+def convT4s2_dgrad(dy, w, dx, act, mask_channels: int, ws: Workspace):
+    """Backward-data of UpShuffle; channels [0, mask_channels) of dx are ReLU-masked by act, the rest stored raw."""
+    lib = _lib_for(dy)
+    B, H, W, Cin = dx.shape
+    check(lib.gct2_convT4s2_dgrad(ptr(dy), _nhwc(dy, torch.bfloat16), ptr(w), ptr(dx), _nhwc(dx, torch.bfloat16),
+                                  ptr(act), _nhwc(act, torch.bfloat16), mask_channels, B, H, W, Cin, dy.shape[3],
+                                  ptr(ws.buf), ws.nbytes, current_stream()))
+    return dx
+
+
+def convT4s2_wgrad(x, dy, dw):
+    lib = _lib_for(x)
+    B, H, W, Cin = x.shape
+    check(lib.gct2_convT4s2_wgrad(ptr(x), _nhwc(x, torch.bfloat16), ptr(dy), _nhwc(dy, torch.bfloat16), ptr(dw), B, H, W,
+                                  Cin, dy.shape[3], current_stream()))
+    return dw
+
+
+def bias_grad(dz, db):
+    lib = _lib_for(dz)
+    ld = _nhwc(dz, torch.bfloat16)
+    rows = dz.shape[0] * dz.shape[1] * dz.shape[2]
+    check(lib.gct2_bias_grad(ptr(dz), ld, rows, dz.shape[3], ptr(db), current_stream()))
+    return db
+
+
+def dense_mse(u0, noised, x, wd, bd, loss, inv_n: float, pred=None, du0=None, dwd=None, dbd=None):
+    """Dense(3) on concat([u0, noised]) (train.py:198-202) fused with the MSE (train.py:262-272) and, when du0 is
+    given, their backward."""
+    lib = _lib_for(u0)
+    backward = du0 is not None
+    pixels = u0.shape[0] * u0.shape[1] * u0.shape[2]
+    check(lib.gct2_dense_mse(ptr(u0), _nhwc(u0, torch.bfloat16), ptr(noised), ptr(x), ptr(wd), ptr(bd), ptr(pred),
+                             ptr(loss), ptr(du0), _nhwc(du0, torch.bfloat16) if backward else 0, ptr(dwd), ptr(dbd),
+                             pixels, u0.shape[3], inv_n, int(backward), current_stream()))
+    return loss
+
+
+def adam_keras(w, m, v, g, w_bf16, iterations, hyper, base_lr: float, warmup_steps: int, beta1: float = 0.9,
+               beta2: float = 0.999, eps: float = 1e-7, grad_scale: float = 1.0):
+    """tf.keras.optimizers.Adam(WarmUp(base_lr, warmup_steps)) on flat fp32 buffers (train.py:50-65,75)."""
+    lib = _lib_for(w)
+    check(lib.gct2_adam_keras(ptr(w), ptr(m), ptr(v), ptr(g), ptr(w_bf16), w.numel(), ptr(iterations), ptr(hyper),
+                              base_lr, warmup_steps, beta1, beta2, eps, grad_scale, current_stream()))
+
+
+def cast_bf16(src, dst):
+    lib = _lib_for(src)
+    check(lib.gct2_cast_bf16(ptr(src), ptr(dst), src.numel(), current_stream()))
+    return dst

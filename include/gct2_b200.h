@@ -35,6 +35,8 @@ const char* gct2_last_error(void);
  * Fails (non-zero) when the device is not sm_100. */
 int gct2_init(int device);
 int gct2_num_sms(void);
+/* Number of kernels (and memset nodes of split-K paths) this library has enqueued so far in this process. */
+long long gct2_launch_count(void);
 /* Test hook (not part of the drop-in surface): key 0/1 override the MN-major UMMA descriptor LBO/SBO bytes,
  * key 2 = verbose plan logging, key 3 = force N tile, key 4 = force split-K. */
 void gct2_debug_set(int key, int value);

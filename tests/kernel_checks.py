@@ -1,0 +1,355 @@
+"""Per-kernel parity checks: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Shared by tests/test_kernels_gpu.py (pytest, -m gpu) and tools/diag_kernels.py (prints every metric even when a
+case fails).  Each check returns {"name", "err": rel-L2 error, "max": max abs error / max |ref|, "tol"}.
+Tolerances: bf16 outputs carry one rounding (2^-9 relative) on top of fp32 accumulation-order noise -> rel-L2
+<= 4e-3; fp32 outputs (weight/bias gradients, loss) only differ by accumulation order -> rel-L2 <= 2e-5 * sqrt(K).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+from oracle import oracle as O
+
+BF16_TOL = 4e-3
+F32_TOL = 3e-4
+
+
+def _dev():
+    return torch.device("cuda", 0)
+
+
+def _bf(t):
+    return t.to(torch.bfloat16)
+
+
+def _metrics(name, got, ref, tol):
+    got = got.detach().float().cpu()
+    ref = ref.detach().float().cpu()
+    denom = ref.norm().item() or 1.0
+    err = (got - ref).norm().item() / denom
+    mx = (got - ref).abs().max().item() / (ref.abs().max().item() or 1.0)
+    bad = not math.isfinite(err)
+    return {"name": name, "err": float("inf") if bad else err, "max": mx, "tol": tol}
+
+
+def _rand(shape, gen, scale=1.0):
+    return (torch.randn(shape, generator=gen) * scale)
+
+
+def _ops():
+    from gan_class_transfer2_b200 import ops
+    return ops
+
+
+def _slice_buf(B, H, W, C, pad_front, pad_back, dev, fill=None):
+    """A [B,H,W,C] bf16 view living inside a wider NHWC buffer (exercises pixel strides / concat slices)."""
+    full = torch.full((B, H, W, pad_front + C + pad_back), 7.0 if fill is None else fill, dtype=torch.bfloat16,
+                      device=dev)
+    return full, full[..., pad_front:pad_front + C]
+
+
+# ---------------------------------------------------------------------------------------------- conv (down)
+def check_conv_fprop(B, H, Cin, Cout, seed=0, pad=64):
+    ops = _ops()
+    g = torch.Generator().manual_seed(seed)
+    x = _bf(_rand((B, H, H, Cin), g))
+    w = _bf(_rand((4, 4, Cin, Cout), g, 1.0 / math.sqrt(16 * Cin)))
+    b = _rand((Cout,), g, 0.1)
+    ref = O.down_shuffle(x.float(), w.float(), b)
+    dev = _dev()
+    xfull, xv = _slice_buf(B, H, H, Cin, pad, 0, dev)
+    xv.copy_(x)
+    yfull, yv = _slice_buf(B, H // 2, H // 2, Cout, 0, pad, dev)
+    ws = ops.Workspace(4 * B * (H // 2) ** 2 * Cout, dev)
+    ops.conv4s2_fprop(xv, w.to(dev), b.to(dev), yv, ws)
+    torch.cuda.synchronize()
+    m = _metrics(f"conv4s2_fprop B{B} H{H} {Cin}->{Cout}", yv, ref, BF16_TOL)
+    m["pad_intact"] = bool((yfull[..., Cout:] == 7.0).all().item()) if pad else True
+    m["ws_zero"] = bool((ws.buf == 0).all().item())
+    return m
+
+
+def check_conv_dgrad(B, H, Cin, Cout, add_old=True, seed=1, pad=64):
+    ops = _ops()
+    g = torch.Generator().manual_seed(seed)
+    dy = _bf(_rand((B, H // 2, H // 2, Cout), g))
+    w = _bf(_rand((4, 4, Cin, Cout), g, 1.0 / math.sqrt(16 * Cin)))
+    act = _bf(_rand((B, H, H, Cin), g).clamp_min(0))
+    old = _bf(_rand((B, H, H, Cin), g))
+    xr = torch.zeros(B, H, H, Cin, requires_grad=True)
+    y = F.conv2d(xr.permute(0, 3, 1, 2), w.float().permute(3, 2, 0, 1), None, stride=2, padding=1)
+    y.backward(dy.float().permute(0, 3, 1, 2))
+    ref = xr.grad
+    if add_old:
+        ref = ref + old.float()
+    ref = ref * (act.float() > 0)
+    dev = _dev()
+    _, dyv = _slice_buf(B, H // 2, H // 2, Cout, 0, pad, dev)
+    dyv.copy_(dy)
+    dxfull, dxv = _slice_buf(B, H, H, Cin, pad, 0, dev)
+    dxv.copy_(old)
+    _, actv = _slice_buf(B, H, H, Cin, pad, 0, dev)
+    actv.copy_(act)
+    ws = ops.Workspace(4 * B * H * H * Cin, dev)
+    ops.conv4s2_dgrad(dyv, w.to(dev), dxv, actv, add_old, ws)
+    torch.cuda.synchronize()
+    m = _metrics(f"conv4s2_dgrad B{B} H{H} {Cin}<-{Cout} add{int(add_old)}", dxv, ref, BF16_TOL)
+    m["pad_intact"] = bool((dxfull[..., :pad] == 7.0).all().item()) if pad else True
+    m["ws_zero"] = bool((ws.buf == 0).all().item())
+    return m
+
+
+def check_conv_wgrad(B, H, Cin, Cout, seed=2, pad=64):
+    ops = _ops()
+    g = torch.Generator().manual_seed(seed)
+    x = _bf(_rand((B, H, H, Cin), g))
+    dy = _bf(_rand((B, H // 2, H // 2, Cout), g))
+    wr = torch.zeros(4, 4, Cin, Cout, requires_grad=True)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), wr.permute(3, 2, 0, 1), None, stride=2, padding=1)
+    y.backward(dy.float().permute(0, 3, 1, 2))
+    ref = wr.grad
+    dev = _dev()
+    _, xv = _slice_buf(B, H, H, Cin, pad, 0, dev)
+    xv.copy_(x)
+    _, dyv = _slice_buf(B, H // 2, H // 2, Cout, 0, pad, dev)
+    dyv.copy_(dy)
+    dw = torch.full((4, 4, Cin, Cout), 3.0, dtype=torch.float32, device=dev)
+    ops.conv4s2_wgrad(xv, dyv, dw)
+    torch.cuda.synchronize()
+    return _metrics(f"conv4s2_wgrad B{B} H{H} {Cin}x{Cout}", dw, ref, F32_TOL)
+
+
+# ---------------------------------------------------------------------------------------------- convT (up)
+def check_convT_fprop(B, H, Cin, Cout, seed=3, pad=64):
+    ops = _ops()
+    g = torch.Generator().manual_seed(seed)
+    x = _bf(_rand((B, H, H, Cin), g))
+    w = _bf(_rand((4, 4, Cout, Cin), g, 1.0 / math.sqrt(4 * Cin)))
+    b = _rand((Cout,), g, 0.1)
+    ref = O.up_shuffle(x.float(), w.float(), b)
+    dev = _dev()
+    _, xv = _slice_buf(B, H, H, Cin, 0, pad, dev)
+    xv.copy_(x)
+    yfull, yv = _slice_buf(B, 2 * H, 2 * H, Cout, 0, pad, dev)
+    ws = ops.Workspace(4 * B * 4 * H * H * Cout, dev)
+    ops.convT4s2_fprop(xv, w.to(dev), b.to(dev), yv, ws)
+    torch.cuda.synchronize()
+    m = _metrics(f"convT4s2_fprop B{B} H{H} {Cin}->{Cout}", yv, ref, BF16_TOL)
+    m["pad_intact"] = bool((yfull[..., Cout:] == 7.0).all().item()) if pad else True
+    m["ws_zero"] = bool((ws.buf == 0).all().item())
+    return m
+
+
+def check_convT_dgrad(B, H, Cin, Cout, mask_channels=None, seed=4, pad=64):
+    ops = _ops()
+    g = torch.Generator().manual_seed(seed)
+    if mask_channels is None:
+        mask_channels = Cin // 2
+    dy = _bf(_rand((B, 2 * H, 2 * H, Cout), g))
+    w = _bf(_rand((4, 4, Cout, Cin), g, 1.0 / math.sqrt(16 * Cout)))
+    act = _bf(_rand((B, H, H, Cin), g).clamp_min(0))
+    xr = torch.zeros(B, H, H, Cin, requires_grad=True)
+    y = F.conv_transpose2d(xr.permute(0, 3, 1, 2), w.float().permute(3, 2, 0, 1), None, stride=2, padding=1)
+    y.backward(dy.float().permute(0, 3, 1, 2))
+    ref = xr.grad.clone()
+    ref[..., :mask_channels] *= (act.float()[..., :mask_channels] > 0)
+    dev = _dev()
+    _, dyv = _slice_buf(B, 2 * H, 2 * H, Cout, 0, pad, dev)
+    dyv.copy_(dy)
+    dxfull, dxv = _slice_buf(B, H, H, Cin, 0, pad, dev)
+    _, actv = _slice_buf(B, H, H, Cin, 0, pad, dev)
+    actv.copy_(act)
+    ws = ops.Workspace(4 * B * H * H * Cin, dev)
+    ops.convT4s2_dgrad(dyv, w.to(dev), dxv, actv, mask_channels, ws)
+    torch.cuda.synchronize()
+    m = _metrics(f"convT4s2_dgrad B{B} H{H} {Cin}<-{Cout} mask{mask_channels}", dxv, ref, BF16_TOL)
+    m["pad_intact"] = bool((dxfull[..., Cin:] == 7.0).all().item()) if pad else True
+    m["ws_zero"] = bool((ws.buf == 0).all().item())
+    return m
+
+
+def check_convT_wgrad(B, H, Cin, Cout, seed=5, pad=64):
+    ops = _ops()
+    g = torch.Generator().manual_seed(seed)
+    x = _bf(_rand((B, H, H, Cin), g))
+    dy = _bf(_rand((B, 2 * H, 2 * H, Cout), g))
+    wr = torch.zeros(4, 4, Cout, Cin, requires_grad=True)
+    y = F.conv_transpose2d(x.float().permute(0, 3, 1, 2), wr.permute(3, 2, 0, 1), None, stride=2, padding=1)
+    y.backward(dy.float().permute(0, 3, 1, 2))
+    ref = wr.grad
+    dev = _dev()
+    _, xv = _slice_buf(B, H, H, Cin, 0, pad, dev)
+    xv.copy_(x)
+    _, dyv = _slice_buf(B, 2 * H, 2 * H, Cout, 0, pad, dev)
+    dyv.copy_(dy)
+    dw = torch.full((4, 4, Cout, Cin), 3.0, dtype=torch.float32, device=dev)
+    ops.convT4s2_wgrad(xv, dyv, dw)
+    torch.cuda.synchronize()
+    return _metrics(f"convT4s2_wgrad B{B} H{H} {Cout}x{Cin}", dw, ref, F32_TOL)
+
+
+# ---------------------------------------------------------------------------------------------- HBM-bound kernels
+def check_noise(B=3, H=32, seed=6):
+    ops = _ops()
+    cfg = O.Config(size=H)
+    x, t_int, eps = O.synthetic_batch(cfg, B, seed)
+    ref = O.noise_images(x, t_int, eps, cfg)
+    dev = _dev()
+    out = torch.empty_like(x, device=dev)
+    ops.noise_images(x.to(dev), eps.to(dev), t_int.to(dev), out, cfg.steps)
+    torch.cuda.synchronize()
+    return _metrics(f"noise_images B{B} H{H}", out, ref, 2e-6)
+
+
+def check_c3_fprop(B=2, H=32, Cout=128, seed=7):
+    ops = _ops()
+    g = torch.Generator().manual_seed(seed)
+    x = _rand((B, H, H, 3), g)
+    w = _rand((4, 4, 3, Cout), g, 0.2)
+    b = _rand((Cout,), g, 0.1)
+    ref = O.down_shuffle(x, w, b)
+    dev = _dev()
+    yfull, yv = _slice_buf(B, H // 2, H // 2, Cout, 64, 0, dev)
+    ops.conv4s2_c3_fprop(x.to(dev), w.to(dev), b.to(dev), yv)
+    torch.cuda.synchronize()
+    m = _metrics(f"conv4s2_c3_fprop B{B} H{H} 3->{Cout}", yv, ref, BF16_TOL)
+    m["pad_intact"] = bool((yfull[..., :64] == 7.0).all().item())
+    return m
+
+
+def check_c3_wgrad(B=2, H=32, Cout=128, seed=8):
+    ops = _ops()
+    g = torch.Generator().manual_seed(seed)
+    x = _rand((B, H, H, 3), g)
+    dz = _bf(_rand((B, H // 2, H // 2, Cout), g))
+    wr = torch.zeros(4, 4, 3, Cout, requires_grad=True)
+    y = F.conv2d(x.permute(0, 3, 1, 2), wr.permute(3, 2, 0, 1), None, stride=2, padding=1)
+    y.backward(dz.float().permute(0, 3, 1, 2))
+    dev = _dev()
+    _, dzv = _slice_buf(B, H // 2, H // 2, Cout, 64, 0, dev)
+    dzv.copy_(dz)
+    dw = torch.full((4, 4, 3, Cout), 3.0, device=dev)
+    db = torch.full((Cout,), 3.0, device=dev)
+    ops.conv4s2_c3_wgrad(x.to(dev), dzv, dw, db)
+    torch.cuda.synchronize()
+    m = _metrics(f"conv4s2_c3_wgrad B{B} H{H}", dw, wr.grad, F32_TOL)
+    m2 = _metrics("c3 bias grad", db, dz.float().sum((0, 1, 2)), F32_TOL)
+    m["err"] = max(m["err"], m2["err"])
+    return m
+
+
+def check_bias_grad(B=2, H=16, C=256, seed=9):
+    ops = _ops()
+    g = torch.Generator().manual_seed(seed)
+    dz = _bf(_rand((B, H, H, C), g))
+    dev = _dev()
+    _, dzv = _slice_buf(B, H, H, C, 0, 64, dev)
+    dzv.copy_(dz)
+    db = torch.full((C,), 3.0, device=dev)
+    ops.bias_grad(dzv, db)
+    torch.cuda.synchronize()
+    return _metrics(f"bias_grad B{B} H{H} C{C}", db, dz.float().sum((0, 1, 2)), F32_TOL)
+
+
+def check_dense_mse(B=2, H=32, Cu=64, seed=10):
+    ops = _ops()
+    g = torch.Generator().manual_seed(seed)
+    u0 = _bf(_rand((B, H, H, Cu), g).clamp_min(0))
+    noised = _rand((B, H, H, 3), g)
+    x = _rand((B, H, H, 3), g)
+    wd = _rand((Cu + 3, 3), g, 0.2).requires_grad_(True)
+    bd = _rand((3,), g, 0.1).requires_grad_(True)
+    u0r = u0.float().requires_grad_(True)
+    pred = O.dense(torch.cat([u0r, noised], -1), wd, bd)
+    loss = ((x - pred) ** 2).mean()
+    loss.backward()
+    du0_ref = u0r.grad * (u0.float() > 0)
+    dev = _dev()
+    _, u0v = _slice_buf(B, H, H, Cu, 0, 64, dev)
+    u0v.copy_(u0)
+    du0 = torch.full((B, H, H, Cu), 7.0, dtype=torch.bfloat16, device=dev)
+    predg = torch.empty(B, H, H, 3, device=dev)
+    lossg = torch.full((1,), 5.0, device=dev)
+    dwd = torch.full((Cu + 3, 3), 3.0, device=dev)
+    dbd = torch.full((3,), 3.0, device=dev)
+    ops.dense_mse(u0v, noised.to(dev), x.to(dev), wd.detach().to(dev), bd.detach().to(dev), lossg,
+                  1.0 / (B * H * H * 3), pred=predg, du0=du0, dwd=dwd, dbd=dbd)
+    torch.cuda.synchronize()
+    ms = [_metrics("dense pred", predg, pred, 2e-5), _metrics("mse loss", lossg, loss.reshape(1), 2e-5),
+          _metrics("dense du0", du0, du0_ref, BF16_TOL), _metrics("dense dW", dwd, wd.grad, F32_TOL),
+          _metrics("dense db", dbd, bd.grad, F32_TOL)]
+    worst = max(ms, key=lambda m: m["err"] / m["tol"])
+    worst = dict(worst)
+    worst["name"] = f"dense_mse B{B} H{H} (worst: {worst['name']})"
+    return worst
+
+
+def check_adam(n=4096 + 128, steps=3, seed=11):
+    ops = _ops()
+    g = torch.Generator().manual_seed(seed)
+    cfg = O.Config(warm_up=2)
+    w = _rand((n,), g)
+    # Keras-epsilon-sensitive magnitudes: most gradients of this model are below 1e-6
+    gr = [_rand((n,), g) * (10.0 ** torch.randint(-9, -2, (n,), generator=g).float()) for _ in range(steps)]
+    wo, m, v = w.clone(), torch.zeros(n), torch.zeros(n)
+    dev = _dev()
+    wg, mg, vg = w.clone().to(dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    wb = torch.zeros(n, dtype=torch.bfloat16, device=dev)
+    it = torch.zeros(1, dtype=torch.int64, device=dev)
+    hyper = torch.zeros(2, device=dev)
+    for s in range(steps):
+        O.keras_adam_update(wo, m, v, gr[s], s, cfg)
+        ops.adam_keras(wg, mg, vg, gr[s].to(dev), wb, it, hyper, cfg.base_lr, cfg.warm_up, cfg.beta1, cfg.beta2,
+                       cfg.epsilon, 1.0)
+    torch.cuda.synchronize()
+    # w ~ 1 and |delta| ~ 1e-5: the fp32 ulp of w (1.2e-7) caps how well the *delta* can agree (two fp32 pipelines
+    # that differ by one ulp in sqrt/div round w differently) -> compare w tightly and the delta loosely.
+    md = _metrics("adam delta-w", wg.cpu() - w, wo - w, 5e-3)
+    mw = _metrics("adam w", wg, wo, 2e-7)
+    mm = _metrics("adam m", mg, m, 1e-5)
+    mv = _metrics("adam v", vg, v, 1e-5)
+    mb = _metrics("adam bf16 shadow", wb, wo, BF16_TOL)
+    worst = dict(max([md, mw, mm, mv, mb], key=lambda q: q["err"] / q["tol"]))
+    worst["name"] = f"adam_keras n{n} steps{steps} (worst: {worst['name']})"
+    worst["iterations"] = int(it.item())
+    return worst
+
+
+# (function, kwargs) -- sized so the CPU references finish in seconds.
+CONV_CASES = [
+    (check_conv_fprop, dict(B=2, H=16, Cin=64, Cout=64)),
+    (check_conv_fprop, dict(B=1, H=32, Cin=128, Cout=256)),
+    (check_conv_fprop, dict(B=3, H=8, Cin=256, Cout=128)),
+    (check_convT_fprop, dict(B=2, H=8, Cin=64, Cout=64)),
+    (check_convT_fprop, dict(B=1, H=16, Cin=256, Cout=128)),
+    (check_convT_fprop, dict(B=3, H=4, Cin=128, Cout=256)),
+    (check_conv_dgrad, dict(B=2, H=16, Cin=64, Cout=64, add_old=True)),
+    (check_conv_dgrad, dict(B=1, H=32, Cin=128, Cout=256, add_old=False)),
+    (check_conv_dgrad, dict(B=3, H=8, Cin=256, Cout=128, add_old=True)),
+    (check_convT_dgrad, dict(B=2, H=8, Cin=128, Cout=64)),
+    (check_convT_dgrad, dict(B=1, H=16, Cin=256, Cout=128, mask_channels=256)),
+    (check_convT_dgrad, dict(B=3, H=4, Cin=128, Cout=256, mask_channels=0)),
+    (check_conv_wgrad, dict(B=2, H=16, Cin=128, Cout=64)),
+    (check_conv_wgrad, dict(B=1, H=32, Cin=64, Cout=128)),
+    (check_conv_wgrad, dict(B=3, H=8, Cin=256, Cout=256)),
+    (check_convT_wgrad, dict(B=2, H=8, Cin=128, Cout=64)),
+    (check_convT_wgrad, dict(B=1, H=16, Cin=64, Cout=128)),
+    (check_convT_wgrad, dict(B=3, H=4, Cin=256, Cout=256)),
+]
+EW_CASES = [
+    (check_noise, {}),
+    (check_c3_fprop, {}),
+    (check_c3_wgrad, {}),
+    (check_bias_grad, {}),
+    (check_bias_grad, dict(B=1, H=8, C=1024)),
+    (check_dense_mse, {}),
+    (check_adam, {}),
+]
+
+
+def passed(m) -> bool:
+    return m["err"] <= m["tol"] and m.get("pad_intact", True) and m.get("ws_zero", True)

@@ -1,0 +1,28 @@
+"""-m gpu: every CUDA kernel, called through the C ABI, against the CPU oracle on the same seeded inputs."""
+import pytest
+
+from tests import kernel_checks as K
+
+pytestmark = pytest.mark.gpu
+
+
+def _id(case):
+    fn, kw = case
+    return fn.__name__.replace("check_", "") + "-" + "-".join(f"{k}{v}" for k, v in kw.items())
+
+
+@pytest.mark.parametrize("case", K.CONV_CASES, ids=_id)
+def test_conv_family_matches_oracle(case):
+    fn, kw = case
+    m = fn(**kw)
+    assert m["err"] <= m["tol"], m
+    assert m.get("pad_intact", True), f"kernel wrote outside its channel slice: {m}"
+    assert m.get("ws_zero", True), f"split-K workspace not returned zeroed: {m}"
+
+
+@pytest.mark.parametrize("case", K.EW_CASES, ids=_id)
+def test_hbm_bound_kernels_match_oracle(case):
+    fn, kw = case
+    m = fn(**kw)
+    assert m["err"] <= m["tol"], m
+    assert m.get("pad_intact", True), m
