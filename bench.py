@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""Headline benchmark: training images/sec of train.py's step (noising -> U-Net fwd -> MSE -> bwd -> Keras-Adam).
+
+    python bench.py --gpus 1 --steps K --warmup W            # this implementation, one B200
+    torchrun ... bench.py --gpus N --steps K --warmup W      # data parallel, one rank per GPU (weak scaling)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port) on host cores
+
+Prints ONE JSON line (rank 0).  Workload: BASELINE.json configs[1] -- train.py's default model (256x256x3, 6 octaves,
+41.69 M parameters, 128.525 GFLOP per image per step), batch 1 per GPU, synthetic images, glorot-init weights.
+  value     images/s, inputs already resident in HBM (x staged in the engine; t_int/eps drawn on the device per step)
+  e2e       images/s through the public API (train.Trainer.train_step) with a pinned HOST batch copied in every step
+            and the scalar loss read back every step
+  roofline  the dominant kernel family (tcgen05 implicit-GEMM convs): algorithmic FLOPs / summed CUDA-event durations
+            of its launches in one instrumented step, against the measured bf16 peak (MEASURED_PEAKS.json)
+  cpu_baseline  the oracle (PyTorch-CPU fp32 restatement of train.py) timed on this box's host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GFLOP_PER_IMAGE = 128.525  # SURVEY.md 8(d), default config
+METRIC = "train_images_per_sec"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"bf16_burst": p["bf16_tflops"], "bf16_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "hbm": p["hbm_gbs"], "source": "measured"}
+    except Exception:  # noqa: BLE001
+        return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed regions run."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference(batch: int, steps: int, warmup: int, budget_s: float):
+    """Times the oracle's training step (the reference's CPU path as restated in oracle/oracle.py) on host cores."""
+    import torch
+    from oracle import oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.DEFAULT
+    tr = O.OracleTrainer(cfg, seed=0)
+    batches = [O.synthetic_batch(cfg, batch, 1 + i) for i in range(2)]
+    t0 = time.perf_counter()
+    tr.train_step(*batches[0])
+    first = time.perf_counter() - t0
+    done_w = 1
+    # bound the run: the oracle needs ~0.5-1 s per image
+    total = max(1, min(steps + warmup, int(budget_s / max(first, 1e-3))))
+    eff_warm = min(warmup, max(1, total // 4))
+    eff_steps = max(1, min(steps, total - eff_warm))
+    while done_w < eff_warm:
+        tr.train_step(*batches[done_w % 2])
+        done_w += 1
+    t0 = time.perf_counter()
+    for i in range(eff_steps):
+        tr.train_step(*batches[i % 2])
+    dt = time.perf_counter() - t0
+    return {"value": batch * eff_steps / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{eff_steps} full training steps (fwd+loss+bwd+Keras-Adam) of the default model at batch {batch} "
+                      f"after {eff_warm} warm-up, PyTorch-CPU fp32 (oneDNN) restatement of train.py -- not TensorFlow",
+            "ms_per_step": dt / eff_steps * 1e3, "steps": eff_steps, "warmup": eff_warm}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = args.batch_per_gpu
+    r = cpu_reference(batch, args.steps, args.warmup, budget_s=150.0)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "images/s", "n_gpus": args.gpus,
+            "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(batch, 1),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(batch_per_gpu: int, world: int):
+    return {"workload": "train.py default Denoiser U-Net step (size=256, pixel_size=128, max_size=512, octaves=6; "
+                        "41,691,660 params; 128.525 GFLOP/image/step), synthetic images, glorot-uniform init",
+            "batch_per_gpu": batch_per_gpu, "global_batch": batch_per_gpu * world,
+            "parallelism": f"dp{world}" if world > 1 else "single",
+            "l2": "per-step working set ~1.4 GB (fp32 w/m/v/g + bf16 shadow + activations) exceeds the 126 MB L2; "
+                  "no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def instrumented_step(eng, torch, ops):
+    """One eager step with every op bracketed by CUDA events (the GPU is kept busy first so that host launch latency
+    is not inside the brackets).  Returns {op name: [durations in us]}."""
+    saved = eng._save_state()
+    torch.cuda.synchronize()
+    torch.cuda._sleep(int(3e7))
+    ops.profile_ops(True)
+    eng._step_body(False)
+    rec = ops.profile_ops(False)
+    torch.cuda.synchronize()
+    eng._restore_state(saved)
+    out = {}
+    for name, s, e in rec:
+        out.setdefault(name, []).append(s.elapsed_time(e) * 1e3)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch-per-gpu", type=int, default=1)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    from gan_class_transfer2_b200 import _lib, ops
+    from gan_class_transfer2_b200 import train as T
+    from gan_class_transfer2_b200.engine import DataParallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback for the training step "
+                         "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        T.data_parallel = DataParallel(overlap=not args.no_overlap)
+    _lib.init(local)
+
+    B = args.batch_per_gpu
+    T.use_cuda_graph = not args.no_graph
+    denoiser = T.Denoiser()
+    trainer = T.Trainer(denoiser)
+    trainer.compile(T.optimizer, T.identity)
+    eng = denoiser.engine(B, T.size)
+
+    from oracle import oracle as O  # synthetic_batch only: the same images the CPU arm sees (not a compute path)
+    x_cpu, _, _ = O.synthetic_batch(O.DEFAULT, B, 1 + rank)
+    x_host = x_cpu.pin_memory()
+    loss_host = torch.zeros(1).pin_memory()
+    eng.set_batch(x_host)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up (also captures the CUDA graph)
+    for _ in range(args.warmup):
+        eng.run_step(draw=True)
+    barrier()
+    launches_per_step = eng.launches_per_step()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    # ---- value: K steps, inputs resident in HBM
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    s.record()
+    for _ in range(args.steps):
+        eng.run_step(draw=True)
+    e.record()
+    barrier()
+    ms_total = max_over_ranks(s.elapsed_time(e))
+    ms_per_step = ms_total / args.steps
+    value = B * world * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: public API, pinned host batch in, loss out, every step
+    for _ in range(3):
+        trainer.train_step((x_host, x_host))
+    barrier()
+    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s2.record()
+    for _ in range(args.steps):
+        loss = trainer.train_step((x_host, x_host))["loss"]
+        loss_host.copy_(loss.reshape(1), non_blocking=True)
+    e2.record()
+    barrier()
+    ms_e2e = max_over_ranks(s2.elapsed_time(e2))
+    clocks = sampler.stop()
+    final_loss = float(loss_host.item())
+
+    # ---- roofline of the dominant kernel family, measured live
+    pk = peaks()
+    prof = instrumented_step(eng, torch, ops)
+    conv_ops = [k for k in prof if k.startswith("conv") and "c3" not in k]
+    conv_us = sum(sum(prof[k]) for k in conv_ops)
+    conv_launches = sum(len(prof[k]) for k in conv_ops)
+    total_us = sum(sum(v) for v in prof.values())
+    # FLOPs of the tensor-core family = step total minus down0 (fprop+wgrad, CUDA cores) and dense (fwd+2 bwd)
+    flops_conv = (GFLOP_PER_IMAGE - 2 * 0.2013 - 3 * 0.0263) * 1e9 * B
+    achieved = flops_conv / (conv_us * 1e-6) / 1e12 if conv_us else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            traffic = json.load(f).get("traffic_bytes_per_launch")
+    except Exception:  # noqa: BLE001
+        pass
+    roofline = {"bound": "tensor", "kernel": "conv_umma_kernel<MODE,BN> (tcgen05 implicit-GEMM conv family, "
+                                             f"{conv_launches} launches/step)",
+                "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / pk["bf16_sustained"], "traffic": traffic, "peak_source": pk["source"] + " (sustained)",
+                "avg_launch_us": conv_us / max(conv_launches, 1), "family_share_of_step": conv_us / max(total_us, 1e-9),
+                "step_achieved": value / world * GFLOP_PER_IMAGE * 1e9 / 1e12,
+                "step_frac": value / world * GFLOP_PER_IMAGE * 1e9 / 1e12 / pk["bf16_sustained"],
+                "per_op_us": {k: round(sum(v), 1) for k, v in prof.items()}}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference(B, 4, 1, budget_s=25.0)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(B, world),
+            "e2e": {"value": B * world * args.steps / (ms_e2e * 1e-3), "unit": "images/s",
+                    "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps, "api": "train.Trainer.train_step((x_host, x_host))"},
+            "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+            "cuda_graph": not args.no_graph, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "final_loss": final_loss}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

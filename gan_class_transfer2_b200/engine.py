@@ -40,11 +40,18 @@ class NetConfig:
     beta1: float = 0.9
     beta2: float = 0.999
     epsilon: float = 1e-7
+    #: explicit per-octave filter counts (what a layer tree built by hand carries); default = train.py's formulas
+    down_filters: Optional[Tuple[int, ...]] = None
+    up_filters: Optional[Tuple[int, ...]] = None
 
     def down_c(self, i: int) -> int:  # train.py:181
+        if self.down_filters is not None:
+            return self.down_filters[i]
         return min(self.pixel_size * 2 ** i, self.max_size)
 
     def up_c(self, i: int) -> int:  # train.py:188
+        if self.up_filters is not None:
+            return self.up_filters[i]
         return min(self.pixel_size * 2 ** i // 2, self.max_size)
 
     def up_in(self, i: int) -> int:
@@ -85,6 +92,42 @@ def glorot_uniform(shape, generator) -> torch.Tensor:
     return (torch.rand(shape, generator=generator, dtype=torch.float32) * 2 - 1) * limit
 
 
+def param_offsets(cfg: NetConfig) -> Tuple[Dict[str, Tuple[int, int]], int]:
+    """name -> (offset, count) in the flat Keras-order buffer, and the total element count."""
+    offsets: Dict[str, Tuple[int, int]] = {}
+    off = 0
+    for name, shape in variable_specs(cfg):
+        cnt = math.prod(shape)
+        offsets[name] = (off, cnt)
+        off += cnt
+    return offsets, off
+
+
+def grad_buckets(cfg: NetConfig, bucket_bytes: int) -> List[Tuple[int, int, str]]:
+    """Data-parallel gradient buckets: contiguous [start, end) ranges of the flat fp32 gradient buffer, listed tail
+    to head (the order backward completes them: dense, up0..up{n-1}, down{n-1}..down0), each closed by the layer whose
+    weight gradient completes it.  Together they tile [0, P) exactly once."""
+    offsets, total = param_offsets(cfg)
+    order = ["dense"] + [f"up{i}" for i in range(cfg.octaves)] + [f"down{i}" for i in reversed(range(cfg.octaves))]
+    buckets: List[Tuple[int, int, str]] = []
+    cur_end = total
+    for layer in order:
+        start = offsets[f"{layer}/kernel"][0]
+        if (cur_end - start) * 4 >= bucket_bytes or layer == order[-1]:
+            buckets.append((start, cur_end, f"{layer}/kernel"))
+            cur_end = start
+    return buckets
+
+
+def shard_batch(global_batch: int, world: int, rank: int) -> Tuple[int, int]:
+    """[lo, hi) sample range of one rank: the batch shards evenly, samples are independent (no cross-sample op but
+    the loss mean, train.py:272)."""
+    if global_batch % world:
+        raise ValueError(f"global batch {global_batch} is not divisible by {world} ranks")
+    per = global_batch // world
+    return rank * per, (rank + 1) * per
+
+
 class DataParallel:
     """Data-parallel context: the batch shards over ranks, gradient buckets are summed with NCCL."""
 
@@ -100,7 +143,7 @@ class DataParallel:
 
 class UNetEngine:
     def __init__(self, cfg: NetConfig, batch: int, device=None, dp: Optional[DataParallel] = None,
-                 use_graph: bool = False):
+                 use_graph: bool = False, share_params_with: Optional["UNetEngine"] = None):
         cfg.validate()
         self.cfg = cfg
         self.B = batch
@@ -115,23 +158,25 @@ class UNetEngine:
 
         # ---- parameters, flat in Keras order
         self.specs = variable_specs(cfg)
-        self.offsets: Dict[str, Tuple[int, int]] = {}
-        off = 0
-        for name, shape in self.specs:
-            cnt = math.prod(shape)
-            self.offsets[name] = (off, cnt)
-            off += cnt
-        self.P = off
+        self.offsets, self.P = param_offsets(cfg)
         if self.P % 4:
             raise ValueError("parameter count must be a multiple of 4")
         f32 = dict(dtype=torch.float32, device=dev)
-        self.w = torch.zeros(self.P, **f32)
-        self.m = torch.zeros(self.P, **f32)
-        self.v = torch.zeros(self.P, **f32)
-        self.g = torch.zeros(self.P, **f32)
-        self.w16 = torch.zeros(self.P, dtype=torch.bfloat16, device=dev)
-        self.iterations = torch.zeros(1, dtype=torch.int64, device=dev)
-        self.hyper = torch.zeros(2, **f32)
+        if share_params_with is not None:
+            # a second batch size over the same variables (e.g. the reference's batch-6 sampling, train.py:432-450)
+            o = share_params_with
+            if o.specs != self.specs:
+                raise ValueError("engines sharing parameters must have the same variable list")
+            self.w, self.m, self.v, self.g, self.w16 = o.w, o.m, o.v, o.g, o.w16
+            self.iterations, self.hyper = o.iterations, o.hyper
+        else:
+            self.w = torch.zeros(self.P, **f32)
+            self.m = torch.zeros(self.P, **f32)
+            self.v = torch.zeros(self.P, **f32)
+            self.g = torch.zeros(self.P, **f32)
+            self.w16 = torch.zeros(self.P, dtype=torch.bfloat16, device=dev)
+            self.iterations = torch.zeros(1, dtype=torch.int64, device=dev)
+            self.hyper = torch.zeros(2, **f32)
 
         # ---- activations and their gradients
         bf = dict(dtype=torch.bfloat16, device=dev)
@@ -249,19 +294,7 @@ class UNetEngine:
 
     # ------------------------------------------------------------------------------------------ data parallel
     def _make_buckets(self) -> List[Tuple[int, int, str]]:
-        """Contiguous [start, end) ranges of the flat gradient buffer, tail to head, each closed by the layer whose
-        weight gradient completes it."""
-        order = ["dense"] + [f"up{i}" for i in range(self.cfg.octaves)] + \
-                [f"down{i}" for i in reversed(range(self.cfg.octaves))]
-        buckets: List[Tuple[int, int, str]] = []
-        end = self.P
-        cur_end = end
-        for layer in order:
-            start = self.offsets[f"{layer}/kernel"][0]
-            if (cur_end - start) * 4 >= self.dp.bucket_bytes or layer == order[-1]:
-                buckets.append((start, cur_end, f"{layer}/kernel"))
-                cur_end = start
-        return buckets
+        return grad_buckets(self.cfg, self.dp.bucket_bytes)
 
     def _bucket_ready(self, name: str) -> None:
         if not self.dp or self.dp.world == 1:
@@ -283,10 +316,14 @@ class UNetEngine:
         self.dp.dist.all_reduce(self.loss, group=self.dp.group)
 
     # ------------------------------------------------------------------------------------------ public steps
-    def _step_body(self) -> None:
+    def _step_body(self, draw: bool) -> None:
         cfg = self.cfg
         self._pending, self._deferred = [], []
         inv_n = 1.0 / (self.global_batch * cfg.size * cfg.size * 3)
+        if draw:
+            # train.py:224-227: t_int ~ U{1..steps}, epsilon ~ N(0,1), drawn on the device every step
+            self.t_int.random_(1, cfg.steps + 1)
+            self.eps.normal_()
         ops.noise_images(self.x, self.eps, self.t_int, self.noised, cfg.steps)
         self._forward(want_pred=False, backward=True, inv_n=inv_n)
         self._backward()
@@ -296,58 +333,64 @@ class UNetEngine:
 
     def set_batch(self, x: torch.Tensor, t_int: Optional[torch.Tensor] = None,
                   eps: Optional[torch.Tensor] = None) -> None:
-        """Stages one batch into the engine's input buffers (host tensors are copied asynchronously).  t_int / eps
-        default to fresh device-side draws: U{1..steps} and N(0,1) as in train.py:224-227."""
+        """Stages one batch into the engine's input buffers (host tensors are copied asynchronously).  t_int / eps,
+        when given, are the injected RNG draws of the parity tests."""
         self.x.copy_(x, non_blocking=True)
-        if t_int is None:
-            self.t_int.random_(1, self.cfg.steps + 1)
-        else:
+        if t_int is not None:
             self.t_int.copy_(t_int, non_blocking=True)
-        if eps is None:
-            self.eps.normal_()
-        else:
+        if eps is not None:
             self.eps.copy_(eps, non_blocking=True)
 
     def train_step(self, x: torch.Tensor, t_int: Optional[torch.Tensor] = None,
                    eps: Optional[torch.Tensor] = None) -> torch.Tensor:
         """One training step on the batch x [B,S,S,3] fp32 (host or device).  Returns the device scalar loss
-        (global mean over all ranks).  Everything is enqueued on the current stream; nothing synchronises."""
+        (global mean over all ranks).  Everything is enqueued on the current stream; nothing synchronises.
+        Without t_int/eps the step draws them on the device like the reference (train.py:224-227)."""
+        if (t_int is None) != (eps is None):
+            raise ValueError("inject both t_int and eps, or neither")
         self.set_batch(x, t_int, eps)
-        self.run_step()
+        self.run_step(draw=t_int is None)
         return self.loss
 
-    def run_step(self) -> None:
+    def _save_state(self):
+        return [t.clone() for t in (self.w, self.m, self.v, self.w16, self.iterations)]
+
+    def _restore_state(self, saved) -> None:
+        for dst, src in zip((self.w, self.m, self.v, self.w16, self.iterations), saved):
+            dst.copy_(src)
+
+    def run_step(self, draw: bool = True) -> None:
         """The step on whatever set_batch staged (the part bench.py times as `value`)."""
         if not self.use_graph:
-            self._step_body()
+            self._step_body(draw)
             return
         if self._graph is None:
+            self._graph = {}
+        if draw not in self._graph:
             # warm up once eagerly on a side stream (lazy inits must not happen under capture), then capture
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                saved = (self.w.clone(), self.m.clone(), self.v.clone(), self.w16.clone(), self.iterations.clone())
-                self._step_body()
-                for dst, src in zip((self.w, self.m, self.v, self.w16, self.iterations), saved):
-                    dst.copy_(src)
+                saved = self._save_state()
+                self._step_body(draw)
+                self._restore_state(saved)
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             before = ops.launch_count()
             with torch.cuda.graph(graph):
-                self._step_body()
+                self._step_body(draw)
             self._graph_launches = ops.launch_count() - before
-            self._graph = graph
-        self._graph.replay()
+            self._graph[draw] = graph
+        self._graph[draw].replay()
 
     def launches_per_step(self) -> int:
-        """Kernels of ours one step enqueues (counted inside the C library; graph replays re-issue the same nodes)."""
-        if self.use_graph and self._graph is not None:
+        """Kernels of ours one step enqueues (counted inside the C library; a graph replay re-issues the same nodes)."""
+        if self.use_graph and self._graph:
             return self._graph_launches
         before = ops.launch_count()
-        saved = (self.w.clone(), self.m.clone(), self.v.clone(), self.w16.clone(), self.iterations.clone())
-        self._step_body()
-        for dst, src in zip((self.w, self.m, self.v, self.w16, self.iterations), saved):
-            dst.copy_(src)
+        saved = self._save_state()
+        self._step_body(False)
+        self._restore_state(saved)
         return ops.launch_count() - before
 
     def loss_and_grads(self, x, t_int, eps) -> torch.Tensor:

@@ -21,6 +21,37 @@ def launch_count() -> int:
     return int(_lib.load().gct2_launch_count())
 
 
+#: when a list, every op appends (op name, start event, end event) -- bench.py's per-kernel timing pass
+_profile = None
+
+
+def profile_ops(enable: bool):
+    """Starts (True) or stops (False) per-op CUDA-event bracketing; stopping returns the recorded list."""
+    global _profile
+    if enable:
+        _profile = []
+        return None
+    rec, _profile = _profile, None
+    return rec
+
+
+def _timed(fn):
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*a, **kw):
+        if _profile is None:
+            return fn(*a, **kw)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        out = fn(*a, **kw)
+        e.record()
+        _profile.append((fn.__name__, s, e))
+        return out
+
+    return wrapper
+
+
 def _lib_for(t: torch.Tensor):
     if not t.is_cuda:
         raise _lib.Gct2Error("gct2 ops need CUDA tensors: there is no CPU path")
@@ -49,6 +80,7 @@ class Workspace:
         return self.buf.numel() * 4
 
 
+@_timed
 def noise_images(x, eps, t_int, out, steps: int = 200):
     """train.py:224-234: out = x*sqrt(abar(t)) + eps*sqrt(1-abar(t)); x, eps, out fp32 [B,H,W,3]; t_int int32 [B]."""
     lib = _lib_for(x)
@@ -57,6 +89,7 @@ def noise_images(x, eps, t_int, out, steps: int = 200):
     return out
 
 
+@_timed
 def conv4s2_c3_fprop(x, w, bias, y):
     """DownShuffle on the fp32 3-channel image (train.py:158-169, down0). w fp32 [4,4,3,Cout]."""
     lib = _lib_for(x)
@@ -66,6 +99,7 @@ def conv4s2_c3_fprop(x, w, bias, y):
     return y
 
 
+@_timed
 def conv4s2_c3_wgrad(x, dz, dw, db):
     lib = _lib_for(x)
     B, H, W, _ = x.shape
@@ -73,6 +107,7 @@ def conv4s2_c3_wgrad(x, dz, dw, db):
                                     current_stream()))
 
 
+@_timed
 def conv4s2_fprop(x, w, bias, y, ws: Workspace):
     """DownShuffle forward (train.py:158-169): y = relu(conv2d(x, w, s=2, SAME) + b).  w bf16 [4,4,Cin,Cout]."""
     lib = _lib_for(x)
@@ -82,6 +117,7 @@ def conv4s2_fprop(x, w, bias, y, ws: Workspace):
     return y
 
 
+@_timed
 def conv4s2_dgrad(dy, w, dx, act, add_old: bool, ws: Workspace):
     """Backward-data of DownShuffle, fused with the ReLU mask of the layer that produced the input and the add of
     the skip-path gradient already sitting in dx."""
@@ -93,6 +129,7 @@ def conv4s2_dgrad(dy, w, dx, act, add_old: bool, ws: Workspace):
     return dx
 
 
+@_timed
 def conv4s2_wgrad(x, dy, dw):
     lib = _lib_for(x)
     B, H, W, Cin = x.shape
@@ -101,6 +138,7 @@ def conv4s2_wgrad(x, dy, dw):
     return dw
 
 
+@_timed
 def convT4s2_fprop(x, w, bias, y, ws: Workspace):
     """UpShuffle forward (train.py:145-156): y = relu(conv2d_transpose(x, w, s=2, SAME) + b). w bf16 [4,4,Cout,Cin]."""
     lib = _lib_for(x)
@@ -111,6 +149,7 @@ def convT4s2_fprop(x, w, bias, y, ws: Workspace):
     return y
 
 
+@_timed
 def convT4s2_dgrad(dy, w, dx, act, mask_channels: int, ws: Workspace):
     """Backward-data of UpShuffle; channels [0, mask_channels) of dx are ReLU-masked by act, the rest stored raw."""
     lib = _lib_for(dy)
@@ -121,6 +160,7 @@ def convT4s2_dgrad(dy, w, dx, act, mask_channels: int, ws: Workspace):
     return dx
 
 
+@_timed
 def convT4s2_wgrad(x, dy, dw):
     lib = _lib_for(x)
     B, H, W, Cin = x.shape
@@ -129,6 +169,7 @@ def convT4s2_wgrad(x, dy, dw):
     return dw
 
 
+@_timed
 def bias_grad(dz, db):
     lib = _lib_for(dz)
     ld = _nhwc(dz, torch.bfloat16)
@@ -137,6 +178,7 @@ def bias_grad(dz, db):
     return db
 
 
+@_timed
 def dense_mse(u0, noised, x, wd, bd, loss, inv_n: float, pred=None, du0=None, dwd=None, dbd=None):
     """Dense(3) on concat([u0, noised]) (train.py:198-202) fused with the MSE (train.py:262-272) and, when du0 is
     given, their backward."""
@@ -149,6 +191,7 @@ def dense_mse(u0, noised, x, wd, bd, loss, inv_n: float, pred=None, du0=None, dw
     return loss
 
 
+@_timed
 def adam_keras(w, m, v, g, w_bf16, iterations, hyper, base_lr: float, warmup_steps: int, beta1: float = 0.9,
                beta2: float = 0.999, eps: float = 1e-7, grad_scale: float = 1.0):
     """tf.keras.optimizers.Adam(WarmUp(base_lr, warmup_steps)) on flat fp32 buffers (train.py:50-65,75)."""
@@ -157,6 +200,7 @@ def adam_keras(w, m, v, g, w_bf16, iterations, hyper, base_lr: float, warmup_ste
                               base_lr, warmup_steps, beta1, beta2, eps, grad_scale, current_stream()))
 
 
+@_timed
 def cast_bf16(src, dst):
     lib = _lib_for(src)
     check(lib.gct2_cast_bf16(ptr(src), ptr(dst), src.numel(), current_stream()))

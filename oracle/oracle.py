@@ -164,20 +164,38 @@ def dense(x_nhwc, kernel, bias):
     return x_nhwc @ kernel + bias
 
 
+class _RoundBF16(torch.autograd.Function):
+    """Rounds to bf16 in the forward AND the backward direction (where the CUDA path stores bf16 tensors)."""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t.to(torch.bfloat16).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(torch.float32)
+
+
 def denoiser_forward(weights: Dict[str, torch.Tensor], x_nhwc: torch.Tensor, cfg: Config = DEFAULT,
-                     taps: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+                     taps: Optional[Dict[str, torch.Tensor]] = None, emulate_bf16: bool = False) -> torch.Tensor:
     """Denoiser.call (train.py:206-215): `t` is ignored by the reference; Block is identity at block_depth=0.
 
     Residual_i(h) = concat([Up_i(Residual_{i+1}(Down_i(h))), h], -1) with the module output FIRST (train.py:113-119).
     `taps`, when given, collects every layer output (post-ReLU) by name.
+
+    emulate_bf16=False is the reference's arithmetic (fp32).  emulate_bf16=True additionally rounds to bf16 exactly
+    where the CUDA path stores bf16 (tensor-core kernels' weights, every layer output and its gradient), which turns
+    the loose fp32-vs-bf16 comparison into a tight one for the tests; it is not the reference's arithmetic.
     """
+    rnd = _RoundBF16.apply if emulate_bf16 else (lambda t: t)
 
     def residual(i: int, h):
-        d = down_shuffle(h, weights[f"down{i}/kernel"], weights[f"down{i}/bias"])
+        kd = weights[f"down{i}/kernel"] if i == 0 else rnd(weights[f"down{i}/kernel"])  # down0 runs in fp32
+        d = rnd(down_shuffle(h, kd, weights[f"down{i}/bias"]))
         if taps is not None:
             taps[f"down{i}"] = d
         inner = residual(i + 1, d) if i + 1 < cfg.octaves else d
-        u = up_shuffle(inner, weights[f"up{i}/kernel"], weights[f"up{i}/bias"])
+        u = rnd(up_shuffle(inner, rnd(weights[f"up{i}/kernel"]), weights[f"up{i}/bias"]))
         if taps is not None:
             taps[f"up{i}"] = u
         return torch.cat([u, h], dim=-1)
@@ -196,14 +214,15 @@ def noise_images(x, t_int, eps, cfg: Config = DEFAULT):
     return x * a ** 0.5 + eps * (1 - a) ** 0.5
 
 
-def trainer_loss(weights, x, t_int, eps, cfg: Config = DEFAULT, taps=None, global_elems: Optional[int] = None):
+def trainer_loss(weights, x, t_int, eps, cfg: Config = DEFAULT, taps=None, global_elems: Optional[int] = None,
+                 emulate_bf16: bool = False):
     """Trainer.call with predict_x=True (train.py:223-236,243-244,262-263,272) -> scalar mean squared error.
 
     global_elems overrides the mean's denominator (data-parallel shards of one global batch)."""
     noised = noise_images(x, t_int, eps, cfg)
     if taps is not None:
         taps["noised"] = noised
-    pred = denoiser_forward(weights, noised, cfg, taps)
+    pred = denoiser_forward(weights, noised, cfg, taps, emulate_bf16)
     sq = (x.to(torch.float32) - pred.to(torch.float32)) ** 2
     if global_elems is None:
         return sq.mean()
@@ -216,12 +235,12 @@ def identity(y_true, y_pred):
 
 
 def loss_and_grads(weights, x, t_int, eps, cfg: Config = DEFAULT, want_taps: bool = False,
-                   global_elems: Optional[int] = None):
+                   global_elems: Optional[int] = None, emulate_bf16: bool = False):
     """One forward+backward (what Keras train_step's GradientTape does, train.py:516): returns
     (loss, {name: grad}, taps) where taps also carries d(loss)/d(layer output) under 'd<name>' when requested."""
     ws = {k: v.detach().clone().requires_grad_(True) for k, v in weights.items()}
     taps: Optional[Dict[str, torch.Tensor]] = {} if want_taps else None
-    loss = identity(None, trainer_loss(ws, x, t_int, eps, cfg, taps, global_elems))
+    loss = identity(None, trainer_loss(ws, x, t_int, eps, cfg, taps, global_elems, emulate_bf16))
     if want_taps:
         for v in taps.values():
             if v.requires_grad:

@@ -1,0 +1,37 @@
+"""Generates tests/golden/tiny_step.npz from the oracle (run once; re-run only when the oracle is deliberately changed).
+
+The reference itself cannot produce vectors here: it needs TensorFlow (not installed, no network), a GPU at
+train.py:40 and the author's dataset at train.py:305,315.  These vectors therefore pin the oracle against drift
+and give the CUDA path a committed fixture; they do not pin the oracle to TensorFlow ("parity unpinned").
+
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import oracle as O  # noqa: E402
+
+
+def main():
+    cfg = O.TINY
+    tr = O.OracleTrainer(cfg, seed=0)
+    x, t, e = O.synthetic_batch(cfg, 2, 1)
+    loss, grads, taps = O.loss_and_grads(tr.weights, x, t, e, cfg, want_taps=True)
+    out = {"loss": np.float32(loss), "pred_corner": taps["pred"][0, :4, :4].numpy()}
+    for k, g in grads.items():
+        out["gnorm/" + k] = np.float32(g.norm())
+    for k in ("down0", "down3", "up3", "up0"):
+        out["anorm/" + k] = np.float32(taps[k].norm())
+    out["losses3"] = np.array([tr.train_step(*O.synthetic_batch(cfg, 2, 100 + s)) for s in range(3)], dtype=np.float32)
+    out["w_after3/dense/kernel"] = tr.weights["dense/kernel"].numpy()
+    np.savez(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tiny_step.npz"), **out)
+    print({k: (v.tolist() if v.size < 4 else v.shape) for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,90 @@
+"""CPU: host-side logic of the drop-in surface (no kernels are launched)."""
+import math
+
+import pytest
+import torch
+
+from gan_class_transfer2_b200 import engine as E
+from gan_class_transfer2_b200 import train as T
+from oracle import oracle as O
+
+
+def test_train_py_names_and_defaults():
+    for name, val in dict(size=256, pixel_size=128, max_size=512, block_depth=0, octaves=6, batch_size=1, steps=200,
+                          residual=False, concat=True, predict_x=True, mixed_precision=False, warm_up=2000,
+                          test_step=25).items():
+        assert getattr(T, name) == val, name
+    for cls in ("WarmUp", "Residual", "Block", "UpShuffle", "DownShuffle", "Denoiser", "Trainer"):
+        assert isinstance(getattr(T, cls), type)
+    assert callable(T.identity) and callable(T.alpha_dash)
+    assert isinstance(T.optimizer.learning_rate, T.WarmUp)
+    assert (T.optimizer.beta_1, T.optimizer.beta_2, T.optimizer.epsilon) == (0.9, 0.999, 1e-7)
+
+
+def test_construction_recursion_matches_reference_shapes():
+    d = T.Denoiser()
+    cfg = d.net_config(256)
+    assert cfg.down_filters == (128, 256, 512, 512, 512, 512)
+    assert cfg.up_filters == (64, 128, 256, 512, 512, 512)
+    assert E.variable_specs(cfg) == O.variable_specs(O.DEFAULT)
+    offsets, total = E.param_offsets(cfg)
+    assert total == 41_691_660
+    assert all(off % 8 == 0 for name, (off, _) in offsets.items() if name.endswith("kernel") and "dense" not in name)
+
+
+def test_variable_specs_follow_formulas_for_the_widened_variant():
+    cfg = E.NetConfig(size=512, pixel_size=256, max_size=1024, octaves=7)
+    ocfg = O.Config(size=512, pixel_size=256, max_size=1024, octaves=7)
+    assert E.variable_specs(cfg) == O.variable_specs(ocfg)
+    assert E.param_offsets(cfg)[1] == 217_078_796
+
+
+def test_warmup_and_alpha_dash_match_oracle():
+    wu, ou = T.WarmUp(2e-5, 2000), O.WarmUp(2e-5, 2000)
+    for s in (0, 1, 999, 1999, 2000, 5000):
+        assert math.isclose(wu(s), ou(s), rel_tol=1e-6)
+    for t in (1, 25, 200):
+        assert math.isclose(T.alpha_dash(t), O.alpha_dash(t))
+    tt = torch.tensor([1.0, 100.0])
+    assert torch.allclose(T.alpha_dash(tt), O.alpha_dash(tt))
+
+
+def test_unsupported_structures_are_rejected():
+    d = T.Denoiser()
+    d.middle.layers[3] = T.Dense(5)
+    with pytest.raises(NotImplementedError):
+        d.net_config(256)
+    with pytest.raises(ValueError):
+        E.NetConfig(size=48, octaves=2).validate()
+    with pytest.raises(ValueError):
+        E.NetConfig(size=64, octaves=5).validate()  # bottleneck below 4x4
+    with pytest.raises(ValueError):
+        E.NetConfig(size=64, octaves=2, pixel_size=96).validate()
+
+
+def test_layers_refuse_cpu_tensors():
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        T.DownShuffle(64)(torch.zeros(1, 8, 8, 64))
+
+
+def test_buckets_tile_the_flat_gradient_buffer_tail_to_head():
+    for cfg in (E.NetConfig(), E.NetConfig(size=64, max_size=256, octaves=4)):
+        total = E.param_offsets(cfg)[1]
+        for bb in (1 << 20, 16 << 20, 48 << 20, 1 << 40):
+            b = E.grad_buckets(cfg, bb)
+            assert b[0][1] == total and b[-1][0] == 0
+            assert all(b[i][0] == b[i + 1][1] for i in range(len(b) - 1))
+            assert b[-1][2] == "down0/kernel"
+
+
+def test_shard_batch():
+    assert E.shard_batch(8, 4, 1) == (2, 4)
+    with pytest.raises(ValueError):
+        E.shard_batch(6, 4, 0)
+
+
+def test_glorot_limits():
+    g = torch.Generator().manual_seed(0)
+    k = E.glorot_uniform((4, 4, 128, 256), g)
+    lim = math.sqrt(6 / (16 * 128 + 16 * 256))
+    assert k.abs().max() <= lim and k.abs().max() > 0.99 * lim

@@ -1,0 +1,184 @@
+"""CPU tests pinning the oracle.  The reference ships no tests or golden vectors and cannot be
+run here (no TensorFlow), so the oracle is pinned by (a) the TensorFlow/Keras semantics it must satisfy, checked as
+self-consistency identities, and (b) golden vectors generated from it once (tests/golden/make_golden.py) that catch
+drift.  "Parity unpinned" against the real reference remains stated in oracle/oracle.py and DESIGN.md."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "tiny_step.npz")
+
+
+def test_param_count_and_variable_order_match_survey():
+    specs = O.variable_specs(O.DEFAULT)
+    assert O.param_count(O.DEFAULT) == 41_691_660
+    assert len(specs) == 26
+    names = [n for n, _ in specs]
+    assert names[:4] == ["down0/kernel", "down0/bias", "down1/kernel", "down1/bias"]
+    assert names[12:14] == ["up5/kernel", "up5/bias"] and names[-2:] == ["dense/kernel", "dense/bias"]
+    shapes = dict(specs)
+    assert shapes["down0/kernel"] == (4, 4, 3, 128)
+    assert shapes["down2/kernel"] == (4, 4, 256, 512)
+    assert shapes["up5/kernel"] == (4, 4, 512, 512)
+    assert shapes["up4/kernel"] == (4, 4, 512, 1024)
+    assert shapes["up2/kernel"] == (4, 4, 256, 1024)
+    assert shapes["up0/kernel"] == (4, 4, 64, 256)
+    assert shapes["dense/kernel"] == (67, 3)
+
+
+def test_flops_per_image_match_survey():
+    f = O.flops_per_image(O.DEFAULT)
+    assert abs(f["fwd"] / 1e9 - 42.909) < 0.01
+    assert abs(f["step"] / 1e9 - 128.525) < 0.01
+
+
+def test_shape_walk_tiny():
+    cfg = O.TINY
+    w = O.glorot_init(cfg, 0)
+    x, t, e = O.synthetic_batch(cfg, 2, 1)
+    taps = {}
+    pred = O.denoiser_forward(w, x, cfg, taps)
+    assert pred.shape == (2, 64, 64, 3)
+    assert taps["down0"].shape == (2, 32, 32, 128) and taps["down3"].shape == (2, 4, 4, 256)
+    assert taps["up3"].shape == (2, 8, 8, 256) and taps["up0"].shape == (2, 64, 64, 64)
+
+
+def test_same_padding_and_transpose_semantics():
+    """SAME for k4/s2 == pad 1; Conv2DTranspose == the autograd-dgrad of that conv (no flip)."""
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 6, 6, 5, generator=g, dtype=torch.float64)
+    k = torch.randn(4, 4, 7, 5, generator=g, dtype=torch.float64)  # HWOI: Cout=7, Cin=5
+    up = F.conv_transpose2d(x.permute(0, 3, 1, 2), k.permute(3, 2, 0, 1), None, stride=2, padding=1)
+    # dgrad definition: the forward conv maps 12x12x7 -> 6x6x5 with HWIO kernel [4,4,7,5]
+    z = torch.zeros(1, 7, 12, 12, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(z, k.permute(3, 2, 0, 1), None, stride=2, padding=1)
+    y.backward(x.permute(0, 3, 1, 2))
+    assert torch.allclose(up, z.grad, atol=1e-12)
+
+
+def test_four_phase_identity():
+    """out[2m+p] uses taps {1,3} (p=0; inputs m, m-1) or {0,2} (p=1; inputs m+1, m): what the CUDA phase form does."""
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 5, 5, 3, generator=g, dtype=torch.float64)
+    k = torch.randn(4, 4, 4, 3, generator=g, dtype=torch.float64)
+    ref = F.conv_transpose2d(x.permute(0, 3, 1, 2), k.permute(3, 2, 0, 1), None, stride=2, padding=1).permute(0, 2, 3, 1)
+    xp = F.pad(x, (0, 0, 1, 1, 1, 1))
+    out = torch.zeros_like(ref)
+    for py in range(2):
+        for px in range(2):
+            acc = 0
+            for ty in range(2):
+                for tx in range(2):
+                    ky, kx = (1 - py) + 2 * ty, (1 - px) + 2 * tx
+                    dy, dx = py - ty, px - tx
+                    patch = xp[:, 1 + dy:1 + dy + 5, 1 + dx:1 + dx + 5, :]
+                    acc = acc + patch @ k[ky, kx].T
+            out[:, py::2, px::2, :] = acc
+    assert torch.allclose(out, ref, atol=1e-12)
+
+
+def test_dense_is_last_axis_contraction():
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(1, 4, 4, 67, generator=g)
+    k, b = torch.randn(67, 3, generator=g), torch.randn(3, generator=g)
+    ref = F.conv2d(x.permute(0, 3, 1, 2), k.T[:, :, None, None], b).permute(0, 2, 3, 1)
+    assert torch.allclose(O.dense(x, k, b), ref, atol=1e-5)
+
+
+def test_alpha_dash_range_and_noising():
+    assert math.isclose(O.alpha_dash(1), (1 - 1 / 201) ** 2 * 0.25)
+    assert math.isclose(O.alpha_dash(200), (1 / 201) ** 2 * 0.25)
+    cfg = O.Config(size=8)
+    x, t, e = O.synthetic_batch(cfg, 3, 0)
+    n = O.noise_images(x, t, e, cfg)
+    a = O.alpha_dash(t.float())[:, None, None, None]
+    assert torch.allclose(n, x * a.sqrt() + e * (1 - a).sqrt())
+    assert x.min() >= -1 and x.max() <= 127 / 128 and t.min() >= 1 and t.max() <= 200
+
+
+def test_finite_difference_gradients():
+    """Central differences in float64 against autograd through the restated layers (the loss is formed here in
+    float64: trainer_loss itself casts to fp32 like train.py:262-263, which would quantise the differences)."""
+    cfg = O.Config(size=16, pixel_size=4, max_size=16, octaves=2)
+    w = {k: v.double() for k, v in O.glorot_init(cfg, 3).items()}
+    for k in w:
+        if k.endswith("bias"):
+            w[k] = w[k] + 0.05  # move off the ReLU kink
+    x, t, e = O.synthetic_batch(cfg, 2, 4)
+    x, e = x.double(), e.double()
+
+    def loss_fn(ws):
+        return ((x - O.denoiser_forward(ws, O.noise_images(x, t, e, cfg), cfg)) ** 2).mean()
+
+    ws = {k: v.clone().requires_grad_(True) for k, v in w.items()}
+    loss_fn(ws).backward()
+    g = torch.Generator().manual_seed(5)
+    for name in ["down0/kernel", "down1/bias", "up1/kernel", "up0/bias", "dense/kernel"]:
+        d = torch.randn(w[name].shape, generator=g, dtype=torch.float64)
+        h = 1e-6
+        wp, wm = dict(w), dict(w)
+        wp[name] = w[name] + h * d
+        wm[name] = w[name] - h * d
+        fd = (loss_fn(wp) - loss_fn(wm)) / (2 * h)
+        an = (ws[name].grad * d).sum()
+        assert abs(fd - an) <= 1e-5 * max(1.0, abs(an)), (name, float(fd), float(an))
+    # and the fp32 path used everywhere else agrees with the float64 autograd
+    _, g32, _ = O.loss_and_grads({k: v.float() for k, v in w.items()}, x.float(), t, e.float(), cfg)
+    for name in g32:
+        assert torch.allclose(g32[name].double(), ws[name].grad, rtol=1e-3, atol=1e-7), name
+
+
+def test_keras_adam_closed_form_first_step():
+    """first step, m=v=0: m1=(1-b1)g, v1=(1-b2)g^2, alpha=lr*sqrt(1-b2)/(1-b1)
+    -> dw = -lr * sqrt(1-b2) * g / (sqrt(1-b2)|g| + eps); NOT torch's Adam (eps placement)."""
+    cfg = O.DEFAULT
+    g = torch.tensor([1e-8, -1e-6, 1e-3, 0.0, 2.0])
+    w, m, v = torch.zeros(5), torch.zeros(5), torch.zeros(5)
+    O.keras_adam_update(w, m, v, g, 0, cfg)
+    lr = 2e-5 / 2001
+    s = math.sqrt(1 - 0.999)
+    expect = -lr * s * g.double() / (s * g.double().abs() + 1e-7)
+    assert torch.allclose(w.double(), expect, rtol=2e-5, atol=1e-18)
+    assert math.isclose(abs(w[0].item()) / lr, 0.0031, rel_tol=0.05)   # |g|=1e-8  (torch-Adam would give 0.09)
+    assert math.isclose(abs(w[1].item()) / lr, 0.2403, rel_tol=0.01)   # |g|=1e-6  (torch-Adam: 0.91)
+
+
+def test_warmup_schedule():
+    wu = O.WarmUp(2e-5, 2000)
+    assert math.isclose(wu(0), 2e-5 / 2001, rel_tol=1e-6)
+    assert math.isclose(wu(1999), 2e-5 * 2000 / 2001, rel_tol=1e-6)
+    assert wu(2000) == 2e-5 and wu(10 ** 6) == 2e-5
+
+
+def test_data_parallel_shards_reproduce_the_global_gradient():
+    """each shard scales by 1/N_global; summing shard gradients gives the full-batch gradient."""
+    cfg = O.Config(size=16, pixel_size=4, max_size=16, octaves=2)
+    w = O.glorot_init(cfg, 0)
+    x, t, e = O.synthetic_batch(cfg, 4, 1)
+    loss, grads, _ = O.loss_and_grads(w, x, t, e, cfg)
+    n = x.numel()
+    parts = [O.loss_and_grads(w, x[i:i + 2], t[i:i + 2], e[i:i + 2], cfg, global_elems=n) for i in (0, 2)]
+    assert math.isclose(float(parts[0][0] + parts[1][0]), float(loss), rel_tol=1e-5)
+    for k in grads:
+        assert torch.allclose(parts[0][1][k] + parts[1][1][k], grads[k], rtol=1e-4, atol=1e-8), k
+
+
+def test_golden_vectors_tiny_step():
+    """Drift check: the oracle reproduces the vectors it generated when it was pinned (make_golden.py)."""
+    gold = np.load(GOLDEN)
+    cfg = O.TINY
+    tr = O.OracleTrainer(cfg, seed=0)
+    x, t, e = O.synthetic_batch(cfg, 2, 1)
+    loss, grads, taps = O.loss_and_grads(tr.weights, x, t, e, cfg, want_taps=True)
+    assert math.isclose(float(loss), float(gold["loss"]), rel_tol=1e-5)
+    for k in grads:
+        assert math.isclose(float(grads[k].norm()), float(gold["gnorm/" + k]), rel_tol=2e-4), k
+    assert np.allclose(taps["pred"][0, :4, :4].numpy(), gold["pred_corner"], rtol=1e-4, atol=1e-6)
+    losses = [tr.train_step(*O.synthetic_batch(cfg, 2, 100 + s)) for s in range(3)]
+    assert np.allclose(losses, gold["losses3"], rtol=1e-5)
