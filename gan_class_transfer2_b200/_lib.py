@@ -43,7 +43,7 @@ _PROTOS = {
     "gct2_debug_set": (None, [c_int, c_int]),
     "gct2_noise_images": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "gct2_conv4s2_c3_fprop": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
-    "gct2_conv4s2_c3_wgrad": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "gct2_conv4s2_c3_wgrad": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "gct2_conv4s2_fprop": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "gct2_conv4s2_dgrad": (c_int, [_P, c_int, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                    _P, c_size_t, _P]),
@@ -53,8 +53,9 @@ _PROTOS = {
                                     _P, c_size_t, _P]),
     "gct2_convT4s2_wgrad": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "gct2_bias_grad": (c_int, [_P, c_int, c_longlong, c_int, _P, _P]),
+    "gct2_bias_grad_multi": (c_int, [c_int, _P, _P, _P, _P, _P, c_int, _P]),
     "gct2_dense_mse": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, c_longlong, c_int, c_float,
-                               c_int, _P]),
+                               c_int, c_int, _P]),
     "gct2_adam_keras": (c_int, [_P, _P, _P, _P, _P, c_longlong, _P, _P, c_float, c_int, c_float, c_float, c_float,
                                 c_float, _P]),
     "gct2_cast_bf16": (c_int, [_P, _P, c_longlong, _P]),

@@ -79,8 +79,8 @@ int gct2_conv4s2_c3_fprop(const float* x, const float* w, const float* bias, uin
   return conv4s2_c3_fprop(x, w, bias, MB(y), ldy, B, H, W, Cout, S(stream));
 }
 int gct2_conv4s2_c3_wgrad(const float* x, const uint16_t* dz, int lddz, float* dw, float* db, int B, int H, int W,
-                          int Cout, void* stream) {
-  return conv4s2_c3_wgrad(x, CB(dz), lddz, dw, db, B, H, W, Cout, S(stream));
+                          int Cout, int accumulate, void* stream) {
+  return conv4s2_c3_wgrad(x, CB(dz), lddz, dw, db, B, H, W, Cout, accumulate ? 0 : 1, S(stream));
 }
 
 int gct2_conv4s2_fprop(const uint16_t* x, int ldx, const uint16_t* w, const float* bias, uint16_t* y, int ldy,
@@ -158,12 +158,17 @@ int gct2_convT4s2_wgrad(const uint16_t* x, int ldx, const uint16_t* dy, int lddy
 int gct2_bias_grad(const uint16_t* dz, int ld, long long rows, int C, float* db, void* stream) {
   return bias_grad(CB(dz), ld, rows, C, db, S(stream));
 }
+int gct2_bias_grad_multi(int n, const uint16_t* const* dz, const int* ld, const long long* rows, const int* C,
+                         float* const* db, int accumulate, void* stream) {
+  return bias_grad_multi(n, reinterpret_cast<const __nv_bfloat16* const*>(dz), ld, rows, C, db, accumulate ? 0 : 1,
+                         S(stream));
+}
 
 int gct2_dense_mse(const uint16_t* u0, int ldu, const float* noised, const float* x, const float* wd,
                    const float* bd, float* pred, float* loss, uint16_t* du0, int lddu, float* dwd, float* dbd,
-                   long long pixels, int Cu, float inv_n, int backward, void* stream) {
+                   long long pixels, int Cu, float inv_n, int backward, int accumulate, void* stream) {
   return dense_mse(CB(u0), ldu, noised, x, wd, bd, pred, loss, MB(du0), lddu, dwd, dbd, pixels, Cu, inv_n, backward,
-                   S(stream));
+                   accumulate ? 0 : 1, S(stream));
 }
 
 int gct2_adam_keras(float* w, float* m, float* v, const float* g, uint16_t* w_bf16, long long n,

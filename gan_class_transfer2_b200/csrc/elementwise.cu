@@ -167,20 +167,22 @@ __global__ void __launch_bounds__(128) conv_c3_wgrad_kernel(const float* __restr
   }
 #pragma unroll
   for (int k = 0; k < 48; ++k) atomicAdd(dw + k * Cout + co, acc[k]);
-  atomicAdd(db + co, accb);
+  if (db != nullptr) atomicAdd(db + co, accb);
 }
 
 int conv4s2_c3_wgrad(const float* x, const __nv_bfloat16* dz, int lddz, float* dw, float* db, int B, int H, int W,
-                     int Cout, cudaStream_t st) {
+                     int Cout, int zero, cudaStream_t st) {
   if ((H / 2) % C3_T || (W / 2) % C3_T || Cout % 128) {
     set_error("conv4s2_c3_wgrad: unsupported shape H=%d W=%d Cout=%d", H, W, Cout);
     return 1;
   }
-  cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)48 * Cout * sizeof(float), st);
-  if (e == cudaSuccess) e = cudaMemsetAsync(db, 0, (size_t)Cout * sizeof(float), st);
-  if (e != cudaSuccess) {
-    set_error("conv4s2_c3_wgrad memset: %s", cudaGetErrorString(e));
-    return 1;
+  if (zero) {
+    cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)48 * Cout * sizeof(float), st);
+    if (e == cudaSuccess && db != nullptr) e = cudaMemsetAsync(db, 0, (size_t)Cout * sizeof(float), st);
+    if (e != cudaSuccess) {
+      set_error("conv4s2_c3_wgrad memset: %s", cudaGetErrorString(e));
+      return 1;
+    }
   }
   const int numTiles = B * (H / 2 / C3_T) * (W / 2 / C3_T);
   int gx = numTiles < 2 * g_ew_sms ? numTiles : 2 * g_ew_sms;
@@ -191,10 +193,12 @@ int conv4s2_c3_wgrad(const float* x, const __nv_bfloat16* dz, int lddz, float* d
 }
 
 // ------------------------------------------------------------------------------------ Dense(3) + MSE (a6,a7)
-// One warp walks pixels; lane l owns channels 2l, 2l+1 of the 64-channel up0 output, the 3 image channels are
-// handled redundantly by every lane.  Emits pred (optional), the loss partial, du0 = relu'(u0) * (dpred . Wd^T)
-// as bf16, and the Dense weight/bias gradients (warp-shuffle reductions, one atomic per warp per value).
-//   pred = [u0 | noised] . Wd + bd ;  loss = mean((x - pred)^2) ;  dpred = 2 (pred - x) / Ntot
+// LPP lanes share one pixel (lane `sub` owns 8 of the Cu = 8*LPP up0 channels: one 16-byte load / store), so a warp
+// walks 32/LPP pixels per iteration; the 3 image channels are handled by every lane of the group (broadcast loads).
+//   pred = [u0 | noised] . Wd + bd ;  loss = sum((pred - x)^2) * invN ;  dpred = 2 (pred - x) * invN
+//   du0 = relu'(u0) * (dpred . Wd^T)  (bf16) ;  dWd, dbd by warp-shuffle + shared-memory reduction, one atomic per
+//   block per value (the caller zeroes loss / dwd / dbd).
+template <int LPP>
 __global__ void __launch_bounds__(256) dense_mse_kernel(const __nv_bfloat16* __restrict__ u0, int ldu,
                                                         const float* __restrict__ noised,
                                                         const float* __restrict__ x, const float* __restrict__ wd,
@@ -202,145 +206,261 @@ __global__ void __launch_bounds__(256) dense_mse_kernel(const __nv_bfloat16* __r
                                                         float* __restrict__ loss, __nv_bfloat16* __restrict__ du0,
                                                         int lddu, float* __restrict__ dwd, float* __restrict__ dbd,
                                                         long long pixels, float invN, int backward) {
-  const int lane = threadIdx.x & 31;
-  const int warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int numWarps = (gridDim.x * blockDim.x) >> 5;
-  float w0[3], w1[3], wn[9], bv[3];
+  constexpr int PPW = 32 / LPP;        // pixels per warp iteration
+  constexpr int CU = 8 * LPP;
+  constexpr int NRED = CU * 3 + 9 + 3 + 1;  // dWd(u0 part) | dWd(image part) | dbd | loss
+  __shared__ float red[8][NRED];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane % LPP, pg = lane / LPP;
+  const long long warpGlobal = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  const long long numWarps = (long long)gridDim.x * (blockDim.x >> 5);
+  float w[8][3], wn[9], bv[3];
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    w0[j] = __ldg(wd + (2 * lane) * 3 + j);
-    w1[j] = __ldg(wd + (2 * lane + 1) * 3 + j);
-    bv[j] = __ldg(bd + j);
-  }
+  for (int c = 0; c < 8; ++c)
 #pragma unroll
-  for (int k = 0; k < 9; ++k) wn[k] = __ldg(wd + 64 * 3 + k);
-  float g0[3] = {0.f, 0.f, 0.f}, g1[3] = {0.f, 0.f, 0.f}, gn[9], gb[3] = {0.f, 0.f, 0.f};
+    for (int j = 0; j < 3; ++j) w[c][j] = __ldg(wd + (sub * 8 + c) * 3 + j);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) wn[k] = __ldg(wd + CU * 3 + k);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) bv[j] = __ldg(bd + j);
+  float g[8][3], gn[9], gb[3] = {0.f, 0.f, 0.f}, lossAcc = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) g[c][0] = g[c][1] = g[c][2] = 0.f;
 #pragma unroll
   for (int k = 0; k < 9; ++k) gn[k] = 0.f;
-  float lossAcc = 0.f;
-  for (long long p = warpGlobal; p < pixels; p += numWarps) {
-    const uint32_t uv = __ldg(reinterpret_cast<const uint32_t*>(u0 + p * ldu) + lane);
-    const float a0 = bf16_lo(uv), a1 = bf16_hi(uv);
-    float s[3];
+
+  for (long long p0 = warpGlobal * PPW; p0 < pixels; p0 += numWarps * PPW) {
+    const long long p = p0 + pg;
+    const bool live = p < pixels;
+    float a[8];
+    float nz[3] = {0.f, 0.f, 0.f}, xv[3] = {0.f, 0.f, 0.f};
+    if (live) {
+      const uint4 uv = __ldg(reinterpret_cast<const uint4*>(u0 + p * ldu + sub * 8));
+      a[0] = bf16_lo(uv.x); a[1] = bf16_hi(uv.x); a[2] = bf16_lo(uv.y); a[3] = bf16_hi(uv.y);
+      a[4] = bf16_lo(uv.z); a[5] = bf16_hi(uv.z); a[6] = bf16_lo(uv.w); a[7] = bf16_hi(uv.w);
 #pragma unroll
-    for (int j = 0; j < 3; ++j) s[j] = warp_sum(a0 * w0[j] + a1 * w1[j]);
-    float nz[3], xv[3], d[3];
+      for (int c = 0; c < 3; ++c) {
+        nz[c] = __ldg(noised + p * 3 + c);
+        xv[c] = __ldg(x + p * 3 + c);
+      }
+    } else {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      nz[c] = __ldg(noised + p * 3 + c);
-      xv[c] = __ldg(x + p * 3 + c);
+      for (int c = 0; c < 8; ++c) a[c] = 0.f;
     }
+    float s[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) s[j] = fmaf(a[c], w[c][j], s[j]);
+#pragma unroll
+    for (int o = LPP / 2; o > 0; o >>= 1)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+    float d[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const float pj = s[j] + nz[0] * wn[j] + nz[1] * wn[3 + j] + nz[2] * wn[6 + j] + bv[j];
-      if (pred != nullptr && lane == j) pred[p * 3 + j] = pj;
-      const float diff = pj - xv[j];
-      lossAcc += diff * diff;
+      if (pred != nullptr && live && sub == j) pred[p * 3 + j] = pj;
+      const float diff = live ? pj - xv[j] : 0.f;
+      if (sub == 0) lossAcc = fmaf(diff, diff, lossAcc);
       d[j] = 2.f * diff * invN;
     }
-    if (backward) {
-      const float r0 = a0 > 0.f ? d[0] * w0[0] + d[1] * w0[1] + d[2] * w0[2] : 0.f;
-      const float r1 = a1 > 0.f ? d[0] * w1[0] + d[1] * w1[1] + d[2] * w1[2] : 0.f;
-      reinterpret_cast<uint32_t*>(du0 + p * lddu)[lane] = pack_bf16x2(r0, r1);
+    if (backward && live) {
+      float r[8];
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        g0[j] = fmaf(a0, d[j], g0[j]);
-        g1[j] = fmaf(a1, d[j], g1[j]);
-        gb[j] += d[j];
+      for (int c = 0; c < 8; ++c) {
+        r[c] = a[c] > 0.f ? d[0] * w[c][0] + d[1] * w[c][1] + d[2] * w[c][2] : 0.f;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) gn[c * 3 + j] = fmaf(nz[c], d[j], gn[c * 3 + j]);
+        for (int j = 0; j < 3; ++j) g[c][j] = fmaf(a[c], d[j], g[c][j]);
+      }
+      uint4 o;
+      o.x = pack_bf16x2(r[0], r[1]); o.y = pack_bf16x2(r[2], r[3]);
+      o.z = pack_bf16x2(r[4], r[5]); o.w = pack_bf16x2(r[6], r[7]);
+      *reinterpret_cast<uint4*>(du0 + p * lddu + sub * 8) = o;
+      if (sub == 0) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          gb[j] += d[j];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) gn[c * 3 + j] = fmaf(nz[c], d[j], gn[c * 3 + j]);
+        }
       }
     }
   }
-  // every lane accumulated the same lossAcc / gn / gb (redundant work), so lane 0 publishes them.
-  if (lane == 0) atomicAdd(loss, lossAcc * invN);
-  if (backward) {
+  // reduce over the pixel groups of the warp (lanes with equal `sub`), then over the block's warps
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      atomicAdd(dwd + (2 * lane) * 3 + j, g0[j]);
-      atomicAdd(dwd + (2 * lane + 1) * 3 + j, g1[j]);
+  for (int o = LPP; o < 32; o <<= 1) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) g[c][j] += __shfl_xor_sync(0xffffffffu, g[c][j], o);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) gn[k] += __shfl_xor_sync(0xffffffffu, gn[k], o);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) gb[j] += __shfl_xor_sync(0xffffffffu, gb[j], o);
+    lossAcc += __shfl_xor_sync(0xffffffffu, lossAcc, o);
+  }
+  if (pg == 0) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) red[warp][(sub * 8 + c) * 3 + j] = g[c][j];
+    if (sub == 0) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) red[warp][CU * 3 + k] = gn[k];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) red[warp][CU * 3 + 9 + j] = gb[j];
+      red[warp][CU * 3 + 12] = lossAcc;
     }
-    if (lane == 0) {
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NRED; i += blockDim.x) {
+    float v = 0.f;
 #pragma unroll
-      for (int k = 0; k < 9; ++k) atomicAdd(dwd + 64 * 3 + k, gn[k]);
-#pragma unroll
-      for (int j = 0; j < 3; ++j) atomicAdd(dbd + j, gb[j]);
+    for (int wv = 0; wv < 8; ++wv) v += red[wv][i];
+    if (i == CU * 3 + 12)
+      atomicAdd(loss, v * invN);
+    else if (backward) {
+      if (i < CU * 3 + 9)
+        atomicAdd(dwd + i, v);
+      else
+        atomicAdd(dbd + (i - CU * 3 - 9), v);
     }
   }
 }
 
 int dense_mse(const __nv_bfloat16* u0, int ldu, const float* noised, const float* x, const float* wd,
               const float* bd, float* pred, float* loss, __nv_bfloat16* du0, int lddu, float* dwd, float* dbd,
-              long long pixels, int Cu, float invN, int backward, cudaStream_t st) {
-  if (Cu != 64) {
-    set_error("dense_mse: the fused kernel expects 64 up0 channels (+3 image channels), got %d", Cu);
+              long long pixels, int Cu, float invN, int backward, int zero, cudaStream_t st) {
+  if (Cu != 64 && Cu != 128) {
+    set_error("dense_mse: the fused kernel expects 64 or 128 up0 channels (+3 image channels), got %d", Cu);
     return 1;
   }
-  cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), st);
-  if (backward && e == cudaSuccess) e = cudaMemsetAsync(dwd, 0, 67 * 3 * sizeof(float), st);
-  if (backward && e == cudaSuccess) e = cudaMemsetAsync(dbd, 0, 3 * sizeof(float), st);
-  if (e != cudaSuccess) {
-    set_error("dense_mse memset: %s", cudaGetErrorString(e));
+  if ((ldu % 8) || (backward && (lddu % 8))) {
+    set_error("dense_mse: pixel strides must be multiples of 8 elements");
     return 1;
   }
-  const int blocks = g_ew_sms * 4;
-  dense_mse_kernel<<<blocks, 256, 0, st>>>(u0, ldu, noised, x, wd, bd, pred, loss, du0, lddu, dwd, dbd, pixels, invN,
-                                          backward);
+  if (zero) {
+    cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), st);
+    if (backward && e == cudaSuccess) e = cudaMemsetAsync(dwd, 0, (size_t)(Cu + 3) * 3 * sizeof(float), st);
+    if (backward && e == cudaSuccess) e = cudaMemsetAsync(dbd, 0, 3 * sizeof(float), st);
+    if (e != cudaSuccess) {
+      set_error("dense_mse memset: %s", cudaGetErrorString(e));
+      return 1;
+    }
+  }
+  long long want = (pixels * (Cu / 8) + 255) / 256;  // one 16-byte vector per thread per iteration
+  int blocks = (int)(want < (long long)g_ew_sms * 2 ? want : (long long)g_ew_sms * 2);
+  if (blocks < 1) blocks = 1;
+  if (Cu == 64)
+    dense_mse_kernel<8><<<blocks, 256, 0, st>>>(u0, ldu, noised, x, wd, bd, pred, loss, du0, lddu, dwd, dbd, pixels, invN,
+                                                backward);
+  else
+    dense_mse_kernel<16><<<blocks, 256, 0, st>>>(u0, ldu, noised, x, wd, bd, pred, loss, du0, lddu, dwd, dbd, pixels,
+                                                 invN, backward);
   GCT2_CHECK_LAUNCH("dense_mse_kernel");
   return 0;
 }
 
-// ------------------------------------------------------------------------------------ bias gradient
-// db[c] = sum_rows dz[row, c]; thread = channel pair, blockDim.y row groups, one atomic per block per channel.
-__global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ dz, int ld, long long rows, int C,
-                                 float* __restrict__ db, int rowsPerBlock) {
+// ------------------------------------------------------------------------------------ bias gradients
+// db[c] = sum_rows dz[row, c] for up to BG_MAX_SEG tensors in ONE launch (every conv layer's BiasAddGrad).  A block
+// owns a row range of one segment; thread = channel pair, blockDim.x/pairs row groups; shared-memory reduce, one
+// atomic per block per channel (the caller zeroes the outputs).
+constexpr int BG_MAX_SEG = 16;
+struct BiasGradSegs {
+  const __nv_bfloat16* dz[BG_MAX_SEG];
+  float* db[BG_MAX_SEG];
+  long long rows[BG_MAX_SEG];
+  int ld[BG_MAX_SEG], C[BG_MAX_SEG], firstBlock[BG_MAX_SEG + 1], rowsPerBlock[BG_MAX_SEG];
+  int n;
+};
+
+__global__ void __launch_bounds__(512) bias_grad_kernel(const __grid_constant__ BiasGradSegs sg) {
   extern __shared__ float red[];  // [groups][C]
+  int s = 0;
+  while (s + 1 < sg.n && (int)blockIdx.x >= sg.firstBlock[s + 1]) ++s;
+  const __nv_bfloat16* __restrict__ dz = sg.dz[s];
+  const int C = sg.C[s], ld = sg.ld[s];
   const int pairs = C / 2;
   const int groups = blockDim.x / pairs;
   const int pr = threadIdx.x % pairs, grp = threadIdx.x / pairs;
-  const long long r0 = (long long)blockIdx.x * rowsPerBlock;
-  long long r1 = r0 + rowsPerBlock;
-  if (r1 > rows) r1 = rows;
-  float s0 = 0.f, s1 = 0.f;
+  const long long r0 = (long long)(blockIdx.x - sg.firstBlock[s]) * sg.rowsPerBlock[s];
+  long long r1 = r0 + sg.rowsPerBlock[s];
+  if (r1 > sg.rows[s]) r1 = sg.rows[s];
   if (grp < groups) {
-    for (long long r = r0 + grp; r < r1; r += groups) {
+    float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
+    long long r = r0 + grp;
+    for (; r + groups < r1; r += 2 * groups) {  // two independent loads in flight
       const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(dz + r * ld) + pr);
-      s0 += bf16_lo(v);
-      s1 += bf16_hi(v);
+      const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(dz + (r + groups) * ld) + pr);
+      s0 += bf16_lo(v); s1 += bf16_hi(v);
+      t0 += bf16_lo(u); t1 += bf16_hi(u);
     }
-    red[grp * C + 2 * pr] = s0;
-    red[grp * C + 2 * pr + 1] = s1;
+    if (r < r1) {
+      const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(dz + r * ld) + pr);
+      s0 += bf16_lo(v); s1 += bf16_hi(v);
+    }
+    red[grp * C + 2 * pr] = s0 + t0;
+    red[grp * C + 2 * pr + 1] = s1 + t1;
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f;
-    for (int g = 0; g < groups; ++g) s += red[g * C + c];
-    atomicAdd(db + c, s);
+    float v = 0.f;
+    for (int g = 0; g < groups; ++g) v += red[g * C + c];
+    atomicAdd(sg.db[s] + c, v);
   }
 }
 
-int bias_grad(const __nv_bfloat16* dz, int ld, long long rows, int C, float* db, cudaStream_t st) {
-  if (C % 2 || C > 1024 || C < 2) {
-    set_error("bias_grad: unsupported channel count %d", C);
+int bias_grad_multi(int n, const __nv_bfloat16* const* dz, const int* ld, const long long* rows, const int* C,
+                    float* const* db, int zero, cudaStream_t st) {
+  if (n < 1 || n > BG_MAX_SEG) {
+    set_error("bias_grad: between 1 and %d tensors per call, got %d", BG_MAX_SEG, n);
     return 1;
   }
-  cudaError_t e = cudaMemsetAsync(db, 0, (size_t)C * sizeof(float), st);
-  if (e != cudaSuccess) {
-    set_error("bias_grad memset: %s", cudaGetErrorString(e));
-    return 1;
+  BiasGradSegs sg;
+  sg.n = n;
+  int block = 0, maxC = 0;
+  long long totalRows = 0;
+  for (int i = 0; i < n; ++i) totalRows += rows[i];
+  const long long budget = (long long)g_ew_sms * 8;  // blocks over all segments
+  for (int i = 0; i < n; ++i) {
+    if (C[i] % 2 || C[i] > 1024 || C[i] < 2 || rows[i] < 1) {
+      set_error("bias_grad: unsupported tensor %d (C=%d rows=%lld)", i, C[i], rows[i]);
+      return 1;
+    }
+    long long nb = (budget * rows[i] + totalRows - 1) / totalRows;
+    const long long cap = (rows[i] + 31) / 32;  // at least 32 rows per block
+    if (nb > cap) nb = cap;
+    if (nb < 1) nb = 1;
+    const int rpb = (int)((rows[i] + nb - 1) / nb);
+    nb = (rows[i] + rpb - 1) / rpb;
+    sg.dz[i] = dz[i]; sg.db[i] = db[i]; sg.rows[i] = rows[i]; sg.ld[i] = ld[i]; sg.C[i] = C[i];
+    sg.firstBlock[i] = block; sg.rowsPerBlock[i] = rpb;
+    block += (int)nb;
+    if (C[i] > maxC) maxC = C[i];
+    if (zero) {
+      cudaError_t e = cudaMemsetAsync(db[i], 0, (size_t)C[i] * sizeof(float), st);
+      if (e != cudaSuccess) {
+        set_error("bias_grad memset: %s", cudaGetErrorString(e));
+        return 1;
+      }
+    }
   }
-  const int pairs = C / 2;
-  int threads = pairs >= 256 ? pairs : (256 / pairs) * pairs;
-  const int groups = threads / pairs;
-  long long blocks = (rows + 63) / 64;
-  if (blocks > g_ew_sms * 4) blocks = g_ew_sms * 4;
-  if (blocks < 1) blocks = 1;
-  const int rowsPerBlock = (int)((rows + blocks - 1) / blocks);
-  blocks = (rows + rowsPerBlock - 1) / rowsPerBlock;
-  bias_grad_kernel<<<(int)blocks, threads, (size_t)groups * C * sizeof(float), st>>>(dz, ld, rows, C, db,
-                                                                                     rowsPerBlock);
+  sg.firstBlock[n] = block;
+  // 512 threads: pairs <= 512 always fits; groups = 512 / pairs (pairs need not divide 512: spare threads idle)
+  const int threads = 512;
+  size_t smem = 0;
+  for (int i = 0; i < n; ++i) {
+    const size_t need = (size_t)(threads / (C[i] / 2)) * C[i] * sizeof(float);
+    if (need > smem) smem = need;
+  }
+  bias_grad_kernel<<<block, threads, smem, st>>>(sg);
   GCT2_CHECK_LAUNCH("bias_grad_kernel");
   return 0;
+}
+
+int bias_grad(const __nv_bfloat16* dz, int ld, long long rows, int C, float* db, cudaStream_t st) {
+  return bias_grad_multi(1, &dz, &ld, &rows, &C, &db, 1, st);
 }
 
 // ------------------------------------------------------------------------------------ Keras Adam (a9)

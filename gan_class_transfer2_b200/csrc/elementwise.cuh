@@ -11,10 +11,12 @@ int noise_images(const float* x, const float* eps, const int* t_int, float* nois
 int conv4s2_c3_fprop(const float* x, const float* w, const float* bias, __nv_bfloat16* y, int ldy, int B, int H,
                      int W, int Cout, cudaStream_t st);
 int conv4s2_c3_wgrad(const float* x, const __nv_bfloat16* dz, int lddz, float* dw, float* db, int B, int H, int W,
-                     int Cout, cudaStream_t st);
+                     int Cout, int zero, cudaStream_t st);
 int dense_mse(const __nv_bfloat16* u0, int ldu, const float* noised, const float* x, const float* wd,
               const float* bd, float* pred, float* loss, __nv_bfloat16* du0, int lddu, float* dwd, float* dbd,
-              long long pixels, int Cu, float invN, int backward, cudaStream_t st);
+              long long pixels, int Cu, float invN, int backward, int zero, cudaStream_t st);
+int bias_grad_multi(int n, const __nv_bfloat16* const* dz, const int* ld, const long long* rows, const int* C,
+                    float* const* db, int zero, cudaStream_t st);
 int bias_grad(const __nv_bfloat16* dz, int ld, long long rows, int C, float* db, cudaStream_t st);
 int adam_keras(float* w, float* m, float* v, const float* g, __nv_bfloat16* w_bf16, long long n,
                long long* iterations, float* hyper, float base_lr, int warmup_steps, float beta1, float beta2,

@@ -11,10 +11,11 @@ Data layout in HBM (B = per-GPU batch, S = size, n = octaves; all activations NH
   bot               bf16 [B,S/2^n,S/2^n,down_c[n-1]]      bottleneck (down_{n-1} output)
   u0                bf16 [B,S,S,up_c[0]]                  up_0 output; Dense(3) reads u0 and noised separately
   gcat[j], gbot, gu0   same shapes: gradients w.r.t. the *pre-activation* of the producing layer (ReLU mask applied)
-  w, m, v, g        fp32 flat [P] in Keras variable order (down0..down{n-1}, up{n-1}..up0, dense; kernel, bias)
+  w, m, v, g        fp32 flat [P]: a small head region (down0's kernel, all biases, Dense) followed by the
+                    tensor-core kernels down1..down{n-1}, up{n-1}..up0 (see param_offsets)
   w16               bf16 flat [P] shadow copy read by the tensor-core kernels (rewritten by the Adam kernel)
-Backward walks the flat gradient buffer from its end to its start (dense, up0..up{n-1}, down{n-1}..down0), so the
-data-parallel buckets are contiguous tail-to-head ranges that become ready in order.
+Backward completes the flat gradient buffer from its end to its start (up0..up{n-1}, down{n-1}..down1, small region),
+so the data-parallel buckets are contiguous tail-to-head ranges that become ready in order.
 """
 from __future__ import annotations
 
@@ -92,30 +93,59 @@ def glorot_uniform(shape, generator) -> torch.Tensor:
     return (torch.rand(shape, generator=generator, dtype=torch.float32) * 2 - 1) * limit
 
 
+def small_names(cfg: NetConfig) -> List[str]:
+    """Variables whose gradients are accumulated with atomics by HBM-bound kernels (down0's kernel, every bias, the
+    Dense layer): they live together at the head of the flat buffers so that one memset zeroes their gradients."""
+    names = ["down0/kernel"] + [n for n, _ in variable_specs(cfg) if n.endswith("bias") and not n.startswith("dense")]
+    return names + ["dense/kernel", "dense/bias"]
+
+
 def param_offsets(cfg: NetConfig) -> Tuple[Dict[str, Tuple[int, int]], int]:
-    """name -> (offset, count) in the flat Keras-order buffer, and the total element count."""
+    """name -> (offset, count) in the flat buffers, and the total element count.
+
+    Internal layout (the Keras variable order of variable_specs is the *naming* convention, not the address order):
+      [ small region: down0/kernel, biases in Keras order, dense/kernel, dense/bias, padded to 64 elements ]
+      [ down1/kernel .. down{n-1}/kernel, up{n-1}/kernel .. up0/kernel ]
+    Backward completes the tensor-core kernels' gradients from the tail (up0) to down1 and the small region last, so
+    data-parallel buckets are contiguous tail-to-head ranges.  Every tensor-core kernel starts on a 128-byte boundary
+    (TMA needs 16)."""
+    shapes = dict(variable_specs(cfg))
     offsets: Dict[str, Tuple[int, int]] = {}
     off = 0
+    for name in small_names(cfg):
+        cnt = math.prod(shapes[name])
+        offsets[name] = (off, cnt)
+        off += cnt
+    off = (off + 63) // 64 * 64
     for name, shape in variable_specs(cfg):
+        if name in offsets:
+            continue
         cnt = math.prod(shape)
         offsets[name] = (off, cnt)
         off += cnt
     return offsets, off
 
 
+def small_region(cfg: NetConfig) -> int:
+    """Element count of the head region described in param_offsets (including its padding)."""
+    offsets, _ = param_offsets(cfg)
+    return min(off for name, (off, _) in offsets.items() if name not in small_names(cfg))
+
+
 def grad_buckets(cfg: NetConfig, bucket_bytes: int) -> List[Tuple[int, int, str]]:
     """Data-parallel gradient buckets: contiguous [start, end) ranges of the flat fp32 gradient buffer, listed tail
-    to head (the order backward completes them: dense, up0..up{n-1}, down{n-1}..down0), each closed by the layer whose
-    weight gradient completes it.  Together they tile [0, P) exactly once."""
+    to head (the order backward completes them: up0..up{n-1}, down{n-1}..down1, then the small region), each closed by
+    the variable whose gradient completes it.  Together they tile [0, P) exactly once."""
     offsets, total = param_offsets(cfg)
-    order = ["dense"] + [f"up{i}" for i in range(cfg.octaves)] + [f"down{i}" for i in reversed(range(cfg.octaves))]
+    order = [f"up{i}/kernel" for i in range(cfg.octaves)] + [f"down{i}/kernel" for i in reversed(range(1, cfg.octaves))]
     buckets: List[Tuple[int, int, str]] = []
     cur_end = total
-    for layer in order:
-        start = offsets[f"{layer}/kernel"][0]
-        if (cur_end - start) * 4 >= bucket_bytes or layer == order[-1]:
-            buckets.append((start, cur_end, f"{layer}/kernel"))
+    for name in order:
+        start = offsets[name][0]
+        if (cur_end - start) * 4 >= bucket_bytes:
+            buckets.append((start, cur_end, name))
             cur_end = start
+    buckets.append((0, cur_end, "down0/kernel"))  # remaining kernels (if any) + the small region, ready last
     return buckets
 
 
@@ -159,8 +189,9 @@ class UNetEngine:
         # ---- parameters, flat in Keras order
         self.specs = variable_specs(cfg)
         self.offsets, self.P = param_offsets(cfg)
+        self.small = small_region(cfg)
         if self.P % 4:
-            raise ValueError("parameter count must be a multiple of 4")
+            raise ValueError("flat parameter buffer must be a multiple of 4 elements")
         f32 = dict(dtype=torch.float32, device=dev)
         if share_params_with is not None:
             # a second batch size over the same variables (e.g. the reference's batch-6 sampling, train.py:432-450)
@@ -200,6 +231,9 @@ class UNetEngine:
         self.ws = ops.Workspace(4 * biggest, dev)
         self.global_batch = B * (dp.world if dp else 1)
         self._buckets = self._make_buckets() if dp else []
+        layers = [f"down{i}" for i in range(n)] + [f"up{i}" for i in range(n)]
+        self._bias_plan = ops.BiasGradPlan([self.gdown_out(i) for i in range(n)] + [self.gup_out(i) for i in range(n)],
+                                           [self.view(self.g, f"{l}/bias") for l in layers])
 
     # ------------------------------------------------------------------------------------------ parameter access
     def view(self, buf: torch.Tensor, name: str) -> torch.Tensor:
@@ -267,15 +301,13 @@ class UNetEngine:
         ops.dense_mse(self.u0, self.noised, self.x, self.view(self.w, "dense/kernel"), self.view(self.w, "dense/bias"),
                       self.loss, inv_n, pred=self.pred if want_pred else None,
                       du0=self.gu0 if backward else None, dwd=self.view(self.g, "dense/kernel") if backward else None,
-                      dbd=self.view(self.g, "dense/bias") if backward else None)
+                      dbd=self.view(self.g, "dense/bias") if backward else None, accumulate=True)
 
     def _backward(self) -> None:
         cfg, n = self.cfg, self.cfg.octaves
-        self._bucket_ready("dense/kernel")
         for i in range(n):  # up0 .. up{n-1}
             dz = self.gup_out(i)
             ops.convT4s2_wgrad(self.up_in_buf(i), dz, self.view(self.g, f"up{i}/kernel"))
-            ops.bias_grad(dz, self.view(self.g, f"up{i}/bias"))
             self._bucket_ready(f"up{i}/kernel")
             mask = cfg.down_c(i) if i == n - 1 else cfg.up_c(i + 1)
             ops.convT4s2_dgrad(dz, self.view(self.w16, f"up{i}/kernel"), self.gup_in_buf(i), self.up_in_buf(i), mask,
@@ -283,14 +315,19 @@ class UNetEngine:
         for i in reversed(range(1, n)):  # down{n-1} .. down1
             dz = self.gdown_out(i)
             ops.conv4s2_wgrad(self.down_in(i), dz, self.view(self.g, f"down{i}/kernel"))
-            ops.bias_grad(dz, self.view(self.g, f"down{i}/bias"))
             self._bucket_ready(f"down{i}/kernel")
             # total gradient of down_{i-1}'s output = skip-path part (already stored raw by up_{i-1}'s dgrad) + this
             ops.conv4s2_dgrad(dz, self.view(self.w16, f"down{i}/kernel"), self.gcat[i][..., cfg.up_c(i):],
                               self.down_in(i), True, self.ws)
-        ops.conv4s2_c3_wgrad(self.noised, self.gdown_out(0), self.view(self.g, "down0/kernel"),
-                             self.view(self.g, "down0/bias"))
+        ops.conv4s2_c3_wgrad(self.noised, self.gdown_out(0), self.view(self.g, "down0/kernel"), None, accumulate=True)
+        # every conv layer's BiasAddGrad in one launch: the pre-activation gradients all still sit in their buffers
+        ops.bias_grad_multi(self._bias_plan, accumulate=True)
         self._bucket_ready("down0/kernel")
+
+    def _zero_small_grads(self) -> None:
+        """One memset for everything the HBM-bound kernels accumulate atomically (param_offsets' head region) + loss."""
+        self.g[:self.small].zero_()
+        self.loss.zero_()
 
     # ------------------------------------------------------------------------------------------ data parallel
     def _make_buckets(self) -> List[Tuple[int, int, str]]:
@@ -324,6 +361,7 @@ class UNetEngine:
             # train.py:224-227: t_int ~ U{1..steps}, epsilon ~ N(0,1), drawn on the device every step
             self.t_int.random_(1, cfg.steps + 1)
             self.eps.normal_()
+        self._zero_small_grads()
         ops.noise_images(self.x, self.eps, self.t_int, self.noised, cfg.steps)
         self._forward(want_pred=False, backward=True, inv_n=inv_n)
         self._backward()
@@ -398,6 +436,7 @@ class UNetEngine:
         self.set_batch(x, t_int, eps)
         self._pending, self._deferred = [], []
         inv_n = 1.0 / (self.global_batch * self.cfg.size * self.cfg.size * 3)
+        self._zero_small_grads()
         ops.noise_images(self.x, self.eps, self.t_int, self.noised, self.cfg.steps)
         self._forward(want_pred=True, backward=True, inv_n=inv_n)
         self._backward()
@@ -408,5 +447,6 @@ class UNetEngine:
         """Denoiser.call (train.py:206-215): forward only on an already-noised image; returns the fp32 prediction."""
         self.noised.copy_(noised, non_blocking=True)
         self.x.copy_(self.noised)
+        self.loss.zero_()
         self._forward(want_pred=True, backward=False, inv_n=1.0)
         return self.pred

@@ -100,11 +100,12 @@ def conv4s2_c3_fprop(x, w, bias, y):
 
 
 @_timed
-def conv4s2_c3_wgrad(x, dz, dw, db):
+def conv4s2_c3_wgrad(x, dz, dw, db=None, accumulate: bool = False):
+    """Weight (and, when db is given, bias) gradient of down0.  accumulate=True adds into pre-zeroed outputs."""
     lib = _lib_for(x)
     B, H, W, _ = x.shape
     check(lib.gct2_conv4s2_c3_wgrad(ptr(x), ptr(dz), _nhwc(dz, torch.bfloat16), ptr(dw), ptr(db), B, H, W, dz.shape[3],
-                                    current_stream()))
+                                    int(accumulate), current_stream()))
 
 
 @_timed
@@ -178,8 +179,35 @@ def bias_grad(dz, db):
     return db
 
 
+class BiasGradPlan:
+    """Host-side argument arrays of gct2_bias_grad_multi, built once for a fixed set of buffers."""
+
+    def __init__(self, dzs, dbs):
+        import ctypes
+        n = len(dzs)
+        self.n = n
+        self.keep = (list(dzs), list(dbs))
+        self.dz = (ctypes.c_void_p * n)(*[ptr(t) for t in dzs])
+        self.db = (ctypes.c_void_p * n)(*[ptr(t) for t in dbs])
+        self.ld = (ctypes.c_int * n)(*[_nhwc(t, torch.bfloat16) for t in dzs])
+        self.rows = (ctypes.c_longlong * n)(*[t.shape[0] * t.shape[1] * t.shape[2] for t in dzs])
+        self.C = (ctypes.c_int * n)(*[t.shape[3] for t in dzs])
+        for t, d in zip(dzs, dbs):
+            if d.numel() != t.shape[3] or d.dtype != torch.float32:
+                raise _lib.Gct2Error("bias gradient outputs must be fp32 [C]")
+
+
 @_timed
-def dense_mse(u0, noised, x, wd, bd, loss, inv_n: float, pred=None, du0=None, dwd=None, dbd=None):
+def bias_grad_multi(plan: BiasGradPlan, accumulate: bool = False):
+    """BiasAddGrad of every conv layer in one launch: db_i[c] = sum over pixels of dz_i[..., c]."""
+    lib = _lib_for(plan.keep[0][0])
+    check(lib.gct2_bias_grad_multi(plan.n, plan.dz, plan.ld, plan.rows, plan.C, plan.db, int(accumulate),
+                                   current_stream()))
+
+
+@_timed
+def dense_mse(u0, noised, x, wd, bd, loss, inv_n: float, pred=None, du0=None, dwd=None, dbd=None,
+              accumulate: bool = False):
     """Dense(3) on concat([u0, noised]) (train.py:198-202) fused with the MSE (train.py:262-272) and, when du0 is
     given, their backward."""
     lib = _lib_for(u0)
@@ -187,7 +215,7 @@ def dense_mse(u0, noised, x, wd, bd, loss, inv_n: float, pred=None, du0=None, dw
     pixels = u0.shape[0] * u0.shape[1] * u0.shape[2]
     check(lib.gct2_dense_mse(ptr(u0), _nhwc(u0, torch.bfloat16), ptr(noised), ptr(x), ptr(wd), ptr(bd), ptr(pred),
                              ptr(loss), ptr(du0), _nhwc(du0, torch.bfloat16) if backward else 0, ptr(dwd), ptr(dbd),
-                             pixels, u0.shape[3], inv_n, int(backward), current_stream()))
+                             pixels, u0.shape[3], inv_n, int(backward), int(accumulate), current_stream()))
     return loss
 
 

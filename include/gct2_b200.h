@@ -52,9 +52,10 @@ int gct2_noise_images(const float* x, const float* eps, const int32_t* t_int, fl
 int gct2_conv4s2_c3_fprop(const float* x, const float* w, const float* bias, uint16_t* y, int ldy, int B, int H,
                           int W, int Cout, void* stream);
 /* Backward of the above w.r.t. kernel and bias (Keras train_step, implicit at train.py:516):
- * dz bf16 [B,H/2,W/2,Cout] (already ReLU-masked); dw fp32 [4,4,3,Cout]; db fp32 [Cout]. Overwrites dw, db. */
+ * dz bf16 [B,H/2,W/2,Cout] (already ReLU-masked); dw fp32 [4,4,3,Cout]; db fp32 [Cout] or NULL (bias gradient taken
+ * elsewhere).  accumulate == 0: dw, db are overwritten; != 0: added into (the caller zeroed them). */
 int gct2_conv4s2_c3_wgrad(const float* x, const uint16_t* dz, int lddz, float* dw, float* db, int B, int H, int W,
-                          int Cout, void* stream);
+                          int Cout, int accumulate, void* stream);
 
 /* train.py:158-169 DownShuffle forward (Cin % 64 == 0): y = relu(conv2d(x, w[4,4,Cin,Cout], s=2, SAME) + b).
  * x bf16 [B,H,W,Cin] stride ldx; y bf16 [B,H/2,W/2,Cout] stride ldy. tcgen05 implicit GEMM (strided form).
@@ -88,15 +89,20 @@ int gct2_convT4s2_wgrad(const uint16_t* x, int ldx, const uint16_t* dy, int lddy
 
 /* BiasAddGrad of every conv layer: db[c] = sum over rows of dz[row*ld + c]; dz bf16, db fp32 (overwritten). */
 int gct2_bias_grad(const uint16_t* dz, int ld, long long rows, int C, float* db, void* stream);
+/* The same for n <= 16 tensors in ONE launch (all conv layers of a step).  dz, ld, rows, C, db are HOST arrays of
+ * length n holding device pointers / sizes.  accumulate as above. */
+int gct2_bias_grad_multi(int n, const uint16_t* const* dz, const int* ld, const long long* rows, const int* C,
+                         float* const* db, int accumulate, void* stream);
 
 /* train.py:198-202 Dense(3) on concat([up0_out(64), noised(3)]) fused with train.py:262-272 MSE and their
  * backward.  u0 bf16 [pixels,64] stride ldu; noised, x fp32 [pixels,3]; wd fp32 [67,3]; bd fp32 [3].
  * pred (nullable) fp32 [pixels,3]; loss: one fp32, overwritten with sum((pred-x)^2)*inv_n; inv_n = 1/(global
  * element count) so data-parallel ranks produce partial means.  When backward != 0 also writes
- * du0 = (u0>0) * (dpred . wd^T) (bf16, stride lddu), dwd fp32 [67,3], dbd fp32 [3], dpred = 2(pred-x)*inv_n. */
+ * du0 = (u0>0) * (dpred . wd^T) (bf16, stride lddu), dwd fp32 [Cu+3,3], dbd fp32 [3], dpred = 2(pred-x)*inv_n.
+ * Cu is 64 or 128.  accumulate == 0: loss, dwd, dbd are overwritten; != 0: added into (the caller zeroed them). */
 int gct2_dense_mse(const uint16_t* u0, int ldu, const float* noised, const float* x, const float* wd,
                    const float* bd, float* pred, float* loss, uint16_t* du0, int lddu, float* dwd, float* dbd,
-                   long long pixels, int Cu, float inv_n, int backward, void* stream);
+                   long long pixels, int Cu, float inv_n, int backward, int accumulate, void* stream);
 
 /* train.py:50-65,75 -- tf.keras.optimizers.Adam(WarmUp(base_lr, warmup_steps)), Keras formula (epsilon added to
  * the un-bias-corrected sqrt(v)).  All n parameters live in flat fp32 buffers; w_bf16 receives the shadow copy.

@@ -69,7 +69,7 @@ def step_parity(cfg: O.Config, batch: int, seed: int = 0) -> Dict[str, Dict[str,
         for name, ref in rt.items():
             if name == "dpred" or name not in got_taps:
                 continue
-            if name.startswith("d"):
+            if name.startswith(("ddown", "dup")):
                 ref = ref * (rt[name[1:]] > 0)
             out.setdefault("act/" + name, {})[flavour] = rel(got_taps[name], ref)
         for name, ref in rg.items():
@@ -84,7 +84,7 @@ def check_step_parity(cfg: O.Config, batch: int, seed: int = 0):
     for name, errs in res.items():
         if name == "loss":
             lim = {"emu": 1e-3, "f32": 1e-3}
-        elif name.startswith("act/d"):
+        elif name.startswith(("act/ddown", "act/dup")):
             lim = {"emu": 1.5e-2, "f32": tol_f32_grad(cfg, name[5:])}
         elif name.startswith("act/"):
             lim = {"emu": 1e-2, "f32": 1e-2}

@@ -255,6 +255,29 @@ def check_bias_grad(B=2, H=16, C=256, seed=9):
     return _metrics(f"bias_grad B{B} H{H} C{C}", db, dz.float().sum((0, 1, 2)), F32_TOL)
 
 
+def check_bias_grad_multi(seed=12):
+    """All layers' BiasAddGrad in one launch, ragged shapes, accumulate mode on top of a pre-filled output."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(seed)
+    dev = _dev()
+    shapes = [(2, 16, 16, 64), (1, 4, 4, 512), (3, 8, 8, 256), (1, 32, 32, 128), (2, 4, 4, 1024)]
+    dzs, dbs, refs = [], [], []
+    for i, sh in enumerate(shapes):
+        dz = _bf(_rand(sh, g))
+        _, v = _slice_buf(*sh, 64 * (i % 2), 64, dev)
+        v.copy_(dz)
+        dzs.append(v)
+        dbs.append(torch.full((sh[3],), 0.5, device=dev))
+        refs.append(dz.float().sum((0, 1, 2)) + 0.5)
+    plan = ops.BiasGradPlan(dzs, dbs)
+    ops.bias_grad_multi(plan, accumulate=True)
+    torch.cuda.synchronize()
+    ms = [_metrics(f"bias_grad_multi seg{i}", d, r, F32_TOL) for i, (d, r) in enumerate(zip(dbs, refs))]
+    worst = dict(max(ms, key=lambda m: m["err"]))
+    worst["name"] = f"bias_grad_multi 5 tensors (worst: {worst['name']})"
+    return worst
+
+
 def check_dense_mse(B=2, H=32, Cu=64, seed=10):
     ops = _ops()
     g = torch.Generator().manual_seed(seed)
@@ -346,7 +369,10 @@ EW_CASES = [
     (check_c3_wgrad, {}),
     (check_bias_grad, {}),
     (check_bias_grad, dict(B=1, H=8, C=1024)),
+    (check_bias_grad_multi, {}),
     (check_dense_mse, {}),
+    (check_dense_mse, dict(B=1, H=16, Cu=128)),
+    (check_dense_mse, dict(B=3, H=5, Cu=64)),
     (check_adam, {}),
 ]
 

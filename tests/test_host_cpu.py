@@ -28,15 +28,22 @@ def test_construction_recursion_matches_reference_shapes():
     assert cfg.up_filters == (64, 128, 256, 512, 512, 512)
     assert E.variable_specs(cfg) == O.variable_specs(O.DEFAULT)
     offsets, total = E.param_offsets(cfg)
-    assert total == 41_691_660
-    assert all(off % 8 == 0 for name, (off, _) in offsets.items() if name.endswith("kernel") and "dense" not in name)
+    assert sum(cnt for _, cnt in offsets.values()) == 41_691_660
+    assert 0 <= total - 41_691_660 < 64 and total % 4 == 0          # head-region padding only
+    assert all(off % 64 == 0 for name, (off, _) in offsets.items() if name.endswith("kernel") and name[:5] not in
+               ("dense", "down0"))
+    # no overlaps, and the head region holds exactly the atomically-accumulated variables
+    spans = sorted((off, off + cnt, name) for name, (off, cnt) in offsets.items())
+    assert all(spans[i][1] <= spans[i + 1][0] for i in range(len(spans) - 1))
+    small = E.small_region(cfg)
+    assert {n for n, (off, _) in offsets.items() if off < small} == set(E.small_names(cfg))
 
 
 def test_variable_specs_follow_formulas_for_the_widened_variant():
     cfg = E.NetConfig(size=512, pixel_size=256, max_size=1024, octaves=7)
     ocfg = O.Config(size=512, pixel_size=256, max_size=1024, octaves=7)
     assert E.variable_specs(cfg) == O.variable_specs(ocfg)
-    assert E.param_offsets(cfg)[1] == 217_078_796
+    assert sum(cnt for _, cnt in E.param_offsets(cfg)[0].values()) == 217_078_796
 
 
 def test_warmup_and_alpha_dash_match_oracle():
