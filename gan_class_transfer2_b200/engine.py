@@ -180,6 +180,8 @@ class UNetEngine:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.dp = dp
         self.use_graph = use_graph
+        self.overlap_wgrad = True
+        self._side = torch.cuda.Stream(device=self.device)
         self._graph = None
         self._graph_launches = 0
         dev, n, S, B = self.device, cfg.octaves, cfg.size, batch
@@ -304,24 +306,44 @@ class UNetEngine:
                       dbd=self.view(self.g, "dense/bias") if backward else None, accumulate=True)
 
     def _backward(self) -> None:
+        """dgrad chain on the current stream; the weight gradients (which nothing in backward depends on) on a side
+        stream, each released by an event as soon as its dz exists.  At batch 1 most layers cannot fill 148 SMs on
+        their own, so the two chains share the GPU."""
         cfg, n = self.cfg, self.cfg.octaves
-        for i in range(n):  # up0 .. up{n-1}
-            dz = self.gup_out(i)
-            ops.convT4s2_wgrad(self.up_in_buf(i), dz, self.view(self.g, f"up{i}/kernel"))
+        main = torch.cuda.current_stream()
+        side = self._side if self.overlap_wgrad else main
+
+        def on_side(fn):
+            if side is main:
+                fn()
+                return
+            side.wait_stream(main)  # dz of this layer is complete on the main stream
+            with torch.cuda.stream(side):
+                fn()
+
+        def up_w(i):
+            ops.convT4s2_wgrad(self.up_in_buf(i), self.gup_out(i), self.view(self.g, f"up{i}/kernel"))
             self._bucket_ready(f"up{i}/kernel")
-            mask = cfg.down_c(i) if i == n - 1 else cfg.up_c(i + 1)
-            ops.convT4s2_dgrad(dz, self.view(self.w16, f"up{i}/kernel"), self.gup_in_buf(i), self.up_in_buf(i), mask,
-                               self.ws)
-        for i in reversed(range(1, n)):  # down{n-1} .. down1
-            dz = self.gdown_out(i)
-            ops.conv4s2_wgrad(self.down_in(i), dz, self.view(self.g, f"down{i}/kernel"))
+
+        def down_w(i):
+            ops.conv4s2_wgrad(self.down_in(i), self.gdown_out(i), self.view(self.g, f"down{i}/kernel"))
             self._bucket_ready(f"down{i}/kernel")
+
+        for i in range(n):  # up0 .. up{n-1}
+            on_side(lambda: up_w(i))
+            mask = cfg.down_c(i) if i == n - 1 else cfg.up_c(i + 1)
+            ops.convT4s2_dgrad(self.gup_out(i), self.view(self.w16, f"up{i}/kernel"), self.gup_in_buf(i),
+                               self.up_in_buf(i), mask, self.ws)
+        for i in reversed(range(1, n)):  # down{n-1} .. down1
+            on_side(lambda: down_w(i))
             # total gradient of down_{i-1}'s output = skip-path part (already stored raw by up_{i-1}'s dgrad) + this
-            ops.conv4s2_dgrad(dz, self.view(self.w16, f"down{i}/kernel"), self.gcat[i][..., cfg.up_c(i):],
+            ops.conv4s2_dgrad(self.gdown_out(i), self.view(self.w16, f"down{i}/kernel"), self.gcat[i][..., cfg.up_c(i):],
                               self.down_in(i), True, self.ws)
         ops.conv4s2_c3_wgrad(self.noised, self.gdown_out(0), self.view(self.g, "down0/kernel"), None, accumulate=True)
         # every conv layer's BiasAddGrad in one launch: the pre-activation gradients all still sit in their buffers
         ops.bias_grad_multi(self._bias_plan, accumulate=True)
+        if side is not main:
+            main.wait_stream(side)
         self._bucket_ready("down0/kernel")
 
     def _zero_small_grads(self) -> None:
