@@ -267,8 +267,12 @@ def keras_adam_update(w, m, v, g, iteration: int, cfg: Config = DEFAULT):
     b1p = torch.tensor(cfg.beta1, dtype=torch.float32) ** t
     b2p = torch.tensor(cfg.beta2, dtype=torch.float32) ** t
     alpha = (torch.tensor(lr, dtype=torch.float32) * torch.sqrt(1 - b2p) / (1 - b1p)).item()
-    m.add_((g - m) * (1 - cfg.beta1))
-    v.add_((g * g - v) * (1 - cfg.beta2))
+    # ResourceApplyAdam receives beta1/beta2 as scalars of the variable dtype and forms (1 - beta) in that dtype:
+    # 1 - float32(0.999) = 0.00100004673, not 0.001 (4.7e-5 relative -- visible in v).
+    one_minus_b1 = float(torch.tensor(1.0, dtype=w.dtype) - torch.tensor(cfg.beta1, dtype=w.dtype))
+    one_minus_b2 = float(torch.tensor(1.0, dtype=w.dtype) - torch.tensor(cfg.beta2, dtype=w.dtype))
+    m.add_((g - m) * one_minus_b1)
+    v.add_((g * g - v) * one_minus_b2)
     w.sub_(alpha * m / (torch.sqrt(v) + cfg.epsilon))
     return alpha
 
