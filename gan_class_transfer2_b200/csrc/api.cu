@@ -108,12 +108,13 @@ int gct2_conv4s2_dgrad(const uint16_t* dy, int lddy, const uint16_t* w, uint16_t
 }
 
 int gct2_conv4s2_wgrad(const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, int B, int H, int W,
-                       int Cin, int Cout, void* stream) {
+                       int Cin, int Cout, float* ws, size_t ws_bytes, void* stream) {
   if (check_conv("gct2_conv4s2_wgrad", B, H / 2, W / 2, Cin, Cout)) return 1;
   ConvArgs a = blank(MODE_W, B, H / 2, W / 2);
   a.hi = CB(x); a.ldHi = ldx; a.Chi = Cin;
   a.lo = CB(dy); a.ldLo = lddy; a.Clo = Cout;
   a.dw = dw;
+  a.ws = ws; a.wsBytes = ws_bytes;
   return conv_launch(a, S(stream));
 }
 
@@ -146,12 +147,13 @@ int gct2_convT4s2_dgrad(const uint16_t* dy, int lddy, const uint16_t* w, uint16_
 }
 
 int gct2_convT4s2_wgrad(const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, int B, int H, int W,
-                        int Cin, int Cout, void* stream) {
+                        int Cin, int Cout, float* ws, size_t ws_bytes, void* stream) {
   if (check_conv("gct2_convT4s2_wgrad", B, H, W, Cin, Cout)) return 1;
   ConvArgs a = blank(MODE_W, B, H, W);
   a.hi = CB(dy); a.ldHi = lddy; a.Chi = Cout;
   a.lo = CB(x); a.ldLo = ldx; a.Clo = Cin;
   a.dw = dw;
+  a.ws = ws; a.wsBytes = ws_bytes;
   return conv_launch(a, S(stream));
 }
 

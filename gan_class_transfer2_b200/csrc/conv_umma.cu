@@ -128,19 +128,23 @@ static int map_w3(CUtensorMap* m, const __nv_bfloat16* p, int R, int Cc, int box
 }
 
 // ------------------------------------------------------------------------------------ split-K finish
-// ws fp32 [pixels][N] -> bf16 out with the real epilogue; re-zeroes ws for its next user.
-__global__ void splitk_finish_kernel(float* __restrict__ ws, int N, long long pixels, int epi,
-                                     __nv_bfloat16* __restrict__ out, int ldo, const float* __restrict__ bias,
-                                     const __nv_bfloat16* __restrict__ act, int ldact, int maskN, int addOld) {
+// ws fp32 [splits][pixels][N] -> bf16 out with the real epilogue.  Slabs are summed in split order (deterministic).
+__global__ void splitk_finish_kernel(const float* __restrict__ ws, long long splitStride, int splits, int N,
+                                     long long pixels, int epi, __nv_bfloat16* __restrict__ out, int ldo,
+                                     const float* __restrict__ bias, const __nv_bfloat16* __restrict__ act, int ldact,
+                                     int maskN, int addOld) {
   const int vecPerRow = N / 4;
   const long long total = pixels * vecPerRow;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long pix = i / vecPerRow;
     const int n = (int)(i % vecPerRow) * 4;
-    float4* wp = reinterpret_cast<float4*>(ws + pix * N + n);
-    float4 v = *wp;
-    *wp = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* wp = reinterpret_cast<const float4*>(ws + pix * N + n);
+    float4 v = __ldg(wp);
+    for (int sidx = 1; sidx < splits; ++sidx) {
+      const float4 u = __ldg(reinterpret_cast<const float4*>(ws + sidx * splitStride + pix * N + n));
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
     __nv_bfloat16* o = out + pix * ldo + n;
     if (epi == EPI_BIAS_RELU) {
       const float4 b = *reinterpret_cast<const float4*>(bias + n);
@@ -171,6 +175,20 @@ __global__ void splitk_finish_kernel(float* __restrict__ ws, int N, long long pi
   }
 }
 
+// dw[i] = sum over splits of slab[s][i] (weight-gradient split-K), fixed order.
+__global__ void wgrad_reduce_kernel(const float4* __restrict__ ws, long long splitStrideVec, int splits,
+                                    float4* __restrict__ dw, long long nvec) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 v = __ldg(ws + i);
+    for (int sidx = 1; sidx < splits; ++sidx) {
+      const float4 u = __ldg(ws + sidx * splitStrideVec + i);
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
+    dw[i] = v;
+  }
+}
+
 // ------------------------------------------------------------------------------------ heuristics
 static int stages_for(int BN) { return BN == 256 ? 4 : (BN == 128 ? 5 : 4); }
 static int occupancy_for(int BN) { return BN == 64 ? 2 : 1; }
@@ -181,7 +199,7 @@ struct Choice {
 };
 
 static Choice choose(int baseItemsPerN /* items excluding the N split */, int N, int kTotal, bool isW,
-                     int forceBN, int forceSplits) {
+                     int forceBN, int forceSplits, size_t slabBytes, size_t wsBytes) {
   Choice best{0, 1};
   double bestCost = 1e30;
   const int bns[3] = {256, 128, 64};
@@ -193,6 +211,7 @@ static Choice choose(int baseItemsPerN /* items excluding the N split */, int N,
     for (int splits = 1; splits <= 64; splits *= 2) {
       if (kTotal % splits) break;
       if (forceSplits && splits != forceSplits) continue;
+      if (splits > 1 && slabBytes * splits > wsBytes) break;  // partial slabs must fit the caller's workspace
       const int kIters = kTotal / splits;
       const long long items = (long long)baseItemsPerN * (N / BN) * splits;
       const long long rounds = (items + g_num_sms - 1) / g_num_sms;
@@ -268,7 +287,8 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     const int phases = a.mode == MODE_S ? 1 : 4;
     p.kcPer = Ck / 64;
     const int kTotal = taps * p.kcPer;
-    Choice c = choose(pixTiles * phases, N, kTotal, false, a.forceBN, a.forceSplits);
+    const size_t slab = (size_t)a.B * (a.mode == MODE_S ? 1 : 4) * a.Hlo * a.Wlo * N * sizeof(float);
+    Choice c = choose(pixTiles * phases, N, kTotal, false, a.forceBN, a.forceSplits, slab, a.ws ? a.wsBytes : 0);
     if (c.BN == 0) {
       set_error("conv: no tile shape for N=%d", N);
       return 1;
@@ -291,13 +311,9 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     p.addOld = a.addOld;
     p.epi = a.epi;
     if (c.splits > 1) {
-      const size_t need = (size_t)a.B * p.Hout * p.Wout * N * sizeof(float);
-      if (a.ws == nullptr || a.wsBytes < need) {
-        set_error("conv: split-K workspace too small (%zu < %zu bytes)", a.wsBytes, need);
-        return 1;
-      }
-      p.epi = EPI_WS_ATOMIC;
+      p.epi = EPI_WS_SLAB;
       p.ws = a.ws;
+      p.wsSplitStride = (long long)a.B * p.Hout * p.Wout * N;
     }
     if (a.mode == MODE_S) {
       p.ldG = a.ldHi;
@@ -317,7 +333,8 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
       return 1;
     }
     const int chunks = pixTiles;
-    Choice c = choose(16 * (Mch / 128), Nch, chunks, true, a.forceBN, a.forceSplits);
+    const size_t slab = (size_t)16 * a.Chi * a.Clo * sizeof(float);
+    Choice c = choose(16 * (Mch / 128), Nch, chunks, true, a.forceBN, a.forceSplits, slab, a.ws ? a.wsBytes : 0);
     if (c.BN == 0) {
       set_error("wgrad: no tile shape for N=%d", Nch);
       return 1;
@@ -342,12 +359,8 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     mapA = p.gIsA ? mg : mp;
     mapB = p.gIsA ? mp : mg;
     if (p.atomic) {
-      cudaError_t e = cudaMemsetAsync(a.dw, 0, (size_t)16 * a.Chi * a.Clo * sizeof(float), stream);
-      count_launch();
-      if (e != cudaSuccess) {
-        set_error("wgrad memset: %s", cudaGetErrorString(e));
-        return 1;
-      }
+      p.ws = a.ws;
+      p.wsSplitStride = (long long)16 * a.Chi * a.Clo;
     }
   }
 
@@ -376,11 +389,24 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     const long long total = pixels * (p.N / 4);
     int blocks = (int)((total + 255) / 256);
     if (blocks > g_num_sms * 8) blocks = g_num_sms * 8;
-    splitk_finish_kernel<<<blocks, 256, 0, stream>>>(a.ws, p.N, pixels, a.epi, a.out, a.ldo, a.bias, a.act, a.ldact,
-                                                     a.maskN, a.addOld);
+    splitk_finish_kernel<<<blocks, 256, 0, stream>>>(a.ws, p.wsSplitStride, p.splits, p.N, pixels, a.epi, a.out, a.ldo,
+                                                     a.bias, a.act, a.ldact, a.maskN, a.addOld);
     e = cudaGetLastError();
     if (e != cudaSuccess) {
       set_error("splitk_finish_kernel launch: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    count_launch();
+  }
+  if (a.mode == MODE_W && p.splits > 1) {
+    const long long nvec = (long long)4 * a.Chi * a.Clo;  // 16 taps * Chi * Clo / 4
+    int blocks = (int)((nvec + 255) / 256);
+    if (blocks > g_num_sms * 8) blocks = g_num_sms * 8;
+    wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(a.ws), p.wsSplitStride / 4, p.splits,
+                                                    reinterpret_cast<float4*>(a.dw), nvec);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      set_error("wgrad_reduce_kernel launch: %s", cudaGetErrorString(e));
       return 1;
     }
     count_launch();

@@ -23,7 +23,7 @@
 namespace gct2 {
 
 enum : int { MODE_S = 0, MODE_P = 1, MODE_W = 2 };
-enum : int { EPI_BIAS_RELU = 0, EPI_DGRAD = 1, EPI_WS_ATOMIC = 2, EPI_WGRAD = 3 };
+enum : int { EPI_BIAS_RELU = 0, EPI_DGRAD = 1, EPI_WS_SLAB = 2, EPI_WGRAD = 3 };
 
 struct ConvParams {
   int B, Hlo, Wlo;             // lo-res spatial extent (hi-res = 2x)
@@ -50,11 +50,12 @@ struct ConvParams {
   int ldact;
   int maskN;                   // EPI_DGRAD: columns [0,maskN) are ReLU-masked
   int addOld;                  // EPI_DGRAD: add the value already stored in out (skip-path gradient)
-  float* ws;                   // EPI_WS_ATOMIC: fp32 [outPixels][N]
+  float* ws;                   // EPI_WS_SLAB: fp32 [splits][outPixels][N]; EPI_WGRAD split-K: fp32 [splits][16*Chi*Clo]
+  long long wsSplitStride;     // elements between consecutive split slabs
   float* dw;                   // EPI_WGRAD: fp32 [16][...]
   long long tapStride;
   int rowStride, colStride;    // element strides of the (M-row, N-col) accumulator tile inside one tap
-  int atomic;                  // EPI_WGRAD: accumulate with red.add (split-K) instead of store
+  int atomic;                  // EPI_WGRAD: split-K -> each split stores its partial into its own slab of ws
 };
 
 struct WorkItem {
@@ -318,19 +319,21 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
               dst[g] = o;
             }
           }
-        } else if (p.epi == EPI_WS_ATOMIC) {
+        } else if (p.epi == EPI_WS_SLAB) {
+          // split-K partial: plain stores into this split's slab (no atomics: the finishing pass sums the slabs in a
+          // fixed order, so the step is bit-reproducible)
           if (valid) {
-            float* dst = p.ws + pix * p.N + n;
+            float4* dst = reinterpret_cast<float4*>(p.ws + (long long)w.split * p.wsSplitStride + pix * p.N + n);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) red_add_f32(dst + j, __uint_as_float(v[j]));
+            for (int g = 0; g < 8; ++g)
+              dst[g] = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
+                                   __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
           }
         } else {  // EPI_WGRAD: row = M-side channel, columns = N-side channels
-          float* base = p.dw + (long long)w.ph * p.tapStride + (long long)(w.mt * 128 + r) * p.rowStride +
+          float* base = (p.atomic ? p.ws + (long long)w.split * p.wsSplitStride : p.dw) +
+                        (long long)w.ph * p.tapStride + (long long)(w.mt * 128 + r) * p.rowStride +
                         (long long)n * p.colStride;
-          if (p.atomic) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) red_add_f32(base + (long long)j * p.colStride, __uint_as_float(v[j]));
-          } else if (p.colStride == 1) {
+          if (p.colStride == 1) {
             float4* d4 = reinterpret_cast<float4*>(base);
 #pragma unroll
             for (int g = 0; g < 8; ++g)

@@ -230,7 +230,9 @@ class UNetEngine:
         self.u0 = torch.zeros(B, S, S, cfg.up_c(0), **bf)
         self.gu0 = torch.zeros_like(self.u0)
         biggest = max([self.u0.numel(), self.bot.numel()] + [c.numel() for c in self.cat.values()])
-        self.ws = ops.Workspace(4 * biggest, dev)
+        # split-K scratch: one for the main stream (fprop / dgrad partial outputs), one for the side stream (wgrad)
+        self.ws = ops.Workspace(max(4 * 4 * biggest, 64 << 20), dev)
+        self.ws_w = ops.Workspace(64 << 20, dev)
         self.global_batch = B * (dp.world if dp else 1)
         self._buckets = self._make_buckets() if dp else []
         layers = [f"down{i}" for i in range(n)] + [f"up{i}" for i in range(n)]
@@ -322,11 +324,11 @@ class UNetEngine:
                 fn()
 
         def up_w(i):
-            ops.convT4s2_wgrad(self.up_in_buf(i), self.gup_out(i), self.view(self.g, f"up{i}/kernel"))
+            ops.convT4s2_wgrad(self.up_in_buf(i), self.gup_out(i), self.view(self.g, f"up{i}/kernel"), self.ws_w)
             self._bucket_ready(f"up{i}/kernel")
 
         def down_w(i):
-            ops.conv4s2_wgrad(self.down_in(i), self.gdown_out(i), self.view(self.g, f"down{i}/kernel"))
+            ops.conv4s2_wgrad(self.down_in(i), self.gdown_out(i), self.view(self.g, f"down{i}/kernel"), self.ws_w)
             self._bucket_ready(f"down{i}/kernel")
 
         for i in range(n):  # up0 .. up{n-1}

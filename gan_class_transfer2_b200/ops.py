@@ -10,6 +10,8 @@ Activation tensors are NHWC bf16; kernels are in the Keras layouts (Conv2D [4,4,
 """
 from __future__ import annotations
 
+from typing import Optional
+
 import torch
 
 from . import _lib
@@ -70,10 +72,10 @@ def _nhwc(t: torch.Tensor, dtype) -> int:
 
 
 class Workspace:
-    """fp32 split-K scratch shared by all conv calls on one stream (zero on entry, returned zeroed)."""
+    """fp32 split-K scratch shared by the conv calls of ONE stream (contents irrelevant between calls)."""
 
     def __init__(self, nbytes: int, device):
-        self.buf = torch.zeros(max(nbytes, 16) // 4, dtype=torch.float32, device=device)
+        self.buf = torch.empty(max(nbytes, 16) // 4, dtype=torch.float32, device=device)
 
     @property
     def nbytes(self) -> int:
@@ -131,11 +133,11 @@ def conv4s2_dgrad(dy, w, dx, act, add_old: bool, ws: Workspace):
 
 
 @_timed
-def conv4s2_wgrad(x, dy, dw):
+def conv4s2_wgrad(x, dy, dw, ws: Optional[Workspace] = None):
     lib = _lib_for(x)
     B, H, W, Cin = x.shape
     check(lib.gct2_conv4s2_wgrad(ptr(x), _nhwc(x, torch.bfloat16), ptr(dy), _nhwc(dy, torch.bfloat16), ptr(dw), B, H, W,
-                                 Cin, dy.shape[3], current_stream()))
+                                 Cin, dy.shape[3], ptr(ws.buf) if ws else 0, ws.nbytes if ws else 0, current_stream()))
     return dw
 
 
@@ -162,11 +164,11 @@ def convT4s2_dgrad(dy, w, dx, act, mask_channels: int, ws: Workspace):
 
 
 @_timed
-def convT4s2_wgrad(x, dy, dw):
+def convT4s2_wgrad(x, dy, dw, ws: Optional[Workspace] = None):
     lib = _lib_for(x)
     B, H, W, Cin = x.shape
     check(lib.gct2_convT4s2_wgrad(ptr(x), _nhwc(x, torch.bfloat16), ptr(dy), _nhwc(dy, torch.bfloat16), ptr(dw), B, H, W,
-                                  Cin, dy.shape[3], current_stream()))
+                                  Cin, dy.shape[3], ptr(ws.buf) if ws else 0, ws.nbytes if ws else 0, current_stream()))
     return dw
 
 

@@ -59,7 +59,9 @@ int gct2_conv4s2_c3_wgrad(const float* x, const uint16_t* dz, int lddz, float* d
 
 /* train.py:158-169 DownShuffle forward (Cin % 64 == 0): y = relu(conv2d(x, w[4,4,Cin,Cout], s=2, SAME) + b).
  * x bf16 [B,H,W,Cin] stride ldx; y bf16 [B,H/2,W/2,Cout] stride ldy. tcgen05 implicit GEMM (strided form).
- * ws: fp32 split-K workspace of >= B*(H/2)*(W/2)*Cout floats, zero on entry, returned zeroed. */
+ * ws: fp32 split-K scratch (contents irrelevant on entry and exit).  Split-K is used only when `splits` partial
+ * outputs (splits * B*(H/2)*(W/2)*Cout floats) fit in ws_bytes; partials are summed in a fixed order, so results are
+ * bit-reproducible.  ws may be NULL (no split-K).  The same holds for every ws argument below. */
 int gct2_conv4s2_fprop(const uint16_t* x, int ldx, const uint16_t* w, const float* bias, uint16_t* y, int ldy,
                        int B, int H, int W, int Cin, int Cout, float* ws, size_t ws_bytes, void* stream);
 /* Backward-data of DownShuffle: dx[b,iy,ix,ci] (+)= sum dy[b,oy,ox,co]*w[ky,kx,ci,co], then ReLU-masked by the
@@ -68,9 +70,10 @@ int gct2_conv4s2_fprop(const uint16_t* x, int ldx, const uint16_t* w, const floa
 int gct2_conv4s2_dgrad(const uint16_t* dy, int lddy, const uint16_t* w, uint16_t* dx, int lddx,
                        const uint16_t* act, int ldact, int add_old, int B, int H, int W, int Cin, int Cout,
                        float* ws, size_t ws_bytes, void* stream);
-/* Backward-filter of DownShuffle: dw[ky,kx,ci,co] = sum x[b,2oy-1+ky,2ox-1+kx,ci]*dy[b,oy,ox,co]; fp32, overwritten. */
+/* Backward-filter of DownShuffle: dw[ky,kx,ci,co] = sum x[b,2oy-1+ky,2ox-1+kx,ci]*dy[b,oy,ox,co]; fp32, overwritten.
+ * ws: split-K scratch for splits * 16*Cin*Cout floats (must not be shared with a concurrently running call). */
 int gct2_conv4s2_wgrad(const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, int B, int H, int W,
-                       int Cin, int Cout, void* stream);
+                       int Cin, int Cout, float* ws, size_t ws_bytes, void* stream);
 
 /* train.py:145-156 UpShuffle forward: y = relu(conv2d_transpose(x, w[4,4,Cout,Cin], s=2, SAME) + b).
  * x bf16 [B,H,W,Cin] stride ldx; y bf16 [B,2H,2W,Cout] stride ldy (phase form). ws >= B*2H*2W*Cout floats. */
@@ -85,7 +88,7 @@ int gct2_convT4s2_dgrad(const uint16_t* dy, int lddy, const uint16_t* w, uint16_
                         float* ws, size_t ws_bytes, void* stream);
 /* Backward-filter of UpShuffle: dw[ky,kx,co,ci] = sum dy[b,2iy-1+ky,2ix-1+kx,co]*x[b,iy,ix,ci]; fp32, overwritten. */
 int gct2_convT4s2_wgrad(const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, int B, int H, int W,
-                        int Cin, int Cout, void* stream);
+                        int Cin, int Cout, float* ws, size_t ws_bytes, void* stream);
 
 /* BiasAddGrad of every conv layer: db[c] = sum over rows of dz[row*ld + c]; dz bf16, db fp32 (overwritten). */
 int gct2_bias_grad(const uint16_t* dz, int ld, long long rows, int C, float* db, void* stream);

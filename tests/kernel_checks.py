@@ -69,7 +69,6 @@ def check_conv_fprop(B, H, Cin, Cout, seed=0, pad=64):
     torch.cuda.synchronize()
     m = _metrics(f"conv4s2_fprop B{B} H{H} {Cin}->{Cout}", yv, ref, BF16_TOL)
     m["pad_intact"] = bool((yfull[..., Cout:] == 7.0).all().item()) if pad else True
-    m["ws_zero"] = bool((ws.buf == 0).all().item())
     return m
 
 
@@ -99,7 +98,6 @@ def check_conv_dgrad(B, H, Cin, Cout, add_old=True, seed=1, pad=64):
     torch.cuda.synchronize()
     m = _metrics(f"conv4s2_dgrad B{B} H{H} {Cin}<-{Cout} add{int(add_old)}", dxv, ref, BF16_TOL)
     m["pad_intact"] = bool((dxfull[..., :pad] == 7.0).all().item()) if pad else True
-    m["ws_zero"] = bool((ws.buf == 0).all().item())
     return m
 
 
@@ -118,7 +116,7 @@ def check_conv_wgrad(B, H, Cin, Cout, seed=2, pad=64):
     _, dyv = _slice_buf(B, H // 2, H // 2, Cout, 0, pad, dev)
     dyv.copy_(dy)
     dw = torch.full((4, 4, Cin, Cout), 3.0, dtype=torch.float32, device=dev)
-    ops.conv4s2_wgrad(xv, dyv, dw)
+    ops.conv4s2_wgrad(xv, dyv, dw, ops.Workspace(64 << 20, dev))
     torch.cuda.synchronize()
     return _metrics(f"conv4s2_wgrad B{B} H{H} {Cin}x{Cout}", dw, ref, F32_TOL)
 
@@ -140,7 +138,6 @@ def check_convT_fprop(B, H, Cin, Cout, seed=3, pad=64):
     torch.cuda.synchronize()
     m = _metrics(f"convT4s2_fprop B{B} H{H} {Cin}->{Cout}", yv, ref, BF16_TOL)
     m["pad_intact"] = bool((yfull[..., Cout:] == 7.0).all().item()) if pad else True
-    m["ws_zero"] = bool((ws.buf == 0).all().item())
     return m
 
 
@@ -168,7 +165,6 @@ def check_convT_dgrad(B, H, Cin, Cout, mask_channels=None, seed=4, pad=64):
     torch.cuda.synchronize()
     m = _metrics(f"convT4s2_dgrad B{B} H{H} {Cin}<-{Cout} mask{mask_channels}", dxv, ref, BF16_TOL)
     m["pad_intact"] = bool((dxfull[..., Cin:] == 7.0).all().item()) if pad else True
-    m["ws_zero"] = bool((ws.buf == 0).all().item())
     return m
 
 
@@ -187,7 +183,7 @@ def check_convT_wgrad(B, H, Cin, Cout, seed=5, pad=64):
     _, dyv = _slice_buf(B, 2 * H, 2 * H, Cout, 0, pad, dev)
     dyv.copy_(dy)
     dw = torch.full((4, 4, Cout, Cin), 3.0, dtype=torch.float32, device=dev)
-    ops.convT4s2_wgrad(xv, dyv, dw)
+    ops.convT4s2_wgrad(xv, dyv, dw, ops.Workspace(64 << 20, dev))
     torch.cuda.synchronize()
     return _metrics(f"convT4s2_wgrad B{B} H{H} {Cout}x{Cin}", dw, ref, F32_TOL)
 
@@ -377,5 +373,40 @@ EW_CASES = [
 ]
 
 
+def forced(fn, BN=0, splits=0, **kw):
+    """Runs a conv check with the tile width / split-K factor pinned (test hook gct2_debug_set keys 3, 4) so that
+    every template instantiation and the split-K finishing passes are exercised regardless of the heuristics."""
+    from gan_class_transfer2_b200 import _lib
+    lib = _lib.init(0)
+    lib.gct2_debug_set(3, BN)
+    lib.gct2_debug_set(4, splits)
+    try:
+        m = fn(**kw)
+    finally:
+        lib.gct2_debug_set(3, 0)
+        lib.gct2_debug_set(4, 0)
+    m["name"] += f" [BN={BN or 'auto'} splits={splits or 'auto'}]"
+    return m
+
+
+FORCED_CASES = [
+    (check_conv_fprop, dict(B=2, H=16, Cin=128, Cout=256), dict(BN=64, splits=1)),
+    (check_conv_fprop, dict(B=2, H=16, Cin=128, Cout=256), dict(BN=128, splits=4)),
+    (check_conv_fprop, dict(B=2, H=16, Cin=128, Cout=256), dict(BN=256, splits=16)),
+    (check_convT_fprop, dict(B=2, H=8, Cin=128, Cout=256), dict(BN=64, splits=2)),
+    (check_convT_fprop, dict(B=2, H=8, Cin=128, Cout=256), dict(BN=128, splits=1)),
+    (check_convT_fprop, dict(B=2, H=8, Cin=128, Cout=256), dict(BN=256, splits=8)),
+    (check_conv_dgrad, dict(B=2, H=16, Cin=256, Cout=128, add_old=True), dict(BN=256, splits=4)),
+    (check_conv_dgrad, dict(B=2, H=16, Cin=256, Cout=128, add_old=True), dict(BN=128, splits=1)),
+    (check_convT_dgrad, dict(B=2, H=8, Cin=256, Cout=128), dict(BN=256, splits=2)),
+    (check_convT_dgrad, dict(B=2, H=8, Cin=256, Cout=128), dict(BN=64, splits=32)),
+    (check_conv_wgrad, dict(B=4, H=32, Cin=128, Cout=256), dict(BN=64, splits=8)),
+    (check_conv_wgrad, dict(B=4, H=32, Cin=128, Cout=256), dict(BN=128, splits=1)),
+    (check_conv_wgrad, dict(B=4, H=32, Cin=128, Cout=256), dict(BN=256, splits=2)),
+    (check_convT_wgrad, dict(B=4, H=16, Cin=256, Cout=64), dict(BN=64, splits=4)),
+    (check_convT_wgrad, dict(B=4, H=16, Cin=256, Cout=128), dict(BN=256, splits=16)),
+]
+
+
 def passed(m) -> bool:
-    return m["err"] <= m["tol"] and m.get("pad_intact", True) and m.get("ws_zero", True)
+    return m["err"] <= m["tol"] and m.get("pad_intact", True)

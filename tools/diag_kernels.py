@@ -19,6 +19,8 @@ def groups():
     out = {}
     for fn, kw in K.CONV_CASES + K.EW_CASES:
         out.setdefault(fn.__name__, []).append((fn, kw))
+    for fn, kw, force in K.FORCED_CASES:
+        out.setdefault("forced_" + fn.__name__, []).append((lambda fn=fn, force=force, **k: K.forced(fn, **force, **k), kw))
     return out
 
 
