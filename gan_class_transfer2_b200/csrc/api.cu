@@ -180,6 +180,15 @@ int gct2_adam_keras(float* w, float* m, float* v, const float* g, uint16_t* w_bf
                     grad_scale, S(stream));
 }
 
+int gct2_adam_prepare(long long* iterations, float* hyper, float base_lr, int warmup_steps, float beta1, float beta2,
+                      void* stream) {
+  return adam_prepare(iterations, hyper, base_lr, warmup_steps, beta1, beta2, S(stream));
+}
+int gct2_adam_apply(float* w, float* m, float* v, const float* g, uint16_t* w_bf16, long long n, const float* hyper,
+                    float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  return adam_apply(w, m, v, g, MB(w_bf16), n, hyper, beta1, beta2, eps, grad_scale, S(stream));
+}
+
 int gct2_cast_bf16(const float* src, uint16_t* dst, long long n, void* stream) {
   return cast_bf16(src, MB(dst), n, S(stream));
 }

@@ -506,16 +506,22 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ w, float
   }
 }
 
-int adam_keras(float* w, float* m, float* v, const float* g, __nv_bfloat16* w_bf16, long long n,
-               long long* iterations, float* hyper, float base_lr, int warmup_steps, float beta1, float beta2,
-               float eps, float grad_scale, cudaStream_t st) {
-  if (n % 4) {
-    set_error("adam_keras: parameter count must be a multiple of 4 (pad the flat buffer), got %lld", n);
-    return 1;
-  }
+int adam_prepare(long long* iterations, float* hyper, float base_lr, int warmup_steps, float beta1, float beta2,
+                 cudaStream_t st) {
   adam_prepare_kernel<<<1, 1, 0, st>>>(iterations, hyper, base_lr, warmup_steps, beta1, beta2);
   GCT2_CHECK_LAUNCH("adam_prepare_kernel");
+  return 0;
+}
+
+int adam_apply(float* w, float* m, float* v, const float* g, __nv_bfloat16* w_bf16, long long n, const float* hyper,
+               float beta1, float beta2, float eps, float grad_scale, cudaStream_t st) {
+  if (n % 4 || (reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v) |
+                reinterpret_cast<uintptr_t>(g)) % 16 || reinterpret_cast<uintptr_t>(w_bf16) % 8) {
+    set_error("adam: ranges must start on 16-byte boundaries and hold a multiple of 4 elements (n=%lld)", n);
+    return 1;
+  }
   const long long nvec = n / 4;
+  if (nvec == 0) return 0;
   long long blocks = (nvec + 255) / 256;
   if (blocks > g_ew_sms * 8) blocks = g_ew_sms * 8;
   adam_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<float4*>(w), reinterpret_cast<float4*>(m),
@@ -524,6 +530,13 @@ int adam_keras(float* w, float* m, float* v, const float* g, __nv_bfloat16* w_bf
                                            grad_scale);
   GCT2_CHECK_LAUNCH("adam_kernel");
   return 0;
+}
+
+int adam_keras(float* w, float* m, float* v, const float* g, __nv_bfloat16* w_bf16, long long n,
+               long long* iterations, float* hyper, float base_lr, int warmup_steps, float beta1, float beta2,
+               float eps, float grad_scale, cudaStream_t st) {
+  if (adam_prepare(iterations, hyper, base_lr, warmup_steps, beta1, beta2, st)) return 1;
+  return adam_apply(w, m, v, g, w_bf16, n, hyper, beta1, beta2, eps, grad_scale, st);
 }
 
 // ------------------------------------------------------------------------------------ fp32 -> bf16 shadow

@@ -21,6 +21,10 @@ int bias_grad(const __nv_bfloat16* dz, int ld, long long rows, int C, float* db,
 int adam_keras(float* w, float* m, float* v, const float* g, __nv_bfloat16* w_bf16, long long n,
                long long* iterations, float* hyper, float base_lr, int warmup_steps, float beta1, float beta2,
                float eps, float grad_scale, cudaStream_t st);
+int adam_prepare(long long* iterations, float* hyper, float base_lr, int warmup_steps, float beta1, float beta2,
+                 cudaStream_t st);
+int adam_apply(float* w, float* m, float* v, const float* g, __nv_bfloat16* w_bf16, long long n, const float* hyper,
+               float beta1, float beta2, float eps, float grad_scale, cudaStream_t st);
 int cast_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t st);
 
 }  // namespace gct2

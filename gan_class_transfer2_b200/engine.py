@@ -182,6 +182,7 @@ class UNetEngine:
         self.use_graph = use_graph
         self.overlap_wgrad = True
         self._side = torch.cuda.Stream(device=self.device)
+        self._side_adam = torch.cuda.Stream(device=self.device)
         self._graph = None
         self._graph_launches = 0
         dev, n, S, B = self.device, cfg.octaves, cfg.size, batch
@@ -234,7 +235,8 @@ class UNetEngine:
         self.ws = ops.Workspace(max(4 * 4 * biggest, 64 << 20), dev)
         self.ws_w = ops.Workspace(64 << 20, dev)
         self.global_batch = B * (dp.world if dp else 1)
-        self._buckets = self._make_buckets() if dp else []
+        # gradient buckets: all-reduce granularity (data parallel) and the granularity at which Adam chases backward
+        self._buckets = grad_buckets(cfg, dp.bucket_bytes if dp else (24 << 20))
         layers = [f"down{i}" for i in range(n)] + [f"up{i}" for i in range(n)]
         self._bias_plan = ops.BiasGradPlan([self.gdown_out(i) for i in range(n)] + [self.gup_out(i) for i in range(n)],
                                            [self.view(self.g, f"{l}/bias") for l in layers])
@@ -307,91 +309,97 @@ class UNetEngine:
                       du0=self.gu0 if backward else None, dwd=self.view(self.g, "dense/kernel") if backward else None,
                       dbd=self.view(self.g, "dense/bias") if backward else None, accumulate=True)
 
-    def _backward(self) -> None:
-        """dgrad chain on the current stream; the weight gradients (which nothing in backward depends on) on a side
-        stream, each released by an event as soon as its dz exists.  At batch 1 most layers cannot fill 148 SMs on
-        their own, so the two chains share the GPU."""
+    def _backward(self, apply_adam: bool) -> None:
+        """Three chains that share the GPU (at batch 1 no layer fills 148 SMs on its own):
+          main stream  the dgrad chain (the only true dependency chain of backward), then down0's wgrad + bias grads;
+          side_w       the 12 tensor-core weight gradients, each released as soon as its dz exists, and -- data
+                       parallel -- the NCCL all-reduce of every gradient bucket the moment its last wgrad is enqueued;
+          side_a       Keras-Adam on each bucket as soon as the bucket is complete AND the dgrad that still reads the
+                       bucket's bf16 weights has been enqueued (HBM-bound, overlaps the L2/tensor-bound dgrad chain).
+        Everything rejoins the main stream before the step ends, so the whole step captures into one CUDA graph."""
         cfg, n = self.cfg, self.cfg.octaves
         main = torch.cuda.current_stream()
-        side = self._side if self.overlap_wgrad else main
+        sw = self._side if self.overlap_wgrad else main
+        sa = self._side_adam if self.overlap_wgrad else main
+        dp = self.dp if (self.dp and self.dp.world > 1) else None
+        pending = []
 
         def on_side(fn):
-            if side is main:
+            if sw is main:
                 fn()
                 return
-            side.wait_stream(main)  # dz of this layer is complete on the main stream
-            with torch.cuda.stream(side):
+            sw.wait_stream(main)  # dz of this layer is complete on the main stream
+            with torch.cuda.stream(sw):
                 fn()
 
-        def up_w(i):
-            ops.convT4s2_wgrad(self.up_in_buf(i), self.gup_out(i), self.view(self.g, f"up{i}/kernel"), self.ws_w)
-            self._bucket_ready(f"up{i}/kernel")
-
-        def down_w(i):
-            ops.conv4s2_wgrad(self.down_in(i), self.gdown_out(i), self.view(self.g, f"down{i}/kernel"), self.ws_w)
-            self._bucket_ready(f"down{i}/kernel")
+        def bucket_done(trigger: str):
+            """Called once the dgrad reading `trigger`'s weights is on the main stream."""
+            for start, end, name in self._buckets:
+                if name != trigger:
+                    continue
+                work = None
+                if dp:
+                    if sw is not main and trigger == "down0/kernel":
+                        sw.wait_stream(main)  # the small region is produced on the main stream
+                    with torch.cuda.stream(sw):
+                        work = dp.dist.all_reduce(self.g[start:end], group=dp.group, async_op=True)
+                if not apply_adam:
+                    if work is not None:
+                        pending.append(work)
+                    continue
+                if sa is not main:
+                    sa.wait_stream(main)
+                    sa.wait_stream(sw)
+                with torch.cuda.stream(sa):
+                    if work is not None:
+                        work.wait()
+                    ops.adam_apply(self.w[start:end], self.m[start:end], self.v[start:end], self.g[start:end],
+                                   self.w16[start:end], self.hyper, cfg.beta1, cfg.beta2, cfg.epsilon, 1.0)
 
         for i in range(n):  # up0 .. up{n-1}
-            on_side(lambda: up_w(i))
+            on_side(lambda: ops.convT4s2_wgrad(self.up_in_buf(i), self.gup_out(i), self.view(self.g, f"up{i}/kernel"),
+                                               self.ws_w))
             mask = cfg.down_c(i) if i == n - 1 else cfg.up_c(i + 1)
             ops.convT4s2_dgrad(self.gup_out(i), self.view(self.w16, f"up{i}/kernel"), self.gup_in_buf(i),
                                self.up_in_buf(i), mask, self.ws)
+            bucket_done(f"up{i}/kernel")
         for i in reversed(range(1, n)):  # down{n-1} .. down1
-            on_side(lambda: down_w(i))
+            on_side(lambda: ops.conv4s2_wgrad(self.down_in(i), self.gdown_out(i), self.view(self.g, f"down{i}/kernel"),
+                                              self.ws_w))
             # total gradient of down_{i-1}'s output = skip-path part (already stored raw by up_{i-1}'s dgrad) + this
             ops.conv4s2_dgrad(self.gdown_out(i), self.view(self.w16, f"down{i}/kernel"), self.gcat[i][..., cfg.up_c(i):],
                               self.down_in(i), True, self.ws)
+            bucket_done(f"down{i}/kernel")
         ops.conv4s2_c3_wgrad(self.noised, self.gdown_out(0), self.view(self.g, "down0/kernel"), None, accumulate=True)
         # every conv layer's BiasAddGrad in one launch: the pre-activation gradients all still sit in their buffers
         ops.bias_grad_multi(self._bias_plan, accumulate=True)
-        if side is not main:
-            main.wait_stream(side)
-        self._bucket_ready("down0/kernel")
+        bucket_done("down0/kernel")
+        if sw is not main:
+            main.wait_stream(sw)
+            main.wait_stream(sa)
+        for work in pending:
+            work.wait()
+        if dp:
+            dp.dist.all_reduce(self.loss, group=dp.group)
 
     def _zero_small_grads(self) -> None:
         """One memset for everything the HBM-bound kernels accumulate atomically (param_offsets' head region) + loss."""
         self.g[:self.small].zero_()
         self.loss.zero_()
 
-    # ------------------------------------------------------------------------------------------ data parallel
-    def _make_buckets(self) -> List[Tuple[int, int, str]]:
-        return grad_buckets(self.cfg, self.dp.bucket_bytes)
-
-    def _bucket_ready(self, name: str) -> None:
-        if not self.dp or self.dp.world == 1:
-            return
-        for start, end, trigger in self._buckets:
-            if trigger == name:
-                if self.dp.overlap:
-                    self._pending.append(self.dp.dist.all_reduce(self.g[start:end], group=self.dp.group, async_op=True))
-                else:
-                    self._deferred.append((start, end))
-
-    def _finish_allreduce(self) -> None:
-        if not self.dp or self.dp.world == 1:
-            return
-        for start, end in self._deferred:
-            self.dp.dist.all_reduce(self.g[start:end], group=self.dp.group)
-        for work in self._pending:
-            work.wait()
-        self.dp.dist.all_reduce(self.loss, group=self.dp.group)
-
     # ------------------------------------------------------------------------------------------ public steps
     def _step_body(self, draw: bool) -> None:
         cfg = self.cfg
-        self._pending, self._deferred = [], []
         inv_n = 1.0 / (self.global_batch * cfg.size * cfg.size * 3)
         if draw:
             # train.py:224-227: t_int ~ U{1..steps}, epsilon ~ N(0,1), drawn on the device every step
             self.t_int.random_(1, cfg.steps + 1)
             self.eps.normal_()
         self._zero_small_grads()
+        ops.adam_prepare(self.iterations, self.hyper, cfg.base_lr, cfg.warm_up, cfg.beta1, cfg.beta2)
         ops.noise_images(self.x, self.eps, self.t_int, self.noised, cfg.steps)
         self._forward(want_pred=False, backward=True, inv_n=inv_n)
-        self._backward()
-        self._finish_allreduce()
-        ops.adam_keras(self.w, self.m, self.v, self.g, self.w16, self.iterations, self.hyper, cfg.base_lr, cfg.warm_up,
-                       cfg.beta1, cfg.beta2, cfg.epsilon, 1.0)
+        self._backward(apply_adam=True)
 
     def set_batch(self, x: torch.Tensor, t_int: Optional[torch.Tensor] = None,
                   eps: Optional[torch.Tensor] = None) -> None:
@@ -458,13 +466,11 @@ class UNetEngine:
     def loss_and_grads(self, x, t_int, eps) -> torch.Tensor:
         """Forward + backward without the optimiser update (parity tests compare self.g with the oracle)."""
         self.set_batch(x, t_int, eps)
-        self._pending, self._deferred = [], []
         inv_n = 1.0 / (self.global_batch * self.cfg.size * self.cfg.size * 3)
         self._zero_small_grads()
         ops.noise_images(self.x, self.eps, self.t_int, self.noised, self.cfg.steps)
         self._forward(want_pred=True, backward=True, inv_n=inv_n)
-        self._backward()
-        self._finish_allreduce()
+        self._backward(apply_adam=False)
         return self.loss
 
     def denoise(self, noised: torch.Tensor) -> torch.Tensor:

@@ -231,6 +231,22 @@ def adam_keras(w, m, v, g, w_bf16, iterations, hyper, base_lr: float, warmup_ste
 
 
 @_timed
+def adam_prepare(iterations, hyper, base_lr: float, warmup_steps: int, beta1: float = 0.9, beta2: float = 0.999):
+    """Once per step: alpha = lr(step)*sqrt(1-b2^t)/(1-b1^t) into hyper[0], then iterations += 1."""
+    lib = _lib_for(hyper)
+    check(lib.gct2_adam_prepare(ptr(iterations), ptr(hyper), base_lr, warmup_steps, beta1, beta2, current_stream()))
+
+
+@_timed
+def adam_apply(w, m, v, g, w_bf16, hyper, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-7,
+               grad_scale: float = 1.0):
+    """Keras-Adam update of one contiguous range of the flat buffers (views starting on 16-byte boundaries)."""
+    lib = _lib_for(w)
+    check(lib.gct2_adam_apply(ptr(w), ptr(m), ptr(v), ptr(g), ptr(w_bf16), w.numel(), ptr(hyper), beta1, beta2, eps,
+                              grad_scale, current_stream()))
+
+
+@_timed
 def cast_bf16(src, dst):
     lib = _lib_for(src)
     check(lib.gct2_cast_bf16(ptr(src), ptr(dst), src.numel(), current_stream()))

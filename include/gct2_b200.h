@@ -114,6 +114,13 @@ int gct2_dense_mse(const uint16_t* u0, int ldu, const float* noised, const float
 int gct2_adam_keras(float* w, float* m, float* v, const float* g, uint16_t* w_bf16, long long n,
                     long long* iterations, float* hyper, float base_lr, int warmup_steps, float beta1, float beta2,
                     float eps, float grad_scale, void* stream);
+/* The same optimiser in two parts, so that the update of a contiguous range of variables can start as soon as that
+ * range's gradients are complete (overlapping the rest of backward): gct2_adam_prepare once per step (computes
+ * alpha/lr of this step into hyper[0..1], increments *iterations), then gct2_adam_apply per range. */
+int gct2_adam_prepare(long long* iterations, float* hyper, float base_lr, int warmup_steps, float beta1, float beta2,
+                      void* stream);
+int gct2_adam_apply(float* w, float* m, float* v, const float* g, uint16_t* w_bf16, long long n, const float* hyper,
+                    float beta1, float beta2, float eps, float grad_scale, void* stream);
 /* fp32 -> bf16 (round to nearest even); builds the first shadow copy of the weights. */
 int gct2_cast_bf16(const float* src, uint16_t* dst, long long n, void* stream);
 
