@@ -157,6 +157,7 @@ def instrumented_step(eng, torch, ops):
     out = {}
     for name, s, e in rec:
         out.setdefault(name, []).append(s.elapsed_time(e) * 1e3)
+    out["__sequence__"] = [(name, round(s.elapsed_time(e) * 1e3, 1)) for name, s, e in rec]
     return out
 
 
@@ -170,6 +171,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--dump-ops", default="", help="write the instrumented step's per-launch (op, us) list here")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -260,6 +262,10 @@ def main():
     # ---- roofline of the dominant kernel family, measured live
     pk = peaks()
     prof = instrumented_step(eng, torch, ops)
+    sequence = prof.pop("__sequence__")
+    if args.dump_ops and rank == 0:
+        with open(args.dump_ops, "w") as f:
+            json.dump(sequence, f)
     conv_ops = [k for k in prof if k.startswith("conv") and "c3" not in k]
     conv_us = sum(sum(prof[k]) for k in conv_ops)
     conv_launches = sum(len(prof[k]) for k in conv_ops)

@@ -11,7 +11,7 @@
 using namespace gct2;
 
 namespace {
-int g_force_bn = 0, g_force_splits = 0, g_sms = 0;
+int g_force_bn = 0, g_force_splits = 0, g_force_cm = 0, g_force_cn = 0, g_sms = 0;
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline const __nv_bfloat16* CB(const uint16_t* p) { return reinterpret_cast<const __nv_bfloat16*>(p); }
 inline __nv_bfloat16* MB(uint16_t* p) { return reinterpret_cast<__nv_bfloat16*>(p); }
@@ -37,6 +37,8 @@ ConvArgs blank(int mode, int B, int Hlo, int Wlo) {
   a.Wlo = Wlo;
   a.forceBN = g_force_bn;
   a.forceSplits = g_force_splits;
+  a.forceCm = g_force_cm;
+  a.forceCn = g_force_cn;
   return a;
 }
 }  // namespace
@@ -65,6 +67,10 @@ void gct2_debug_set(int key, int value) {
     g_force_bn = value;
   else if (key == 4)
     g_force_splits = value;
+  else if (key == 5)
+    g_force_cm = value;
+  else if (key == 6)
+    g_force_cn = value;
   else
     conv_set_debug(key, value);
 }

@@ -29,6 +29,7 @@ struct ConvArgs {
   float* dw;                     // fp32 [16][Chi][Clo]
   // tuning overrides (0 = heuristic)
   int forceBN, forceSplits;
+  int forceCm, forceCn;          // cluster shape override (0 = heuristic, 1 = no cluster along that axis)
 };
 
 int conv_init(int device);                       // once per process/device

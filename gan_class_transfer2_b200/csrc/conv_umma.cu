@@ -49,6 +49,8 @@ static int set_attr() {
   return 0;
 }
 
+static void query_all_clusters();
+
 int conv_init(int device) {
   if (g_inited) return 0;
   cudaError_t e = cudaSetDevice(device);
@@ -80,6 +82,7 @@ int conv_init(int device) {
   rc |= set_attr<MODE_P, 64>() | set_attr<MODE_P, 128>() | set_attr<MODE_P, 256>();
   rc |= set_attr<MODE_W, 64>() | set_attr<MODE_W, 128>() | set_attr<MODE_W, 256>();
   if (rc) return 1;
+  query_all_clusters();
   g_inited = true;
   return 0;
 }
@@ -195,48 +198,133 @@ static int occupancy_for(int BN) { return BN == 64 ? 2 : 1; }
 static size_t smem_for(int BN) { return (size_t)stages_for(BN) * (16384 + BN * 128) + 1024 + 256; }
 
 struct Choice {
-  int BN, splits;
+  int BN, splits, cm, cn;
 };
 
-static Choice choose(int baseItemsPerN /* items excluding the N split */, int N, int kTotal, bool isW,
-                     int forceBN, int forceSplits, size_t slabBytes, size_t wsBytes) {
-  Choice best{0, 1};
+// Maximum number of co-resident clusters of `csize` CTAs for each tile width (queried once; 0 = unsupported).
+static int g_max_clusters[3][3][9];  // [mode][BN index][cluster size]
+static int bn_index(int BN) { return BN == 64 ? 0 : (BN == 128 ? 1 : 2); }
+
+template <int MODE, int BN>
+static void query_clusters() {
+  for (int cs = 2; cs <= 8; cs *= 2) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(cs * 32);
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = smem_for(BN);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, conv_umma_kernel<MODE, BN>, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      n = 0;
+    }
+    g_max_clusters[MODE][bn_index(BN)][cs] = n;
+  }
+}
+
+static void query_all_clusters() {
+  query_clusters<MODE_S, 64>(); query_clusters<MODE_S, 128>(); query_clusters<MODE_S, 256>();
+  query_clusters<MODE_P, 64>(); query_clusters<MODE_P, 128>(); query_clusters<MODE_P, 256>();
+}
+
+// Cost model (SM cycles) for one launch; constants fitted to the r1a ncu capture (profiles/):
+//   * a 128 x BN x 64 k-step needs 2*BN tensor-pipe cycles;
+//   * operand bytes come from L2 at ~4800 B/clk for the whole chip (9.5 TB/s), shared by the active CTAs; a tile that is
+//     multicast to c CTAs is read from L2 once per c CTAs;
+//   * every item pays a pipeline fill (L2/DRAM latency) and an epilogue; split-K adds the partial stores and the
+//     finishing pass.
+static Choice choose(int mode, int mTiles, int phases, int N, int kTotal, long long outElems, int forceBN,
+                     int forceSplits, int forceCm, int forceCn, size_t slabBytes, size_t wsBytes) {
+  Choice best{0, 1, 1, 1};
   double bestCost = 1e30;
   const int bns[3] = {256, 128, 64};
+  const int cms[4] = {1, 2, 4, 8}, cns[3] = {1, 2, 4};
+  const bool isW = mode == MODE_W;
   for (int bi = 0; bi < 3; ++bi) {
     const int BN = bns[bi];
     if (N % BN) continue;
     if (forceBN && BN != forceBN) continue;
-    const double tk = BN == 256 ? 1024.0 : (BN == 128 ? 700.0 : 520.0);
+    const int nTiles = N / BN;
     for (int splits = 1; splits <= 64; splits *= 2) {
       if (kTotal % splits) break;
       if (forceSplits && splits != forceSplits) continue;
       if (splits > 1 && slabBytes * splits > wsBytes) break;  // partial slabs must fit the caller's workspace
       const int kIters = kTotal / splits;
-      const long long items = (long long)baseItemsPerN * (N / BN) * splits;
-      const long long rounds = (items + g_num_sms - 1) / g_num_sms;
-      double epi = 6.0 * BN;
-      if (splits > 1) epi = isW ? 12.0 * BN : 14.0 * BN;
-      double cost = rounds * (1800.0 + kIters * tk + epi);
-      if (splits > 1) cost += isW ? 2500.0 : 6000.0;  // memset / finishing pass
-      if (cost < bestCost) {
-        bestCost = cost;
-        best = Choice{BN, splits};
+      for (int a = 0; a < 4; ++a) {
+        for (int b = 0; b < 3; ++b) {
+          const int cm = cms[a], cn = cns[b], cs = cm * cn;
+          if (cs > 8 || mTiles % cm || nTiles % cn) continue;
+          if (isW && cs > 1) continue;
+          if (forceCm >= 1 && cm != forceCm) continue;
+          if (forceCn >= 1 && cn != forceCn) continue;
+          int maxCtas = g_num_sms * occupancy_for(BN);
+          if (cs > 1) {
+            const int mc = g_max_clusters[mode][bn_index(BN)][cs];
+            if (mc <= 0) continue;
+            maxCtas = mc * cs;
+          }
+          const long long items = (long long)mTiles * phases * (isW ? 16 : 1) * nTiles * splits;
+          const long long active = items < maxCtas ? items : maxCtas;
+          const long long rounds = (items + active - 1) / active;
+          const double bytes = 16384.0 / cn + BN * 128.0 / cm;  // L2 reads per CTA per k-step
+          double tk = 2.0 * BN;
+          const double l2 = bytes * (double)active / 4800.0;
+          if (l2 > tk) tk = l2;
+          const double ingest = (16384.0 + BN * 128.0) / 96.0;  // per-SM fill rate
+          if (ingest > tk) tk = ingest;
+          if (cs > 1) tk *= 1.06;
+          // TMEM is double-buffered and the producer runs ahead: only the first fill and the last epilogue of a CTA
+          // are exposed (plus whatever part of an epilogue outlasts the next main loop)
+          const double epi = (splits > 1 || isW) ? 700.0 + 5.0 * BN : 700.0 + 3.5 * BN;
+          const double main = kIters * tk;
+          double cost = 5000.0 + 2500.0 + rounds * main + epi + (rounds - 1) * (epi > main ? epi - main : 0.0);
+          if (splits > 1) cost += 6000.0 + (double)outElems * (4.0 * splits + 6.0) / 4800.0;
+          if (cost < bestCost) {
+            bestCost = cost;
+            best = Choice{BN, splits, cm, cn};
+          }
+        }
       }
     }
   }
   return best;
 }
 
+template <int MODE, int BN>
+static cudaError_t launch_one(int grid, int csize, size_t smem, cudaStream_t st, const CUtensorMap& a,
+                              const CUtensorMap& b, const ConvParams& p) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  cfg.attrs = at;
+  cfg.numAttrs = 0;
+  if (csize > 1) {
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = csize;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, conv_umma_kernel<MODE, BN>, a, b, p);
+}
+
 template <int MODE>
-static cudaError_t launch_bn(int BN, int grid, size_t smem, cudaStream_t st, const CUtensorMap& a,
+static cudaError_t launch_bn(int BN, int grid, int csize, size_t smem, cudaStream_t st, const CUtensorMap& a,
                              const CUtensorMap& b, const ConvParams& p) {
   switch (BN) {
-    case 64: conv_umma_kernel<MODE, 64><<<grid, 192, smem, st>>>(a, b, p); break;
-    case 128: conv_umma_kernel<MODE, 128><<<grid, 192, smem, st>>>(a, b, p); break;
-    default: conv_umma_kernel<MODE, 256><<<grid, 192, smem, st>>>(a, b, p); break;
+    case 64: return launch_one<MODE, 64>(grid, csize, smem, st, a, b, p);
+    case 128: return launch_one<MODE, 128>(grid, csize, smem, st, a, b, p);
+    default: return launch_one<MODE, 256>(grid, csize, smem, st, a, b, p);
   }
-  return cudaGetLastError();
 }
 
 static void pixel_tile(int rows, int H, int W, int* Wt, int* Ht, int* Nb) {
@@ -288,7 +376,8 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     p.kcPer = Ck / 64;
     const int kTotal = taps * p.kcPer;
     const size_t slab = (size_t)a.B * (a.mode == MODE_S ? 1 : 4) * a.Hlo * a.Wlo * N * sizeof(float);
-    Choice c = choose(pixTiles * phases, N, kTotal, false, a.forceBN, a.forceSplits, slab, a.ws ? a.wsBytes : 0);
+    Choice c = choose(a.mode, pixTiles, phases, N, kTotal, (long long)(slab / sizeof(float)), a.forceBN, a.forceSplits,
+                      a.forceCm, a.forceCn, slab, a.ws ? a.wsBytes : 0);
     if (c.BN == 0) {
       set_error("conv: no tile shape for N=%d", N);
       return 1;
@@ -299,6 +388,8 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     p.splits = c.splits;
     p.kIters = kTotal / c.splits;
     p.numItems = pixTiles * p.nTiles * phases * c.splits;
+    p.cm = c.cm;
+    p.cn = c.cn;
     p.N = N;
     p.Hout = a.mode == MODE_S ? a.Hlo : 2 * a.Hlo;
     p.Wout = a.mode == MODE_S ? a.Wlo : 2 * a.Wlo;
@@ -334,7 +425,8 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     }
     const int chunks = pixTiles;
     const size_t slab = (size_t)16 * a.Chi * a.Clo * sizeof(float);
-    Choice c = choose(16 * (Mch / 128), Nch, chunks, true, a.forceBN, a.forceSplits, slab, a.ws ? a.wsBytes : 0);
+    Choice c = choose(MODE_W, Mch / 128, 1, Nch, chunks, (long long)(slab / sizeof(float)), a.forceBN, a.forceSplits, 1, 1,
+                      slab, a.ws ? a.wsBytes : 0);
     if (c.BN == 0) {
       set_error("wgrad: no tile shape for N=%d", Nch);
       return 1;
@@ -345,6 +437,8 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     p.splits = c.splits;
     p.kIters = chunks / c.splits;
     p.numItems = 16 * p.mTiles * p.nTiles * c.splits;
+    p.cm = 1;
+    p.cn = 1;
     p.N = Nch;
     p.ldG = a.ldHi;
     p.epi = EPI_WGRAD;
@@ -366,19 +460,25 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
 
   p.stages = stages_for(BN);
   const size_t smem = smem_for(BN);
-  int grid = g_num_sms * occupancy_for(BN);
-  if (grid > p.numItems) grid = p.numItems;
+  const int csize = p.cm * p.cn;
+  p.numClusterItems = p.numItems / csize;
+  int maxCtas = g_num_sms * occupancy_for(BN);
+  if (csize > 1) maxCtas = g_max_clusters[a.mode][bn_index(BN)][csize] * csize;
+  int grid = p.numItems < maxCtas ? p.numItems : maxCtas;
+  grid -= grid % csize;
   if (g_verbose)
     fprintf(stderr,
-            "gct2 conv mode %d B %d lo %dx%d tile %dx%dx%d BN %d splits %d kIters %d items %d grid %d stages %d smem %zu\n",
-            a.mode, a.B, a.Hlo, a.Wlo, p.Nb, p.Ht, p.Wt, BN, p.splits, p.kIters, p.numItems, grid, p.stages, smem);
+            "gct2 conv mode %d B %d lo %dx%d tile %dx%dx%d BN %d splits %d cluster %dx%d kIters %d items %d grid %d stages %d "
+            "smem %zu\n",
+            a.mode, a.B, a.Hlo, a.Wlo, p.Nb, p.Ht, p.Wt, BN, p.splits, p.cm, p.cn, p.kIters, p.numItems, grid, p.stages,
+            smem);
   cudaError_t e;
   if (a.mode == MODE_S)
-    e = launch_bn<MODE_S>(BN, grid, smem, stream, mapA, mapB, p);
+    e = launch_bn<MODE_S>(BN, grid, csize, smem, stream, mapA, mapB, p);
   else if (a.mode == MODE_P)
-    e = launch_bn<MODE_P>(BN, grid, smem, stream, mapA, mapB, p);
+    e = launch_bn<MODE_P>(BN, grid, csize, smem, stream, mapA, mapB, p);
   else
-    e = launch_bn<MODE_W>(BN, grid, smem, stream, mapA, mapB, p);
+    e = launch_bn<MODE_W>(BN, grid, csize, smem, stream, mapA, mapB, p);
   if (e != cudaSuccess) {
     set_error("conv_umma_kernel launch: %s", cudaGetErrorString(e));
     return 1;

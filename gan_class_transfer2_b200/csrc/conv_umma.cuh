@@ -39,6 +39,9 @@ struct ConvParams {
   int ldG;                     // S / W(G operand): pixel stride (elements) of the gathered hi-res tensor
   int gIsA;                    // W: 1 when the gathered operand supplies the M side
   int mnLbo, mnSbo;            // MN-major descriptor offsets (bytes)
+  int cm, cn;                  // thread-block cluster = cm x cn CTAs: cm consecutive M tiles x cn consecutive N tiles of
+                               // one (phase, split); A tiles are TMA-multicast along cn, B tiles along cm
+  int numClusterItems;         // numItems / (cm*cn)
   // epilogue
   int epi;
   int N;                       // total output columns (S/P) ; W: N-side channels
@@ -62,21 +65,23 @@ struct WorkItem {
   int mt, nt, ph, split;       // ph: phase (P) or tap (W)
 };
 
+// item = index of a cluster item (a cm x cn block of tiles); (rm, rn) = this CTA's position inside its cluster.
 template <int MODE>
-__device__ __forceinline__ WorkItem decode_item(const ConvParams& p, int item) {
+__device__ __forceinline__ WorkItem decode_item(const ConvParams& p, int item, int rm, int rn) {
   WorkItem w;
-  w.mt = item % p.mTiles;
-  int r = item / p.mTiles;
+  const int mTilesC = p.mTiles / p.cm, nTilesC = p.nTiles / p.cn;
+  w.mt = (item % mTilesC) * p.cm + rm;
+  int r = item / mTilesC;
   if (MODE == MODE_W) {
-    w.nt = r % p.nTiles;
-    r /= p.nTiles;
+    w.nt = (r % nTilesC) * p.cn + rn;
+    r /= nTilesC;
     w.split = r % p.splits;
     w.ph = r / p.splits;
   } else {
     w.split = r % p.splits;
     r /= p.splits;
-    w.nt = r % p.nTiles;
-    w.ph = r / p.nTiles;
+    w.nt = (r % nTilesC) * p.cn + rn;
+    w.ph = r / nTilesC;
   }
   return w;
 }
@@ -107,6 +112,16 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  // cluster geometry (cm*cn == 1: plain launch, every mask below is unused)
+  const int csize = p.cm * p.cn;
+  const int crank = csize > 1 ? (int)cluster_ctarank() : 0;
+  const int rm = crank / p.cn, rn = crank % p.cn;
+  const int clusterId = blockIdx.x / csize, numClusters = gridDim.x / csize;
+  const uint16_t rowMask = (uint16_t)(((1u << p.cn) - 1u) << (rm * p.cn));   // CTAs sharing my M tile (A multicast)
+  uint16_t colMask = 0;                                                        // CTAs sharing my N tile (B multicast)
+  for (int j = 0; j < p.cm; ++j) colMask |= (uint16_t)(1u << (j * p.cn + rn));
+  const uint16_t peerMask = rowMask | colMask;
+
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
@@ -114,7 +129,8 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      // a slot is free once every CTA that multicasts into it ... i.e. every consumer of my row and column is done
+      mbar_init(&empty[i], p.cm + p.cn - 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
@@ -128,6 +144,7 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -137,8 +154,8 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int item = blockIdx.x; item < p.numItems; item += gridDim.x) {
-        const WorkItem w = decode_item<MODE>(p, item);
+      for (int item = clusterId; item < p.numClusterItems; item += numClusters) {
+        const WorkItem w = decode_item<MODE>(p, item, rm, rn);
         int x0 = 0, y0 = 0, b0 = 0;
         if (MODE != MODE_W) {
           x0 = (w.mt % p.tilesX) * p.Wt;
@@ -151,22 +168,47 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
           mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
+          // In a cluster the CTAs of a row take turns fetching the shared A tile (and those of a column the shared
+          // B tile) and multicast it; every CTA still expects the full stage on its own barrier.
+          const bool doA = p.cn == 1 || (it % p.cn) == rn;
+          const bool doB = p.cm == 1 || (it % p.cm) == rm;
           if (MODE == MODE_S) {
             const int tap = kit / p.kcPer, kc = kit % p.kcPer;
             const int ky = tap >> 2, kx = tap & 3;
             const int py = (ky + 1) & 1, px = (kx + 1) & 1;
             const int hy = ((ky + 1) >> 1) - 1, hx = ((kx + 1) >> 1) - 1;
-            tma_load_5d(sa, &mapA, &full[stage], px * p.ldG + kc * 64, x0 + hx, py, y0 + hy, b0);
+            if (doA) {
+              if (p.cn == 1)
+                tma_load_5d(sa, &mapA, &full[stage], px * p.ldG + kc * 64, x0 + hx, py, y0 + hy, b0);
+              else
+                tma_load_5d_mc(sa, &mapA, &full[stage], px * p.ldG + kc * 64, x0 + hx, py, y0 + hy, b0, rowMask);
+            }
+            if (doB) {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_3d(sb + j * BLK, &mapB, &full[stage], w.nt * BN + j * 64, kc * 64, tap);
+              for (int j = 0; j < BN / 64; ++j) {
+                if (p.cm == 1)
+                  tma_load_3d(sb + j * BLK, &mapB, &full[stage], w.nt * BN + j * 64, kc * 64, tap);
+                else
+                  tma_load_3d_mc(sb + j * BLK, &mapB, &full[stage], w.nt * BN + j * 64, kc * 64, tap, colMask);
+              }
+            }
           } else if (MODE == MODE_P) {
             const int t4 = kit / p.kcPer, kc = kit % p.kcPer;
             const int ty = t4 >> 1, tx = t4 & 1;
             const int py = w.ph >> 1, px = w.ph & 1;
             const int ky = (1 - py) + 2 * ty, kx = (1 - px) + 2 * tx;
-            tma_load_4d(sa, &mapA, &full[stage], kc * 64, x0 + (px - tx), y0 + (py - ty), b0);
-            tma_load_3d(sb, &mapB, &full[stage], kc * 64, w.nt * BN, ky * 4 + kx);
+            if (doA) {
+              if (p.cn == 1)
+                tma_load_4d(sa, &mapA, &full[stage], kc * 64, x0 + (px - tx), y0 + (py - ty), b0);
+              else
+                tma_load_4d_mc(sa, &mapA, &full[stage], kc * 64, x0 + (px - tx), y0 + (py - ty), b0, rowMask);
+            }
+            if (doB) {
+              if (p.cm == 1)
+                tma_load_3d(sb, &mapB, &full[stage], kc * 64, w.nt * BN, ky * 4 + kx);
+              else
+                tma_load_3d_mc(sb, &mapB, &full[stage], kc * 64, w.nt * BN, ky * 4 + kx, colMask);
+            }
           } else {
             // pixel chunk -> (batch tile, y tile, x tile)
             const int cx = (kit % p.tilesX) * p.Wt;
@@ -211,7 +253,7 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
       constexpr uint32_t a_kstep = A_MN ? 2048u : 32u;  // bytes per UMMA_K = 16 along K
       constexpr uint32_t b_kstep = B_MN ? 2048u : 32u;
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int item = blockIdx.x; item < p.numItems; item += gridDim.x) {
+      for (int item = clusterId; item < p.numClusterItems; item += numClusters) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -226,7 +268,12 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
             const uint64_t db = make_smem_desc(sb + k * b_kstep, b_lbo, b_sbo);
             umma_bf16(d_tmem, da, db, idesc, (it | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+          // frees the smem slot once these MMAs have read it -- in my CTA and, in a cluster, in every CTA that
+          // multicasts into my slot (my row and my column)
+          if (csize == 1)
+            umma_commit(&empty[stage]);
+          else
+            umma_commit_mc(&empty[stage], peerMask);
           if (++stage == (uint32_t)S) {
             stage = 0;
             phase ^= 1;
@@ -242,8 +289,8 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;
     uint32_t acc = 0, acc_phase = 0;
-    for (int item = blockIdx.x; item < p.numItems; item += gridDim.x) {
-      const WorkItem w = decode_item<MODE>(p, item);
+    for (int item = clusterId; item < p.numClusterItems; item += numClusters) {
+      const WorkItem w = decode_item<MODE>(p, item, rm, rn);
       const int n0 = w.nt * BN;
       // row -> output location
       bool valid = true;
@@ -355,6 +402,7 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();  // no CTA leaves while a peer may still signal its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);

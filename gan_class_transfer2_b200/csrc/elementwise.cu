@@ -375,39 +375,46 @@ struct BiasGradSegs {
   int n;
 };
 
-__global__ void __launch_bounds__(512) bias_grad_kernel(const __grid_constant__ BiasGradSegs sg) {
-  extern __shared__ float red[];  // [groups][C]
+__global__ void __launch_bounds__(256) bias_grad_kernel(const __grid_constant__ BiasGradSegs sg) {
+  extern __shared__ float red[];  // [rowsPerIter][C]
   int s = 0;
   while (s + 1 < sg.n && (int)blockIdx.x >= sg.firstBlock[s + 1]) ++s;
   const __nv_bfloat16* __restrict__ dz = sg.dz[s];
   const int C = sg.C[s], ld = sg.ld[s];
-  const int pairs = C / 2;
-  const int groups = blockDim.x / pairs;
-  const int pr = threadIdx.x % pairs, grp = threadIdx.x / pairs;
+  const int vecs = C / 8;                  // threads per row, 16 bytes each
+  const int rpi = blockDim.x / vecs;       // rows per iteration
+  const int v = threadIdx.x % vecs, rg = threadIdx.x / vecs;
   const long long r0 = (long long)(blockIdx.x - sg.firstBlock[s]) * sg.rowsPerBlock[s];
   long long r1 = r0 + sg.rowsPerBlock[s];
   if (r1 > sg.rows[s]) r1 = sg.rows[s];
-  if (grp < groups) {
-    float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
-    long long r = r0 + grp;
-    for (; r + groups < r1; r += 2 * groups) {  // two independent loads in flight
-      const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(dz + r * ld) + pr);
-      const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(dz + (r + groups) * ld) + pr);
-      s0 += bf16_lo(v); s1 += bf16_hi(v);
-      t0 += bf16_lo(u); t1 += bf16_hi(u);
+  if (rg < rpi) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    long long r = r0 + rg;
+    for (; r + 3LL * rpi < r1; r += 4LL * rpi) {  // four independent 16-byte loads in flight
+      uint4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) q[u] = __ldg(reinterpret_cast<const uint4*>(dz + (r + (long long)u * rpi) * ld) + v);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc[0] += bf16_lo(q[u].x); acc[1] += bf16_hi(q[u].x); acc[2] += bf16_lo(q[u].y); acc[3] += bf16_hi(q[u].y);
+        acc[4] += bf16_lo(q[u].z); acc[5] += bf16_hi(q[u].z); acc[6] += bf16_lo(q[u].w); acc[7] += bf16_hi(q[u].w);
+      }
     }
-    if (r < r1) {
-      const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(dz + r * ld) + pr);
-      s0 += bf16_lo(v); s1 += bf16_hi(v);
+    for (; r < r1; r += rpi) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(dz + r * ld) + v);
+      acc[0] += bf16_lo(q.x); acc[1] += bf16_hi(q.x); acc[2] += bf16_lo(q.y); acc[3] += bf16_hi(q.y);
+      acc[4] += bf16_lo(q.z); acc[5] += bf16_hi(q.z); acc[6] += bf16_lo(q.w); acc[7] += bf16_hi(q.w);
     }
-    red[grp * C + 2 * pr] = s0 + t0;
-    red[grp * C + 2 * pr + 1] = s1 + t1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[rg * C + v * 8 + j] = acc[j];
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float v = 0.f;
-    for (int g = 0; g < groups; ++g) v += red[g * C + c];
-    atomicAdd(sg.db[s] + c, v);
+    float t = 0.f;
+    for (int g = 0; g < rpi; ++g) t += red[g * C + c];
+    atomicAdd(sg.db[s] + c, t);
   }
 }
 
@@ -419,17 +426,23 @@ int bias_grad_multi(int n, const __nv_bfloat16* const* dz, const int* ld, const 
   }
   BiasGradSegs sg;
   sg.n = n;
-  int block = 0, maxC = 0;
-  long long totalRows = 0;
-  for (int i = 0; i < n; ++i) totalRows += rows[i];
-  const long long budget = (long long)g_ew_sms * 8;  // blocks over all segments
+  const int threads = 256;
+  int block = 0;
+  double totalBytes = 0;
   for (int i = 0; i < n; ++i) {
-    if (C[i] % 2 || C[i] > 1024 || C[i] < 2 || rows[i] < 1) {
-      set_error("bias_grad: unsupported tensor %d (C=%d rows=%lld)", i, C[i], rows[i]);
+    if (C[i] % 8 || C[i] > 2048 || C[i] < 8 || rows[i] < 1 || ld[i] % 8) {
+      set_error("bias_grad: unsupported tensor %d (C=%d ld=%d rows=%lld): channels and pixel stride must be multiples of 8",
+                i, C[i], ld[i], rows[i]);
       return 1;
     }
-    long long nb = (budget * rows[i] + totalRows - 1) / totalRows;
-    const long long cap = (rows[i] + 31) / 32;  // at least 32 rows per block
+    totalBytes += (double)rows[i] * C[i];
+  }
+  const double budget = (double)g_ew_sms * 8;  // blocks over all segments, shared in proportion to bytes
+  size_t smem = 0;
+  for (int i = 0; i < n; ++i) {
+    const int rpi = threads / (C[i] / 8);
+    long long nb = (long long)(budget * ((double)rows[i] * C[i]) / totalBytes + 0.999);
+    const long long cap = (rows[i] + 4LL * rpi - 1) / (4LL * rpi);  // at least one unrolled iteration per block
     if (nb > cap) nb = cap;
     if (nb < 1) nb = 1;
     const int rpb = (int)((rows[i] + nb - 1) / nb);
@@ -437,7 +450,8 @@ int bias_grad_multi(int n, const __nv_bfloat16* const* dz, const int* ld, const 
     sg.dz[i] = dz[i]; sg.db[i] = db[i]; sg.rows[i] = rows[i]; sg.ld[i] = ld[i]; sg.C[i] = C[i];
     sg.firstBlock[i] = block; sg.rowsPerBlock[i] = rpb;
     block += (int)nb;
-    if (C[i] > maxC) maxC = C[i];
+    const size_t need = (size_t)rpi * C[i] * sizeof(float);
+    if (need > smem) smem = need;
     if (zero) {
       cudaError_t e = cudaMemsetAsync(db[i], 0, (size_t)C[i] * sizeof(float), st);
       if (e != cudaSuccess) {
@@ -447,13 +461,6 @@ int bias_grad_multi(int n, const __nv_bfloat16* const* dz, const int* ld, const 
     }
   }
   sg.firstBlock[n] = block;
-  // 512 threads: pairs <= 512 always fits; groups = 512 / pairs (pairs need not divide 512: spare threads idle)
-  const int threads = 512;
-  size_t smem = 0;
-  for (int i = 0; i < n; ++i) {
-    const size_t need = (size_t)(threads / (C[i] / 2)) * C[i] * sizeof(float);
-    if (need > smem) smem = need;
-  }
   bias_grad_kernel<<<block, threads, smem, st>>>(sg);
   GCT2_CHECK_LAUNCH("bias_grad_kernel");
   return 0;

@@ -38,7 +38,8 @@ int gct2_num_sms(void);
 /* Number of kernels (and memset nodes of split-K paths) this library has enqueued so far in this process. */
 long long gct2_launch_count(void);
 /* Test hook (not part of the drop-in surface): key 0/1 override the MN-major UMMA descriptor LBO/SBO bytes,
- * key 2 = verbose plan logging, key 3 = force N tile, key 4 = force split-K. */
+ * key 2 = verbose plan logging, key 3 = force N tile, key 4 = force split-K, keys 5/6 = force the cluster shape
+ * (CTAs along M / along N; 0 = heuristic, 1 = none). */
 void gct2_debug_set(int key, int value);
 
 /* train.py:224-234 + :85-93 -- Trainer.call noising with alpha_dash:

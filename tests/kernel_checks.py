@@ -64,7 +64,7 @@ def check_conv_fprop(B, H, Cin, Cout, seed=0, pad=64):
     xfull, xv = _slice_buf(B, H, H, Cin, pad, 0, dev)
     xv.copy_(x)
     yfull, yv = _slice_buf(B, H // 2, H // 2, Cout, 0, pad, dev)
-    ws = ops.Workspace(4 * B * (H // 2) ** 2 * Cout, dev)
+    ws = ops.Workspace(64 << 20, dev)
     ops.conv4s2_fprop(xv, w.to(dev), b.to(dev), yv, ws)
     torch.cuda.synchronize()
     m = _metrics(f"conv4s2_fprop B{B} H{H} {Cin}->{Cout}", yv, ref, BF16_TOL)
@@ -93,7 +93,7 @@ def check_conv_dgrad(B, H, Cin, Cout, add_old=True, seed=1, pad=64):
     dxv.copy_(old)
     _, actv = _slice_buf(B, H, H, Cin, pad, 0, dev)
     actv.copy_(act)
-    ws = ops.Workspace(4 * B * H * H * Cin, dev)
+    ws = ops.Workspace(64 << 20, dev)
     ops.conv4s2_dgrad(dyv, w.to(dev), dxv, actv, add_old, ws)
     torch.cuda.synchronize()
     m = _metrics(f"conv4s2_dgrad B{B} H{H} {Cin}<-{Cout} add{int(add_old)}", dxv, ref, BF16_TOL)
@@ -133,7 +133,7 @@ def check_convT_fprop(B, H, Cin, Cout, seed=3, pad=64):
     _, xv = _slice_buf(B, H, H, Cin, 0, pad, dev)
     xv.copy_(x)
     yfull, yv = _slice_buf(B, 2 * H, 2 * H, Cout, 0, pad, dev)
-    ws = ops.Workspace(4 * B * 4 * H * H * Cout, dev)
+    ws = ops.Workspace(64 << 20, dev)
     ops.convT4s2_fprop(xv, w.to(dev), b.to(dev), yv, ws)
     torch.cuda.synchronize()
     m = _metrics(f"convT4s2_fprop B{B} H{H} {Cin}->{Cout}", yv, ref, BF16_TOL)
@@ -160,7 +160,7 @@ def check_convT_dgrad(B, H, Cin, Cout, mask_channels=None, seed=4, pad=64):
     dxfull, dxv = _slice_buf(B, H, H, Cin, 0, pad, dev)
     _, actv = _slice_buf(B, H, H, Cin, 0, pad, dev)
     actv.copy_(act)
-    ws = ops.Workspace(4 * B * H * H * Cin, dev)
+    ws = ops.Workspace(64 << 20, dev)
     ops.convT4s2_dgrad(dyv, w.to(dev), dxv, actv, mask_channels, ws)
     torch.cuda.synchronize()
     m = _metrics(f"convT4s2_dgrad B{B} H{H} {Cin}<-{Cout} mask{mask_channels}", dxv, ref, BF16_TOL)
@@ -373,19 +373,19 @@ EW_CASES = [
 ]
 
 
-def forced(fn, BN=0, splits=0, **kw):
+def forced(fn, BN=0, splits=0, cm=0, cn=0, **kw):
     """Runs a conv check with the tile width / split-K factor pinned (test hook gct2_debug_set keys 3, 4) so that
     every template instantiation and the split-K finishing passes are exercised regardless of the heuristics."""
     from gan_class_transfer2_b200 import _lib
     lib = _lib.init(0)
-    lib.gct2_debug_set(3, BN)
-    lib.gct2_debug_set(4, splits)
+    for key, val in ((3, BN), (4, splits), (5, cm), (6, cn)):
+        lib.gct2_debug_set(key, val)
     try:
         m = fn(**kw)
     finally:
-        lib.gct2_debug_set(3, 0)
-        lib.gct2_debug_set(4, 0)
-    m["name"] += f" [BN={BN or 'auto'} splits={splits or 'auto'}]"
+        for key in (3, 4, 5, 6):
+            lib.gct2_debug_set(key, 0)
+    m["name"] += f" [BN={BN or 'auto'} splits={splits or 'auto'} cluster={cm or 'auto'}x{cn or 'auto'}]"
     return m
 
 
@@ -405,6 +405,20 @@ FORCED_CASES = [
     (check_conv_wgrad, dict(B=4, H=32, Cin=128, Cout=256), dict(BN=256, splits=2)),
     (check_convT_wgrad, dict(B=4, H=16, Cin=256, Cout=64), dict(BN=64, splits=4)),
     (check_convT_wgrad, dict(B=4, H=16, Cin=256, Cout=128), dict(BN=256, splits=16)),
+    # thread-block clusters with TMA multicast (A along cn, B along cm); the last ones loop persistently
+    (check_conv_fprop, dict(B=2, H=32, Cin=128, Cout=256), dict(BN=64, splits=1, cm=1, cn=1)),
+    (check_conv_fprop, dict(B=2, H=32, Cin=128, Cout=256), dict(BN=64, splits=1, cm=2, cn=1)),
+    (check_conv_fprop, dict(B=2, H=32, Cin=128, Cout=256), dict(BN=64, splits=1, cm=1, cn=4)),
+    (check_conv_fprop, dict(B=2, H=32, Cin=128, Cout=256), dict(BN=64, splits=2, cm=2, cn=4)),
+    (check_conv_fprop, dict(B=2, H=32, Cin=128, Cout=256), dict(BN=128, splits=4, cm=4, cn=2)),
+    (check_convT_fprop, dict(B=2, H=16, Cin=128, Cout=128), dict(BN=64, splits=1, cm=4, cn=2)),
+    (check_convT_fprop, dict(B=2, H=16, Cin=128, Cout=128), dict(BN=128, splits=2, cm=4, cn=1)),
+    (check_conv_dgrad, dict(B=2, H=32, Cin=256, Cout=128, add_old=True), dict(BN=64, splits=1, cm=2, cn=4)),
+    (check_conv_dgrad, dict(B=2, H=32, Cin=256, Cout=128, add_old=False), dict(BN=256, splits=1, cm=8, cn=1)),
+    (check_convT_dgrad, dict(B=2, H=16, Cin=256, Cout=128), dict(BN=128, splits=1, cm=2, cn=2)),
+    (check_convT_dgrad, dict(B=2, H=16, Cin=256, Cout=128), dict(BN=64, splits=4, cm=1, cn=4)),
+    (check_conv_fprop, dict(B=16, H=64, Cin=64, Cout=128), dict(BN=64, splits=1, cm=4, cn=2)),
+    (check_convT_fprop, dict(B=16, H=16, Cin=64, Cout=64), dict(BN=64, splits=1, cm=8, cn=1)),
 ]
 
 

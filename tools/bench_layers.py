@@ -50,6 +50,7 @@ def time_fn(fn, iters, flush):
     for _ in range(iters):
         if flush is not None:
             flush.fill_(1.0)
+        torch.cuda._sleep(200000)  # keep the GPU busy while the host prepares the launch (tensor maps, ctypes)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         fn()
@@ -69,8 +70,15 @@ def main():
     ap.add_argument("--max-size", type=int, default=512)
     ap.add_argument("--octaves", type=int, default=6)
     ap.add_argument("--only", default="")
+    ap.add_argument("--debug", action="append", default=[], help="key=value for gct2_debug_set (2=verbose plans, "
+                    "3=BN, 4=splits, 5=cluster M, 6=cluster N)")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
+    from gan_class_transfer2_b200 import _lib
+    lib = _lib.init(0)
+    for d in a.debug:
+        k, v = (int(t) for t in d.split("="))
+        lib.gct2_debug_set(k, v)
     tf_peak, hbm_peak, src = peaks()
     flush = None if a.no_flush else torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
     B = a.batch
@@ -87,18 +95,18 @@ def main():
         w = (torch.randn(wshape, device=dev, generator=g) * 0.02).to(torch.bfloat16)
         dw = torch.empty(wshape, device=dev, dtype=torch.float32)
         bias = torch.zeros(Cout, device=dev)
-        ws = ops.Workspace(4 * max(x.numel(), y.numel()), dev)
+        ws = ops.Workspace(256 << 20, dev)
         lo = min(Hin, Hout)
         flops = 2.0 * B * lo * lo * 16 * Cin * Cout
         act_bytes = 2.0 * (x.numel() + y.numel())
         if kind == "down":
             passes = {"fprop": lambda: ops.conv4s2_fprop(x, w, bias, y, ws),
                       "dgrad": lambda: ops.conv4s2_dgrad(dy, w, dx, x, False, ws),
-                      "wgrad": lambda: ops.conv4s2_wgrad(x, dy, dw)}
+                      "wgrad": lambda: ops.conv4s2_wgrad(x, dy, dw, ws)}
         else:
             passes = {"fprop": lambda: ops.convT4s2_fprop(x, w, bias, y, ws),
                       "dgrad": lambda: ops.convT4s2_dgrad(dy, w, dx, x, Cin, ws),
-                      "wgrad": lambda: ops.convT4s2_wgrad(x, dy, dw)}
+                      "wgrad": lambda: ops.convT4s2_wgrad(x, dy, dw, ws)}
         for pname, fn in passes.items():
             us = time_fn(fn, a.iters, flush)
             algo_bytes = act_bytes + (4.0 if pname == "wgrad" else 2.0) * w.numel()
