@@ -1,0 +1,72 @@
+"""-m gpu, needs >= 2 GPUs (skipped otherwise): two ranks over NCCL, batch sharded, bucketed gradient all-reduce
+overlapped with backward, Adam chasing the buckets; checked against the oracle on the full batch."""
+import os
+import socket
+
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out, use_graph):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from gan_class_transfer2_b200.engine import DataParallel, NetConfig, UNetEngine, shard_batch
+        cfg = O.TINY
+        ncfg = NetConfig(size=cfg.size, pixel_size=cfg.pixel_size, max_size=cfg.max_size, octaves=cfg.octaves)
+        per = 2
+        eng = UNetEngine(ncfg, per, dp=DataParallel(bucket_bytes=1 << 20), use_graph=use_graph)
+        eng.load_weights(O.glorot_init(cfg, 0))
+        x, t, e = O.synthetic_batch(cfg, per * world, 1)
+        lo, hi = shard_batch(per * world, world, rank)
+        loss = eng.loss_and_grads(x[lo:hi].cuda(), t[lo:hi].cuda(), e[lo:hi].cuda()).clone()
+        grads = {k: v.cpu() for k, v in eng.grads().items()}
+        losses = []
+        for s in range(4):
+            xs, ts, es = O.synthetic_batch(cfg, per * world, 100 + s)
+            losses.append(float(eng.train_step(xs[lo:hi].cuda(), ts[lo:hi].cuda(), es[lo:hi].cuda())))
+        torch.cuda.synchronize()
+        w = eng.w.clone()
+        gathered = [torch.empty_like(w) for _ in range(world)]
+        dist.all_gather(gathered, w)
+        if rank == 0:
+            torch.save({"loss": float(loss), "grads": grads, "losses": losses,
+                        "replicas_equal": all(torch.equal(gathered[0], g) for g in gathered),
+                        "weights": {k: v.cpu() for k, v in eng.weights().items()}}, out)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("use_graph", [False, True], ids=["eager", "cuda_graph"])
+def test_two_gpu_data_parallel_step_matches_oracle(tmp_path, use_graph):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    from tests import engine_checks as E
+    out = str(tmp_path / "dp.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out, use_graph), nprocs=2, join=True)
+    got = torch.load(out)
+    cfg = O.TINY
+    weights = O.glorot_init(cfg, 0)
+    x, t, e = O.synthetic_batch(cfg, 4, 1)
+    loss, grads, _ = O.loss_and_grads(weights, x, t, e, cfg)
+    assert abs(got["loss"] - float(loss)) <= 1e-3 * float(loss)
+    for k, g in grads.items():
+        assert E.rel(got["grads"][k], g) <= E.tol_f32_grad(cfg, k), k
+    assert got["replicas_equal"], "ranks diverged: the summed gradients (and so the weights) must be bit-identical"
+    tr = O.OracleTrainer(cfg, weights=weights)
+    ref = [tr.train_step(*O.synthetic_batch(cfg, 4, 100 + s)) for s in range(4)]
+    assert max(abs(a - b) / b for a, b in zip(got["losses"], ref)) <= 1e-3, (got["losses"], ref)
