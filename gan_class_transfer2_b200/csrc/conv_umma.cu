@@ -195,7 +195,8 @@ __global__ void wgrad_reduce_kernel(const float4* __restrict__ ws, long long spl
 // ------------------------------------------------------------------------------------ heuristics
 static int stages_for(int BN) { return BN == 256 ? 4 : (BN == 128 ? 5 : 4); }
 static int occupancy_for(int BN) { return BN == 64 ? 2 : 1; }
-static size_t smem_for(int BN) { return (size_t)stages_for(BN) * (16384 + BN * 128) + 1024 + 256; }
+// pipeline stages + barriers (256 B) + 4 epilogue transpose tiles of 32 x 33 floats + 1 KB alignment slack
+static size_t smem_for(int BN) { return (size_t)stages_for(BN) * (16384 + BN * 128) + 1024 + 256 + 4 * 32 * 33 * 4; }
 
 struct Choice {
   int BN, splits, cm, cn;

@@ -14,7 +14,7 @@
 //           both operands MN-major (pixels are the contraction dim and are the slow smem axis).
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue
-// (TMEM -> registers -> global).  Accumulators are double-buffered in TMEM (2 x BN columns) so the
+// (TMEM -> registers -> shared-memory transpose -> line-coalesced global accesses).  Accumulators are double-buffered in TMEM (2 x BN columns) so the
 // epilogue of tile i overlaps the main loop of tile i+1.
 #pragma once
 #include <cuda_bf16.h>
@@ -286,109 +286,101 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // tcgen05.ld hands lane l the accumulator row (q*32 + l); writing global memory in that arrangement touches 32
+    // different lines per instruction.  Each 32x32 chunk is therefore transposed through a padded shared-memory
+    // tile so that 8 consecutive lanes own 32 consecutive columns of ONE row (4 rows per instruction): loads of the
+    // saved activation / skip gradient and all stores become line-coalesced.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int r = q * 32 + lane;
+    float* stg = reinterpret_cast<float*>(smem + S * STAGE_BYTES + 256) + q * (32 * 33);
+    const int sub = lane >> 3;       // row inside a group of 4
+    const int cg = (lane & 7) * 4;   // first of my 4 columns inside the 32-column chunk
     uint32_t acc = 0, acc_phase = 0;
     for (int item = clusterId; item < p.numClusterItems; item += numClusters) {
       const WorkItem w = decode_item<MODE>(p, item, rm, rn);
       const int n0 = w.nt * BN;
-      // row -> output location
-      bool valid = true;
-      long long pix = 0;
-      if (MODE != MODE_W) {
-        const int xl = r % p.Wt, yl = (r / p.Wt) % p.Ht, bl = r / (p.Wt * p.Ht);
-        const int x = (w.mt % p.tilesX) * p.Wt + xl;
-        const int y = ((w.mt / p.tilesX) % p.tilesY) * p.Ht + yl;
-        const int b = (w.mt / tilesXY) * p.Nb + bl;
-        valid = b < p.B;
-        int oy = y, ox = x;
-        if (MODE == MODE_P) {
-          oy = 2 * y + (w.ph >> 1);
-          ox = 2 * x + (w.ph & 1);
+      // my 8 rows after the transpose: r_k = q*32 + 4k + sub -> output location
+      long long pixk[8];
+      uint32_t validMask = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int r = q * 32 + 4 * k + sub;
+        if (MODE != MODE_W) {
+          const int xl = r % p.Wt, yl = (r / p.Wt) % p.Ht, bl = r / (p.Wt * p.Ht);
+          const int x = (w.mt % p.tilesX) * p.Wt + xl;
+          const int y = ((w.mt / p.tilesX) % p.tilesY) * p.Ht + yl;
+          const int b = (w.mt / tilesXY) * p.Nb + bl;
+          if (b < p.B) validMask |= 1u << k;
+          int oy = y, ox = x;
+          if (MODE == MODE_P) {
+            oy = 2 * y + (w.ph >> 1);
+            ox = 2 * x + (w.ph & 1);
+          }
+          pixk[k] = ((long long)b * p.Hout + oy) * p.Wout + ox;
+        } else {
+          pixk[k] = w.mt * 128 + r;  // M-side channel
+          validMask |= 1u << k;
         }
-        pix = ((long long)b * p.Hout + oy) * p.Wout + ox;
       }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+      const bool direct = (p.epi == EPI_WGRAD) && p.colStride != 1;  // rows already contiguous in memory
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32(t_row + c0, v);
         tmem_ld_wait();
-        const int n = n0 + c0;
-        if (p.epi == EPI_BIAS_RELU) {
-          if (valid) {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
-            uint4* dst = reinterpret_cast<uint4*>(p.out + pix * p.ldo + n);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const float4 b0 = __ldg(bp + 2 * g), b1 = __ldg(bp + 2 * g + 1);
-              uint4 o;
-              o.x = pack_bf16x2(fmaxf(__uint_as_float(v[8 * g + 0]) + b0.x, 0.f),
-                                fmaxf(__uint_as_float(v[8 * g + 1]) + b0.y, 0.f));
-              o.y = pack_bf16x2(fmaxf(__uint_as_float(v[8 * g + 2]) + b0.z, 0.f),
-                                fmaxf(__uint_as_float(v[8 * g + 3]) + b0.w, 0.f));
-              o.z = pack_bf16x2(fmaxf(__uint_as_float(v[8 * g + 4]) + b1.x, 0.f),
-                                fmaxf(__uint_as_float(v[8 * g + 5]) + b1.y, 0.f));
-              o.w = pack_bf16x2(fmaxf(__uint_as_float(v[8 * g + 6]) + b1.z, 0.f),
-                                fmaxf(__uint_as_float(v[8 * g + 7]) + b1.w, 0.f));
-              dst[g] = o;
-            }
-          }
-        } else if (p.epi == EPI_DGRAD) {
-          if (valid) {
-            uint4* dst = reinterpret_cast<uint4*>(p.out + pix * p.ldo + n);
-            const uint4* ap = reinterpret_cast<const uint4*>(p.act + pix * p.ldact + n);
-            const bool masked = n < p.maskN;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float f[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[8 * g + j]);
-              if (p.addOld) {
-                const uint4 o = dst[g];
-                f[0] += bf16_lo(o.x); f[1] += bf16_hi(o.x); f[2] += bf16_lo(o.y); f[3] += bf16_hi(o.y);
-                f[4] += bf16_lo(o.z); f[5] += bf16_hi(o.z); f[6] += bf16_lo(o.w); f[7] += bf16_hi(o.w);
-              }
-              if (masked) {
-                const uint4 a = __ldg(ap + g);
-                f[0] = bf16_lo(a.x) > 0.f ? f[0] : 0.f; f[1] = bf16_hi(a.x) > 0.f ? f[1] : 0.f;
-                f[2] = bf16_lo(a.y) > 0.f ? f[2] : 0.f; f[3] = bf16_hi(a.y) > 0.f ? f[3] : 0.f;
-                f[4] = bf16_lo(a.z) > 0.f ? f[4] : 0.f; f[5] = bf16_hi(a.z) > 0.f ? f[5] : 0.f;
-                f[6] = bf16_lo(a.w) > 0.f ? f[6] : 0.f; f[7] = bf16_hi(a.w) > 0.f ? f[7] : 0.f;
-              }
-              uint4 o;
-              o.x = pack_bf16x2(f[0], f[1]);
-              o.y = pack_bf16x2(f[2], f[3]);
-              o.z = pack_bf16x2(f[4], f[5]);
-              o.w = pack_bf16x2(f[6], f[7]);
-              dst[g] = o;
-            }
-          }
-        } else if (p.epi == EPI_WS_SLAB) {
-          // split-K partial: plain stores into this split's slab (no atomics: the finishing pass sums the slabs in a
-          // fixed order, so the step is bit-reproducible)
-          if (valid) {
-            float4* dst = reinterpret_cast<float4*>(p.ws + (long long)w.split * p.wsSplitStride + pix * p.N + n);
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-              dst[g] = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
-                                   __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
-          }
-        } else {  // EPI_WGRAD: row = M-side channel, columns = N-side channels
+        if (direct) {
+          // dw[tap][n][row]: lane = row -> each store instruction writes 32 consecutive floats
           float* base = (p.atomic ? p.ws + (long long)w.split * p.wsSplitStride : p.dw) +
-                        (long long)w.ph * p.tapStride + (long long)(w.mt * 128 + r) * p.rowStride +
-                        (long long)n * p.colStride;
-          if (p.colStride == 1) {
-            float4* d4 = reinterpret_cast<float4*>(base);
+                        (long long)w.ph * p.tapStride + (long long)(w.mt * 128 + q * 32 + lane) * p.rowStride +
+                        (long long)(n0 + c0) * p.colStride;
 #pragma unroll
-            for (int g = 0; g < 8; ++g)
-              d4[g] = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
-                                  __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
-          } else {
+          for (int j = 0; j < 32; ++j) base[(long long)j * p.colStride] = __uint_as_float(v[j]);
+          continue;
+        }
+        __syncwarp();  // the previous chunk has been read out of the staging tile
 #pragma unroll
-            for (int j = 0; j < 32; ++j) base[(long long)j * p.colStride] = __uint_as_float(v[j]);
+        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        const int n = n0 + c0 + cg;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.epi == EPI_BIAS_RELU) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float* sp = stg + (4 * k + sub) * 33 + cg;
+          float f0 = sp[0], f1 = sp[1], f2 = sp[2], f3 = sp[3];
+          if (!((validMask >> k) & 1u)) continue;
+          const long long pix = pixk[k];
+          if (p.epi == EPI_BIAS_RELU) {
+            uint2 o;
+            o.x = pack_bf16x2(fmaxf(f0 + bias4.x, 0.f), fmaxf(f1 + bias4.y, 0.f));
+            o.y = pack_bf16x2(fmaxf(f2 + bias4.z, 0.f), fmaxf(f3 + bias4.w, 0.f));
+            *reinterpret_cast<uint2*>(p.out + pix * p.ldo + n) = o;
+          } else if (p.epi == EPI_DGRAD) {
+            uint2* dst = reinterpret_cast<uint2*>(p.out + pix * p.ldo + n);
+            if (p.addOld) {
+              const uint2 o = *dst;
+              f0 += bf16_lo(o.x); f1 += bf16_hi(o.x); f2 += bf16_lo(o.y); f3 += bf16_hi(o.y);
+            }
+            if (n < p.maskN) {
+              const uint2 a = __ldg(reinterpret_cast<const uint2*>(p.act + pix * p.ldact + n));
+              f0 = bf16_lo(a.x) > 0.f ? f0 : 0.f; f1 = bf16_hi(a.x) > 0.f ? f1 : 0.f;
+              f2 = bf16_lo(a.y) > 0.f ? f2 : 0.f; f3 = bf16_hi(a.y) > 0.f ? f3 : 0.f;
+            }
+            uint2 o;
+            o.x = pack_bf16x2(f0, f1);
+            o.y = pack_bf16x2(f2, f3);
+            *dst = o;
+          } else if (p.epi == EPI_WS_SLAB) {
+            // split-K partial: plain stores into this split's slab (no atomics: the finishing pass sums the slabs
+            // in a fixed order, so the step is bit-reproducible)
+            *reinterpret_cast<float4*>(p.ws + (long long)w.split * p.wsSplitStride + pix * p.N + n) =
+                make_float4(f0, f1, f2, f3);
+          } else {  // EPI_WGRAD, rows = M-side channels with N contiguous (colStride == 1)
+            float* base = (p.atomic ? p.ws + (long long)w.split * p.wsSplitStride : p.dw) +
+                          (long long)w.ph * p.tapStride + pix * p.rowStride + n;
+            *reinterpret_cast<float4*>(base) = make_float4(f0, f1, f2, f3);
           }
         }
       }

@@ -414,7 +414,7 @@ FORCED_CASES = [
     (check_convT_fprop, dict(B=2, H=16, Cin=128, Cout=128), dict(BN=64, splits=1, cm=4, cn=2)),
     (check_convT_fprop, dict(B=2, H=16, Cin=128, Cout=128), dict(BN=128, splits=2, cm=4, cn=1)),
     (check_conv_dgrad, dict(B=2, H=32, Cin=256, Cout=128, add_old=True), dict(BN=64, splits=1, cm=2, cn=4)),
-    (check_conv_dgrad, dict(B=2, H=32, Cin=256, Cout=128, add_old=False), dict(BN=256, splits=1, cm=8, cn=1)),
+    (check_conv_dgrad, dict(B=4, H=32, Cin=256, Cout=128, add_old=False), dict(BN=256, splits=1, cm=8, cn=1)),
     (check_convT_dgrad, dict(B=2, H=16, Cin=256, Cout=128), dict(BN=128, splits=1, cm=2, cn=2)),
     (check_convT_dgrad, dict(B=2, H=16, Cin=256, Cout=128), dict(BN=64, splits=4, cm=1, cn=4)),
     (check_conv_fprop, dict(B=16, H=64, Cin=64, Cout=128), dict(BN=64, splits=1, cm=4, cn=2)),
