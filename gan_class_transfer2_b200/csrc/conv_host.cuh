@@ -34,6 +34,7 @@ struct ConvArgs {
 
 int conv_init(int device);                       // once per process/device
 int conv_launch(const ConvArgs& a, cudaStream_t stream);
+int debug_read_timeline(unsigned long long* host, int max_ctas);  // test hook, see gct2_debug_timeline
 void conv_set_debug(int key, int value);         // test hook: 0 = MN-major LBO, 1 = MN-major SBO, 2 = verbose
 const char* last_error();
 void count_launch(int n = 1);                   // kernels/memsets enqueued by this library (gct2_launch_count)

@@ -12,6 +12,7 @@ namespace gct2 {
 // ------------------------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
 const char* last_error() { return g_err; }
+int debug_read_timeline(unsigned long long* host, int max_ctas);
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -30,12 +31,30 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 static EncodeTiledFn g_encode = nullptr;
 static int g_num_sms = 148;
 static int g_mn_lbo = 8192, g_mn_sbo = 1024, g_verbose = 0;
+static unsigned long long* g_dbg = nullptr;  // test hook (key 7): phase timestamps of the most recent conv launch
+static int g_dbg_ctas = 0;
+constexpr int DBG_MAX_CTAS = 512;
 static bool g_inited = false;
+
+int debug_read_timeline(unsigned long long* host, int max_ctas) {
+  if (g_dbg == nullptr) return 0;
+  const int n = g_dbg_ctas < max_ctas ? g_dbg_ctas : max_ctas;
+  cudaDeviceSynchronize();
+  cudaMemcpy(host, g_dbg, (size_t)n * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  return n;
+}
 
 void conv_set_debug(int key, int value) {
   if (key == 0) g_mn_lbo = value;
   if (key == 1) g_mn_sbo = value;
   if (key == 2) g_verbose = value;
+  if (key == 7) {
+    if (value && g_dbg == nullptr) cudaMalloc(&g_dbg, (size_t)DBG_MAX_CTAS * 8 * sizeof(unsigned long long));
+    if (!value && g_dbg != nullptr) {
+      cudaFree(g_dbg);
+      g_dbg = nullptr;
+    }
+  }
 }
 
 template <int MODE, int BN>
@@ -473,6 +492,11 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
             "smem %zu\n",
             a.mode, a.B, a.Hlo, a.Wlo, p.Nb, p.Ht, p.Wt, BN, p.splits, p.cm, p.cn, p.kIters, p.numItems, grid, p.stages,
             smem);
+  if (g_dbg != nullptr && grid <= DBG_MAX_CTAS) {
+    cudaMemsetAsync(g_dbg, 0, (size_t)grid * 8 * sizeof(unsigned long long), stream);
+    p.dbg = g_dbg;
+    g_dbg_ctas = grid;
+  }
   cudaError_t e;
   if (a.mode == MODE_S)
     e = launch_bn<MODE_S>(BN, grid, csize, smem, stream, mapA, mapB, p);

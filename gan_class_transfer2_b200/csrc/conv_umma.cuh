@@ -42,6 +42,7 @@ struct ConvParams {
   int cm, cn;                  // thread-block cluster = cm x cn CTAs: cm consecutive M tiles x cn consecutive N tiles of
                                // one (phase, split); A tiles are TMA-multicast along cn, B tiles along cm
   int numClusterItems;         // numItems / (cm*cn)
+  unsigned long long* dbg;     // test hook: per-CTA phase timestamps (8 x u64 per CTA, %globaltimer ns) or nullptr
   // epilogue
   int epi;
   int N;                       // total output columns (S/P) ; W: N-side channels
@@ -86,6 +87,16 @@ __device__ __forceinline__ WorkItem decode_item(const ConvParams& p, int item, i
   return w;
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define GCT2_STAMP(slot)                                                              \
+  do {                                                                                \
+    if (p.dbg != nullptr) p.dbg[(size_t)blockIdx.x * 8 + (slot)] = globaltimer_ns();  \
+  } while (0)
+
 __device__ __forceinline__ void red_add_f32(float* addr, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
@@ -111,6 +122,7 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) GCT2_STAMP(0);  // kernel entry
 
   // cluster geometry (cm*cn == 1: plain launch, every mask below is unused)
   const int csize = p.cm * p.cn;
@@ -147,6 +159,7 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
   if (csize > 1) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) GCT2_STAMP(1);  // prologue done
 
   const int tilesXY = p.tilesX * p.tilesY;
 
@@ -259,6 +272,7 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int it = 0; it < p.kIters; ++it) {
           mbar_wait(&full[stage], phase);
+          if (it == 0 && item == clusterId) GCT2_STAMP(2);  // first operands have landed
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
@@ -280,6 +294,7 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
           }
         }
         umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        if (item == clusterId) GCT2_STAMP(3);  // all MMAs of the first item issued
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -322,12 +337,32 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
         }
       }
       mbar_wait(&tfull[acc], acc_phase);
+      if (item == clusterId && warp == 2 && lane == 0) GCT2_STAMP(4);  // first accumulator complete
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
       const bool direct = (p.epi == EPI_WGRAD) && p.colStride != 1;  // rows already contiguous in memory
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
+        const int n = n0 + c0 + cg;
+        // global operands of this chunk's epilogue are requested before the accumulator is read, so their latency
+        // hides behind the TMEM load and the transpose
+        uint2 actv[8], oldv[8];
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.epi == EPI_DGRAD) {
+          const bool masked = n < p.maskN;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            actv[k] = make_uint2(0x3f803f80u, 0x3f803f80u);  // bf16 1.0: "keep" when this column is not masked
+            oldv[k] = make_uint2(0u, 0u);
+            if ((validMask >> k) & 1u) {
+              if (masked) actv[k] = __ldg(reinterpret_cast<const uint2*>(p.act + pixk[k] * p.ldact + n));
+              if (p.addOld) oldv[k] = *reinterpret_cast<const uint2*>(p.out + pixk[k] * p.ldo + n);
+            }
+          }
+        } else if (p.epi == EPI_BIAS_RELU) {
+          bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+        }
         tmem_ld_32x32(t_row + c0, v);
         tmem_ld_wait();
         if (direct) {
@@ -343,9 +378,6 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
         __syncwarp();
-        const int n = n0 + c0 + cg;
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.epi == EPI_BIAS_RELU) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const float* sp = stg + (4 * k + sub) * 33 + cg;
@@ -358,20 +390,13 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
             o.y = pack_bf16x2(fmaxf(f2 + bias4.z, 0.f), fmaxf(f3 + bias4.w, 0.f));
             *reinterpret_cast<uint2*>(p.out + pix * p.ldo + n) = o;
           } else if (p.epi == EPI_DGRAD) {
-            uint2* dst = reinterpret_cast<uint2*>(p.out + pix * p.ldo + n);
-            if (p.addOld) {
-              const uint2 o = *dst;
-              f0 += bf16_lo(o.x); f1 += bf16_hi(o.x); f2 += bf16_lo(o.y); f3 += bf16_hi(o.y);
-            }
-            if (n < p.maskN) {
-              const uint2 a = __ldg(reinterpret_cast<const uint2*>(p.act + pix * p.ldact + n));
-              f0 = bf16_lo(a.x) > 0.f ? f0 : 0.f; f1 = bf16_hi(a.x) > 0.f ? f1 : 0.f;
-              f2 = bf16_lo(a.y) > 0.f ? f2 : 0.f; f3 = bf16_hi(a.y) > 0.f ? f3 : 0.f;
-            }
+            f0 += bf16_lo(oldv[k].x); f1 += bf16_hi(oldv[k].x); f2 += bf16_lo(oldv[k].y); f3 += bf16_hi(oldv[k].y);
+            f0 = bf16_lo(actv[k].x) > 0.f ? f0 : 0.f; f1 = bf16_hi(actv[k].x) > 0.f ? f1 : 0.f;
+            f2 = bf16_lo(actv[k].y) > 0.f ? f2 : 0.f; f3 = bf16_hi(actv[k].y) > 0.f ? f3 : 0.f;
             uint2 o;
             o.x = pack_bf16x2(f0, f1);
             o.y = pack_bf16x2(f2, f3);
-            *dst = o;
+            *reinterpret_cast<uint2*>(p.out + pix * p.ldo + n) = o;
           } else if (p.epi == EPI_WS_SLAB) {
             // split-K partial: plain stores into this split's slab (no atomics: the finishing pass sums the slabs
             // in a fixed order, so the step is bit-reproducible)
@@ -386,6 +411,7 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
+      if (item == clusterId && warp == 2 && lane == 0) GCT2_STAMP(5);  // first epilogue done
       if (lane == 0) mbar_arrive(&tempty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -395,6 +421,7 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   if (csize > 1) cluster_sync_all();  // no CTA leaves while a peer may still signal its barriers
+  if (threadIdx.x == 0) GCT2_STAMP(6);  // all work of this CTA done
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);

@@ -39,8 +39,13 @@ int gct2_num_sms(void);
 long long gct2_launch_count(void);
 /* Test hook (not part of the drop-in surface): key 0/1 override the MN-major UMMA descriptor LBO/SBO bytes,
  * key 2 = verbose plan logging, key 3 = force N tile, key 4 = force split-K, keys 5/6 = force the cluster shape
- * (CTAs along M / along N; 0 = heuristic, 1 = none). */
+ * (CTAs along M / along N; 0 = heuristic, 1 = none), key 7 = record per-CTA phase timestamps (gct2_debug_timeline). */
 void gct2_debug_set(int key, int value);
+/* Test hook: after gct2_debug_set(7, 1) every tensor-core conv launch records, per CTA, 8 %globaltimer stamps (ns):
+ * [0] entry, [1] prologue done, [2] first operands landed, [3] MMAs of the first tile issued, [4] first accumulator
+ * complete, [5] first epilogue done, [6] CTA done.  Synchronises the device and copies the stamps of the most
+ * recent launch (up to max_ctas CTAs) to `host`; returns the number of CTAs. */
+int gct2_debug_timeline(unsigned long long* host, int max_ctas);
 
 /* train.py:224-234 + :85-93 -- Trainer.call noising with alpha_dash:
  *   noised = x*sqrt(abar(t)) + eps*sqrt(1-abar(t)), abar(t) = (1 - t/(steps+1))^2 * 0.25.
