@@ -193,8 +193,14 @@ int gct2_adam_prepare(long long* iterations, float* hyper, float base_lr, int wa
   return adam_prepare(iterations, hyper, base_lr, warmup_steps, beta1, beta2, S(stream));
 }
 int gct2_adam_apply(float* w, float* m, float* v, const float* g, uint16_t* w_bf16, long long n, const float* hyper,
-                    float beta1, float beta2, float eps, float grad_scale, void* stream) {
-  return adam_apply(w, m, v, g, MB(w_bf16), n, hyper, beta1, beta2, eps, grad_scale, S(stream));
+                    float beta1, float beta2, float eps, float grad_scale, long long* iterations_inc, void* stream) {
+  return adam_apply(w, m, v, g, MB(w_bf16), n, hyper, beta1, beta2, eps, grad_scale, iterations_inc, S(stream));
+}
+int gct2_step_begin(const float* x, float* noised, float* eps_out, int32_t* t_out, int B, int elems_per_image, int steps,
+                    unsigned long long seed, const long long* iterations, float* hyper, float base_lr, int warmup_steps,
+                    float beta1, float beta2, float* gsmall, long long nsmall, float* loss, void* stream) {
+  return step_begin(x, noised, eps_out, t_out, B, elems_per_image, steps, seed, iterations, hyper, base_lr, warmup_steps,
+                    beta1, beta2, gsmall, nsmall, loss, S(stream));
 }
 
 int gct2_cast_bf16(const float* src, uint16_t* dst, long long n, void* stream) {

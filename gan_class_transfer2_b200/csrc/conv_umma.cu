@@ -212,10 +212,11 @@ __global__ void wgrad_reduce_kernel(const float4* __restrict__ ws, long long spl
 }
 
 // ------------------------------------------------------------------------------------ heuristics
-static int stages_for(int BN) { return BN == 256 ? 4 : (BN == 128 ? 5 : 4); }
-static int occupancy_for(int BN) { return BN == 64 ? 2 : 1; }
-// pipeline stages + barriers (256 B) + 4 epilogue transpose tiles of 32 x 33 floats + 1 KB alignment slack
-static size_t smem_for(int BN) { return (size_t)stages_for(BN) * (16384 + BN * 128) + 1024 + 256 + 4 * 32 * 33 * 4; }
+// every tile width fills the same 192 KB of pipeline: a CTA's operand ingest rate is (bytes in flight) / (TMA round
+// trip, ~1.4 us), so the ring is as deep as shared memory allows -- 8 x 24 KB, 6 x 32 KB, 4 x 48 KB
+static int stages_for(int BN) { return BN == 256 ? 4 : (BN == 128 ? 6 : 8); }
+// pipeline stages + barriers (256 B) + 1 KB alignment slack
+static size_t smem_for(int BN) { return (size_t)stages_for(BN) * (16384 + BN * 128) + 1024 + 256; }
 
 struct Choice {
   int BN, splits, cm, cn;
@@ -230,7 +231,7 @@ static void query_clusters() {
   for (int cs = 2; cs <= 8; cs *= 2) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(cs * 32);
-    cfg.blockDim = dim3(192);
+    cfg.blockDim = dim3(kConvThreads<BN>());
     cfg.dynamicSmemBytes = smem_for(BN);
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -253,14 +254,17 @@ static void query_all_clusters() {
   query_clusters<MODE_P, 64>(); query_clusters<MODE_P, 128>(); query_clusters<MODE_P, 256>();
 }
 
-// Cost model (SM cycles) for one launch; constants fitted to the r1a ncu capture (profiles/):
-//   * a 128 x BN x 64 k-step needs 2*BN tensor-pipe cycles;
-//   * operand bytes come from L2 at ~4800 B/clk for the whole chip (9.5 TB/s), shared by the active CTAs; a tile that is
-//     multicast to c CTAs is read from L2 once per c CTAs;
-//   * every item pays a pipeline fill (L2/DRAM latency) and an epilogue; split-K adds the partial stores and the
-//     finishing pass.
-static Choice choose(int mode, int mTiles, int phases, int N, int kTotal, long long outElems, int forceBN,
-                     int forceSplits, int forceCm, int forceCn, size_t slabBytes, size_t wsBytes) {
+// Cost model (SM cycles at ~1.97 GHz) for one launch, fitted to per-CTA phase timelines measured on B200
+// (tools/timeline.py, profiles/r1b_timeline_b1.txt):
+//   * a CTA ingests operands at a per-SM rate: one 128 x BN x 64 k-step costs 665 + stage_bytes/153 cycles (0.42 us at
+//     BN=64 ... 0.50 us at BN=256) whether 32 or 128 CTAs are active and with or without multicast -- the tensor pipe
+//     (2*BN cycles per k-step) is never the limit at these tile shapes, so the plan that minimises ingested bytes per
+//     SM wins: wide tiles, split-K to occupy every SM;
+//   * fixed per CTA: prologue 0.5 us + first TMA round trip 1.4 us + teardown 0.2 us (clusters: +1.3 us);
+//   * epilogue (16 warps; 8 at BN=64): ~1 us + 4 ns per column, 1.6x for the dgrad epilogue (two extra operand loads);
+//   * split-K: partial stores cost like a wide epilogue, then a finishing pass (launch gap + slab traffic).
+static Choice choose(int mode, int mTiles, int phases, int N, int kTotal, long long outElems, bool dgradEpi,
+                     int forceBN, int forceSplits, int forceCm, int forceCn, size_t slabBytes, size_t wsBytes) {
   Choice best{0, 1, 1, 1};
   double bestCost = 1e30;
   const int bns[3] = {256, 128, 64};
@@ -281,9 +285,10 @@ static Choice choose(int mode, int mTiles, int phases, int N, int kTotal, long l
           const int cm = cms[a], cn = cns[b], cs = cm * cn;
           if (cs > 8 || mTiles % cm || nTiles % cn) continue;
           if (isW && cs > 1) continue;
-          if (forceCm >= 1 && cm != forceCm) continue;
-          if (forceCn >= 1 && cn != forceCn) continue;
-          int maxCtas = g_num_sms * occupancy_for(BN);
+          // clusters cost 1.3 us per launch and do not raise the per-SM ingest rate: only on request (debug keys 5/6)
+          if (forceCm >= 1 ? cm != forceCm : cm != 1) continue;
+          if (forceCn >= 1 ? cn != forceCn : cn != 1) continue;
+          int maxCtas = g_num_sms;
           if (cs > 1) {
             const int mc = g_max_clusters[mode][bn_index(BN)][cs];
             if (mc <= 0) continue;
@@ -292,19 +297,12 @@ static Choice choose(int mode, int mTiles, int phases, int N, int kTotal, long l
           const long long items = (long long)mTiles * phases * (isW ? 16 : 1) * nTiles * splits;
           const long long active = items < maxCtas ? items : maxCtas;
           const long long rounds = (items + active - 1) / active;
-          const double bytes = 16384.0 / cn + BN * 128.0 / cm;  // L2 reads per CTA per k-step
-          double tk = 2.0 * BN;
-          const double l2 = bytes * (double)active / 4800.0;
-          if (l2 > tk) tk = l2;
-          const double ingest = (16384.0 + BN * 128.0) / 96.0;  // per-SM fill rate
-          if (ingest > tk) tk = ingest;
-          if (cs > 1) tk *= 1.06;
-          // TMEM is double-buffered and the producer runs ahead: only the first fill and the last epilogue of a CTA
-          // are exposed (plus whatever part of an epilogue outlasts the next main loop)
-          const double epi = (splits > 1 || isW) ? 700.0 + 5.0 * BN : 700.0 + 3.5 * BN;
+          const double tk = 665.0 + (16384.0 + BN * 128.0) / 153.0;
+          double epi = 2000.0 + 8.0 * BN;
+          if (splits == 1 && dgradEpi) epi *= 1.6;
           const double main = kIters * tk;
-          double cost = 5000.0 + 2500.0 + rounds * main + epi + (rounds - 1) * (epi > main ? epi - main : 0.0);
-          if (splits > 1) cost += 6000.0 + (double)outElems * (4.0 * splits + 6.0) / 4800.0;
+          double cost = 4100.0 + (cs > 1 ? 2600.0 : 0.0) + rounds * main + epi + (rounds - 1) * (epi > main ? epi - main : 0.0);
+          if (splits > 1) cost += 5000.0 + (double)outElems * (4.0 * splits + 6.0) / 2000.0;
           if (cost < bestCost) {
             bestCost = cost;
             best = Choice{BN, splits, cm, cn};
@@ -321,7 +319,7 @@ static cudaError_t launch_one(int grid, int csize, size_t smem, cudaStream_t st,
                               const CUtensorMap& b, const ConvParams& p) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(192);
+  cfg.blockDim = dim3(kConvThreads<BN>());
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute at[1];
@@ -396,8 +394,8 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     p.kcPer = Ck / 64;
     const int kTotal = taps * p.kcPer;
     const size_t slab = (size_t)a.B * (a.mode == MODE_S ? 1 : 4) * a.Hlo * a.Wlo * N * sizeof(float);
-    Choice c = choose(a.mode, pixTiles, phases, N, kTotal, (long long)(slab / sizeof(float)), a.forceBN, a.forceSplits,
-                      a.forceCm, a.forceCn, slab, a.ws ? a.wsBytes : 0);
+    Choice c = choose(a.mode, pixTiles, phases, N, kTotal, (long long)(slab / sizeof(float)), a.epi == EPI_DGRAD,
+                      a.forceBN, a.forceSplits, a.forceCm, a.forceCn, slab, a.ws ? a.wsBytes : 0);
     if (c.BN == 0) {
       set_error("conv: no tile shape for N=%d", N);
       return 1;
@@ -445,8 +443,8 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     }
     const int chunks = pixTiles;
     const size_t slab = (size_t)16 * a.Chi * a.Clo * sizeof(float);
-    Choice c = choose(MODE_W, Mch / 128, 1, Nch, chunks, (long long)(slab / sizeof(float)), a.forceBN, a.forceSplits, 1, 1,
-                      slab, a.ws ? a.wsBytes : 0);
+    Choice c = choose(MODE_W, Mch / 128, 1, Nch, chunks, (long long)(slab / sizeof(float)), false, a.forceBN,
+                      a.forceSplits, 1, 1, slab, a.ws ? a.wsBytes : 0);
     if (c.BN == 0) {
       set_error("wgrad: no tile shape for N=%d", Nch);
       return 1;
@@ -482,7 +480,7 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
   const size_t smem = smem_for(BN);
   const int csize = p.cm * p.cn;
   p.numClusterItems = p.numItems / csize;
-  int maxCtas = g_num_sms * occupancy_for(BN);
+  int maxCtas = g_num_sms;  // one CTA per SM: the per-SM operand ingest rate, not occupancy, bounds a CTA's speed
   if (csize > 1) maxCtas = g_max_clusters[a.mode][bn_index(BN)][csize] * csize;
   int grid = p.numItems < maxCtas ? p.numItems : maxCtas;
   grid -= grid % csize;

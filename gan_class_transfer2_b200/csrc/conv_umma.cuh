@@ -13,8 +13,8 @@
 //   MODE_W  weight gradient  dW[tap][g][p] = sum_pix G_hi[pix @ tap, g] * P_lo[pix, p]
 //           both operands MN-major (pixels are the contraction dim and are the slow smem axis).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue
-// (TMEM -> registers -> shared-memory transpose -> line-coalesced global accesses).  Accumulators are double-buffered in TMEM (2 x BN columns) so the
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warp 3 idle, warps 4.. = epilogue
+// (8 warps for BN = 64, 16 otherwise; TMEM -> registers -> global).  Accumulators are double-buffered in TMEM (2 x BN columns) so the
 // epilogue of tile i overlaps the main loop of tile i+1.
 #pragma once
 #include <cuda_bf16.h>
@@ -101,8 +101,18 @@ __device__ __forceinline__ void red_add_f32(float* addr, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
 
+// Epilogue warps per tile width: 8 (two 32-column slices) for BN = 64, 16 (four slices) for BN = 128 / 256.
+template <int BN>
+__host__ __device__ constexpr int kEpilogueWarps() {
+  return BN == 64 ? 8 : 16;
+}
+template <int BN>
+__host__ __device__ constexpr int kConvThreads() {
+  return 128 + 32 * kEpilogueWarps<BN>();
+}
+
 template <int MODE, int BN>
-__global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ CUtensorMap mapA,
+__global__ void __launch_bounds__(kConvThreads<BN>(), 1) conv_umma_kernel(const __grid_constant__ CUtensorMap mapA,
                                                         const __grid_constant__ CUtensorMap mapB,
                                                         const ConvParams p) {
   constexpr int A_BYTES = 128 * 128;  // 128 rows x 64 bf16 (S/P) or 2 blocks of 64 pixels x 64 channels (W)
@@ -146,7 +156,7 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], kEpilogueWarps<BN>());
     }
     fence_mbar_init();
   }
@@ -300,121 +310,137 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    // tcgen05.ld hands lane l the accumulator row (q*32 + l); writing global memory in that arrangement touches 32
-    // different lines per instruction.  Each 32x32 chunk is therefore transposed through a padded shared-memory
-    // tile so that 8 consecutive lanes own 32 consecutive columns of ONE row (4 rows per instruction): loads of the
-    // saved activation / skip gradient and all stores become line-coalesced.
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    float* stg = reinterpret_cast<float*>(smem + S * STAGE_BYTES + 256) + q * (32 * 33);
-    const int sub = lane >> 3;       // row inside a group of 4
-    const int cg = (lane & 7) * 4;   // first of my 4 columns inside the 32-column chunk
-    uint32_t acc = 0, acc_phase = 0;
-    for (int item = clusterId; item < p.numClusterItems; item += numClusters) {
-      const WorkItem w = decode_item<MODE>(p, item, rm, rn);
-      const int n0 = w.nt * BN;
-      // my 8 rows after the transpose: r_k = q*32 + 4k + sub -> output location
-      long long pixk[8];
-      uint32_t validMask = 0;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int r = q * 32 + 4 * k + sub;
+    // ------------------------------------------------------------------ epilogue (warps 4 .. 4+NE-1)
+    // At batch 1 a CTA owns a single tile, so nothing overlaps its epilogue: it is spread over NE warps.  Warp w may
+    // only read TMEM lanes 32*(w%4)..+31 (hardware rule), so warps w, w+4, w+8, ... share a lane quarter and split the
+    // tile's columns.  Lane l of a warp owns accumulator row (q*32 + l): 16-byte vector accesses per row.
+    if (warp < 4) {
+      // warps 2, 3: nothing to do until teardown
+    } else {
+      constexpr int NE = kEpilogueWarps<BN>();
+      constexpr int COLS = BN / (NE / 4);  // columns per warp (32 or 64)
+      const int q = warp & 3;              // TMEM lane quarter this warp may access
+      const int cgrp = (warp - 4) >> 2;    // which slice of the tile's columns
+      const int r = q * 32 + lane;
+      uint32_t acc = 0, acc_phase = 0;
+      for (int item = clusterId; item < p.numClusterItems; item += numClusters) {
+        const WorkItem w = decode_item<MODE>(p, item, rm, rn);
+        const int n0 = w.nt * BN + cgrp * COLS;
+        // row -> output location
+        bool valid = true;
+        long long pix = 0;
         if (MODE != MODE_W) {
           const int xl = r % p.Wt, yl = (r / p.Wt) % p.Ht, bl = r / (p.Wt * p.Ht);
           const int x = (w.mt % p.tilesX) * p.Wt + xl;
           const int y = ((w.mt / p.tilesX) % p.tilesY) * p.Ht + yl;
           const int b = (w.mt / tilesXY) * p.Nb + bl;
-          if (b < p.B) validMask |= 1u << k;
+          valid = b < p.B;
           int oy = y, ox = x;
           if (MODE == MODE_P) {
             oy = 2 * y + (w.ph >> 1);
             ox = 2 * x + (w.ph & 1);
           }
-          pixk[k] = ((long long)b * p.Hout + oy) * p.Wout + ox;
-        } else {
-          pixk[k] = w.mt * 128 + r;  // M-side channel
-          validMask |= 1u << k;
+          pix = ((long long)b * p.Hout + oy) * p.Wout + ox;
         }
-      }
-      mbar_wait(&tfull[acc], acc_phase);
-      if (item == clusterId && warp == 2 && lane == 0) GCT2_STAMP(4);  // first accumulator complete
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
-      const bool direct = (p.epi == EPI_WGRAD) && p.colStride != 1;  // rows already contiguous in memory
+        mbar_wait(&tfull[acc], acc_phase);
+        if (item == clusterId && warp == 4 && lane == 0) GCT2_STAMP(4);  // first accumulator complete
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN + cgrp * COLS;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        const int n = n0 + c0 + cg;
-        // global operands of this chunk's epilogue are requested before the accumulator is read, so their latency
-        // hides behind the TMEM load and the transpose
-        uint2 actv[8], oldv[8];
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.epi == EPI_DGRAD) {
-          const bool masked = n < p.maskN;
+        for (int c0 = 0; c0 < COLS; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + c0, v);
+          const int n = n0 + c0;
+          if (p.epi == EPI_BIAS_RELU) {
+            tmem_ld_wait();
+            if (valid) {
+              const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
+              uint4* dst = reinterpret_cast<uint4*>(p.out + pix * p.ldo + n);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            actv[k] = make_uint2(0x3f803f80u, 0x3f803f80u);  // bf16 1.0: "keep" when this column is not masked
-            oldv[k] = make_uint2(0u, 0u);
-            if ((validMask >> k) & 1u) {
-              if (masked) actv[k] = __ldg(reinterpret_cast<const uint2*>(p.act + pixk[k] * p.ldact + n));
-              if (p.addOld) oldv[k] = *reinterpret_cast<const uint2*>(p.out + pixk[k] * p.ldo + n);
+              for (int g = 0; g < 4; ++g) {
+                const float4 b0 = __ldg(bp + 2 * g), b1 = __ldg(bp + 2 * g + 1);
+                uint4 o;
+                o.x = pack_bf16x2(fmaxf(__uint_as_float(v[8 * g + 0]) + b0.x, 0.f),
+                                  fmaxf(__uint_as_float(v[8 * g + 1]) + b0.y, 0.f));
+                o.y = pack_bf16x2(fmaxf(__uint_as_float(v[8 * g + 2]) + b0.z, 0.f),
+                                  fmaxf(__uint_as_float(v[8 * g + 3]) + b0.w, 0.f));
+                o.z = pack_bf16x2(fmaxf(__uint_as_float(v[8 * g + 4]) + b1.x, 0.f),
+                                  fmaxf(__uint_as_float(v[8 * g + 5]) + b1.y, 0.f));
+                o.w = pack_bf16x2(fmaxf(__uint_as_float(v[8 * g + 6]) + b1.z, 0.f),
+                                  fmaxf(__uint_as_float(v[8 * g + 7]) + b1.w, 0.f));
+                dst[g] = o;
+              }
+            }
+          } else if (p.epi == EPI_DGRAD) {
+            // the saved activation and the skip gradient are requested while the TMEM load is in flight
+            uint4* dst = reinterpret_cast<uint4*>(p.out + pix * p.ldo + n);
+            const uint4* ap = reinterpret_cast<const uint4*>(p.act + pix * p.ldact + n);
+            const bool masked = valid && n < p.maskN, add = valid && p.addOld;
+            uint4 av[4], ov[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              av[g] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);  // bf16 1.0 = keep
+              ov[g] = make_uint4(0u, 0u, 0u, 0u);
+              if (masked) av[g] = __ldg(ap + g);
+              if (add) ov[g] = dst[g];
+            }
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[8 * g + j]);
+                const uint4 o = ov[g], a = av[g];
+                f[0] += bf16_lo(o.x); f[1] += bf16_hi(o.x); f[2] += bf16_lo(o.y); f[3] += bf16_hi(o.y);
+                f[4] += bf16_lo(o.z); f[5] += bf16_hi(o.z); f[6] += bf16_lo(o.w); f[7] += bf16_hi(o.w);
+                f[0] = bf16_lo(a.x) > 0.f ? f[0] : 0.f; f[1] = bf16_hi(a.x) > 0.f ? f[1] : 0.f;
+                f[2] = bf16_lo(a.y) > 0.f ? f[2] : 0.f; f[3] = bf16_hi(a.y) > 0.f ? f[3] : 0.f;
+                f[4] = bf16_lo(a.z) > 0.f ? f[4] : 0.f; f[5] = bf16_hi(a.z) > 0.f ? f[5] : 0.f;
+                f[6] = bf16_lo(a.w) > 0.f ? f[6] : 0.f; f[7] = bf16_hi(a.w) > 0.f ? f[7] : 0.f;
+                uint4 res;
+                res.x = pack_bf16x2(f[0], f[1]);
+                res.y = pack_bf16x2(f[2], f[3]);
+                res.z = pack_bf16x2(f[4], f[5]);
+                res.w = pack_bf16x2(f[6], f[7]);
+                dst[g] = res;
+              }
+            }
+          } else if (p.epi == EPI_WS_SLAB) {
+            // split-K partial: plain stores into this split's slab (no atomics: the finishing pass sums the slabs in
+            // a fixed order, so the step is bit-reproducible)
+            tmem_ld_wait();
+            if (valid) {
+              float4* dst = reinterpret_cast<float4*>(p.ws + (long long)w.split * p.wsSplitStride + pix * p.N + n);
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                dst[g] = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
+                                     __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+            }
+          } else {  // EPI_WGRAD: row = M-side channel, columns = N-side channels
+            tmem_ld_wait();
+            float* base = (p.atomic ? p.ws + (long long)w.split * p.wsSplitStride : p.dw) +
+                          (long long)w.ph * p.tapStride + (long long)(w.mt * 128 + r) * p.rowStride +
+                          (long long)n * p.colStride;
+            if (p.colStride == 1) {
+              float4* d4 = reinterpret_cast<float4*>(base);
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                d4[g] = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
+                                    __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) base[(long long)j * p.colStride] = __uint_as_float(v[j]);
             }
           }
-        } else if (p.epi == EPI_BIAS_RELU) {
-          bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
         }
-        tmem_ld_32x32(t_row + c0, v);
-        tmem_ld_wait();
-        if (direct) {
-          // dw[tap][n][row]: lane = row -> each store instruction writes 32 consecutive floats
-          float* base = (p.atomic ? p.ws + (long long)w.split * p.wsSplitStride : p.dw) +
-                        (long long)w.ph * p.tapStride + (long long)(w.mt * 128 + q * 32 + lane) * p.rowStride +
-                        (long long)(n0 + c0) * p.colStride;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) base[(long long)j * p.colStride] = __uint_as_float(v[j]);
-          continue;
-        }
-        __syncwarp();  // the previous chunk has been read out of the staging tile
-#pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
+        tc_fence_before();
         __syncwarp();
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float* sp = stg + (4 * k + sub) * 33 + cg;
-          float f0 = sp[0], f1 = sp[1], f2 = sp[2], f3 = sp[3];
-          if (!((validMask >> k) & 1u)) continue;
-          const long long pix = pixk[k];
-          if (p.epi == EPI_BIAS_RELU) {
-            uint2 o;
-            o.x = pack_bf16x2(fmaxf(f0 + bias4.x, 0.f), fmaxf(f1 + bias4.y, 0.f));
-            o.y = pack_bf16x2(fmaxf(f2 + bias4.z, 0.f), fmaxf(f3 + bias4.w, 0.f));
-            *reinterpret_cast<uint2*>(p.out + pix * p.ldo + n) = o;
-          } else if (p.epi == EPI_DGRAD) {
-            f0 += bf16_lo(oldv[k].x); f1 += bf16_hi(oldv[k].x); f2 += bf16_lo(oldv[k].y); f3 += bf16_hi(oldv[k].y);
-            f0 = bf16_lo(actv[k].x) > 0.f ? f0 : 0.f; f1 = bf16_hi(actv[k].x) > 0.f ? f1 : 0.f;
-            f2 = bf16_lo(actv[k].y) > 0.f ? f2 : 0.f; f3 = bf16_hi(actv[k].y) > 0.f ? f3 : 0.f;
-            uint2 o;
-            o.x = pack_bf16x2(f0, f1);
-            o.y = pack_bf16x2(f2, f3);
-            *reinterpret_cast<uint2*>(p.out + pix * p.ldo + n) = o;
-          } else if (p.epi == EPI_WS_SLAB) {
-            // split-K partial: plain stores into this split's slab (no atomics: the finishing pass sums the slabs
-            // in a fixed order, so the step is bit-reproducible)
-            *reinterpret_cast<float4*>(p.ws + (long long)w.split * p.wsSplitStride + pix * p.N + n) =
-                make_float4(f0, f1, f2, f3);
-          } else {  // EPI_WGRAD, rows = M-side channels with N contiguous (colStride == 1)
-            float* base = (p.atomic ? p.ws + (long long)w.split * p.wsSplitStride : p.dw) +
-                          (long long)w.ph * p.tapStride + pix * p.rowStride + n;
-            *reinterpret_cast<float4*>(base) = make_float4(f0, f1, f2, f3);
-          }
-        }
+        if (item == clusterId && warp == 4 && lane == 0) GCT2_STAMP(5);  // first epilogue (of warp 4) done
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
       }
-      tc_fence_before();
-      __syncwarp();
-      if (item == clusterId && warp == 2 && lane == 0) GCT2_STAMP(5);  // first epilogue done
-      if (lane == 0) mbar_arrive(&tempty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
   }
 

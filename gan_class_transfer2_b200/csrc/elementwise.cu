@@ -67,6 +67,91 @@ int noise_images(const float* x, const float* eps, const int* t_int, float* nois
   return 0;
 }
 
+// ------------------------------------------------------------------------------------ fused step prologue
+// One launch for everything the step needs before the first convolution (train.py:224-234 + optimiser bookkeeping):
+//   t_int ~ U{1..steps} per image, eps ~ N(0,1) per element (Philox4x32-10 keyed by `seed`, offset by the optimiser
+//   iteration so every step draws fresh numbers; Box-Muller), noised = x*sqrt(abar) + eps*sqrt(1-abar);
+//   zeroes the atomically-accumulated gradient region and the loss; computes this step's Adam alpha/lr.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+    const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += W0;
+    k.y += W1;
+  }
+  return c;
+}
+__device__ __forceinline__ float u32_to_unit_open(uint32_t v) {  // (0, 1]
+  return ((float)(v >> 8) + 1.0f) * (1.0f / 16777216.0f);
+}
+
+__global__ void __launch_bounds__(256) step_begin_kernel(const float4* __restrict__ x, float4* __restrict__ noised,
+                                                         float4* __restrict__ eps_out, int* __restrict__ t_out,
+                                                         int B, int vecPerImage, int steps, unsigned long long seed,
+                                                         const long long* __restrict__ iterations,
+                                                         float* __restrict__ hyper, float base, int warmup, float b1,
+                                                         float b2, float4* __restrict__ gsmall, long long nsmallVec,
+                                                         float* __restrict__ loss) {
+  const long long step = *iterations;
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  if (tid == 0) {
+    float lr = base;
+    if (step < warmup) lr = base * (float)(step + 1) / (float)(warmup + 1);
+    const float t = (float)(step + 1);
+    hyper[0] = lr * sqrtf(1.f - powf(b2, t)) / (1.f - powf(b1, t));
+    hyper[1] = lr;
+    *loss = 0.f;
+  }
+  for (long long i = tid; i < nsmallVec; i += nthreads) gsmall[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long total = (long long)B * vecPerImage;
+  for (long long i = tid; i < total; i += nthreads) {
+    const int b = (int)(i / vecPerImage);
+    // stream 1: one draw per image; stream 0: four normals per float4
+    const uint4 ti = philox4x32_10(make_uint4((uint32_t)b, 0u, (uint32_t)step, 0x80000000u | (uint32_t)(step >> 32)), key);
+    const int tint = 1 + (int)(ti.x % (uint32_t)steps);
+    if (t_out != nullptr && i % vecPerImage == 0) t_out[b] = tint;
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)step, (uint32_t)(step >> 32) & 0x7fffffffu),
+                                  key);
+    const float ra = sqrtf(-2.f * __logf(u32_to_unit_open(r.x))), rb = sqrtf(-2.f * __logf(u32_to_unit_open(r.z)));
+    float s0, c0, s1, c1;
+    __sincosf(6.283185307179586f * u32_to_unit_open(r.y), &s0, &c0);
+    __sincosf(6.283185307179586f * u32_to_unit_open(r.w), &s1, &c1);
+    const float4 ev = make_float4(ra * c0, ra * s0, rb * c1, rb * s1);
+    float t = (float)tint / (float)(steps + 1);
+    const float om = 1.f - t;
+    const float abar = om * om * 0.25f;
+    const float sa = sqrtf(abar), sb = sqrtf(1.f - abar);
+    const float4 xv = __ldg(x + i);
+    if (eps_out != nullptr) eps_out[i] = ev;
+    noised[i] = make_float4(xv.x * sa + ev.x * sb, xv.y * sa + ev.y * sb, xv.z * sa + ev.z * sb, xv.w * sa + ev.w * sb);
+  }
+}
+
+int step_begin(const float* x, float* noised, float* eps_out, int* t_out, int B, int elemsPerImage, int steps,
+               unsigned long long seed, const long long* iterations, float* hyper, float base_lr, int warmup_steps,
+               float beta1, float beta2, float* gsmall, long long nsmall, float* loss, cudaStream_t st) {
+  if (elemsPerImage % 4 || nsmall % 4) {
+    set_error("step_begin: elements per image and the small gradient region must be multiples of 4");
+    return 1;
+  }
+  const int vec = elemsPerImage / 4;
+  const long long total = (long long)B * vec;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > g_ew_sms * 8) blocks = g_ew_sms * 8;
+  if (blocks < 1) blocks = 1;
+  step_begin_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(noised),
+                                           reinterpret_cast<float4*>(eps_out), t_out, B, vec, steps, seed, iterations,
+                                           hyper, base_lr, warmup_steps, beta1, beta2,
+                                           reinterpret_cast<float4*>(gsmall), nsmall / 4, loss);
+  GCT2_CHECK_LAUNCH("step_begin_kernel");
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------ down0 (Cin = 3)
 // Direct conv on CUDA cores: K = 48 is too thin for a tensor-core tile and the layer is bound by its 128-channel
 // output write.  Block = 8x8 output pixels, thread = output channel; the 18x18x3 input patch sits in smem and the
@@ -490,8 +575,9 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ w, float
                                                    float4* __restrict__ v, const float4* __restrict__ g,
                                                    uint2* __restrict__ wb, long long nvec,
                                                    const float* __restrict__ hyper, float b1, float b2, float eps,
-                                                   float gscale) {
+                                                   float gscale, long long* __restrict__ iterations_inc) {
   const float alpha = __ldg(hyper);
+  if (iterations_inc != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *iterations_inc += 1;
   const float c1 = 1.f - b1, c2 = 1.f - b2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
@@ -521,7 +607,7 @@ int adam_prepare(long long* iterations, float* hyper, float base_lr, int warmup_
 }
 
 int adam_apply(float* w, float* m, float* v, const float* g, __nv_bfloat16* w_bf16, long long n, const float* hyper,
-               float beta1, float beta2, float eps, float grad_scale, cudaStream_t st) {
+               float beta1, float beta2, float eps, float grad_scale, long long* iterations_inc, cudaStream_t st) {
   if (n % 4 || (reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v) |
                 reinterpret_cast<uintptr_t>(g)) % 16 || reinterpret_cast<uintptr_t>(w_bf16) % 8) {
     set_error("adam: ranges must start on 16-byte boundaries and hold a multiple of 4 elements (n=%lld)", n);
@@ -534,7 +620,7 @@ int adam_apply(float* w, float* m, float* v, const float* g, __nv_bfloat16* w_bf
   adam_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<float4*>(w), reinterpret_cast<float4*>(m),
                                            reinterpret_cast<float4*>(v), reinterpret_cast<const float4*>(g),
                                            reinterpret_cast<uint2*>(w_bf16), nvec, hyper, beta1, beta2, eps,
-                                           grad_scale);
+                                           grad_scale, iterations_inc);
   GCT2_CHECK_LAUNCH("adam_kernel");
   return 0;
 }
@@ -543,7 +629,7 @@ int adam_keras(float* w, float* m, float* v, const float* g, __nv_bfloat16* w_bf
                long long* iterations, float* hyper, float base_lr, int warmup_steps, float beta1, float beta2,
                float eps, float grad_scale, cudaStream_t st) {
   if (adam_prepare(iterations, hyper, base_lr, warmup_steps, beta1, beta2, st)) return 1;
-  return adam_apply(w, m, v, g, w_bf16, n, hyper, beta1, beta2, eps, grad_scale, st);
+  return adam_apply(w, m, v, g, w_bf16, n, hyper, beta1, beta2, eps, grad_scale, nullptr, st);
 }
 
 // ------------------------------------------------------------------------------------ fp32 -> bf16 shadow

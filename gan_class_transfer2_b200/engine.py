@@ -180,6 +180,7 @@ class UNetEngine:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.dp = dp
         self.use_graph = use_graph
+        self.rng_seed = 0x5DEECE66D + 7919 * (dp.rank if dp else 0)  # every rank draws its own noise
         self.overlap_wgrad = True
         self._side = torch.cuda.Stream(device=self.device)
         self._side_adam = torch.cuda.Stream(device=self.device)
@@ -309,7 +310,7 @@ class UNetEngine:
                       du0=self.gu0 if backward else None, dwd=self.view(self.g, "dense/kernel") if backward else None,
                       dbd=self.view(self.g, "dense/bias") if backward else None, accumulate=True)
 
-    def _backward(self, apply_adam: bool) -> None:
+    def _backward(self, apply_adam: bool, inc_iterations: bool = False) -> None:
         """Three chains that share the GPU (at batch 1 no layer fills 148 SMs on its own):
           main stream  the dgrad chain (the only true dependency chain of backward), then down0's wgrad + bias grads;
           side_w       the 12 tensor-core weight gradients, each released as soon as its dz exists, and -- data
@@ -354,7 +355,8 @@ class UNetEngine:
                     if work is not None:
                         work.wait()
                     ops.adam_apply(self.w[start:end], self.m[start:end], self.v[start:end], self.g[start:end],
-                                   self.w16[start:end], self.hyper, cfg.beta1, cfg.beta2, cfg.epsilon, 1.0)
+                                   self.w16[start:end], self.hyper, cfg.beta1, cfg.beta2, cfg.epsilon, 1.0,
+                                   iterations_inc=self.iterations if (inc_iterations and start == 0) else None)
 
         for i in range(n):  # up0 .. up{n-1}
             on_side(lambda: ops.convT4s2_wgrad(self.up_in_buf(i), self.gup_out(i), self.view(self.g, f"up{i}/kernel"),
@@ -392,14 +394,17 @@ class UNetEngine:
         cfg = self.cfg
         inv_n = 1.0 / (self.global_batch * cfg.size * cfg.size * 3)
         if draw:
-            # train.py:224-227: t_int ~ U{1..steps}, epsilon ~ N(0,1), drawn on the device every step
-            self.t_int.random_(1, cfg.steps + 1)
-            self.eps.normal_()
-        self._zero_small_grads()
-        ops.adam_prepare(self.iterations, self.hyper, cfg.base_lr, cfg.warm_up, cfg.beta1, cfg.beta2)
-        ops.noise_images(self.x, self.eps, self.t_int, self.noised, cfg.steps)
+            # train.py:224-234 in one launch: t_int ~ U{1..steps} and epsilon ~ N(0,1) drawn on the device (Philox,
+            # offset by the optimiser iteration), noising, zeroing of the atomically-accumulated gradients + loss, and
+            # this step's Adam alpha; the iteration counter is advanced by the step's last Adam launch
+            ops.step_begin(self.x, self.noised, self.iterations, self.hyper, self.g[:self.small], self.loss,
+                           self.rng_seed, cfg.steps, cfg.base_lr, cfg.warm_up, cfg.beta1, cfg.beta2, t_out=self.t_int)
+        else:
+            self._zero_small_grads()
+            ops.adam_prepare(self.iterations, self.hyper, cfg.base_lr, cfg.warm_up, cfg.beta1, cfg.beta2)
+            ops.noise_images(self.x, self.eps, self.t_int, self.noised, cfg.steps)
         self._forward(want_pred=False, backward=True, inv_n=inv_n)
-        self._backward(apply_adam=True)
+        self._backward(apply_adam=True, inc_iterations=draw)
 
     def set_batch(self, x: torch.Tensor, t_int: Optional[torch.Tensor] = None,
                   eps: Optional[torch.Tensor] = None) -> None:

@@ -239,11 +239,25 @@ def adam_prepare(iterations, hyper, base_lr: float, warmup_steps: int, beta1: fl
 
 @_timed
 def adam_apply(w, m, v, g, w_bf16, hyper, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-7,
-               grad_scale: float = 1.0):
-    """Keras-Adam update of one contiguous range of the flat buffers (views starting on 16-byte boundaries)."""
+               grad_scale: float = 1.0, iterations_inc=None):
+    """Keras-Adam update of one contiguous range of the flat buffers (views starting on 16-byte boundaries).
+    iterations_inc: the optimiser's iteration counter, incremented by this launch (pass it on the step's last range
+    when the step was opened with step_begin)."""
     lib = _lib_for(w)
     check(lib.gct2_adam_apply(ptr(w), ptr(m), ptr(v), ptr(g), ptr(w_bf16), w.numel(), ptr(hyper), beta1, beta2, eps,
-                              grad_scale, current_stream()))
+                              grad_scale, ptr(iterations_inc), current_stream()))
+
+
+@_timed
+def step_begin(x, noised, iterations, hyper, gsmall, loss, seed: int, steps: int, base_lr: float, warmup_steps: int,
+               beta1: float = 0.9, beta2: float = 0.999, eps_out=None, t_out=None):
+    """Fused step prologue: device-side draws of t_int / eps (train.py:224-227), noising (train.py:231-234), zeroing of
+    the atomically-accumulated gradients and the loss, Adam alpha of this step."""
+    lib = _lib_for(x)
+    B = x.shape[0]
+    check(lib.gct2_step_begin(ptr(x), ptr(noised), ptr(eps_out), ptr(t_out), B, x.numel() // B, steps, seed,
+                              ptr(iterations), ptr(hyper), base_lr, warmup_steps, beta1, beta2, ptr(gsmall),
+                              gsmall.numel(), ptr(loss), current_stream()))
 
 
 @_timed

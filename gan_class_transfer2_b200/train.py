@@ -440,7 +440,7 @@ class Trainer(Model):
             eng.t_int.random_(1, eng.cfg.steps + 1)
             eng.eps.normal_()
         eng.loss.zero_()
-        ops.noise_images(eng.x, eng.eps, eng.t_int, eng.noised, eng.cfg.steps)
+        ops.noise_images(eng.x, eng.eps, eng.t_int, eng.noised, eng.cfg.steps)  # forward-only call: torch's draws
         eng._forward(want_pred=True, backward=False, inv_n=1.0 / (eng.global_batch * eng.cfg.size ** 2 * 3))
         return eng.loss[0]
 

@@ -122,11 +122,21 @@ int gct2_adam_keras(float* w, float* m, float* v, const float* g, uint16_t* w_bf
                     float eps, float grad_scale, void* stream);
 /* The same optimiser in two parts, so that the update of a contiguous range of variables can start as soon as that
  * range's gradients are complete (overlapping the rest of backward): gct2_adam_prepare once per step (computes
- * alpha/lr of this step into hyper[0..1], increments *iterations), then gct2_adam_apply per range. */
+ * alpha/lr of this step into hyper[0..1], increments *iterations), then gct2_adam_apply per range
+ * (iterations_inc: NULL, or a counter to increment by one -- used together with gct2_step_begin). */
 int gct2_adam_prepare(long long* iterations, float* hyper, float base_lr, int warmup_steps, float beta1, float beta2,
                       void* stream);
 int gct2_adam_apply(float* w, float* m, float* v, const float* g, uint16_t* w_bf16, long long n, const float* hyper,
-                    float beta1, float beta2, float eps, float grad_scale, void* stream);
+                    float beta1, float beta2, float eps, float grad_scale, long long* iterations_inc, void* stream);
+/* Everything a step needs before its first convolution, in one launch (train.py:224-234 plus optimiser bookkeeping):
+ * draws t_int ~ U{1..steps} per image and eps ~ N(0,1) per element on the device (Philox4x32-10 keyed by `seed`, offset by
+ * *iterations so every step differs; the reference draws with TF's unseeded generators), writes
+ * noised = x*sqrt(abar(t)) + eps*sqrt(1-abar(t)); optionally stores eps / t_int (eps_out, t_out may be NULL); zeroes
+ * gsmall[0..nsmall) and *loss; writes this step's Adam alpha/lr to hyper[0..1] WITHOUT incrementing *iterations (pass
+ * iterations_inc to the step's last gct2_adam_apply instead). */
+int gct2_step_begin(const float* x, float* noised, float* eps_out, int32_t* t_out, int B, int elems_per_image, int steps,
+                    unsigned long long seed, const long long* iterations, float* hyper, float base_lr, int warmup_steps,
+                    float beta1, float beta2, float* gsmall, long long nsmall, float* loss, void* stream);
 /* fp32 -> bf16 (round to nearest even); builds the first shadow copy of the weights. */
 int gct2_cast_bf16(const float* src, uint16_t* dst, long long n, void* stream);
 

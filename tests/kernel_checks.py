@@ -201,6 +201,57 @@ def check_noise(B=3, H=32, seed=6):
     return _metrics(f"noise_images B{B} H{H}", out, ref, 2e-6)
 
 
+def check_step_begin(B=4, H=64, seed=13):
+    """Fused step prologue: the device-side draws have the right distributions (t_int ~ U{1..steps}, eps ~ N(0,1)),
+    noised follows train.py:231-234 for the draws the kernel reports, the small-gradient region and the loss are zeroed,
+    alpha matches the oracle's WarmUp/Adam arithmetic, draws differ between iterations and repeat for equal (seed, iteration)."""
+    ops = _ops()
+    cfg = O.Config(size=H)
+    x, _, _ = O.synthetic_batch(cfg, B, seed)
+    dev = _dev()
+    xd = x.to(dev)
+    outs = []
+    for it in (0, 0, 5):
+        noised = torch.empty_like(xd)
+        eps = torch.empty_like(xd)
+        t = torch.zeros(B, dtype=torch.int32, device=dev)
+        iters = torch.full((1,), it, dtype=torch.int64, device=dev)
+        hyper = torch.zeros(2, device=dev)
+        gsmall = torch.full((4096,), 3.0, device=dev)
+        loss = torch.full((1,), 3.0, device=dev)
+        ops.step_begin(xd, noised, iters, hyper, gsmall, loss, 1234, cfg.steps, cfg.base_lr, cfg.warm_up, cfg.beta1,
+                       cfg.beta2, eps_out=eps, t_out=t)
+        torch.cuda.synchronize()
+        outs.append((noised.cpu(), eps.cpu(), t.cpu(), hyper.cpu(), gsmall.cpu(), loss.cpu(), int(iters.item())))
+    noised, eps, t, hyper, gsmall, loss, it_after = outs[2]
+    ref = O.noise_images(x, t, eps, cfg)
+    m = _metrics(f"step_begin B{B} H{H} noising", noised, ref, 2e-6)
+    n = eps.numel()
+    w = torch.zeros(1)
+    m_, v_ = torch.zeros(1), torch.zeros(1)
+    alpha = O.keras_adam_update(w, m_, v_, torch.zeros(1), 5, cfg)
+    # many-draw statistics on a second, larger call
+    big_x = torch.zeros(64, 64, 64, 3, device=dev)
+    big_eps = torch.empty_like(big_x)
+    big_t = torch.zeros(64, dtype=torch.int32, device=dev)
+    ops.step_begin(big_x, torch.empty_like(big_x), torch.zeros(1, dtype=torch.int64, device=dev), torch.zeros(2, device=dev),
+                   torch.zeros(4, device=dev), torch.zeros(1, device=dev), 99, 200, 2e-5, 2000, eps_out=big_eps, t_out=big_t)
+    e = big_eps.double().cpu().flatten()
+    ok = (abs(float(e.mean())) < 5e-3 and abs(float(e.var()) - 1) < 1e-2 and abs(float((e ** 4).mean()) - 3) < 0.1
+          and float(e.abs().max()) > 4.0 and int(big_t.min()) >= 1 and int(big_t.max()) <= 200
+          and len(set(big_t.cpu().tolist())) > 30
+          and int(t.min()) >= 1 and int(t.max()) <= cfg.steps
+          and bool((gsmall == 0).all()) and float(loss) == 0.0 and it_after == 5
+          and abs(float(hyper[0]) - alpha) <= 1e-6 * alpha
+          and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])   # reproducible
+          and not torch.equal(outs[0][1], outs[2][1]))                                       # fresh per iteration
+    if not ok:
+        m["err"] = float("inf")
+        m["detail"] = dict(mean=float(e.mean()), var=float(e.var()), kurt=float((e ** 4).mean()), tmin=int(big_t.min()),
+                           tmax=int(big_t.max()), alpha=float(hyper[0]), alpha_ref=alpha, it_after=it_after)
+    return m
+
+
 def check_c3_fprop(B=2, H=32, Cout=128, seed=7):
     ops = _ops()
     g = torch.Generator().manual_seed(seed)
@@ -361,6 +412,7 @@ CONV_CASES = [
 ]
 EW_CASES = [
     (check_noise, {}),
+    (check_step_begin, {}),
     (check_c3_fprop, {}),
     (check_c3_wgrad, {}),
     (check_bias_grad, {}),
