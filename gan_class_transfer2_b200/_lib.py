@@ -94,6 +94,10 @@ def init(device: int = 0) -> ctypes.CDLL:
         if lib.gct2_init(device) != 0:
             raise Gct2Error(lib.gct2_last_error().decode())
         _inited_devices.add(device)
+        # test hook: GCT2_DEBUG="key=value,key=value" -> gct2_debug_set (see include/gct2_b200.h)
+        for item in filter(None, os.environ.get("GCT2_DEBUG", "").split(",")):
+            key, value = item.split("=")
+            lib.gct2_debug_set(int(key), int(value))
     return lib
 
 

@@ -32,6 +32,25 @@ struct ConvArgs {
   int forceCm, forceCn;          // cluster shape override (0 = heuristic, 1 = no cluster along that axis)
 };
 
+extern int g_use_pdl;  // 1 = launch with programmatic stream serialisation (debug key 8 toggles)
+
+// <<<>>> replacement that adds the programmatic-dependent-launch attribute.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 int conv_init(int device);                       // once per process/device
 int conv_launch(const ConvArgs& a, cudaStream_t stream);
 int debug_read_timeline(unsigned long long* host, int max_ctas);  // test hook, see gct2_debug_timeline

@@ -20,6 +20,7 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+int g_use_pdl = 1;
 static long long g_launches = 0;
 void count_launch(int n) { g_launches += n; }
 long long launch_count() { return g_launches; }
@@ -48,6 +49,7 @@ void conv_set_debug(int key, int value) {
   if (key == 0) g_mn_lbo = value;
   if (key == 1) g_mn_sbo = value;
   if (key == 2) g_verbose = value;
+  if (key == 8) g_use_pdl = value ? 0 : 1;  // key 8 != 0 disables programmatic dependent launch
   if (key == 7) {
     if (value && g_dbg == nullptr) cudaMalloc(&g_dbg, (size_t)DBG_MAX_CTAS * 8 * sizeof(unsigned long long));
     if (!value && g_dbg != nullptr) {
@@ -155,6 +157,8 @@ __global__ void splitk_finish_kernel(const float* __restrict__ ws, long long spl
                                      long long pixels, int epi, __nv_bfloat16* __restrict__ out, int ldo,
                                      const float* __restrict__ bias, const __nv_bfloat16* __restrict__ act, int ldact,
                                      int maskN, int addOld) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int vecPerRow = N / 4;
   const long long total = pixels * vecPerRow;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -200,6 +204,8 @@ __global__ void splitk_finish_kernel(const float* __restrict__ ws, long long spl
 // dw[i] = sum over splits of slab[s][i] (weight-gradient split-K), fixed order.
 __global__ void wgrad_reduce_kernel(const float4* __restrict__ ws, long long splitStrideVec, int splits,
                                     float4* __restrict__ dw, long long nvec) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
     float4 v = __ldg(ws + i);
@@ -256,8 +262,9 @@ static void query_all_clusters() {
 
 // Cost model (SM cycles at ~1.97 GHz) for one launch, fitted to per-CTA phase timelines measured on B200
 // (tools/timeline.py, profiles/r1b_timeline_b1.txt):
-//   * a CTA ingests operands at a per-SM rate: one 128 x BN x 64 k-step costs 665 + stage_bytes/153 cycles (0.42 us at
-//     BN=64 ... 0.50 us at BN=256) whether 32 or 128 CTAs are active and with or without multicast -- the tensor pipe
+//   * a CTA ingests operands at a per-SM rate: one 128 x BN x 64 k-step costs (TMA round trip 2800)/stages +
+//     stage_bytes/153 cycles (measured with 4 stages: 0.42 us at BN=64 ... 0.50 us at BN=256) whether 32 or 128 CTAs
+//     are active and with or without multicast -- the tensor pipe
 //     (2*BN cycles per k-step) is never the limit at these tile shapes, so the plan that minimises ingested bytes per
 //     SM wins: wide tiles, split-K to occupy every SM;
 //   * fixed per CTA: prologue 0.5 us + first TMA round trip 1.4 us + teardown 0.2 us (clusters: +1.3 us);
@@ -297,7 +304,7 @@ static Choice choose(int mode, int mTiles, int phases, int N, int kTotal, long l
           const long long items = (long long)mTiles * phases * (isW ? 16 : 1) * nTiles * splits;
           const long long active = items < maxCtas ? items : maxCtas;
           const long long rounds = (items + active - 1) / active;
-          const double tk = 665.0 + (16384.0 + BN * 128.0) / 153.0;
+          const double tk = 2800.0 / stages_for(BN) + (16384.0 + BN * 128.0) / 153.0;
           double epi = 2000.0 + 8.0 * BN;
           if (splits == 1 && dgradEpi) epi *= 1.6;
           const double main = kIters * tk;
@@ -322,15 +329,20 @@ static cudaError_t launch_one(int grid, int csize, size_t smem, cudaStream_t st,
   cfg.blockDim = dim3(kConvThreads<BN>());
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   cfg.attrs = at;
   cfg.numAttrs = 0;
   if (csize > 1) {
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = csize;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.numAttrs = 1;
+    at[cfg.numAttrs].id = cudaLaunchAttributeClusterDimension;
+    at[cfg.numAttrs].val.clusterDim.x = csize;
+    at[cfg.numAttrs].val.clusterDim.y = 1;
+    at[cfg.numAttrs].val.clusterDim.z = 1;
+    ++cfg.numAttrs;
+  }
+  if (g_use_pdl) {
+    at[cfg.numAttrs].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[cfg.numAttrs].val.programmaticStreamSerializationAllowed = 1;
+    ++cfg.numAttrs;
   }
   return cudaLaunchKernelEx(&cfg, conv_umma_kernel<MODE, BN>, a, b, p);
 }
@@ -512,9 +524,8 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     const long long total = pixels * (p.N / 4);
     int blocks = (int)((total + 255) / 256);
     if (blocks > g_num_sms * 8) blocks = g_num_sms * 8;
-    splitk_finish_kernel<<<blocks, 256, 0, stream>>>(a.ws, p.wsSplitStride, p.splits, p.N, pixels, a.epi, a.out, a.ldo,
-                                                     a.bias, a.act, a.ldact, a.maskN, a.addOld);
-    e = cudaGetLastError();
+    e = launch_k(splitk_finish_kernel, dim3(blocks), dim3(256), 0, stream, a.ws, p.wsSplitStride, p.splits, p.N, pixels,
+                 a.epi, a.out, a.ldo, a.bias, a.act, a.ldact, a.maskN, a.addOld);
     if (e != cudaSuccess) {
       set_error("splitk_finish_kernel launch: %s", cudaGetErrorString(e));
       return 1;
@@ -525,9 +536,8 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     const long long nvec = (long long)4 * a.Chi * a.Clo;  // 16 taps * Chi * Clo / 4
     int blocks = (int)((nvec + 255) / 256);
     if (blocks > g_num_sms * 8) blocks = g_num_sms * 8;
-    wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(a.ws), p.wsSplitStride / 4, p.splits,
-                                                    reinterpret_cast<float4*>(a.dw), nvec);
-    e = cudaGetLastError();
+    e = launch_k(wgrad_reduce_kernel, dim3(blocks), dim3(256), 0, stream, reinterpret_cast<const float4*>(a.ws),
+                 p.wsSplitStride / 4, p.splits, reinterpret_cast<float4*>(a.dw), nvec);
     if (e != cudaSuccess) {
       set_error("wgrad_reduce_kernel launch: %s", cudaGetErrorString(e));
       return 1;

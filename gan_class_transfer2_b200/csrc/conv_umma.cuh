@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>(), 1) conv_umma_kernel(const 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) GCT2_STAMP(0);  // kernel entry
+  const unsigned long long t_entry = (p.dbg != nullptr && threadIdx.x == 0) ? globaltimer_ns() : 0ull;
 
   // cluster geometry (cm*cn == 1: plain launch, every mask below is unused)
   const int csize = p.cm * p.cn;
@@ -169,7 +169,13 @@ __global__ void __launch_bounds__(kConvThreads<BN>(), 1) conv_umma_kernel(const 
   if (csize > 1) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 0) GCT2_STAMP(1);  // prologue done
+  // Programmatic dependent launch: everything above ran while the previous kernel of the stream was still draining;
+  // from here on global memory is touched (the stamp below included), so wait for that kernel to complete -- and let
+  // the next kernel start its own prologue now.
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x == 0 && p.dbg != nullptr) p.dbg[(size_t)blockIdx.x * 8 + 0] = t_entry;  // kernel entry
+  if (threadIdx.x == 0) GCT2_STAMP(1);  // prologue done (and the previous kernel complete)
 
   const int tilesXY = p.tilesX * p.tilesY;
 

@@ -36,6 +36,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 __global__ void noise_kernel(const float4* __restrict__ x, const float4* __restrict__ eps,
                              const int* __restrict__ t_int, float4* __restrict__ out, int B, int vecPerImage,
                              int steps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = (long long)B * vecPerImage;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -61,7 +63,7 @@ int noise_images(const float* x, const float* eps, const int* t_int, float* nois
   int blocks = (int)((total + 255) / 256);
   if (blocks > g_ew_sms * 8) blocks = g_ew_sms * 8;
   if (blocks < 1) blocks = 1;
-  noise_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(eps), t_int,
+  launch_k(noise_kernel, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(eps), t_int,
                                       reinterpret_cast<float4*>(noised), B, vec, steps);
   GCT2_CHECK_LAUNCH("noise_kernel");
   return 0;
@@ -95,6 +97,8 @@ __global__ void __launch_bounds__(256) step_begin_kernel(const float4* __restric
                                                          float* __restrict__ hyper, float base, int warmup, float b1,
                                                          float b2, float4* __restrict__ gsmall, long long nsmallVec,
                                                          float* __restrict__ loss) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long step = *iterations;
   const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
   const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -144,7 +148,7 @@ int step_begin(const float* x, float* noised, float* eps_out, int* t_out, int B,
   int blocks = (int)((total + 255) / 256);
   if (blocks > g_ew_sms * 8) blocks = g_ew_sms * 8;
   if (blocks < 1) blocks = 1;
-  step_begin_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(noised),
+  launch_k(step_begin_kernel, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(noised),
                                            reinterpret_cast<float4*>(eps_out), t_out, B, vec, steps, seed, iterations,
                                            hyper, base_lr, warmup_steps, beta1, beta2,
                                            reinterpret_cast<float4*>(gsmall), nsmall / 4, loss);
@@ -175,6 +179,8 @@ __global__ void __launch_bounds__(128) conv_c3_fprop_kernel(const float* __restr
                                                             const float* __restrict__ bias,
                                                             __nv_bfloat16* __restrict__ y, int ldy, int B, int H,
                                                             int W, int Cout) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ __align__(16) float patch[C3_P][C3_ROW];
   const int Ho = H / 2, Wo = W / 2;
   const int tilesX = Wo / C3_T, tilesY = Ho / C3_T;
@@ -211,7 +217,7 @@ int conv4s2_c3_fprop(const float* x, const float* w, const float* bias, __nv_bfl
     return 1;
   }
   dim3 grid(B * (H / 2 / C3_T) * (W / 2 / C3_T), Cout / 128);
-  conv_c3_fprop_kernel<<<grid, 128, 0, st>>>(x, w, bias, y, ldy, B, H, W, Cout);
+  launch_k(conv_c3_fprop_kernel, dim3(grid), dim3(128), 0, st, x, w, bias, y, ldy, B, H, W, Cout);
   GCT2_CHECK_LAUNCH("conv_c3_fprop_kernel");
   return 0;
 }
@@ -221,6 +227,8 @@ __global__ void __launch_bounds__(128) conv_c3_wgrad_kernel(const float* __restr
                                                             const __nv_bfloat16* __restrict__ dz, int lddz,
                                                             float* __restrict__ dw, float* __restrict__ db, int B,
                                                             int H, int W, int Cout, int numTiles) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ __align__(16) float patch[C3_P][C3_ROW];
   const int Ho = H / 2, Wo = W / 2;
   const int tilesX = Wo / C3_T, tilesY = Ho / C3_T;
@@ -272,7 +280,7 @@ int conv4s2_c3_wgrad(const float* x, const __nv_bfloat16* dz, int lddz, float* d
   const int numTiles = B * (H / 2 / C3_T) * (W / 2 / C3_T);
   int gx = numTiles < 2 * g_ew_sms ? numTiles : 2 * g_ew_sms;
   dim3 grid(gx, Cout / 128);
-  conv_c3_wgrad_kernel<<<grid, 128, 0, st>>>(x, dz, lddz, dw, db, B, H, W, Cout, numTiles);
+  launch_k(conv_c3_wgrad_kernel, dim3(grid), dim3(128), 0, st, x, dz, lddz, dw, db, B, H, W, Cout, numTiles);
   GCT2_CHECK_LAUNCH("conv_c3_wgrad_kernel");
   return 0;
 }
@@ -291,6 +299,8 @@ __global__ void __launch_bounds__(256) dense_mse_kernel(const __nv_bfloat16* __r
                                                         float* __restrict__ loss, __nv_bfloat16* __restrict__ du0,
                                                         int lddu, float* __restrict__ dwd, float* __restrict__ dbd,
                                                         long long pixels, float invN, int backward) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int PPW = 32 / LPP;        // pixels per warp iteration
   constexpr int CU = 8 * LPP;
   constexpr int NRED = CU * 3 + 9 + 3 + 1;  // dWd(u0 part) | dWd(image part) | dbd | loss
@@ -438,10 +448,10 @@ int dense_mse(const __nv_bfloat16* u0, int ldu, const float* noised, const float
   int blocks = (int)(want < (long long)g_ew_sms * 2 ? want : (long long)g_ew_sms * 2);
   if (blocks < 1) blocks = 1;
   if (Cu == 64)
-    dense_mse_kernel<8><<<blocks, 256, 0, st>>>(u0, ldu, noised, x, wd, bd, pred, loss, du0, lddu, dwd, dbd, pixels, invN,
+    launch_k(dense_mse_kernel<8>, dim3(blocks), dim3(256), 0, st, u0, ldu, noised, x, wd, bd, pred, loss, du0, lddu, dwd, dbd, pixels, invN,
                                                 backward);
   else
-    dense_mse_kernel<16><<<blocks, 256, 0, st>>>(u0, ldu, noised, x, wd, bd, pred, loss, du0, lddu, dwd, dbd, pixels,
+    launch_k(dense_mse_kernel<16>, dim3(blocks), dim3(256), 0, st, u0, ldu, noised, x, wd, bd, pred, loss, du0, lddu, dwd, dbd, pixels,
                                                  invN, backward);
   GCT2_CHECK_LAUNCH("dense_mse_kernel");
   return 0;
@@ -461,6 +471,8 @@ struct BiasGradSegs {
 };
 
 __global__ void __launch_bounds__(256) bias_grad_kernel(const __grid_constant__ BiasGradSegs sg) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float red[];  // [rowsPerIter][C]
   int s = 0;
   while (s + 1 < sg.n && (int)blockIdx.x >= sg.firstBlock[s + 1]) ++s;
@@ -546,7 +558,7 @@ int bias_grad_multi(int n, const __nv_bfloat16* const* dz, const int* ld, const 
     }
   }
   sg.firstBlock[n] = block;
-  bias_grad_kernel<<<block, threads, smem, st>>>(sg);
+  launch_k(bias_grad_kernel, dim3(block), dim3(threads), smem, st, sg);
   GCT2_CHECK_LAUNCH("bias_grad_kernel");
   return 0;
 }
@@ -561,6 +573,8 @@ int bias_grad(const __nv_bfloat16* dz, int ld, long long rows, int C, float* db,
 //   alpha = lr*sqrt(1-b2^t)/(1-b1^t), t = step+1 ; m += (g-m)(1-b1) ; v += (g*g-v)(1-b2) ; w -= alpha*m/(sqrt(v)+eps)
 __global__ void adam_prepare_kernel(long long* __restrict__ iterations, float* __restrict__ hyper, float base,
                                     int warmup, float b1, float b2) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long step = *iterations;
   float lr = base;
   if (step < warmup) lr = base * (float)(step + 1) / (float)(warmup + 1);
@@ -576,6 +590,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ w, float
                                                    uint2* __restrict__ wb, long long nvec,
                                                    const float* __restrict__ hyper, float b1, float b2, float eps,
                                                    float gscale, long long* __restrict__ iterations_inc) {
+  pdl_launch_dependents();
+  pdl_wait();
   const float alpha = __ldg(hyper);
   if (iterations_inc != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *iterations_inc += 1;
   const float c1 = 1.f - b1, c2 = 1.f - b2;
@@ -601,7 +617,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ w, float
 
 int adam_prepare(long long* iterations, float* hyper, float base_lr, int warmup_steps, float beta1, float beta2,
                  cudaStream_t st) {
-  adam_prepare_kernel<<<1, 1, 0, st>>>(iterations, hyper, base_lr, warmup_steps, beta1, beta2);
+  launch_k(adam_prepare_kernel, dim3(1), dim3(1), 0, st, iterations, hyper, base_lr, warmup_steps, beta1, beta2);
   GCT2_CHECK_LAUNCH("adam_prepare_kernel");
   return 0;
 }
@@ -617,7 +633,7 @@ int adam_apply(float* w, float* m, float* v, const float* g, __nv_bfloat16* w_bf
   if (nvec == 0) return 0;
   long long blocks = (nvec + 255) / 256;
   if (blocks > g_ew_sms * 8) blocks = g_ew_sms * 8;
-  adam_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<float4*>(w), reinterpret_cast<float4*>(m),
+  launch_k(adam_kernel, dim3((int)blocks), dim3(256), 0, st, reinterpret_cast<float4*>(w), reinterpret_cast<float4*>(m),
                                            reinterpret_cast<float4*>(v), reinterpret_cast<const float4*>(g),
                                            reinterpret_cast<uint2*>(w_bf16), nvec, hyper, beta1, beta2, eps,
                                            grad_scale, iterations_inc);
@@ -634,6 +650,8 @@ int adam_keras(float* w, float* m, float* v, const float* g, __nv_bfloat16* w_bf
 
 // ------------------------------------------------------------------------------------ fp32 -> bf16 shadow
 __global__ void cast_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, long long nvec) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
     const float4 s = __ldg(src + i);
@@ -653,7 +671,7 @@ int cast_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t st
   long long blocks = (nvec + 255) / 256;
   if (blocks > g_ew_sms * 8) blocks = g_ew_sms * 8;
   if (blocks < 1) blocks = 1;
-  cast_bf16_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(dst),
+  launch_k(cast_bf16_kernel, dim3((int)blocks), dim3(256), 0, st, reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(dst),
                                                 nvec);
   GCT2_CHECK_LAUNCH("cast_bf16_kernel");
   return 0;

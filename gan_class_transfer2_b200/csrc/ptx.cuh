@@ -124,6 +124,13 @@ __device__ __forceinline__ void tma_load_5d_mc(void* dst, const CUtensorMap* m, 
       : "memory");
 }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// Every kernel of this library is launched with programmatic stream serialisation: it may start (and run its
+// prologue) while the previous kernel of the stream is still draining, and must call pdl_wait() before it touches
+// global memory; pdl_launch_dependents() lets the next kernel do the same with respect to this one.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
