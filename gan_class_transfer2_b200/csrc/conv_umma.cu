@@ -21,6 +21,7 @@ void set_error(const char* fmt, ...) {
 }
 
 int g_use_pdl = 1;
+static int g_cap_w = 0, g_cap_sp = 0;  // debug keys 9 / 10: CTA budget of wgrad / fprop+dgrad launches (0 = all SMs)
 static long long g_launches = 0;
 void count_launch(int n) { g_launches += n; }
 long long launch_count() { return g_launches; }
@@ -50,6 +51,8 @@ void conv_set_debug(int key, int value) {
   if (key == 1) g_mn_sbo = value;
   if (key == 2) g_verbose = value;
   if (key == 8) g_use_pdl = value ? 0 : 1;  // key 8 != 0 disables programmatic dependent launch
+  if (key == 9) g_cap_w = value;
+  if (key == 10) g_cap_sp = value;
   if (key == 7) {
     if (value && g_dbg == nullptr) cudaMalloc(&g_dbg, (size_t)DBG_MAX_CTAS * 8 * sizeof(unsigned long long));
     if (!value && g_dbg != nullptr) {
@@ -296,6 +299,8 @@ static Choice choose(int mode, int mTiles, int phases, int N, int kTotal, long l
           if (forceCm >= 1 ? cm != forceCm : cm != 1) continue;
           if (forceCn >= 1 ? cn != forceCn : cn != 1) continue;
           int maxCtas = g_num_sms;
+          const int cap = isW ? g_cap_w : g_cap_sp;
+          if (cap > 0 && cap < maxCtas) maxCtas = cap;
           if (cs > 1) {
             const int mc = g_max_clusters[mode][bn_index(BN)][cs];
             if (mc <= 0) continue;
@@ -493,6 +498,10 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
   const int csize = p.cm * p.cn;
   p.numClusterItems = p.numItems / csize;
   int maxCtas = g_num_sms;  // one CTA per SM: the per-SM operand ingest rate, not occupancy, bounds a CTA's speed
+  {
+    const int cap = a.mode == MODE_W ? g_cap_w : g_cap_sp;
+    if (cap > 0 && cap < maxCtas) maxCtas = cap;
+  }
   if (csize > 1) maxCtas = g_max_clusters[a.mode][bn_index(BN)][csize] * csize;
   int grid = p.numItems < maxCtas ? p.numItems : maxCtas;
   grid -= grid % csize;

@@ -40,7 +40,8 @@ long long gct2_launch_count(void);
 /* Test hook (not part of the drop-in surface): key 0/1 override the MN-major UMMA descriptor LBO/SBO bytes,
  * key 2 = verbose plan logging, key 3 = force N tile, key 4 = force split-K, keys 5/6 = force the cluster shape
  * (CTAs along M / along N; 0 = heuristic, 1 = none), key 7 = record per-CTA phase timestamps (gct2_debug_timeline),
- * key 8 != 0 = launch without programmatic dependent launch. */
+ * key 8 != 0 = launch without programmatic dependent launch, keys 9 / 10 = CTA budget of the wgrad / fprop+dgrad
+ * launches (0 = all SMs; lets the concurrent backward chains run on disjoint SM sets). */
 void gct2_debug_set(int key, int value);
 /* Test hook: after gct2_debug_set(7, 1) every tensor-core conv launch records, per CTA, 8 %globaltimer stamps (ns):
  * [0] entry, [1] prologue done, [2] first operands landed, [3] MMAs of the first tile issued, [4] first accumulator
