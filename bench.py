@@ -145,14 +145,15 @@ def instrumented_step(eng, torch, ops):
     """One eager step with every op bracketed by CUDA events (the GPU is kept busy first so that host launch latency
     is not inside the brackets).  Returns {op name: [durations in us]}."""
     saved = eng._save_state()
-    overlap, eng.overlap_wgrad = eng.overlap_wgrad, False  # serialise: per-op durations must be additive
+    overlap = (eng.overlap_wgrad, eng.overlap_adam)
+    eng.overlap_wgrad = eng.overlap_adam = False  # serialise: per-op durations must be additive
     torch.cuda.synchronize()
     torch.cuda._sleep(int(3e7))
     ops.profile_ops(True)
     eng._step_body(False)
     rec = ops.profile_ops(False)
     torch.cuda.synchronize()
-    eng.overlap_wgrad = overlap
+    eng.overlap_wgrad, eng.overlap_adam = overlap
     eng._restore_state(saved)
     out = {}
     for name, s, e in rec:

@@ -42,6 +42,7 @@ _PROTOS = {
     "gct2_launch_count": (c_longlong, []),
     "gct2_debug_set": (None, [c_int, c_int]),
     "gct2_debug_timeline": (c_int, [_P, c_int]),
+    "gct2_debug_trace": (c_int, [_P, c_int]),
     "gct2_noise_images": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "gct2_conv4s2_c3_fprop": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "gct2_conv4s2_c3_wgrad": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),

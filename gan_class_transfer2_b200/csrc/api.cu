@@ -62,6 +62,7 @@ int gct2_init(int device) {
 int gct2_num_sms(void) { return g_sms; }
 long long gct2_launch_count(void) { return launch_count(); }
 
+int gct2_debug_trace(unsigned long long* host, int max_records) { return debug_read_trace(host, max_records); }
 int gct2_debug_timeline(unsigned long long* host, int max_ctas) { return debug_read_timeline(host, max_ctas); }
 
 void gct2_debug_set(int key, int value) {

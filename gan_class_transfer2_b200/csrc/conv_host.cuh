@@ -54,6 +54,7 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
 int conv_init(int device);                       // once per process/device
 int conv_launch(const ConvArgs& a, cudaStream_t stream);
 int debug_read_timeline(unsigned long long* host, int max_ctas);  // test hook, see gct2_debug_timeline
+int debug_read_trace(unsigned long long* host, int max_records);   // test hook, see gct2_debug_trace
 void conv_set_debug(int key, int value);         // test hook: 0 = MN-major LBO, 1 = MN-major SBO, 2 = verbose
 const char* last_error();
 void count_launch(int n = 1);                   // kernels/memsets enqueued by this library (gct2_launch_count)

@@ -46,7 +46,30 @@ int debug_read_timeline(unsigned long long* host, int max_ctas) {
   return n;
 }
 
+static unsigned long long* g_trace_host_ptr = nullptr;
+void trace_set_elementwise(unsigned long long* buf);  // elementwise.cu's copy of the pointer
+int debug_read_trace(unsigned long long* host, int max_records) {
+  if (g_trace_host_ptr == nullptr) return 0;
+  cudaDeviceSynchronize();
+  unsigned long long n = 0;
+  cudaMemcpy(&n, g_trace_host_ptr, sizeof(n), cudaMemcpyDeviceToHost);
+  if (n > TRACE_MAX_RECORDS) n = TRACE_MAX_RECORDS;
+  if ((int)n > max_records) n = max_records;
+  cudaMemcpy(host, g_trace_host_ptr + 1, n * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaMemset(g_trace_host_ptr, 0, sizeof(unsigned long long));
+  return (int)n;
+}
+
 void conv_set_debug(int key, int value) {
+  if (key == 11) {
+    if (value && g_trace_host_ptr == nullptr) {
+      cudaMalloc(&g_trace_host_ptr, (1 + TRACE_MAX_RECORDS * 4) * sizeof(unsigned long long));
+      cudaMemset(g_trace_host_ptr, 0, (1 + TRACE_MAX_RECORDS * 4) * sizeof(unsigned long long));
+    }
+    unsigned long long* dev = value ? g_trace_host_ptr : nullptr;
+    cudaMemcpyToSymbol(g_trace_buf, &dev, sizeof(dev));
+    trace_set_elementwise(dev);
+  }
   if (key == 0) g_mn_lbo = value;
   if (key == 1) g_mn_sbo = value;
   if (key == 2) g_verbose = value;
@@ -160,6 +183,7 @@ __global__ void splitk_finish_kernel(const float* __restrict__ ws, long long spl
                                      long long pixels, int epi, __nv_bfloat16* __restrict__ out, int ldo,
                                      const float* __restrict__ bias, const __nv_bfloat16* __restrict__ act, int ldact,
                                      int maskN, int addOld) {
+  TraceScope trace(20);
   pdl_launch_dependents();
   pdl_wait();
   const int vecPerRow = N / 4;
@@ -202,11 +226,13 @@ __global__ void splitk_finish_kernel(const float* __restrict__ ws, long long spl
     r.y = pack_bf16x2(v.z, v.w);
     *reinterpret_cast<uint2*>(o) = r;
   }
+  trace.end();
 }
 
 // dw[i] = sum over splits of slab[s][i] (weight-gradient split-K), fixed order.
 __global__ void wgrad_reduce_kernel(const float4* __restrict__ ws, long long splitStrideVec, int splits,
                                     float4* __restrict__ dw, long long nvec) {
+  TraceScope trace(21);
   pdl_launch_dependents();
   pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
@@ -218,6 +244,7 @@ __global__ void wgrad_reduce_kernel(const float4* __restrict__ ws, long long spl
     }
     dw[i] = v;
   }
+  trace.end();
 }
 
 // ------------------------------------------------------------------------------------ heuristics

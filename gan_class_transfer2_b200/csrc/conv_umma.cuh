@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + 128, 1) conv_umma_kernel(
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  TraceScope trace(100 + MODE * 10 + BN / 64);
   const unsigned long long t_entry = (p.dbg != nullptr && threadIdx.x == 0) ? globaltimer_ns() : 0ull;
 
   // cluster geometry (cm*cn == 1: plain launch, every mask below is unused)
@@ -457,6 +458,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + 128, 1) conv_umma_kernel(
   __syncthreads();
   if (csize > 1) cluster_sync_all();  // no CTA leaves while a peer may still signal its barriers
   if (threadIdx.x == 0) GCT2_STAMP(6);  // all work of this CTA done
+  trace.end();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);

@@ -12,6 +12,8 @@
 
 namespace gct2 {
 
+void trace_set_elementwise(unsigned long long* buf) { cudaMemcpyToSymbol(g_trace_buf, &buf, sizeof(buf)); }
+
 static int g_ew_sms = 148;
 void elementwise_set_sms(int n) { g_ew_sms = n; }
 
@@ -36,6 +38,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 __global__ void noise_kernel(const float4* __restrict__ x, const float4* __restrict__ eps,
                              const int* __restrict__ t_int, float4* __restrict__ out, int B, int vecPerImage,
                              int steps) {
+  TraceScope trace(1);
   pdl_launch_dependents();
   pdl_wait();
   const long long total = (long long)B * vecPerImage;
@@ -50,6 +53,7 @@ __global__ void noise_kernel(const float4* __restrict__ x, const float4* __restr
     const float4 xv = __ldg(x + i), ev = __ldg(eps + i);
     out[i] = make_float4(xv.x * sa + ev.x * sb, xv.y * sa + ev.y * sb, xv.z * sa + ev.z * sb, xv.w * sa + ev.w * sb);
   }
+  trace.end();
 }
 
 int noise_images(const float* x, const float* eps, const int* t_int, float* noised, int B, int elemsPerImage,
@@ -97,6 +101,7 @@ __global__ void __launch_bounds__(256) step_begin_kernel(const float4* __restric
                                                          float* __restrict__ hyper, float base, int warmup, float b1,
                                                          float b2, float4* __restrict__ gsmall, long long nsmallVec,
                                                          float* __restrict__ loss) {
+  TraceScope trace(2);
   pdl_launch_dependents();
   pdl_wait();
   const long long step = *iterations;
@@ -134,6 +139,7 @@ __global__ void __launch_bounds__(256) step_begin_kernel(const float4* __restric
     if (eps_out != nullptr) eps_out[i] = ev;
     noised[i] = make_float4(xv.x * sa + ev.x * sb, xv.y * sa + ev.y * sb, xv.z * sa + ev.z * sb, xv.w * sa + ev.w * sb);
   }
+  trace.end();
 }
 
 int step_begin(const float* x, float* noised, float* eps_out, int* t_out, int B, int elemsPerImage, int steps,
@@ -179,6 +185,7 @@ __global__ void __launch_bounds__(128) conv_c3_fprop_kernel(const float* __restr
                                                             const float* __restrict__ bias,
                                                             __nv_bfloat16* __restrict__ y, int ldy, int B, int H,
                                                             int W, int Cout) {
+  TraceScope trace(3);
   pdl_launch_dependents();
   pdl_wait();
   __shared__ __align__(16) float patch[C3_P][C3_ROW];
@@ -208,6 +215,7 @@ __global__ void __launch_bounds__(128) conv_c3_fprop_kernel(const float* __restr
       y[pix * ldy + co] = __float2bfloat16(fmaxf(acc, 0.f));
     }
   }
+  trace.end();
 }
 
 int conv4s2_c3_fprop(const float* x, const float* w, const float* bias, __nv_bfloat16* y, int ldy, int B, int H,
@@ -227,6 +235,7 @@ __global__ void __launch_bounds__(128) conv_c3_wgrad_kernel(const float* __restr
                                                             const __nv_bfloat16* __restrict__ dz, int lddz,
                                                             float* __restrict__ dw, float* __restrict__ db, int B,
                                                             int H, int W, int Cout, int numTiles) {
+  TraceScope trace(4);
   pdl_launch_dependents();
   pdl_wait();
   __shared__ __align__(16) float patch[C3_P][C3_ROW];
@@ -261,6 +270,7 @@ __global__ void __launch_bounds__(128) conv_c3_wgrad_kernel(const float* __restr
 #pragma unroll
   for (int k = 0; k < 48; ++k) atomicAdd(dw + k * Cout + co, acc[k]);
   if (db != nullptr) atomicAdd(db + co, accb);
+  trace.end();
 }
 
 int conv4s2_c3_wgrad(const float* x, const __nv_bfloat16* dz, int lddz, float* dw, float* db, int B, int H, int W,
@@ -299,6 +309,7 @@ __global__ void __launch_bounds__(256) dense_mse_kernel(const __nv_bfloat16* __r
                                                         float* __restrict__ loss, __nv_bfloat16* __restrict__ du0,
                                                         int lddu, float* __restrict__ dwd, float* __restrict__ dbd,
                                                         long long pixels, float invN, int backward) {
+  TraceScope trace(5);
   pdl_launch_dependents();
   pdl_wait();
   constexpr int PPW = 32 / LPP;        // pixels per warp iteration
@@ -422,6 +433,7 @@ __global__ void __launch_bounds__(256) dense_mse_kernel(const __nv_bfloat16* __r
         atomicAdd(dbd + (i - CU * 3 - 9), v);
     }
   }
+  trace.end();
 }
 
 int dense_mse(const __nv_bfloat16* u0, int ldu, const float* noised, const float* x, const float* wd,
@@ -471,6 +483,7 @@ struct BiasGradSegs {
 };
 
 __global__ void __launch_bounds__(256) bias_grad_kernel(const __grid_constant__ BiasGradSegs sg) {
+  TraceScope trace(6);
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float red[];  // [rowsPerIter][C]
@@ -513,6 +526,7 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const __grid_constant__ 
     for (int g = 0; g < rpi; ++g) t += red[g * C + c];
     atomicAdd(sg.db[s] + c, t);
   }
+  trace.end();
 }
 
 int bias_grad_multi(int n, const __nv_bfloat16* const* dz, const int* ld, const long long* rows, const int* C,
@@ -573,6 +587,7 @@ int bias_grad(const __nv_bfloat16* dz, int ld, long long rows, int C, float* db,
 //   alpha = lr*sqrt(1-b2^t)/(1-b1^t), t = step+1 ; m += (g-m)(1-b1) ; v += (g*g-v)(1-b2) ; w -= alpha*m/(sqrt(v)+eps)
 __global__ void adam_prepare_kernel(long long* __restrict__ iterations, float* __restrict__ hyper, float base,
                                     int warmup, float b1, float b2) {
+  TraceScope trace(7);
   pdl_launch_dependents();
   pdl_wait();
   const long long step = *iterations;
@@ -583,6 +598,7 @@ __global__ void adam_prepare_kernel(long long* __restrict__ iterations, float* _
   hyper[0] = lr * sqrtf(1.f - b2p) / (1.f - b1p);
   hyper[1] = lr;
   *iterations = step + 1;
+  trace.end();
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ w, float4* __restrict__ m,
@@ -590,6 +606,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ w, float
                                                    uint2* __restrict__ wb, long long nvec,
                                                    const float* __restrict__ hyper, float b1, float b2, float eps,
                                                    float gscale, long long* __restrict__ iterations_inc) {
+  TraceScope trace(8);
   pdl_launch_dependents();
   pdl_wait();
   const float alpha = __ldg(hyper);
@@ -613,6 +630,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ w, float
     o.y = pack_bf16x2(wv.z, wv.w);
     wb[i] = o;
   }
+  trace.end();
 }
 
 int adam_prepare(long long* iterations, float* hyper, float base_lr, int warmup_steps, float beta1, float beta2,
@@ -650,6 +668,7 @@ int adam_keras(float* w, float* m, float* v, const float* g, __nv_bfloat16* w_bf
 
 // ------------------------------------------------------------------------------------ fp32 -> bf16 shadow
 __global__ void cast_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, long long nvec) {
+  TraceScope trace(9);
   pdl_launch_dependents();
   pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
@@ -660,6 +679,7 @@ __global__ void cast_bf16_kernel(const float4* __restrict__ src, uint2* __restri
     o.y = pack_bf16x2(s.z, s.w);
     dst[i] = o;
   }
+  trace.end();
 }
 
 int cast_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t st) {

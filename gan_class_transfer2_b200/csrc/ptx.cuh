@@ -131,6 +131,41 @@ __device__ __forceinline__ void tma_load_5d_mc(void* dst, const CUtensorMap* m, 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// ----------------------------------------------------------------------------- step trace (test hook)
+// When enabled (gct2_debug_set(11, 1)) the first and the last block of every launch append
+// {kernel id, blockIdx | gridDim << 32, t_entry, t_exit} (%globaltimer ns) to a device buffer: a whole-step timeline
+// that shows which launches actually overlap.  One copy of the pointer per translation unit (set by trace_set_*).
+static __device__ unsigned long long* g_trace_buf = nullptr;  // [0] = record count, then 4 u64 per record
+constexpr unsigned long long TRACE_MAX_RECORDS = 8192;
+__device__ __forceinline__ unsigned long long trace_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+struct TraceScope {
+  unsigned long long t0;
+  int id;
+  bool on;
+  __device__ __forceinline__ explicit TraceScope(int kernel_id) : t0(0), id(kernel_id), on(false) {
+    if (g_trace_buf != nullptr && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {
+      on = true;
+      t0 = trace_now();
+    }
+  }
+  __device__ __forceinline__ void end() {
+    if (on) {
+      const unsigned long long slot = atomicAdd(g_trace_buf, 1ull);
+      if (slot < TRACE_MAX_RECORDS) {
+        unsigned long long* r = g_trace_buf + 1 + slot * 4;
+        r[0] = (unsigned long long)id;
+        r[1] = (unsigned long long)blockIdx.x | ((unsigned long long)gridDim.x << 32);
+        r[2] = t0;
+        r[3] = trace_now();
+      }
+    }
+  }
+};
+
 // ----------------------------------------------------------------------------- clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

@@ -181,7 +181,10 @@ class UNetEngine:
         self.dp = dp
         self.use_graph = use_graph
         self.rng_seed = 0x5DEECE66D + 7919 * (dp.rank if dp else 0)  # every rank draws its own noise
-        self.overlap_wgrad = True
+        import os
+        mode = os.environ.get("GCT2_OVERLAP", "all")  # test hook: none | wgrad | adam | all
+        self.overlap_wgrad = mode in ("all", "wgrad")
+        self.overlap_adam = mode in ("all", "adam")
         self._side = torch.cuda.Stream(device=self.device)
         self._side_adam = torch.cuda.Stream(device=self.device)
         self._graph = None
@@ -321,7 +324,7 @@ class UNetEngine:
         cfg, n = self.cfg, self.cfg.octaves
         main = torch.cuda.current_stream()
         sw = self._side if self.overlap_wgrad else main
-        sa = self._side_adam if self.overlap_wgrad else main
+        sa = self._side_adam if self.overlap_adam else main
         dp = self.dp if (self.dp and self.dp.world > 1) else None
         pending = []
 
@@ -350,7 +353,10 @@ class UNetEngine:
                     continue
                 if sa is not main:
                     sa.wait_stream(main)
-                    sa.wait_stream(sw)
+                    if sw is not main:
+                        sa.wait_stream(sw)
+                elif sw is not main:
+                    main.wait_stream(sw)
                 with torch.cuda.stream(sa):
                     if work is not None:
                         work.wait()
@@ -378,6 +384,7 @@ class UNetEngine:
         bucket_done("down0/kernel")
         if sw is not main:
             main.wait_stream(sw)
+        if sa is not main:
             main.wait_stream(sa)
         for work in pending:
             work.wait()

@@ -41,13 +41,20 @@ long long gct2_launch_count(void);
  * key 2 = verbose plan logging, key 3 = force N tile, key 4 = force split-K, keys 5/6 = force the cluster shape
  * (CTAs along M / along N; 0 = heuristic, 1 = none), key 7 = record per-CTA phase timestamps (gct2_debug_timeline),
  * key 8 != 0 = launch without programmatic dependent launch, keys 9 / 10 = CTA budget of the wgrad / fprop+dgrad
- * launches (0 = all SMs; lets the concurrent backward chains run on disjoint SM sets). */
+ * launches (0 = all SMs; lets the concurrent backward chains run on disjoint SM sets), key 11 = whole-step launch
+ * trace (gct2_debug_trace). */
 void gct2_debug_set(int key, int value);
 /* Test hook: after gct2_debug_set(7, 1) every tensor-core conv launch records, per CTA, 8 %globaltimer stamps (ns):
  * [0] entry, [1] prologue done, [2] first operands landed, [3] MMAs of the first tile issued, [4] first accumulator
  * complete, [5] first epilogue done, [6] CTA done.  Synchronises the device and copies the stamps of the most
  * recent launch (up to max_ctas CTAs) to `host`; returns the number of CTAs. */
 int gct2_debug_timeline(unsigned long long* host, int max_ctas);
+/* Test hook: after gct2_debug_set(11, 1) the first and last block of EVERY launch of this library append
+ * {kernel id, blockIdx | gridDim << 32, entry ns, exit ns}; this call synchronises, copies up to max_records records
+ * (4 x u64 each) to `host`, clears the buffer and returns the count.  Kernel ids: 1 noise, 2 step_begin, 3/4 down0
+ * fprop/wgrad, 5 dense+mse, 6 bias grads, 7 adam_prepare, 8 adam, 9 cast, 20 split-K finish, 21 wgrad reduce,
+ * 100 + 10*mode + BN/64 tensor-core conv (mode 0 strided, 1 phase, 2 wgrad). */
+int gct2_debug_trace(unsigned long long* host, int max_records);
 
 /* train.py:224-234 + :85-93 -- Trainer.call noising with alpha_dash:
  *   noised = x*sqrt(abar(t)) + eps*sqrt(1-abar(t)), abar(t) = (1 - t/(steps+1))^2 * 0.25.
