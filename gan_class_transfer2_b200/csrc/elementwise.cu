@@ -231,7 +231,9 @@ int conv4s2_c3_fprop(const float* x, const float* w, const float* bias, __nv_bfl
 }
 
 // dW[ky,kx,c,co] = sum_pix x[pix@tap, c] * dz[pix, co];  db[co] = sum_pix dz[pix, co]
-__global__ void __launch_bounds__(128) conv_c3_wgrad_kernel(const float* __restrict__ x,
+// 256 threads: thread = (output channel, half of the tile's rows).  A block walks several tiles, the two halves are
+// combined through shared memory and only then added to dw/db: 49 atomics per channel per BLOCK.
+__global__ void __launch_bounds__(256) conv_c3_wgrad_kernel(const float* __restrict__ x,
                                                             const __nv_bfloat16* __restrict__ dz, int lddz,
                                                             float* __restrict__ dw, float* __restrict__ db, int B,
                                                             int H, int W, int Cout, int numTiles) {
@@ -239,9 +241,11 @@ __global__ void __launch_bounds__(128) conv_c3_wgrad_kernel(const float* __restr
   pdl_launch_dependents();
   pdl_wait();
   __shared__ __align__(16) float patch[C3_P][C3_ROW];
+  __shared__ float comb[49][128];
   const int Ho = H / 2, Wo = W / 2;
   const int tilesX = Wo / C3_T, tilesY = Ho / C3_T;
-  const int co = blockIdx.y * blockDim.x + threadIdx.x;
+  const int lane_c = threadIdx.x & 127, half = threadIdx.x >> 7;
+  const int co = blockIdx.y * 128 + lane_c;
   float acc[48];
 #pragma unroll
   for (int k = 0; k < 48; ++k) acc[k] = 0.f;
@@ -252,24 +256,34 @@ __global__ void __launch_bounds__(128) conv_c3_wgrad_kernel(const float* __restr
     __syncthreads();
     c3_load_patch(patch, x, b, oy0, ox0, H, W);
     __syncthreads();
-    for (int py = 0; py < C3_T; ++py) {
+    for (int py = half * (C3_T / 2); py < (half + 1) * (C3_T / 2); ++py) {
+      float g[C3_T];
+#pragma unroll
+      for (int px = 0; px < C3_T; ++px)  // the row's 8 gradients are requested together
+        g[px] = __bfloat162float(dz[(((long long)b * Ho + oy0 + py) * Wo + ox0 + px) * lddz + co]);
 #pragma unroll
       for (int px = 0; px < C3_T; ++px) {
-        const long long pix = ((long long)b * Ho + oy0 + py) * Wo + ox0 + px;
-        const float g = __bfloat162float(dz[pix * lddz + co]);
-        accb += g;
+        accb += g[px];
 #pragma unroll
         for (int ky = 0; ky < 4; ++ky) {
           const float* row = &patch[2 * py + ky][2 * px * 3];
 #pragma unroll
-          for (int j = 0; j < 12; ++j) acc[ky * 12 + j] = fmaf(row[j], g, acc[ky * 12 + j]);
+          for (int j = 0; j < 12; ++j) acc[ky * 12 + j] = fmaf(row[j], g[px], acc[ky * 12 + j]);
         }
       }
     }
   }
+  if (half == 1) {
 #pragma unroll
-  for (int k = 0; k < 48; ++k) atomicAdd(dw + k * Cout + co, acc[k]);
-  if (db != nullptr) atomicAdd(db + co, accb);
+    for (int k = 0; k < 48; ++k) comb[k][lane_c] = acc[k];
+    comb[48][lane_c] = accb;
+  }
+  __syncthreads();
+  if (half == 0) {
+#pragma unroll
+    for (int k = 0; k < 48; ++k) atomicAdd(dw + k * Cout + co, acc[k] + comb[k][lane_c]);
+    if (db != nullptr) atomicAdd(db + co, accb + comb[48][lane_c]);
+  }
   trace.end();
 }
 
@@ -288,9 +302,13 @@ int conv4s2_c3_wgrad(const float* x, const __nv_bfloat16* dz, int lddz, float* d
     }
   }
   const int numTiles = B * (H / 2 / C3_T) * (W / 2 / C3_T);
-  int gx = numTiles < 2 * g_ew_sms ? numTiles : 2 * g_ew_sms;
+  // few blocks, several tiles each: the atomics per block (49 x 128) are the cost that does not shrink with the tile count
+  int gx = numTiles / 4;
+  if (gx < g_ew_sms / 2) gx = g_ew_sms / 2;
+  if (gx > 2 * g_ew_sms) gx = 2 * g_ew_sms;
+  if (gx > numTiles) gx = numTiles;
   dim3 grid(gx, Cout / 128);
-  launch_k(conv_c3_wgrad_kernel, dim3(grid), dim3(128), 0, st, x, dz, lddz, dw, db, B, H, W, Cout, numTiles);
+  launch_k(conv_c3_wgrad_kernel, dim3(grid), dim3(256), 0, st, x, dz, lddz, dw, db, B, H, W, Cout, numTiles);
   GCT2_CHECK_LAUNCH("conv_c3_wgrad_kernel");
   return 0;
 }
