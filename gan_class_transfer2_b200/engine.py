@@ -185,9 +185,6 @@ class UNetEngine:
         mode = os.environ.get("GCT2_OVERLAP", "all")  # test hook: none | wgrad | adam | all
         self.overlap_wgrad = mode in ("all", "wgrad")
         self.overlap_adam = mode in ("all", "adam")
-        # The critical chain (forward, dgrads) runs at high priority so that its CTAs get an SM the moment one frees up;
-        # the weight-gradient and Adam chains fill in behind it at normal priority.
-        self._main = torch.cuda.Stream(device=self.device, priority=-1)
         self._side = torch.cuda.Stream(device=self.device)
         self._side_adam = torch.cuda.Stream(device=self.device)
         self._graph = None
@@ -401,13 +398,6 @@ class UNetEngine:
 
     # ------------------------------------------------------------------------------------------ public steps
     def _step_body(self, draw: bool) -> None:
-        caller = torch.cuda.current_stream()
-        self._main.wait_stream(caller)
-        with torch.cuda.stream(self._main):
-            self._step_body_main(draw)
-        caller.wait_stream(self._main)
-
-    def _step_body_main(self, draw: bool) -> None:
         cfg = self.cfg
         inv_n = 1.0 / (self.global_batch * cfg.size * cfg.size * 3)
         if draw:
