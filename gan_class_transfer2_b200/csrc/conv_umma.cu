@@ -21,6 +21,9 @@ void set_error(const char* fmt, ...) {
 }
 
 int g_use_pdl = 1;
+static int g_fuse_finish = 1;          // debug key 12 != 0 disables the in-kernel split-K finish
+static int* g_cnt = nullptr;           // rendezvous counters of the fused finish: [FUSE_MAX_TILES][2], zero at rest
+constexpr int FUSE_MAX_TILES = 4096;
 static int g_cap_w = 0, g_cap_sp = 0;  // debug keys 9 / 10: CTA budget of wgrad / fprop+dgrad launches (0 = all SMs)
 static long long g_launches = 0;
 void count_launch(int n) { g_launches += n; }
@@ -75,6 +78,7 @@ void conv_set_debug(int key, int value) {
   if (key == 2) g_verbose = value;
   if (key == 8) g_use_pdl = value ? 0 : 1;  // key 8 != 0 disables programmatic dependent launch
   if (key == 9) g_cap_w = value;
+  if (key == 12) g_fuse_finish = value ? 0 : 1;
   if (key == 10) g_cap_sp = value;
   if (key == 7) {
     if (value && g_dbg == nullptr) cudaMalloc(&g_dbg, (size_t)DBG_MAX_CTAS * 8 * sizeof(unsigned long long));
@@ -130,6 +134,11 @@ int conv_init(int device) {
   rc |= set_attr<MODE_W, 64>() | set_attr<MODE_W, 128>() | set_attr<MODE_W, 256>();
   if (rc) return 1;
   query_all_clusters();
+  if (cudaMalloc(&g_cnt, (size_t)FUSE_MAX_TILES * 2 * sizeof(int)) != cudaSuccess ||
+      cudaMemset(g_cnt, 0, (size_t)FUSE_MAX_TILES * 2 * sizeof(int)) != cudaSuccess) {
+    set_error("could not allocate the split-K rendezvous counters");
+    return 1;
+  }
   g_inited = true;
   return 0;
 }
@@ -315,7 +324,9 @@ static Choice choose(int mode, int mTiles, int phases, int N, int kTotal, long l
     for (int splits = 1; splits <= 64; splits *= 2) {
       if (kTotal % splits) break;
       if (forceSplits && splits != forceSplits) continue;
-      if (splits > 1 && slabBytes * splits > wsBytes) break;  // partial slabs must fit the caller's workspace
+      // partial slabs must fit the caller's workspace (tile-major slabs of the fused finish hold whole 128-row tiles)
+      const size_t tileSlab = isW ? 0 : (size_t)mTiles * phases * 128 * N * sizeof(float);
+      if (splits > 1 && (slabBytes > tileSlab ? slabBytes : tileSlab) * splits > wsBytes) break;
       const int kIters = kTotal / splits;
       for (int a = 0; a < 4; ++a) {
         for (int b = 0; b < 3; ++b) {
@@ -467,6 +478,13 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
       p.epi = EPI_WS_SLAB;
       p.ws = a.ws;
       p.wsSplitStride = (long long)a.B * p.Hout * p.Wout * N;
+      p.numTiles = phases * p.nTiles * pixTiles;
+      // finish inside the launch when every item has its own resident CTA (so the splits of a tile can wait for each
+      // other); otherwise a finishing kernel sums the slabs
+      p.fused = (g_fuse_finish && c.cm * c.cn == 1 && p.numItems <= g_num_sms && p.numTiles <= FUSE_MAX_TILES &&
+                 !(g_cap_sp > 0 && p.numItems > g_cap_sp)) ? 1 : 0;
+      p.realEpi = a.epi;
+      p.cnt = g_cnt;
     }
     if (a.mode == MODE_S) {
       p.ldG = a.ldHi;
@@ -555,7 +573,7 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     return 1;
   }
   count_launch();
-  if (a.mode != MODE_W && p.splits > 1) {
+  if (a.mode != MODE_W && p.splits > 1 && !p.fused) {
     const long long pixels = (long long)a.B * p.Hout * p.Wout;
     const long long total = pixels * (p.N / 4);
     int blocks = (int)((total + 255) / 256);

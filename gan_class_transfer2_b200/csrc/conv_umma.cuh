@@ -25,6 +25,15 @@ namespace gct2 {
 enum : int { MODE_S = 0, MODE_P = 1, MODE_W = 2 };
 enum : int { EPI_BIAS_RELU = 0, EPI_DGRAD = 1, EPI_WS_SLAB = 2, EPI_WGRAD = 3 };
 
+__device__ __forceinline__ void epi_bar_sync(int nthreads) {  // named barrier 1: epilogue warps only
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 struct ConvParams {
   int B, Hlo, Wlo;             // lo-res spatial extent (hi-res = 2x)
   int Wt, Ht, Nb;              // pixel-tile geometry; rows = Nb*Ht*Wt (128 for S/P, 64 for W)
@@ -42,6 +51,10 @@ struct ConvParams {
   int cm, cn;                  // thread-block cluster = cm x cn CTAs: cm consecutive M tiles x cn consecutive N tiles of
                                // one (phase, split); A tiles are TMA-multicast along cn, B tiles along cm
   int numClusterItems;         // numItems / (cm*cn)
+  int fused;                   // split-K finished inside this launch (tile-major slabs + arrive/depart counters)
+  int realEpi;                 // fused: the epilogue to apply after the slabs are summed (EPI_BIAS_RELU / EPI_DGRAD)
+  int numTiles;                // fused: phases * nTiles * mTiles
+  int* cnt;                    // fused: [numTiles][2] arrive / depart counters, zero between launches
   unsigned long long* dbg;     // test hook: per-CTA phase timestamps (8 x u64 per CTA, %globaltimer ns) or nullptr
   // epilogue
   int epi;
@@ -111,11 +124,8 @@ __host__ __device__ constexpr int kConvThreads() {
   return 128 + 32 * kEpilogueWarps<BN>();
 }
 
-// Register budget: the launch bound is declared 128 threads above the real block size so that ptxas caps the wide
-// variants at 80 registers per thread (640 x 80 = 51 K of the SM's 64 K): the rest of the register file is what lets a
-// 256-thread block of an HBM-bound kernel (Adam, bias gradients) share the SM with a resident conv CTA.
 template <int MODE, int BN>
-__global__ void __launch_bounds__(kConvThreads<BN>() + 128, 1) conv_umma_kernel(const __grid_constant__ CUtensorMap mapA,
+__global__ void __launch_bounds__(kConvThreads<BN>(), 1) conv_umma_kernel(const __grid_constant__ CUtensorMap mapA,
                                                         const __grid_constant__ CUtensorMap mapB,
                                                         const ConvParams p) {
   constexpr int A_BYTES = 128 * 128;  // 128 rows x 64 bf16 (S/P) or 2 blocks of 64 pixels x 64 channels (W)
@@ -336,6 +346,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + 128, 1) conv_umma_kernel(
       for (int item = clusterId; item < p.numClusterItems; item += numClusters) {
         const WorkItem w = decode_item<MODE>(p, item, rm, rn);
         const int n0 = w.nt * BN + cgrp * COLS;
+        const int tileId = (w.ph * p.nTiles + w.nt) * p.mTiles + w.mt;
         // row -> output location
         bool valid = true;
         long long pix = 0;
@@ -421,7 +432,11 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + 128, 1) conv_umma_kernel(
             // a fixed order, so the step is bit-reproducible)
             tmem_ld_wait();
             if (valid) {
-              float4* dst = reinterpret_cast<float4*>(p.ws + (long long)w.split * p.wsSplitStride + pix * p.N + n);
+              // fused finish: tile-major slab [split][tile][row][col] (compact, read back coalesced below);
+              // finishing kernel: pixel-major slab [split][pixel][N]
+              float4* dst = reinterpret_cast<float4*>(
+                  p.fused ? p.ws + (((long long)w.split * p.numTiles + tileId) * 128 + r) * BN + (n - w.nt * BN)
+                          : p.ws + (long long)w.split * p.wsSplitStride + pix * p.N + n);
 #pragma unroll
               for (int g = 0; g < 8; ++g)
                 dst[g] = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
@@ -446,6 +461,78 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + 128, 1) conv_umma_kernel(
         }
         tc_fence_before();
         __syncwarp();
+        if (p.fused) {
+          // ---- split-K finished in place.  Every split of this tile has its own CTA, all resident at once (the
+          // host only fuses when the grid holds one item per CTA), so they can wait for each other: once all `splits`
+          // partial tiles are in the slabs, split s sums rows [s*R, (s+1)*R) over the slabs in split order (bit-
+          // reproducible), applies the real epilogue and writes the bf16 output -- coalesced, no extra launch.
+          constexpr int NT = NE * 32;
+          const int et = (warp - 4) * 32 + lane;
+          __threadfence();
+          epi_bar_sync(NT);
+          if (et == 0) {
+            atomicAdd(p.cnt + 2 * tileId, 1);
+            uint32_t spins = 0;
+            while (ld_acquire_gpu(p.cnt + 2 * tileId) < p.splits) {
+              __nanosleep(40);
+              if (++spins > (1u << 22)) {
+                printf("gct2: split-K rendezvous watchdog block %d tile %d\n", (int)blockIdx.x, tileId);
+                __trap();
+              }
+            }
+          }
+          epi_bar_sync(NT);
+          const int R = 128 / p.splits, vecPerRow = BN / 4;
+          const float* slab0 = p.ws + ((long long)tileId * 128) * BN;
+          const long long splitStride = (long long)p.numTiles * 128 * BN;
+          for (int idx = et; idx < R * vecPerRow; idx += NT) {
+            const int rr = w.split * R + idx / vecPerRow, c4 = (idx % vecPerRow) * 4;
+            const int xl = rr % p.Wt, yl = (rr / p.Wt) % p.Ht, bl = rr / (p.Wt * p.Ht);
+            const int b = (w.mt / tilesXY) * p.Nb + bl;
+            if (b >= p.B) continue;
+            int oy = ((w.mt / p.tilesX) % p.tilesY) * p.Ht + yl, ox = (w.mt % p.tilesX) * p.Wt + xl;
+            if (MODE == MODE_P) {
+              oy = 2 * oy + (w.ph >> 1);
+              ox = 2 * ox + (w.ph & 1);
+            }
+            const long long opix = ((long long)b * p.Hout + oy) * p.Wout + ox;
+            const float* sp = slab0 + (long long)rr * BN + c4;
+            float4 v = __ldcg(reinterpret_cast<const float4*>(sp));
+            for (int sidx = 1; sidx < p.splits; ++sidx) {
+              const float4 u = __ldcg(reinterpret_cast<const float4*>(sp + sidx * splitStride));
+              v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+            }
+            const int nn = w.nt * BN + c4;
+            __nv_bfloat16* o = p.out + opix * p.ldo + nn;
+            if (p.realEpi == EPI_BIAS_RELU) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + nn));
+              v.x = fmaxf(v.x + bb.x, 0.f); v.y = fmaxf(v.y + bb.y, 0.f);
+              v.z = fmaxf(v.z + bb.z, 0.f); v.w = fmaxf(v.w + bb.w, 0.f);
+            } else {
+              if (p.addOld) {
+                const uint2 old = *reinterpret_cast<const uint2*>(o);
+                v.x += bf16_lo(old.x); v.y += bf16_hi(old.x); v.z += bf16_lo(old.y); v.w += bf16_hi(old.y);
+              }
+              if (nn < p.maskN) {
+                const uint2 am = __ldg(reinterpret_cast<const uint2*>(p.act + opix * p.ldact + nn));
+                v.x = bf16_lo(am.x) > 0.f ? v.x : 0.f; v.y = bf16_hi(am.x) > 0.f ? v.y : 0.f;
+                v.z = bf16_lo(am.y) > 0.f ? v.z : 0.f; v.w = bf16_hi(am.y) > 0.f ? v.w : 0.f;
+              }
+            }
+            uint2 res;
+            res.x = pack_bf16x2(v.x, v.y);
+            res.y = pack_bf16x2(v.z, v.w);
+            *reinterpret_cast<uint2*>(o) = res;
+          }
+          epi_bar_sync(NT);
+          if (et == 0) {
+            const int old = atomicAdd(p.cnt + 2 * tileId + 1, 1);
+            if (old == p.splits - 1) {  // every split has passed the rendezvous: re-arm the counters
+              p.cnt[2 * tileId] = 0;
+              p.cnt[2 * tileId + 1] = 0;
+            }
+          }
+        }
         if (item == clusterId && warp == 4 && lane == 0) GCT2_STAMP(5);  // first epilogue (of warp 4) done
         if (lane == 0) mbar_arrive(&tempty[acc]);
         acc ^= 1;

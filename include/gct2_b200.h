@@ -42,7 +42,7 @@ long long gct2_launch_count(void);
  * (CTAs along M / along N; 0 = heuristic, 1 = none), key 7 = record per-CTA phase timestamps (gct2_debug_timeline),
  * key 8 != 0 = launch without programmatic dependent launch, keys 9 / 10 = CTA budget of the wgrad / fprop+dgrad
  * launches (0 = all SMs; lets the concurrent backward chains run on disjoint SM sets), key 11 = whole-step launch
- * trace (gct2_debug_trace). */
+ * trace (gct2_debug_trace), key 12 != 0 = finish split-K with a separate kernel instead of inside the launch. */
 void gct2_debug_set(int key, int value);
 /* Test hook: after gct2_debug_set(7, 1) every tensor-core conv launch records, per CTA, 8 %globaltimer stamps (ns):
  * [0] entry, [1] prologue done, [2] first operands landed, [3] MMAs of the first tile issued, [4] first accumulator
@@ -76,7 +76,10 @@ int gct2_conv4s2_c3_wgrad(const float* x, const uint16_t* dz, int lddz, float* d
  * x bf16 [B,H,W,Cin] stride ldx; y bf16 [B,H/2,W/2,Cout] stride ldy. tcgen05 implicit GEMM (strided form).
  * ws: fp32 split-K scratch (contents irrelevant on entry and exit).  Split-K is used only when `splits` partial
  * outputs (splits * B*(H/2)*(W/2)*Cout floats) fit in ws_bytes; partials are summed in a fixed order, so results are
- * bit-reproducible.  ws may be NULL (no split-K).  The same holds for every ws argument below. */
+ * bit-reproducible.  ws may be NULL (no split-K).  The same holds for every ws argument below.
+ * Concurrency: when every work item has its own resident CTA, split-K is finished inside the launch (the CTAs of a
+ * tile wait for each other), so fprop/dgrad calls must not run concurrently with each other on different streams
+ * of one device; wgrad calls never wait and may overlap anything. */
 int gct2_conv4s2_fprop(const uint16_t* x, int ldx, const uint16_t* w, const float* bias, uint16_t* y, int ldy,
                        int B, int H, int W, int Cin, int Cout, float* ws, size_t ws_bytes, void* stream);
 /* Backward-data of DownShuffle: dx[b,iy,ix,ci] (+)= sum dy[b,oy,ox,co]*w[ky,kx,ci,co], then ReLU-masked by the

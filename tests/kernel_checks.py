@@ -425,19 +425,20 @@ EW_CASES = [
 ]
 
 
-def forced(fn, BN=0, splits=0, cm=0, cn=0, **kw):
+def forced(fn, BN=0, splits=0, cm=0, cn=0, nofuse=0, **kw):
     """Runs a conv check with the tile width / split-K factor pinned (test hook gct2_debug_set keys 3, 4) so that
     every template instantiation and the split-K finishing passes are exercised regardless of the heuristics."""
     from gan_class_transfer2_b200 import _lib
     lib = _lib.init(0)
-    for key, val in ((3, BN), (4, splits), (5, cm), (6, cn)):
+    for key, val in ((3, BN), (4, splits), (5, cm), (6, cn), (12, nofuse)):
         lib.gct2_debug_set(key, val)
     try:
         m = fn(**kw)
     finally:
-        for key in (3, 4, 5, 6):
+        for key in (3, 4, 5, 6, 12):
             lib.gct2_debug_set(key, 0)
-    m["name"] += f" [BN={BN or 'auto'} splits={splits or 'auto'} cluster={cm or 'auto'}x{cn or 'auto'}]"
+    m["name"] += (f" [BN={BN or 'auto'} splits={splits or 'auto'} cluster={cm or 'auto'}x{cn or 'auto'}"
+                  f"{' finish-kernel' if nofuse else ''}]")
     return m
 
 
@@ -457,6 +458,14 @@ FORCED_CASES = [
     (check_conv_wgrad, dict(B=4, H=32, Cin=128, Cout=256), dict(BN=256, splits=2)),
     (check_convT_wgrad, dict(B=4, H=16, Cin=256, Cout=64), dict(BN=64, splits=4)),
     (check_convT_wgrad, dict(B=4, H=16, Cin=256, Cout=128), dict(BN=256, splits=16)),
+    # split-K finished by the separate kernel (the fallback when a CTA owns more than one work item)
+    (check_conv_fprop, dict(B=2, H=16, Cin=128, Cout=256), dict(BN=128, splits=4, nofuse=1)),
+    (check_convT_fprop, dict(B=2, H=8, Cin=128, Cout=256), dict(BN=256, splits=8, nofuse=1)),
+    (check_conv_dgrad, dict(B=2, H=16, Cin=256, Cout=128, add_old=True), dict(BN=256, splits=4, nofuse=1)),
+    (check_convT_dgrad, dict(B=2, H=8, Cin=256, Cout=128), dict(BN=64, splits=32, nofuse=1)),
+    # split-K with a ragged batch: rows of the tile beyond the batch are neither stored nor finished
+    (check_conv_fprop, dict(B=3, H=8, Cin=256, Cout=128), dict(BN=64, splits=16)),
+    (check_convT_dgrad, dict(B=3, H=4, Cin=128, Cout=256, mask_channels=64), dict(BN=128, splits=8)),
     # thread-block clusters with TMA multicast (A along cn, B along cm); the last ones loop persistently
     (check_conv_fprop, dict(B=2, H=32, Cin=128, Cout=256), dict(BN=64, splits=1, cm=1, cn=1)),
     (check_conv_fprop, dict(B=2, H=32, Cin=128, Cout=256), dict(BN=64, splits=1, cm=2, cn=1)),

@@ -27,8 +27,8 @@ def test_hbm_bound_kernels_match_oracle(case):
     assert m.get("pad_intact", True), m
 
 
-@pytest.mark.parametrize("case", K.FORCED_CASES, ids=lambda c: c[0].__name__.replace("check_", "") + "-BN%d-s%d-c%dx%d" % (
-    c[2]["BN"], c[2]["splits"], c[2].get("cm", 0), c[2].get("cn", 0)))
+@pytest.mark.parametrize("case", K.FORCED_CASES, ids=lambda c: c[0].__name__.replace("check_", "") + "-BN%d-s%d-c%dx%d%s" % (
+    c[2]["BN"], c[2]["splits"], c[2].get("cm", 0), c[2].get("cn", 0), "-finishkernel" if c[2].get("nofuse") else ""))
 def test_every_tile_width_and_split_k_path(case):
     fn, kw, force = case
     m = K.forced(fn, **force, **kw)
