@@ -333,9 +333,10 @@ static Choice choose(int mode, int mTiles, int phases, int N, int kTotal, long l
           const int cm = cms[a], cn = cns[b], cs = cm * cn;
           if (cs > 8 || mTiles % cm || nTiles % cn) continue;
           if (isW && cs > 1) continue;
-          // clusters cost 1.3 us per launch and do not raise the per-SM ingest rate: only on request (debug keys 5/6)
-          if (forceCm >= 1 ? cm != forceCm : cm != 1) continue;
-          if (forceCn >= 1 ? cn != forceCn : cn != 1) continue;
+          // clusters cost 1.3 us per launch and do not raise the per-SM ingest rate; they pay when the launch is long
+          // and all SMs together pull more than L2 can deliver (large batches): multicast divides the L2 reads
+          if (forceCm >= 1 && cm != forceCm) continue;
+          if (forceCn >= 1 && cn != forceCn) continue;
           int maxCtas = g_num_sms;
           const int cap = isW ? g_cap_w : g_cap_sp;
           if (cap > 0 && cap < maxCtas) maxCtas = cap;
@@ -347,7 +348,9 @@ static Choice choose(int mode, int mTiles, int phases, int N, int kTotal, long l
           const long long items = (long long)mTiles * phases * (isW ? 16 : 1) * nTiles * splits;
           const long long active = items < maxCtas ? items : maxCtas;
           const long long rounds = (items + active - 1) / active;
-          const double tk = 2800.0 / stages_for(BN) + (16384.0 + BN * 128.0) / 153.0;
+          double tk = 2800.0 / stages_for(BN) + (16384.0 + BN * 128.0) / 153.0;
+          const double l2 = (16384.0 / cn + BN * 128.0 / cm) * (double)active / 4800.0;  // chip-wide L2 read rate
+          if (l2 > tk) tk = l2;
           double epi = 2000.0 + 8.0 * BN;
           if (splits == 1 && dgradEpi) epi *= 1.6;
           const double main = kIters * tk;
