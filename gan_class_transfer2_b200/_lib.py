@@ -12,7 +12,7 @@ import subprocess
 from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgct2_b200.so")
+LIB_PATH = os.environ.get("GCT2_LIB") or os.path.join(_HERE, "libgct2_b200.so")  # GCT2_LIB: test hook (A/B builds)
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 _lib = None

@@ -74,6 +74,8 @@ void gct2_debug_set(int key, int value) {
     g_force_cm = value;
   else if (key == 6)
     g_force_cn = value;
+  else if (key == 13)
+    elementwise_set_debug(key, value);
   else
     conv_set_debug(key, value);
 }

@@ -333,10 +333,10 @@ static Choice choose(int mode, int mTiles, int phases, int N, int kTotal, long l
           const int cm = cms[a], cn = cns[b], cs = cm * cn;
           if (cs > 8 || mTiles % cm || nTiles % cn) continue;
           if (isW && cs > 1) continue;
-          // clusters cost 1.3 us per launch and do not raise the per-SM ingest rate; they pay when the launch is long
-          // and all SMs together pull more than L2 can deliver (large batches): multicast divides the L2 reads
-          if (forceCm >= 1 && cm != forceCm) continue;
-          if (forceCn >= 1 && cn != forceCn) continue;
+          // clusters cost 1.3 us per launch and do not raise the per-SM ingest rate; measured slower than plain launches
+          // at 1, 8 and 32 images per GPU (profiles/README.md), so they are used only on request (debug keys 5/6)
+          if (forceCm >= 1 ? cm != forceCm : cm != 1) continue;
+          if (forceCn >= 1 ? cn != forceCn : cn != 1) continue;
           int maxCtas = g_num_sms;
           const int cap = isW ? g_cap_w : g_cap_sp;
           if (cap > 0 && cap < maxCtas) maxCtas = cap;

@@ -124,8 +124,11 @@ __host__ __device__ constexpr int kConvThreads() {
   return 128 + 32 * kEpilogueWarps<BN>();
 }
 
+#ifndef GCT2_CONV_EXTRA_BOUND
+#define GCT2_CONV_EXTRA_BOUND 0
+#endif
 template <int MODE, int BN>
-__global__ void __launch_bounds__(kConvThreads<BN>(), 1) conv_umma_kernel(const __grid_constant__ CUtensorMap mapA,
+__global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1) conv_umma_kernel(const __grid_constant__ CUtensorMap mapA,
                                                         const __grid_constant__ CUtensorMap mapB,
                                                         const ConvParams p) {
   constexpr int A_BYTES = 128 * 128;  // 128 rows x 64 bf16 (S/P) or 2 blocks of 64 pixels x 64 channels (W)

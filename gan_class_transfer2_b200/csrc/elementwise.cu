@@ -15,6 +15,10 @@ namespace gct2 {
 void trace_set_elementwise(unsigned long long* buf) { cudaMemcpyToSymbol(g_trace_buf, &buf, sizeof(buf)); }
 
 static int g_ew_sms = 148;
+static int g_adam_blocks = 0;  // debug key 13: grid cap of the Adam kernel (0 = 8 blocks per SM)
+void elementwise_set_debug(int key, int value) {
+  if (key == 13) g_adam_blocks = value;
+}
 void elementwise_set_sms(int n) { g_ew_sms = n; }
 
 #define GCT2_CHECK_LAUNCH(name)                                       \
@@ -668,7 +672,8 @@ int adam_apply(float* w, float* m, float* v, const float* g, __nv_bfloat16* w_bf
   const long long nvec = n / 4;
   if (nvec == 0) return 0;
   long long blocks = (nvec + 255) / 256;
-  if (blocks > g_ew_sms * 8) blocks = g_ew_sms * 8;
+  const long long cap = g_adam_blocks > 0 ? g_adam_blocks : (long long)g_ew_sms * 8;
+  if (blocks > cap) blocks = cap;
   launch_k(adam_kernel, dim3((int)blocks), dim3(256), 0, st, reinterpret_cast<float4*>(w), reinterpret_cast<float4*>(m),
                                            reinterpret_cast<float4*>(v), reinterpret_cast<const float4*>(g),
                                            reinterpret_cast<uint2*>(w_bf16), nvec, hyper, beta1, beta2, eps,
