@@ -289,9 +289,22 @@ def main():
                 "step_frac": value / world * GFLOP_PER_IMAGE * 1e9 / 1e12 / pk["bf16_sustained"],
                 "per_op_us": {k: round(sum(v), 1) for k, v in prof.items()}}
 
+    def teardown():
+        """Captured NCCL collectives keep the communicator busy: drop the graphs first, and never let a stuck
+        communicator teardown keep the ranks (and the driver's clock) waiting."""
+        if dist is None:
+            return
+        sys.stdout.flush()
+        eng.release_graphs()
+        barrier()
+        timer = threading.Timer(20.0, lambda: os._exit(0))
+        timer.daemon = True
+        timer.start()
+        dist.destroy_process_group()
+        timer.cancel()
+
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        teardown()
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -307,8 +320,7 @@ def main():
             "cuda_graph": not args.no_graph, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "final_loss": final_loss}
     print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    teardown()
 
 
 if __name__ == "__main__":

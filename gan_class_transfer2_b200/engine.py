@@ -191,7 +191,14 @@ class UNetEngine:
         self._graph_launches = 0
         dev, n, S, B = self.device, cfg.octaves, cfg.size, batch
         from . import _lib
-        _lib.init(self.device.index or 0)
+        lib = _lib.init(self.device.index or 0)
+        if dp is not None and dp.world > 1:
+            # The in-launch split-K finish makes the CTAs of a conv launch wait for one another, which is only safe
+            # while every other kernel on the GPU terminates on its own.  An NCCL kernel waits for its peer GPU and
+            # must itself be fully resident: a half-placed conv launch and a half-placed NCCL kernel can then hold all
+            # 148 SMs between them forever (seen as a hang of the captured 2-GPU step).  Data-parallel steps finish
+            # split-K with the separate finishing kernel instead.
+            lib.gct2_debug_set(12, 1)
 
         # ---- parameters, flat in Keras order
         self.specs = variable_specs(cfg)
@@ -464,6 +471,13 @@ class UNetEngine:
             self._graph_launches = ops.launch_count() - before
             self._graph[draw] = graph
         self._graph[draw].replay()
+
+    def release_graphs(self) -> None:
+        """Drops the captured step graphs.  Data-parallel callers do this before ``destroy_process_group``: NCCL keeps a
+        communicator alive (and its destruction waits) while a CUDA graph that captured one of its collectives
+        exists -- seen as a hang at teardown of the captured 2-GPU step."""
+        self._graph = None
+        torch.cuda.synchronize(self.device)
 
     def launches_per_step(self) -> int:
         """Kernels of ours one step enqueues (counted inside the C library; a graph replay re-issues the same nodes)."""

@@ -23,6 +23,7 @@ def _worker(rank, world, port, out, use_graph):
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    eng = None
     try:
         from gan_class_transfer2_b200.engine import DataParallel, NetConfig, UNetEngine, shard_batch
         cfg = O.TINY
@@ -47,6 +48,8 @@ def _worker(rank, world, port, out, use_graph):
                         "replicas_equal": all(torch.equal(gathered[0], g) for g in gathered),
                         "weights": {k: v.cpu() for k, v in eng.weights().items()}}, out)
     finally:
+        if eng is not None:
+            eng.release_graphs()  # a live graph holding captured NCCL collectives blocks the communicator teardown
         dist.destroy_process_group()
 
 
