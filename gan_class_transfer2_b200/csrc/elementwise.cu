@@ -45,6 +45,7 @@ __global__ void noise_kernel(const float4* __restrict__ x, const float4* __restr
   TraceScope trace(1);
   pdl_launch_dependents();
   pdl_wait();
+  trace.ready();
   const long long total = (long long)B * vecPerImage;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(256) step_begin_kernel(const float4* __restric
   TraceScope trace(2);
   pdl_launch_dependents();
   pdl_wait();
+  trace.ready();
   const long long step = *iterations;
   const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
   const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -192,6 +194,7 @@ __global__ void __launch_bounds__(128) conv_c3_fprop_kernel(const float* __restr
   TraceScope trace(3);
   pdl_launch_dependents();
   pdl_wait();
+  trace.ready();
   __shared__ __align__(16) float patch[C3_P][C3_ROW];
   const int Ho = H / 2, Wo = W / 2;
   const int tilesX = Wo / C3_T, tilesY = Ho / C3_T;
@@ -244,6 +247,7 @@ __global__ void __launch_bounds__(256) conv_c3_wgrad_kernel(const float* __restr
   TraceScope trace(4);
   pdl_launch_dependents();
   pdl_wait();
+  trace.ready();
   __shared__ __align__(16) float patch[C3_P][C3_ROW];
   __shared__ float comb[49][128];
   const int Ho = H / 2, Wo = W / 2;
@@ -334,6 +338,7 @@ __global__ void __launch_bounds__(256) dense_mse_kernel(const __nv_bfloat16* __r
   TraceScope trace(5);
   pdl_launch_dependents();
   pdl_wait();
+  trace.ready();
   constexpr int PPW = 32 / LPP;        // pixels per warp iteration
   constexpr int CU = 8 * LPP;
   constexpr int NRED = CU * 3 + 9 + 3 + 1;  // dWd(u0 part) | dWd(image part) | dbd | loss
@@ -508,6 +513,7 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const __grid_constant__ 
   TraceScope trace(6);
   pdl_launch_dependents();
   pdl_wait();
+  trace.ready();
   extern __shared__ float red[];  // [rowsPerIter][C]
   int s = 0;
   while (s + 1 < sg.n && (int)blockIdx.x >= sg.firstBlock[s + 1]) ++s;
@@ -612,6 +618,7 @@ __global__ void adam_prepare_kernel(long long* __restrict__ iterations, float* _
   TraceScope trace(7);
   pdl_launch_dependents();
   pdl_wait();
+  trace.ready();
   const long long step = *iterations;
   float lr = base;
   if (step < warmup) lr = base * (float)(step + 1) / (float)(warmup + 1);
@@ -623,34 +630,63 @@ __global__ void adam_prepare_kernel(long long* __restrict__ iterations, float* _
   trace.end();
 }
 
-__global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ w, float4* __restrict__ m,
-                                                   float4* __restrict__ v, const float4* __restrict__ g,
-                                                   uint2* __restrict__ wb, long long nvec,
-                                                   const float* __restrict__ hyper, float b1, float b2, float eps,
-                                                   float gscale, long long* __restrict__ iterations_inc) {
+// Memory-level parallelism is what this kernel lives on: it shares SMs with the conv CTAs (which leave room for ~14 K
+// registers, i.e. one small block), so each thread keeps ADAM_U float4 of every array in flight (16 x 16-byte loads
+// issued before the first use) and a block is only 128 threads.  Element order and arithmetic are unchanged.
+constexpr int ADAM_U = 4;
+constexpr int ADAM_THREADS = 128;
+__device__ __forceinline__ void adam_update(float4& wv, float4& mv, float4& vv, float4 gv, float gscale, float c1,
+                                            float c2, float alpha, float eps) {
+  gv.x *= gscale; gv.y *= gscale; gv.z *= gscale; gv.w *= gscale;
+  adam_elem4(wv, mv, vv, gv, c1, c2, alpha, eps);
+}
+__global__ void __launch_bounds__(ADAM_THREADS, 5) adam_kernel(float4* __restrict__ w, float4* __restrict__ m,
+                                                            float4* __restrict__ v, const float4* __restrict__ g,
+                                                            uint2* __restrict__ wb, long long nvec,
+                                                            const float* __restrict__ hyper, float b1, float b2,
+                                                            float eps, float gscale,
+                                                            long long* __restrict__ iterations_inc) {
   TraceScope trace(8);
   pdl_launch_dependents();
   pdl_wait();
+  trace.ready();
   const float alpha = __ldg(hyper);
   if (iterations_inc != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *iterations_inc += 1;
   const float c1 = 1.f - b1, c2 = 1.f - b2;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
-       i += (long long)gridDim.x * blockDim.x) {
-    float4 gv = __ldg(g + i);
-    gv.x *= gscale; gv.y *= gscale; gv.z *= gscale; gv.w *= gscale;
-    float4 mv = m[i], vv = v[i], wv = w[i];
-    mv.x += (gv.x - mv.x) * c1; mv.y += (gv.y - mv.y) * c1; mv.z += (gv.z - mv.z) * c1; mv.w += (gv.w - mv.w) * c1;
-    vv.x += (gv.x * gv.x - vv.x) * c2; vv.y += (gv.y * gv.y - vv.y) * c2;
-    vv.z += (gv.z * gv.z - vv.z) * c2; vv.w += (gv.w * gv.w - vv.w) * c2;
-    wv.x -= alpha * mv.x / (sqrtf(vv.x) + eps); wv.y -= alpha * mv.y / (sqrtf(vv.y) + eps);
-    wv.z -= alpha * mv.z / (sqrtf(vv.z) + eps); wv.w -= alpha * mv.w / (sqrtf(vv.w) + eps);
-    m[i] = mv;
-    v[i] = vv;
-    w[i] = wv;
+  const long long T = (long long)gridDim.x * blockDim.x;
+  long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  // full groups: ADAM_U strided vectors per thread, all loads in flight before the first use
+  for (; i0 + (ADAM_U - 1) * T < nvec; i0 += T * ADAM_U) {
+    float4 gv[ADAM_U], mv[ADAM_U], vv[ADAM_U], wv[ADAM_U];
+#pragma unroll
+    for (int u = 0; u < ADAM_U; ++u) {
+      gv[u] = __ldcs(g + i0 + u * T);  // the gradient is dead after this read
+      mv[u] = m[i0 + u * T];
+      vv[u] = v[i0 + u * T];
+      wv[u] = w[i0 + u * T];
+    }
+#pragma unroll
+    for (int u = 0; u < ADAM_U; ++u) {
+      adam_update(wv[u], mv[u], vv[u], gv[u], gscale, c1, c2, alpha, eps);
+      m[i0 + u * T] = mv[u];
+      v[i0 + u * T] = vv[u];
+      w[i0 + u * T] = wv[u];
+      uint2 o;
+      o.x = pack_bf16x2(wv[u].x, wv[u].y);
+      o.y = pack_bf16x2(wv[u].z, wv[u].w);
+      wb[i0 + u * T] = o;
+    }
+  }
+  for (; i0 < nvec; i0 += T) {  // ragged tail
+    float4 gv = __ldcs(g + i0), mv = m[i0], vv = v[i0], wv = w[i0];
+    adam_update(wv, mv, vv, gv, gscale, c1, c2, alpha, eps);
+    m[i0] = mv;
+    v[i0] = vv;
+    w[i0] = wv;
     uint2 o;
     o.x = pack_bf16x2(wv.x, wv.y);
     o.y = pack_bf16x2(wv.z, wv.w);
-    wb[i] = o;
+    wb[i0] = o;
   }
   trace.end();
 }
@@ -671,10 +707,10 @@ int adam_apply(float* w, float* m, float* v, const float* g, __nv_bfloat16* w_bf
   }
   const long long nvec = n / 4;
   if (nvec == 0) return 0;
-  long long blocks = (nvec + 255) / 256;
+  long long blocks = (nvec + ADAM_THREADS * ADAM_U - 1) / (ADAM_THREADS * ADAM_U);
   const long long cap = g_adam_blocks > 0 ? g_adam_blocks : (long long)g_ew_sms * 8;
   if (blocks > cap) blocks = cap;
-  launch_k(adam_kernel, dim3((int)blocks), dim3(256), 0, st, reinterpret_cast<float4*>(w), reinterpret_cast<float4*>(m),
+  launch_k(adam_kernel, dim3((int)blocks), dim3(ADAM_THREADS), 0, st, reinterpret_cast<float4*>(w), reinterpret_cast<float4*>(m),
                                            reinterpret_cast<float4*>(v), reinterpret_cast<const float4*>(g),
                                            reinterpret_cast<uint2*>(w_bf16), nvec, hyper, beta1, beta2, eps,
                                            grad_scale, iterations_inc);
@@ -694,6 +730,7 @@ __global__ void cast_bf16_kernel(const float4* __restrict__ src, uint2* __restri
   TraceScope trace(9);
   pdl_launch_dependents();
   pdl_wait();
+  trace.ready();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
     const float4 s = __ldg(src + i);

@@ -97,6 +97,15 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// L2 prefetch of one box (no shared-memory destination, no barrier): used for the weight operand, whose HBM fetch
+// is started before the kernel's first real load can be issued.
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
 // Multicast variants: the box lands at the same shared-memory offset in every CTA of `mask` (bit = rank in cluster) and
 // each destination CTA's own mbarrier (same offset) receives the complete_tx.
 __device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
@@ -207,21 +216,26 @@ __device__ __forceinline__ unsigned long long trace_now() {
   return t;
 }
 struct TraceScope {
-  unsigned long long t0;
+  unsigned long long t0, t1;
   int id;
   bool on;
-  __device__ __forceinline__ explicit TraceScope(int kernel_id) : t0(0), id(kernel_id), on(false) {
+  __device__ __forceinline__ explicit TraceScope(int kernel_id) : t0(0), t1(0), id(kernel_id), on(false) {
     if (g_trace_buf != nullptr && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {
       on = true;
       t0 = trace_now();
     }
+  }
+  // call right after griddepcontrol.wait: the record then also carries how long the block sat waiting for the
+  // previous kernel (entry -> ready, ns, in bits 16.. of the id word)
+  __device__ __forceinline__ void ready() {
+    if (on) t1 = trace_now();
   }
   __device__ __forceinline__ void end() {
     if (on) {
       const unsigned long long slot = atomicAdd(g_trace_buf, 1ull);
       if (slot < TRACE_MAX_RECORDS) {
         unsigned long long* r = g_trace_buf + 1 + slot * 4;
-        r[0] = (unsigned long long)id;
+        r[0] = (unsigned long long)id | ((t1 > t0 ? t1 - t0 : 0ull) << 16);
         r[1] = (unsigned long long)blockIdx.x | ((unsigned long long)gridDim.x << 32);
         r[2] = t0;
         r[3] = trace_now();
@@ -300,6 +314,17 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
       : "memory");
 }
 
+// 32 lanes x 16 consecutive fp32 columns.
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
 // ----------------------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor for tcgen05.mma (SWIZZLE_128B, descriptor version 1 = sm_100).
 //   bits [0,14)  start address >> 4        bits [16,30) leading-dim byte offset >> 4
@@ -323,6 +348,30 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, int a_mn_ma
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// ----------------------------------------------------------------------------- Keras-Adam, one element
+// train.py:75 (tf.keras.optimizers.Adam): m += (g-m)(1-b1); v += (g^2-v)(1-b2); w -= alpha*m/(sqrt(v)+eps)
+// with c1 = 1-b1, c2 = 1-b2 and epsilon added to the un-bias-corrected sqrt(v).  The Adam kernel is nearly as much
+// issue-bound as HBM-bound (41.7 M elements per step), so the square root and the quotient use the hardware
+// approximations (sqrt.approx.ftz / rcp.approx.ftz, each within 1 ulp; v below 1.2e-38 counts as 0, far under eps): the update differs from the IEEE sequence by a few
+// 1e-7 of ITSELF, far inside every stated tolerance, for a quarter of the instructions.  Every path that applies the
+// optimiser (adam_kernel, the wgrad epilogue, the split-K reduction) calls this one function, so they agree bit for bit.
+__device__ __forceinline__ void adam_elem(float& w, float& m, float& v, float g, float c1, float c2, float alpha,
+                                          float eps) {
+  m = __fmaf_rn(g - m, c1, m);
+  v = __fmaf_rn(__fmaf_rn(g, g, -v), c2, v);
+  float s, r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(v));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s + eps));
+  w = __fmaf_rn(-(alpha * m), r, w);
+}
+__device__ __forceinline__ void adam_elem4(float4& w, float4& m, float4& v, const float4& g, float c1, float c2,
+                                           float alpha, float eps) {
+  adam_elem(w.x, m.x, v.x, g.x, c1, c2, alpha, eps);
+  adam_elem(w.y, m.y, v.y, g.y, c1, c2, alpha, eps);
+  adam_elem(w.z, m.z, v.z, g.z, c1, c2, alpha, eps);
+  adam_elem(w.w, m.w, v.w, g.w, c1, c2, alpha, eps);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

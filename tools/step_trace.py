@@ -44,7 +44,8 @@ def main():
     n = lib.gct2_debug_trace(buf, 8192)
     lib.gct2_debug_set(11, 0)
     rec = np.frombuffer(buf, dtype=np.uint64)[: n * 4].reshape(n, 4).astype(np.int64)
-    ids, blk, grid = rec[:, 0], rec[:, 1] & 0xFFFFFFFF, rec[:, 1] >> 32
+    ids, blk, grid = rec[:, 0] & 0xFFFF, rec[:, 1] & 0xFFFFFFFF, rec[:, 1] >> 32
+    waited = rec[:, 0] >> 16  # ns between block entry and the return of griddepcontrol.wait (conv kernels only)
     t0 = rec[:, 2].min()
     # one launch = its first-block record (+ last-block record when the grid has more than one block)
     order = np.argsort(rec[:, 2])
@@ -55,27 +56,32 @@ def main():
             continue
         used[i] = True
         start, end = rec[i, 2], rec[i, 3]
+        ready = rec[i, 2] + waited[i] if waited[i] else 0
         if grid[i] > 1:
             cand = [j for j in order if not used[j] and ids[j] == ids[i] and grid[j] == grid[i] and blk[j] == grid[i] - 1]
             if cand:
                 j = min(cand, key=lambda j: abs(rec[j, 2] - rec[i, 2]))
                 used[j] = True
                 start, end = min(start, rec[j, 2]), max(end, rec[j, 3])
-        launches.append((int(ids[i]), int(grid[i]), (start - t0) / 1e3, (end - t0) / 1e3))
+                if waited[j]:
+                    ready = max(ready, rec[j, 2] + waited[j])
+        launches.append((int(ids[i]), int(grid[i]), (start - t0) / 1e3, (end - t0) / 1e3,
+                         (ready - t0) / 1e3 if ready else -1.0))
     launches.sort(key=lambda r: r[2])
-    lines = ["kernel,grid,start_us,end_us,dur_us,running_at_start"]
+    lines = ["kernel,grid,start_us,end_us,dur_us,running_at_start,ready_us,work_us"]
     busy = 0.0
     last_end = 0.0
-    for k, (kid, g, s, e) in enumerate(launches):
-        running = sum(1 for (_, _, s2, e2) in launches if s2 < s < e2)
-        lines.append(f"{NAMES.get(kid, kid)},{g},{s:.1f},{e:.1f},{e - s:.1f},{running}")
+    for k, (kid, g, s, e, r) in enumerate(launches):
+        running = sum(1 for (_, _, s2, e2, _) in launches if s2 < s < e2)
+        tail = f",{r:.1f},{e - r:.1f}" if r >= 0 else ",,"
+        lines.append(f"{NAMES.get(kid, kid)},{g},{s:.1f},{e:.1f},{e - s:.1f},{running}{tail}")
         if e > last_end:
             busy += e - max(s, last_end)
             last_end = e
-    total = max(e for (_, _, _, e) in launches)
+    total = max(e for (_, _, _, e, _) in launches)
     print("\n".join(lines))
     print(f"# {len(launches)} launches, step span {total:.1f} us, union of kernel intervals {busy:.1f} us "
-          f"(idle {total - busy:.1f} us), sum of durations {sum(e - s for (_, _, s, e) in launches):.1f} us")
+          f"(idle {total - busy:.1f} us), sum of durations {sum(e - s for (_, _, s, e, _) in launches):.1f} us")
     if a.csv:
         with open(a.csv, "w") as f:
             f.write("\n".join(lines) + "\n")

@@ -37,6 +37,9 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--only", default="")
     ap.add_argument("--debug", action="append", default=[])
+    ap.add_argument("--cold-weights", action="store_true",
+                    help="flush L2 before the measured launch, then re-touch the activations only: the state a layer "
+                         "finds inside a training step (the optimiser has streamed 1.3 GB through L2 since)")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     lib = _lib.init(0)
@@ -75,6 +78,12 @@ def main():
             torch.cuda.synchronize()
             lib.gct2_debug_set(2, 1)
             sys.stderr.flush()
+            if a.cold_weights:
+                flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+                flush.fill_(1)
+                for t_ in (x, dy, y, dx):
+                    t_.float().sum()
+                torch.cuda.synchronize()
             fn()
             t = read_timeline(lib)
             t0 = t[:, 0].min()
