@@ -54,10 +54,6 @@ _PROTOS = {
     "gct2_convT4s2_dgrad": (c_int, [_P, c_int, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                     _P, c_size_t, _P]),
     "gct2_convT4s2_wgrad": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
-    "gct2_conv4s2_wgrad_adam": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, c_float, c_float, c_float,
-                                        c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
-    "gct2_convT4s2_wgrad_adam": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, c_float, c_float, c_float,
-                                         c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "gct2_bias_grad": (c_int, [_P, c_int, c_longlong, c_int, _P, _P]),
     "gct2_bias_grad_multi": (c_int, [c_int, _P, _P, _P, _P, _P, c_int, _P]),
     "gct2_dense_mse": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, c_longlong, c_int, c_float,

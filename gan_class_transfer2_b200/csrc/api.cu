@@ -168,48 +168,6 @@ int gct2_convT4s2_wgrad(const uint16_t* x, int ldx, const uint16_t* dy, int lddy
   return conv_launch(a, S(stream));
 }
 
-namespace {
-void set_adam(ConvArgs& a, float* w, float* m, float* v, uint16_t* w_bf16, const float* hyper, float beta1,
-              float beta2, float eps) {
-  a.adamW = w; a.adamM = m; a.adamV = v; a.adamW16 = MB(w_bf16);
-  a.hyper = hyper; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
-}
-}  // namespace
-
-int gct2_conv4s2_wgrad_adam(const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, float* w, float* m,
-                            float* v, uint16_t* w_bf16, const float* hyper, float beta1, float beta2, float eps,
-                            int B, int H, int W, int Cin, int Cout, float* ws, size_t ws_bytes, void* stream) {
-  if (check_conv("gct2_conv4s2_wgrad_adam", B, H / 2, W / 2, Cin, Cout)) return 1;
-  if (!w || !m || !v || !w_bf16 || !hyper) {
-    set_error("gct2_conv4s2_wgrad_adam: w, m, v, w_bf16 and hyper must be non-null");
-    return 1;
-  }
-  ConvArgs a = blank(MODE_W, B, H / 2, W / 2);
-  a.hi = CB(x); a.ldHi = ldx; a.Chi = Cin;
-  a.lo = CB(dy); a.ldLo = lddy; a.Clo = Cout;
-  a.dw = dw;
-  a.ws = ws; a.wsBytes = ws_bytes;
-  set_adam(a, w, m, v, w_bf16, hyper, beta1, beta2, eps);
-  return conv_launch(a, S(stream));
-}
-
-int gct2_convT4s2_wgrad_adam(const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, float* w, float* m,
-                             float* v, uint16_t* w_bf16, const float* hyper, float beta1, float beta2, float eps,
-                             int B, int H, int W, int Cin, int Cout, float* ws, size_t ws_bytes, void* stream) {
-  if (check_conv("gct2_convT4s2_wgrad_adam", B, H, W, Cin, Cout)) return 1;
-  if (!w || !m || !v || !w_bf16 || !hyper) {
-    set_error("gct2_convT4s2_wgrad_adam: w, m, v, w_bf16 and hyper must be non-null");
-    return 1;
-  }
-  ConvArgs a = blank(MODE_W, B, H, W);
-  a.hi = CB(dy); a.ldHi = lddy; a.Chi = Cout;
-  a.lo = CB(x); a.ldLo = ldx; a.Clo = Cin;
-  a.dw = dw;
-  a.ws = ws; a.wsBytes = ws_bytes;
-  set_adam(a, w, m, v, w_bf16, hyper, beta1, beta2, eps);
-  return conv_launch(a, S(stream));
-}
-
 int gct2_bias_grad(const uint16_t* dz, int ld, long long rows, int C, float* db, void* stream) {
   return bias_grad(CB(dz), ld, rows, C, db, S(stream));
 }

@@ -27,14 +27,6 @@ struct ConvArgs {
   size_t wsBytes;
   // W
   float* dw;                     // fp32 [16][Chi][Clo]
-  // W with the optimiser fused (adamW != nullptr): Keras-Adam is applied to this variable by the same call -- inside
-  // the wgrad epilogue, or inside the split-K reduction -- and dw becomes optional (nullptr = gradient not stored)
-  float* adamW;
-  float* adamM;
-  float* adamV;
-  __nv_bfloat16* adamW16;
-  const float* hyper;
-  float beta1, beta2, eps;
   // tuning overrides (0 = heuristic)
   int forceBN, forceSplits;
   int forceCm, forceCn;          // cluster shape override (0 = heuristic, 1 = no cluster along that axis)

@@ -21,11 +21,10 @@ void set_error(const char* fmt, ...) {
 }
 
 int g_use_pdl = 1;
-static int g_prefetch_b = 0;           // debug key 14 != 0 enables an L2 prefetch of the weight operand (measured: no gain)
 static int g_fuse_finish = 1;          // debug key 12 != 0 disables the in-kernel split-K finish
 static int* g_cnt = nullptr;           // rendezvous counters of the fused finish: [FUSE_MAX_TILES][2], zero at rest
 constexpr int FUSE_MAX_TILES = 4096;
-static int g_cap_w = 0, g_cap_sp = 0;  // debug keys 9 / 10: CTA budget of wgrad / fprop+dgrad launches (0 = all SMs)
+static int g_cap_w = 0, g_cap_sp = 0;  // debug keys 9 / 10: CTA budget of wgrad / dgrad launches (0 = all SMs)
 static long long g_launches = 0;
 void count_launch(int n) { g_launches += n; }
 long long launch_count() { return g_launches; }
@@ -80,7 +79,6 @@ void conv_set_debug(int key, int value) {
   if (key == 8) g_use_pdl = value ? 0 : 1;  // key 8 != 0 disables programmatic dependent launch
   if (key == 9) g_cap_w = value;
   if (key == 12) g_fuse_finish = value ? 0 : 1;
-  if (key == 14) g_prefetch_b = value ? 1 : 0;
   if (key == 10) g_cap_sp = value;
   if (key == 7) {
     if (value && g_dbg == nullptr) cudaMalloc(&g_dbg, (size_t)DBG_MAX_CTAS * 8 * sizeof(unsigned long long));
@@ -241,36 +239,21 @@ __global__ void splitk_finish_kernel(const float* __restrict__ ws, long long spl
   trace.end();
 }
 
-// dw[i] = sum over splits of slab[s][i] (weight-gradient split-K), fixed order; with the optimiser fused (aw != nullptr)
-// the sum feeds Keras-Adam directly (same arithmetic as adam_kernel) and dw is optional.
+// dw[i] = sum over splits of slab[s][i] (weight-gradient split-K), fixed order.
 __global__ void wgrad_reduce_kernel(const float4* __restrict__ ws, long long splitStrideVec, int splits,
-                                    float4* __restrict__ dw, long long nvec, float4* __restrict__ aw,
-                                    float4* __restrict__ am, float4* __restrict__ av, uint2* __restrict__ aw16,
-                                    const float* __restrict__ hyper, float c1, float c2, float eps) {
+                                    float4* __restrict__ dw, long long nvec) {
   TraceScope trace(21);
   pdl_launch_dependents();
   pdl_wait();
   trace.ready();
-  const float alpha = aw != nullptr ? __ldg(hyper) : 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
-    float4 v = __ldcs(ws + i);
+    float4 v = __ldg(ws + i);
     for (int sidx = 1; sidx < splits; ++sidx) {
-      const float4 u = __ldcs(ws + sidx * splitStrideVec + i);
+      const float4 u = __ldg(ws + sidx * splitStrideVec + i);
       v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
     }
-    if (aw != nullptr) {
-      float4 mv = __ldcs(am + i), vv = __ldcs(av + i), wv = __ldcs(aw + i);
-      adam_elem4(wv, mv, vv, v, c1, c2, alpha, eps);
-      __stcs(am + i, mv);
-      __stcs(av + i, vv);
-      __stcs(aw + i, wv);
-      uint2 o;
-      o.x = pack_bf16x2(wv.x, wv.y);
-      o.y = pack_bf16x2(wv.z, wv.w);
-      aw16[i] = o;
-    }
-    if (dw != nullptr) dw[i] = v;
+    dw[i] = v;
   }
   trace.end();
 }
@@ -280,10 +263,7 @@ __global__ void wgrad_reduce_kernel(const float4* __restrict__ ws, long long spl
 // trip, ~1.4 us), so the ring is as deep as shared memory allows -- 8 x 24 KB, 6 x 32 KB, 4 x 48 KB
 static int stages_for(int BN) { return BN == 256 ? 4 : (BN == 128 ? 6 : 8); }
 // pipeline stages + barriers (256 B) + 1 KB alignment slack
-// + 2 KB of transpose staging per epilogue warp (8 warps at BN = 64, 16 otherwise)
-static size_t smem_for(int BN) {
-  return (size_t)stages_for(BN) * (16384 + BN * 128) + 1024 + 256 + (size_t)(BN == 64 ? 8 : 16) * 2048;
-}
+static size_t smem_for(int BN) { return (size_t)stages_for(BN) * (16384 + BN * 128) + 1024 + 256; }
 
 struct Choice {
   int BN, splits, cm, cn;
@@ -360,7 +340,7 @@ static Choice choose(int mode, int mTiles, int phases, int N, int kTotal, long l
           if (forceCm >= 1 ? cm != forceCm : cm != 1) continue;
           if (forceCn >= 1 ? cn != forceCn : cn != 1) continue;
           int maxCtas = g_num_sms;
-          const int cap = isW ? g_cap_w : g_cap_sp;
+          const int cap = isW ? g_cap_w : (dgradEpi ? g_cap_sp : 0);
           if (cap > 0 && cap < maxCtas) maxCtas = cap;
           if (cs > 1) {
             const int mc = g_max_clusters[mode][bn_index(BN)][cs];
@@ -552,25 +532,6 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     p.rowStride = p.gIsA ? a.Clo : 1;
     p.colStride = p.gIsA ? 1 : a.Clo;
     p.atomic = c.splits > 1;
-    if (a.adamW != nullptr) {
-      if ((reinterpret_cast<uintptr_t>(a.adamW) | reinterpret_cast<uintptr_t>(a.adamM) |
-           reinterpret_cast<uintptr_t>(a.adamV)) % 16 || reinterpret_cast<uintptr_t>(a.adamW16) % 8 ||
-          a.hyper == nullptr) {
-        set_error("wgrad+adam: w/m/v must be 16-byte aligned, the bf16 shadow 8-byte aligned, hyper non-null");
-        return 1;
-      }
-      p.adamW = a.adamW;
-      p.adamM = a.adamM;
-      p.adamV = a.adamV;
-      p.adamW16 = a.adamW16;
-      p.hyper = a.hyper;
-      p.c1 = 1.f - a.beta1;
-      p.c2 = 1.f - a.beta2;
-      p.eps = a.eps;
-    } else if (a.dw == nullptr) {
-      set_error("wgrad: dw is null and no optimiser state was given");
-      return 1;
-    }
     CUtensorMap mg, mp;
     if (map_hi5(&mg, a.hi, a.ldHi, a.Chi, a.B, 2 * a.Hlo, 2 * a.Wlo, p.Wt, p.Ht, p.Nb)) return 1;
     if (map_lo4(&mp, a.lo, a.ldLo, a.Clo, a.B, a.Hlo, a.Wlo, p.Wt, p.Ht, p.Nb)) return 1;
@@ -583,13 +544,12 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
   }
 
   p.stages = stages_for(BN);
-  p.prefetchB = (a.mode != MODE_W && g_prefetch_b) ? 1 : 0;
   const size_t smem = smem_for(BN);
   const int csize = p.cm * p.cn;
   p.numClusterItems = p.numItems / csize;
   int maxCtas = g_num_sms;  // one CTA per SM: the per-SM operand ingest rate, not occupancy, bounds a CTA's speed
   {
-    const int cap = a.mode == MODE_W ? g_cap_w : g_cap_sp;
+    const int cap = a.mode == MODE_W ? g_cap_w : (a.epi == EPI_DGRAD ? g_cap_sp : 0);
     if (cap > 0 && cap < maxCtas) maxCtas = cap;
   }
   if (csize > 1) maxCtas = g_max_clusters[a.mode][bn_index(BN)][csize] * csize;
@@ -636,10 +596,7 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     int blocks = (int)((nvec + 255) / 256);
     if (blocks > g_num_sms * 8) blocks = g_num_sms * 8;
     e = launch_k(wgrad_reduce_kernel, dim3(blocks), dim3(256), 0, stream, reinterpret_cast<const float4*>(a.ws),
-                 p.wsSplitStride / 4, p.splits, reinterpret_cast<float4*>(a.dw), nvec,
-                 reinterpret_cast<float4*>(a.adamW), reinterpret_cast<float4*>(a.adamM),
-                 reinterpret_cast<float4*>(a.adamV), reinterpret_cast<uint2*>(a.adamW16), a.hyper, 1.f - a.beta1,
-                 1.f - a.beta2, a.eps);
+                 p.wsSplitStride / 4, p.splits, reinterpret_cast<float4*>(a.dw), nvec);
     if (e != cudaSuccess) {
       set_error("wgrad_reduce_kernel launch: %s", cudaGetErrorString(e));
       return 1;

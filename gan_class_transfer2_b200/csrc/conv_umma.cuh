@@ -13,7 +13,7 @@
 //   MODE_W  weight gradient  dW[tap][g][p] = sum_pix G_hi[pix @ tap, g] * P_lo[pix, p]
 //           both operands MN-major (pixels are the contraction dim and are the slow smem axis).
 //
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warp 3 idle, warps 4.. = epilogue
+// Warp roles: warps 0, 2, 3 = TMA producers (k-iterations round-robin; warp 2 also allocates TMEM), warp 1 = MMA issuer, warps 4.. = epilogue
 // (8 warps for BN = 64, 16 otherwise; TMEM -> registers -> global).  Accumulators are double-buffered in TMEM (2 x BN columns) so the
 // epilogue of tile i overlaps the main loop of tile i+1.
 #pragma once
@@ -51,7 +51,6 @@ struct ConvParams {
   int cm, cn;                  // thread-block cluster = cm x cn CTAs: cm consecutive M tiles x cn consecutive N tiles of
                                // one (phase, split); A tiles are TMA-multicast along cn, B tiles along cm
   int numClusterItems;         // numItems / (cm*cn)
-  int prefetchB;               // S/P: prefetch the first item's weight boxes into L2 during the prologue
   int fused;                   // split-K finished inside this launch (tile-major slabs + arrive/depart counters)
   int realEpi;                 // fused: the epilogue to apply after the slabs are summed (EPI_BIAS_RELU / EPI_DGRAD)
   int numTiles;                // fused: phases * nTiles * mTiles
@@ -74,13 +73,6 @@ struct ConvParams {
   long long tapStride;
   int rowStride, colStride;    // element strides of the (M-row, N-col) accumulator tile inside one tap
   int atomic;                  // EPI_WGRAD: split-K -> each split stores its partial into its own slab of ws
-  // EPI_WGRAD with the optimiser fused (adamW != nullptr): Keras-Adam on the tile, indices as for dw (dw may be null)
-  float* adamW;
-  float* adamM;
-  float* adamV;
-  __nv_bfloat16* adamW16;
-  const float* hyper;          // hyper[0] = alpha of this step (adam_prepare / step_begin)
-  float c1, c2, eps;           // 1 - beta1, 1 - beta2, epsilon
 };
 
 struct WorkItem {
@@ -198,26 +190,6 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
   // from here on global memory is touched (the stamp below included), so wait for that kernel to complete -- and let
   // the next kernel start its own prologue now.
   pdl_launch_dependents();
-  if (MODE != MODE_W && warp == 3 && lane == 0 && p.prefetchB) {  // warp 3 has no other job
-    // Experiment kept behind debug key 14 (off): pull this CTA's weight boxes into L2 before griddepcontrol.wait
-    // (legal: it only moves lines into L2, the point of coherence).  Measured on B200: no gain -- cold weights cost
-    // the first load ~0.4 us and nothing after (tools/timeline.py --cold-weights), and the prefetches queue ahead of
-    // the real loads in the TMA unit.
-    tma_prefetch_desc(&mapB);
-    const WorkItem w = decode_item<MODE>(p, clusterId, rm, rn);
-    const int nIt = p.kIters < 64 ? p.kIters : 64;
-    for (int it = 0; it < nIt; ++it) {
-      const int kit = w.split * p.kIters + it;
-      const int t = kit / p.kcPer, kc = kit % p.kcPer;
-      if (MODE == MODE_S) {
-#pragma unroll
-        for (int j = 0; j < BN / 64; ++j) tma_prefetch_l2_3d(&mapB, w.nt * BN + j * 64, kc * 64, t);
-      } else {
-        const int ky = (1 - (w.ph >> 1)) + 2 * (t >> 1), kx = (1 - (w.ph & 1)) + 2 * (t & 1);
-        tma_prefetch_l2_3d(&mapB, kc * 64, w.nt * BN, ky * 4 + kx);
-      }
-    }
-  }
   pdl_wait();
   trace.ready();
   if (threadIdx.x == 0 && p.dbg != nullptr) p.dbg[(size_t)blockIdx.x * 8 + 0] = t_entry;  // kernel entry
@@ -225,11 +197,18 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
 
   const int tilesXY = p.tilesX * p.tilesY;
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+  if (warp == 0 || warp == 2 || warp == 3) {
+    // ------------------------------------------------------------------ TMA producers (three warps)
+    // One thread needs ~600-900 cycles to get one stage on its way (empty-wait, expect_tx and 2-5 TMA instructions
+    // issue back to back at ~150 cycles each: tools/probes/tma_ingest_probe.cu), more than the tensor pipe needs to
+    // consume it (128-512 cycles), and a deeper ring does not help because the limit is issue, not latency.  Three
+    // producer threads in three warps take the k-iterations round-robin (producer j owns global iteration g = j mod
+    // 3): measured 2.6x the single-producer rate in isolation.
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int item = clusterId; item < p.numClusterItems; item += numClusters) {
+      constexpr uint32_t NP = 3;
+      const uint32_t pj = warp == 0 ? 0u : (uint32_t)warp - 1u;
+      uint32_t gbase = 0;
+      for (int item = clusterId; item < p.numClusterItems; item += numClusters, gbase += (uint32_t)p.kIters) {
         const WorkItem w = decode_item<MODE>(p, item, rm, rn);
         int x0 = 0, y0 = 0, b0 = 0;
         if (MODE != MODE_W) {
@@ -237,8 +216,10 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
           y0 = ((w.mt / p.tilesX) % p.tilesY) * p.Ht;
           b0 = (w.mt / tilesXY) * p.Nb;
         }
-        for (int it = 0; it < p.kIters; ++it) {
+        for (int it = (int)((pj + NP - gbase % NP) % NP); it < p.kIters; it += (int)NP) {
           const int kit = w.split * p.kIters + it;
+          const uint32_t g = gbase + (uint32_t)it;
+          const uint32_t stage = g % (uint32_t)S, phase = (g / (uint32_t)S) & 1u;
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
           uint8_t* sa = smem + stage * STAGE_BYTES;
@@ -310,10 +291,6 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
                             cy + hy, cb);
             }
           }
-          if (++stage == (uint32_t)S) {
-            stage = 0;
-            phase ^= 1;
-          }
         }
       }
     }
@@ -366,191 +343,128 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
     // At batch 1 a CTA owns a single tile, so nothing overlaps its epilogue: it is spread over NE warps.  Warp w may
     // only read TMEM lanes 32*(w%4)..+31 (hardware rule), so warps w, w+4, w+8, ... share a lane quarter and split the
     // tile's columns.  Lane l of a warp owns accumulator row (q*32 + l): 16-byte vector accesses per row.
-    if (warp < 4) {
-      // warps 2, 3: nothing to do until teardown
-    } else {
+    {
       constexpr int NE = kEpilogueWarps<BN>();
       constexpr int COLS = BN / (NE / 4);  // columns per warp (32 or 64)
       const int q = warp & 3;              // TMEM lane quarter this warp may access
       const int cgrp = (warp - 4) >> 2;    // which slice of the tile's columns
-      // Accumulators leave TMEM with lane = row (32 rows x 16 fp32 columns per load).  Storing that shape directly
-      // makes every warp-level store touch 32 different 128-byte lines (one 16-byte piece each) and the LSU, at one
-      // line per cycle, becomes the epilogue's bound (4-5 us for a 128 x 256 fp32 tile).  Each warp therefore passes
-      // its 32 x 16 block through a private 2 KB shared-memory patch (XOR-swizzled 16-byte pieces, conflict-free both
-      // ways) and comes out with lane -> (row = 8i + lane/4, 4 consecutive columns), i = 0..3: one instruction then
-      // covers 8 rows x 64 contiguous bytes (fp32) / 32 bytes (bf16), 4x / 2x fewer line requests.
-      uint8_t* stg = smem + S * STAGE_BYTES + 256 + (warp - 4) * 2048;
-      const int sub = lane >> 2, jj = lane & 3;
-      const float4* stg_rd[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int rl = i * 8 + sub;
-        stg_rd[i] = reinterpret_cast<const float4*>(stg + rl * 64 + ((jj ^ ((rl >> 1) & 3)) << 4));
-      }
-      float4* stg_wr[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        stg_wr[j] = reinterpret_cast<float4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
+      const int r = q * 32 + lane;
       uint32_t acc = 0, acc_phase = 0;
       for (int item = clusterId; item < p.numClusterItems; item += numClusters) {
         const WorkItem w = decode_item<MODE>(p, item, rm, rn);
         const int n0 = w.nt * BN + cgrp * COLS;
         const int tileId = (w.ph * p.nTiles + w.nt) * p.mTiles + w.mt;
-        // my four rows -> output pixel (-1: padding row of a ragged batch tile)
-        int pixv[4] = {0, 0, 0, 0};
+        // row -> output location
+        bool valid = true;
+        long long pix = 0;
         if (MODE != MODE_W) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = q * 32 + i * 8 + sub;
-            const int xl = r % p.Wt, yl = (r / p.Wt) % p.Ht, bl = r / (p.Wt * p.Ht);
-            const int x = (w.mt % p.tilesX) * p.Wt + xl;
-            const int y = ((w.mt / p.tilesX) % p.tilesY) * p.Ht + yl;
-            const int b = (w.mt / tilesXY) * p.Nb + bl;
-            int oy = y, ox = x;
-            if (MODE == MODE_P) {
-              oy = 2 * y + (w.ph >> 1);
-              ox = 2 * x + (w.ph & 1);
-            }
-            pixv[i] = b < p.B ? (b * p.Hout + oy) * p.Wout + ox : -1;
+          const int xl = r % p.Wt, yl = (r / p.Wt) % p.Ht, bl = r / (p.Wt * p.Ht);
+          const int x = (w.mt % p.tilesX) * p.Wt + xl;
+          const int y = ((w.mt / p.tilesX) % p.tilesY) * p.Ht + yl;
+          const int b = (w.mt / tilesXY) * p.Nb + bl;
+          valid = b < p.B;
+          int oy = y, ox = x;
+          if (MODE == MODE_P) {
+            oy = 2 * y + (w.ph >> 1);
+            ox = 2 * x + (w.ph & 1);
           }
+          pix = ((long long)b * p.Hout + oy) * p.Wout + ox;
         }
         mbar_wait(&tfull[acc], acc_phase);
         if (item == clusterId && warp == 4 && lane == 0) GCT2_STAMP(4);  // first accumulator complete
         tc_fence_after();
         const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN + cgrp * COLS;
-        const float alpha = (MODE == MODE_W && p.adamW != nullptr) ? __ldg(p.hyper) : 0.f;
 #pragma unroll 1
-        for (int c0 = 0; c0 < COLS; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld_32x16(t_row + c0, v);
-          const int n = n0 + c0 + jj * 4;  // first of my four columns after the transpose
-          if (MODE == MODE_W && p.colStride != 1) {
-            // rows are the contiguous axis of dW here (up0: M side = the 256 input channels): the TMEM shape is already
-            // the coalesced one -- lane = row, 32 lanes x 4 bytes per column
-            tmem_ld_wait();
-            const long long e0 = (long long)w.ph * p.tapStride + (long long)(w.mt * 128 + q * 32 + lane) * p.rowStride +
-                                 (long long)(n0 + c0) * p.colStride;
-            float* gbase = p.atomic ? p.ws + (long long)w.split * p.wsSplitStride : p.dw;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const long long e = e0 + (long long)j * p.colStride;
-              const float gval = __uint_as_float(v[j]);
-              if (p.adamW != nullptr && !p.atomic) {
-                float mv = p.adamM[e], vv = p.adamV[e], wv = p.adamW[e];
-                adam_elem(wv, mv, vv, gval, p.c1, p.c2, alpha, p.eps);
-                p.adamM[e] = mv;
-                p.adamV[e] = vv;
-                p.adamW[e] = wv;
-                p.adamW16[e] = __float2bfloat16_rn(wv);
-                if (p.dw != nullptr) p.dw[e] = gval;
-              } else {
-                gbase[e] = gval;
-              }
-            }
-            continue;
-          }
-          if (p.epi == EPI_DGRAD) {
-            // the saved activation and the skip gradient are requested while the TMEM load is in flight
-            uint2 av[4], ov[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              av[i] = make_uint2(0x3f803f80u, 0x3f803f80u);  // bf16 1.0 = keep
-              ov[i] = make_uint2(0u, 0u);
-              if (pixv[i] >= 0) {
-                if (n < p.maskN) av[i] = __ldg(reinterpret_cast<const uint2*>(p.act + (long long)pixv[i] * p.ldact + n));
-                if (p.addOld) ov[i] = *reinterpret_cast<const uint2*>(p.out + (long long)pixv[i] * p.ldo + n);
-              }
-            }
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *stg_wr[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              float4 f = *stg_rd[i];
-              if (pixv[i] < 0) continue;
-              f.x += bf16_lo(ov[i].x); f.y += bf16_hi(ov[i].x); f.z += bf16_lo(ov[i].y); f.w += bf16_hi(ov[i].y);
-              f.x = bf16_lo(av[i].x) > 0.f ? f.x : 0.f; f.y = bf16_hi(av[i].x) > 0.f ? f.y : 0.f;
-              f.z = bf16_lo(av[i].y) > 0.f ? f.z : 0.f; f.w = bf16_hi(av[i].y) > 0.f ? f.w : 0.f;
-              uint2 res;
-              res.x = pack_bf16x2(f.x, f.y);
-              res.y = pack_bf16x2(f.z, f.w);
-              *reinterpret_cast<uint2*>(p.out + (long long)pixv[i] * p.ldo + n) = res;
-            }
-            __syncwarp();
-            continue;
-          }
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *stg_wr[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                     __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-          __syncwarp();
+        for (int c0 = 0; c0 < COLS; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + c0, v);
+          const int n = n0 + c0;
           if (p.epi == EPI_BIAS_RELU) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            tmem_ld_wait();
+            if (valid) {
+              const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
+              uint4* dst = reinterpret_cast<uint4*>(p.out + pix * p.ldo + n);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 f = *stg_rd[i];
-              if (pixv[i] < 0) continue;
-              uint2 res;
-              res.x = pack_bf16x2(fmaxf(f.x + bb.x, 0.f), fmaxf(f.y + bb.y, 0.f));
-              res.y = pack_bf16x2(fmaxf(f.z + bb.z, 0.f), fmaxf(f.w + bb.w, 0.f));
-              *reinterpret_cast<uint2*>(p.out + (long long)pixv[i] * p.ldo + n) = res;
+              for (int g = 0; g < 4; ++g) {
+                const float4 b0 = __ldg(bp + 2 * g), b1 = __ldg(bp + 2 * g + 1);
+                uint4 o;
+                o.x = pack_bf16x2(fmaxf(__uint_as_float(v[8 * g + 0]) + b0.x, 0.f),
+                                  fmaxf(__uint_as_float(v[8 * g + 1]) + b0.y, 0.f));
+                o.y = pack_bf16x2(fmaxf(__uint_as_float(v[8 * g + 2]) + b0.z, 0.f),
+                                  fmaxf(__uint_as_float(v[8 * g + 3]) + b0.w, 0.f));
+                o.z = pack_bf16x2(fmaxf(__uint_as_float(v[8 * g + 4]) + b1.x, 0.f),
+                                  fmaxf(__uint_as_float(v[8 * g + 5]) + b1.y, 0.f));
+                o.w = pack_bf16x2(fmaxf(__uint_as_float(v[8 * g + 6]) + b1.z, 0.f),
+                                  fmaxf(__uint_as_float(v[8 * g + 7]) + b1.w, 0.f));
+                dst[g] = o;
+              }
+            }
+          } else if (p.epi == EPI_DGRAD) {
+            // the saved activation and the skip gradient are requested while the TMEM load is in flight
+            uint4* dst = reinterpret_cast<uint4*>(p.out + pix * p.ldo + n);
+            const uint4* ap = reinterpret_cast<const uint4*>(p.act + pix * p.ldact + n);
+            const bool masked = valid && n < p.maskN, add = valid && p.addOld;
+            uint4 av[4], ov[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              av[g] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);  // bf16 1.0 = keep
+              ov[g] = make_uint4(0u, 0u, 0u, 0u);
+              if (masked) av[g] = __ldg(ap + g);
+              if (add) ov[g] = dst[g];
+            }
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[8 * g + j]);
+                const uint4 o = ov[g], a = av[g];
+                f[0] += bf16_lo(o.x); f[1] += bf16_hi(o.x); f[2] += bf16_lo(o.y); f[3] += bf16_hi(o.y);
+                f[4] += bf16_lo(o.z); f[5] += bf16_hi(o.z); f[6] += bf16_lo(o.w); f[7] += bf16_hi(o.w);
+                f[0] = bf16_lo(a.x) > 0.f ? f[0] : 0.f; f[1] = bf16_hi(a.x) > 0.f ? f[1] : 0.f;
+                f[2] = bf16_lo(a.y) > 0.f ? f[2] : 0.f; f[3] = bf16_hi(a.y) > 0.f ? f[3] : 0.f;
+                f[4] = bf16_lo(a.z) > 0.f ? f[4] : 0.f; f[5] = bf16_hi(a.z) > 0.f ? f[5] : 0.f;
+                f[6] = bf16_lo(a.w) > 0.f ? f[6] : 0.f; f[7] = bf16_hi(a.w) > 0.f ? f[7] : 0.f;
+                uint4 res;
+                res.x = pack_bf16x2(f[0], f[1]);
+                res.y = pack_bf16x2(f[2], f[3]);
+                res.z = pack_bf16x2(f[4], f[5]);
+                res.w = pack_bf16x2(f[6], f[7]);
+                dst[g] = res;
+              }
             }
           } else if (p.epi == EPI_WS_SLAB) {
             // split-K partial: plain stores into this split's slab (no atomics: the finishing pass sums the slabs in
-            // a fixed order, so the step is bit-reproducible).  fused finish: tile-major slab [split][tile][row][col]
-            // (compact, read back coalesced below); finishing kernel: pixel-major slab [split][pixel][N]
+            // a fixed order, so the step is bit-reproducible)
+            tmem_ld_wait();
+            if (valid) {
+              // fused finish: tile-major slab [split][tile][row][col] (compact, read back coalesced below);
+              // finishing kernel: pixel-major slab [split][pixel][N]
+              float4* dst = reinterpret_cast<float4*>(
+                  p.fused ? p.ws + (((long long)w.split * p.numTiles + tileId) * 128 + r) * BN + (n - w.nt * BN)
+                          : p.ws + (long long)w.split * p.wsSplitStride + pix * p.N + n);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 f = *stg_rd[i];
-              if (pixv[i] < 0) continue;
-              const int r = q * 32 + i * 8 + sub;
-              float* dst = p.fused ? p.ws + (((long long)w.split * p.numTiles + tileId) * 128 + r) * BN + (n - w.nt * BN)
-                                   : p.ws + (long long)w.split * p.wsSplitStride + (long long)pixv[i] * p.N + n;
-              *reinterpret_cast<float4*>(dst) = f;
+              for (int g = 0; g < 8; ++g)
+                dst[g] = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
+                                     __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
             }
-          } else {  // EPI_WGRAD, columns contiguous: row = M-side channel, my 4 columns = N-side channels
-            const long long ebase = (long long)w.ph * p.tapStride + n;
-            if (p.adamW != nullptr && !p.atomic) {
-              // Keras-Adam applied to the tile while it is still in registers (train.py:75): the
-              // gradient never travels to HBM and back, m / v / w stream through once, the bf16 shadow is rewritten.
+          } else {  // EPI_WGRAD: row = M-side channel, columns = N-side channels
+            tmem_ld_wait();
+            float* base = (p.atomic ? p.ws + (long long)w.split * p.wsSplitStride : p.dw) +
+                          (long long)w.ph * p.tapStride + (long long)(w.mt * 128 + r) * p.rowStride +
+                          (long long)n * p.colStride;
+            if (p.colStride == 1) {
+              float4* d4 = reinterpret_cast<float4*>(base);
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                float4 mv[2], vv[2], wv[2];
-                long long e[2];
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                  e[k] = ebase + (long long)(w.mt * 128 + q * 32 + (2 * h + k) * 8 + sub) * p.rowStride;
-                  mv[k] = __ldcs(reinterpret_cast<const float4*>(p.adamM + e[k]));
-                  vv[k] = __ldcs(reinterpret_cast<const float4*>(p.adamV + e[k]));
-                  wv[k] = __ldcs(reinterpret_cast<const float4*>(p.adamW + e[k]));
-                }
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                  const float4 g = *stg_rd[2 * h + k];
-                  adam_elem4(wv[k], mv[k], vv[k], g, p.c1, p.c2, alpha, p.eps);
-                  __stcs(reinterpret_cast<float4*>(p.adamM + e[k]), mv[k]);
-                  __stcs(reinterpret_cast<float4*>(p.adamV + e[k]), vv[k]);
-                  __stcs(reinterpret_cast<float4*>(p.adamW + e[k]), wv[k]);
-                  uint2 o;
-                  o.x = pack_bf16x2(wv[k].x, wv[k].y);
-                  o.y = pack_bf16x2(wv[k].z, wv[k].w);
-                  *reinterpret_cast<uint2*>(p.adamW16 + e[k]) = o;
-                  if (p.dw != nullptr) *reinterpret_cast<float4*>(p.dw + e[k]) = g;
-                }
-              }
+              for (int g = 0; g < 8; ++g)
+                d4[g] = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
+                                    __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
             } else {
-              float* gbase = p.atomic ? p.ws + (long long)w.split * p.wsSplitStride : p.dw;
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                *reinterpret_cast<float4*>(gbase + ebase + (long long)(w.mt * 128 + q * 32 + i * 8 + sub) * p.rowStride) =
-                    *stg_rd[i];
+              for (int j = 0; j < 32; ++j) base[(long long)j * p.colStride] = __uint_as_float(v[j]);
             }
           }
-          __syncwarp();
         }
         tc_fence_before();
         __syncwarp();

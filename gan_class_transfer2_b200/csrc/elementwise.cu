@@ -15,9 +15,11 @@ namespace gct2 {
 void trace_set_elementwise(unsigned long long* buf) { cudaMemcpyToSymbol(g_trace_buf, &buf, sizeof(buf)); }
 
 static int g_ew_sms = 148;
+static int g_c3w_blocks = 0;   // debug key 15: grid cap of down0's weight-gradient kernel (0 = 2 blocks per SM)
 static int g_adam_blocks = 0;  // debug key 13: grid cap of the Adam kernel (0 = 8 blocks per SM)
 void elementwise_set_debug(int key, int value) {
   if (key == 13) g_adam_blocks = value;
+  if (key == 15) g_c3w_blocks = value;
 }
 void elementwise_set_sms(int n) { g_ew_sms = n; }
 
@@ -274,9 +276,14 @@ __global__ void __launch_bounds__(256) conv_c3_wgrad_kernel(const float* __restr
         accb += g[px];
 #pragma unroll
         for (int ky = 0; ky < 4; ++ky) {
-          const float* row = &patch[2 * py + ky][2 * px * 3];
+          // the 12 floats of this tap row start 24*px bytes into a 16-byte aligned row: six 8-byte broadcast loads
+          const float2* row = reinterpret_cast<const float2*>(&patch[2 * py + ky][2 * px * 3]);
 #pragma unroll
-          for (int j = 0; j < 12; ++j) acc[ky * 12 + j] = fmaf(row[j], g[px], acc[ky * 12 + j]);
+          for (int j = 0; j < 6; ++j) {
+            const float2 xv = row[j];
+            acc[ky * 12 + 2 * j] = fmaf(xv.x, g[px], acc[ky * 12 + 2 * j]);
+            acc[ky * 12 + 2 * j + 1] = fmaf(xv.y, g[px], acc[ky * 12 + 2 * j + 1]);
+          }
         }
       }
     }
@@ -310,10 +317,10 @@ int conv4s2_c3_wgrad(const float* x, const __nv_bfloat16* dz, int lddz, float* d
     }
   }
   const int numTiles = B * (H / 2 / C3_T) * (W / 2 / C3_T);
-  // few blocks, several tiles each: the atomics per block (49 x 128) are the cost that does not shrink with the tile count
-  int gx = numTiles / 4;
-  if (gx < g_ew_sms / 2) gx = g_ew_sms / 2;
-  if (gx > 2 * g_ew_sms) gx = 2 * g_ew_sms;
+  // Two blocks per SM (16 warps hide the shared-memory latency of the FMA loop); beyond that a block walks several
+  // tiles, because the atomics per block (49 x 128) are the cost that does not shrink with the tile count.  Measured
+  // at batch 1: 74 blocks x 3.5 tiles = 47 us, 256 blocks x 1 tile (debug key 15 to vary) -- see profiles/.
+  int gx = g_c3w_blocks > 0 ? g_c3w_blocks : 2 * g_ew_sms;
   if (gx > numTiles) gx = numTiles;
   dim3 grid(gx, Cout / 128);
   launch_k(conv_c3_wgrad_kernel, dim3(grid), dim3(256), 0, st, x, dz, lddz, dw, db, B, H, W, Cout, numTiles);
@@ -633,14 +640,20 @@ __global__ void adam_prepare_kernel(long long* __restrict__ iterations, float* _
 // Memory-level parallelism is what this kernel lives on: it shares SMs with the conv CTAs (which leave room for ~14 K
 // registers, i.e. one small block), so each thread keeps ADAM_U float4 of every array in flight (16 x 16-byte loads
 // issued before the first use) and a block is only 128 threads.  Element order and arithmetic are unchanged.
-constexpr int ADAM_U = 4;
-constexpr int ADAM_THREADS = 128;
+#ifndef GCT2_ADAM_U
+#define GCT2_ADAM_U 1
+#endif
+#ifndef GCT2_ADAM_THREADS
+#define GCT2_ADAM_THREADS 256
+#endif
+constexpr int ADAM_U = GCT2_ADAM_U;
+constexpr int ADAM_THREADS = GCT2_ADAM_THREADS;
 __device__ __forceinline__ void adam_update(float4& wv, float4& mv, float4& vv, float4 gv, float gscale, float c1,
                                             float c2, float alpha, float eps) {
   gv.x *= gscale; gv.y *= gscale; gv.z *= gscale; gv.w *= gscale;
   adam_elem4(wv, mv, vv, gv, c1, c2, alpha, eps);
 }
-__global__ void __launch_bounds__(ADAM_THREADS, 5) adam_kernel(float4* __restrict__ w, float4* __restrict__ m,
+__global__ void __launch_bounds__(ADAM_THREADS, 640 / ADAM_THREADS) adam_kernel(float4* __restrict__ w, float4* __restrict__ m,
                                                             float4* __restrict__ v, const float4* __restrict__ g,
                                                             uint2* __restrict__ wb, long long nvec,
                                                             const float* __restrict__ hyper, float b1, float b2,

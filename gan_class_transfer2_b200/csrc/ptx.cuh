@@ -97,13 +97,8 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
-// L2 prefetch of one box (no shared-memory destination, no barrier): used for the weight operand, whose HBM fetch
-// is started before the kernel's first real load can be issued.
-__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* m, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(
-                   reinterpret_cast<uint64_t>(m)),
-               "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 // Multicast variants: the box lands at the same shared-memory offset in every CTA of `mask` (bit = rank in cluster) and

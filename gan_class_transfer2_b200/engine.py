@@ -185,7 +185,6 @@ class UNetEngine:
         mode = os.environ.get("GCT2_OVERLAP", "all")  # test hook: none | wgrad | adam | all
         self.overlap_wgrad = mode in ("all", "wgrad")
         self.overlap_adam = mode in ("all", "adam")
-        self.fuse_adam = os.environ.get("GCT2_FUSE_ADAM", "0") == "1"  # 1 = optimiser inside the wgrad launches
         self._side = torch.cuda.Stream(device=self.device)
         self._side_adam = torch.cuda.Stream(device=self.device)
         self._graph = None
@@ -373,63 +372,27 @@ class UNetEngine:
                                    self.w16[start:end], self.hyper, cfg.beta1, cfg.beta2, cfg.epsilon, 1.0,
                                    iterations_inc=self.iterations if (inc_iterations and start == 0) else None)
 
-        # Single GPU: the optimiser rides on the weight gradients (gct2_*_wgrad_adam) -- the gradient of a tensor-core
-        # kernel never goes to HBM and back and only the small head region is left for the Adam kernel.  That launch
-        # rewrites the layer's bf16 weights, so it is released after the layer's own dgrad (their last reader), one
-        # link later in the chain than a plain wgrad.  Data parallel: gradients must exist to be summed -- plain wgrad.
-        fuse = self.fuse_adam and apply_adam and dp is None
-
-        def wgrad_up(i):
-            name = f"up{i}/kernel"
-            if fuse:
-                ops.convT4s2_wgrad_adam(self.up_in_buf(i), self.gup_out(i), None, self.view(self.w, name),
-                                        self.view(self.m, name), self.view(self.v, name), self.view(self.w16, name),
-                                        self.hyper, cfg.beta1, cfg.beta2, cfg.epsilon, self.ws_w)
-            else:
-                ops.convT4s2_wgrad(self.up_in_buf(i), self.gup_out(i), self.view(self.g, name), self.ws_w)
-
-        def wgrad_down(i):
-            name = f"down{i}/kernel"
-            if fuse:
-                ops.conv4s2_wgrad_adam(self.down_in(i), self.gdown_out(i), None, self.view(self.w, name),
-                                       self.view(self.m, name), self.view(self.v, name), self.view(self.w16, name),
-                                       self.hyper, cfg.beta1, cfg.beta2, cfg.epsilon, self.ws_w)
-            else:
-                ops.conv4s2_wgrad(self.down_in(i), self.gdown_out(i), self.view(self.g, name), self.ws_w)
-
         for i in range(n):  # up0 .. up{n-1}
-            if not fuse:
-                on_side(lambda: wgrad_up(i))
+            on_side(lambda: ops.convT4s2_wgrad(self.up_in_buf(i), self.gup_out(i), self.view(self.g, f"up{i}/kernel"),
+                                               self.ws_w))
             mask = cfg.down_c(i) if i == n - 1 else cfg.up_c(i + 1)
             ops.convT4s2_dgrad(self.gup_out(i), self.view(self.w16, f"up{i}/kernel"), self.gup_in_buf(i),
                                self.up_in_buf(i), mask, self.ws)
-            if fuse:
-                on_side(lambda: wgrad_up(i))
-            else:
-                bucket_done(f"up{i}/kernel")
+            bucket_done(f"up{i}/kernel")
         for i in reversed(range(1, n)):  # down{n-1} .. down1
-            if not fuse:
-                on_side(lambda: wgrad_down(i))
+            on_side(lambda: ops.conv4s2_wgrad(self.down_in(i), self.gdown_out(i), self.view(self.g, f"down{i}/kernel"),
+                                              self.ws_w))
             # total gradient of down_{i-1}'s output = skip-path part (already stored raw by up_{i-1}'s dgrad) + this
             ops.conv4s2_dgrad(self.gdown_out(i), self.view(self.w16, f"down{i}/kernel"), self.gcat[i][..., cfg.up_c(i):],
                               self.down_in(i), True, self.ws)
-            if fuse:
-                on_side(lambda: wgrad_down(i))
-            else:
-                bucket_done(f"down{i}/kernel")
+            bucket_done(f"down{i}/kernel")
         ops.conv4s2_c3_wgrad(self.noised, self.gdown_out(0), self.view(self.g, "down0/kernel"), None, accumulate=True)
         # every conv layer's BiasAddGrad in one launch: the pre-activation gradients all still sit in their buffers
         ops.bias_grad_multi(self._bias_plan, accumulate=True)
-        if fuse:
-            # what is left for the Adam kernel: down0's kernel, every bias, the Dense layer (the head region)
-            ops.adam_apply(self.w[:self.small], self.m[:self.small], self.v[:self.small], self.g[:self.small],
-                           self.w16[:self.small], self.hyper, cfg.beta1, cfg.beta2, cfg.epsilon, 1.0,
-                           iterations_inc=self.iterations if inc_iterations else None)
-        else:
-            bucket_done("down0/kernel")
+        bucket_done("down0/kernel")
         if sw is not main:
             main.wait_stream(sw)
-        if sa is not main and not fuse:  # (fused: nothing was enqueued on the Adam stream)
+        if sa is not main:
             main.wait_stream(sa)
         for work in pending:
             work.wait()

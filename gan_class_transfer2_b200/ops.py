@@ -173,30 +173,6 @@ def convT4s2_wgrad(x, dy, dw, ws: Optional[Workspace] = None):
 
 
 @_timed
-def conv4s2_wgrad_adam(x, dy, dw, w, m, v, w_bf16, hyper, beta1: float, beta2: float, eps: float,
-                       ws: Optional[Workspace] = None):
-    """DownShuffle weight gradient fed straight into Keras-Adam for this kernel (dw may be None: not stored)."""
-    lib = _lib_for(x)
-    B, H, W, Cin = x.shape
-    check(lib.gct2_conv4s2_wgrad_adam(ptr(x), _nhwc(x, torch.bfloat16), ptr(dy), _nhwc(dy, torch.bfloat16), ptr(dw),
-                                      ptr(w), ptr(m), ptr(v), ptr(w_bf16), ptr(hyper), beta1, beta2, eps, B, H, W,
-                                      Cin, dy.shape[3], ptr(ws.buf) if ws else 0, ws.nbytes if ws else 0,
-                                      current_stream()))
-
-
-@_timed
-def convT4s2_wgrad_adam(x, dy, dw, w, m, v, w_bf16, hyper, beta1: float, beta2: float, eps: float,
-                        ws: Optional[Workspace] = None):
-    """UpShuffle weight gradient fed straight into Keras-Adam for this kernel (dw may be None: not stored)."""
-    lib = _lib_for(x)
-    B, H, W, Cin = x.shape
-    check(lib.gct2_convT4s2_wgrad_adam(ptr(x), _nhwc(x, torch.bfloat16), ptr(dy), _nhwc(dy, torch.bfloat16), ptr(dw),
-                                       ptr(w), ptr(m), ptr(v), ptr(w_bf16), ptr(hyper), beta1, beta2, eps, B, H, W,
-                                       Cin, dy.shape[3], ptr(ws.buf) if ws else 0, ws.nbytes if ws else 0,
-                                       current_stream()))
-
-
-@_timed
 def bias_grad(dz, db):
     lib = _lib_for(dz)
     ld = _nhwc(dz, torch.bfloat16)

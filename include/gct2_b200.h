@@ -40,10 +40,10 @@ long long gct2_launch_count(void);
 /* Test hook (not part of the drop-in surface): key 0/1 override the MN-major UMMA descriptor LBO/SBO bytes,
  * key 2 = verbose plan logging, key 3 = force N tile, key 4 = force split-K, keys 5/6 = force the cluster shape
  * (CTAs along M / along N; 0 = heuristic, 1 = none), key 7 = record per-CTA phase timestamps (gct2_debug_timeline),
- * key 8 != 0 = launch without programmatic dependent launch, keys 9 / 10 = CTA budget of the wgrad / fprop+dgrad
+ * key 8 != 0 = launch without programmatic dependent launch, keys 9 / 10 = CTA budget of the wgrad / dgrad
  * launches (0 = all SMs; lets the concurrent backward chains run on disjoint SM sets), key 11 = whole-step launch
  * trace (gct2_debug_trace), key 12 != 0 = finish split-K with a separate kernel instead of inside the launch, key 13 = grid cap of the
- * Adam kernel (0 = 8 blocks per SM), key 14 != 0 = L2 prefetch of the weight operand in the conv prologue (experiment, off). */
+ * Adam kernel (0 = 8 blocks per SM), key 15 = grid cap of the down0 weight-gradient kernel (0 = 2 blocks per SM). */
 void gct2_debug_set(int key, int value);
 /* Test hook: after gct2_debug_set(7, 1) every tensor-core conv launch records, per CTA, 8 %globaltimer stamps (ns):
  * [0] entry, [1] prologue done, [2] first operands landed, [3] MMAs of the first tile issued, [4] first accumulator
@@ -108,20 +108,6 @@ int gct2_convT4s2_dgrad(const uint16_t* dy, int lddy, const uint16_t* w, uint16_
 /* Backward-filter of UpShuffle: dw[ky,kx,co,ci] = sum dy[b,2iy-1+ky,2ix-1+kx,co]*x[b,iy,ix,ci]; fp32, overwritten. */
 int gct2_convT4s2_wgrad(const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, int B, int H, int W,
                         int Cin, int Cout, float* ws, size_t ws_bytes, void* stream);
-
-/* Backward-filter fused with the optimiser (Keras train_step's tape.gradient + Adam.apply_gradients for ONE kernel
- * variable, train.py:75,516): the weight gradient of gct2_conv4s2_wgrad / gct2_convT4s2_wgrad is fed to Keras-Adam
- * while it is still on chip -- in the wgrad epilogue, or in the split-K reduction -- so it never makes the HBM round
- * trip.  w, m, v: fp32 variable and Adam slots in the kernel's Keras layout (updated in place); w_bf16: the bf16 copy
- * the tensor-core kernels read (rewritten); hyper[0] = this step's alpha (gct2_adam_prepare / gct2_step_begin);
- * dw: fp32 gradient output or NULL (not stored).  Same arithmetic, element for element, as gct2_adam_apply on dw.
- * The caller must order the call after every reader of w_bf16 of this step (the layer's own dgrad). */
-int gct2_conv4s2_wgrad_adam(const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, float* w, float* m,
-                            float* v, uint16_t* w_bf16, const float* hyper, float beta1, float beta2, float eps,
-                            int B, int H, int W, int Cin, int Cout, float* ws, size_t ws_bytes, void* stream);
-int gct2_convT4s2_wgrad_adam(const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, float* w, float* m,
-                             float* v, uint16_t* w_bf16, const float* hyper, float beta1, float beta2, float eps,
-                             int B, int H, int W, int Cin, int Cout, float* ws, size_t ws_bytes, void* stream);
 
 /* BiasAddGrad of every conv layer: db[c] = sum over rows of dz[row*ld + c]; dz bf16, db fp32 (overwritten). */
 int gct2_bias_grad(const uint16_t* dz, int ld, long long rows, int C, float* db, void* stream);

@@ -389,43 +389,6 @@ def check_adam(n=4096 + 128, steps=3, seed=11):
     return worst
 
 
-def check_wgrad_adam(B, H, Cin, Cout, up=False, seed=14, steps=2):
-    """gct2_*_wgrad_adam == gct2_*_wgrad followed by gct2_adam_apply, bit for bit (w, m, v, bf16 shadow, stored dw) --
-    and the unfused pair is what check_*_wgrad / check_adam pin against the oracle.  Second call: dw=None."""
-    ops = _ops()
-    g = torch.Generator().manual_seed(seed)
-    dev = _dev()
-    hi = 2 * H if up else H          # resolution of the high-res side
-    xs = (B, H, H, Cin)
-    dys = (B, 2 * H, 2 * H, Cout) if up else (B, H // 2, H // 2, Cout)
-    kshape = (4, 4, Cout, Cin) if up else (4, 4, Cin, Cout)
-    n = 16 * Cin * Cout
-    w0 = _rand(kshape, g).to(dev)
-    state = {k: [w0.clone(), torch.zeros(kshape, device=dev), torch.zeros(kshape, device=dev),
-                 torch.zeros(kshape, dtype=torch.bfloat16, device=dev)] for k in ("fused", "plain")}
-    hyper = torch.tensor([3e-4, 1e-3], device=dev)
-    ws = ops.Workspace(64 << 20, dev)
-    wgrad = ops.convT4s2_wgrad if up else ops.conv4s2_wgrad
-    fused = ops.convT4s2_wgrad_adam if up else ops.conv4s2_wgrad_adam
-    worst = 0.0
-    for s in range(steps):
-        x = _bf(_rand(xs, g)).to(dev)
-        dy = _bf(_rand(dys, g) * 1e-3).to(dev)
-        dw_plain = torch.empty(kshape, device=dev)
-        wgrad(x, dy, dw_plain, ws)
-        wp, mp, vp, bp = state["plain"]
-        ops.adam_apply(wp.view(-1), mp.view(-1), vp.view(-1), dw_plain.view(-1), bp.view(-1), hyper, 0.9, 0.999, 1e-7)
-        dw_fused = torch.full(kshape, 5.0, device=dev) if s == 0 else None
-        wf, mf, vf, bf = state["fused"]
-        fused(x, dy, dw_fused, wf, mf, vf, bf, hyper, 0.9, 0.999, 1e-7, ws)
-        torch.cuda.synchronize()
-        pairs = [(wf, wp), (mf, mp), (vf, vp), (bf.float(), bp.float())] + ([(dw_fused, dw_plain)] if s == 0 else [])
-        worst = max([worst] + [float((a - b).abs().max()) for a, b in pairs])
-    moved = float((state["fused"][0] - w0).abs().max())
-    return {"name": f"{'convT' if up else 'conv'}4s2_wgrad_adam B{B} H{H} {Cin}x{Cout} hi{hi} n{n}", "err": worst,
-            "tol": 0.0, "moved": moved, "pad_intact": moved > 0.0}
-
-
 # (function, kwargs) -- sized so the CPU references finish in seconds.
 CONV_CASES = [
     (check_conv_fprop, dict(B=2, H=16, Cin=64, Cout=64)),
@@ -446,11 +409,6 @@ CONV_CASES = [
     (check_convT_wgrad, dict(B=2, H=8, Cin=128, Cout=64)),
     (check_convT_wgrad, dict(B=1, H=16, Cin=64, Cout=128)),
     (check_convT_wgrad, dict(B=3, H=4, Cin=256, Cout=256)),
-    # optimiser fused into the weight gradient: epilogue path (rows = 128-multiples), rows-contiguous path (Chi = 64)
-    (check_wgrad_adam, dict(B=1, H=8, Cin=256, Cout=256)),
-    (check_wgrad_adam, dict(B=2, H=16, Cin=128, Cout=64)),
-    (check_wgrad_adam, dict(B=1, H=4, Cin=512, Cout=256, up=True)),
-    (check_wgrad_adam, dict(B=1, H=8, Cin=256, Cout=64, up=True)),
 ]
 EW_CASES = [
     (check_noise, {}),
@@ -500,13 +458,6 @@ FORCED_CASES = [
     (check_conv_wgrad, dict(B=4, H=32, Cin=128, Cout=256), dict(BN=256, splits=2)),
     (check_convT_wgrad, dict(B=4, H=16, Cin=256, Cout=64), dict(BN=64, splits=4)),
     (check_convT_wgrad, dict(B=4, H=16, Cin=256, Cout=128), dict(BN=256, splits=16)),
-    # ... and the optimiser inside the split-K reduction / inside every epilogue width
-    (check_wgrad_adam, dict(B=4, H=32, Cin=128, Cout=256), dict(BN=64, splits=8)),
-    (check_wgrad_adam, dict(B=4, H=32, Cin=128, Cout=256), dict(BN=128, splits=1)),
-    (check_wgrad_adam, dict(B=4, H=32, Cin=128, Cout=256), dict(BN=256, splits=1)),
-    (check_wgrad_adam, dict(B=2, H=8, Cin=256, Cout=64, up=True), dict(BN=64, splits=1)),
-    (check_wgrad_adam, dict(B=2, H=8, Cin=256, Cout=64, up=True), dict(BN=64, splits=2)),
-    (check_wgrad_adam, dict(B=2, H=8, Cin=256, Cout=256, up=True), dict(BN=256, splits=1)),
     # split-K finished by the separate kernel (the fallback when a CTA owns more than one work item)
     (check_conv_fprop, dict(B=2, H=16, Cin=128, Cout=256), dict(BN=128, splits=4, nofuse=1)),
     (check_convT_fprop, dict(B=2, H=8, Cin=128, Cout=256), dict(BN=256, splits=8, nofuse=1)),
