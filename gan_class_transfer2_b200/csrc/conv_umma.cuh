@@ -204,7 +204,10 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
     // consume it (128-512 cycles), and a deeper ring does not help because the limit is issue, not latency.  Three
     // producer threads in three warps take the k-iterations round-robin (producer j owns global iteration g = j mod
     // 3): measured 2.6x the single-producer rate in isolation.
-    if (lane == 0) {
+    // elect.sync (not `lane == 0`) picks the thread: ptxas then knows exactly one thread runs the loop and feeds the
+    // uniform-datapath instructions (UTMALDG / UTCHMMA / UTCBAR) directly instead of wrapping each one in a
+    // vote-and-branch loop over "possibly several" active threads.
+    if (elect_one()) {
       constexpr uint32_t NP = 3;
       const uint32_t pj = warp == 0 ? 0u : (uint32_t)warp - 1u;
       uint32_t gbase = 0;
@@ -296,7 +299,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr int A_MN = (MODE == MODE_W) ? 1 : 0;
       constexpr int B_MN = (MODE == MODE_P) ? 0 : 1;
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, A_MN, B_MN);
@@ -315,12 +318,12 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
+          // one descriptor pair per stage; the four K = 16 slices only advance the 14-bit address field
+          const uint64_t da0 = make_smem_desc(sa, a_lbo, a_sbo), db0 = make_smem_desc(sb, b_lbo, b_sbo);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo);
-            const uint64_t db = make_smem_desc(sb + k * b_kstep, b_lbo, b_sbo);
-            umma_bf16(d_tmem, da, db, idesc, (it | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d_tmem, da0 + (uint64_t)((k * a_kstep) >> 4), db0 + (uint64_t)((k * b_kstep) >> 4), idesc,
+                      (it | k) != 0 ? 1u : 0u);
           // frees the smem slot once these MMAs have read it -- in my CTA and, in a cluster, in every CTA that
           // multicasts into my slot (my row and my column)
           if (csize == 1)
