@@ -21,6 +21,7 @@ void set_error(const char* fmt, ...) {
 }
 
 int g_use_pdl = 1;
+static int g_stamp_pos = 0;            // debug key 16: see ConvParams::stampPos
 static int g_fuse_finish = 1;          // debug key 12 != 0 disables the in-kernel split-K finish
 static int* g_cnt = nullptr;           // rendezvous counters of the fused finish: [FUSE_MAX_TILES][2], zero at rest
 constexpr int FUSE_MAX_TILES = 4096;
@@ -79,6 +80,7 @@ void conv_set_debug(int key, int value) {
   if (key == 8) g_use_pdl = value ? 0 : 1;  // key 8 != 0 disables programmatic dependent launch
   if (key == 9) g_cap_w = value;
   if (key == 12) g_fuse_finish = value ? 0 : 1;
+  if (key == 16) g_stamp_pos = value;
   if (key == 10) g_cap_sp = value;
   if (key == 7) {
     if (value && g_dbg == nullptr) cudaMalloc(&g_dbg, (size_t)DBG_MAX_CTAS * 8 * sizeof(unsigned long long));
@@ -544,6 +546,22 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
   }
 
   p.stages = stages_for(BN);
+  p.stampPos = g_stamp_pos;
+  {
+    auto lg2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
+    if ((p.Wt & (p.Wt - 1)) || (p.Ht & (p.Ht - 1)) || (p.tilesX & (p.tilesX - 1)) || (p.tilesY & (p.tilesY - 1))) {
+      set_error("conv: pixel-tile geometry must be power-of-two (tile %dx%d, tiles %dx%d)", p.Ht, p.Wt, p.tilesY, p.tilesX);
+      return 1;
+    }
+    p.lgWt = lg2(p.Wt); p.lgHt = lg2(p.Ht); p.lgTilesX = lg2(p.tilesX); p.lgTilesY = lg2(p.tilesY);
+    p.fdMTilesC = make_fastdiv((uint32_t)(p.mTiles / p.cm));
+    p.fdNTilesC = make_fastdiv((uint32_t)(p.nTiles / p.cn));
+    p.fdSplits = make_fastdiv((uint32_t)p.splits);
+    p.fdKcPer = make_fastdiv((uint32_t)(p.kcPer > 0 ? p.kcPer : 1));
+    p.fdStages = make_fastdiv((uint32_t)p.stages);
+    p.fdCn = make_fastdiv((uint32_t)p.cn);
+    p.fdCm = make_fastdiv((uint32_t)p.cm);
+  }
   const size_t smem = smem_for(BN);
   const int csize = p.cm * p.cn;
   p.numClusterItems = p.numItems / csize;

@@ -34,6 +34,28 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   return v;
 }
 
+// n / d for 0 <= n < 2^31 with a multiply-high and a shift (host-side magic numbers): an integer division by a run-time
+// value costs a single thread 150-300 cycles, and the producer's start-up alone had ten of them on the critical path
+// of every launch (1.2 us of the 2.4 us between griddepcontrol.wait and the first MMA, tools/timeline.py + key 16).
+struct FastDiv {
+  uint32_t d, mul, shr;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f{d, 0u, 0u};
+  if (d > 1) {
+    uint32_t lg = 0;
+    while ((1u << lg) < d) ++lg;
+    const uint32_t pw = 31 + lg;
+    f.mul = (uint32_t)(((1ull << pw) + d - 1) / d);
+    f.shr = pw - 32;
+  }
+  return f;
+}
+__device__ __forceinline__ int fd_div(const FastDiv& f, int n) {
+  return f.d == 1 ? n : (int)(__umulhi((uint32_t)n, f.mul) >> f.shr);
+}
+__device__ __forceinline__ int fd_mod(const FastDiv& f, int n) { return n - fd_div(f, n) * (int)f.d; }
+
 struct ConvParams {
   int B, Hlo, Wlo;             // lo-res spatial extent (hi-res = 2x)
   int Wt, Ht, Nb;              // pixel-tile geometry; rows = Nb*Ht*Wt (128 for S/P, 64 for W)
@@ -55,6 +77,10 @@ struct ConvParams {
   int realEpi;                 // fused: the epilogue to apply after the slabs are summed (EPI_BIAS_RELU / EPI_DGRAD)
   int numTiles;                // fused: phases * nTiles * mTiles
   int* cnt;                    // fused: [numTiles][2] arrive / depart counters, zero between launches
+  // fast division by the launch constants used in index decoding (all set by conv_launch)
+  FastDiv fdMTilesC, fdNTilesC, fdSplits, fdKcPer, fdStages, fdCn, fdCm;
+  int lgWt, lgHt, lgTilesX, lgTilesY;  // pixel-tile geometry is power-of-two by construction
+  int stampPos;                // test hook (debug key 16): which point of the producer's start-up stamp 7 records
   unsigned long long* dbg;     // test hook: per-CTA phase timestamps (8 x u64 per CTA, %globaltimer ns) or nullptr
   // epilogue
   int epi;
@@ -83,19 +109,18 @@ struct WorkItem {
 template <int MODE>
 __device__ __forceinline__ WorkItem decode_item(const ConvParams& p, int item, int rm, int rn) {
   WorkItem w;
-  const int mTilesC = p.mTiles / p.cm, nTilesC = p.nTiles / p.cn;
-  w.mt = (item % mTilesC) * p.cm + rm;
-  int r = item / mTilesC;
+  w.mt = fd_mod(p.fdMTilesC, item) * p.cm + rm;
+  int r = fd_div(p.fdMTilesC, item);
   if (MODE == MODE_W) {
-    w.nt = (r % nTilesC) * p.cn + rn;
-    r /= nTilesC;
-    w.split = r % p.splits;
-    w.ph = r / p.splits;
+    w.nt = fd_mod(p.fdNTilesC, r) * p.cn + rn;
+    r = fd_div(p.fdNTilesC, r);
+    w.split = fd_mod(p.fdSplits, r);
+    w.ph = fd_div(p.fdSplits, r);
   } else {
-    w.split = r % p.splits;
-    r /= p.splits;
-    w.nt = (r % nTilesC) * p.cn + rn;
-    w.ph = r / nTilesC;
+    w.split = fd_mod(p.fdSplits, r);
+    r = fd_div(p.fdSplits, r);
+    w.nt = fd_mod(p.fdNTilesC, r) * p.cn + rn;
+    w.ph = fd_div(p.fdNTilesC, r);
   }
   return w;
 }
@@ -154,7 +179,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
   // cluster geometry (cm*cn == 1: plain launch, every mask below is unused)
   const int csize = p.cm * p.cn;
   const int crank = csize > 1 ? (int)cluster_ctarank() : 0;
-  const int rm = crank / p.cn, rn = crank % p.cn;
+  const int rm = fd_div(p.fdCn, crank), rn = fd_mod(p.fdCn, crank);
   const int clusterId = blockIdx.x / csize, numClusters = gridDim.x / csize;
   const uint16_t rowMask = (uint16_t)(((1u << p.cn) - 1u) << (rm * p.cn));   // CTAs sharing my M tile (A multicast)
   uint16_t colMask = 0;                                                        // CTAs sharing my N tile (B multicast)
@@ -208,6 +233,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
     // uniform-datapath instructions (UTMALDG / UTCHMMA / UTCBAR) directly instead of wrapping each one in a
     // vote-and-branch loop over "possibly several" active threads.
     if (elect_one()) {
+      if (warp == 0 && p.stampPos == 0) GCT2_STAMP(7);  // test hook: where the time before the first load goes
       constexpr uint32_t NP = 3;
       const uint32_t pj = warp == 0 ? 0u : (uint32_t)warp - 1u;
       uint32_t gbase = 0;
@@ -215,24 +241,27 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
         const WorkItem w = decode_item<MODE>(p, item, rm, rn);
         int x0 = 0, y0 = 0, b0 = 0;
         if (MODE != MODE_W) {
-          x0 = (w.mt % p.tilesX) * p.Wt;
-          y0 = ((w.mt / p.tilesX) % p.tilesY) * p.Ht;
-          b0 = (w.mt / tilesXY) * p.Nb;
+          x0 = (w.mt & (p.tilesX - 1)) << p.lgWt;
+          y0 = ((w.mt >> p.lgTilesX) & (p.tilesY - 1)) << p.lgHt;
+          b0 = (w.mt >> (p.lgTilesX + p.lgTilesY)) * p.Nb;
         }
+        if (warp == 0 && item == clusterId && p.stampPos == 1) GCT2_STAMP(7);
         for (int it = (int)((pj + NP - gbase % NP) % NP); it < p.kIters; it += (int)NP) {
           const int kit = w.split * p.kIters + it;
           const uint32_t g = gbase + (uint32_t)it;
-          const uint32_t stage = g % (uint32_t)S, phase = (g / (uint32_t)S) & 1u;
+          const uint32_t ring = (uint32_t)fd_div(p.fdStages, (int)g), stage = g - ring * (uint32_t)S, phase = ring & 1u;
+          if (g == 0 && p.stampPos == 2) GCT2_STAMP(7);
           mbar_wait(&empty[stage], phase ^ 1);
+          if (g == 0 && p.stampPos == 3) GCT2_STAMP(7);
           mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           // In a cluster the CTAs of a row take turns fetching the shared A tile (and those of a column the shared
           // B tile) and multicast it; every CTA still expects the full stage on its own barrier.
-          const bool doA = p.cn == 1 || (it % p.cn) == rn;
-          const bool doB = p.cm == 1 || (it % p.cm) == rm;
+          const bool doA = p.cn == 1 || fd_mod(p.fdCn, it) == rn;
+          const bool doB = p.cm == 1 || fd_mod(p.fdCm, it) == rm;
           if (MODE == MODE_S) {
-            const int tap = kit / p.kcPer, kc = kit % p.kcPer;
+            const int tap = fd_div(p.fdKcPer, kit), kc = kit - tap * p.kcPer;
             const int ky = tap >> 2, kx = tap & 3;
             const int py = (ky + 1) & 1, px = (kx + 1) & 1;
             const int hy = ((ky + 1) >> 1) - 1, hx = ((kx + 1) >> 1) - 1;
@@ -252,7 +281,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
               }
             }
           } else if (MODE == MODE_P) {
-            const int t4 = kit / p.kcPer, kc = kit % p.kcPer;
+            const int t4 = fd_div(p.fdKcPer, kit), kc = kit - t4 * p.kcPer;
             const int ty = t4 >> 1, tx = t4 & 1;
             const int py = w.ph >> 1, px = w.ph & 1;
             const int ky = (1 - py) + 2 * ty, kx = (1 - px) + 2 * tx;
@@ -270,9 +299,9 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
             }
           } else {
             // pixel chunk -> (batch tile, y tile, x tile)
-            const int cx = (kit % p.tilesX) * p.Wt;
-            const int cy = ((kit / p.tilesX) % p.tilesY) * p.Ht;
-            const int cb = (kit / tilesXY) * p.Nb;
+            const int cx = (kit & (p.tilesX - 1)) << p.lgWt;
+            const int cy = ((kit >> p.lgTilesX) & (p.tilesY - 1)) << p.lgHt;
+            const int cb = (kit >> (p.lgTilesX + p.lgTilesY)) * p.Nb;
             const int ky = w.ph >> 2, kx = w.ph & 3;
             const int py = (ky + 1) & 1, px = (kx + 1) & 1;
             const int hy = ((ky + 1) >> 1) - 1, hx = ((kx + 1) >> 1) - 1;
@@ -294,6 +323,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
                             cy + hy, cb);
             }
           }
+          if (g == 0 && p.stampPos == 4) GCT2_STAMP(7);
         }
       }
     }
@@ -361,10 +391,10 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
         bool valid = true;
         long long pix = 0;
         if (MODE != MODE_W) {
-          const int xl = r % p.Wt, yl = (r / p.Wt) % p.Ht, bl = r / (p.Wt * p.Ht);
-          const int x = (w.mt % p.tilesX) * p.Wt + xl;
-          const int y = ((w.mt / p.tilesX) % p.tilesY) * p.Ht + yl;
-          const int b = (w.mt / tilesXY) * p.Nb + bl;
+          const int xl = r & (p.Wt - 1), yl = (r >> p.lgWt) & (p.Ht - 1), bl = r >> (p.lgWt + p.lgHt);
+          const int x = ((w.mt & (p.tilesX - 1)) << p.lgWt) + xl;
+          const int y = (((w.mt >> p.lgTilesX) & (p.tilesY - 1)) << p.lgHt) + yl;
+          const int b = (w.mt >> (p.lgTilesX + p.lgTilesY)) * p.Nb + bl;
           valid = b < p.B;
           int oy = y, ox = x;
           if (MODE == MODE_P) {
@@ -497,10 +527,10 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
           const long long splitStride = (long long)p.numTiles * 128 * BN;
           for (int idx = et; idx < R * vecPerRow; idx += NT) {
             const int rr = w.split * R + idx / vecPerRow, c4 = (idx % vecPerRow) * 4;
-            const int xl = rr % p.Wt, yl = (rr / p.Wt) % p.Ht, bl = rr / (p.Wt * p.Ht);
-            const int b = (w.mt / tilesXY) * p.Nb + bl;
+            const int xl = rr & (p.Wt - 1), yl = (rr >> p.lgWt) & (p.Ht - 1), bl = rr >> (p.lgWt + p.lgHt);
+            const int b = (w.mt >> (p.lgTilesX + p.lgTilesY)) * p.Nb + bl;
             if (b >= p.B) continue;
-            int oy = ((w.mt / p.tilesX) % p.tilesY) * p.Ht + yl, ox = (w.mt % p.tilesX) * p.Wt + xl;
+            int oy = (((w.mt >> p.lgTilesX) & (p.tilesY - 1)) << p.lgHt) + yl, ox = ((w.mt & (p.tilesX - 1)) << p.lgWt) + xl;
             if (MODE == MODE_P) {
               oy = 2 * oy + (w.ph >> 1);
               ox = 2 * ox + (w.ph & 1);

@@ -128,6 +128,36 @@ __global__ void __launch_bounds__(256, 1) probe_ab(const __grid_constant__ CUten
   __syncthreads();
 }
 
+// Latency of ONE TMA box load (issue -> mbarrier complete), first use of the descriptor in the launch vs later uses.
+__global__ void __launch_bounds__(128, 1) probe_lat(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                                                    int prefetchDesc, unsigned long long* out) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bar = (uint64_t*)(smem + 65536);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (prefetchDesc) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&mapA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&mapB) : "memory");
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (prefetchDesc) { long long t = clock64(); while (clock64() - t < 4000) {} }   // give the prefetch 2 us
+    uint32_t ph = 0;
+    for (int rep = 0; rep < 6; ++rep) {
+      const long long t0 = clock64();
+      mbar_expect(bar, rep < 3 ? 16384 : 8192);
+      if (rep < 3) tma5(smem, &mapA, bar, (rep & 1) * 512, rep * 16, 0, 8 * rep, 0);
+      else tma3(smem + 16384, &mapB, bar, 64 * rep, 64 * rep, rep);
+      mbar_wait(bar, ph);
+      ph ^= 1;
+      out[blockIdx.x * 8 + rep] = (unsigned long long)(clock64() - t0);
+    }
+  }
+}
+
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int main() {
@@ -175,12 +205,23 @@ int main() {
       }
     }
   }
+  CK(cudaFuncSetAttribute(probe_lat, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  printf("\nlatency_cycles,prefetch_desc,A5d_first,A5d_2nd,A5d_3rd,B3d_first,B3d_2nd,B3d_3rd\n");
+  for (int pf : {0, 1}) {
+    for (int rep = 0; rep < 2; ++rep) {
+      probe_lat<<<1, 128, 90 * 1024>>>(m5, m3, pf, out);
+      CK(cudaDeviceSynchronize());
+      unsigned long long h[8];
+      CK(cudaMemcpy(h, out, 64, cudaMemcpyDeviceToHost));
+      printf("lat,%d,%llu,%llu,%llu,%llu,%llu,%llu\n", pf, h[0], h[1], h[2], h[3], h[4], h[5]);
+    }
+  }
   CK(cudaFuncSetAttribute(probe_ab, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   printf("\nkernel_like,nb,stage_KB,stages,producers,ctas,cycles_per_stage,B_per_clk_per_SM,aggregate_TBs\n");
   for (int nb : {1, 2, 4}) {
     const int stageBytes = 16384 + nb * 8192;
     const int stages = 192 * 1024 / stageBytes;
-    for (int producers : {1, 2, 3, 4, 6}) {
+    for (int producers : {1, 3}) {
       for (int ctas : {32, 148}) {
         const int iters = 1200;
         for (int rep = 0; rep < 2; ++rep) probe_ab<<<ctas, 256, 200 * 1024 + 2048>>>(m5, m3, stages, iters, nb, producers, out);
