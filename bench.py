@@ -10,8 +10,9 @@ Prints ONE JSON line (rank 0).  Workload: BASELINE.json configs[1] -- train.py's
   value     images/s, inputs already resident in HBM (x staged in the engine; t_int/eps drawn on the device per step)
   e2e       images/s through the public API (train.Trainer.train_step) with a pinned HOST batch copied in every step
             and the scalar loss read back every step
-  roofline  the dominant kernel family (tcgen05 implicit-GEMM convs): algorithmic FLOPs / summed CUDA-event durations
-            of its launches in one instrumented step, against the measured bf16 peak (MEASURED_PEAKS.json)
+  roofline  the dominant kernel family (tcgen05 implicit-GEMM convs): algorithmic FLOPs / CUDA-event time of its 33
+            launches of one step replayed back to back from a CUDA graph, against the measured sustained bf16 peak
+            (MEASURED_PEAKS.json); traffic = DRAM bytes per launch from the committed ncu capture (profiles/)
   cpu_baseline  the oracle (PyTorch-CPU fp32 restatement of train.py) timed on this box's host cores
 """
 from __future__ import annotations
@@ -261,14 +262,39 @@ def main():
     final_loss = float(loss_host.item())
 
     # ---- roofline of the dominant kernel family, measured live
+    # (a) the family alone: its 33 launches of one step captured into a CUDA graph (same plans and launch chaining as
+    #     in the step, nothing else running), replayed and timed with CUDA events -> average launch duration;
+    # (b) one eager step with every op bracketed by events -> each op's share of the step (serialised).
     pk = peaks()
+    fam_graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        eng.conv_family_pass()
+    torch.cuda.current_stream().wait_stream(side)
+    before = ops.launch_count()
+    with torch.cuda.graph(fam_graph):
+        eng.conv_family_pass()
+    fam_launches = ops.launch_count() - before
+    for _ in range(3):
+        fam_graph.replay()
+    reps = 50
+    s3, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    s3.record()
+    for _ in range(reps):
+        fam_graph.replay()
+    e3.record()
+    torch.cuda.synchronize()
+    conv_us = s3.elapsed_time(e3) * 1e3 / reps
+    del fam_graph
     prof = instrumented_step(eng, torch, ops)
     sequence = prof.pop("__sequence__")
     if args.dump_ops and rank == 0:
         with open(args.dump_ops, "w") as f:
             json.dump(sequence, f)
     conv_ops = [k for k in prof if k.startswith("conv") and "c3" not in k]
-    conv_us = sum(sum(prof[k]) for k in conv_ops)
+    conv_us_eager = sum(sum(prof[k]) for k in conv_ops)
     conv_launches = sum(len(prof[k]) for k in conv_ops)
     total_us = sum(sum(v) for v in prof.values())
     # FLOPs of the tensor-core family = step total minus down0 (fprop+wgrad, CUDA cores) and dense (fwd+2 bwd)
@@ -277,14 +303,17 @@ def main():
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            traffic = json.load(f).get("traffic_bytes_per_launch")
+            traffic = json.load(f).get(f"traffic_bytes_per_launch_b{B}")
     except Exception:  # noqa: BLE001
         pass
     roofline = {"bound": "tensor", "kernel": "conv_umma_kernel<MODE,BN> (tcgen05 implicit-GEMM conv family, "
                                              f"{conv_launches} launches/step)",
                 "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["bf16_sustained"], "traffic": traffic, "peak_source": pk["source"] + " (sustained)",
-                "avg_launch_us": conv_us / max(conv_launches, 1), "family_share_of_step": conv_us / max(total_us, 1e-9),
+                "how": f"{flops_conv / 1e9:.1f} GFLOP of the family per step / CUDA-event time of its launches replayed "
+                       f"back to back from a graph ({fam_launches} launches incl. split-K passes, {reps} replays)",
+                "avg_launch_us": conv_us / max(conv_launches, 1), "family_us_per_step": conv_us,
+                "family_share_of_step": conv_us_eager / max(total_us, 1e-9),
                 "step_achieved": value / world * GFLOP_PER_IMAGE * 1e9 / 1e12,
                 "step_frac": value / world * GFLOP_PER_IMAGE * 1e9 / 1e12 / pk["bf16_sustained"],
                 "per_op_us": {k: round(sum(v), 1) for k, v in prof.items()}}

@@ -304,15 +304,12 @@ static void query_all_clusters() {
 }
 
 // Cost model (SM cycles at ~1.97 GHz) for one launch, fitted to per-CTA phase timelines measured on B200
-// (tools/timeline.py, profiles/r1b_timeline_b1.txt):
-//   * a CTA ingests operands at a per-SM rate: one 128 x BN x 64 k-step costs (TMA round trip 2800)/stages +
-//     stage_bytes/153 cycles (measured with 4 stages: 0.42 us at BN=64 ... 0.50 us at BN=256) whether 32 or 128 CTAs
-//     are active and with or without multicast -- the tensor pipe
-//     (2*BN cycles per k-step) is never the limit at these tile shapes, so the plan that minimises ingested bytes per
-//     SM wins: wide tiles, split-K to occupy every SM;
-//   * fixed per CTA: prologue 0.5 us + first TMA round trip 1.4 us + teardown 0.2 us (clusters: +1.3 us);
-//   * epilogue (16 warps; 8 at BN=64): ~1 us + 4 ns per column, 1.6x for the dgrad epilogue (two extra operand loads);
-//   * split-K: partial stores cost like a wide epilogue, then a finishing pass (launch gap + slab traffic).
+// (tools/timeline.py; profiles/): fixed start-up + k-steps + epilogue, where
+//   * a k-step is issue-bound (MMA issuer: wait, 4 UMMAs, commit; three TMA producers keep up) until all SMs together
+//     exceed what L2 delivers -- wide tiles ingest fewer bytes per FLOP and win at large batch;
+//   * split-K buys parallelism for the price of a partial tile's round trip through L2 and a rendezvous (fused) or an
+//     extra launch (finishing kernel) -- with cheap k-steps it pays only when a layer has very few tiles;
+//   * epilogues scale with the tile's real rows: deep layers at batch 1 fill 16-64 of a tile's 128 rows.
 static Choice choose(int mode, int mTiles, int phases, int N, int kTotal, long long outElems, bool dgradEpi,
                      int forceBN, int forceSplits, int forceCm, int forceCn, size_t slabBytes, size_t wsBytes) {
   Choice best{0, 1, 1, 1};
@@ -352,14 +349,30 @@ static Choice choose(int mode, int mTiles, int phases, int N, int kTotal, long l
           const long long items = (long long)mTiles * phases * (isW ? 16 : 1) * nTiles * splits;
           const long long active = items < maxCtas ? items : maxCtas;
           const long long rounds = (items + active - 1) / active;
-          double tk = 2800.0 / stages_for(BN) + (16384.0 + BN * 128.0) / 153.0;
-          const double l2 = (16384.0 / cn + BN * 128.0 / cm) * (double)active / 4800.0;  // chip-wide L2 read rate
+          // one k-step: issue-bound at small grids (measured 470 / 525 / 655 cycles at BN = 64 / 128 / 256), bound by
+          // the chip-wide L2 -> SM rate (~6000 B/clk) when every SM pulls at once
+          double tk = 408.0 + 0.96 * BN;
+          const double l2 = (16384.0 / cn + BN * 128.0 / cm) * (double)active / 6000.0;
           if (l2 > tk) tk = l2;
-          double epi = 2000.0 + 8.0 * BN;
-          if (splits == 1 && dgradEpi) epi *= 1.6;
           const double main = kIters * tk;
-          double cost = 4100.0 + (cs > 1 ? 2600.0 : 0.0) + rounds * main + epi + (rounds - 1) * (epi > main ? epi - main : 0.0);
-          if (splits > 1) cost += 5000.0 + (double)outElems * (4.0 * splits + 6.0) / 2000.0;
+          // rows of a 128-row tile that hold real pixels (deep layers at batch 1 have 16 .. 64)
+          double validRows = isW ? 128.0 : (double)outElems / ((double)N * mTiles * phases);
+          if (validRows > 128.0) validRows = 128.0;
+          double epi;
+          if (splits > 1 && !isW) {
+            // partial tile to its slab and back through L2 (~14.5 B/clk per CTA each way) + the rendezvous
+            epi = 5000.0 + 2.0 * validRows * BN * 4.0 / 14.5;
+            // finished by a separate kernel: a launch + every slab read once more, at the chip-wide rate
+            if (items > maxCtas || cs > 1) epi += 6000.0 + (double)outElems * 4.0 * (splits + 0.5) / 3000.0;
+          } else if (isW) {
+            epi = 35.0 * BN;                                // fp32 tile straight to HBM
+            if (splits > 1) epi += 5000.0 + (double)outElems * 4.0 * (splits + 1.0) / 3000.0;  // + reduction kernel
+          } else {
+            epi = dgradEpi ? 600.0 + 30.0 * BN : 1000.0 + 15.0 * BN;
+            epi *= 0.25 + 0.75 * validRows / 128.0;
+          }
+          // fixed per launch: prologue 0.7 us + first loads 1.45 us + teardown 0.25 us (clusters: + 1.3 us)
+          double cost = 4800.0 + (cs > 1 ? 2600.0 : 0.0) + rounds * main + epi + (rounds - 1) * (epi > main ? epi - main : 0.0);
           if (cost < bestCost) {
             bestCost = cost;
             best = Choice{BN, splits, cm, cn};

@@ -473,6 +473,28 @@ class UNetEngine:
             self._graph[draw] = graph
         self._graph[draw].replay()
 
+    def conv_family_pass(self) -> None:
+        """Measurement aid (bench.py's roofline): the 33 tensor-core launches of one step -- 11 fprops, 11 dgrads,
+        11 wgrads, in step order -- back to back on the current stream and nothing else, over whatever the buffers
+        hold.  Same plans, same programmatic dependent launch chaining as inside the step; the optimiser, the
+        CUDA-core kernels and the side streams are left out so that the time is the family's alone."""
+        cfg, n = self.cfg, self.cfg.octaves
+        for i in range(1, n):
+            ops.conv4s2_fprop(self.down_in(i), self.view(self.w16, f"down{i}/kernel"),
+                              self.view(self.w, f"down{i}/bias"), self.down_out(i), self.ws)
+        for i in reversed(range(n)):
+            ops.convT4s2_fprop(self.up_in_buf(i), self.view(self.w16, f"up{i}/kernel"),
+                               self.view(self.w, f"up{i}/bias"), self.up_out(i), self.ws)
+        for i in range(n):
+            ops.convT4s2_wgrad(self.up_in_buf(i), self.gup_out(i), self.view(self.g, f"up{i}/kernel"), self.ws_w)
+            mask = cfg.down_c(i) if i == n - 1 else cfg.up_c(i + 1)
+            ops.convT4s2_dgrad(self.gup_out(i), self.view(self.w16, f"up{i}/kernel"), self.gup_in_buf(i),
+                               self.up_in_buf(i), mask, self.ws)
+        for i in reversed(range(1, n)):
+            ops.conv4s2_wgrad(self.down_in(i), self.gdown_out(i), self.view(self.g, f"down{i}/kernel"), self.ws_w)
+            ops.conv4s2_dgrad(self.gdown_out(i), self.view(self.w16, f"down{i}/kernel"), self.gcat[i][..., cfg.up_c(i):],
+                              self.down_in(i), True, self.ws)
+
     def release_graphs(self) -> None:
         """Drops the captured step graphs.  Data-parallel callers do this before ``destroy_process_group``: NCCL keeps a
         communicator alive (and its destruction waits) while a CUDA graph that captured one of its collectives
