@@ -21,6 +21,7 @@ void set_error(const char* fmt, ...) {
 }
 
 int g_use_pdl = 1;
+static int g_stages = 0;               // debug key 17: cap of the pipeline depth (0 = as deep as shared memory allows)
 static int g_stamp_pos = 0;            // debug key 16: see ConvParams::stampPos
 static int g_fuse_finish = 1;          // debug key 12 != 0 disables the in-kernel split-K finish
 static int* g_cnt = nullptr;           // rendezvous counters of the fused finish: [FUSE_MAX_TILES][2], zero at rest
@@ -81,6 +82,7 @@ void conv_set_debug(int key, int value) {
   if (key == 9) g_cap_w = value;
   if (key == 12) g_fuse_finish = value ? 0 : 1;
   if (key == 16) g_stamp_pos = value;
+  if (key == 17) g_stages = value;
   if (key == 10) g_cap_sp = value;
   if (key == 7) {
     if (value && g_dbg == nullptr) cudaMalloc(&g_dbg, (size_t)DBG_MAX_CTAS * 8 * sizeof(unsigned long long));
@@ -263,7 +265,10 @@ __global__ void wgrad_reduce_kernel(const float4* __restrict__ ws, long long spl
 // ------------------------------------------------------------------------------------ heuristics
 // every tile width fills the same 192 KB of pipeline: a CTA's operand ingest rate is (bytes in flight) / (TMA round
 // trip, ~1.4 us), so the ring is as deep as shared memory allows -- 8 x 24 KB, 6 x 32 KB, 4 x 48 KB
-static int stages_for(int BN) { return BN == 256 ? 4 : (BN == 128 ? 6 : 8); }
+static int stages_for(int BN) {
+  const int s = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  return g_stages > 0 && g_stages < s ? g_stages : s;
+}
 // pipeline stages + barriers (256 B) + 1 KB alignment slack
 static size_t smem_for(int BN) { return (size_t)stages_for(BN) * (16384 + BN * 128) + 1024 + 256; }
 

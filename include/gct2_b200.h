@@ -43,11 +43,12 @@ long long gct2_launch_count(void);
  * key 8 != 0 = launch without programmatic dependent launch, keys 9 / 10 = CTA budget of the wgrad / dgrad
  * launches (0 = all SMs; lets the concurrent backward chains run on disjoint SM sets), key 11 = whole-step launch
  * trace (gct2_debug_trace), key 12 != 0 = finish split-K with a separate kernel instead of inside the launch, key 13 = grid cap of the
- * Adam kernel (0 = 8 blocks per SM), key 15 = grid cap of the down0 weight-gradient kernel (0 = 2 blocks per SM). */
+ * Adam kernel (0 = 8 blocks per SM), key 15 = grid cap of the down0 weight-gradient kernel (0 = 2 blocks per SM), key 16 = which
+ * point of the TMA producer's start-up timeline stamp [7] records (0 loop entry .. 4 first loads issued). */
 void gct2_debug_set(int key, int value);
 /* Test hook: after gct2_debug_set(7, 1) every tensor-core conv launch records, per CTA, 8 %globaltimer stamps (ns):
  * [0] entry, [1] prologue done, [2] first operands landed, [3] MMAs of the first tile issued, [4] first accumulator
- * complete, [5] first epilogue done, [6] CTA done.  Synchronises the device and copies the stamps of the most
+ * complete, [5] first epilogue done, [6] CTA done, [7] see key 16.  Synchronises the device and copies the stamps of the most
  * recent launch (up to max_ctas CTAs) to `host`; returns the number of CTAs. */
 int gct2_debug_timeline(unsigned long long* host, int max_ctas);
 /* Test hook: after gct2_debug_set(11, 1) the first and last block of EVERY launch of this library append
