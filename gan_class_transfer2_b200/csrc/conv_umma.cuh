@@ -232,10 +232,15 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
     // elect.sync (not `lane == 0`) picks the thread: ptxas then knows exactly one thread runs the loop and feeds the
     // uniform-datapath instructions (UTMALDG / UTCHMMA / UTCBAR) directly instead of wrapping each one in a
     // vote-and-branch loop over "possibly several" active threads.
-    if (elect_one()) {
+    // No more producers than ring slots: producer j may only wait for slot s's r-th release once the (r-1)-th has
+    // happened, or the parity wait aliases and it overwrites a live slot.  Its previous stage (g - NP) could be issued
+    // only after the consumer released g - NP - S, and the consumer releases in order, so g - 2S is released whenever
+    // S >= NP.  (The default rings have 4-8 slots; the guard matters for the depth cap of debug key 17.)
+    const uint32_t NP = S < 3 ? (uint32_t)S : 3u;
+    const uint32_t pj = warp == 0 ? 0u : (uint32_t)warp - 1u;
+    auto modNP = [NP](uint32_t x) { return NP == 3u ? x % 3u : (NP == 2u ? (x & 1u) : 0u); };
+    if (pj < NP && elect_one()) {
       if (warp == 0 && p.stampPos == 0) GCT2_STAMP(7);  // test hook: where the time before the first load goes
-      constexpr uint32_t NP = 3;
-      const uint32_t pj = warp == 0 ? 0u : (uint32_t)warp - 1u;
       uint32_t gbase = 0;
       for (int item = clusterId; item < p.numClusterItems; item += numClusters, gbase += (uint32_t)p.kIters) {
         const WorkItem w = decode_item<MODE>(p, item, rm, rn);
@@ -246,7 +251,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
           b0 = (w.mt >> (p.lgTilesX + p.lgTilesY)) * p.Nb;
         }
         if (warp == 0 && item == clusterId && p.stampPos == 1) GCT2_STAMP(7);
-        for (int it = (int)((pj + NP - gbase % NP) % NP); it < p.kIters; it += (int)NP) {
+        for (int it = (int)modNP(pj + NP - modNP(gbase)); it < p.kIters; it += (int)NP) {
           const int kit = w.split * p.kIters + it;
           const uint32_t g = gbase + (uint32_t)it;
           const uint32_t ring = (uint32_t)fd_div(p.fdStages, (int)g), stage = g - ring * (uint32_t)S, phase = ring & 1u;
