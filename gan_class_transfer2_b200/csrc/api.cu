@@ -202,8 +202,19 @@ int gct2_adam_apply(float* w, float* m, float* v, const float* g, uint16_t* w_bf
 int gct2_step_begin(const float* x, float* noised, float* eps_out, int32_t* t_out, int B, int elems_per_image, int steps,
                     unsigned long long seed, const long long* iterations, float* hyper, float base_lr, int warmup_steps,
                     float beta1, float beta2, float* gsmall, long long nsmall, float* loss, void* stream) {
-  return step_begin(x, noised, eps_out, t_out, B, elems_per_image, steps, seed, iterations, hyper, base_lr, warmup_steps,
-                    beta1, beta2, gsmall, nsmall, loss, S(stream));
+  return step_begin(x, nullptr, nullptr, nullptr, 0, noised, eps_out, t_out, B, elems_per_image, steps, seed, iterations,
+                    hyper, base_lr, warmup_steps, beta1, beta2, gsmall, nsmall, loss, S(stream));
+}
+int gct2_step_begin_u8(const uint8_t* img, const uint8_t* flip, float* x_out, int width, float* noised, float* eps_out,
+                       int32_t* t_out, int B, int elems_per_image, int steps, unsigned long long seed,
+                       const long long* iterations, float* hyper, float base_lr, int warmup_steps, float beta1,
+                       float beta2, float* gsmall, long long nsmall, float* loss, void* stream) {
+  if (img == nullptr) {
+    set_error("gct2_step_begin_u8: img is null");
+    return 1;
+  }
+  return step_begin(nullptr, img, flip, x_out, width, noised, eps_out, t_out, B, elems_per_image, steps, seed, iterations,
+                    hyper, base_lr, warmup_steps, beta1, beta2, gsmall, nsmall, loss, S(stream));
 }
 
 int gct2_cast_bf16(const float* src, uint16_t* dst, long long n, void* stream) {

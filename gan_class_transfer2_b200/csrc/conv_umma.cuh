@@ -80,6 +80,8 @@ struct ConvParams {
   // fast division by the launch constants used in index decoding (all set by conv_launch)
   FastDiv fdMTilesC, fdNTilesC, fdSplits, fdKcPer, fdStages, fdCn, fdCm;
   int lgWt, lgHt, lgTilesX, lgTilesY;  // pixel-tile geometry is power-of-two by construction
+  int pair;                    // CTA pairs (cta_group::2): needs cm == 2, cn == 1, BN >= 128; each CTA keeps its own M tile,
+                               // loads half of the B tile, and rank 0 issues one 256-row MMA for both
   int stampPos;                // test hook (debug key 16): which point of the producer's start-up stamp 7 records
   unsigned long long* dbg;     // test hook: per-CTA phase timestamps (8 x u64 per CTA, %globaltimer ns) or nullptr
   // epilogue
@@ -152,14 +154,18 @@ __host__ __device__ constexpr int kConvThreads() {
 #ifndef GCT2_CONV_EXTRA_BOUND
 #define GCT2_CONV_EXTRA_BOUND 0
 #endif
-template <int MODE, int BN>
+// PAIR = 1: the cta_group::2 variant (a separate instantiation: a kernel that contains cta_group::2 instructions can
+// only be launched as a cluster of an even number of CTAs).
+template <int MODE, int BN, int PAIR = 0>
 __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1) conv_umma_kernel(const __grid_constant__ CUtensorMap mapA,
                                                         const __grid_constant__ CUtensorMap mapB,
                                                         const ConvParams p) {
   constexpr int A_BYTES = 128 * 128;  // 128 rows x 64 bf16 (S/P) or 2 blocks of 64 pixels x 64 channels (W)
   constexpr int B_BYTES = BN * 128;
-  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int BLK = 64 * 128;       // one 64x64 bf16 block = one TMA box of an MN-major operand
+  constexpr bool pair = PAIR != 0;
+  // a CTA of a pair stages only its half of the B tile
+  const int STAGE_BYTES = A_BYTES + (pair ? B_BYTES / 2 : B_BYTES);
   constexpr uint32_t TMEM_COLS = 2 * BN;
 
   extern __shared__ uint8_t smem_raw[];
@@ -193,18 +199,25 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S; ++i) {
       mbar_init(&full[i], 1);
-      // a slot is free once every CTA that multicasts into it ... i.e. every consumer of my row and column is done
-      mbar_init(&empty[i], p.cm + p.cn - 1);
+      // a slot is free once every CTA that multicasts into it ... i.e. every consumer of my row and column is done;
+      // in a pair the leader's single commit is multicast to both CTAs
+      mbar_init(&empty[i], pair ? 1 : p.cm + p.cn - 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], kEpilogueWarps<BN>());
+      // pair: the leader's accumulator buffer is free once the epilogues of BOTH CTAs have drained theirs
+      mbar_init(&tempty[i], (pair ? 2 : 1) * kEpilogueWarps<BN>());
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if (pair) {
+      tmem_alloc_pair(tmem_slot, TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -258,7 +271,11 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
           if (g == 0 && p.stampPos == 2) GCT2_STAMP(7);
           mbar_wait(&empty[stage], phase ^ 1);
           if (g == 0 && p.stampPos == 3) GCT2_STAMP(7);
-          mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+          // pair: one arrival on the LEADER's barrier announces the bytes of both CTAs; the loads of both complete there
+          if (!pair)
+            mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+          else if (rm == 0)
+            mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           // In a cluster the CTAs of a row take turns fetching the shared A tile (and those of a column the shared
@@ -270,13 +287,18 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
             const int ky = tap >> 2, kx = tap & 3;
             const int py = (ky + 1) & 1, px = (kx + 1) & 1;
             const int hy = ((ky + 1) >> 1) - 1, hx = ((kx + 1) >> 1) - 1;
-            if (doA) {
+            if (pair) {
+              tma_load_5d_pair(sa, &mapA, &full[stage], px * p.ldG + kc * 64, x0 + hx, py, y0 + hy, b0);
+#pragma unroll
+              for (int j = 0; j < BN / 128; ++j)  // my half of the tile's columns
+                tma_load_3d_pair(sb + j * BLK, &mapB, &full[stage], w.nt * BN + rm * (BN / 2) + j * 64, kc * 64, tap);
+            } else if (doA) {
               if (p.cn == 1)
                 tma_load_5d(sa, &mapA, &full[stage], px * p.ldG + kc * 64, x0 + hx, py, y0 + hy, b0);
               else
                 tma_load_5d_mc(sa, &mapA, &full[stage], px * p.ldG + kc * 64, x0 + hx, py, y0 + hy, b0, rowMask);
             }
-            if (doB) {
+            if (doB && !pair) {
 #pragma unroll
               for (int j = 0; j < BN / 64; ++j) {
                 if (p.cm == 1)
@@ -290,13 +312,17 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
             const int ty = t4 >> 1, tx = t4 & 1;
             const int py = w.ph >> 1, px = w.ph & 1;
             const int ky = (1 - py) + 2 * ty, kx = (1 - px) + 2 * tx;
-            if (doA) {
+            if (pair) {
+              tma_load_4d_pair(sa, &mapA, &full[stage], kc * 64, x0 + (px - tx), y0 + (py - ty), b0);
+              // my half of the tile's rows (the host built this map with BN/2-row boxes)
+              tma_load_3d_pair(sb, &mapB, &full[stage], kc * 64, w.nt * BN + rm * (BN / 2), ky * 4 + kx);
+            } else if (doA) {
               if (p.cn == 1)
                 tma_load_4d(sa, &mapA, &full[stage], kc * 64, x0 + (px - tx), y0 + (py - ty), b0);
               else
                 tma_load_4d_mc(sa, &mapA, &full[stage], kc * 64, x0 + (px - tx), y0 + (py - ty), b0, rowMask);
             }
-            if (doB) {
+            if (doB && !pair) {
               if (p.cm == 1)
                 tma_load_3d(sb, &mapB, &full[stage], kc * 64, w.nt * BN, ky * 4 + kx);
               else
@@ -310,7 +336,27 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
             const int ky = w.ph >> 2, kx = w.ph & 3;
             const int py = (ky + 1) & 1, px = (kx + 1) & 1;
             const int hy = ((ky + 1) >> 1) - 1, hx = ((kx + 1) >> 1) - 1;
-            if (p.gIsA) {
+            if (pair) {
+              // my own 128 M-side channels, my half of the N-side channels; both land on the leader's barrier
+              const int nb0 = w.nt * BN + rm * (BN / 2);
+              if (p.gIsA) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                  tma_load_5d_pair(sa + j * BLK, &mapA, &full[stage], px * p.ldG + w.mt * 128 + j * 64, cx + hx, py,
+                                   cy + hy, cb);
+#pragma unroll
+                for (int j = 0; j < BN / 128; ++j)
+                  tma_load_4d_pair(sb + j * BLK, &mapB, &full[stage], nb0 + j * 64, cx, cy, cb);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                  tma_load_4d_pair(sa + j * BLK, &mapA, &full[stage], w.mt * 128 + j * 64, cx, cy, cb);
+#pragma unroll
+                for (int j = 0; j < BN / 128; ++j)
+                  tma_load_5d_pair(sb + j * BLK, &mapB, &full[stage], px * p.ldG + nb0 + j * 64, cx + hx, py,
+                                   cy + hy, cb);
+              }
+            } else if (p.gIsA) {
 #pragma unroll
               for (int j = 0; j < 2; ++j)
                 tma_load_5d(sa + j * BLK, &mapA, &full[stage], px * p.ldG + w.mt * 128 + j * 64, cx + hx, py,
@@ -333,11 +379,12 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
+    // ------------------------------------------------------------------ MMA issuer (pair: the leader CTA only)
+    if ((!pair || rm == 0) && elect_one()) {
       constexpr int A_MN = (MODE == MODE_W) ? 1 : 0;
       constexpr int B_MN = (MODE == MODE_P) ? 0 : 1;
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, A_MN, B_MN);
+      constexpr uint32_t idesc2 = make_idesc_bf16(256, BN, A_MN, B_MN);  // cta_group::2: 256 rows over the pair
       const uint32_t a_lbo = A_MN ? (uint32_t)p.mnLbo : 16u, a_sbo = A_MN ? (uint32_t)p.mnSbo : 1024u;
       const uint32_t b_lbo = B_MN ? (uint32_t)p.mnLbo : 16u, b_sbo = B_MN ? (uint32_t)p.mnSbo : 1024u;
       constexpr uint32_t a_kstep = A_MN ? 2048u : 32u;  // bytes per UMMA_K = 16 along K
@@ -355,13 +402,22 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
           const uint32_t sb = sa + A_BYTES;
           // one descriptor pair per stage; the four K = 16 slices only advance the 14-bit address field
           const uint64_t da0 = make_smem_desc(sa, a_lbo, a_sbo), db0 = make_smem_desc(sb, b_lbo, b_sbo);
+          if (pair) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(d_tmem, da0 + (uint64_t)((k * a_kstep) >> 4), db0 + (uint64_t)((k * b_kstep) >> 4), idesc,
-                      (it | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_pair(d_tmem, da0 + (uint64_t)((k * a_kstep) >> 4), db0 + (uint64_t)((k * b_kstep) >> 4), idesc2,
+                             (it | k) != 0 ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d_tmem, da0 + (uint64_t)((k * a_kstep) >> 4), db0 + (uint64_t)((k * b_kstep) >> 4), idesc,
+                        (it | k) != 0 ? 1u : 0u);
+          }
           // frees the smem slot once these MMAs have read it -- in my CTA and, in a cluster, in every CTA that
           // multicasts into my slot (my row and my column)
-          if (csize == 1)
+          if (pair)
+            umma_commit_pair(&empty[stage], 0x3);  // the slot is free in both CTAs
+          else if (csize == 1)
             umma_commit(&empty[stage]);
           else
             umma_commit_mc(&empty[stage], peerMask);
@@ -370,7 +426,10 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
             phase ^= 1;
           }
         }
-        umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        if (pair)
+          umma_commit_pair(&tfull[acc], 0x3);  // both CTAs' accumulator halves complete -> both epilogues
+        else
+          umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
         if (item == clusterId) GCT2_STAMP(3);  // all MMAs of the first item issued
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
@@ -579,7 +638,12 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
           }
         }
         if (item == clusterId && warp == 4 && lane == 0) GCT2_STAMP(5);  // first epilogue (of warp 4) done
-        if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (lane == 0) {
+          if (pair && rm != 0)
+            mbar_arrive_remote(&tempty[acc], 0);  // the leader's MMA thread waits for both CTAs' epilogues
+          else
+            mbar_arrive(&tempty[acc]);
+        }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -593,7 +657,10 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
   trace.end();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (pair)
+      tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else
+      tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 

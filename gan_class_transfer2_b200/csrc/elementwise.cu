@@ -101,7 +101,13 @@ __device__ __forceinline__ float u32_to_unit_open(uint32_t v) {  // (0, 1]
   return ((float)(v >> 8) + 1.0f) * (1.0f / 16777216.0f);
 }
 
-__global__ void __launch_bounds__(256) step_begin_kernel(const float4* __restrict__ x, float4* __restrict__ noised,
+// U8: the batch arrives as the decoded JPEG bytes (train.py:285-293 decode_file): x = u8 / 128 - 1, optionally mirrored
+// left-right per image (tf.image.random_flip_left_right, the draw stays with the caller); the fp32 image is written
+// for the loss and never read back by this kernel.
+template <bool U8>
+__global__ void __launch_bounds__(256) step_begin_kernel(const float4* __restrict__ x, const uint8_t* __restrict__ x_u8,
+                                                         const uint8_t* __restrict__ flip, float4* __restrict__ x_out,
+                                                         int W, float4* __restrict__ noised,
                                                          float4* __restrict__ eps_out, int* __restrict__ t_out,
                                                          int B, int vecPerImage, int steps, unsigned long long seed,
                                                          const long long* __restrict__ iterations,
@@ -143,14 +149,37 @@ __global__ void __launch_bounds__(256) step_begin_kernel(const float4* __restric
     const float om = 1.f - t;
     const float abar = om * om * 0.25f;
     const float sa = sqrtf(abar), sb = sqrtf(1.f - abar);
-    const float4 xv = __ldg(x + i);
+    float4 xv;
+    if (U8) {
+      const long long e0 = (i - (long long)b * vecPerImage) * 4;  // first of my four scalars inside image b (HWC, C = 3)
+      const uint8_t* img = x_u8 + (long long)b * vecPerImage * 4;
+      const bool mirror = flip != nullptr && flip[b] != 0;
+      float f[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        long long e = e0 + j;
+        if (mirror) {
+          const long long pix = e / 3;
+          const int c = (int)(e - pix * 3);
+          const long long row = pix / W;
+          const int col = (int)(pix - row * W);
+          e = (row * W + (W - 1 - col)) * 3 + c;
+        }
+        f[j] = (float)__ldg(img + e) * (1.0f / 128.0f) - 1.0f;
+      }
+      xv = make_float4(f[0], f[1], f[2], f[3]);
+      x_out[i] = xv;
+    } else {
+      xv = __ldg(x + i);
+    }
     if (eps_out != nullptr) eps_out[i] = ev;
     noised[i] = make_float4(xv.x * sa + ev.x * sb, xv.y * sa + ev.y * sb, xv.z * sa + ev.z * sb, xv.w * sa + ev.w * sb);
   }
   trace.end();
 }
 
-int step_begin(const float* x, float* noised, float* eps_out, int* t_out, int B, int elemsPerImage, int steps,
+int step_begin(const float* x, const uint8_t* x_u8, const uint8_t* flip, float* x_out, int W, float* noised,
+               float* eps_out, int* t_out, int B, int elemsPerImage, int steps,
                unsigned long long seed, const long long* iterations, float* hyper, float base_lr, int warmup_steps,
                float beta1, float beta2, float* gsmall, long long nsmall, float* loss, cudaStream_t st) {
   if (elemsPerImage % 4 || nsmall % 4) {
@@ -162,7 +191,20 @@ int step_begin(const float* x, float* noised, float* eps_out, int* t_out, int B,
   int blocks = (int)((total + 255) / 256);
   if (blocks > g_ew_sms * 8) blocks = g_ew_sms * 8;
   if (blocks < 1) blocks = 1;
-  launch_k(step_begin_kernel, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(noised),
+  if (x_u8 != nullptr) {
+    if (x_out == nullptr || W < 1 || elemsPerImage % (3 * W)) {
+      set_error("step_begin: the uint8 input needs x_out and a width that divides the image (W=%d)", W);
+      return 1;
+    }
+    launch_k(step_begin_kernel<true>, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const float4*>(x), x_u8, flip,
+             reinterpret_cast<float4*>(x_out), W, reinterpret_cast<float4*>(noised), reinterpret_cast<float4*>(eps_out),
+             t_out, B, vec, steps, seed, iterations, hyper, base_lr, warmup_steps, beta1, beta2,
+             reinterpret_cast<float4*>(gsmall), nsmall / 4, loss);
+    GCT2_CHECK_LAUNCH("step_begin_kernel<u8>");
+    return 0;
+  }
+  launch_k(step_begin_kernel<false>, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const float4*>(x), x_u8, flip,
+           reinterpret_cast<float4*>(x_out), W, reinterpret_cast<float4*>(noised),
                                            reinterpret_cast<float4*>(eps_out), t_out, B, vec, steps, seed, iterations,
                                            hyper, base_lr, warmup_steps, beta1, beta2,
                                            reinterpret_cast<float4*>(gsmall), nsmall / 4, loss);

@@ -226,6 +226,8 @@ class UNetEngine:
         # ---- activations and their gradients
         bf = dict(dtype=torch.bfloat16, device=dev)
         self.x = torch.zeros(B, S, S, 3, **f32)
+        self.x_u8 = torch.zeros(B, S, S, 3, dtype=torch.uint8, device=dev)   # decode_file's bytes (train.py:285-293)
+        self.flip = torch.zeros(B, dtype=torch.uint8, device=dev)           # per-image left-right flip flags
         self.eps = torch.zeros(B, S, S, 3, **f32)
         self.t_int = torch.ones(B, dtype=torch.int32, device=dev)
         self.noised = torch.zeros(B, S, S, 3, **f32)
@@ -405,10 +407,15 @@ class UNetEngine:
         self.loss.zero_()
 
     # ------------------------------------------------------------------------------------------ public steps
-    def _step_body(self, draw: bool) -> None:
+    def _step_body(self, draw: bool, u8: bool = False) -> None:
         cfg = self.cfg
         inv_n = 1.0 / (self.global_batch * cfg.size * cfg.size * 3)
-        if draw:
+        if u8:
+            # the batch as decode_file's uint8 bytes: decode (+ flip) happens inside the prologue launch
+            ops.step_begin_u8(self.x_u8, self.flip, self.x, self.noised, self.iterations, self.hyper,
+                              self.g[:self.small], self.loss, self.rng_seed, cfg.steps, cfg.base_lr, cfg.warm_up,
+                              cfg.beta1, cfg.beta2, t_out=self.t_int)
+        elif draw:
             # train.py:224-234 in one launch: t_int ~ U{1..steps} and epsilon ~ N(0,1) drawn on the device (Philox,
             # offset by the optimiser iteration), noising, zeroing of the atomically-accumulated gradients + loss, and
             # this step's Adam alpha; the iteration counter is advanced by the step's last Adam launch
@@ -419,7 +426,19 @@ class UNetEngine:
             ops.adam_prepare(self.iterations, self.hyper, cfg.base_lr, cfg.warm_up, cfg.beta1, cfg.beta2)
             ops.noise_images(self.x, self.eps, self.t_int, self.noised, cfg.steps)
         self._forward(want_pred=False, backward=True, inv_n=inv_n)
-        self._backward(apply_adam=True, inc_iterations=draw)
+        self._backward(apply_adam=True, inc_iterations=draw or u8)
+
+    def train_step_u8(self, img: torch.Tensor, flip: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One training step on the batch as it leaves the reference's decode_file before the cast
+        (train.py:285-293): img uint8 [B,S,S,3] (host or device), flip uint8 [B] or None (no mirroring).  A quarter of
+        the host-to-device bytes of train_step; t_int / eps are drawn on the device."""
+        self.x_u8.copy_(img, non_blocking=True)
+        if flip is None:
+            self.flip.zero_()
+        else:
+            self.flip.copy_(flip, non_blocking=True)
+        self.run_step(draw=True, u8=True)
+        return self.loss
 
     def set_batch(self, x: torch.Tensor, t_int: Optional[torch.Tensor] = None,
                   eps: Optional[torch.Tensor] = None) -> None:
@@ -449,29 +468,30 @@ class UNetEngine:
         for dst, src in zip((self.w, self.m, self.v, self.w16, self.iterations), saved):
             dst.copy_(src)
 
-    def run_step(self, draw: bool = True) -> None:
+    def run_step(self, draw: bool = True, u8: bool = False) -> None:
         """The step on whatever set_batch staged (the part bench.py times as `value`)."""
         if not self.use_graph:
-            self._step_body(draw)
+            self._step_body(draw, u8)
             return
         if self._graph is None:
             self._graph = {}
-        if draw not in self._graph:
+        key = (draw, u8)
+        if key not in self._graph:
             # warm up once eagerly on a side stream (lazy inits must not happen under capture), then capture
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 saved = self._save_state()
-                self._step_body(draw)
+                self._step_body(draw, u8)
                 self._restore_state(saved)
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             before = ops.launch_count()
             with torch.cuda.graph(graph):
-                self._step_body(draw)
+                self._step_body(draw, u8)
             self._graph_launches = ops.launch_count() - before
-            self._graph[draw] = graph
-        self._graph[draw].replay()
+            self._graph[key] = graph
+        self._graph[key].replay()
 
     def conv_family_pass(self) -> None:
         """Measurement aid (bench.py's roofline): the 33 tensor-core launches of one step -- 11 fprops, 11 dgrads,

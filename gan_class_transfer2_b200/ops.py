@@ -261,6 +261,22 @@ def step_begin(x, noised, iterations, hyper, gsmall, loss, seed: int, steps: int
 
 
 @_timed
+def step_begin_u8(img, flip, x_out, noised, iterations, hyper, gsmall, loss, seed: int, steps: int, base_lr: float,
+                  warmup_steps: int, beta1: float = 0.9, beta2: float = 0.999, eps_out=None, t_out=None):
+    """step_begin on the uint8 batch of decode_file (train.py:285-293): x = img/128 - 1 (+ per-image left-right flip)
+    is decoded on the fly, written to x_out for the loss, and noised."""
+    lib = _lib_for(img)
+    if img.dtype != torch.uint8 or not img.is_contiguous() or img.dim() != 4 or img.shape[3] != 3:
+        raise ValueError("step_begin_u8 expects a contiguous uint8 [B,H,W,3] batch")
+    if flip is not None and (flip.dtype != torch.uint8 or flip.numel() != img.shape[0]):
+        raise ValueError("flip must be uint8 [B]")
+    B = img.shape[0]
+    check(lib.gct2_step_begin_u8(ptr(img), ptr(flip), ptr(x_out), img.shape[2], ptr(noised), ptr(eps_out), ptr(t_out), B,
+                                 img.numel() // B, steps, seed, ptr(iterations), ptr(hyper), base_lr, warmup_steps,
+                                 beta1, beta2, ptr(gsmall), gsmall.numel(), ptr(loss), current_stream()))
+
+
+@_timed
 def cast_bf16(src, dst):
     lib = _lib_for(src)
     check(lib.gct2_cast_bf16(ptr(src), ptr(dst), src.numel(), current_stream()))

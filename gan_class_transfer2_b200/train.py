@@ -452,7 +452,13 @@ class Trainer(Model):
         scalar}; nothing synchronises with the host."""
         x = data[0] if isinstance(data, (tuple, list)) else data
         eng = self._engine_for(x)
-        loss = eng.train_step(x, t_int, epsilon)[0]
+        if x.dtype == torch.uint8:
+            # the dataset stops one op short of decode_file's cast (train.py:292): bytes in, /128 - 1 on the device
+            if t_int is not None or epsilon is not None:
+                raise ValueError("injected t_int / epsilon need the float32 batch")
+            loss = eng.train_step_u8(x)[0]
+        else:
+            loss = eng.train_step(x, t_int, epsilon)[0]
         # identity (train.py:171-173) is the mean of an already-scalar loss: skip the extra launch
         return {"loss": loss if self.compiled_loss is identity else self.compiled_loss(None, loss)}
 

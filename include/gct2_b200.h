@@ -44,7 +44,8 @@ long long gct2_launch_count(void);
  * launches (0 = all SMs; lets the concurrent backward chains run on disjoint SM sets), key 11 = whole-step launch
  * trace (gct2_debug_trace), key 12 != 0 = finish split-K with a separate kernel instead of inside the launch, key 13 = grid cap of the
  * Adam kernel (0 = 8 blocks per SM), key 15 = grid cap of the down0 weight-gradient kernel (0 = 2 blocks per SM), key 16 = which
- * point of the TMA producer's start-up timeline stamp [7] records (0 loop entry .. 4 first loads issued). */
+ * point of the TMA producer's start-up timeline stamp [7] records (0 loop entry .. 4 first loads issued), key 17 = cap of
+ * the shared-memory ring depth, key 19 = CTA pairs (cta_group::2): 0 heuristic, 1 wherever legal, 2 never. */
 void gct2_debug_set(int key, int value);
 /* Test hook: after gct2_debug_set(7, 1) every tensor-core conv launch records, per CTA, 8 %globaltimer stamps (ns):
  * [0] entry, [1] prologue done, [2] first operands landed, [3] MMAs of the first tile issued, [4] first accumulator
@@ -151,6 +152,14 @@ int gct2_adam_apply(float* w, float* m, float* v, const float* g, uint16_t* w_bf
 int gct2_step_begin(const float* x, float* noised, float* eps_out, int32_t* t_out, int B, int elems_per_image, int steps,
                     unsigned long long seed, const long long* iterations, float* hyper, float base_lr, int warmup_steps,
                     float beta1, float beta2, float* gsmall, long long nsmall, float* loss, void* stream);
+/* The same with the batch as it leaves the reference's decode_file (train.py:285-293), i.e. one step EARLIER than x:
+ * img uint8 [B,H,W,3]; x = img/128 - 1, image b mirrored left-right when flip != NULL and flip[b] != 0
+ * (tf.image.random_flip_left_right; the draw is the caller's, like the crop).  x_out fp32 [B,H,W,3] receives the decoded
+ * image (the loss target); everything else as gct2_step_begin.  A quarter of the host-to-device bytes per step. */
+int gct2_step_begin_u8(const uint8_t* img, const uint8_t* flip, float* x_out, int width, float* noised, float* eps_out,
+                       int32_t* t_out, int B, int elems_per_image, int steps, unsigned long long seed,
+                       const long long* iterations, float* hyper, float base_lr, int warmup_steps, float beta1,
+                       float beta2, float* gsmall, long long nsmall, float* loss, void* stream);
 /* fp32 -> bf16 (round to nearest even); builds the first shadow copy of the weights. */
 int gct2_cast_bf16(const float* src, uint16_t* dst, long long n, void* stream);
 

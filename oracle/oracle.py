@@ -137,6 +137,19 @@ def synthetic_batch(cfg: Config, batch: int, seed: int = 1):
     return x, t_int, eps
 
 
+def decode_u8(img_u8: torch.Tensor, flip=None) -> torch.Tensor:
+    """train.py:285-293 decode_file after the crop: (optional) left-right mirror per image
+    (tf.image.random_flip_left_right, :290 -- the random draw is an input here, like every RNG of the oracle), then
+    cast(image, float32) / 128 - 1 (:292).  img_u8 uint8 [B,H,W,3]; flip: iterable of B flags or None."""
+    x = img_u8.to(torch.float32) / 128 - 1
+    if flip is not None:
+        x = x.clone()
+        for b, f in enumerate(flip):
+            if int(f):
+                x[b] = torch.flip(x[b], dims=[1])
+    return x
+
+
 # --------------------------------------------------------------------------------------------- layers
 def _nchw(x):
     return x.permute(0, 3, 1, 2)

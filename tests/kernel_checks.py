@@ -252,6 +252,47 @@ def check_step_begin(B=4, H=64, seed=13):
     return m
 
 
+def check_step_begin_u8(B=3, H=32, seed=15):
+    """The step prologue fed with decode_file's bytes (train.py:285-293): the decoded image (with the per-image
+    left-right flip) must equal the oracle's decode bit for bit (u8/128 - 1 is exact in fp32), noised must follow
+    train.py:231-234 for the draws the kernel reports, and the draws must equal those of the fp32 entry point."""
+    ops = _ops()
+    cfg = O.Config(size=H)
+    g = torch.Generator().manual_seed(seed)
+    img = torch.randint(0, 256, (B, H, H, 3), generator=g, dtype=torch.uint8)
+    flip = torch.tensor([1, 0, 1][:B] + [0] * max(0, B - 3), dtype=torch.uint8)
+    dev = _dev()
+    worst = None
+    for fl in (flip, None):
+        ref_x = O.decode_u8(img, fl)
+        x_out = torch.full((B, H, H, 3), 9.0, device=dev)
+        noised = torch.empty_like(x_out)
+        eps = torch.empty_like(x_out)
+        t = torch.zeros(B, dtype=torch.int32, device=dev)
+        iters = torch.full((1,), 7, dtype=torch.int64, device=dev)
+        ops.step_begin_u8(img.to(dev), None if fl is None else fl.to(dev), x_out, noised, iters, torch.zeros(2, device=dev),
+                          torch.zeros(8, device=dev), torch.zeros(1, device=dev), 1234, cfg.steps, cfg.base_lr, cfg.warm_up,
+                          cfg.beta1, cfg.beta2, eps_out=eps, t_out=t)
+        # same seed and iteration through the fp32 entry point: identical draws, identical noised
+        noised32 = torch.empty_like(x_out)
+        eps32 = torch.empty_like(x_out)
+        t32 = torch.zeros(B, dtype=torch.int32, device=dev)
+        ops.step_begin(ref_x.to(dev), noised32, iters, torch.zeros(2, device=dev), torch.zeros(8, device=dev),
+                       torch.zeros(1, device=dev), 1234, cfg.steps, cfg.base_lr, cfg.warm_up, cfg.beta1, cfg.beta2,
+                       eps_out=eps32, t_out=t32)
+        torch.cuda.synchronize()
+        m = _metrics(f"step_begin_u8 B{B} H{H} flip={'yes' if fl is not None else 'no'} noising", noised,
+                     O.noise_images(ref_x, t.cpu(), eps.cpu(), cfg), 2e-6)
+        exact = (torch.equal(x_out.cpu(), ref_x) and torch.equal(eps.cpu(), eps32.cpu()) and torch.equal(t.cpu(), t32.cpu())
+                 and torch.equal(noised.cpu(), noised32.cpu()))
+        if not exact:
+            m["err"] = float("inf")
+            m["detail"] = "decoded image / draws differ from the oracle decode or from the fp32 entry point"
+        if worst is None or m["err"] / m["tol"] > worst["err"] / worst["tol"]:
+            worst = m
+    return worst
+
+
 def check_c3_fprop(B=2, H=32, Cout=128, seed=7):
     ops = _ops()
     g = torch.Generator().manual_seed(seed)
@@ -413,6 +454,7 @@ CONV_CASES = [
 EW_CASES = [
     (check_noise, {}),
     (check_step_begin, {}),
+    (check_step_begin_u8, {}),
     (check_c3_fprop, {}),
     (check_c3_wgrad, {}),
     (check_bias_grad, {}),

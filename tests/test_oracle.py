@@ -182,3 +182,14 @@ def test_golden_vectors_tiny_step():
     assert np.allclose(taps["pred"][0, :4, :4].numpy(), gold["pred_corner"], rtol=1e-4, atol=1e-6)
     losses = [tr.train_step(*O.synthetic_batch(cfg, 2, 100 + s)) for s in range(3)]
     assert np.allclose(losses, gold["losses3"], rtol=1e-5)
+
+
+def test_decode_u8_matches_decode_file_arithmetic():
+    """train.py:290-292: random_flip_left_right then cast/128 - 1; values land on the k/128 - 1 grid in [-1, 1)."""
+    g = torch.Generator().manual_seed(3)
+    img = torch.randint(0, 256, (2, 4, 6, 3), generator=g, dtype=torch.uint8)
+    x = O.decode_u8(img, [1, 0])
+    assert x.dtype == torch.float32 and float(x.min()) >= -1.0 and float(x.max()) < 1.0
+    assert torch.equal(x[1], img[1].float() / 128 - 1)
+    assert torch.equal(x[0, :, 0], img[0, :, 5].float() / 128 - 1) and torch.equal(x[0, :, 5], img[0, :, 0].float() / 128 - 1)
+    assert torch.equal((x * 128 + 128).round().to(torch.uint8)[1], img[1])
