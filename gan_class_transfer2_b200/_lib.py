@@ -66,6 +66,7 @@ _PROTOS = {
                                 c_float, _P, c_longlong, _P, _P]),
     "gct2_step_begin_u8": (c_int, [_P, _P, _P, c_int, _P, _P, _P, c_int, c_int, c_int, ctypes.c_ulonglong, _P, _P, c_float,
                                    c_int, c_float, c_float, _P, c_longlong, _P, _P]),
+    "gct2_sample_update": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_longlong, _P]),
     "gct2_cast_bf16": (c_int, [_P, _P, c_longlong, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOS)

@@ -217,6 +217,11 @@ int gct2_step_begin_u8(const uint8_t* img, const uint8_t* flip, float* x_out, in
                     hyper, base_lr, warmup_steps, beta1, beta2, gsmall, nsmall, loss, S(stream));
 }
 
+int gct2_sample_update(const float* pred, float* fake, float* x_theta, float* eps_theta, int t, int t_next, int steps,
+                       long long n, void* stream) {
+  return sample_update(pred, fake, x_theta, eps_theta, t, t_next, steps, n, S(stream));
+}
+
 int gct2_cast_bf16(const float* src, uint16_t* dst, long long n, void* stream) {
   return cast_bf16(src, MB(dst), n, S(stream));
 }

@@ -80,6 +80,62 @@ int noise_images(const float* x, const float* eps, const int* t_int, float* nois
   return 0;
 }
 
+// ------------------------------------------------------------------------------------ sampling-loop update (f1)
+// train.py:365-398 / :441-468 (predict_x branch), everything between two Denoiser calls of log_sample in one launch:
+//   x_theta = prediction ; eps_theta = (fake - sqrt(abar_t) x_theta) / sqrt(1 - abar_t)            (after the call at t)
+//   fake'   = sqrt(abar_t') x_theta + sqrt(1 - abar_t') eps_theta                                  (input of the call at t')
+// pred == nullptr: only the second line, from the given x_theta / eps_theta (the loop's first mix).  t_next outside
+// [1, steps]: only the first line (the loop's last update).  fake is read (at t) and overwritten (for t_next) in place.
+__device__ __forceinline__ float abar_of(int t, int steps) {
+  const float om = 1.f - (float)t / (float)(steps + 1);
+  return om * om * 0.25f;
+}
+__global__ void sample_update_kernel(const float4* __restrict__ pred, float4* __restrict__ fake, float4* __restrict__ x_theta,
+                                     float4* __restrict__ eps_theta, int t, int t_next, int steps, long long nvec) {
+  TraceScope trace(10);
+  pdl_launch_dependents();
+  pdl_wait();
+  trace.ready();
+  const float a = abar_of(t, steps), sa = sqrtf(a), sb = sqrtf(1.f - a);
+  const bool mix = t_next >= 1 && t_next <= steps;
+  const float an = abar_of(mix ? t_next : t, steps), san = sqrtf(an), sbn = sqrtf(1.f - an);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 xt, et;
+    if (pred != nullptr) {
+      xt = __ldg(pred + i);
+      const float4 f = fake[i];
+      et = make_float4((f.x - sa * xt.x) / sb, (f.y - sa * xt.y) / sb, (f.z - sa * xt.z) / sb, (f.w - sa * xt.w) / sb);
+      x_theta[i] = xt;
+      eps_theta[i] = et;
+    } else {
+      xt = x_theta[i];
+      et = eps_theta[i];
+    }
+    if (mix)
+      fake[i] = make_float4(san * xt.x + sbn * et.x, san * xt.y + sbn * et.y, san * xt.z + sbn * et.z,
+                            san * xt.w + sbn * et.w);
+  }
+  trace.end();
+}
+
+int sample_update(const float* pred, float* fake, float* x_theta, float* eps_theta, int t, int t_next, int steps,
+                  long long n, cudaStream_t st) {
+  if (n % 4 || steps < 1 || (pred != nullptr && (t < 1 || t > steps))) {
+    set_error("sample_update: n must be a multiple of 4 and 1 <= t <= steps (n=%lld t=%d steps=%d)", n, t, steps);
+    return 1;
+  }
+  const long long nvec = n / 4;
+  int blocks = (int)((nvec + 255) / 256);
+  if (blocks > g_ew_sms * 8) blocks = g_ew_sms * 8;
+  if (blocks < 1) blocks = 1;
+  launch_k(sample_update_kernel, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const float4*>(pred),
+           reinterpret_cast<float4*>(fake), reinterpret_cast<float4*>(x_theta), reinterpret_cast<float4*>(eps_theta), t,
+           t_next, steps, nvec);
+  GCT2_CHECK_LAUNCH("sample_update_kernel");
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------ fused step prologue
 // One launch for everything the step needs before the first convolution (train.py:224-234 + optimiser bookkeeping):
 //   t_int ~ U{1..steps} per image, eps ~ N(0,1) per element (Philox4x32-10 keyed by `seed`, offset by the optimiser

@@ -26,6 +26,8 @@ int adam_prepare(long long* iterations, float* hyper, float base_lr, int warmup_
                  cudaStream_t st);
 int adam_apply(float* w, float* m, float* v, const float* g, __nv_bfloat16* w_bf16, long long n, const float* hyper,
                float beta1, float beta2, float eps, float grad_scale, long long* iterations_inc, cudaStream_t st);
+int sample_update(const float* pred, float* fake, float* x_theta, float* eps_theta, int t, int t_next, int steps,
+                  long long n, cudaStream_t st);
 int step_begin(const float* x, const uint8_t* x_u8, const uint8_t* flip, float* x_out, int W, float* noised,
                float* eps_out, int* t_out, int B, int elemsPerImage, int steps,
                unsigned long long seed, const long long* iterations, float* hyper, float base_lr, int warmup_steps,

@@ -542,6 +542,51 @@ class UNetEngine:
         self._backward(apply_adam=False)
         return self.loss
 
+    def sample(self, x_theta: torch.Tensor, eps_theta: torch.Tensor, t_values) -> Tuple[torch.Tensor, torch.Tensor]:
+        """log_sample's diffusion loops (train.py:365-398 ascending t, :441-468 descending t; predict_x branch): for t in
+        t_values:  fake = sqrt(abar_t) x_theta + sqrt(1-abar_t) eps_theta;  x_theta = Denoiser(fake);
+        eps_theta = (fake - sqrt(abar_t) x_theta) / sqrt(1-abar_t).  Returns the final (x_theta, eps_theta), fp32
+        [B,S,S,3] device tensors owned by the engine.  The whole loop -- len(t_values) forward passes and the fused
+        update between them -- is one CUDA graph per schedule (when the engine uses graphs)."""
+        t_values = tuple(int(t) for t in t_values)
+        if not t_values or min(t_values) < 1 or max(t_values) > self.cfg.steps:
+            raise ValueError("t_values must be a non-empty sequence inside [1, steps]")
+        if not hasattr(self, "xt"):
+            self.xt = torch.zeros_like(self.x)
+            self.et = torch.zeros_like(self.x)
+        self.xt.copy_(x_theta, non_blocking=True)
+        self.et.copy_(eps_theta, non_blocking=True)
+
+        def body():
+            steps = self.cfg.steps
+            ops.sample_update(None, self.noised, self.xt, self.et, t_values[0], t_values[0], steps)  # first mix
+            for k, t in enumerate(t_values):
+                self._forward(want_pred=True, backward=False, inv_n=1.0)
+                ops.sample_update(self.pred, self.noised, self.xt, self.et, t,
+                                  t_values[k + 1] if k + 1 < len(t_values) else 0, steps)
+
+        if not self.use_graph:
+            body()
+            return self.xt, self.et
+        if self._graph is None:
+            self._graph = {}
+        key = ("sample", t_values)
+        if key not in self._graph:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                saved = (self.xt.clone(), self.et.clone())
+                body()
+                self.xt.copy_(saved[0])
+                self.et.copy_(saved[1])
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                body()
+            self._graph[key] = graph
+        self._graph[key].replay()
+        return self.xt, self.et
+
     def denoise(self, noised: torch.Tensor) -> torch.Tensor:
         """Denoiser.call (train.py:206-215): forward only on an already-noised image; returns the fp32 prediction."""
         self.noised.copy_(noised, non_blocking=True)

@@ -277,6 +277,15 @@ def step_begin_u8(img, flip, x_out, noised, iterations, hyper, gsmall, loss, see
 
 
 @_timed
+def sample_update(pred, fake, x_theta, eps_theta, t: int, t_next: int, steps: int = 200):
+    """log_sample's per-step arithmetic (train.py:365-398, 441-468, predict_x branch): x_theta / eps_theta from the
+    prediction at step t, and the next Denoiser input (fake, in place) for step t_next.  pred=None: first mix only."""
+    lib = _lib_for(fake)
+    check(lib.gct2_sample_update(ptr(pred), ptr(fake), ptr(x_theta), ptr(eps_theta), t, t_next, steps, fake.numel(),
+                                 current_stream()))
+
+
+@_timed
 def cast_bf16(src, dst):
     lib = _lib_for(src)
     check(lib.gct2_cast_bf16(ptr(src), ptr(dst), src.numel(), current_stream()))

@@ -373,6 +373,19 @@ class Denoiser(Model):
             self._engines[key] = eng
         return self._engines[key]
 
+    def sample(self, x_theta, epsilon_theta, t_values):
+        """The diffusion loops of log_sample (train.py:365-398: `reversed(range(steps, 0, -1))`, batch 1;
+        train.py:441-468: `range(steps, 0, -1)`, batch 6) for the reference's default target (predict_x):
+        every iteration mixes `fake`, calls the denoiser and re-derives (x_theta, epsilon_theta).  Returns the final
+        pair as fp32 NHWC device tensors.  One CUDA graph per (batch, schedule)."""
+        if not (predict_x and not ordinary_differential_equation):
+            raise NotImplementedError("only the reference's default target (predict_x=True) is accelerated")
+        B, H, W, C = x_theta.shape
+        if C != 3 or H != W or tuple(epsilon_theta.shape) != tuple(x_theta.shape):
+            raise ValueError("sample expects two square NHWC tensors [B,S,S,3] of equal shape")
+        xt, et = self.engine(B, H).sample(x_theta, epsilon_theta, t_values)
+        return xt.clone(), et.clone()
+
     def _bind_variables(self, eng: UNetEngine) -> None:
         """Layers own their variables in Keras; here they are views into the engine's flat fp32 buffer."""
         downs, ups, dense = self._walk()

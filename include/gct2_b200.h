@@ -55,7 +55,7 @@ int gct2_debug_timeline(unsigned long long* host, int max_ctas);
 /* Test hook: after gct2_debug_set(11, 1) the first and last block of EVERY launch of this library append
  * {kernel id, blockIdx | gridDim << 32, entry ns, exit ns}; this call synchronises, copies up to max_records records
  * (4 x u64 each) to `host`, clears the buffer and returns the count.  Kernel ids: 1 noise, 2 step_begin, 3/4 down0
- * fprop/wgrad, 5 dense+mse, 6 bias grads, 7 adam_prepare, 8 adam, 9 cast, 20 split-K finish, 21 wgrad reduce,
+ * fprop/wgrad, 5 dense+mse, 6 bias grads, 7 adam_prepare, 8 adam, 9 cast, 10 sample update, 20 split-K finish, 21 wgrad reduce,
  * 100 + 10*mode + BN/64 tensor-core conv (mode 0 strided, 1 phase, 2 wgrad). */
 int gct2_debug_trace(unsigned long long* host, int max_records);
 
@@ -160,6 +160,14 @@ int gct2_step_begin_u8(const uint8_t* img, const uint8_t* flip, float* x_out, in
                        int32_t* t_out, int B, int elems_per_image, int steps, unsigned long long seed,
                        const long long* iterations, float* hyper, float base_lr, int warmup_steps, float beta1,
                        float beta2, float* gsmall, long long nsmall, float* loss, void* stream);
+
+/* train.py:365-398 and :441-468 -- log_sample's diffusion loops (predict_x branch), the arithmetic between two
+ * Denoiser calls in one launch.  After the call at step t:  x_theta = pred;  eps_theta = (fake - sqrt(abar(t)) x_theta)
+ * / sqrt(1 - abar(t));  then, if 1 <= t_next <= steps, the next call's input  fake = sqrt(abar(t_next)) x_theta +
+ * sqrt(1 - abar(t_next)) eps_theta  (in place).  pred == NULL: only the mix, from the given x_theta / eps_theta (the
+ * loop's first iteration).  All tensors fp32 with n elements. */
+int gct2_sample_update(const float* pred, float* fake, float* x_theta, float* eps_theta, int t, int t_next, int steps,
+                       long long n, void* stream);
 /* fp32 -> bf16 (round to nearest even); builds the first shadow copy of the weights. */
 int gct2_cast_bf16(const float* src, uint16_t* dst, long long n, void* stream);
 

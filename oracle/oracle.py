@@ -150,6 +150,27 @@ def decode_u8(img_u8: torch.Tensor, flip=None) -> torch.Tensor:
     return x
 
 
+def sample_loop(weights, x_theta: torch.Tensor, eps_theta: torch.Tensor, t_values, cfg: "Config" = None,
+                emulate_bf16: bool = False):
+    """log_sample's diffusion loops, predict_x branch (train.py:365-398 with t ascending from 1, train.py:441-468 with
+    t descending from steps):
+        fake = alpha_dash(t)**0.5 * x_theta + (1 - alpha_dash(t))**0.5 * epsilon_theta        (:369-372, :445-448)
+        prediction = denoiser((fake, [t]))                                                     (:374-377, :450-453)
+        x_theta = prediction                                                                   (:394, :465)
+        epsilon_theta = (fake - alpha_dash(t)**0.5 * x_theta) / (1 - alpha_dash(t))**0.5       (:395-397, :466-468)
+    Returns the final (x_theta, epsilon_theta) and the list of x_theta after every step."""
+    cfg = DEFAULT if cfg is None else cfg
+    trace = []
+    for t in t_values:
+        a = alpha_dash(float(t), cfg.steps)
+        fake = a ** 0.5 * x_theta + (1 - a) ** 0.5 * eps_theta
+        pred = denoiser_forward(weights, fake, cfg, emulate_bf16=emulate_bf16)
+        x_theta = pred
+        eps_theta = (fake - a ** 0.5 * x_theta) / (1 - a) ** 0.5
+        trace.append(x_theta)
+    return x_theta, eps_theta, trace
+
+
 # --------------------------------------------------------------------------------------------- layers
 def _nchw(x):
     return x.permute(0, 3, 1, 2)

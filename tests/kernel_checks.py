@@ -293,6 +293,35 @@ def check_step_begin_u8(B=3, H=32, seed=15):
     return worst
 
 
+def check_sample_update(B=2, H=16, seed=16):
+    """gct2_sample_update against the loop arithmetic of train.py:369-372 / :394-397 (fp32 elementwise)."""
+    ops = _ops()
+    cfg = O.Config(size=H)
+    g = torch.Generator().manual_seed(seed)
+    dev = _dev()
+    shape = (B, H, H, 3)
+    x0, e0, pred = _rand(shape, g), _rand(shape, g), _rand(shape, g)
+    t, tn = 7, 8
+    a, an = O.alpha_dash(float(t), cfg.steps), O.alpha_dash(float(tn), cfg.steps)
+    fake_ref = a ** 0.5 * x0 + (1 - a) ** 0.5 * e0
+    fake = torch.zeros(shape, device=dev)
+    xt, et = x0.to(dev), e0.to(dev)
+    ops.sample_update(None, fake, xt, et, t, t, cfg.steps)            # first mix
+    m1 = _metrics("sample_update mix", fake, fake_ref, 2e-6)
+    ops.sample_update(pred.to(dev), fake, xt, et, t, tn, cfg.steps)   # update + next mix
+    e_ref = (fake_ref - a ** 0.5 * pred) / (1 - a) ** 0.5
+    m2 = _metrics("sample_update eps_theta", et, e_ref, 2e-6)
+    m3 = _metrics("sample_update next fake", fake, an ** 0.5 * pred + (1 - an) ** 0.5 * e_ref, 2e-6)
+    keep = fake.clone()
+    ops.sample_update(pred.to(dev), fake, xt, et, tn, 0, cfg.steps)   # last step: fake untouched
+    torch.cuda.synchronize()
+    worst = dict(max([m1, m2, m3], key=lambda q: q["err"] / q["tol"]))
+    if not (torch.equal(xt.cpu(), pred) and torch.equal(keep, fake)):
+        worst["err"] = float("inf")
+    worst["name"] = f"sample_update B{B} H{H} (worst: {worst['name']})"
+    return worst
+
+
 def check_c3_fprop(B=2, H=32, Cout=128, seed=7):
     ops = _ops()
     g = torch.Generator().manual_seed(seed)
@@ -455,6 +484,7 @@ EW_CASES = [
     (check_noise, {}),
     (check_step_begin, {}),
     (check_step_begin_u8, {}),
+    (check_sample_update, {}),
     (check_c3_fprop, {}),
     (check_c3_wgrad, {}),
     (check_bias_grad, {}),

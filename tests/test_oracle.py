@@ -193,3 +193,21 @@ def test_decode_u8_matches_decode_file_arithmetic():
     assert torch.equal(x[1], img[1].float() / 128 - 1)
     assert torch.equal(x[0, :, 0], img[0, :, 5].float() / 128 - 1) and torch.equal(x[0, :, 5], img[0, :, 0].float() / 128 - 1)
     assert torch.equal((x * 128 + 128).round().to(torch.uint8)[1], img[1])
+
+
+def test_sample_loop_algebra():
+    """train.py:365-398: whatever the denoiser predicts, (x_theta, epsilon_theta) re-mixed at the same t reproduce
+    `fake` exactly, and a denoiser that returned its input scaled by 1/sqrt(abar) would leave epsilon_theta at 0."""
+    cfg = O.Config(size=16, pixel_size=64, max_size=64, octaves=2)
+    w = O.glorot_init(cfg, 0)
+    g = torch.Generator().manual_seed(5)
+    x0 = torch.rand(1, 16, 16, 3, generator=g) * 2 - 1
+    xt, et, trace = O.sample_loop(w, x0, x0, [1, 2, 3], cfg)
+    assert len(trace) == 3 and xt.shape == x0.shape and torch.isfinite(et).all()
+    # invariant of every step: sqrt(a) x_theta' + sqrt(1-a) eps_theta' == fake
+    a = O.alpha_dash(3.0, cfg.steps)
+    a2 = O.alpha_dash(2.0, cfg.steps)
+    xt2, et2, _ = O.sample_loop(w, x0, x0, [1, 2], cfg)
+    fake3 = a ** 0.5 * xt2 + (1 - a) ** 0.5 * et2
+    assert torch.allclose(a ** 0.5 * xt + (1 - a) ** 0.5 * et, fake3, atol=1e-5)
+    assert a2 > a  # the schedule decays with t (train.py:85-93)
