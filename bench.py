@@ -258,6 +258,19 @@ def main():
     e2.record()
     barrier()
     ms_e2e = max_over_ranks(s2.elapsed_time(e2))
+    # the same with the batch as decode_file's uint8 bytes (a quarter of the H2D traffic; decode fused into the prologue)
+    u8_host = ((x_cpu + 1) * 128).round().clamp(0, 255).to(torch.uint8).pin_memory()
+    for _ in range(3):
+        trainer.train_step((u8_host, u8_host))
+    barrier()
+    s4, e4 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s4.record()
+    for _ in range(args.steps):
+        loss = trainer.train_step((u8_host, u8_host))["loss"]
+        loss_host.copy_(loss.reshape(1), non_blocking=True)
+    e4.record()
+    barrier()
+    ms_e2e_u8 = max_over_ranks(s4.elapsed_time(e4))
     clocks = sampler.stop()
     final_loss = float(loss_host.item())
 
@@ -345,6 +358,10 @@ def main():
             "e2e": {"value": B * world * args.steps / (ms_e2e * 1e-3), "unit": "images/s",
                     "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps, "api": "train.Trainer.train_step((x_host, x_host))"},
+            "e2e_uint8": {"value": B * world * args.steps / (ms_e2e_u8 * 1e-3), "unit": "images/s",
+                          "h2d_bytes_per_step": u8_host.numel(), "d2h_bytes_per_step": 4,
+                          "api": "train.Trainer.train_step((img_u8_host, img_u8_host)) -- decode_file's bytes, "
+                                 "/128-1 on the device (SURVEY 8 f2)"},
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
             "cuda_graph": not args.no_graph, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "final_loss": final_loss}
