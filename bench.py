@@ -197,7 +197,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        T.data_parallel = DataParallel(overlap=not args.no_overlap)
+        T.data_parallel = DataParallel(overlap=not args.no_overlap,
+                                       shard_optimizer=os.environ.get("GCT2_DP_SHARD", "1") != "0")
     _lib.init(local)
 
     B = args.batch_per_gpu

@@ -149,6 +149,18 @@ def grad_buckets(cfg: NetConfig, bucket_bytes: int) -> List[Tuple[int, int, str]
     return buckets
 
 
+def optimizer_shard(start: int, end: int, small: int, world: int, rank: int) -> Optional[Tuple[int, int, int, int]]:
+    """Sharded optimiser: the part [lo, end) of a gradient bucket above the replicated head region [0, small) is cut
+    into `world` equal slices of whole float4 vectors; returns (lo, end, own_lo, own_hi) of `rank`, or None when the
+    bucket has nothing above the head region or cannot be cut evenly (then it stays replicated: all-reduce + Adam on
+    every rank)."""
+    lo = max(start, small)
+    if end <= lo or (end - lo) % (4 * world):
+        return None
+    chunk = (end - lo) // world
+    return lo, end, lo + rank * chunk, lo + (rank + 1) * chunk
+
+
 def shard_batch(global_batch: int, world: int, rank: int) -> Tuple[int, int]:
     """[lo, hi) sample range of one rank: the batch shards evenly, samples are independent (no cross-sample op but
     the loss mean, train.py:272)."""
@@ -161,7 +173,8 @@ def shard_batch(global_batch: int, world: int, rank: int) -> Tuple[int, int]:
 class DataParallel:
     """Data-parallel context: the batch shards over ranks, gradient buckets are summed with NCCL."""
 
-    def __init__(self, group=None, bucket_bytes: int = 48 << 20, overlap: bool = True):
+    def __init__(self, group=None, bucket_bytes: int = 48 << 20, overlap: bool = True,
+                 shard_optimizer: bool = True):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
@@ -169,6 +182,11 @@ class DataParallel:
         self.rank = dist.get_rank(group)
         self.bucket_bytes = bucket_bytes
         self.overlap = overlap
+        #: SURVEY.md 8(e) "optimisation": per bucket, reduce-scatter the fp32 gradients, run Keras-Adam on this rank's
+        #: 1/N slice only, all-gather the bf16 weights the tensor-core kernels read.  0.75x the bytes of an fp32
+        #: all-reduce on the wire and 1/N of the optimiser's HBM traffic per GPU.  The fp32 masters of the other ranks'
+        #: slices go stale until UNetEngine.gather_master_weights() (called by weights()).
+        self.shard_optimizer = shard_optimizer
 
 
 class UNetEngine:
@@ -189,6 +207,8 @@ class UNetEngine:
         self._side_adam = torch.cuda.Stream(device=self.device)
         self._graph = None
         self._graph_launches = 0
+        self._masters_stale = False
+        self._sharded_ranges = set()  # (lo, end) ranges whose fp32 masters are updated on their owner rank only
         dev, n, S, B = self.device, cfg.octaves, cfg.size, batch
         from . import _lib
         lib = _lib.init(self.device.index or 0)
@@ -278,7 +298,25 @@ class UNetEngine:
         self.load_weights({name: torch.zeros(shape) if name.endswith("bias") else glorot_uniform(shape, gen)
                            for name, shape in self.specs})
 
+    def gather_master_weights(self) -> None:
+        """Sharded optimiser (DataParallel.shard_optimizer): brings the fp32 masters of the other ranks' slices up to
+        date (all ranks must call it).  The training step itself never needs them -- it reads the bf16 copies."""
+        dp = self.dp
+        if not dp or dp.world == 1 or not self._sharded_ranges:
+            self._masters_stale = False
+            return
+        torch.cuda.synchronize(self.device)
+        for lo, end in sorted(self._sharded_ranges):
+            chunk = (end - lo) // dp.world
+            own = lo + dp.rank * chunk
+            dp.dist.all_gather_into_tensor(self.w[lo:end], self.w[own:own + chunk], group=dp.group)
+        torch.cuda.synchronize(self.device)
+        self._masters_stale = False
+
     def weights(self) -> Dict[str, torch.Tensor]:
+        if self._masters_stale:
+            raise RuntimeError("sharded optimiser: call gather_master_weights() on every rank before reading the fp32 "
+                               "weights (each rank has updated the masters of its own slice only)")
         return {name: self.view(self.w, name).detach().clone() for name, _ in self.specs}
 
     def grads(self) -> Dict[str, torch.Tensor]:
@@ -352,6 +390,36 @@ class UNetEngine:
                 if name != trigger:
                     continue
                 work = None
+                if dp and apply_adam and dp.shard_optimizer:
+                    # sharded optimiser: everything above the small head region of this bucket
+                    cut = optimizer_shard(start, end, self.small, dp.world, dp.rank)
+                    if cut is not None:
+                        lo, _, own, own_hi = cut
+                        chunk = own_hi - own
+                        if sw is not main and trigger == "down0/kernel":
+                            sw.wait_stream(main)
+                        with torch.cuda.stream(sw):
+                            # in place: my slice of the bucket receives the sum of everybody's slice
+                            rs = dp.dist.reduce_scatter_tensor(self.g[own:own + chunk], self.g[lo:end], group=dp.group,
+                                                               async_op=True)
+                        if sa is not main:
+                            sa.wait_stream(main)
+                            if sw is not main:
+                                sa.wait_stream(sw)
+                        elif sw is not main:
+                            main.wait_stream(sw)
+                        with torch.cuda.stream(sa):
+                            rs.wait()
+                            ops.adam_apply(self.w[own:own + chunk], self.m[own:own + chunk], self.v[own:own + chunk],
+                                           self.g[own:own + chunk], self.w16[own:own + chunk], self.hyper, cfg.beta1,
+                                           cfg.beta2, cfg.epsilon, 1.0)
+                            # every rank's freshly written bf16 slice to everybody (in place)
+                            pending.append(dp.dist.all_gather_into_tensor(self.w16[lo:end], self.w16[own:own + chunk],
+                                                                          group=dp.group, async_op=True))
+                        self._sharded_ranges.add((lo, end))
+                        if start >= self.small:
+                            continue
+                        end = self.small  # the head region below stays replicated
                 if dp:
                     if sw is not main and trigger == "down0/kernel":
                         sw.wait_stream(main)  # the small region is produced on the main stream
@@ -470,6 +538,8 @@ class UNetEngine:
 
     def run_step(self, draw: bool = True, u8: bool = False) -> None:
         """The step on whatever set_batch staged (the part bench.py times as `value`)."""
+        if self.dp is not None and self.dp.world > 1 and self.dp.shard_optimizer:
+            self._masters_stale = True  # from here on every rank holds current fp32 masters for its own slices only
         if not self.use_graph:
             self._step_body(draw, u8)
             return

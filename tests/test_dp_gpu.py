@@ -40,11 +40,17 @@ def _worker(rank, world, port, out, use_graph):
             xs, ts, es = O.synthetic_batch(cfg, per * world, 100 + s)
             losses.append(float(eng.train_step(xs[lo:hi].cuda(), ts[lo:hi].cuda(), es[lo:hi].cuda())))
         torch.cuda.synchronize()
+        stale_raises = False
+        try:
+            eng.weights()
+        except RuntimeError:
+            stale_raises = True  # sharded optimiser: reading stale masters must fail loudly, not return old values
+        eng.gather_master_weights()  # ... every rank updates the fp32 masters of its own slice only (collective)
         w = eng.w.clone()
         gathered = [torch.empty_like(w) for _ in range(world)]
         dist.all_gather(gathered, w)
         if rank == 0:
-            torch.save({"loss": float(loss), "grads": grads, "losses": losses,
+            torch.save({"loss": float(loss), "grads": grads, "losses": losses, "stale_raises": stale_raises,
                         "replicas_equal": all(torch.equal(gathered[0], g) for g in gathered),
                         "weights": {k: v.cpu() for k, v in eng.weights().items()}}, out)
     finally:
@@ -69,6 +75,7 @@ def test_two_gpu_data_parallel_step_matches_oracle(tmp_path, use_graph):
     assert abs(got["loss"] - float(loss)) <= 1e-3 * float(loss)
     for k, g in grads.items():
         assert E.rel(got["grads"][k], g) <= E.tol_f32_grad(cfg, k), k
+    assert got["stale_raises"], "weights() returned stale fp32 masters under the sharded optimiser"
     assert got["replicas_equal"], "ranks diverged: the summed gradients (and so the weights) must be bit-identical"
     tr = O.OracleTrainer(cfg, weights=weights)
     ref = [tr.train_step(*O.synthetic_batch(cfg, 4, 100 + s)) for s in range(4)]

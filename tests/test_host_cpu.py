@@ -95,3 +95,26 @@ def test_glorot_limits():
     k = E.glorot_uniform((4, 4, 128, 256), g)
     lim = math.sqrt(6 / (16 * 128 + 16 * 256))
     assert k.abs().max() <= lim and k.abs().max() > 0.99 * lim
+
+
+def test_optimizer_shards_tile_every_bucket():
+    """Sharded optimiser: for every bucket of the default and the tiny model and 2/4/8 ranks, the slices of
+    all ranks tile the part above the replicated head region exactly once, on float4 boundaries; the head region is
+    never sharded."""
+    from gan_class_transfer2_b200 import engine as E
+    for cfg in (E.NetConfig(), E.NetConfig(size=64, pixel_size=128, max_size=256, octaves=4)):
+        small = E.small_region(cfg)
+        _, total = E.param_offsets(cfg)
+        for world in (2, 4, 8):
+            covered = 0
+            for start, end, _ in E.grad_buckets(cfg, 48 << 20):
+                cuts = [E.optimizer_shard(start, end, small, world, r) for r in range(world)]
+                assert all(c is not None for c in cuts), (start, end, world)
+                lo = max(start, small)
+                assert [c[2] for c in cuts] == [lo + r * (end - lo) // world for r in range(world)]
+                assert cuts[-1][3] == end and all(a[3] == b[2] for a, b in zip(cuts, cuts[1:]))
+                assert all(c[2] % 4 == 0 and (c[3] - c[2]) % 4 == 0 for c in cuts)
+                covered += end - lo
+            assert covered == total - small
+    assert E.optimizer_shard(0, 100, 128, 2, 0) is None      # nothing above the head region
+    assert E.optimizer_shard(128, 128 + 12, 128, 8, 0) is None  # not divisible: stays replicated
