@@ -268,10 +268,10 @@ __global__ void wgrad_reduce_kernel(const float4* __restrict__ ws, long long spl
 }
 
 // ------------------------------------------------------------------------------------ heuristics
-// every tile width fills the same 192 KB of pipeline: a CTA's operand ingest rate is (bytes in flight) / (TMA round
-// trip, ~1.4 us), so the ring is as deep as shared memory allows -- 8 x 24 KB, 6 x 32 KB, 4 x 48 KB
-// every tile width fills the same 192 KB of pipeline -- 8 x 24 KB, 6 x 32 KB, 4 x 48 KB; a CTA of a pair stages only
-// half of the B tile: 8 x 24 KB at BN = 128, 6 x 32 KB at BN = 256
+// Ring depth: every tile width fills the same 192 KB of pipeline -- 8 x 24 KB, 6 x 32 KB, 4 x 48 KB; a CTA of a pair
+// stages only half of the B tile: 8 x 24 KB at BN = 128, 6 x 32 KB at BN = 256.  (A TMA round trip is ~500 cycles and a
+// k-step 470-655, so the ring is deeper than steady state needs; the depth absorbs the start-up burst.  Two- to four-
+// slot rings that would let two CTAs share an SM were measured: -16 % at batch 1, -25 % at batch 32.)
 static int stages_for(int BN, bool pair = false) {
   int s = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
   if (pair) s = BN == 256 ? 6 : 8;
@@ -351,7 +351,7 @@ static Choice choose(int mode, int mTiles, int phases, int N, int kTotal, long l
           const int cm = cms[a], cn = cns[b], cs = cm * cn;
           if (cs > 8 || mTiles % cm || nTiles % cn) continue;
           if (isW && cs > 1) continue;
-          // clusters cost 1.3 us per launch and do not raise the per-SM ingest rate; measured slower than plain launches
+          // multicast clusters cost 1.3 us per launch and the main loop is issue-bound, not ingest-bound; measured slower
           // at 1, 8 and 32 images per GPU (profiles/README.md), so they are used only on request (debug keys 5/6)
           if (forceCm >= 1 ? cm != forceCm : cm != 1) continue;
           if (forceCn >= 1 ? cn != forceCn : cn != 1) continue;
@@ -615,7 +615,7 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
   const size_t smem = smem_for(BN, p.pair != 0);
   const int csize = p.cm * p.cn;
   p.numClusterItems = p.numItems / csize;
-  int maxCtas = g_num_sms;  // one CTA per SM: the per-SM operand ingest rate, not occupancy, bounds a CTA's speed
+  int maxCtas = g_num_sms;  // one CTA per SM (198 KB of shared memory, 61 K registers)
   {
     const int cap = a.mode == MODE_W ? g_cap_w : (a.epi == EPI_DGRAD ? g_cap_sp : 0);
     if (cap > 0 && cap < maxCtas) maxCtas = cap;
