@@ -397,7 +397,11 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
         for (int it = 0; it < p.kIters; ++it) {
           mbar_wait(&full[stage], phase);
           if (it == 0 && item == clusterId) GCT2_STAMP(2);  // first operands have landed
+          // (no tcgen05.fence here: the operands were written by the async proxy (TMA) and are read by the async proxy
+          // (tcgen05.mma); the mbarrier's completion orders the two)
+#ifdef GCT2_KLOOP_FENCE
           tc_fence_after();
+#endif
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
           // one descriptor pair per stage; the four K = 16 slices only advance the 14-bit address field
