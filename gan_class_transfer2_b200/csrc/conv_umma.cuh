@@ -18,6 +18,7 @@
 // epilogue of tile i overlaps the main loop of tile i+1.
 #pragma once
 #include <cuda_bf16.h>
+#include <type_traits>
 #include "ptx.cuh"
 
 namespace gct2 {
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
   constexpr int BLK = 64 * 128;       // one 64x64 bf16 block = one TMA box of an MN-major operand
   constexpr bool pair = PAIR != 0;
   // a CTA of a pair stages only its half of the B tile
-  const int STAGE_BYTES = A_BYTES + (pair ? B_BYTES / 2 : B_BYTES);
+  constexpr int STAGE_BYTES = A_BYTES + (pair ? B_BYTES / 2 : B_BYTES);
   constexpr uint32_t TMEM_COLS = 2 * BN;
 
   extern __shared__ uint8_t smem_raw[];
@@ -390,44 +391,66 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
       constexpr uint32_t a_kstep = A_MN ? 2048u : 32u;  // bytes per UMMA_K = 16 along K
       constexpr uint32_t b_kstep = B_MN ? 2048u : 32u;
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      // The issuing thread's own instruction stream is the main loop's bound (one warp, mostly dependent
+      // uniform-datapath instructions: 77 per k-step = ~470 cycles before this form), so everything that can be
+      // carried across iterations is: the stage's descriptor pair and barrier addresses advance by constants and wrap
+      // with the ring; the four K = 16 slices add immediates to the 14-bit address field.
+      const uint32_t smem_base = smem_u32(smem);
+      const uint64_t da_first = make_smem_desc(smem_base, a_lbo, a_sbo);
+      const uint64_t db_first = make_smem_desc(smem_base + A_BYTES, b_lbo, b_sbo);
+      const uint64_t dstep = (uint64_t)(STAGE_BYTES >> 4);
+      const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
+      constexpr uint64_t ka = a_kstep >> 4, kb = b_kstep >> 4;
+      // one k-step on ring slot `slot`: wait for the operands, four MMAs, release the slot
+      auto kstep = [&](uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t full_a, uint32_t empty_a, uint32_t ph,
+                       uint32_t accumulate) {
+        mbar_wait_addr(full_a, ph);
+        // (no tcgen05.fence here: the operands were written by the async proxy (TMA) and are read by the async proxy
+        // (tcgen05.mma); the mbarrier's completion orders the two)
+        if (pair) {
+          umma_bf16_pair(d_tmem, da, db, idesc2, accumulate);
+          umma_bf16_pair(d_tmem, da + ka, db + kb, idesc2, 1u);
+          umma_bf16_pair(d_tmem, da + 2 * ka, db + 2 * kb, idesc2, 1u);
+          umma_bf16_pair(d_tmem, da + 3 * ka, db + 3 * kb, idesc2, 1u);
+          umma_commit_pair_addr(empty_a, 0x3);  // the slot is free in both CTAs
+        } else {
+          umma_bf16(d_tmem, da, db, idesc, accumulate);
+          umma_bf16(d_tmem, da + ka, db + kb, idesc, 1u);
+          umma_bf16(d_tmem, da + 2 * ka, db + 2 * kb, idesc, 1u);
+          umma_bf16(d_tmem, da + 3 * ka, db + 3 * kb, idesc, 1u);
+          // frees the smem slot once these MMAs have read it -- in my CTA and, in a cluster, in every CTA that
+          // multicasts into my slot (my row and my column)
+          if (csize == 1)
+            umma_commit_addr(empty_a);
+          else
+            umma_commit_mc_addr(empty_a, peerMask);
+        }
+      };
+      // (Unrolling the ring over its slots -- descriptor pairs as immediates -- was measured too: the k-step drops from
+      // 224 to 185 ns at BN = 64, but the three unrolled copies per kernel cost more at start-up than they save.)
+      uint64_t da = da_first, db = db_first;
+      uint32_t full_a = full0, empty_a = empty0;
       for (int item = clusterId; item < p.numClusterItems; item += numClusters) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
+        if (item == clusterId && p.dbg != nullptr) {  // test hook: when did the first operands land?
+          mbar_wait_addr(full_a, phase);
+          GCT2_STAMP(2);
+        }
         for (int it = 0; it < p.kIters; ++it) {
-          mbar_wait(&full[stage], phase);
-          if (it == 0 && item == clusterId) GCT2_STAMP(2);  // first operands have landed
-          // (no tcgen05.fence here: the operands were written by the async proxy (TMA) and are read by the async proxy
-          // (tcgen05.mma); the mbarrier's completion orders the two)
-#ifdef GCT2_KLOOP_FENCE
-          tc_fence_after();
-#endif
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
-          // one descriptor pair per stage; the four K = 16 slices only advance the 14-bit address field
-          const uint64_t da0 = make_smem_desc(sa, a_lbo, a_sbo), db0 = make_smem_desc(sb, b_lbo, b_sbo);
-          if (pair) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_pair(d_tmem, da0 + (uint64_t)((k * a_kstep) >> 4), db0 + (uint64_t)((k * b_kstep) >> 4), idesc2,
-                             (it | k) != 0 ? 1u : 0u);
-          } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(d_tmem, da0 + (uint64_t)((k * a_kstep) >> 4), db0 + (uint64_t)((k * b_kstep) >> 4), idesc,
-                        (it | k) != 0 ? 1u : 0u);
-          }
-          // frees the smem slot once these MMAs have read it -- in my CTA and, in a cluster, in every CTA that
-          // multicasts into my slot (my row and my column)
-          if (pair)
-            umma_commit_pair(&empty[stage], 0x3);  // the slot is free in both CTAs
-          else if (csize == 1)
-            umma_commit(&empty[stage]);
-          else
-            umma_commit_mc(&empty[stage], peerMask);
+          kstep(d_tmem, da, db, full_a, empty_a, phase, it != 0 ? 1u : 0u);
+          da += dstep;
+          db += dstep;
+          full_a += 8;
+          empty_a += 8;
           if (++stage == (uint32_t)S) {
             stage = 0;
             phase ^= 1;
+            da = da_first;
+            db = db_first;
+            full_a = full0;
+            empty_a = empty0;
           }
         }
         if (pair)

@@ -69,6 +69,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Address-based forms for the MMA issuer's loop (barrier addresses are carried across iterations as plain u32).
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parity) {
+  uint32_t spins = 0, ok = 0;
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > (1u << 24)) {
+      printf("gct2: mbarrier watchdog block %d thread %d bar %u parity %u\n", (int)blockIdx.x, (int)threadIdx.x,
+             bar_addr, parity);
+      __trap();
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------- TMA loads
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -164,6 +186,12 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
           smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_addr(uint32_t bar_addr, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar_addr),
       "h"(mask)
       : "memory");
 }
@@ -284,6 +312,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar_addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc_addr(uint32_t bar_addr, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar_addr),
+      "h"(mask)
+      : "memory");
 }
 // The same arrive, delivered to the mbarrier at this offset in every CTA of `mask` (cluster multicast).
 __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {

@@ -97,7 +97,7 @@ def main():
             print(json.dumps({"layer": name, "pass": pname, "ctas": int(t.shape[0]),
                               "span": round(float(rel[ok, 6].max()), 2),
                               "entry_spread": round(float(rel[ok, 0].max()), 2),
-                              "prologue": st(0, 1), "fill": st(1, 2), "issue": st(1, 7), "mma": st(2, 4), "epi": st(4, 5), "rest": st(5, 6),
+                              "prologue": st(0, 1), "fill": st(1, 2), "issue": st(1, 7), "mma_issue": st(2, 3), "mma": st(2, 4), "epi": st(4, 5), "rest": st(5, 6),
                               "cta_life": st(0, 6)}), flush=True)
 
 
