@@ -118,3 +118,35 @@ def test_optimizer_shards_tile_every_bucket():
             assert covered == total - small
     assert E.optimizer_shard(0, 100, 128, 2, 0) is None      # nothing above the head region
     assert E.optimizer_shard(128, 128 + 12, 128, 8, 0) is None  # not divisible: stays replicated
+
+
+def test_fast_division_magic_numbers():
+    """The multiply-shift constants of csrc/conv_umma.cuh:make_fastdiv (index decoding without integer divisions),
+    restated here: q = umulhi(n, mul) >> shr with p = 31 + ceil(log2 d), mul = ceil(2^p / d), shr = p - 32 must equal
+    n // d for every 0 <= n < 2^31 -- checked on edge values and random samples for small, power-of-two-adjacent and
+    random divisors (non-power-of-two divisors occur with channel counts like 192 = 3 x 64)."""
+    import random
+    rnd = random.Random(0)
+
+    def make(d):
+        if d <= 1:
+            return d, 0, 0
+        lg = (d - 1).bit_length()
+        p = 31 + lg
+        mul = ((1 << p) + d - 1) // d
+        assert mul < (1 << 32)
+        return d, mul, p - 32
+
+    def div(f, n):
+        d, mul, shr = f
+        return n if d == 1 else ((n * mul) >> 32) >> shr
+
+    divisors = list(range(1, 600)) + [2 ** k + s for k in range(1, 20) for s in (-1, 0, 1) if 2 ** k + s > 0]
+    divisors += [rnd.randrange(1, 1 << 20) for _ in range(300)]
+    for d in divisors:
+        f = make(d)
+        ns = [0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, (1 << 31) - 1, (1 << 31) - d, 1 << 30]
+        ns += [rnd.randrange(0, 1 << 31) for _ in range(50)]
+        for n in ns:
+            if 0 <= n < (1 << 31):
+                assert div(f, n) == n // d, (d, n)
