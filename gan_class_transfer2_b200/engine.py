@@ -71,6 +71,12 @@ class NetConfig:
             raise ValueError("down0 filters must be a multiple of 128")
         if self.up_c(0) not in (64, 128):
             raise ValueError("the fused Dense(3)+MSE kernel supports 64 or 128 up0 channels")
+        # weight gradients put one side's channels on the 128-row M axis of the tensor-core tile
+        pairs = [(self.down_c(i - 1), self.down_c(i)) for i in range(1, n)] + [(self.up_in(i), self.up_c(i)) for i in range(n)]
+        for a, b in pairs:
+            if a % 128 and b % 128:
+                raise ValueError(f"a conv layer with {a} -> {b} channels has no side that is a multiple of 128 "
+                                 "(needed by the weight-gradient kernel)")
 
 
 def variable_specs(cfg: NetConfig) -> List[Tuple[str, Tuple[int, ...]]]:
