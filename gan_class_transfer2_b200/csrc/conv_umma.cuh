@@ -13,9 +13,11 @@
 //   MODE_W  weight gradient  dW[tap][g][p] = sum_pix G_hi[pix @ tap, g] * P_lo[pix, p]
 //           both operands MN-major (pixels are the contraction dim and are the slow smem axis).
 //
-// Warp roles: warps 0, 2, 3 = TMA producers (k-iterations round-robin; warp 2 also allocates TMEM), warp 1 = MMA issuer, warps 4.. = epilogue
-// (8 warps for BN = 64, 16 otherwise; TMEM -> registers -> global).  Accumulators are double-buffered in TMEM (2 x BN columns) so the
-// epilogue of tile i overlaps the main loop of tile i+1.
+// Warp roles: warps 0, 2, 3 = TMA producers (k-iterations round-robin; warp 2 also allocates TMEM), warp 1 = MMA
+// issuer, warps 4.. = epilogue (8 warps for BN = 64, 16 otherwise; TMEM -> registers -> global).  Accumulators are
+// double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the main loop of tile i+1.
+// PAIR = 1 instances run as clusters of two CTAs on tcgen05 cta_group::2: each CTA keeps its own 128-row tile, stages
+// half of the B tile, and rank 0 issues one 256-row MMA per K = 16 slice for both (see ptx.cuh, "CTA pairs").
 #pragma once
 #include <cuda_bf16.h>
 #include <type_traits>
