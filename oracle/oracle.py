@@ -8,7 +8,10 @@ not installable in this environment, and train.py cannot even be imported withou
 dataset (train.py:40,305,315).  This restatement therefore follows the TensorFlow/Keras semantics documented
 in SURVEY.md Appendix A and is pinned only by its own self-consistency tests (tests/test_oracle.py): parameter
 count 41 691 660, shape walk, conv-transpose == autograd-dgrad of the SAME-padded strided conv, the 4-phase
-identity, Dense == 1x1 conv, a finite-difference gradient check and an Adam closed-form known answer.
+identity, Dense == 1x1 conv, a finite-difference gradient check and an Adam closed-form known answer -- and by
+tests/test_oracle_direct.py against oracle/direct.c, a plain-C loop-level restatement written from the TensorFlow
+definitions of the same ops (SAME padding from TF's rule, Conv2DTranspose as Conv2D's input-gradient scatter) that
+shares no code with this file.
 
 What follows what (reference = /root/reference/train.py):
   Config            :17-36   module-level hyper-parameters
