@@ -42,17 +42,21 @@ _PROTOS = {
     "gct2_launch_count": (c_longlong, []),
     "gct2_debug_set": (None, [c_int, c_int]),
     "gct2_debug_timeline": (c_int, [_P, c_int]),
+    "gct2_debug_last_plan": (None, [_P]),
+    "gct2_set_sm_budget": (None, [c_int]),
     "gct2_debug_trace": (c_int, [_P, c_int]),
     "gct2_noise_images": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "gct2_conv4s2_c3_fprop": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "gct2_conv4s2_c3_wgrad": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
-    "gct2_conv4s2_fprop": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "gct2_conv4s2_fprop": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, c_int,
+                                   _P]),
     "gct2_conv4s2_dgrad": (c_int, [_P, c_int, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                                   _P, c_size_t, _P]),
+                                   _P, c_size_t, c_int, _P]),
     "gct2_conv4s2_wgrad": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
-    "gct2_convT4s2_fprop": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "gct2_convT4s2_fprop": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, c_int,
+                                    _P]),
     "gct2_convT4s2_dgrad": (c_int, [_P, c_int, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                                    _P, c_size_t, _P]),
+                                    _P, c_size_t, c_int, _P]),
     "gct2_convT4s2_wgrad": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "gct2_bias_grad": (c_int, [_P, c_int, c_longlong, c_int, _P, _P]),
     "gct2_bias_grad_multi": (c_int, [c_int, _P, _P, _P, _P, _P, c_int, _P]),
@@ -86,7 +90,7 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.gct2_abi_version() != 1:
+    if lib.gct2_abi_version() != 2:
         raise Gct2Error("libgct2_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -11,7 +11,7 @@
 using namespace gct2;
 
 namespace {
-int g_force_bn = 0, g_force_splits = 0, g_force_cm = 0, g_force_cn = 0, g_sms = 0;
+int g_force_bn = 0, g_force_splits = 0, g_sms = 0;
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline const __nv_bfloat16* CB(const uint16_t* p) { return reinterpret_cast<const __nv_bfloat16*>(p); }
 inline __nv_bfloat16* MB(uint16_t* p) { return reinterpret_cast<__nv_bfloat16*>(p); }
@@ -37,8 +37,6 @@ ConvArgs blank(int mode, int B, int Hlo, int Wlo) {
   a.Wlo = Wlo;
   a.forceBN = g_force_bn;
   a.forceSplits = g_force_splits;
-  a.forceCm = g_force_cm;
-  a.forceCn = g_force_cn;
   return a;
 }
 }  // namespace
@@ -64,17 +62,15 @@ long long gct2_launch_count(void) { return launch_count(); }
 
 int gct2_debug_trace(unsigned long long* host, int max_records) { return debug_read_trace(host, max_records); }
 int gct2_debug_timeline(unsigned long long* host, int max_ctas) { return debug_read_timeline(host, max_ctas); }
+void gct2_debug_last_plan(int* out8) { debug_last_plan(out8); }
+void gct2_set_sm_budget(int sms) { conv_set_sm_budget(sms); }
 
 void gct2_debug_set(int key, int value) {
   if (key == 3)
     g_force_bn = value;
   else if (key == 4)
     g_force_splits = value;
-  else if (key == 5)
-    g_force_cm = value;
-  else if (key == 6)
-    g_force_cn = value;
-  else if (key == 13)
+  else if (key == 13 || key == 15 || key == 23)
     elementwise_set_debug(key, value);
   else
     conv_set_debug(key, value);
@@ -95,26 +91,26 @@ int gct2_conv4s2_c3_wgrad(const float* x, const uint16_t* dz, int lddz, float* d
 }
 
 int gct2_conv4s2_fprop(const uint16_t* x, int ldx, const uint16_t* w, const float* bias, uint16_t* y, int ldy,
-                       int B, int H, int W, int Cin, int Cout, float* ws, size_t ws_bytes, void* stream) {
+                       int B, int H, int W, int Cin, int Cout, float* ws, size_t ws_bytes, int flags, void* stream) {
   if (check_conv("gct2_conv4s2_fprop", B, H / 2, W / 2, Cin, Cout)) return 1;
   ConvArgs a = blank(MODE_S, B, H / 2, W / 2);
   a.hi = CB(x); a.ldHi = ldx; a.Chi = Cin;
   a.w = CB(w); a.R = Cin; a.Cc = Cout;
   a.epi = EPI_BIAS_RELU; a.out = MB(y); a.ldo = ldy; a.bias = bias;
-  a.ws = ws; a.wsBytes = ws_bytes;
+  a.ws = ws; a.wsBytes = ws_bytes; a.flags = (flags & GCT2_WEIGHTS_STABLE) ? CONV_WEIGHTS_STABLE : 0;
   return conv_launch(a, S(stream));
 }
 
 int gct2_conv4s2_dgrad(const uint16_t* dy, int lddy, const uint16_t* w, uint16_t* dx, int lddx,
                        const uint16_t* act, int ldact, int add_old, int B, int H, int W, int Cin, int Cout,
-                       float* ws, size_t ws_bytes, void* stream) {
+                       float* ws, size_t ws_bytes, int flags, void* stream) {
   if (check_conv("gct2_conv4s2_dgrad", B, H / 2, W / 2, Cin, Cout)) return 1;
   ConvArgs a = blank(MODE_P, B, H / 2, W / 2);
   a.lo = CB(dy); a.ldLo = lddy; a.Clo = Cout;
   a.w = CB(w); a.R = Cin; a.Cc = Cout;
   a.epi = EPI_DGRAD; a.out = MB(dx); a.ldo = lddx; a.act = CB(act); a.ldact = ldact; a.maskN = Cin;
   a.addOld = add_old ? 1 : 0;
-  a.ws = ws; a.wsBytes = ws_bytes;
+  a.ws = ws; a.wsBytes = ws_bytes; a.flags = (flags & GCT2_WEIGHTS_STABLE) ? CONV_WEIGHTS_STABLE : 0;
   return conv_launch(a, S(stream));
 }
 
@@ -130,19 +126,19 @@ int gct2_conv4s2_wgrad(const uint16_t* x, int ldx, const uint16_t* dy, int lddy,
 }
 
 int gct2_convT4s2_fprop(const uint16_t* x, int ldx, const uint16_t* w, const float* bias, uint16_t* y, int ldy,
-                        int B, int H, int W, int Cin, int Cout, float* ws, size_t ws_bytes, void* stream) {
+                        int B, int H, int W, int Cin, int Cout, float* ws, size_t ws_bytes, int flags, void* stream) {
   if (check_conv("gct2_convT4s2_fprop", B, H, W, Cin, Cout)) return 1;
   ConvArgs a = blank(MODE_P, B, H, W);
   a.lo = CB(x); a.ldLo = ldx; a.Clo = Cin;
   a.w = CB(w); a.R = Cout; a.Cc = Cin;
   a.epi = EPI_BIAS_RELU; a.out = MB(y); a.ldo = ldy; a.bias = bias;
-  a.ws = ws; a.wsBytes = ws_bytes;
+  a.ws = ws; a.wsBytes = ws_bytes; a.flags = (flags & GCT2_WEIGHTS_STABLE) ? CONV_WEIGHTS_STABLE : 0;
   return conv_launch(a, S(stream));
 }
 
 int gct2_convT4s2_dgrad(const uint16_t* dy, int lddy, const uint16_t* w, uint16_t* dx, int lddx,
                         const uint16_t* act, int ldact, int mask_channels, int B, int H, int W, int Cin, int Cout,
-                        float* ws, size_t ws_bytes, void* stream) {
+                        float* ws, size_t ws_bytes, int flags, void* stream) {
   if (check_conv("gct2_convT4s2_dgrad", B, H, W, Cin, Cout)) return 1;
   if (mask_channels % 32 || mask_channels < 0 || mask_channels > Cin) {
     set_error("gct2_convT4s2_dgrad: mask_channels must be a multiple of 32 in [0, Cin] (got %d)", mask_channels);
@@ -153,7 +149,7 @@ int gct2_convT4s2_dgrad(const uint16_t* dy, int lddy, const uint16_t* w, uint16_
   a.w = CB(w); a.R = Cout; a.Cc = Cin;
   a.epi = EPI_DGRAD; a.out = MB(dx); a.ldo = lddx; a.act = CB(act); a.ldact = ldact; a.maskN = mask_channels;
   a.addOld = 0;
-  a.ws = ws; a.wsBytes = ws_bytes;
+  a.ws = ws; a.wsBytes = ws_bytes; a.flags = (flags & GCT2_WEIGHTS_STABLE) ? CONV_WEIGHTS_STABLE : 0;
   return conv_launch(a, S(stream));
 }
 

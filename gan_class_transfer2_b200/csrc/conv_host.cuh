@@ -23,14 +23,16 @@ struct ConvArgs {
   const float* bias;
   const __nv_bfloat16* act;
   int ldact, maskN, addOld;
-  float* ws;                     // fp32 split-K workspace (zero on entry, left zero on exit)
+  float* ws;                     // fp32 split-K workspace (contents irrelevant on entry and on exit)
   size_t wsBytes;
+  int flags;                     // CONV_WEIGHTS_STABLE: `w` is not being written by any launch that may still be running
+                                 // when this one starts, so its boxes may be fetched before griddepcontrol.wait
   // W
   float* dw;                     // fp32 [16][Chi][Clo]
   // tuning overrides (0 = heuristic)
   int forceBN, forceSplits;
-  int forceCm, forceCn;          // cluster shape override (0 = heuristic, 1 = no cluster along that axis)
 };
+enum : int { CONV_WEIGHTS_STABLE = 1 };
 
 extern int g_use_pdl;  // 1 = launch with programmatic stream serialisation (debug key 8 toggles)
 
@@ -55,7 +57,9 @@ int conv_init(int device);                       // once per process/device
 int conv_launch(const ConvArgs& a, cudaStream_t stream);
 int debug_read_timeline(unsigned long long* host, int max_ctas);  // test hook, see gct2_debug_timeline
 int debug_read_trace(unsigned long long* host, int max_records);   // test hook, see gct2_debug_trace
-void conv_set_debug(int key, int value);         // test hook: 0 = MN-major LBO, 1 = MN-major SBO, 2 = verbose
+void conv_set_debug(int key, int value);         // test hooks, see gct2_debug_set in include/gct2_b200.h
+void conv_set_sm_budget(int n);                  // CTAs a conv launch may occupy (0 = all SMs)
+void debug_last_plan(int* out8);                 // test hook, see gct2_debug_last_plan
 const char* last_error();
 void count_launch(int n = 1);                   // kernels/memsets enqueued by this library (gct2_launch_count)
 long long launch_count();

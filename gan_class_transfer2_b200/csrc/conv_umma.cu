@@ -23,33 +23,58 @@ void set_error(const char* fmt, ...) {
 int g_use_pdl = 1;
 static int g_pair = 0;                 // debug key 19: 0 = CTA pairs (cta_group::2) when a launch has more tiles than SMs,
                                        // 1 = wherever legal, 2 = never
-static int g_stages = 0;               // debug key 17: cap of the pipeline depth (0 = as deep as shared memory allows)
-static int g_stamp_pos = 0;            // debug key 16: see ConvParams::stampPos
 static int g_fuse_finish = 1;          // debug key 12 != 0 disables the in-kernel split-K finish
-static int* g_cnt = nullptr;           // rendezvous counters of the fused finish: [FUSE_MAX_TILES][2], zero at rest
-constexpr int FUSE_MAX_TILES = 4096;
 static int g_cap_w = 0, g_cap_sp = 0;  // debug keys 9 / 10: CTA budget of wgrad / dgrad launches (0 = all SMs)
+static int g_sm_budget = 0;            // key 22 / gct2_set_sm_budget: CTAs any conv launch may occupy (0 = all SMs)
+static int g_b_early = 1;              // debug key 21 != 0 disables the weight fetch before griddepcontrol.wait
+static unsigned g_spin_limit = 1u << 28;  // debug key 20: rendezvous watchdog in polls of ~40 ns (default ~10 s; 0 = none)
+static int g_stamp_pos = 0;            // debug key 16 (-DGCT2_TIMELINE builds): see ConvParams::stampPos
 static long long g_launches = 0;
 void count_launch(int n) { g_launches += n; }
 long long launch_count() { return g_launches; }
+static int g_last_plan[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // BN, splits, pair, fused, grid, stages, rounds, early
+void debug_last_plan(int* out8) {
+  for (int i = 0; i < 8; ++i) out8[i] = g_last_plan[i];
+}
 
 // ------------------------------------------------------------------------------------ globals
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
-static int g_num_sms = 148;
 static int g_mn_lbo = 8192, g_mn_sbo = 1024, g_verbose = 0;
 static unsigned long long* g_dbg = nullptr;  // test hook (key 7): phase timestamps of the most recent conv launch
 static int g_dbg_ctas = 0;
 constexpr int DBG_MAX_CTAS = 512;
-static bool g_inited = false;
+
+// Per-device state: the library may be initialised on several devices of one process (one engine per device); every
+// launch looks its device up with cudaGetDevice().
+constexpr int MAX_DEVICES = 16;
+constexpr int CNT_RING_INTS = 1 << 20;  // rendezvous counters of the fused split-K finish: a ring every fused launch cuts
+                                        // its own [numTiles][2] region from, so launches in flight on different streams
+                                        // (a second engine, sampling beside training) never share counters
+struct DeviceState {
+  bool inited = false;
+  int num_sms = 148;
+  int* cnt = nullptr;
+  size_t cnt_next = 0;
+  int max_pairs[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};  // co-resident 2-CTA clusters [mode][BN index] (0 = unsupported)
+};
+static DeviceState g_dev[MAX_DEVICES];
+static DeviceState* cur_dev() {
+  int d = -1;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= MAX_DEVICES || !g_dev[d].inited) return nullptr;
+  return &g_dev[d];
+}
 
 int debug_read_timeline(unsigned long long* host, int max_ctas) {
   if (g_dbg == nullptr) return 0;
   const int n = g_dbg_ctas < max_ctas ? g_dbg_ctas : max_ctas;
-  cudaDeviceSynchronize();
-  cudaMemcpy(host, g_dbg, (size_t)n * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  if (cudaDeviceSynchronize() != cudaSuccess ||
+      cudaMemcpy(host, g_dbg, (size_t)n * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    set_error("debug_read_timeline: %s", cudaGetErrorString(cudaGetLastError()));
+    return -1;
+  }
   return n;
 }
 
@@ -57,24 +82,37 @@ static unsigned long long* g_trace_host_ptr = nullptr;
 void trace_set_elementwise(unsigned long long* buf);  // elementwise.cu's copy of the pointer
 int debug_read_trace(unsigned long long* host, int max_records) {
   if (g_trace_host_ptr == nullptr) return 0;
-  cudaDeviceSynchronize();
   unsigned long long n = 0;
-  cudaMemcpy(&n, g_trace_host_ptr, sizeof(n), cudaMemcpyDeviceToHost);
+  if (cudaDeviceSynchronize() != cudaSuccess ||
+      cudaMemcpy(&n, g_trace_host_ptr, sizeof(n), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    set_error("debug_read_trace: %s", cudaGetErrorString(cudaGetLastError()));
+    return -1;
+  }
   if (n > TRACE_MAX_RECORDS) n = TRACE_MAX_RECORDS;
   if ((int)n > max_records) n = max_records;
-  cudaMemcpy(host, g_trace_host_ptr + 1, n * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-  cudaMemset(g_trace_host_ptr, 0, sizeof(unsigned long long));
+  if (cudaMemcpy(host, g_trace_host_ptr + 1, n * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess ||
+      cudaMemset(g_trace_host_ptr, 0, sizeof(unsigned long long)) != cudaSuccess) {
+    set_error("debug_read_trace: %s", cudaGetErrorString(cudaGetLastError()));
+    return -1;
+  }
   return (int)n;
 }
+
+void conv_set_sm_budget(int n) { g_sm_budget = n > 0 ? n : 0; }
 
 void conv_set_debug(int key, int value) {
   if (key == 11) {
     if (value && g_trace_host_ptr == nullptr) {
-      cudaMalloc(&g_trace_host_ptr, (1 + TRACE_MAX_RECORDS * 4) * sizeof(unsigned long long));
-      cudaMemset(g_trace_host_ptr, 0, (1 + TRACE_MAX_RECORDS * 4) * sizeof(unsigned long long));
+      const size_t bytes = (1 + TRACE_MAX_RECORDS * 4) * sizeof(unsigned long long);
+      if (cudaMalloc(&g_trace_host_ptr, bytes) != cudaSuccess || cudaMemset(g_trace_host_ptr, 0, bytes) != cudaSuccess) {
+        set_error("step trace buffer: %s", cudaGetErrorString(cudaGetLastError()));
+        g_trace_host_ptr = nullptr;
+        return;
+      }
     }
     unsigned long long* dev = value ? g_trace_host_ptr : nullptr;
-    cudaMemcpyToSymbol(g_trace_buf, &dev, sizeof(dev));
+    if (cudaMemcpyToSymbol(g_trace_buf, &dev, sizeof(dev)) != cudaSuccess)
+      set_error("step trace symbol: %s", cudaGetErrorString(cudaGetLastError()));
     trace_set_elementwise(dev);
   }
   if (key == 0) g_mn_lbo = value;
@@ -82,13 +120,19 @@ void conv_set_debug(int key, int value) {
   if (key == 2) g_verbose = value;
   if (key == 8) g_use_pdl = value ? 0 : 1;  // key 8 != 0 disables programmatic dependent launch
   if (key == 9) g_cap_w = value;
+  if (key == 10) g_cap_sp = value;
   if (key == 12) g_fuse_finish = value ? 0 : 1;
   if (key == 16) g_stamp_pos = value;
-  if (key == 17) g_stages = value;
   if (key == 19) g_pair = value;
-  if (key == 10) g_cap_sp = value;
+  if (key == 20) g_spin_limit = (unsigned)value;
+  if (key == 21) g_b_early = value ? 0 : 1;
+  if (key == 22) conv_set_sm_budget(value);
   if (key == 7) {
-    if (value && g_dbg == nullptr) cudaMalloc(&g_dbg, (size_t)DBG_MAX_CTAS * 8 * sizeof(unsigned long long));
+    if (value && g_dbg == nullptr &&
+        cudaMalloc(&g_dbg, (size_t)DBG_MAX_CTAS * 8 * sizeof(unsigned long long)) != cudaSuccess) {
+      set_error("timeline buffer: %s", cudaGetErrorString(cudaGetLastError()));
+      g_dbg = nullptr;
+    }
     if (!value && g_dbg != nullptr) {
       cudaFree(g_dbg);
       g_dbg = nullptr;
@@ -101,16 +145,28 @@ static int set_attr() {
   cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<MODE, BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        227 * 1024);
   if (e != cudaSuccess) {
-    set_error("cudaFuncSetAttribute(conv_umma_kernel<%d,%d>): %s", MODE, BN, cudaGetErrorString(e));
+    set_error("cudaFuncSetAttribute(conv_umma_kernel<%d,%d,%d>): %s", MODE, BN, PAIR, cudaGetErrorString(e));
     return 1;
   }
   return 0;
 }
 
-static void query_all_clusters();
+static void query_all_pairs(DeviceState& ds);
 
 int conv_init(int device) {
-  if (g_inited) return 0;
+  if (device < 0 || device >= MAX_DEVICES) {
+    set_error("gct2_init: device %d out of range", device);
+    return 1;
+  }
+  if (g_dev[device].inited) return 0;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  struct Restore {
+    int prev;
+    ~Restore() {
+      if (prev >= 0) cudaSetDevice(prev);  // never leave the caller on another device
+    }
+  } restore{prev};
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) {
     set_error("cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
@@ -126,29 +182,33 @@ int conv_init(int device) {
     set_error("gct2 requires an sm_100a device (B200); found sm_%d%d", prop.major, prop.minor);
     return 1;
   }
-  g_num_sms = prop.multiProcessorCount;
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
-    set_error("cuTensorMapEncodeTiled entry point unavailable: %s", cudaGetErrorString(e));
-    return 1;
+  DeviceState& ds = g_dev[device];
+  ds.num_sms = prop.multiProcessorCount;
+  if (g_encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled entry point unavailable: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
-  int rc = 0;
+  int rc = 0;  // function attributes are per device: set them on every device that is initialised
   rc |= set_attr<MODE_S, 64>() | set_attr<MODE_S, 128>() | set_attr<MODE_S, 256>();
   rc |= set_attr<MODE_P, 64>() | set_attr<MODE_P, 128>() | set_attr<MODE_P, 256>();
   rc |= set_attr<MODE_W, 64>() | set_attr<MODE_W, 128>() | set_attr<MODE_W, 256>();
   rc |= set_attr<MODE_S, 128, 1>() | set_attr<MODE_S, 256, 1>() | set_attr<MODE_P, 128, 1>() | set_attr<MODE_P, 256, 1>();
   rc |= set_attr<MODE_W, 128, 1>() | set_attr<MODE_W, 256, 1>();
   if (rc) return 1;
-  query_all_clusters();
-  if (cudaMalloc(&g_cnt, (size_t)FUSE_MAX_TILES * 2 * sizeof(int)) != cudaSuccess ||
-      cudaMemset(g_cnt, 0, (size_t)FUSE_MAX_TILES * 2 * sizeof(int)) != cudaSuccess) {
+  query_all_pairs(ds);
+  if (cudaMalloc(&ds.cnt, (size_t)CNT_RING_INTS * sizeof(int)) != cudaSuccess ||
+      cudaMemset(ds.cnt, 0, (size_t)CNT_RING_INTS * sizeof(int)) != cudaSuccess) {
     set_error("could not allocate the split-K rendezvous counters");
     return 1;
   }
-  g_inited = true;
+  ds.cnt_next = 0;
+  ds.inited = true;
   return 0;
 }
 
@@ -268,72 +328,80 @@ __global__ void wgrad_reduce_kernel(const float4* __restrict__ ws, long long spl
 }
 
 // ------------------------------------------------------------------------------------ heuristics
-// Ring depth: every tile width fills the same 192 KB of pipeline -- 8 x 24 KB, 6 x 32 KB, 4 x 48 KB; a CTA of a pair
-// stages only half of the B tile: 8 x 24 KB at BN = 128, 6 x 32 KB at BN = 256.  (A TMA round trip is ~500 cycles and a
-// k-step 470-655, so the ring is deeper than steady state needs; the depth absorbs the start-up burst.  Two- to four-
-// slot rings that would let two CTAs share an SM were measured: -16 % at batch 1, -25 % at batch 32.)
-static int stages_for(int BN, bool pair = false) {
-  int s = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
-  if (pair) s = BN == 256 ? 6 : 8;
-  return g_stages > 0 && g_stages < s ? g_stages : s;
-}
+// Ring: every shape fills the same 192 KB of pipeline (conv_umma.cuh: kStages / kStageBytes) -- 4 x 48 KB at BN = 64 and
+// 3 x 64 KB at BN = 128 (two k-chunks per slot), 4 x 48 KB at BN = 256; a CTA of a pair stages only half of the B tile:
+// 4 x 48 KB at BN = 128, 6 x 32 KB at BN = 256.  (Two- to four-slot rings that would let two CTAs share an SM were
+// measured in round 1: -16 % at batch 1, -25 % at batch 32.)
 // pipeline stages + barriers (256 B) + 1 KB alignment slack
 static size_t smem_for(int BN, bool pair = false) {
-  return (size_t)stages_for(BN, pair) * (16384 + (pair ? BN * 64 : BN * 128)) + 1024 + 256;
+  (void)BN;
+  (void)pair;
+  return (size_t)192 * 1024 + 1024 + 256;
 }
+static int stages_for(int BN, bool pair) {
+  if (pair) return BN == 256 ? kStages<256, 1>() : kStages<128, 1>();
+  return BN == 256 ? kStages<256, 0>() : (BN == 128 ? kStages<128, 0>() : kStages<64, 0>());
+}
+static int kps_for(int BN) { return BN == 256 ? 1 : 2; }
 
 struct Choice {
-  int BN, splits, cm, cn;
+  int BN, splits;
   int pair = 0;
 };
 
-// Maximum number of co-resident clusters of `csize` CTAs for each tile width (queried once; 0 = unsupported).
-static int g_max_clusters[3][3][9];  // [mode][BN index][cluster size]
 static int bn_index(int BN) { return BN == 64 ? 0 : (BN == 128 ? 1 : 2); }
 
 template <int MODE, int BN>
-static void query_clusters() {
-  for (int cs = 2; cs <= 8; cs *= 2) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(cs * 32);
-    cfg.blockDim = dim3(kConvThreads<BN>());
-    cfg.dynamicSmemBytes = smem_for(BN);
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = cs;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, conv_umma_kernel<MODE, BN>, &cfg) != cudaSuccess) {
-      cudaGetLastError();
-      n = 0;
-    }
-    g_max_clusters[MODE][bn_index(BN)][cs] = n;
+static void query_pairs(DeviceState& ds) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * 32);
+  cfg.blockDim = dim3(kConvThreads<BN>());
+  cfg.dynamicSmemBytes = smem_for(BN, true);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, conv_umma_kernel<MODE, BN, 1>, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
   }
+  ds.max_pairs[MODE][bn_index(BN)] = n;
 }
 
-static void query_all_clusters() {
-  query_clusters<MODE_S, 64>(); query_clusters<MODE_S, 128>(); query_clusters<MODE_S, 256>();
-  query_clusters<MODE_P, 64>(); query_clusters<MODE_P, 128>(); query_clusters<MODE_P, 256>();
-  query_clusters<MODE_W, 64>(); query_clusters<MODE_W, 128>(); query_clusters<MODE_W, 256>();
+static void query_all_pairs(DeviceState& ds) {
+  query_pairs<MODE_S, 128>(ds); query_pairs<MODE_S, 256>(ds);
+  query_pairs<MODE_P, 128>(ds); query_pairs<MODE_P, 256>(ds);
+  query_pairs<MODE_W, 128>(ds); query_pairs<MODE_W, 256>(ds);
+}
+
+// CTAs a launch may occupy: all SMs, or the caller's budget (gct2_set_sm_budget: SMs left to a concurrently running
+// NCCL kernel or optimiser launch), further capped by the per-chain test hooks.
+static int cta_budget(const DeviceState& ds, int mode, bool dgradEpi) {
+  int n = ds.num_sms;
+  if (g_sm_budget > 0 && g_sm_budget < n) n = g_sm_budget;
+  const int cap = mode == MODE_W ? g_cap_w : (dgradEpi ? g_cap_sp : 0);
+  if (cap > 0 && cap < n) n = cap;
+  return n;
 }
 
 // Cost model (SM cycles at ~1.97 GHz) for one launch, fitted to per-CTA phase timelines measured on B200
-// (tools/timeline.py; profiles/): fixed start-up + k-steps + epilogue, where
-//   * a k-step is issue-bound (MMA issuer: wait, 4 UMMAs, commit; three TMA producers keep up) until all SMs together
-//     exceed what L2 delivers -- wide tiles ingest fewer bytes per FLOP and win at large batch;
+// (tools/timeline.py; profiles/): fixed start-up + ring rounds + epilogue, where
+//   * a ring round is issue-bound (MMA issuer: wait, 4 UMMAs per k-chunk, commit; three TMA producers keep up) until all
+//     SMs together exceed what L2 delivers -- wide tiles ingest fewer bytes per FLOP and win at large batch;
 //   * split-K buys parallelism for the price of a partial tile's round trip through L2 and a rendezvous (fused) or an
 //     extra launch (finishing kernel) -- with cheap k-steps it pays only when a layer has very few tiles;
 //   * epilogues scale with the tile's real rows: deep layers at batch 1 fill 16-64 of a tile's 128 rows.
-static Choice choose(int mode, int mTiles, int phases, int N, int kTotal, long long outElems, bool dgradEpi,
-                     int forceBN, int forceSplits, int forceCm, int forceCn, size_t slabBytes, size_t wsBytes) {
-  Choice best{0, 1, 1, 1};
+static Choice choose(const DeviceState& ds, int mode, int mTiles, int phases, int N, int kTotal, long long outElems,
+                     bool dgradEpi, int forceBN, int forceSplits, size_t slabBytes, size_t wsBytes) {
+  Choice best{0, 1};
   double bestCost = 1e30;
   const int bns[3] = {256, 128, 64};
-  const int cms[4] = {1, 2, 4, 8}, cns[3] = {1, 2, 4};
   const bool isW = mode == MODE_W;
+  const int maxCtas = cta_budget(ds, mode, dgradEpi);
   for (int bi = 0; bi < 3; ++bi) {
     const int BN = bns[bi];
     if (N % BN) continue;
@@ -346,55 +414,39 @@ static Choice choose(int mode, int mTiles, int phases, int N, int kTotal, long l
       const size_t tileSlab = isW ? 0 : (size_t)mTiles * phases * 128 * N * sizeof(float);
       if (splits > 1 && (slabBytes > tileSlab ? slabBytes : tileSlab) * splits > wsBytes) break;
       const int kIters = kTotal / splits;
-      for (int a = 0; a < 4; ++a) {
-        for (int b = 0; b < 3; ++b) {
-          const int cm = cms[a], cn = cns[b], cs = cm * cn;
-          if (cs > 8 || mTiles % cm || nTiles % cn) continue;
-          if (isW && cs > 1) continue;
-          // multicast clusters cost 1.3 us per launch and the main loop is issue-bound, not ingest-bound; measured slower
-          // at 1, 8 and 32 images per GPU (profiles/README.md), so they are used only on request (debug keys 5/6)
-          if (forceCm >= 1 ? cm != forceCm : cm != 1) continue;
-          if (forceCn >= 1 ? cn != forceCn : cn != 1) continue;
-          int maxCtas = g_num_sms;
-          const int cap = isW ? g_cap_w : (dgradEpi ? g_cap_sp : 0);
-          if (cap > 0 && cap < maxCtas) maxCtas = cap;
-          if (cs > 1) {
-            const int mc = g_max_clusters[mode][bn_index(BN)][cs];
-            if (mc <= 0) continue;
-            maxCtas = mc * cs;
-          }
-          const long long items = (long long)mTiles * phases * (isW ? 16 : 1) * nTiles * splits;
-          const long long active = items < maxCtas ? items : maxCtas;
-          const long long rounds = (items + active - 1) / active;
-          // one k-step: issue-bound at small grids (measured 470 / 525 / 655 cycles at BN = 64 / 128 / 256), bound by
-          // the chip-wide L2 -> SM rate (~6000 B/clk) when every SM pulls at once
-          double tk = 408.0 + 0.96 * BN;
-          const double l2 = (16384.0 / cn + BN * 128.0 / cm) * (double)active / 6000.0;
-          if (l2 > tk) tk = l2;
-          const double main = kIters * tk;
-          // rows of a 128-row tile that hold real pixels (deep layers at batch 1 have 16 .. 64)
-          double validRows = isW ? 128.0 : (double)outElems / ((double)N * mTiles * phases);
-          if (validRows > 128.0) validRows = 128.0;
-          double epi;
-          if (splits > 1 && !isW) {
-            // partial tile to its slab and back through L2 (~14.5 B/clk per CTA each way) + the rendezvous
-            epi = 5000.0 + 2.0 * validRows * BN * 4.0 / 14.5;
-            // finished by a separate kernel: a launch + every slab read once more, at the chip-wide rate
-            if (items > maxCtas || cs > 1) epi += 6000.0 + (double)outElems * 4.0 * (splits + 0.5) / 3000.0;
-          } else if (isW) {
-            epi = 35.0 * BN;                                // fp32 tile straight to HBM
-            if (splits > 1) epi += 5000.0 + (double)outElems * 4.0 * (splits + 1.0) / 3000.0;  // + reduction kernel
-          } else {
-            epi = dgradEpi ? 600.0 + 30.0 * BN : 1000.0 + 15.0 * BN;
-            epi *= 0.25 + 0.75 * validRows / 128.0;
-          }
-          // fixed per launch: prologue 0.7 us + first loads 1.45 us + teardown 0.25 us (clusters: + 1.3 us)
-          double cost = 4800.0 + (cs > 1 ? 2600.0 : 0.0) + rounds * main + epi + (rounds - 1) * (epi > main ? epi - main : 0.0);
-          if (cost < bestCost) {
-            bestCost = cost;
-            best = Choice{BN, splits, cm, cn};
-          }
-        }
+      const long long items = (long long)mTiles * phases * (isW ? 16 : 1) * nTiles * splits;
+      const long long active = items < maxCtas ? items : maxCtas;
+      const long long waves = (items + active - 1) / active;
+      // one 64-wide k-chunk: issue-bound at small grids (a ring round = wait + commit + 4 UMMAs per chunk: measured
+      // 470 / 525 / 655 cycles per chunk with one chunk per round at BN = 64 / 128 / 256; two chunks share the round at
+      // BN <= 128), never below the tensor pipe's 2*BN cycles, and bound by the chip-wide L2 -> SM rate (~6000 B/clk)
+      // when every SM pulls at once
+      double tk = kps_for(BN) == 2 ? 290.0 : 408.0 + 0.96 * BN;
+      if (tk < 2.1 * BN) tk = 2.1 * BN;
+      const double l2 = (16384.0 + BN * 128.0) * (double)active / 6000.0;
+      if (l2 > tk) tk = l2;
+      const double main = kIters * tk;
+      // rows of a 128-row tile that hold real pixels (deep layers at batch 1 have 16 .. 64)
+      double validRows = isW ? 128.0 : (double)outElems / ((double)N * mTiles * phases);
+      if (validRows > 128.0) validRows = 128.0;
+      double epi;
+      if (splits > 1 && !isW) {
+        // partial tile to its slab and back through L2 (~14.5 B/clk per CTA each way) + the rendezvous
+        epi = 5000.0 + 2.0 * validRows * BN * 4.0 / 14.5;
+        // finished by a separate kernel: a launch + every slab read once more, at the chip-wide rate
+        if (items > maxCtas) epi += 6000.0 + (double)outElems * 4.0 * (splits + 0.5) / 3000.0;
+      } else if (isW) {
+        epi = 35.0 * BN;                                // fp32 tile straight to HBM
+        if (splits > 1) epi += 5000.0 + (double)outElems * 4.0 * (splits + 1.0) / 3000.0;  // + reduction kernel
+      } else {
+        epi = dgradEpi ? 600.0 + 30.0 * BN : 1000.0 + 15.0 * BN;
+        epi *= 0.25 + 0.75 * validRows / 128.0;
+      }
+      // fixed per launch: prologue 0.7 us + first loads 1.45 us + teardown 0.25 us
+      const double cost = 4800.0 + waves * main + epi + (waves - 1) * (epi > main ? epi - main : 0.0);
+      if (cost < bestCost) {
+        bestCost = cost;
+        best = Choice{BN, splits};
       }
     }
   }
@@ -402,8 +454,8 @@ static Choice choose(int mode, int mTiles, int phases, int N, int kTotal, long l
 }
 
 template <int MODE, int BN, int PAIR = 0>
-static cudaError_t launch_one(int grid, int csize, size_t smem, cudaStream_t st, const CUtensorMap& a,
-                              const CUtensorMap& b, const ConvParams& p) {
+static cudaError_t launch_one(int grid, size_t smem, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b,
+                              const ConvParams& p) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kConvThreads<BN>());
@@ -412,9 +464,9 @@ static cudaError_t launch_one(int grid, int csize, size_t smem, cudaStream_t st,
   cudaLaunchAttribute at[2];
   cfg.attrs = at;
   cfg.numAttrs = 0;
-  if (csize > 1) {
+  if (PAIR) {
     at[cfg.numAttrs].id = cudaLaunchAttributeClusterDimension;
-    at[cfg.numAttrs].val.clusterDim.x = csize;
+    at[cfg.numAttrs].val.clusterDim.x = 2;
     at[cfg.numAttrs].val.clusterDim.y = 1;
     at[cfg.numAttrs].val.clusterDim.z = 1;
     ++cfg.numAttrs;
@@ -428,17 +480,16 @@ static cudaError_t launch_one(int grid, int csize, size_t smem, cudaStream_t st,
 }
 
 template <int MODE>
-static cudaError_t launch_bn(int BN, int grid, int csize, size_t smem, cudaStream_t st, const CUtensorMap& a,
-                             const CUtensorMap& b, const ConvParams& p) {
-  if (p.pair) {
+static cudaError_t launch_bn(int BN, int grid, size_t smem, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b,
+                             const ConvParams& p) {
+  if (p.cm == 2) {
     if (BN < 128) return cudaErrorInvalidValue;
-    return BN == 128 ? launch_one<MODE, 128, 1>(grid, csize, smem, st, a, b, p)
-                     : launch_one<MODE, 256, 1>(grid, csize, smem, st, a, b, p);
+    return BN == 128 ? launch_one<MODE, 128, 1>(grid, smem, st, a, b, p) : launch_one<MODE, 256, 1>(grid, smem, st, a, b, p);
   }
   switch (BN) {
-    case 64: return launch_one<MODE, 64>(grid, csize, smem, st, a, b, p);
-    case 128: return launch_one<MODE, 128>(grid, csize, smem, st, a, b, p);
-    default: return launch_one<MODE, 256>(grid, csize, smem, st, a, b, p);
+    case 64: return launch_one<MODE, 64>(grid, smem, st, a, b, p);
+    case 128: return launch_one<MODE, 128>(grid, smem, st, a, b, p);
+    default: return launch_one<MODE, 256>(grid, smem, st, a, b, p);
   }
 }
 
@@ -453,10 +504,12 @@ static void pixel_tile(int rows, int H, int W, int* Wt, int* Ht, int* Nb) {
 }
 
 int conv_launch(const ConvArgs& a, cudaStream_t stream) {
-  if (!g_inited) {
-    set_error("gct2_init was not called");
+  DeviceState* dsp = cur_dev();
+  if (dsp == nullptr) {
+    set_error("gct2_init was not called for the current device");
     return 1;
   }
+  DeviceState& ds = *dsp;
   ConvParams p;
   memset(&p, 0, sizeof(p));
   CUtensorMap mapA, mapB;
@@ -475,7 +528,9 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
   p.tilesY = a.Hlo / p.Ht;
   const int tilesB = (a.B + p.Nb - 1) / p.Nb;
   const int pixTiles = p.tilesX * p.tilesY * tilesB;
+  const int maxCtas = cta_budget(ds, a.mode, a.epi == EPI_DGRAD);
   int BN = 0;
+  p.cm = 1;
 
   if (a.mode == MODE_S || a.mode == MODE_P) {
     const int Ck = a.mode == MODE_S ? a.Chi : a.Clo;
@@ -491,8 +546,8 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     p.kcPer = Ck / 64;
     const int kTotal = taps * p.kcPer;
     const size_t slab = (size_t)a.B * (a.mode == MODE_S ? 1 : 4) * a.Hlo * a.Wlo * N * sizeof(float);
-    Choice c = choose(a.mode, pixTiles, phases, N, kTotal, (long long)(slab / sizeof(float)), a.epi == EPI_DGRAD,
-                      a.forceBN, a.forceSplits, a.forceCm, a.forceCn, slab, a.ws ? a.wsBytes : 0);
+    Choice c = choose(ds, a.mode, pixTiles, phases, N, kTotal, (long long)(slab / sizeof(float)), a.epi == EPI_DGRAD,
+                      a.forceBN, a.forceSplits, slab, a.ws ? a.wsBytes : 0);
     if (c.BN == 0) {
       set_error("conv: no tile shape for N=%d", N);
       return 1;
@@ -501,20 +556,16 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     // (measured: +4 % step throughput at 8 images/GPU, +6 % at 32, -1 % at batch 1 where a CTA owns one tile and
     // the cluster launch costs more than the shared B tile saves -- hence only for launches of more than one wave)
     const long long itemsPlain = (long long)pixTiles * (N / c.BN) * phases * c.splits;
-    if ((g_pair == 1 || (g_pair == 0 && itemsPlain > g_num_sms)) && c.cm * c.cn == 1 && c.BN >= 128 &&
-        pixTiles % 2 == 0 && g_max_clusters[a.mode][bn_index(c.BN)][2] > 0) {
-      c.cm = 2;
+    if ((g_pair == 1 || (g_pair == 0 && itemsPlain > maxCtas)) && c.BN >= 128 && pixTiles % 2 == 0 &&
+        ds.max_pairs[a.mode][bn_index(c.BN)] > 0)
       c.pair = 1;
-    }
     BN = c.BN;
     p.mTiles = pixTiles;
     p.nTiles = N / BN;
     p.splits = c.splits;
     p.kIters = kTotal / c.splits;
     p.numItems = pixTiles * p.nTiles * phases * c.splits;
-    p.cm = c.cm;
-    p.cn = c.cn;
-    p.pair = c.pair;
+    p.cm = c.pair ? 2 : 1;
     p.N = N;
     p.Hout = a.mode == MODE_S ? a.Hlo : 2 * a.Hlo;
     p.Wout = a.mode == MODE_S ? a.Wlo : 2 * a.Wlo;
@@ -526,6 +577,7 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     p.maskN = a.maskN;
     p.addOld = a.addOld;
     p.epi = a.epi;
+    p.bEarly = (g_b_early && (a.flags & CONV_WEIGHTS_STABLE)) ? 1 : 0;
     if (c.splits > 1) {
       p.epi = EPI_WS_SLAB;
       p.ws = a.ws;
@@ -533,10 +585,18 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
       p.numTiles = phases * p.nTiles * pixTiles;
       // finish inside the launch when every item has its own resident CTA (so the splits of a tile can wait for each
       // other); otherwise a finishing kernel sums the slabs
-      p.fused = (g_fuse_finish && (c.cm * c.cn == 1 || c.pair) && p.numItems <= g_num_sms && p.numTiles <= FUSE_MAX_TILES &&
-                 !(g_cap_sp > 0 && p.numItems > g_cap_sp)) ? 1 : 0;
+      int resident = maxCtas;  // CTAs of this launch that can be on the chip at once
+      if (c.pair && ds.max_pairs[a.mode][bn_index(BN)] * 2 < resident) resident = ds.max_pairs[a.mode][bn_index(BN)] * 2;
+      p.fused = (g_fuse_finish && p.numItems <= resident && (size_t)p.numTiles * 2 <= (size_t)CNT_RING_INTS / 4) ? 1 : 0;
       p.realEpi = a.epi;
-      p.cnt = g_cnt;
+      if (p.fused) {
+        // this launch's own counter region (zero at rest: the last split through the rendezvous re-arms it)
+        const size_t need = (size_t)p.numTiles * 2;
+        if (ds.cnt_next + need > (size_t)CNT_RING_INTS) ds.cnt_next = 0;
+        p.cnt = ds.cnt + ds.cnt_next;
+        ds.cnt_next += need;
+        p.spinLimit = g_spin_limit;
+      }
     }
     if (a.mode == MODE_S) {
       p.ldG = a.ldHi;
@@ -544,7 +604,7 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
       if (map_w3(&mapB, a.w, a.R, a.Cc, 64)) return 1;
     } else {
       if (map_lo4(&mapA, a.lo, a.ldLo, a.Clo, a.B, a.Hlo, a.Wlo, p.Wt, p.Ht, p.Nb)) return 1;
-      if (map_w3(&mapB, a.w, a.R, a.Cc, p.pair ? BN / 2 : BN)) return 1;
+      if (map_w3(&mapB, a.w, a.R, a.Cc, c.pair ? BN / 2 : BN)) return 1;
     }
   } else {
     // wgrad: dw[tap][Chi][Clo]; the M side must be a multiple of 128
@@ -557,15 +617,15 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     }
     const int chunks = pixTiles;
     const size_t slab = (size_t)16 * a.Chi * a.Clo * sizeof(float);
-    Choice c = choose(MODE_W, Mch / 128, 1, Nch, chunks, (long long)(slab / sizeof(float)), false, a.forceBN,
-                      a.forceSplits, 1, 1, slab, a.ws ? a.wsBytes : 0);
+    Choice c = choose(ds, MODE_W, Mch / 128, 1, Nch, chunks, (long long)(slab / sizeof(float)), false, a.forceBN,
+                      a.forceSplits, slab, a.ws ? a.wsBytes : 0);
     if (c.BN == 0) {
       set_error("wgrad: no tile shape for N=%d", Nch);
       return 1;
     }
     const long long itemsPlainW = (long long)16 * (Mch / 128) * (Nch / c.BN) * c.splits;
-    if ((g_pair == 1 || (g_pair == 0 && itemsPlainW > g_num_sms)) && c.BN >= 128 && (Mch / 128) % 2 == 0 &&
-        g_max_clusters[MODE_W][bn_index(c.BN)][2] > 0)
+    if ((g_pair == 1 || (g_pair == 0 && itemsPlainW > maxCtas)) && c.BN >= 128 && (Mch / 128) % 2 == 0 &&
+        ds.max_pairs[MODE_W][bn_index(c.BN)] > 0)
       c.pair = 1;
     BN = c.BN;
     p.mTiles = Mch / 128;
@@ -574,8 +634,6 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     p.kIters = chunks / c.splits;
     p.numItems = 16 * p.mTiles * p.nTiles * c.splits;
     p.cm = c.pair ? 2 : 1;
-    p.cn = 1;
-    p.pair = c.pair;
     p.N = Nch;
     p.ldG = a.ldHi;
     p.epi = EPI_WGRAD;
@@ -595,7 +653,8 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     }
   }
 
-  p.stages = stages_for(BN, p.pair != 0);
+  const int kps = kps_for(BN);
+  p.rounds = (p.kIters + kps - 1) / kps;
   p.stampPos = g_stamp_pos;
   {
     auto lg2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
@@ -605,42 +664,41 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     }
     p.lgWt = lg2(p.Wt); p.lgHt = lg2(p.Ht); p.lgTilesX = lg2(p.tilesX); p.lgTilesY = lg2(p.tilesY);
     p.fdMTilesC = make_fastdiv((uint32_t)(p.mTiles / p.cm));
-    p.fdNTilesC = make_fastdiv((uint32_t)(p.nTiles / p.cn));
+    p.fdNTiles = make_fastdiv((uint32_t)p.nTiles);
     p.fdSplits = make_fastdiv((uint32_t)p.splits);
     p.fdKcPer = make_fastdiv((uint32_t)(p.kcPer > 0 ? p.kcPer : 1));
-    p.fdStages = make_fastdiv((uint32_t)p.stages);
-    p.fdCn = make_fastdiv((uint32_t)p.cn);
-    p.fdCm = make_fastdiv((uint32_t)p.cm);
   }
-  const size_t smem = smem_for(BN, p.pair != 0);
-  const int csize = p.cm * p.cn;
-  p.numClusterItems = p.numItems / csize;
-  int maxCtas = g_num_sms;  // one CTA per SM (198 KB of shared memory, 61 K registers)
-  {
-    const int cap = a.mode == MODE_W ? g_cap_w : (a.epi == EPI_DGRAD ? g_cap_sp : 0);
-    if (cap > 0 && cap < maxCtas) maxCtas = cap;
+  const size_t smem = smem_for(BN, p.cm == 2);
+  p.numClusterItems = p.numItems / p.cm;
+  int ctas = maxCtas;  // one CTA per SM (194 KB of shared memory, 61 K registers)
+  if (p.cm == 2) {
+    const int mp = ds.max_pairs[a.mode][bn_index(BN)] * 2;
+    if (mp < ctas) ctas = mp;
   }
-  if (csize > 1) maxCtas = g_max_clusters[a.mode][bn_index(BN)][csize] * csize;
-  int grid = p.numItems < maxCtas ? p.numItems : maxCtas;
-  grid -= grid % csize;
+  int grid = p.numItems < ctas ? p.numItems : ctas;
+  grid -= grid % p.cm;
+  g_last_plan[0] = BN; g_last_plan[1] = p.splits; g_last_plan[2] = p.cm == 2; g_last_plan[3] = p.fused;
+  g_last_plan[4] = grid; g_last_plan[5] = stages_for(BN, p.cm == 2); g_last_plan[6] = p.rounds; g_last_plan[7] = p.bEarly;
   if (g_verbose)
     fprintf(stderr,
-            "gct2 conv mode %d B %d lo %dx%d tile %dx%dx%d BN %d splits %d cluster %dx%d kIters %d items %d grid %d stages %d "
-            "smem %zu\n",
-            a.mode, a.B, a.Hlo, a.Wlo, p.Nb, p.Ht, p.Wt, BN, p.splits, p.cm, p.cn, p.kIters, p.numItems, grid, p.stages,
-            smem);
+            "gct2 conv mode %d B %d lo %dx%d tile %dx%dx%d BN %d splits %d pair %d kIters %d rounds %d items %d grid %d "
+            "stages %d fused %d early %d\n",
+            a.mode, a.B, a.Hlo, a.Wlo, p.Nb, p.Ht, p.Wt, BN, p.splits, p.cm == 2, p.kIters, p.rounds, p.numItems, grid,
+            stages_for(BN, p.cm == 2), p.fused, p.bEarly);
+#ifdef GCT2_TIMELINE
   if (g_dbg != nullptr && grid <= DBG_MAX_CTAS) {
     cudaMemsetAsync(g_dbg, 0, (size_t)grid * 8 * sizeof(unsigned long long), stream);
     p.dbg = g_dbg;
     g_dbg_ctas = grid;
   }
+#endif
   cudaError_t e;
   if (a.mode == MODE_S)
-    e = launch_bn<MODE_S>(BN, grid, csize, smem, stream, mapA, mapB, p);
+    e = launch_bn<MODE_S>(BN, grid, smem, stream, mapA, mapB, p);
   else if (a.mode == MODE_P)
-    e = launch_bn<MODE_P>(BN, grid, csize, smem, stream, mapA, mapB, p);
+    e = launch_bn<MODE_P>(BN, grid, smem, stream, mapA, mapB, p);
   else
-    e = launch_bn<MODE_W>(BN, grid, csize, smem, stream, mapA, mapB, p);
+    e = launch_bn<MODE_W>(BN, grid, smem, stream, mapA, mapB, p);
   if (e != cudaSuccess) {
     set_error("conv_umma_kernel launch: %s", cudaGetErrorString(e));
     return 1;
@@ -650,7 +708,7 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     const long long pixels = (long long)a.B * p.Hout * p.Wout;
     const long long total = pixels * (p.N / 4);
     int blocks = (int)((total + 255) / 256);
-    if (blocks > g_num_sms * 8) blocks = g_num_sms * 8;
+    if (blocks > ds.num_sms * 8) blocks = ds.num_sms * 8;
     e = launch_k(splitk_finish_kernel, dim3(blocks), dim3(256), 0, stream, a.ws, p.wsSplitStride, p.splits, p.N, pixels,
                  a.epi, a.out, a.ldo, a.bias, a.act, a.ldact, a.maskN, a.addOld);
     if (e != cudaSuccess) {
@@ -662,7 +720,7 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
   if (a.mode == MODE_W && p.splits > 1) {
     const long long nvec = (long long)4 * a.Chi * a.Clo;  // 16 taps * Chi * Clo / 4
     int blocks = (int)((nvec + 255) / 256);
-    if (blocks > g_num_sms * 8) blocks = g_num_sms * 8;
+    if (blocks > ds.num_sms * 8) blocks = ds.num_sms * 8;
     e = launch_k(wgrad_reduce_kernel, dim3(blocks), dim3(256), 0, stream, reinterpret_cast<const float4*>(a.ws),
                  p.wsSplitStride / 4, p.splits, reinterpret_cast<float4*>(a.dw), nvec);
     if (e != cudaSuccess) {

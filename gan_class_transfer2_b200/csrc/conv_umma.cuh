@@ -13,11 +13,24 @@
 //   MODE_W  weight gradient  dW[tap][g][p] = sum_pix G_hi[pix @ tap, g] * P_lo[pix, p]
 //           both operands MN-major (pixels are the contraction dim and are the slow smem axis).
 //
-// Warp roles: warps 0, 2, 3 = TMA producers (k-iterations round-robin; warp 2 also allocates TMEM), warp 1 = MMA
+// Warp roles: warps 0, 2, 3 = TMA producers (ring rounds round-robin; warp 2 also allocates TMEM), warp 1 = MMA
 // issuer, warps 4.. = epilogue (8 warps for BN = 64, 16 otherwise; TMEM -> registers -> global).  Accumulators are
 // double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// Ring: a slot holds KPS k-chunks of 64 (KPS = 2 for BN <= 128, 1 for BN = 256), i.e. one full/empty barrier round trip
+// feeds 8 (or 4) K = 16 MMAs.  The MMA-issuing thread's own instruction stream bounds the main loop (round 1: ~410
+// cycles per 4-MMA round against a 128-cycle tensor floor at BN = 64), so narrow tiles pay the barrier round once per
+// 128 of K instead of once per 64.
+//
 // PAIR = 1 instances run as clusters of two CTAs on tcgen05 cta_group::2: each CTA keeps its own 128-row tile, stages
 // half of the B tile, and rank 0 issues one 256-row MMA per K = 16 slice for both (see ptx.cuh, "CTA pairs").
+//
+// Weights before the dependency: the S/P launches fetch the B (weight) boxes of their first ring pass BEFORE
+// griddepcontrol.wait when the caller vouches that the kernel tensor is not being written by anything still running
+// (ConvParams::bEarly, GCT2_WEIGHTS_STABLE in the C ABI); the A boxes (activations of the previous launch) follow after it.
+//
+// Per-CTA phase stamps (tools/timeline.py) are compiled in only with -DGCT2_TIMELINE: the production main loops carry
+// no test-hook instructions.
 #pragma once
 #include <cuda_bf16.h>
 #include <type_traits>
@@ -39,7 +52,7 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 
 // n / d for 0 <= n < 2^31 with a multiply-high and a shift (host-side magic numbers): an integer division by a run-time
 // value costs a single thread 150-300 cycles, and the producer's start-up alone had ten of them on the critical path
-// of every launch (1.2 us of the 2.4 us between griddepcontrol.wait and the first MMA, tools/timeline.py + key 16).
+// of every launch (1.2 us of the 2.4 us between griddepcontrol.wait and the first MMA, tools/timeline.py).
 struct FastDiv {
   uint32_t d, mul, shr;
 };
@@ -66,27 +79,27 @@ struct ConvParams {
   int mTiles;                  // S/P: pixel tiles; W: (M-side channels)/128
   int nTiles;                  // N / BN
   int splits;                  // split-K factor
-  int kIters;                  // k-iterations per work item
+  int kIters;                  // 64-wide k-chunks per work item
+  int rounds;                  // ring rounds per work item = ceil(kIters / KPS)
   int kcPer;                   // S/P: 64-channel chunks per tap
   int numItems;                // total work items
-  int stages;                  // smem pipeline depth
   int ldG;                     // S / W(G operand): pixel stride (elements) of the gathered hi-res tensor
   int gIsA;                    // W: 1 when the gathered operand supplies the M side
   int mnLbo, mnSbo;            // MN-major descriptor offsets (bytes)
-  int cm, cn;                  // thread-block cluster = cm x cn CTAs: cm consecutive M tiles x cn consecutive N tiles of
-                               // one (phase, split); A tiles are TMA-multicast along cn, B tiles along cm
-  int numClusterItems;         // numItems / (cm*cn)
+  int cm;                      // CTAs per cluster: 1, or 2 for a cta_group::2 pair (two consecutive M tiles of one
+                               // (phase, N tile, split) share their B tile)
+  int numClusterItems;         // numItems / cm
   int fused;                   // split-K finished inside this launch (tile-major slabs + arrive/depart counters)
   int realEpi;                 // fused: the epilogue to apply after the slabs are summed (EPI_BIAS_RELU / EPI_DGRAD)
   int numTiles;                // fused: phases * nTiles * mTiles
-  int* cnt;                    // fused: [numTiles][2] arrive / depart counters, zero between launches
+  int* cnt;                    // fused: [numTiles][2] arrive / depart counters of THIS launch, zero between launches
+  unsigned spinLimit;          // fused: rendezvous watchdog (polls of ~40 ns; 0 = wait for ever)
+  int bEarly;                  // S/P: fetch the first ring pass of weight boxes before griddepcontrol.wait
   // fast division by the launch constants used in index decoding (all set by conv_launch)
-  FastDiv fdMTilesC, fdNTilesC, fdSplits, fdKcPer, fdStages, fdCn, fdCm;
+  FastDiv fdMTilesC, fdNTiles, fdSplits, fdKcPer;
   int lgWt, lgHt, lgTilesX, lgTilesY;  // pixel-tile geometry is power-of-two by construction
-  int pair;                    // CTA pairs (cta_group::2): needs cm == 2, cn == 1, BN >= 128; each CTA keeps its own M tile,
-                               // loads half of the B tile, and rank 0 issues one 256-row MMA for both
-  int stampPos;                // test hook (debug key 16): which point of the producer's start-up stamp 7 records
-  unsigned long long* dbg;     // test hook: per-CTA phase timestamps (8 x u64 per CTA, %globaltimer ns) or nullptr
+  int stampPos;                // -DGCT2_TIMELINE only: which point of the producer's start-up stamp 7 records
+  unsigned long long* dbg;     // -DGCT2_TIMELINE only: per-CTA phase timestamps (8 x u64 per CTA, %globaltimer ns)
   // epilogue
   int epi;
   int N;                       // total output columns (S/P) ; W: N-side channels
@@ -110,22 +123,22 @@ struct WorkItem {
   int mt, nt, ph, split;       // ph: phase (P) or tap (W)
 };
 
-// item = index of a cluster item (a cm x cn block of tiles); (rm, rn) = this CTA's position inside its cluster.
+// item = index of a cluster item (cm consecutive M tiles); rm = this CTA's rank inside its cluster.
 template <int MODE>
-__device__ __forceinline__ WorkItem decode_item(const ConvParams& p, int item, int rm, int rn) {
+__device__ __forceinline__ WorkItem decode_item(const ConvParams& p, int item, int rm) {
   WorkItem w;
   w.mt = fd_mod(p.fdMTilesC, item) * p.cm + rm;
   int r = fd_div(p.fdMTilesC, item);
   if (MODE == MODE_W) {
-    w.nt = fd_mod(p.fdNTilesC, r) * p.cn + rn;
-    r = fd_div(p.fdNTilesC, r);
+    w.nt = fd_mod(p.fdNTiles, r);
+    r = fd_div(p.fdNTiles, r);
     w.split = fd_mod(p.fdSplits, r);
     w.ph = fd_div(p.fdSplits, r);
   } else {
     w.split = fd_mod(p.fdSplits, r);
     r = fd_div(p.fdSplits, r);
-    w.nt = fd_mod(p.fdNTilesC, r) * p.cn + rn;
-    w.ph = fd_div(p.fdNTilesC, r);
+    w.nt = fd_mod(p.fdNTiles, r);
+    w.ph = fd_div(p.fdNTiles, r);
   }
   return w;
 }
@@ -135,14 +148,14 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+#ifdef GCT2_TIMELINE
 #define GCT2_STAMP(slot)                                                              \
   do {                                                                                \
     if (p.dbg != nullptr) p.dbg[(size_t)blockIdx.x * 8 + (slot)] = globaltimer_ns();  \
   } while (0)
-
-__device__ __forceinline__ void red_add_f32(float* addr, float v) {
-  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
-}
+#else
+#define GCT2_STAMP(slot) do { } while (0)
+#endif
 
 // Epilogue warps per tile width: 8 (two 32-column slices) for BN = 64, 16 (four slices) for BN = 128 / 256.
 template <int BN>
@@ -152,6 +165,108 @@ __host__ __device__ constexpr int kEpilogueWarps() {
 template <int BN>
 __host__ __device__ constexpr int kConvThreads() {
   return 128 + 32 * kEpilogueWarps<BN>();
+}
+// Ring geometry (shared by the kernel and the host-side shared-memory size).
+template <int BN>
+__host__ __device__ constexpr int kChunksPerStage() {
+  return BN == 256 ? 1 : 2;
+}
+template <int BN, int PAIR>
+__host__ __device__ constexpr int kSubBytes() {  // one k-chunk: 128 x 64 bf16 of A + (half of) BN x 64 bf16 of B
+  return 128 * 128 + (PAIR ? BN * 64 : BN * 128);
+}
+template <int BN, int PAIR>
+__host__ __device__ constexpr int kStageBytes() {
+  return kChunksPerStage<BN>() * kSubBytes<BN, PAIR>();
+}
+template <int BN, int PAIR>
+__host__ __device__ constexpr int kStages() {  // every shape fills the same 192 KB of pipeline
+  return (192 * 1024) / kStageBytes<BN, PAIR>();
+}
+
+// One k-chunk (64 of K) of one work item on its way: the A box(es) and/or the B box(es) of ring position (sa, sb).
+template <int MODE, int BN, int PAIR>
+__device__ __forceinline__ void issue_chunk(const ConvParams& p, const CUtensorMap* mapA, const CUtensorMap* mapB,
+                                            uint64_t* bar, uint8_t* sa, uint8_t* sb, const WorkItem& w, int x0, int y0,
+                                            int b0, int kit, int rm, bool doA, bool doB) {
+  constexpr int BLK = 64 * 128;  // one 64x64 bf16 block = one TMA box of an MN-major operand
+  constexpr bool pair = PAIR != 0;
+  if (MODE == MODE_S) {
+    const int tap = fd_div(p.fdKcPer, kit), kc = kit - tap * p.kcPer;
+    const int ky = tap >> 2, kx = tap & 3;
+    const int py = (ky + 1) & 1, px = (kx + 1) & 1;
+    const int hy = ((ky + 1) >> 1) - 1, hx = ((kx + 1) >> 1) - 1;
+    if (doA) {
+      if (pair)
+        tma_load_5d_pair(sa, mapA, bar, px * p.ldG + kc * 64, x0 + hx, py, y0 + hy, b0);
+      else
+        tma_load_5d(sa, mapA, bar, px * p.ldG + kc * 64, x0 + hx, py, y0 + hy, b0);
+    }
+    if (doB) {
+      if (pair) {
+#pragma unroll
+        for (int j = 0; j < BN / 128; ++j)  // my half of the tile's columns
+          tma_load_3d_pair(sb + j * BLK, mapB, bar, w.nt * BN + rm * (BN / 2) + j * 64, kc * 64, tap);
+      } else {
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j) tma_load_3d(sb + j * BLK, mapB, bar, w.nt * BN + j * 64, kc * 64, tap);
+      }
+    }
+  } else if (MODE == MODE_P) {
+    const int t4 = fd_div(p.fdKcPer, kit), kc = kit - t4 * p.kcPer;
+    const int ty = t4 >> 1, tx = t4 & 1;
+    const int py = w.ph >> 1, px = w.ph & 1;
+    const int ky = (1 - py) + 2 * ty, kx = (1 - px) + 2 * tx;
+    if (doA) {
+      if (pair)
+        tma_load_4d_pair(sa, mapA, bar, kc * 64, x0 + (px - tx), y0 + (py - ty), b0);
+      else
+        tma_load_4d(sa, mapA, bar, kc * 64, x0 + (px - tx), y0 + (py - ty), b0);
+    }
+    if (doB) {
+      if (pair)  // my half of the tile's rows (the host built this map with BN/2-row boxes)
+        tma_load_3d_pair(sb, mapB, bar, kc * 64, w.nt * BN + rm * (BN / 2), ky * 4 + kx);
+      else
+        tma_load_3d(sb, mapB, bar, kc * 64, w.nt * BN, ky * 4 + kx);
+    }
+  } else {
+    // pixel chunk -> (batch tile, y tile, x tile); both operands are activations: always loaded together
+    const int cx = (kit & (p.tilesX - 1)) << p.lgWt;
+    const int cy = ((kit >> p.lgTilesX) & (p.tilesY - 1)) << p.lgHt;
+    const int cb = (kit >> (p.lgTilesX + p.lgTilesY)) * p.Nb;
+    const int ky = w.ph >> 2, kx = w.ph & 3;
+    const int py = (ky + 1) & 1, px = (kx + 1) & 1;
+    const int hy = ((ky + 1) >> 1) - 1, hx = ((kx + 1) >> 1) - 1;
+    if (pair) {
+      // my own 128 M-side channels, my half of the N-side channels; both land on the leader's barrier
+      const int nb0 = w.nt * BN + rm * (BN / 2);
+      if (p.gIsA) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          tma_load_5d_pair(sa + j * BLK, mapA, bar, px * p.ldG + w.mt * 128 + j * 64, cx + hx, py, cy + hy, cb);
+#pragma unroll
+        for (int j = 0; j < BN / 128; ++j) tma_load_4d_pair(sb + j * BLK, mapB, bar, nb0 + j * 64, cx, cy, cb);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) tma_load_4d_pair(sa + j * BLK, mapA, bar, w.mt * 128 + j * 64, cx, cy, cb);
+#pragma unroll
+        for (int j = 0; j < BN / 128; ++j)
+          tma_load_5d_pair(sb + j * BLK, mapB, bar, px * p.ldG + nb0 + j * 64, cx + hx, py, cy + hy, cb);
+      }
+    } else if (p.gIsA) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        tma_load_5d(sa + j * BLK, mapA, bar, px * p.ldG + w.mt * 128 + j * 64, cx + hx, py, cy + hy, cb);
+#pragma unroll
+      for (int j = 0; j < BN / 64; ++j) tma_load_4d(sb + j * BLK, mapB, bar, w.nt * BN + j * 64, cx, cy, cb);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) tma_load_4d(sa + j * BLK, mapA, bar, w.mt * 128 + j * 64, cx, cy, cb);
+#pragma unroll
+      for (int j = 0; j < BN / 64; ++j)
+        tma_load_5d(sb + j * BLK, mapB, bar, px * p.ldG + w.nt * BN + j * 64, cx + hx, py, cy + hy, cb);
+    }
+  }
 }
 
 #ifndef GCT2_CONV_EXTRA_BOUND
@@ -164,16 +279,16 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
                                                         const __grid_constant__ CUtensorMap mapB,
                                                         const ConvParams p) {
   constexpr int A_BYTES = 128 * 128;  // 128 rows x 64 bf16 (S/P) or 2 blocks of 64 pixels x 64 channels (W)
-  constexpr int B_BYTES = BN * 128;
-  constexpr int BLK = 64 * 128;       // one 64x64 bf16 block = one TMA box of an MN-major operand
   constexpr bool pair = PAIR != 0;
-  // a CTA of a pair stages only its half of the B tile
-  constexpr int STAGE_BYTES = A_BYTES + (pair ? B_BYTES / 2 : B_BYTES);
+  constexpr int KPS = kChunksPerStage<BN>();
+  constexpr int SUB_BYTES = kSubBytes<BN, PAIR>();
+  constexpr int STAGE_BYTES = kStageBytes<BN, PAIR>();
+  constexpr int S = kStages<BN, PAIR>();
   constexpr uint32_t TMEM_COLS = 2 * BN;
+  static_assert(S >= 3, "three producers need at least three ring slots");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int S = p.stages;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * STAGE_BYTES);
   uint64_t* empty = full + S;
   uint64_t* tfull = empty + S;
@@ -183,17 +298,13 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   TraceScope trace(100 + MODE * 10 + BN / 64);
+#ifdef GCT2_TIMELINE
   const unsigned long long t_entry = (p.dbg != nullptr && threadIdx.x == 0) ? globaltimer_ns() : 0ull;
+#endif
 
-  // cluster geometry (cm*cn == 1: plain launch, every mask below is unused)
-  const int csize = p.cm * p.cn;
-  const int crank = csize > 1 ? (int)cluster_ctarank() : 0;
-  const int rm = fd_div(p.fdCn, crank), rn = fd_mod(p.fdCn, crank);
-  const int clusterId = blockIdx.x / csize, numClusters = gridDim.x / csize;
-  const uint16_t rowMask = (uint16_t)(((1u << p.cn) - 1u) << (rm * p.cn));   // CTAs sharing my M tile (A multicast)
-  uint16_t colMask = 0;                                                        // CTAs sharing my N tile (B multicast)
-  for (int j = 0; j < p.cm; ++j) colMask |= (uint16_t)(1u << (j * p.cn + rn));
-  const uint16_t peerMask = rowMask | colMask;
+  const int rm = pair ? (int)cluster_ctarank() : 0;
+  const int clusterId = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int numClusters = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
@@ -202,9 +313,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S; ++i) {
       mbar_init(&full[i], 1);
-      // a slot is free once every CTA that multicasts into it ... i.e. every consumer of my row and column is done;
-      // in a pair the leader's single commit is multicast to both CTAs
-      mbar_init(&empty[i], pair ? 1 : p.cm + p.cn - 1);
+      mbar_init(&empty[i], 1);  // pair: the leader's single commit is multicast to both CTAs
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
@@ -224,160 +333,97 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
   }
   tc_fence_before();
   __syncthreads();
-  if (csize > 1) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts into them
+  if (pair) cluster_sync_all();  // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  // producer identity (warps 0, 2, 3 -> producers 0, 1, 2); elect.sync (not `lane == 0`) picks the thread: ptxas then
+  // knows exactly one thread runs the loop and feeds the uniform-datapath instructions (UTMALDG / UTCHMMA / UTCBAR)
+  // directly instead of wrapping each one in a vote-and-branch loop over "possibly several" active threads.
+  constexpr uint32_t NP = 3;
+  const bool producerWarp = warp == 0 || warp == 2 || warp == 3;
+  const uint32_t pj = warp == 0 ? 0u : (uint32_t)warp - 1u;
+  const bool producer = producerWarp && elect_one();
+  // the full-barrier arrival of one ring round: pair -> one arrival on the LEADER's barrier announces the bytes of both
+  // CTAs (the loads of both complete there)
+  auto expect_round = [&](uint32_t stage, int nch) {
+    if (!pair)
+      mbar_arrive_expect_tx(&full[stage], (uint32_t)(nch * SUB_BYTES));
+    else if (rm == 0)
+      mbar_arrive_expect_tx(&full[stage], (uint32_t)(2 * nch * SUB_BYTES));
+  };
+  const int lastCh = p.kIters - (p.rounds - 1) * KPS;  // chunks of an item's last round (1 or KPS)
+
+  // ---- weights of the first ring pass, before the dependency resolves (they are not produced by the previous launch)
+  const bool early = MODE != MODE_W && p.bEarly != 0;
+  if (early && producer && clusterId < p.numClusterItems) {
+    const WorkItem w = decode_item<MODE>(p, clusterId, rm);
+    const int firstPass = p.rounds < S ? p.rounds : S;
+    for (int rd = (int)pj; rd < firstPass; rd += (int)NP) {
+      const int nch = rd == p.rounds - 1 ? lastCh : KPS;
+      expect_round((uint32_t)rd, nch);
+      uint8_t* st = smem + rd * STAGE_BYTES;
+#pragma unroll
+      for (int c = 0; c < KPS; ++c)
+        if (c < nch)
+          issue_chunk<MODE, BN, PAIR>(p, &mapA, &mapB, &full[rd], st + c * SUB_BYTES, st + c * SUB_BYTES + A_BYTES, w, 0,
+                                      0, 0, w.split * p.kIters + rd * KPS + c, rm, false, true);
+    }
+  }
+
   // Programmatic dependent launch: everything above ran while the previous kernel of the stream was still draining;
-  // from here on global memory is touched (the stamp below included), so wait for that kernel to complete -- and let
-  // the next kernel start its own prologue now.
+  // from here on activations in global memory are touched, so wait for that kernel to complete -- and let the next
+  // kernel start its own prologue now.
   pdl_launch_dependents();
   pdl_wait();
   trace.ready();
+#ifdef GCT2_TIMELINE
   if (threadIdx.x == 0 && p.dbg != nullptr) p.dbg[(size_t)blockIdx.x * 8 + 0] = t_entry;  // kernel entry
   if (threadIdx.x == 0) GCT2_STAMP(1);  // prologue done (and the previous kernel complete)
+#endif
 
-  const int tilesXY = p.tilesX * p.tilesY;
-
-  if (warp == 0 || warp == 2 || warp == 3) {
+  if (producerWarp) {
     // ------------------------------------------------------------------ TMA producers (three warps)
     // One thread needs ~600-900 cycles to get one stage on its way (empty-wait, expect_tx and 2-5 TMA instructions
     // issue back to back at ~150 cycles each: tools/probes/tma_ingest_probe.cu), more than the tensor pipe needs to
-    // consume it (128-512 cycles), and a deeper ring does not help because the limit is issue, not latency.  Three
-    // producer threads in three warps take the k-iterations round-robin (producer j owns global iteration g = j mod
-    // 3): measured 2.6x the single-producer rate in isolation.
-    // elect.sync (not `lane == 0`) picks the thread: ptxas then knows exactly one thread runs the loop and feeds the
-    // uniform-datapath instructions (UTMALDG / UTCHMMA / UTCBAR) directly instead of wrapping each one in a
-    // vote-and-branch loop over "possibly several" active threads.
-    // No more producers than ring slots: producer j may only wait for slot s's r-th release once the (r-1)-th has
-    // happened, or the parity wait aliases and it overwrites a live slot.  Its previous stage (g - NP) could be issued
-    // only after the consumer released g - NP - S, and the consumer releases in order, so g - 2S is released whenever
-    // S >= NP.  (The default rings have 4-8 slots; the guard matters for the depth cap of debug key 17.)
-    const uint32_t NP = S < 3 ? (uint32_t)S : 3u;
-    const uint32_t pj = warp == 0 ? 0u : (uint32_t)warp - 1u;
-    auto modNP = [NP](uint32_t x) { return NP == 3u ? x % 3u : (NP == 2u ? (x & 1u) : 0u); };
-    if (pj < NP && elect_one()) {
-      if (warp == 0 && p.stampPos == 0) GCT2_STAMP(7);  // test hook: where the time before the first load goes
+    // consume it, and a deeper ring does not help because the limit is issue, not latency.  Three producer threads in
+    // three warps take the ring rounds round-robin (producer j owns global round g = j mod 3): measured 2.6x the
+    // single-producer rate in isolation.  S >= 3 keeps a producer's parity wait from aliasing (its previous round
+    // g - 3 could be issued only after the consumer released g - 3 - S, and releases happen in order).
+    if (producer) {
+#ifdef GCT2_TIMELINE
+      if (warp == 0 && p.stampPos == 0) GCT2_STAMP(7);
+#endif
       uint32_t gbase = 0;
-      for (int item = clusterId; item < p.numClusterItems; item += numClusters, gbase += (uint32_t)p.kIters) {
-        const WorkItem w = decode_item<MODE>(p, item, rm, rn);
+      for (int item = clusterId; item < p.numClusterItems; item += numClusters, gbase += (uint32_t)p.rounds) {
+        const WorkItem w = decode_item<MODE>(p, item, rm);
         int x0 = 0, y0 = 0, b0 = 0;
         if (MODE != MODE_W) {
           x0 = (w.mt & (p.tilesX - 1)) << p.lgWt;
           y0 = ((w.mt >> p.lgTilesX) & (p.tilesY - 1)) << p.lgHt;
           b0 = (w.mt >> (p.lgTilesX + p.lgTilesY)) * p.Nb;
         }
-        if (warp == 0 && item == clusterId && p.stampPos == 1) GCT2_STAMP(7);
-        for (int it = (int)modNP(pj + NP - modNP(gbase)); it < p.kIters; it += (int)NP) {
-          const int kit = w.split * p.kIters + it;
-          const uint32_t g = gbase + (uint32_t)it;
-          const uint32_t ring = (uint32_t)fd_div(p.fdStages, (int)g), stage = g - ring * (uint32_t)S, phase = ring & 1u;
-          if (g == 0 && p.stampPos == 2) GCT2_STAMP(7);
-          mbar_wait(&empty[stage], phase ^ 1);
-          if (g == 0 && p.stampPos == 3) GCT2_STAMP(7);
-          // pair: one arrival on the LEADER's barrier announces the bytes of both CTAs; the loads of both complete there
-          if (!pair)
-            mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
-          else if (rm == 0)
-            mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
-          uint8_t* sa = smem + stage * STAGE_BYTES;
-          uint8_t* sb = sa + A_BYTES;
-          // In a cluster the CTAs of a row take turns fetching the shared A tile (and those of a column the shared
-          // B tile) and multicast it; every CTA still expects the full stage on its own barrier.
-          const bool doA = p.cn == 1 || fd_mod(p.fdCn, it) == rn;
-          const bool doB = p.cm == 1 || fd_mod(p.fdCm, it) == rm;
-          if (MODE == MODE_S) {
-            const int tap = fd_div(p.fdKcPer, kit), kc = kit - tap * p.kcPer;
-            const int ky = tap >> 2, kx = tap & 3;
-            const int py = (ky + 1) & 1, px = (kx + 1) & 1;
-            const int hy = ((ky + 1) >> 1) - 1, hx = ((kx + 1) >> 1) - 1;
-            if (pair) {
-              tma_load_5d_pair(sa, &mapA, &full[stage], px * p.ldG + kc * 64, x0 + hx, py, y0 + hy, b0);
-#pragma unroll
-              for (int j = 0; j < BN / 128; ++j)  // my half of the tile's columns
-                tma_load_3d_pair(sb + j * BLK, &mapB, &full[stage], w.nt * BN + rm * (BN / 2) + j * 64, kc * 64, tap);
-            } else if (doA) {
-              if (p.cn == 1)
-                tma_load_5d(sa, &mapA, &full[stage], px * p.ldG + kc * 64, x0 + hx, py, y0 + hy, b0);
-              else
-                tma_load_5d_mc(sa, &mapA, &full[stage], px * p.ldG + kc * 64, x0 + hx, py, y0 + hy, b0, rowMask);
-            }
-            if (doB && !pair) {
-#pragma unroll
-              for (int j = 0; j < BN / 64; ++j) {
-                if (p.cm == 1)
-                  tma_load_3d(sb + j * BLK, &mapB, &full[stage], w.nt * BN + j * 64, kc * 64, tap);
-                else
-                  tma_load_3d_mc(sb + j * BLK, &mapB, &full[stage], w.nt * BN + j * 64, kc * 64, tap, colMask);
-              }
-            }
-          } else if (MODE == MODE_P) {
-            const int t4 = fd_div(p.fdKcPer, kit), kc = kit - t4 * p.kcPer;
-            const int ty = t4 >> 1, tx = t4 & 1;
-            const int py = w.ph >> 1, px = w.ph & 1;
-            const int ky = (1 - py) + 2 * ty, kx = (1 - px) + 2 * tx;
-            if (pair) {
-              tma_load_4d_pair(sa, &mapA, &full[stage], kc * 64, x0 + (px - tx), y0 + (py - ty), b0);
-              // my half of the tile's rows (the host built this map with BN/2-row boxes)
-              tma_load_3d_pair(sb, &mapB, &full[stage], kc * 64, w.nt * BN + rm * (BN / 2), ky * 4 + kx);
-            } else if (doA) {
-              if (p.cn == 1)
-                tma_load_4d(sa, &mapA, &full[stage], kc * 64, x0 + (px - tx), y0 + (py - ty), b0);
-              else
-                tma_load_4d_mc(sa, &mapA, &full[stage], kc * 64, x0 + (px - tx), y0 + (py - ty), b0, rowMask);
-            }
-            if (doB && !pair) {
-              if (p.cm == 1)
-                tma_load_3d(sb, &mapB, &full[stage], kc * 64, w.nt * BN, ky * 4 + kx);
-              else
-                tma_load_3d_mc(sb, &mapB, &full[stage], kc * 64, w.nt * BN, ky * 4 + kx, colMask);
-            }
-          } else {
-            // pixel chunk -> (batch tile, y tile, x tile)
-            const int cx = (kit & (p.tilesX - 1)) << p.lgWt;
-            const int cy = ((kit >> p.lgTilesX) & (p.tilesY - 1)) << p.lgHt;
-            const int cb = (kit >> (p.lgTilesX + p.lgTilesY)) * p.Nb;
-            const int ky = w.ph >> 2, kx = w.ph & 3;
-            const int py = (ky + 1) & 1, px = (kx + 1) & 1;
-            const int hy = ((ky + 1) >> 1) - 1, hx = ((kx + 1) >> 1) - 1;
-            if (pair) {
-              // my own 128 M-side channels, my half of the N-side channels; both land on the leader's barrier
-              const int nb0 = w.nt * BN + rm * (BN / 2);
-              if (p.gIsA) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-                  tma_load_5d_pair(sa + j * BLK, &mapA, &full[stage], px * p.ldG + w.mt * 128 + j * 64, cx + hx, py,
-                                   cy + hy, cb);
-#pragma unroll
-                for (int j = 0; j < BN / 128; ++j)
-                  tma_load_4d_pair(sb + j * BLK, &mapB, &full[stage], nb0 + j * 64, cx, cy, cb);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-                  tma_load_4d_pair(sa + j * BLK, &mapA, &full[stage], w.mt * 128 + j * 64, cx, cy, cb);
-#pragma unroll
-                for (int j = 0; j < BN / 128; ++j)
-                  tma_load_5d_pair(sb + j * BLK, &mapB, &full[stage], px * p.ldG + nb0 + j * 64, cx + hx, py,
-                                   cy + hy, cb);
-              }
-            } else if (p.gIsA) {
-#pragma unroll
-              for (int j = 0; j < 2; ++j)
-                tma_load_5d(sa + j * BLK, &mapA, &full[stage], px * p.ldG + w.mt * 128 + j * 64, cx + hx, py,
-                            cy + hy, cb);
-#pragma unroll
-              for (int j = 0; j < BN / 64; ++j)
-                tma_load_4d(sb + j * BLK, &mapB, &full[stage], w.nt * BN + j * 64, cx, cy, cb);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 2; ++j)
-                tma_load_4d(sa + j * BLK, &mapA, &full[stage], w.mt * 128 + j * 64, cx, cy, cb);
-#pragma unroll
-              for (int j = 0; j < BN / 64; ++j)
-                tma_load_5d(sb + j * BLK, &mapB, &full[stage], px * p.ldG + w.nt * BN + j * 64, cx + hx, py,
-                            cy + hy, cb);
-            }
+        const uint32_t gm = gbase % NP;
+        for (int rd = (int)((pj + NP - gm) % NP); rd < p.rounds; rd += (int)NP) {
+          const uint32_t g = gbase + (uint32_t)rd;
+          const uint32_t ring = g / (uint32_t)S, stage = g - ring * (uint32_t)S, phase = ring & 1u;
+          const int nch = rd == p.rounds - 1 ? lastCh : KPS;
+          // the weights of the first item's first ring pass are already on their way (and its slots were never used)
+          const bool wEarly = early && item == clusterId && rd < S;
+          if (!wEarly) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            expect_round(stage, nch);
           }
+          uint8_t* st = smem + stage * STAGE_BYTES;
+#pragma unroll
+          for (int c = 0; c < KPS; ++c)
+            if (c < nch)
+              issue_chunk<MODE, BN, PAIR>(p, &mapA, &mapB, &full[stage], st + c * SUB_BYTES,
+                                          st + c * SUB_BYTES + A_BYTES, w, x0, y0, b0,
+                                          w.split * p.kIters + rd * KPS + c, rm, true, !wEarly);
+#ifdef GCT2_TIMELINE
           if (g == 0 && p.stampPos == 4) GCT2_STAMP(7);
+#endif
         }
       }
     }
@@ -386,62 +432,58 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
     if ((!pair || rm == 0) && elect_one()) {
       constexpr int A_MN = (MODE == MODE_W) ? 1 : 0;
       constexpr int B_MN = (MODE == MODE_P) ? 0 : 1;
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, A_MN, B_MN);
-      constexpr uint32_t idesc2 = make_idesc_bf16(256, BN, A_MN, B_MN);  // cta_group::2: 256 rows over the pair
+      constexpr uint32_t idesc = make_idesc_bf16(pair ? 256 : 128, BN, A_MN, B_MN);  // cta_group::2: 256 rows over the pair
       const uint32_t a_lbo = A_MN ? (uint32_t)p.mnLbo : 16u, a_sbo = A_MN ? (uint32_t)p.mnSbo : 1024u;
       const uint32_t b_lbo = B_MN ? (uint32_t)p.mnLbo : 16u, b_sbo = B_MN ? (uint32_t)p.mnSbo : 1024u;
       constexpr uint32_t a_kstep = A_MN ? 2048u : 32u;  // bytes per UMMA_K = 16 along K
       constexpr uint32_t b_kstep = B_MN ? 2048u : 32u;
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      // The issuing thread's own instruction stream is the main loop's bound (one warp, mostly dependent
-      // uniform-datapath instructions: 77 per k-step = ~470 cycles before this form), so everything that can be
-      // carried across iterations is: the stage's descriptor pair and barrier addresses advance by constants and wrap
-      // with the ring; the four K = 16 slices add immediates to the 14-bit address field.
+      // Everything that can be carried across iterations is: the stage's descriptor pair and barrier addresses
+      // advance by constants and wrap with the ring; the K = 16 slices add immediates to the 14-bit address field.
       const uint32_t smem_base = smem_u32(smem);
       const uint64_t da_first = make_smem_desc(smem_base, a_lbo, a_sbo);
       const uint64_t db_first = make_smem_desc(smem_base + A_BYTES, b_lbo, b_sbo);
-      const uint64_t dstep = (uint64_t)(STAGE_BYTES >> 4);
+      constexpr uint64_t dstep = (uint64_t)(STAGE_BYTES >> 4);
+      constexpr uint64_t dsub = (uint64_t)(SUB_BYTES >> 4);
       const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
       constexpr uint64_t ka = a_kstep >> 4, kb = b_kstep >> 4;
-      // one k-step on ring slot `slot`: wait for the operands, four MMAs, release the slot
-      auto kstep = [&](uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t full_a, uint32_t empty_a, uint32_t ph,
-                       uint32_t accumulate) {
-        mbar_wait_addr(full_a, ph);
-        // (no tcgen05.fence here: the operands were written by the async proxy (TMA) and are read by the async proxy
-        // (tcgen05.mma); the mbarrier's completion orders the two)
+      auto mma4 = [&](uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t accumulate) {
         if (pair) {
-          umma_bf16_pair(d_tmem, da, db, idesc2, accumulate);
-          umma_bf16_pair(d_tmem, da + ka, db + kb, idesc2, 1u);
-          umma_bf16_pair(d_tmem, da + 2 * ka, db + 2 * kb, idesc2, 1u);
-          umma_bf16_pair(d_tmem, da + 3 * ka, db + 3 * kb, idesc2, 1u);
-          umma_commit_pair_addr(empty_a, 0x3);  // the slot is free in both CTAs
+          umma_bf16_pair(d_tmem, da, db, idesc, accumulate);
+          umma_bf16_pair(d_tmem, da + ka, db + kb, idesc, 1u);
+          umma_bf16_pair(d_tmem, da + 2 * ka, db + 2 * kb, idesc, 1u);
+          umma_bf16_pair(d_tmem, da + 3 * ka, db + 3 * kb, idesc, 1u);
         } else {
           umma_bf16(d_tmem, da, db, idesc, accumulate);
           umma_bf16(d_tmem, da + ka, db + kb, idesc, 1u);
           umma_bf16(d_tmem, da + 2 * ka, db + 2 * kb, idesc, 1u);
           umma_bf16(d_tmem, da + 3 * ka, db + 3 * kb, idesc, 1u);
-          // frees the smem slot once these MMAs have read it -- in my CTA and, in a cluster, in every CTA that
-          // multicasts into my slot (my row and my column)
-          if (csize == 1)
-            umma_commit_addr(empty_a);
-          else
-            umma_commit_mc_addr(empty_a, peerMask);
         }
       };
-      // (Unrolling the ring over its slots -- descriptor pairs as immediates -- was measured too: the k-step drops from
-      // 224 to 185 ns at BN = 64, but the three unrolled copies per kernel cost more at start-up than they save.)
       uint64_t da = da_first, db = db_first;
       uint32_t full_a = full0, empty_a = empty0;
       for (int item = clusterId; item < p.numClusterItems; item += numClusters) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        if (item == clusterId && p.dbg != nullptr) {  // test hook: when did the first operands land?
+#ifdef GCT2_TIMELINE
+        if (item == clusterId && p.dbg != nullptr) {  // when did the first operands land?
           mbar_wait_addr(full_a, phase);
           GCT2_STAMP(2);
         }
-        for (int it = 0; it < p.kIters; ++it) {
-          kstep(d_tmem, da, db, full_a, empty_a, phase, it != 0 ? 1u : 0u);
+#endif
+        for (int rd = 0; rd < p.rounds; ++rd) {
+          // one ring round: wait for the operands, 4 * nch MMAs, release the slot.  (No tcgen05.fence here: the operands
+          // were written by the async proxy (TMA) and are read by the async proxy (tcgen05.mma); the mbarrier's
+          // completion orders the two.)
+          mbar_wait_addr(full_a, phase);
+          mma4(d_tmem, da, db, rd != 0 ? 1u : 0u);
+          if (KPS == 2 && (rd + 1 < p.rounds || lastCh == 2)) mma4(d_tmem, da + dsub, db + dsub, 1u);
+          // frees the smem slot once these MMAs have read it (pair: in both CTAs)
+          if (pair)
+            umma_commit_pair_addr(empty_a, 0x3);
+          else
+            umma_commit_addr(empty_a);
           da += dstep;
           db += dstep;
           full_a += 8;
@@ -459,7 +501,9 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
           umma_commit_pair(&tfull[acc], 0x3);  // both CTAs' accumulator halves complete -> both epilogues
         else
           umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+#ifdef GCT2_TIMELINE
         if (item == clusterId) GCT2_STAMP(3);  // all MMAs of the first item issued
+#endif
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -477,7 +521,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
       const int r = q * 32 + lane;
       uint32_t acc = 0, acc_phase = 0;
       for (int item = clusterId; item < p.numClusterItems; item += numClusters) {
-        const WorkItem w = decode_item<MODE>(p, item, rm, rn);
+        const WorkItem w = decode_item<MODE>(p, item, rm);
         const int n0 = w.nt * BN + cgrp * COLS;
         const int tileId = (w.ph * p.nTiles + w.nt) * p.mTiles + w.mt;
         // row -> output location
@@ -497,7 +541,9 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
           pix = ((long long)b * p.Hout + oy) * p.Wout + ox;
         }
         mbar_wait(&tfull[acc], acc_phase);
+#ifdef GCT2_TIMELINE
         if (item == clusterId && warp == 4 && lane == 0) GCT2_STAMP(4);  // first accumulator complete
+#endif
         tc_fence_after();
         const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN + cgrp * COLS;
 #pragma unroll 1
@@ -608,7 +654,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
             uint32_t spins = 0;
             while (ld_acquire_gpu(p.cnt + 2 * tileId) < p.splits) {
               __nanosleep(40);
-              if (++spins > (1u << 22)) {
+              if (p.spinLimit != 0u && ++spins > p.spinLimit) {
                 printf("gct2: split-K rendezvous watchdog block %d tile %d\n", (int)blockIdx.x, tileId);
                 __trap();
               }
@@ -666,7 +712,9 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
             }
           }
         }
+#ifdef GCT2_TIMELINE
         if (item == clusterId && warp == 4 && lane == 0) GCT2_STAMP(5);  // first epilogue (of warp 4) done
+#endif
         if (lane == 0) {
           if (pair && rm != 0)
             mbar_arrive_remote(&tempty[acc], 0);  // the leader's MMA thread waits for both CTAs' epilogues
@@ -681,8 +729,10 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
 
   tc_fence_before();
   __syncthreads();
-  if (csize > 1) cluster_sync_all();  // no CTA leaves while a peer may still signal its barriers
+  if (pair) cluster_sync_all();  // no CTA leaves while its peer may still signal its barriers
+#ifdef GCT2_TIMELINE
   if (threadIdx.x == 0) GCT2_STAMP(6);  // all work of this CTA done
+#endif
   trace.end();
   if (warp == 2) {
     tc_fence_after();

@@ -17,9 +17,12 @@ void trace_set_elementwise(unsigned long long* buf) { cudaMemcpyToSymbol(g_trace
 static int g_ew_sms = 148;
 static int g_c3w_blocks = 0;   // debug key 15: grid cap of down0's weight-gradient kernel (0 = 2 blocks per SM)
 static int g_adam_blocks = 0;  // debug key 13: grid cap of the Adam kernel (0 = 8 blocks per SM)
+static int g_adam_sms = 0;     // gct2_set_adam_sms / debug key 23: > 0 = run Keras-Adam on that many SMs, one 1024-thread
+                               // CTA each (SM-exclusive through its shared-memory request), leaving the rest to the convs
 void elementwise_set_debug(int key, int value) {
   if (key == 13) g_adam_blocks = value;
   if (key == 15) g_c3w_blocks = value;
+  if (key == 23) g_adam_sms = value > 0 ? value : 0;
 }
 void elementwise_set_sms(int n) { g_ew_sms = n; }
 
@@ -802,6 +805,64 @@ __global__ void __launch_bounds__(ADAM_THREADS, 640 / ADAM_THREADS) adam_kernel(
   trace.end();
 }
 
+// SM-partitioned variant: few CTAs, each alone on its SM (the dynamic shared-memory request keeps every other block --
+// ours or a conv CTA -- off that SM), 1024 threads x 2 float4 of each of the four arrays in flight per thread = 128 KB
+// of loads per SM.  HBM-bound work does not need all 148 SMs to draw most of the bandwidth, and the tensor-core convs of
+// the same step do not need HBM: running the two side by side on disjoint SM sets hides the optimiser (engine.py).
+// Same element order inside a vector and the same adam_elem arithmetic as adam_kernel: bit-identical results.
+constexpr int ADAM_WIDE_THREADS = 1024;
+constexpr int ADAM_WIDE_U = 2;
+constexpr int ADAM_WIDE_SMEM = 120 * 1024;
+__global__ void __launch_bounds__(ADAM_WIDE_THREADS, 1) adam_wide_kernel(float4* __restrict__ w, float4* __restrict__ m,
+                                                                         float4* __restrict__ v, const float4* __restrict__ g,
+                                                                         uint2* __restrict__ wb, long long nvec,
+                                                                         const float* __restrict__ hyper, float b1, float b2,
+                                                                         float eps, float gscale,
+                                                                         long long* __restrict__ iterations_inc) {
+  TraceScope trace(8);
+  pdl_launch_dependents();
+  pdl_wait();
+  trace.ready();
+  const float alpha = __ldg(hyper);
+  if (iterations_inc != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *iterations_inc += 1;
+  const float c1 = 1.f - b1, c2 = 1.f - b2;
+  const long long T = (long long)gridDim.x * blockDim.x;
+  long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  for (; i0 + (ADAM_WIDE_U - 1) * T < nvec; i0 += T * ADAM_WIDE_U) {
+    float4 gv[ADAM_WIDE_U], mv[ADAM_WIDE_U], vv[ADAM_WIDE_U], wv[ADAM_WIDE_U];
+#pragma unroll
+    for (int u = 0; u < ADAM_WIDE_U; ++u) {
+      gv[u] = __ldcs(g + i0 + u * T);
+      mv[u] = __ldcs(m + i0 + u * T);
+      vv[u] = __ldcs(v + i0 + u * T);
+      wv[u] = __ldcs(w + i0 + u * T);
+    }
+#pragma unroll
+    for (int u = 0; u < ADAM_WIDE_U; ++u) {
+      adam_update(wv[u], mv[u], vv[u], gv[u], gscale, c1, c2, alpha, eps);
+      __stcs(m + i0 + u * T, mv[u]);
+      __stcs(v + i0 + u * T, vv[u]);
+      __stcs(w + i0 + u * T, wv[u]);
+      uint2 o;
+      o.x = pack_bf16x2(wv[u].x, wv[u].y);
+      o.y = pack_bf16x2(wv[u].z, wv[u].w);
+      wb[i0 + u * T] = o;
+    }
+  }
+  for (; i0 < nvec; i0 += T) {
+    float4 gv = __ldcs(g + i0), mv = m[i0], vv = v[i0], wv = w[i0];
+    adam_update(wv, mv, vv, gv, gscale, c1, c2, alpha, eps);
+    m[i0] = mv;
+    v[i0] = vv;
+    w[i0] = wv;
+    uint2 o;
+    o.x = pack_bf16x2(wv.x, wv.y);
+    o.y = pack_bf16x2(wv.z, wv.w);
+    wb[i0] = o;
+  }
+  trace.end();
+}
+
 int adam_prepare(long long* iterations, float* hyper, float base_lr, int warmup_steps, float beta1, float beta2,
                  cudaStream_t st) {
   launch_k(adam_prepare_kernel, dim3(1), dim3(1), 0, st, iterations, hyper, base_lr, warmup_steps, beta1, beta2);
@@ -818,6 +879,18 @@ int adam_apply(float* w, float* m, float* v, const float* g, __nv_bfloat16* w_bf
   }
   const long long nvec = n / 4;
   if (nvec == 0) return 0;
+  if (g_adam_sms > 0 && nvec >= (long long)g_adam_sms * ADAM_WIDE_THREADS * ADAM_WIDE_U) {
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(adam_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ADAM_WIDE_SMEM);
+      attr = true;
+    }
+    launch_k(adam_wide_kernel, dim3(g_adam_sms), dim3(ADAM_WIDE_THREADS), ADAM_WIDE_SMEM, st, reinterpret_cast<float4*>(w),
+             reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), reinterpret_cast<const float4*>(g),
+             reinterpret_cast<uint2*>(w_bf16), nvec, hyper, beta1, beta2, eps, grad_scale, iterations_inc);
+    GCT2_CHECK_LAUNCH("adam_wide_kernel");
+    return 0;
+  }
   long long blocks = (nvec + ADAM_THREADS * ADAM_U - 1) / (ADAM_THREADS * ADAM_U);
   const long long cap = g_adam_blocks > 0 ? g_adam_blocks : (long long)g_ew_sms * 8;
   if (blocks > cap) blocks = cap;

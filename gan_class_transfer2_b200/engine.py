@@ -209,6 +209,12 @@ class UNetEngine:
         mode = os.environ.get("GCT2_OVERLAP", "all")  # test hook: none | wgrad | adam | all
         self.overlap_wgrad = mode in ("all", "wgrad")
         self.overlap_adam = mode in ("all", "adam")
+        #: GCT2_WEIGHTS_STABLE for the step's tensor-core launches: the bf16 kernels are only ever written on the side
+        #: streams (Keras-Adam, the data-parallel all-gather), which rejoin the main stream through events -- a full
+        #: dependency -- so no launch that writes them can still be running when a conv launch of the main stream starts
+        #: its prologue.  With the optimiser on the main stream (test hook GCT2_OVERLAP=none|wgrad) an Adam launch could
+        #: still be draining under programmatic dependent launch, and the flag stays off.
+        self.weights_stable = self.overlap_adam and os.environ.get("GCT2_WEIGHTS_EARLY", "1") != "0"
         self._side = torch.cuda.Stream(device=self.device)
         self._side_adam = torch.cuda.Stream(device=self.device)
         self._graph = None
@@ -298,6 +304,8 @@ class UNetEngine:
             self.v.zero_()
             self.iterations.zero_()
         self._graph = None
+        # the bf16 kernels must be at rest before a step may fetch them ahead of its dependencies (weights_stable)
+        torch.cuda.current_stream().synchronize()
 
     def init_glorot(self, seed: int = 0) -> None:
         gen = torch.Generator().manual_seed(seed)
@@ -358,10 +366,10 @@ class UNetEngine:
                              self.down_out(0))
         for i in range(1, n):
             ops.conv4s2_fprop(self.down_in(i), self.view(self.w16, f"down{i}/kernel"),
-                              self.view(self.w, f"down{i}/bias"), self.down_out(i), self.ws)
+                              self.view(self.w, f"down{i}/bias"), self.down_out(i), self.ws, self.weights_stable)
         for i in reversed(range(n)):
             ops.convT4s2_fprop(self.up_in_buf(i), self.view(self.w16, f"up{i}/kernel"),
-                               self.view(self.w, f"up{i}/bias"), self.up_out(i), self.ws)
+                               self.view(self.w, f"up{i}/bias"), self.up_out(i), self.ws, self.weights_stable)
         ops.dense_mse(self.u0, self.noised, self.x, self.view(self.w, "dense/kernel"), self.view(self.w, "dense/bias"),
                       self.loss, inv_n, pred=self.pred if want_pred else None,
                       du0=self.gu0 if backward else None, dwd=self.view(self.g, "dense/kernel") if backward else None,
@@ -453,14 +461,14 @@ class UNetEngine:
                                                self.ws_w))
             mask = cfg.down_c(i) if i == n - 1 else cfg.up_c(i + 1)
             ops.convT4s2_dgrad(self.gup_out(i), self.view(self.w16, f"up{i}/kernel"), self.gup_in_buf(i),
-                               self.up_in_buf(i), mask, self.ws)
+                               self.up_in_buf(i), mask, self.ws, self.weights_stable)
             bucket_done(f"up{i}/kernel")
         for i in reversed(range(1, n)):  # down{n-1} .. down1
             on_side(lambda: ops.conv4s2_wgrad(self.down_in(i), self.gdown_out(i), self.view(self.g, f"down{i}/kernel"),
                                               self.ws_w))
             # total gradient of down_{i-1}'s output = skip-path part (already stored raw by up_{i-1}'s dgrad) + this
             ops.conv4s2_dgrad(self.gdown_out(i), self.view(self.w16, f"down{i}/kernel"), self.gcat[i][..., cfg.up_c(i):],
-                              self.down_in(i), True, self.ws)
+                              self.down_in(i), True, self.ws, self.weights_stable)
             bucket_done(f"down{i}/kernel")
         ops.conv4s2_c3_wgrad(self.noised, self.gdown_out(0), self.view(self.g, "down0/kernel"), None, accumulate=True)
         # every conv layer's BiasAddGrad in one launch: the pre-activation gradients all still sit in their buffers
@@ -541,6 +549,7 @@ class UNetEngine:
     def _restore_state(self, saved) -> None:
         for dst, src in zip((self.w, self.m, self.v, self.w16, self.iterations), saved):
             dst.copy_(src)
+        torch.cuda.current_stream().synchronize()  # see load_weights
 
     def run_step(self, draw: bool = True, u8: bool = False) -> None:
         """The step on whatever set_batch staged (the part bench.py times as `value`)."""
@@ -577,19 +586,19 @@ class UNetEngine:
         cfg, n = self.cfg, self.cfg.octaves
         for i in range(1, n):
             ops.conv4s2_fprop(self.down_in(i), self.view(self.w16, f"down{i}/kernel"),
-                              self.view(self.w, f"down{i}/bias"), self.down_out(i), self.ws)
+                              self.view(self.w, f"down{i}/bias"), self.down_out(i), self.ws, self.weights_stable)
         for i in reversed(range(n)):
             ops.convT4s2_fprop(self.up_in_buf(i), self.view(self.w16, f"up{i}/kernel"),
-                               self.view(self.w, f"up{i}/bias"), self.up_out(i), self.ws)
+                               self.view(self.w, f"up{i}/bias"), self.up_out(i), self.ws, self.weights_stable)
         for i in range(n):
             ops.convT4s2_wgrad(self.up_in_buf(i), self.gup_out(i), self.view(self.g, f"up{i}/kernel"), self.ws_w)
             mask = cfg.down_c(i) if i == n - 1 else cfg.up_c(i + 1)
             ops.convT4s2_dgrad(self.gup_out(i), self.view(self.w16, f"up{i}/kernel"), self.gup_in_buf(i),
-                               self.up_in_buf(i), mask, self.ws)
+                               self.up_in_buf(i), mask, self.ws, self.weights_stable)
         for i in reversed(range(1, n)):
             ops.conv4s2_wgrad(self.down_in(i), self.gdown_out(i), self.view(self.g, f"down{i}/kernel"), self.ws_w)
             ops.conv4s2_dgrad(self.gdown_out(i), self.view(self.w16, f"down{i}/kernel"), self.gcat[i][..., cfg.up_c(i):],
-                              self.down_in(i), True, self.ws)
+                              self.down_in(i), True, self.ws, self.weights_stable)
 
     def release_graphs(self) -> None:
         """Drops the captured step graphs.  Data-parallel callers do this before ``destroy_process_group``: NCCL keeps a

@@ -23,6 +23,20 @@ def launch_count() -> int:
     return int(_lib.load().gct2_launch_count())
 
 
+def last_plan() -> dict:
+    """Test hook: the plan of the most recent tensor-core conv launch (gct2_debug_last_plan)."""
+    import ctypes
+    out = (ctypes.c_int * 8)()
+    _lib.load().gct2_debug_last_plan(out)
+    keys = ("BN", "splits", "pair", "fused", "grid", "stages", "rounds", "early")
+    return dict(zip(keys, list(out)))
+
+
+def set_sm_budget(sms: int) -> None:
+    """CTAs a tensor-core conv launch may occupy (0 = all SMs); see gct2_set_sm_budget."""
+    _lib.load().gct2_set_sm_budget(int(sms))
+
+
 #: when a list, every op appends (op name, start event, end event) -- bench.py's per-kernel timing pass
 _profile = None
 
@@ -111,24 +125,25 @@ def conv4s2_c3_wgrad(x, dz, dw, db=None, accumulate: bool = False):
 
 
 @_timed
-def conv4s2_fprop(x, w, bias, y, ws: Workspace):
-    """DownShuffle forward (train.py:158-169): y = relu(conv2d(x, w, s=2, SAME) + b).  w bf16 [4,4,Cin,Cout]."""
+def conv4s2_fprop(x, w, bias, y, ws: Workspace, weights_stable: bool = False):
+    """DownShuffle forward (train.py:158-169): y = relu(conv2d(x, w, s=2, SAME) + b).  w bf16 [4,4,Cin,Cout].
+    weights_stable: GCT2_WEIGHTS_STABLE (w is not being written by anything that may still run when this launch starts)."""
     lib = _lib_for(x)
     B, H, W, Cin = x.shape
     check(lib.gct2_conv4s2_fprop(ptr(x), _nhwc(x, torch.bfloat16), ptr(w), ptr(bias), ptr(y), _nhwc(y, torch.bfloat16),
-                                 B, H, W, Cin, y.shape[3], ptr(ws.buf), ws.nbytes, current_stream()))
+                                 B, H, W, Cin, y.shape[3], ptr(ws.buf), ws.nbytes, int(weights_stable), current_stream()))
     return y
 
 
 @_timed
-def conv4s2_dgrad(dy, w, dx, act, add_old: bool, ws: Workspace):
+def conv4s2_dgrad(dy, w, dx, act, add_old: bool, ws: Workspace, weights_stable: bool = False):
     """Backward-data of DownShuffle, fused with the ReLU mask of the layer that produced the input and the add of
     the skip-path gradient already sitting in dx."""
     lib = _lib_for(dy)
     B, H, W, Cin = dx.shape
     check(lib.gct2_conv4s2_dgrad(ptr(dy), _nhwc(dy, torch.bfloat16), ptr(w), ptr(dx), _nhwc(dx, torch.bfloat16),
                                  ptr(act), _nhwc(act, torch.bfloat16), int(add_old), B, H, W, Cin, dy.shape[3],
-                                 ptr(ws.buf), ws.nbytes, current_stream()))
+                                 ptr(ws.buf), ws.nbytes, int(weights_stable), current_stream()))
     return dx
 
 
@@ -142,24 +157,24 @@ def conv4s2_wgrad(x, dy, dw, ws: Optional[Workspace] = None):
 
 
 @_timed
-def convT4s2_fprop(x, w, bias, y, ws: Workspace):
+def convT4s2_fprop(x, w, bias, y, ws: Workspace, weights_stable: bool = False):
     """UpShuffle forward (train.py:145-156): y = relu(conv2d_transpose(x, w, s=2, SAME) + b). w bf16 [4,4,Cout,Cin]."""
     lib = _lib_for(x)
     B, H, W, Cin = x.shape
     check(lib.gct2_convT4s2_fprop(ptr(x), _nhwc(x, torch.bfloat16), ptr(w), ptr(bias), ptr(y),
                                   _nhwc(y, torch.bfloat16), B, H, W, Cin, y.shape[3], ptr(ws.buf), ws.nbytes,
-                                  current_stream()))
+                                  int(weights_stable), current_stream()))
     return y
 
 
 @_timed
-def convT4s2_dgrad(dy, w, dx, act, mask_channels: int, ws: Workspace):
+def convT4s2_dgrad(dy, w, dx, act, mask_channels: int, ws: Workspace, weights_stable: bool = False):
     """Backward-data of UpShuffle; channels [0, mask_channels) of dx are ReLU-masked by act, the rest stored raw."""
     lib = _lib_for(dy)
     B, H, W, Cin = dx.shape
     check(lib.gct2_convT4s2_dgrad(ptr(dy), _nhwc(dy, torch.bfloat16), ptr(w), ptr(dx), _nhwc(dx, torch.bfloat16),
                                   ptr(act), _nhwc(act, torch.bfloat16), mask_channels, B, H, W, Cin, dy.shape[3],
-                                  ptr(ws.buf), ws.nbytes, current_stream()))
+                                  ptr(ws.buf), ws.nbytes, int(weights_stable), current_stream()))
     return dx
 
 

@@ -27,7 +27,13 @@
 extern "C" {
 #endif
 
-#define GCT2_ABI_VERSION 1
+#define GCT2_ABI_VERSION 2
+
+/* `flags` of the four tensor-core fprop / dgrad entry points.
+ * GCT2_WEIGHTS_STABLE: the kernel tensor `w` is not being written by any launch that may still be running when this one
+ * starts (the engine's optimiser runs on another stream and is joined by an event), so its first tiles may be fetched
+ * before the programmatic dependency on the previous launch of `stream` resolves.  Without the flag every load waits. */
+#define GCT2_WEIGHTS_STABLE 1
 
 int gct2_abi_version(void);
 const char* gct2_last_error(void);
@@ -38,20 +44,27 @@ int gct2_num_sms(void);
 /* Number of kernels (and memset nodes of split-K paths) this library has enqueued so far in this process. */
 long long gct2_launch_count(void);
 /* Test hook (not part of the drop-in surface): key 0/1 override the MN-major UMMA descriptor LBO/SBO bytes,
- * key 2 = verbose plan logging, key 3 = force N tile, key 4 = force split-K, keys 5/6 = force the cluster shape
- * (CTAs along M / along N; 0 = heuristic, 1 = none), key 7 = record per-CTA phase timestamps (gct2_debug_timeline),
+ * key 2 = verbose plan logging, key 3 = force N tile, key 4 = force split-K, key 7 = record per-CTA phase timestamps
+ * (gct2_debug_timeline; only in libraries built with -DGCT2_TIMELINE -- the production main loops carry no stamps),
  * key 8 != 0 = launch without programmatic dependent launch, keys 9 / 10 = CTA budget of the wgrad / dgrad
- * launches (0 = all SMs; lets the concurrent backward chains run on disjoint SM sets), key 11 = whole-step launch
- * trace (gct2_debug_trace), key 12 != 0 = finish split-K with a separate kernel instead of inside the launch, key 13 = grid cap of the
- * Adam kernel (0 = 8 blocks per SM), key 15 = grid cap of the down0 weight-gradient kernel (0 = 2 blocks per SM), key 16 = which
- * point of the TMA producer's start-up timeline stamp [7] records (0 loop entry .. 4 first loads issued), key 17 = cap of
- * the shared-memory ring depth, key 19 = CTA pairs (cta_group::2): 0 heuristic, 1 wherever legal, 2 never. */
+ * launches (0 = all SMs), key 11 = whole-step launch trace (gct2_debug_trace), key 12 != 0 = finish split-K with a
+ * separate kernel instead of inside the launch, key 13 = grid cap of the Adam kernel (0 = 8 blocks per SM), key 15 = grid
+ * cap of the down0 weight-gradient kernel (0 = 2 blocks per SM), key 16 = which point of the TMA producer's start-up
+ * timeline stamp [7] records, key 19 = CTA pairs (cta_group::2): 0 heuristic, 1 wherever legal, 2 never, key 20 =
+ * split-K rendezvous watchdog in polls of ~40 ns (0 = none; default 2^28), key 21 != 0 = never fetch weights before the
+ * programmatic dependency resolves, key 22 = gct2_set_sm_budget. */
 void gct2_debug_set(int key, int value);
 /* Test hook: after gct2_debug_set(7, 1) every tensor-core conv launch records, per CTA, 8 %globaltimer stamps (ns):
  * [0] entry, [1] prologue done, [2] first operands landed, [3] MMAs of the first tile issued, [4] first accumulator
  * complete, [5] first epilogue done, [6] CTA done, [7] see key 16.  Synchronises the device and copies the stamps of the most
  * recent launch (up to max_ctas CTAs) to `host`; returns the number of CTAs. */
 int gct2_debug_timeline(unsigned long long* host, int max_ctas);
+/* Test hook: the plan of the most recent tensor-core conv launch: out8 = {BN, split-K factor, CTA pairs (0/1), split-K
+ * finished inside the launch (0/1), grid, ring slots, ring rounds per work item, weights fetched early (0/1)}. */
+void gct2_debug_last_plan(int* out8);
+/* CTAs (= SMs) a tensor-core conv launch may occupy; 0 = all.  Data-parallel callers leave room for the NCCL kernels
+ * that run beside backward, so that a conv launch never queues a second wave behind them. */
+void gct2_set_sm_budget(int sms);
 /* Test hook: after gct2_debug_set(11, 1) the first and last block of EVERY launch of this library append
  * {kernel id, blockIdx | gridDim << 32, entry ns, exit ns}; this call synchronises, copies up to max_records records
  * (4 x u64 each) to `host`, clears the buffer and returns the count.  Kernel ids: 1 noise, 2 step_begin, 3/4 down0
@@ -81,16 +94,17 @@ int gct2_conv4s2_c3_wgrad(const float* x, const uint16_t* dz, int lddz, float* d
  * outputs (splits * B*(H/2)*(W/2)*Cout floats) fit in ws_bytes; partials are summed in a fixed order, so results are
  * bit-reproducible.  ws may be NULL (no split-K).  The same holds for every ws argument below.
  * Concurrency: when every work item has its own resident CTA, split-K is finished inside the launch (the CTAs of a
- * tile wait for each other), so fprop/dgrad calls must not run concurrently with each other on different streams
- * of one device; wgrad calls never wait and may overlap anything. */
+ * tile wait for each other at counters of the launch's own), so a fprop/dgrad launch needs all of its CTAs resident:
+ * do not run two of them concurrently on different streams of one device unless gct2_set_sm_budget leaves room for
+ * both; wgrad calls never wait and may overlap anything.  flags: GCT2_WEIGHTS_STABLE or 0. */
 int gct2_conv4s2_fprop(const uint16_t* x, int ldx, const uint16_t* w, const float* bias, uint16_t* y, int ldy,
-                       int B, int H, int W, int Cin, int Cout, float* ws, size_t ws_bytes, void* stream);
+                       int B, int H, int W, int Cin, int Cout, float* ws, size_t ws_bytes, int flags, void* stream);
 /* Backward-data of DownShuffle: dx[b,iy,ix,ci] (+)= sum dy[b,oy,ox,co]*w[ky,kx,ci,co], then ReLU-masked by the
  * producer's saved output: dx = (acc + (add_old ? dx : 0)) * (act > 0).  dy bf16 [B,H/2,W/2,Cout]; dx, act bf16
  * [B,H,W,Cin].  tcgen05 implicit GEMM (phase form).  ws >= B*H*W*Cin floats. */
 int gct2_conv4s2_dgrad(const uint16_t* dy, int lddy, const uint16_t* w, uint16_t* dx, int lddx,
                        const uint16_t* act, int ldact, int add_old, int B, int H, int W, int Cin, int Cout,
-                       float* ws, size_t ws_bytes, void* stream);
+                       float* ws, size_t ws_bytes, int flags, void* stream);
 /* Backward-filter of DownShuffle: dw[ky,kx,ci,co] = sum x[b,2oy-1+ky,2ox-1+kx,ci]*dy[b,oy,ox,co]; fp32, overwritten.
  * ws: split-K scratch for splits * 16*Cin*Cout floats (must not be shared with a concurrently running call). */
 int gct2_conv4s2_wgrad(const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, int B, int H, int W,
@@ -99,14 +113,14 @@ int gct2_conv4s2_wgrad(const uint16_t* x, int ldx, const uint16_t* dy, int lddy,
 /* train.py:145-156 UpShuffle forward: y = relu(conv2d_transpose(x, w[4,4,Cout,Cin], s=2, SAME) + b).
  * x bf16 [B,H,W,Cin] stride ldx; y bf16 [B,2H,2W,Cout] stride ldy (phase form). ws >= B*2H*2W*Cout floats. */
 int gct2_convT4s2_fprop(const uint16_t* x, int ldx, const uint16_t* w, const float* bias, uint16_t* y, int ldy,
-                        int B, int H, int W, int Cin, int Cout, float* ws, size_t ws_bytes, void* stream);
+                        int B, int H, int W, int Cin, int Cout, float* ws, size_t ws_bytes, int flags, void* stream);
 /* Backward-data of UpShuffle: dx[b,iy,ix,ci] = sum dy[b,2iy-1+ky,2ix-1+kx,co]*w[ky,kx,co,ci]; channels
  * [0,mask_channels) are ReLU-masked by act (the saved activation co-located with dx), the rest stored raw
  * (they are the skip-path gradient, consumed by gct2_conv4s2_dgrad(add_old=1)).  Strided form.
  * dy bf16 [B,2H,2W,Cout]; dx, act bf16 [B,H,W,Cin]. ws >= B*H*W*Cin floats. */
 int gct2_convT4s2_dgrad(const uint16_t* dy, int lddy, const uint16_t* w, uint16_t* dx, int lddx,
                         const uint16_t* act, int ldact, int mask_channels, int B, int H, int W, int Cin, int Cout,
-                        float* ws, size_t ws_bytes, void* stream);
+                        float* ws, size_t ws_bytes, int flags, void* stream);
 /* Backward-filter of UpShuffle: dw[ky,kx,co,ci] = sum dy[b,2iy-1+ky,2ix-1+kx,co]*x[b,iy,ix,ci]; fp32, overwritten. */
 int gct2_convT4s2_wgrad(const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, int B, int H, int W,
                         int Cin, int Cout, float* ws, size_t ws_bytes, void* stream);

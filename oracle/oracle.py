@@ -59,6 +59,9 @@ class Config:
 DEFAULT = Config()
 #: shrunken config used by the fast tests (keeps a 4x4 bottleneck like the reference's comment at train.py:21)
 TINY = Config(size=64, pixel_size=128, max_size=256, octaves=4)
+#: BASELINE.json config 4 ("doubled-resolution / widened-channel variant"): 512 px, 7 octaves, up to 1024 channels,
+#: 217 078 796 parameters, 2062 GFLOP per image per step; still a 4x4 bottleneck (train.py:21)
+WIDE = Config(size=512, pixel_size=256, max_size=1024, octaves=7)
 
 
 def alpha_dash(t, steps: int = 200):

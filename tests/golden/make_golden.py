@@ -23,8 +23,28 @@ def main():
     x, t, e = O.synthetic_batch(cfg, 2, 1)
     loss, grads, taps = O.loss_and_grads(tr.weights, x, t, e, cfg, want_taps=True)
     out = {"loss": np.float32(loss), "pred_corner": taps["pred"][0, :4, :4].numpy()}
+    # gradients as TENSORS (a norm cannot see a permuted or transposed gradient): small ones in full, large ones at
+    # 2048 fixed random positions (the indices are stored beside the values)
+    import torch
+    gen = torch.Generator().manual_seed(1234)
     for k, g in grads.items():
         out["gnorm/" + k] = np.float32(g.norm())
+        flat = g.reshape(-1)
+        if flat.numel() <= 4096:
+            idx = torch.arange(flat.numel())
+        else:
+            idx = torch.randperm(flat.numel(), generator=gen)[:2048].sort().values
+        out["gidx/" + k] = idx.numpy().astype(np.int64)
+        out["gval/" + k] = flat[idx].numpy()
+    out["pred"] = taps["pred"].numpy()
+    for k in ("down0", "down3", "up3", "up0", "ddown1", "dup2"):
+        v = taps[k]
+        if k.startswith(("ddown", "dup")):  # gradient w.r.t. the PRE-activation (what the CUDA path stores): ReLU mask applied
+            v = v * (taps[k[1:]] > 0)
+        flat = v.reshape(-1)
+        idx = torch.randperm(flat.numel(), generator=gen)[:2048].sort().values
+        out["aidx/" + k] = idx.numpy().astype(np.int64)
+        out["aval/" + k] = flat[idx].numpy()
     for k in ("down0", "down3", "up3", "up0"):
         out["anorm/" + k] = np.float32(taps[k].norm())
     out["losses3"] = np.array([tr.train_step(*O.synthetic_batch(cfg, 2, 100 + s)) for s in range(3)], dtype=np.float32)

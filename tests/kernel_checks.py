@@ -53,7 +53,7 @@ def _slice_buf(B, H, W, C, pad_front, pad_back, dev, fill=None):
 
 
 # ---------------------------------------------------------------------------------------------- conv (down)
-def check_conv_fprop(B, H, Cin, Cout, seed=0, pad=64):
+def check_conv_fprop(B, H, Cin, Cout, seed=0, pad=64, weights_stable=False):
     ops = _ops()
     g = torch.Generator().manual_seed(seed)
     x = _bf(_rand((B, H, H, Cin), g))
@@ -65,14 +65,14 @@ def check_conv_fprop(B, H, Cin, Cout, seed=0, pad=64):
     xv.copy_(x)
     yfull, yv = _slice_buf(B, H // 2, H // 2, Cout, 0, pad, dev)
     ws = ops.Workspace(64 << 20, dev)
-    ops.conv4s2_fprop(xv, w.to(dev), b.to(dev), yv, ws)
+    ops.conv4s2_fprop(xv, w.to(dev), b.to(dev), yv, ws, weights_stable)
     torch.cuda.synchronize()
     m = _metrics(f"conv4s2_fprop B{B} H{H} {Cin}->{Cout}", yv, ref, BF16_TOL)
     m["pad_intact"] = bool((yfull[..., Cout:] == 7.0).all().item()) if pad else True
     return m
 
 
-def check_conv_dgrad(B, H, Cin, Cout, add_old=True, seed=1, pad=64):
+def check_conv_dgrad(B, H, Cin, Cout, add_old=True, seed=1, pad=64, weights_stable=False):
     ops = _ops()
     g = torch.Generator().manual_seed(seed)
     dy = _bf(_rand((B, H // 2, H // 2, Cout), g))
@@ -94,7 +94,7 @@ def check_conv_dgrad(B, H, Cin, Cout, add_old=True, seed=1, pad=64):
     _, actv = _slice_buf(B, H, H, Cin, pad, 0, dev)
     actv.copy_(act)
     ws = ops.Workspace(64 << 20, dev)
-    ops.conv4s2_dgrad(dyv, w.to(dev), dxv, actv, add_old, ws)
+    ops.conv4s2_dgrad(dyv, w.to(dev), dxv, actv, add_old, ws, weights_stable)
     torch.cuda.synchronize()
     m = _metrics(f"conv4s2_dgrad B{B} H{H} {Cin}<-{Cout} add{int(add_old)}", dxv, ref, BF16_TOL)
     m["pad_intact"] = bool((dxfull[..., :pad] == 7.0).all().item()) if pad else True
@@ -122,7 +122,7 @@ def check_conv_wgrad(B, H, Cin, Cout, seed=2, pad=64):
 
 
 # ---------------------------------------------------------------------------------------------- convT (up)
-def check_convT_fprop(B, H, Cin, Cout, seed=3, pad=64):
+def check_convT_fprop(B, H, Cin, Cout, seed=3, pad=64, weights_stable=False):
     ops = _ops()
     g = torch.Generator().manual_seed(seed)
     x = _bf(_rand((B, H, H, Cin), g))
@@ -134,14 +134,14 @@ def check_convT_fprop(B, H, Cin, Cout, seed=3, pad=64):
     xv.copy_(x)
     yfull, yv = _slice_buf(B, 2 * H, 2 * H, Cout, 0, pad, dev)
     ws = ops.Workspace(64 << 20, dev)
-    ops.convT4s2_fprop(xv, w.to(dev), b.to(dev), yv, ws)
+    ops.convT4s2_fprop(xv, w.to(dev), b.to(dev), yv, ws, weights_stable)
     torch.cuda.synchronize()
     m = _metrics(f"convT4s2_fprop B{B} H{H} {Cin}->{Cout}", yv, ref, BF16_TOL)
     m["pad_intact"] = bool((yfull[..., Cout:] == 7.0).all().item()) if pad else True
     return m
 
 
-def check_convT_dgrad(B, H, Cin, Cout, mask_channels=None, seed=4, pad=64):
+def check_convT_dgrad(B, H, Cin, Cout, mask_channels=None, seed=4, pad=64, weights_stable=False):
     ops = _ops()
     g = torch.Generator().manual_seed(seed)
     if mask_channels is None:
@@ -161,7 +161,7 @@ def check_convT_dgrad(B, H, Cin, Cout, mask_channels=None, seed=4, pad=64):
     _, actv = _slice_buf(B, H, H, Cin, 0, pad, dev)
     actv.copy_(act)
     ws = ops.Workspace(64 << 20, dev)
-    ops.convT4s2_dgrad(dyv, w.to(dev), dxv, actv, mask_channels, ws)
+    ops.convT4s2_dgrad(dyv, w.to(dev), dxv, actv, mask_channels, ws, weights_stable)
     torch.cuda.synchronize()
     m = _metrics(f"convT4s2_dgrad B{B} H{H} {Cin}<-{Cout} mask{mask_channels}", dxv, ref, BF16_TOL)
     m["pad_intact"] = bool((dxfull[..., Cin:] == 7.0).all().item()) if pad else True
@@ -497,23 +497,45 @@ EW_CASES = [
 ]
 
 
-def forced(fn, BN=0, splits=0, cm=0, cn=0, nofuse=0, **kw):
-    """Runs a conv check with the tile width / split-K factor pinned (test hook gct2_debug_set keys 3, 4) so that
-    every template instantiation and the split-K finishing passes are exercised regardless of the heuristics."""
-    from gan_class_transfer2_b200 import _lib
+def forced(fn, BN=0, splits=0, pair=0, nofuse=0, budget=0, **kw):
+    """Runs a conv check with the tile width / split-K factor / CTA-pair mode pinned (test hooks gct2_debug_set keys 3,
+    4, 19, 12 and gct2_set_sm_budget) so that every template instantiation and every split-K finishing path is exercised
+    regardless of the heuristics; then asks the library which plan the launch actually used (gct2_debug_last_plan) --
+    a case that asked for CTA pairs / a fused finish and silently got something else fails."""
+    from gan_class_transfer2_b200 import _lib, ops
     lib = _lib.init(0)
-    for key, val in ((3, BN), (4, splits), (5, cm), (6, cn), (12, nofuse)):
+    for key, val in ((3, BN), (4, splits), (19, pair), (12, nofuse), (22, budget)):
         lib.gct2_debug_set(key, val)
     try:
         m = fn(**kw)
+        plan = ops.last_plan()
     finally:
-        for key in (3, 4, 5, 6, 12):
+        for key in (3, 4, 19, 12, 22):
             lib.gct2_debug_set(key, 0)
-    m["name"] += (f" [BN={BN or 'auto'} splits={splits or 'auto'} cluster={cm or 'auto'}x{cn or 'auto'}"
-                  f"{' finish-kernel' if nofuse else ''}]")
+    m["name"] += (f" [BN={BN or 'auto'} splits={splits or 'auto'} pair={pair}{' finish-kernel' if nofuse else ''}"
+                  f"{f' budget={budget}' if budget else ''} -> {plan}]")
+    want = {}
+    if BN:
+        want["BN"] = BN
+    if splits:
+        want["splits"] = splits
+    if pair == 1:
+        want["pair"] = 1
+    if pair == 2:
+        want["pair"] = 0
+    if nofuse:
+        want["fused"] = 0
+    if budget:
+        assert plan["grid"] <= budget, (plan, budget)
+    wrong = {k: (plan[k], v) for k, v in want.items() if plan[k] != v}
+    if wrong:
+        m["err"] = float("inf")
+        m["detail"] = f"plan differs from the forced one: {wrong}"
+    m["plan"] = plan
     return m
 
 
+# (check, shape kwargs, forced plan)
 FORCED_CASES = [
     (check_conv_fprop, dict(B=2, H=16, Cin=128, Cout=256), dict(BN=64, splits=1)),
     (check_conv_fprop, dict(B=2, H=16, Cin=128, Cout=256), dict(BN=128, splits=4)),
@@ -530,6 +552,11 @@ FORCED_CASES = [
     (check_conv_wgrad, dict(B=4, H=32, Cin=128, Cout=256), dict(BN=256, splits=2)),
     (check_convT_wgrad, dict(B=4, H=16, Cin=256, Cout=64), dict(BN=64, splits=4)),
     (check_convT_wgrad, dict(B=4, H=16, Cin=256, Cout=128), dict(BN=256, splits=16)),
+    # odd number of k-chunks per work item: the last ring round of a two-chunk slot is half full (BN <= 128)
+    (check_conv_wgrad, dict(B=3, H=16, Cin=128, Cout=64), dict(BN=64, splits=1)),       # 3 pixel chunks
+    (check_convT_wgrad, dict(B=1, H=4, Cin=128, Cout=128), dict(BN=128, splits=1)),     # 1 chunk, a quarter full
+    (check_conv_fprop, dict(B=1, H=16, Cin=64, Cout=128), dict(BN=128, splits=16)),     # 1 chunk per split
+    (check_convT_fprop, dict(B=2, H=8, Cin=192, Cout=64), dict(BN=64, splits=4)),       # 3 chunks per split
     # split-K finished by the separate kernel (the fallback when a CTA owns more than one work item)
     (check_conv_fprop, dict(B=2, H=16, Cin=128, Cout=256), dict(BN=128, splits=4, nofuse=1)),
     (check_convT_fprop, dict(B=2, H=8, Cin=128, Cout=256), dict(BN=256, splits=8, nofuse=1)),
@@ -538,20 +565,64 @@ FORCED_CASES = [
     # split-K with a ragged batch: rows of the tile beyond the batch are neither stored nor finished
     (check_conv_fprop, dict(B=3, H=8, Cin=256, Cout=128), dict(BN=64, splits=16)),
     (check_convT_dgrad, dict(B=3, H=4, Cin=128, Cout=256, mask_channels=64), dict(BN=128, splits=8)),
-    # thread-block clusters with TMA multicast (A along cn, B along cm); the last ones loop persistently
-    (check_conv_fprop, dict(B=2, H=32, Cin=128, Cout=256), dict(BN=64, splits=1, cm=1, cn=1)),
-    (check_conv_fprop, dict(B=2, H=32, Cin=128, Cout=256), dict(BN=64, splits=1, cm=2, cn=1)),
-    (check_conv_fprop, dict(B=2, H=32, Cin=128, Cout=256), dict(BN=64, splits=1, cm=1, cn=4)),
-    (check_conv_fprop, dict(B=2, H=32, Cin=128, Cout=256), dict(BN=64, splits=2, cm=2, cn=4)),
-    (check_conv_fprop, dict(B=2, H=32, Cin=128, Cout=256), dict(BN=128, splits=4, cm=4, cn=2)),
-    (check_convT_fprop, dict(B=2, H=16, Cin=128, Cout=128), dict(BN=64, splits=1, cm=4, cn=2)),
-    (check_convT_fprop, dict(B=2, H=16, Cin=128, Cout=128), dict(BN=128, splits=2, cm=4, cn=1)),
-    (check_conv_dgrad, dict(B=2, H=32, Cin=256, Cout=128, add_old=True), dict(BN=64, splits=1, cm=2, cn=4)),
-    (check_conv_dgrad, dict(B=4, H=32, Cin=256, Cout=128, add_old=False), dict(BN=256, splits=1, cm=8, cn=1)),
-    (check_convT_dgrad, dict(B=2, H=16, Cin=256, Cout=128), dict(BN=128, splits=1, cm=2, cn=2)),
-    (check_convT_dgrad, dict(B=2, H=16, Cin=256, Cout=128), dict(BN=64, splits=4, cm=1, cn=4)),
-    (check_conv_fprop, dict(B=16, H=64, Cin=64, Cout=128), dict(BN=64, splits=1, cm=4, cn=2)),
-    (check_convT_fprop, dict(B=16, H=16, Cin=64, Cout=64), dict(BN=64, splits=1, cm=8, cn=1)),
+    # persistent CTAs: more work items than the SM budget (several tiles per CTA, TMEM double buffering, ring wrap)
+    (check_conv_fprop, dict(B=16, H=64, Cin=64, Cout=128), dict(BN=64, splits=1, budget=24)),
+    (check_convT_fprop, dict(B=16, H=16, Cin=64, Cout=64), dict(BN=64, splits=1, budget=20)),
+    (check_conv_dgrad, dict(B=4, H=32, Cin=256, Cout=128, add_old=False), dict(BN=256, splits=1, budget=6)),
+    (check_conv_wgrad, dict(B=4, H=32, Cin=128, Cout=256), dict(BN=128, splits=2, budget=10)),
+    # weights fetched before the programmatic dependency resolves (GCT2_WEIGHTS_STABLE)
+    (check_conv_fprop, dict(B=2, H=16, Cin=128, Cout=256, weights_stable=True), dict(BN=64, splits=1)),
+    (check_conv_fprop, dict(B=2, H=16, Cin=128, Cout=256, weights_stable=True), dict(BN=128, splits=16)),
+    (check_convT_fprop, dict(B=2, H=8, Cin=128, Cout=256, weights_stable=True), dict(BN=256, splits=1)),
+    (check_convT_fprop, dict(B=16, H=16, Cin=64, Cout=64, weights_stable=True), dict(BN=64, splits=1, budget=20)),
+    (check_conv_dgrad, dict(B=2, H=16, Cin=256, Cout=128, add_old=True, weights_stable=True), dict(BN=128, splits=2)),
+    (check_convT_dgrad, dict(B=2, H=8, Cin=256, Cout=128, weights_stable=True), dict(BN=64, splits=4)),
+]
+
+# CTA pairs (tcgen05 cta_group::2): all six PAIR instantiations ({S, P, W} x BN {128, 256}), each with the direct
+# epilogue, split-K finished inside the launch, split-K finished by the separate kernel, a ragged batch, persistent
+# CTA pairs (more tile pairs than resident clusters) and the early weight fetch.  The heuristic picks pairs for every
+# launch with more tiles than SMs (>= 8 images per GPU, BASELINE config 4), so these are the kernels behind those numbers.
+PAIR_CASES = [
+    # MODE_S (DownShuffle fprop / UpShuffle dgrad)
+    (check_conv_fprop, dict(B=2, H=32, Cin=128, Cout=256), dict(BN=128, splits=1, pair=1)),
+    (check_conv_fprop, dict(B=2, H=32, Cin=128, Cout=256), dict(BN=256, splits=1, pair=1)),
+    (check_conv_fprop, dict(B=2, H=32, Cin=128, Cout=256), dict(BN=128, splits=4, pair=1)),
+    (check_conv_fprop, dict(B=2, H=32, Cin=128, Cout=256), dict(BN=256, splits=8, pair=1)),
+    (check_conv_fprop, dict(B=2, H=32, Cin=128, Cout=256), dict(BN=128, splits=4, pair=1, nofuse=1)),
+    (check_conv_fprop, dict(B=2, H=32, Cin=128, Cout=256), dict(BN=256, splits=2, pair=1, nofuse=1)),
+    (check_conv_fprop, dict(B=3, H=16, Cin=128, Cout=256), dict(BN=128, splits=1, pair=1)),            # ragged: 3 of 4 images
+    (check_conv_fprop, dict(B=3, H=16, Cin=128, Cout=256), dict(BN=256, splits=4, pair=1)),
+    (check_conv_fprop, dict(B=16, H=64, Cin=64, Cout=128), dict(BN=128, splits=1, pair=1, budget=12)),  # persistent pairs
+    (check_conv_fprop, dict(B=2, H=32, Cin=128, Cout=256, weights_stable=True), dict(BN=128, splits=2, pair=1)),
+    (check_convT_dgrad, dict(B=2, H=16, Cin=256, Cout=128), dict(BN=128, splits=1, pair=1)),
+    (check_convT_dgrad, dict(B=2, H=16, Cin=256, Cout=128), dict(BN=256, splits=1, pair=1)),
+    (check_convT_dgrad, dict(B=2, H=16, Cin=256, Cout=128, mask_channels=64), dict(BN=128, splits=4, pair=1)),
+    (check_convT_dgrad, dict(B=2, H=16, Cin=256, Cout=128), dict(BN=256, splits=2, pair=1, nofuse=1)),
+    (check_convT_dgrad, dict(B=3, H=8, Cin=256, Cout=128, weights_stable=True), dict(BN=256, splits=4, pair=1)),
+    # MODE_P (UpShuffle fprop / DownShuffle dgrad)
+    (check_convT_fprop, dict(B=2, H=16, Cin=128, Cout=256), dict(BN=128, splits=1, pair=1)),
+    (check_convT_fprop, dict(B=2, H=16, Cin=128, Cout=256), dict(BN=256, splits=1, pair=1)),
+    (check_convT_fprop, dict(B=2, H=16, Cin=128, Cout=256), dict(BN=128, splits=2, pair=1)),
+    (check_convT_fprop, dict(B=2, H=16, Cin=128, Cout=256), dict(BN=256, splits=4, pair=1)),
+    (check_convT_fprop, dict(B=2, H=16, Cin=128, Cout=256), dict(BN=256, splits=4, pair=1, nofuse=1)),
+    (check_convT_fprop, dict(B=3, H=8, Cin=128, Cout=256), dict(BN=128, splits=1, pair=1)),
+    (check_convT_fprop, dict(B=8, H=32, Cin=64, Cout=128), dict(BN=128, splits=1, pair=1, budget=16)),
+    (check_convT_fprop, dict(B=2, H=16, Cin=128, Cout=256, weights_stable=True), dict(BN=256, splits=2, pair=1)),
+    (check_conv_dgrad, dict(B=2, H=32, Cin=256, Cout=128, add_old=True), dict(BN=128, splits=1, pair=1)),
+    (check_conv_dgrad, dict(B=2, H=32, Cin=256, Cout=128, add_old=True), dict(BN=256, splits=1, pair=1)),
+    (check_conv_dgrad, dict(B=2, H=32, Cin=256, Cout=128, add_old=False), dict(BN=256, splits=2, pair=1)),
+    (check_conv_dgrad, dict(B=2, H=32, Cin=256, Cout=128, add_old=True), dict(BN=128, splits=2, pair=1, nofuse=1)),
+    (check_conv_dgrad, dict(B=3, H=16, Cin=256, Cout=128, add_old=True, weights_stable=True), dict(BN=128, splits=2, pair=1)),
+    # MODE_W (both weight gradients; the gathered operand on the M side and on the N side)
+    (check_conv_wgrad, dict(B=2, H=32, Cin=256, Cout=256), dict(BN=128, splits=1, pair=1)),
+    (check_conv_wgrad, dict(B=2, H=32, Cin=256, Cout=256), dict(BN=256, splits=1, pair=1)),
+    (check_conv_wgrad, dict(B=2, H=32, Cin=256, Cout=256), dict(BN=128, splits=4, pair=1)),
+    (check_conv_wgrad, dict(B=3, H=16, Cin=256, Cout=256), dict(BN=256, splits=1, pair=1)),             # 3 chunks
+    (check_conv_wgrad, dict(B=2, H=32, Cin=256, Cout=128), dict(BN=128, splits=2, pair=1, budget=10)),
+    (check_convT_wgrad, dict(B=2, H=16, Cin=256, Cout=256), dict(BN=128, splits=1, pair=1)),
+    (check_convT_wgrad, dict(B=2, H=16, Cin=256, Cout=256), dict(BN=256, splits=2, pair=1)),
+    (check_convT_wgrad, dict(B=3, H=8, Cin=512, Cout=256), dict(BN=256, splits=1, pair=1)),             # 3 chunks, 4 M tiles
 ]
 
 

@@ -42,7 +42,7 @@ def test_binding_covers_every_declared_symbol():
 
 
 def test_abi_version_and_error_string(lib):
-    assert lib.gct2_abi_version() == 1
+    assert lib.gct2_abi_version() == 2
     assert isinstance(lib.gct2_last_error(), bytes)
 
 

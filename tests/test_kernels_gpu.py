@@ -27,10 +27,26 @@ def test_hbm_bound_kernels_match_oracle(case):
     assert m.get("pad_intact", True), m
 
 
-@pytest.mark.parametrize("case", K.FORCED_CASES, ids=lambda c: c[0].__name__.replace("check_", "") + "-BN%d-s%d-c%dx%d%s" % (
-    c[2]["BN"], c[2]["splits"], c[2].get("cm", 0), c[2].get("cn", 0), "-finishkernel" if c[2].get("nofuse") else ""))
+def _fid(c):
+    f = c[2]
+    return (c[0].__name__.replace("check_", "") + "-" + "-".join(f"{k}{v}" for k, v in c[1].items() if k != "seed")
+            + "-" + "-".join(f"{k}{v}" for k, v in f.items()))
+
+
+@pytest.mark.parametrize("case", K.FORCED_CASES, ids=_fid)
 def test_every_tile_width_and_split_k_path(case):
     fn, kw, force = case
     m = K.forced(fn, **force, **kw)
+    assert m["err"] <= m["tol"], m
+    assert m.get("pad_intact", True), m
+
+
+@pytest.mark.parametrize("case", K.PAIR_CASES, ids=_fid)
+def test_cta_pair_kernels_match_oracle(case):
+    """All six cta_group::2 instantiations against the oracle (VERDICT round 1: these were selected automatically for
+    every launch with more tiles than SMs but only ever reached by a property test)."""
+    fn, kw, force = case
+    m = K.forced(fn, **force, **kw)
+    assert m["plan"]["pair"] == 1, m
     assert m["err"] <= m["tol"], m
     assert m.get("pad_intact", True), m

@@ -179,7 +179,15 @@ def test_golden_vectors_tiny_step():
     assert math.isclose(float(loss), float(gold["loss"]), rel_tol=1e-5)
     for k in grads:
         assert math.isclose(float(grads[k].norm()), float(gold["gnorm/" + k]), rel_tol=2e-4), k
+        got = grads[k].reshape(-1)[torch.from_numpy(gold["gidx/" + k])].numpy()
+        ref = gold["gval/" + k]
+        assert np.linalg.norm(got - ref) <= 2e-4 * np.linalg.norm(ref), k   # element for element, not just the norm
     assert np.allclose(taps["pred"][0, :4, :4].numpy(), gold["pred_corner"], rtol=1e-4, atol=1e-6)
+    assert np.allclose(taps["pred"].numpy(), gold["pred"], rtol=1e-4, atol=1e-6)
+    for k in ("down0", "down3", "up3", "up0", "ddown1", "dup2"):
+        v = taps[k] * (taps[k[1:]] > 0) if k.startswith(("ddown", "dup")) else taps[k]
+        got = v.reshape(-1)[torch.from_numpy(gold["aidx/" + k])].numpy()
+        assert np.linalg.norm(got - gold["aval/" + k]) <= 2e-4 * np.linalg.norm(gold["aval/" + k]), k
     losses = [tr.train_step(*O.synthetic_batch(cfg, 2, 100 + s)) for s in range(3)]
     assert np.allclose(losses, gold["losses3"], rtol=1e-5)
 

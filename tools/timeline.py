@@ -21,6 +21,13 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+# the production library carries no stamps in its main loops: use the -DGCT2_TIMELINE build (make -C csrc timeline)
+_TL = os.path.join(ROOT, "gan_class_transfer2_b200", "libgct2_b200_timeline.so")
+if "GCT2_LIB" not in os.environ:
+    if not os.path.exists(_TL):
+        import subprocess
+        subprocess.run(["make", "-C", os.path.join(ROOT, "gan_class_transfer2_b200", "csrc"), "timeline"], check=True)
+    os.environ["GCT2_LIB"] = _TL
 
 from gan_class_transfer2_b200 import _lib, ops  # noqa: E402
 from tools.bench_layers import layer_table  # noqa: E402
@@ -37,6 +44,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--only", default="")
     ap.add_argument("--debug", action="append", default=[])
+    ap.add_argument("--weights-stable", action="store_true", help="pass GCT2_WEIGHTS_STABLE (early weight fetch)")
     ap.add_argument("--cold-weights", action="store_true",
                     help="flush L2 before the measured launch, then re-touch the activations only: the state a layer "
                          "finds inside a training step (the optimiser has streamed 1.3 GB through L2 since)")
@@ -64,12 +72,12 @@ def main():
         bias = torch.zeros(Cout, device=dev)
         ws = ops.Workspace(256 << 20, dev)
         if kind == "down":
-            passes = {"fprop": lambda: ops.conv4s2_fprop(x, w, bias, y, ws),
-                      "dgrad": lambda: ops.conv4s2_dgrad(dy, w, dx, x, False, ws),
+            passes = {"fprop": lambda: ops.conv4s2_fprop(x, w, bias, y, ws, a.weights_stable),
+                      "dgrad": lambda: ops.conv4s2_dgrad(dy, w, dx, x, False, ws, a.weights_stable),
                       "wgrad": lambda: ops.conv4s2_wgrad(x, dy, dw, ws)}
         else:
-            passes = {"fprop": lambda: ops.convT4s2_fprop(x, w, bias, y, ws),
-                      "dgrad": lambda: ops.convT4s2_dgrad(dy, w, dx, x, Cin, ws),
+            passes = {"fprop": lambda: ops.convT4s2_fprop(x, w, bias, y, ws, a.weights_stable),
+                      "dgrad": lambda: ops.convT4s2_dgrad(dy, w, dx, x, Cin, ws, a.weights_stable),
                       "wgrad": lambda: ops.convT4s2_wgrad(x, dy, dw, ws)}
         for pname, fn in passes.items():
             lib.gct2_debug_set(2, 0)
