@@ -142,6 +142,21 @@ def workload_config(batch_per_gpu: int, world: int):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def synthetic_images(batch: int, size: int, seed: int):
+    """SURVEY.md 8(d) synthetic input: x = k/128 - 1, k ~ U{0..255} i.i.d. -- the value grid of decode_file
+    (train.py:292).  Same generator call as oracle.synthetic_batch, restated here so that the GPU arm does not import
+    the oracle."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    k = torch.randint(0, 256, (batch, size, size, 3), generator=g)
+    return k.to(torch.float32) / 128 - 1
+
+
+def kernel_sources_sha() -> str:
+    from tools.sass_summary import kernel_sources_sha as f
+    return f()
+
+
 def instrumented_step(eng, torch, ops):
     """One eager step with every op bracketed by CUDA events (the GPU is kept busy first so that host launch latency
     is not inside the brackets).  Returns {op name: [durations in us]}."""
@@ -172,7 +187,6 @@ def main():
     ap.add_argument("--batch-per-gpu", type=int, default=1)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--dump-ops", default="", help="write the instrumented step's per-launch (op, us) list here")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -197,8 +211,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        T.data_parallel = DataParallel(overlap=not args.no_overlap,
-                                       shard_optimizer=os.environ.get("GCT2_DP_SHARD", "1") != "0")
+        T.data_parallel = DataParallel(shard_optimizer=os.environ.get("GCT2_DP_SHARD", "1") != "0")
     _lib.init(local)
 
     B = args.batch_per_gpu
@@ -208,8 +221,7 @@ def main():
     trainer.compile(T.optimizer, T.identity)
     eng = denoiser.engine(B, T.size)
 
-    from oracle import oracle as O  # synthetic_batch only: the same images the CPU arm sees (not a compute path)
-    x_cpu, _, _ = O.synthetic_batch(O.DEFAULT, B, 1 + rank)
+    x_cpu = synthetic_images(B, T.size, 1 + rank)  # the same images the CPU arm sees; nothing of oracle/ is imported here
     x_host = x_cpu.pin_memory()
     loss_host = torch.zeros(1).pin_memory()
     eng.set_batch(x_host)
@@ -314,23 +326,40 @@ def main():
     # FLOPs of the tensor-core family = step total minus down0 (fprop+wgrad, CUDA cores) and dense (fwd+2 bwd)
     flops_conv = (GFLOP_PER_IMAGE - 2 * 0.2013 - 3 * 0.0263) * 1e9 * B
     achieved = flops_conv / (conv_us * 1e-6) / 1e12 if conv_us else 0.0
-    traffic = None
+    # DRAM bytes per launch come from an ncu capture (never taken inside a timed run); the file names the kernel
+    # sources it was captured from, and a capture of other sources is not reported
+    traffic, traffic_note = None, "no capture"
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            traffic = json.load(f).get(f"traffic_bytes_per_launch_b{B}")
-    except Exception:  # noqa: BLE001
-        pass
+            tj = json.load(f)
+        if tj.get("kernel_sha") == kernel_sources_sha():
+            traffic, traffic_note = tj.get(f"traffic_bytes_per_launch_b{B}"), tj.get("source")
+        else:
+            traffic_note = f"stale capture (kernels {tj.get('kernel_sha')}, now {kernel_sources_sha()})"
+    except Exception as exc:  # noqa: BLE001
+        traffic_note = f"unreadable: {exc}"
+    # the optimiser: the step's largest HBM consumer (30 bytes per parameter: w, m, v, g read; w, m, v, bf16 shadow written)
+    adam_us = sum(prof.get("adam_apply", [])) + sum(prof.get("adam_keras", []))
+    adam_bytes = 30.0 * eng.P / world if (world > 1 and T.data_parallel.shard_optimizer) else 30.0 * eng.P
+    adam_gbs = adam_bytes / (adam_us * 1e-6) / 1e9 if adam_us else 0.0
     roofline = {"bound": "tensor", "kernel": "conv_umma_kernel<MODE,BN> (tcgen05 implicit-GEMM conv family, "
                                              f"{conv_launches} launches/step)",
                 "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["bf16_sustained"], "traffic": traffic, "peak_source": pk["source"] + " (sustained)",
+                "frac": achieved / pk["bf16_sustained"], "frac_burst": achieved / pk["bf16_burst"],
+                "peak_burst": pk["bf16_burst"], "traffic": traffic, "traffic_source": traffic_note,
+                "peak_source": pk["source"] + " (sustained; frac_burst is against the burst figure)",
                 "how": f"{flops_conv / 1e9:.1f} GFLOP of the family per step / CUDA-event time of its launches replayed "
                        f"back to back from a graph ({fam_launches} launches incl. split-K passes, {reps} replays)",
                 "avg_launch_us": conv_us / max(conv_launches, 1), "family_us_per_step": conv_us,
                 "family_share_of_step": conv_us_eager / max(total_us, 1e-9),
                 "step_achieved": value / world * GFLOP_PER_IMAGE * 1e9 / 1e12,
                 "step_frac": value / world * GFLOP_PER_IMAGE * 1e9 / 1e12 / pk["bf16_sustained"],
-                "per_op_us": {k: round(sum(v), 1) for k, v in prof.items()}}
+                "per_op_us": {k: round(sum(v), 1) for k, v in prof.items()},
+                "kernel_sha": kernel_sources_sha()}
+    roofline_adam = {"bound": "hbm", "kernel": "adam_kernel (Keras-Adam, fp32 state + bf16 shadow)", "achieved": adam_gbs,
+                     "peak": pk["hbm"], "unit": "GB/s", "frac": adam_gbs / pk["hbm"], "traffic": None,
+                     "how": f"{adam_bytes / 1e6:.0f} MB algorithmic (30 B/param) / CUDA-event time of the optimiser launches "
+                            "of one serialised eager step", "us_per_step": adam_us}
 
     def teardown():
         """Captured NCCL collectives keep the communicator busy: drop the graphs first, and never let a stuck
@@ -364,7 +393,8 @@ def main():
                           "api": "train.Trainer.train_step((img_u8_host, img_u8_host)) -- decode_file's bytes, "
                                  "/128-1 on the device (SURVEY 8 f2)"},
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
-            "cuda_graph": not args.no_graph, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "cuda_graph": not args.no_graph, "clocks": clocks, "roofline": roofline, "roofline_adam": roofline_adam,
+            "cpu_baseline": cpu,
             "final_loss": final_loss}
     print(json.dumps(line), flush=True)
     teardown()

@@ -44,6 +44,7 @@ _PROTOS = {
     "gct2_debug_timeline": (c_int, [_P, c_int]),
     "gct2_debug_last_plan": (None, [_P]),
     "gct2_set_sm_budget": (None, [c_int]),
+    "gct2_set_adam_sms": (None, [c_int]),
     "gct2_debug_trace": (c_int, [_P, c_int]),
     "gct2_noise_images": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "gct2_conv4s2_c3_fprop": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),

@@ -64,6 +64,7 @@ int gct2_debug_trace(unsigned long long* host, int max_records) { return debug_r
 int gct2_debug_timeline(unsigned long long* host, int max_ctas) { return debug_read_timeline(host, max_ctas); }
 void gct2_debug_last_plan(int* out8) { debug_last_plan(out8); }
 void gct2_set_sm_budget(int sms) { conv_set_sm_budget(sms); }
+void gct2_set_adam_sms(int sms) { elementwise_set_adam_sms(sms); }
 
 void gct2_debug_set(int key, int value) {
   if (key == 3)

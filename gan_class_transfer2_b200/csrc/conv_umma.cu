@@ -417,13 +417,12 @@ static Choice choose(const DeviceState& ds, int mode, int mTiles, int phases, in
       const long long items = (long long)mTiles * phases * (isW ? 16 : 1) * nTiles * splits;
       const long long active = items < maxCtas ? items : maxCtas;
       const long long waves = (items + active - 1) / active;
-      // one 64-wide k-chunk: issue-bound at small grids (a ring round = wait + commit + 4 UMMAs per chunk: measured
-      // 470 / 525 / 655 cycles per chunk with one chunk per round at BN = 64 / 128 / 256; two chunks share the round at
-      // BN <= 128), never below the tensor pipe's 2*BN cycles, and bound by the chip-wide L2 -> SM rate (~6000 B/clk)
-      // when every SM pulls at once
-      double tk = kps_for(BN) == 2 ? 290.0 : 408.0 + 0.96 * BN;
-      if (tk < 2.1 * BN) tk = 2.1 * BN;
-      const double l2 = (16384.0 + BN * 128.0) * (double)active / 6000.0;
+      // one 64-wide k-chunk in steady state, measured per CTA with tools/timeline.py (round 2, two chunks per ring slot
+      // at BN <= 128): 285 / 375 / 665 cycles at BN = 64 / 128 / 256 against tensor floors of 128 / 256 / 512 -- every
+      // shape ingests ~86 bytes per clock per SM (A is re-read for every 64 columns of N, so narrow tiles pay more per
+      // FLOP) -- and bound by the chip-wide L2 -> SM rate (~10 KB/clk with the L2 coalescing identical tile requests) when every SM pulls at once
+      double tk = BN == 64 ? 285.0 : (BN == 128 ? 375.0 : 665.0);
+      const double l2 = (16384.0 + BN * 128.0) * (double)active / 10000.0;  // measured: 128 CTAs at BN = 64 sustain 10.5 KB/clk
       if (l2 > tk) tk = l2;
       const double main = kIters * tk;
       // rows of a 128-row tile that hold real pixels (deep layers at batch 1 have 16 .. 64)

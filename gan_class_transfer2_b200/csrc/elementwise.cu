@@ -25,6 +25,7 @@ void elementwise_set_debug(int key, int value) {
   if (key == 23) g_adam_sms = value > 0 ? value : 0;
 }
 void elementwise_set_sms(int n) { g_ew_sms = n; }
+void elementwise_set_adam_sms(int n) { g_adam_sms = n > 0 ? n : 0; }
 
 #define GCT2_CHECK_LAUNCH(name)                                       \
   do {                                                                \

@@ -7,6 +7,7 @@ namespace gct2 {
 
 void elementwise_set_sms(int n);
 void elementwise_set_debug(int key, int value);
+void elementwise_set_adam_sms(int n);  // see gct2_set_adam_sms
 int noise_images(const float* x, const float* eps, const int* t_int, float* noised, int B, int elemsPerImage,
                  int steps, cudaStream_t st);
 int conv4s2_c3_fprop(const float* x, const float* w, const float* bias, __nv_bfloat16* y, int ldy, int B, int H,

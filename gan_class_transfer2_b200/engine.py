@@ -179,15 +179,13 @@ def shard_batch(global_batch: int, world: int, rank: int) -> Tuple[int, int]:
 class DataParallel:
     """Data-parallel context: the batch shards over ranks, gradient buckets are summed with NCCL."""
 
-    def __init__(self, group=None, bucket_bytes: int = 48 << 20, overlap: bool = True,
-                 shard_optimizer: bool = True):
+    def __init__(self, group=None, bucket_bytes: int = 48 << 20, shard_optimizer: bool = True):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.bucket_bytes = bucket_bytes
-        self.overlap = overlap
         #: SURVEY.md 8(e) "optimisation": per bucket, reduce-scatter the fp32 gradients, run Keras-Adam on this rank's
         #: 1/N slice only, all-gather the bf16 weights the tensor-core kernels read.  0.75x the bytes of an fp32
         #: all-reduce on the wire and 1/N of the optimiser's HBM traffic per GPU.  The fp32 masters of the other ranks'
@@ -215,6 +213,13 @@ class UNetEngine:
         #: its prologue.  With the optimiser on the main stream (test hook GCT2_OVERLAP=none|wgrad) an Adam launch could
         #: still be draining under programmatic dependent launch, and the flag stays off.
         self.weights_stable = self.overlap_adam and os.environ.get("GCT2_WEIGHTS_EARLY", "1") != "0"
+        #: Keras-Adam beside backward on disjoint SMs (single GPU): the optimiser is HBM-bound and draws ~98 GB/s per SM,
+        #: the tensor-core launches of backward need no HBM bandwidth to speak of -- so the first `adam_wide_buckets`
+        #: gradient buckets (backward order: up0 .. up{n-1}, down{n-1} ..) are updated by `adam_sms` SM-exclusive CTAs
+        #: while the conv launches keep to the other SMs (gct2_set_sm_budget); the remaining buckets, complete only when
+        #: backward is over, use the whole chip.  0 = the optimiser always uses the whole chip (takes turns with the convs).
+        self.adam_sms = int(os.environ.get("GCT2_ADAM_SMS", "48"))
+        self.adam_wide_buckets = int(os.environ.get("GCT2_ADAM_WIDE", "5"))
         self._side = torch.cuda.Stream(device=self.device)
         self._side_adam = torch.cuda.Stream(device=self.device)
         self._graph = None
@@ -281,7 +286,7 @@ class UNetEngine:
         self.ws_w = ops.Workspace(64 << 20, dev)
         self.global_batch = B * (dp.world if dp else 1)
         # gradient buckets: all-reduce granularity (data parallel) and the granularity at which Adam chases backward
-        local_bucket = int(float(os.environ.get("GCT2_BUCKET_MB", "24")) * (1 << 20))  # test hook: Adam granularity
+        local_bucket = int(float(os.environ.get("GCT2_BUCKET_MB", "8")) * (1 << 20))  # Adam granularity (8 MB: per layer)
         self._buckets = grad_buckets(cfg, dp.bucket_bytes if dp else local_bucket)
         layers = [f"down{i}" for i in range(n)] + [f"up{i}" for i in range(n)]
         self._bias_plan = ops.BiasGradPlan([self.gdown_out(i) for i in range(n)] + [self.gup_out(i) for i in range(n)],
@@ -389,6 +394,11 @@ class UNetEngine:
         sa = self._side_adam if self.overlap_adam else main
         dp = self.dp if (self.dp and self.dp.world > 1) else None
         pending = []
+        from . import _lib
+        num_sms = _lib.load().gct2_num_sms()
+        # [wide buckets left, conv SM budget active]
+        side = [self.adam_wide_buckets if (apply_adam and dp is None and sa is not main and 0 < self.adam_sms < num_sms)
+                else 0, False]
 
         def on_side(fn):
             if sw is main:
@@ -449,12 +459,21 @@ class UNetEngine:
                         sa.wait_stream(sw)
                 elif sw is not main:
                     main.wait_stream(sw)
+                wide = side[0] > 0 and start != 0
                 with torch.cuda.stream(sa):
                     if work is not None:
                         work.wait()
+                    ops.set_adam_sms(self.adam_sms if wide else 0)
                     ops.adam_apply(self.w[start:end], self.m[start:end], self.v[start:end], self.g[start:end],
                                    self.w16[start:end], self.hyper, cfg.beta1, cfg.beta2, cfg.epsilon, 1.0,
                                    iterations_inc=self.iterations if (inc_iterations and start == 0) else None)
+                    ops.set_adam_sms(0)
+                if wide:
+                    side[0] -= 1
+                    if not side[1]:
+                        # from here to the end of backward the conv launches leave the optimiser's SMs alone
+                        ops.set_sm_budget(num_sms - self.adam_sms)
+                        side[1] = True
 
         for i in range(n):  # up0 .. up{n-1}
             on_side(lambda: ops.convT4s2_wgrad(self.up_in_buf(i), self.gup_out(i), self.view(self.g, f"up{i}/kernel"),
@@ -473,6 +492,8 @@ class UNetEngine:
         ops.conv4s2_c3_wgrad(self.noised, self.gdown_out(0), self.view(self.g, "down0/kernel"), None, accumulate=True)
         # every conv layer's BiasAddGrad in one launch: the pre-activation gradients all still sit in their buffers
         ops.bias_grad_multi(self._bias_plan, accumulate=True)
+        if side[1]:
+            ops.set_sm_budget(0)
         bucket_done("down0/kernel")
         if sw is not main:
             main.wait_stream(sw)

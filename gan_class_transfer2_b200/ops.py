@@ -37,6 +37,11 @@ def set_sm_budget(sms: int) -> None:
     _lib.load().gct2_set_sm_budget(int(sms))
 
 
+def set_adam_sms(sms: int) -> None:
+    """SMs of the following adam_apply launches (0 = whole chip); see gct2_set_adam_sms."""
+    _lib.load().gct2_set_adam_sms(int(sms))
+
+
 #: when a list, every op appends (op name, start event, end event) -- bench.py's per-kernel timing pass
 _profile = None
 

@@ -135,6 +135,18 @@ class Sequential(Layer):
         return self.layers
 
 
+#: one advancing generator for layers that are built standalone (outside a Denoiser): Keras draws every glorot kernel
+#: independently, so two layers of equal shape must not start from equal kernels
+_init_generator: Optional[torch.Generator] = None
+
+
+def _next_init_generator() -> torch.Generator:
+    global _init_generator
+    if _init_generator is None:
+        _init_generator = torch.Generator().manual_seed(torch.initial_seed() % (2 ** 31))
+    return _init_generator
+
+
 class _ConvLayer(Layer):
     """Common part of the two stride-2 4x4 layers: lazily created glorot-uniform kernel in the Keras layout, zero bias
     (train.py:149,162), bf16 shadow for the tensor cores."""
@@ -157,7 +169,7 @@ class _ConvLayer(Layer):
         cin = input_shape[-1]
         shape = (4, 4, self.filters, cin) if self.transposed else (4, 4, cin, self.filters)
         if self.kernel is None:
-            self.kernel = glorot_uniform(shape, torch.Generator().manual_seed(torch.initial_seed() % (2 ** 31))).cuda()
+            self.kernel = glorot_uniform(shape, _next_init_generator()).cuda()
             self.bias = torch.zeros(self.filters, device="cuda")
 
     def _shadow(self):
@@ -250,8 +262,7 @@ class Dense(Layer):
 
     def build(self, input_shape):
         if self.kernel is None:
-            gen = torch.Generator().manual_seed(torch.initial_seed() % (2 ** 31))
-            self.kernel = glorot_uniform((input_shape[-1], self.units), gen).cuda()
+            self.kernel = glorot_uniform((input_shape[-1], self.units), _next_init_generator()).cuda()
             self.bias = torch.zeros(self.units, device="cuda")
 
 
@@ -325,11 +336,15 @@ class Denoiser(Model):
         self._engines: Dict[tuple, UNetEngine] = {}
         self._seed = 0
         self._pending_weights: Optional[Dict[str, torch.Tensor]] = None
+        self._optimizer: Optional[Adam] = None  # set by Trainer.compile; None -> the module-level `optimizer`
 
     # -- structure ---------------------------------------------------------------------------------------------
     def _walk(self):
         """Pattern-matches the layer tree against the one shape the fused engine implements and returns
         (down layers outer->inner, up layers outer->inner, dense)."""
+        if residual or not concat:
+            raise NotImplementedError("the fused engine implements the reference's default skip wiring only "
+                                      "(residual=False, concat=True, train.py:26-27,113-119)")
         outer = self.middle.layers
         if not (len(outer) == 4 and isinstance(outer[0], Block) and isinstance(outer[1], Residual)
                 and isinstance(outer[2], Block) and isinstance(outer[3], Dense) and outer[3].units == 3):
@@ -351,11 +366,25 @@ class Denoiser(Model):
 
     def net_config(self, image_size: int) -> NetConfig:
         downs, ups, _ = self._walk()
-        base_lr, warm = optimizer.schedule()
+        opt = self._optimizer if self._optimizer is not None else optimizer
+        base_lr, warm = opt.schedule()
         return NetConfig(size=image_size, pixel_size=pixel_size, max_size=max_size, octaves=len(downs), steps=steps,
-                         warm_up=warm, base_lr=base_lr, beta1=optimizer.beta_1, beta2=optimizer.beta_2,
-                         epsilon=optimizer.epsilon, down_filters=tuple(d.filters for d in downs),
+                         warm_up=warm, base_lr=base_lr, beta1=opt.beta_1, beta2=opt.beta_2,
+                         epsilon=opt.epsilon, down_filters=tuple(d.filters for d in downs),
                          up_filters=tuple(u.filters for u in ups))
+
+    def use_optimizer(self, opt: "Adam") -> None:
+        """The optimiser the engines are built with (Trainer.compile hands over the one it was given, train.py:511-514)."""
+        if not isinstance(opt, Adam):
+            raise NotImplementedError("only tf.keras.optimizers.Adam (train.py:75) is implemented on the device")
+        if self._engines:
+            cur = self._optimizer if self._optimizer is not None else optimizer
+            same = (cur.schedule() == opt.schedule() and (cur.beta_1, cur.beta_2, cur.epsilon) ==
+                    (opt.beta_1, opt.beta_2, opt.epsilon))
+            if not same:
+                raise RuntimeError("the training engine has already been built with another optimiser; compile() before "
+                                   "the first step")
+        self._optimizer = opt
 
     def engine(self, batch: int, image_size: int) -> UNetEngine:
         key = (batch, image_size)
@@ -421,7 +450,8 @@ class Denoiser(Model):
         B, H, W, C = x.shape
         if C != 3 or H != W:
             raise ValueError("Denoiser expects square NHWC images with 3 channels")
-        return self.engine(B, H).denoise(x.to("cuda", torch.float32))
+        # a fresh tensor per call, like Keras (the engine's own buffer is overwritten by the next call / graph replay)
+        return self.engine(B, H).denoise(x.to("cuda", torch.float32)).clone()
 
     def __call__(self, input, training=None):
         return self.call(input)
@@ -435,6 +465,11 @@ class Trainer(Model):
         self.denoiser = denoiser
         self.optimizer = optimizer
         self.compiled_loss = identity
+
+    def compile(self, optimizer, loss):
+        """train.py:511-514.  The optimiser given here -- not the module-level one -- parameterises the device update."""
+        super().compile(optimizer, loss)
+        self.denoiser.use_optimizer(optimizer)
 
     def _engine_for(self, x) -> UNetEngine:
         B, H, W, C = x.shape
@@ -455,7 +490,7 @@ class Trainer(Model):
         eng.loss.zero_()
         ops.noise_images(eng.x, eng.eps, eng.t_int, eng.noised, eng.cfg.steps)  # forward-only call: torch's draws
         eng._forward(want_pred=True, backward=False, inv_n=1.0 / (eng.global_batch * eng.cfg.size ** 2 * 3))
-        return eng.loss[0]
+        return eng.loss[0].clone()
 
     def __call__(self, x, training=None, **kw):
         return self.call(x, **kw)
@@ -472,6 +507,9 @@ class Trainer(Model):
             loss = eng.train_step_u8(x)[0]
         else:
             loss = eng.train_step(x, t_int, epsilon)[0]
+        # a fresh scalar per step, like Keras: the engine's loss buffer is overwritten by the next replay (one 4-byte
+        # device-to-device copy; a list of per-step losses keeps its values)
+        loss = loss.clone()
         # identity (train.py:171-173) is the mean of an already-scalar loss: skip the extra launch
         return {"loss": loss if self.compiled_loss is identity else self.compiled_loss(None, loss)}
 

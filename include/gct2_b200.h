@@ -52,7 +52,7 @@ long long gct2_launch_count(void);
  * cap of the down0 weight-gradient kernel (0 = 2 blocks per SM), key 16 = which point of the TMA producer's start-up
  * timeline stamp [7] records, key 19 = CTA pairs (cta_group::2): 0 heuristic, 1 wherever legal, 2 never, key 20 =
  * split-K rendezvous watchdog in polls of ~40 ns (0 = none; default 2^28), key 21 != 0 = never fetch weights before the
- * programmatic dependency resolves, key 22 = gct2_set_sm_budget. */
+ * programmatic dependency resolves, key 22 = gct2_set_sm_budget, key 23 = gct2_set_adam_sms. */
 void gct2_debug_set(int key, int value);
 /* Test hook: after gct2_debug_set(7, 1) every tensor-core conv launch records, per CTA, 8 %globaltimer stamps (ns):
  * [0] entry, [1] prologue done, [2] first operands landed, [3] MMAs of the first tile issued, [4] first accumulator
@@ -65,6 +65,11 @@ void gct2_debug_last_plan(int* out8);
 /* CTAs (= SMs) a tensor-core conv launch may occupy; 0 = all.  Data-parallel callers leave room for the NCCL kernels
  * that run beside backward, so that a conv launch never queues a second wave behind them. */
 void gct2_set_sm_budget(int sms);
+/* SMs of the following gct2_adam_apply launches: 0 = the whole chip (many small blocks); n > 0 = n CTAs of 1024 threads,
+ * each alone on its SM (it requests most of the SM's shared memory), the form that runs BESIDE the tensor-core launches
+ * of backward on disjoint SMs (measured: ~98 GB/s of optimiser traffic per SM up to 48 SMs, 5.8 TB/s from 64).  Both
+ * forms compute bit-identical results. */
+void gct2_set_adam_sms(int sms);
 /* Test hook: after gct2_debug_set(11, 1) the first and last block of EVERY launch of this library append
  * {kernel id, blockIdx | gridDim << 32, entry ns, exit ns}; this call synchronises, copies up to max_records records
  * (4 x u64 each) to `host`, clears the buffer and returns the count.  Kernel ids: 1 noise, 2 step_begin, 3/4 down0

@@ -97,6 +97,9 @@ def main():
             t0 = t[:, 0].min()
             rel = (t - t0) / 1e3
             ok = t[:, 6] > 0
+            # BAR.SYNC defers its blocking to the next consumer, so thread 0's "CTA done" stamp [6] can be taken before
+            # the epilogue warps arrive: a CTA is done no earlier than its first epilogue [5]
+            rel[:, 6] = np.maximum(rel[:, 6], rel[:, 5])
 
             def st(col_a, col_b):
                 d = rel[ok, col_b] - rel[ok, col_a]
