@@ -71,7 +71,7 @@ void gct2_debug_set(int key, int value) {
     g_force_bn = value;
   else if (key == 4)
     g_force_splits = value;
-  else if (key == 13 || key == 15 || key == 23)
+  else if (key == 13 || key == 15 || key == 23 || key == 24)
     elementwise_set_debug(key, value);
   else
     conv_set_debug(key, value);

@@ -27,6 +27,11 @@ static int g_fuse_finish = 1;          // debug key 12 != 0 disables the in-kern
 static int g_cap_w = 0, g_cap_sp = 0;  // debug keys 9 / 10: CTA budget of wgrad / dgrad launches (0 = all SMs)
 static int g_sm_budget = 0;            // key 22 / gct2_set_sm_budget: CTAs any conv launch may occupy (0 = all SMs)
 static int g_b_early = 1;              // debug key 21 != 0 disables the weight fetch before griddepcontrol.wait
+static int g_no_l2_finish = 0;         // key 26 != 0: never finish split-K with the L2 rendezvous (it needs every CTA of the
+                                       // launch resident at once, which nothing guarantees beside NCCL kernels); the
+                                       // cluster form and the finishing kernel remain
+static int g_csplit = 0;               // debug key 25: split-K inside a cluster (DSMEM): 0 = when the cost model picks it,
+                                       // 1 = never (partials through L2), 2 = whenever legal
 static unsigned g_spin_limit = 1u << 28;  // debug key 20: rendezvous watchdog in polls of ~40 ns (default ~10 s; 0 = none)
 static int g_stamp_pos = 0;            // debug key 16 (-DGCT2_TIMELINE builds): see ConvParams::stampPos
 static long long g_launches = 0;
@@ -59,6 +64,7 @@ struct DeviceState {
   int* cnt = nullptr;
   size_t cnt_next = 0;
   int max_pairs[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};  // co-resident 2-CTA clusters [mode][BN index] (0 = unsupported)
+  int max_clusters[2][3][4] = {};  // co-resident clusters of 2 / 4 / 8 plain CTAs [mode S|P][BN index][log2 size]
 };
 static DeviceState g_dev[MAX_DEVICES];
 static DeviceState* cur_dev() {
@@ -127,6 +133,8 @@ void conv_set_debug(int key, int value) {
   if (key == 20) g_spin_limit = (unsigned)value;
   if (key == 21) g_b_early = value ? 0 : 1;
   if (key == 22) conv_set_sm_budget(value);
+  if (key == 25) g_csplit = value;
+  if (key == 26) g_no_l2_finish = value;
   if (key == 7) {
     if (value && g_dbg == nullptr &&
         cudaMalloc(&g_dbg, (size_t)DBG_MAX_CTAS * 8 * sizeof(unsigned long long)) != cudaSuccess) {
@@ -347,6 +355,7 @@ static int kps_for(int BN) { return BN == 256 ? 1 : 2; }
 struct Choice {
   int BN, splits;
   int pair = 0;
+  int csplit = 0;  // the splits are the CTAs of one cluster (partials through distributed shared memory)
 };
 
 static int bn_index(int BN) { return BN == 64 ? 0 : (BN == 128 ? 1 : 2); }
@@ -372,7 +381,32 @@ static void query_pairs(DeviceState& ds) {
   ds.max_pairs[MODE][bn_index(BN)] = n;
 }
 
+template <int MODE, int BN>
+static void query_clusters(DeviceState& ds) {
+  for (int lg = 1; lg <= 3; ++lg) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((1 << lg) * 16);
+    cfg.blockDim = dim3(kConvThreads<BN>());
+    cfg.dynamicSmemBytes = smem_for(BN, false);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1 << lg;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, conv_umma_kernel<MODE, BN, 0>, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      n = 0;
+    }
+    ds.max_clusters[MODE][bn_index(BN)][lg] = n;
+  }
+}
+
 static void query_all_pairs(DeviceState& ds) {
+  query_clusters<MODE_S, 64>(ds); query_clusters<MODE_S, 128>(ds); query_clusters<MODE_S, 256>(ds);
+  query_clusters<MODE_P, 64>(ds); query_clusters<MODE_P, 128>(ds); query_clusters<MODE_P, 256>(ds);
   query_pairs<MODE_S, 128>(ds); query_pairs<MODE_S, 256>(ds);
   query_pairs<MODE_P, 128>(ds); query_pairs<MODE_P, 256>(ds);
   query_pairs<MODE_W, 128>(ds); query_pairs<MODE_W, 256>(ds);
@@ -429,11 +463,25 @@ static Choice choose(const DeviceState& ds, int mode, int mTiles, int phases, in
       double validRows = isW ? 128.0 : (double)outElems / ((double)N * mTiles * phases);
       if (validRows > 128.0) validRows = 128.0;
       double epi;
+      int useCluster = 0;
       if (splits > 1 && !isW) {
         // partial tile to its slab and back through L2 (~14.5 B/clk per CTA each way) + the rendezvous
         epi = 5000.0 + 2.0 * validRows * BN * 4.0 / 14.5;
         // finished by a separate kernel: a launch + every slab read once more, at the chip-wide rate
-        if (items > maxCtas) epi += 6000.0 + (double)outElems * 4.0 * (splits + 0.5) / 3000.0;
+        if (items > maxCtas || !g_fuse_finish || g_no_l2_finish) epi += 6000.0 + (double)outElems * 4.0 * (splits + 0.5) / 3000.0;
+        // the splits as one cluster: partial tile to the CTA's own shared memory, each CTA reads 128/splits rows of
+        // every peer through DSMEM; no global traffic, no residency requirement beyond the cluster itself
+        int lg = 0;
+        while ((1 << lg) < splits) ++lg;
+        const int clusters = (splits <= 8 && g_csplit != 1 && g_fuse_finish) ? ds.max_clusters[mode][bn_index(BN)][lg] : 0;
+        if (clusters > 0) {
+          const double epiC = 2500.0 + 20.0 * BN;
+          const bool fits = g_sm_budget == 0 || items <= maxCtas;
+          if (fits && (epiC < epi || g_csplit == 2)) {
+            epi = epiC;
+            useCluster = 1;
+          }
+        }
       } else if (isW) {
         epi = 35.0 * BN;                                // fp32 tile straight to HBM
         if (splits > 1) epi += 5000.0 + (double)outElems * 4.0 * (splits + 1.0) / 3000.0;  // + reduction kernel
@@ -441,11 +489,24 @@ static Choice choose(const DeviceState& ds, int mode, int mTiles, int phases, in
         epi = dgradEpi ? 600.0 + 30.0 * BN : 1000.0 + 15.0 * BN;
         epi *= 0.25 + 0.75 * validRows / 128.0;
       }
+      long long wavesEff = waves;
+      if (useCluster) {
+        int lg = 0;
+        while ((1 << lg) < splits) ++lg;
+        long long cap = (long long)ds.max_clusters[mode][bn_index(BN)][lg] * splits;
+        if (cap > maxCtas) cap = maxCtas - maxCtas % splits;
+        if (cap < splits) cap = splits;
+        wavesEff = (items + cap - 1) / cap;
+        // a cluster launch always has one CTA per work item: under an SM budget (room left for NCCL / the optimiser) it is
+        // only used when it fits the budget in one wave
+      }
       // fixed per launch: prologue 0.7 us + first loads 1.45 us + teardown 0.25 us
-      const double cost = 4800.0 + waves * main + epi + (waves - 1) * (epi > main ? epi - main : 0.0);
+      const double cost = 4800.0 + (useCluster ? 600.0 : 0.0) + wavesEff * main + epi * (useCluster ? wavesEff : 1) +
+                          (useCluster ? 0.0 : (waves - 1) * (epi > main ? epi - main : 0.0));
       if (cost < bestCost) {
         bestCost = cost;
         best = Choice{BN, splits};
+        best.csplit = useCluster;
       }
     }
   }
@@ -455,6 +516,7 @@ static Choice choose(const DeviceState& ds, int mode, int mTiles, int phases, in
 template <int MODE, int BN, int PAIR = 0>
 static cudaError_t launch_one(int grid, size_t smem, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b,
                               const ConvParams& p) {
+  const int clusterSize = PAIR ? 2 : (p.csplit ? p.splits : 1);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kConvThreads<BN>());
@@ -463,9 +525,9 @@ static cudaError_t launch_one(int grid, size_t smem, cudaStream_t st, const CUte
   cudaLaunchAttribute at[2];
   cfg.attrs = at;
   cfg.numAttrs = 0;
-  if (PAIR) {
+  if (clusterSize > 1) {
     at[cfg.numAttrs].id = cudaLaunchAttributeClusterDimension;
-    at[cfg.numAttrs].val.clusterDim.x = 2;
+    at[cfg.numAttrs].val.clusterDim.x = clusterSize;
     at[cfg.numAttrs].val.clusterDim.y = 1;
     at[cfg.numAttrs].val.clusterDim.z = 1;
     ++cfg.numAttrs;
@@ -556,8 +618,10 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     // the cluster launch costs more than the shared B tile saves -- hence only for launches of more than one wave)
     const long long itemsPlain = (long long)pixTiles * (N / c.BN) * phases * c.splits;
     if ((g_pair == 1 || (g_pair == 0 && itemsPlain > maxCtas)) && c.BN >= 128 && pixTiles % 2 == 0 &&
-        ds.max_pairs[a.mode][bn_index(c.BN)] > 0)
+        ds.max_pairs[a.mode][bn_index(c.BN)] > 0) {
       c.pair = 1;
+      c.csplit = 0;  // a cluster is either a cta_group::2 pair or the K slices of one tile
+    }
     BN = c.BN;
     p.mTiles = pixTiles;
     p.nTiles = N / BN;
@@ -586,7 +650,9 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
       // other); otherwise a finishing kernel sums the slabs
       int resident = maxCtas;  // CTAs of this launch that can be on the chip at once
       if (c.pair && ds.max_pairs[a.mode][bn_index(BN)] * 2 < resident) resident = ds.max_pairs[a.mode][bn_index(BN)] * 2;
-      p.fused = (g_fuse_finish && p.numItems <= resident && (size_t)p.numTiles * 2 <= (size_t)CNT_RING_INTS / 4) ? 1 : 0;
+      p.csplit = c.csplit;
+      p.fused = (!c.csplit && g_fuse_finish && !g_no_l2_finish && p.numItems <= resident &&
+                 (size_t)p.numTiles * 2 <= (size_t)CNT_RING_INTS / 4) ? 1 : 0;
       p.realEpi = a.epi;
       if (p.fused) {
         // this launch's own counter region (zero at rest: the last split through the rendezvous re-arms it)
@@ -668,7 +734,7 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     p.fdKcPer = make_fastdiv((uint32_t)(p.kcPer > 0 ? p.kcPer : 1));
   }
   const size_t smem = smem_for(BN, p.cm == 2);
-  p.numClusterItems = p.numItems / p.cm;
+  p.numClusterItems = p.csplit ? p.numItems / p.splits : p.numItems / p.cm;
   int ctas = maxCtas;  // one CTA per SM (194 KB of shared memory, 61 K registers)
   if (p.cm == 2) {
     const int mp = ds.max_pairs[a.mode][bn_index(BN)] * 2;
@@ -676,14 +742,17 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
   }
   int grid = p.numItems < ctas ? p.numItems : ctas;
   grid -= grid % p.cm;
-  g_last_plan[0] = BN; g_last_plan[1] = p.splits; g_last_plan[2] = p.cm == 2; g_last_plan[3] = p.fused;
+  // cluster split-K: exactly one tile per cluster (its partial tile lives in the ring's shared memory, so a CTA must
+  // not start loading another item); clusters beyond the chip's capacity simply run in waves
+  if (p.csplit) grid = p.numItems;
+  g_last_plan[0] = BN; g_last_plan[1] = p.splits; g_last_plan[2] = p.cm == 2; g_last_plan[3] = p.csplit ? 2 : p.fused;
   g_last_plan[4] = grid; g_last_plan[5] = stages_for(BN, p.cm == 2); g_last_plan[6] = p.rounds; g_last_plan[7] = p.bEarly;
   if (g_verbose)
     fprintf(stderr,
             "gct2 conv mode %d B %d lo %dx%d tile %dx%dx%d BN %d splits %d pair %d kIters %d rounds %d items %d grid %d "
-            "stages %d fused %d early %d\n",
+            "stages %d finish %s early %d\n",
             a.mode, a.B, a.Hlo, a.Wlo, p.Nb, p.Ht, p.Wt, BN, p.splits, p.cm == 2, p.kIters, p.rounds, p.numItems, grid,
-            stages_for(BN, p.cm == 2), p.fused, p.bEarly);
+            stages_for(BN, p.cm == 2), p.csplit ? "cluster" : (p.fused ? "l2" : (p.splits > 1 ? "kernel" : "-")), p.bEarly);
 #ifdef GCT2_TIMELINE
   if (g_dbg != nullptr && grid <= DBG_MAX_CTAS) {
     cudaMemsetAsync(g_dbg, 0, (size_t)grid * 8 * sizeof(unsigned long long), stream);
@@ -703,7 +772,7 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     return 1;
   }
   count_launch();
-  if (a.mode != MODE_W && p.splits > 1 && !p.fused) {
+  if (a.mode != MODE_W && p.splits > 1 && !p.fused && !p.csplit) {
     const long long pixels = (long long)a.B * p.Hout * p.Wout;
     const long long total = pixels * (p.N / 4);
     int blocks = (int)((total + 255) / 256);

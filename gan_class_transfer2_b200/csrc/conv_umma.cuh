@@ -89,6 +89,9 @@ struct ConvParams {
   int cm;                      // CTAs per cluster: 1, or 2 for a cta_group::2 pair (two consecutive M tiles of one
                                // (phase, N tile, split) share their B tile)
   int numClusterItems;         // numItems / cm
+  int csplit;                  // split-K inside a thread-block cluster: the `splits` CTAs of a cluster own the K slices of ONE
+                               // tile, keep their partial accumulators in their own shared memory and each finishes
+                               // 128/splits rows by reading its peers' partials through distributed shared memory
   int fused;                   // split-K finished inside this launch (tile-major slabs + arrive/depart counters)
   int realEpi;                 // fused: the epilogue to apply after the slabs are summed (EPI_BIAS_RELU / EPI_DGRAD)
   int numTiles;                // fused: phases * nTiles * mTiles
@@ -123,10 +126,19 @@ struct WorkItem {
   int mt, nt, ph, split;       // ph: phase (P) or tap (W)
 };
 
-// item = index of a cluster item (cm consecutive M tiles); rm = this CTA's rank inside its cluster.
+// item = index of a cluster item; rm = this CTA's rank inside its cluster.  Pairs: a cluster item is two consecutive M
+// tiles and rm picks one; cluster split-K: a cluster item is one tile and rm is the K slice.
 template <int MODE>
 __device__ __forceinline__ WorkItem decode_item(const ConvParams& p, int item, int rm) {
   WorkItem w;
+  if (p.csplit) {
+    w.mt = fd_mod(p.fdMTilesC, item);
+    const int r = fd_div(p.fdMTilesC, item);
+    w.nt = fd_mod(p.fdNTiles, r);
+    w.ph = fd_div(p.fdNTiles, r);
+    w.split = rm;
+    return w;
+  }
   w.mt = fd_mod(p.fdMTilesC, item) * p.cm + rm;
   int r = fd_div(p.fdMTilesC, item);
   if (MODE == MODE_W) {
@@ -293,7 +305,8 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
   uint64_t* empty = full + S;
   uint64_t* tfull = empty + S;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* red_full = tempty + 2;  // cluster split-K: every peer's partial tile is in its shared memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(red_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -302,9 +315,10 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
   const unsigned long long t_entry = (p.dbg != nullptr && threadIdx.x == 0) ? globaltimer_ns() : 0ull;
 #endif
 
-  const int rm = pair ? (int)cluster_ctarank() : 0;
-  const int clusterId = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int numClusters = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const bool csplit = !pair && MODE != MODE_W && p.csplit != 0;
+  const int rm = (pair || csplit) ? (int)cluster_ctarank() : 0;
+  const int clusterId = pair ? (int)(blockIdx.x >> 1) : (csplit ? fd_div(p.fdSplits, (int)blockIdx.x) : (int)blockIdx.x);
+  const int numClusters = pair ? (int)(gridDim.x >> 1) : (csplit ? fd_div(p.fdSplits, (int)gridDim.x) : (int)gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
@@ -320,6 +334,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
       // pair: the leader's accumulator buffer is free once the epilogues of BOTH CTAs have drained theirs
       mbar_init(&tempty[i], (pair ? 2 : 1) * kEpilogueWarps<BN>());
     }
+    mbar_init(red_full, (uint32_t)(p.splits * kEpilogueWarps<BN>()));  // one arrival per epilogue warp of every peer
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -333,7 +348,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
   }
   tc_fence_before();
   __syncthreads();
-  if (pair) cluster_sync_all();  // the peer's barriers are initialised before anyone signals them
+  if (pair || csplit) cluster_sync_all();  // the peers' barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -610,7 +625,17 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
             // split-K partial: plain stores into this split's slab (no atomics: the finishing pass sums the slabs in
             // a fixed order, so the step is bit-reproducible)
             tmem_ld_wait();
-            if (valid) {
+            if (csplit) {
+              // cluster split-K: the partial tile goes to THIS CTA's shared memory (the ring is idle: every MMA of the
+              // CTA's only work item has completed), rows of BN floats with the 16-byte chunks XOR-swizzled by the row
+              // so that the 32 lanes of a warp (32 rows, same chunk) spread over all banks
+              float4* rowp = reinterpret_cast<float4*>(smem) + (size_t)r * (BN / 4);
+              const int ch0 = (cgrp * COLS + c0) >> 2;
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                rowp[(ch0 + g) ^ (r & 7)] = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
+                                                         __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+            } else if (valid) {
               // fused finish: tile-major slab [split][tile][row][col] (compact, read back coalesced below);
               // finishing kernel: pixel-major slab [split][pixel][N]
               float4* dst = reinterpret_cast<float4*>(
@@ -640,27 +665,39 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
         }
         tc_fence_before();
         __syncwarp();
-        if (p.fused) {
-          // ---- split-K finished in place.  Every split of this tile has its own CTA, all resident at once (the
-          // host only fuses when the grid holds one item per CTA), so they can wait for each other: once all `splits`
-          // partial tiles are in the slabs, split s sums rows [s*R, (s+1)*R) over the slabs in split order (bit-
-          // reproducible), applies the real epilogue and writes the bf16 output -- coalesced, no extra launch.
+        if (p.fused || csplit) {
+          // ---- split-K finished in place: split s sums rows [s*R, (s+1)*R) of the tile over all partials in split
+          // order (bit-reproducible), applies the real epilogue and writes the bf16 output -- coalesced, no extra launch.
+          //   cluster form (csplit): the splits are the CTAs of one cluster (co-scheduled by the hardware, so they may
+          //     wait for each other whatever else runs on the GPU); partials are read from the peers' shared memory;
+          //   L2 form (fused): every split of the tile has its own CTA and the host launched no more CTAs than can be
+          //     resident at once; partials go through tile-major fp32 slabs in global memory and a counter rendezvous.
           constexpr int NT = NE * 32;
           const int et = (warp - 4) * 32 + lane;
-          __threadfence();
-          epi_bar_sync(NT);
-          if (et == 0) {
-            atomicAdd(p.cnt + 2 * tileId, 1);
-            uint32_t spins = 0;
-            while (ld_acquire_gpu(p.cnt + 2 * tileId) < p.splits) {
-              __nanosleep(40);
-              if (p.spinLimit != 0u && ++spins > p.spinLimit) {
-                printf("gct2: split-K rendezvous watchdog block %d tile %d\n", (int)blockIdx.x, tileId);
-                __trap();
+          const uint32_t part0 = smem_u32(smem);
+          if (csplit) {
+            __syncwarp();
+            if (lane == 0) {
+              const uint32_t bar = smem_u32(red_full);
+              for (int d = 0; d < p.splits; ++d) mbar_arrive_cluster_release(map_to_rank(bar, (uint32_t)d));
+            }
+            mbar_wait_cluster_acquire(red_full, 0);
+          } else {
+            __threadfence();
+            epi_bar_sync(NT);
+            if (et == 0) {
+              atomicAdd(p.cnt + 2 * tileId, 1);
+              uint32_t spins = 0;
+              while (ld_acquire_gpu(p.cnt + 2 * tileId) < p.splits) {
+                __nanosleep(40);
+                if (p.spinLimit != 0u && ++spins > p.spinLimit) {
+                  printf("gct2: split-K rendezvous watchdog block %d tile %d\n", (int)blockIdx.x, tileId);
+                  __trap();
+                }
               }
             }
+            epi_bar_sync(NT);
           }
-          epi_bar_sync(NT);
           const int R = 128 / p.splits, vecPerRow = BN / 4;
           const float* slab0 = p.ws + ((long long)tileId * 128) * BN;
           const long long splitStride = (long long)p.numTiles * 128 * BN;
@@ -675,11 +712,21 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
               ox = 2 * ox + (w.ph & 1);
             }
             const long long opix = ((long long)b * p.Hout + oy) * p.Wout + ox;
-            const float* sp = slab0 + (long long)rr * BN + c4;
-            float4 v = __ldcg(reinterpret_cast<const float4*>(sp));
-            for (int sidx = 1; sidx < p.splits; ++sidx) {
-              const float4 u = __ldcg(reinterpret_cast<const float4*>(sp + sidx * splitStride));
-              v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+            float4 v;
+            if (csplit) {
+              const uint32_t off = part0 + (uint32_t)(rr * BN * 4) + (uint32_t)((((c4 >> 2) ^ (rr & 7))) << 4);
+              v = ld_dsmem_f4(map_to_rank(off, 0u));
+              for (int sidx = 1; sidx < p.splits; ++sidx) {
+                const float4 u = ld_dsmem_f4(map_to_rank(off, (uint32_t)sidx));
+                v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+              }
+            } else {
+              const float* sp = slab0 + (long long)rr * BN + c4;
+              v = __ldcg(reinterpret_cast<const float4*>(sp));
+              for (int sidx = 1; sidx < p.splits; ++sidx) {
+                const float4 u = __ldcg(reinterpret_cast<const float4*>(sp + sidx * splitStride));
+                v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+              }
             }
             const int nn = w.nt * BN + c4;
             __nv_bfloat16* o = p.out + opix * p.ldo + nn;
@@ -703,12 +750,14 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
             res.y = pack_bf16x2(v.z, v.w);
             *reinterpret_cast<uint2*>(o) = res;
           }
-          epi_bar_sync(NT);
-          if (et == 0) {
-            const int old = atomicAdd(p.cnt + 2 * tileId + 1, 1);
-            if (old == p.splits - 1) {  // every split has passed the rendezvous: re-arm the counters
-              p.cnt[2 * tileId] = 0;
-              p.cnt[2 * tileId + 1] = 0;
+          if (!csplit) {
+            epi_bar_sync(NT);
+            if (et == 0) {
+              const int old = atomicAdd(p.cnt + 2 * tileId + 1, 1);
+              if (old == p.splits - 1) {  // every split has passed the rendezvous: re-arm the counters
+                p.cnt[2 * tileId] = 0;
+                p.cnt[2 * tileId + 1] = 0;
+              }
             }
           }
         }
@@ -729,7 +778,8 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
 
   tc_fence_before();
   __syncthreads();
-  if (pair) cluster_sync_all();  // no CTA leaves while its peer may still signal its barriers
+  // no CTA leaves while a peer may still signal its barriers or read its shared memory
+  if (pair || csplit) cluster_sync_all();
 #ifdef GCT2_TIMELINE
   if (threadIdx.x == 0) GCT2_STAMP(6);  // all work of this CTA done
 #endif

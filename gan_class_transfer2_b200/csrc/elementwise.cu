@@ -19,7 +19,9 @@ static int g_c3w_blocks = 0;   // debug key 15: grid cap of down0's weight-gradi
 static int g_adam_blocks = 0;  // debug key 13: grid cap of the Adam kernel (0 = 8 blocks per SM)
 static int g_adam_sms = 0;     // gct2_set_adam_sms / debug key 23: > 0 = run Keras-Adam on that many SMs, one 1024-thread
                                // CTA each (SM-exclusive through its shared-memory request), leaving the rest to the convs
+static int g_dense_bps = 2;    // debug key 24: blocks per SM of the fused Dense+MSE kernel
 void elementwise_set_debug(int key, int value) {
+  if (key == 24) g_dense_bps = value > 0 ? value : 2;
   if (key == 13) g_adam_blocks = value;
   if (key == 15) g_c3w_blocks = value;
   if (key == 23) g_adam_sms = value > 0 ? value : 0;
@@ -274,15 +276,31 @@ int step_begin(const float* x, const uint8_t* x_u8, const uint8_t* flip, float* 
 
 // ------------------------------------------------------------------------------------ down0 (Cin = 3)
 // Direct conv on CUDA cores: K = 48 is too thin for a tensor-core tile and the layer is bound by its 128-channel
-// output write.  Block = 8x8 output pixels, thread = output channel; the 18x18x3 input patch sits in smem and the
-// thread's 48 weights in registers.
-constexpr int C3_T = 8;                 // output tile edge
-constexpr int C3_P = 2 * C3_T + 2;      // input patch edge (18)
+// output write.  The 48 taps of one output value are consumed as 24 packed pairs: one 8-byte shared-memory load brings
+// two neighbouring patch values, one fma.rn.f32x2 (FFMA2, two fp32 FMAs per instruction on sm_100) multiplies them with
+// the matching pair of weights into an (even-tap, odd-tap) accumulator pair that is summed at the end.  A thread owns
+// TWO output channels, so every patch load feeds four FMAs: the loop is bound by the FMA pipe, not by shared memory.
+constexpr int C3_T = 8;                 // output tile width (and height of the wgrad tile)
+constexpr int C3_P = 2 * C3_T + 2;      // input patch width (18)
 constexpr int C3_ROW = C3_P * 3 + 2;    // padded patch row (56 floats, 16-byte aligned rows)
 
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {  // c + a * b, both lanes
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+
+// rows [oy0, oy0 + TY) x columns [ox0, ox0 + 8) of the output need input rows 2*oy0-1 .. 2*oy0+2*TY, columns 2*ox0-1 ..
+template <int TY>
 __device__ __forceinline__ void c3_load_patch(float (*patch)[C3_ROW], const float* __restrict__ x, int b, int oy0,
                                                int ox0, int H, int W) {
-  for (int i = threadIdx.x; i < C3_P * C3_P * 3; i += blockDim.x) {
+  constexpr int PY = 2 * TY + 2;
+  for (int i = threadIdx.x; i < PY * C3_P * 3; i += blockDim.x) {
     const int c = i % 3, xx = (i / 3) % C3_P, yy = i / (3 * C3_P);
     const int iy = 2 * oy0 - 1 + yy, ix = 2 * ox0 - 1 + xx;
     float v = 0.f;
@@ -291,39 +309,55 @@ __device__ __forceinline__ void c3_load_patch(float (*patch)[C3_ROW], const floa
   }
 }
 
+// fprop: block = 128 threads = 64 channel pairs x 2 row groups; tile = 8 x 4 output pixels (two rows per group).
+constexpr int C3F_TY = 4;
 __global__ void __launch_bounds__(128) conv_c3_fprop_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                             const float* __restrict__ bias,
                                                             __nv_bfloat16* __restrict__ y, int ldy, int B, int H,
                                                             int W, int Cout) {
   TraceScope trace(3);
+  __shared__ __align__(16) float patch[2 * C3F_TY + 2][C3_ROW];
+  const int Ho = H / 2, Wo = W / 2;
+  const int tilesX = Wo / C3_T, tilesY = Ho / C3F_TY;
+  const int tile = blockIdx.x;
+  const int b = tile / (tilesX * tilesY);
+  const int oy0 = ((tile / tilesX) % tilesY) * C3F_TY, ox0 = (tile % tilesX) * C3_T;
+  const int cp = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int co = blockIdx.y * 128 + 2 * cp;
+  // the kernel and the bias are not produced by the previous launch: fetch them before the dependency resolves
+  float2 w2[2][24];
+#pragma unroll
+  for (int j = 0; j < 24; ++j) {  // HWIO: ((ky*4+kx)*3+c)*Cout + co ; pair j = taps (2j, 2j+1)
+    const float2 lo = __ldg(reinterpret_cast<const float2*>(w + (2 * j) * Cout + co));
+    const float2 hi = __ldg(reinterpret_cast<const float2*>(w + (2 * j + 1) * Cout + co));
+    w2[0][j] = make_float2(lo.x, hi.x);
+    w2[1][j] = make_float2(lo.y, hi.y);
+  }
+  const float2 bv = __ldg(reinterpret_cast<const float2*>(bias + co));
   pdl_launch_dependents();
   pdl_wait();
   trace.ready();
-  __shared__ __align__(16) float patch[C3_P][C3_ROW];
-  const int Ho = H / 2, Wo = W / 2;
-  const int tilesX = Wo / C3_T, tilesY = Ho / C3_T;
-  const int tile = blockIdx.x;
-  const int b = tile / (tilesX * tilesY);
-  const int oy0 = ((tile / tilesX) % tilesY) * C3_T, ox0 = (tile % tilesX) * C3_T;
-  const int co = blockIdx.y * blockDim.x + threadIdx.x;
-  c3_load_patch(patch, x, b, oy0, ox0, H, W);
-  float wr[48];
-#pragma unroll
-  for (int k = 0; k < 48; ++k) wr[k] = __ldg(w + k * Cout + co);  // HWIO: ((ky*4+kx)*3+c)*Cout + co
-  const float bv = __ldg(bias + co);
+  c3_load_patch<C3F_TY>(patch, x, b, oy0, ox0, H, W);
   __syncthreads();
-  for (int py = 0; py < C3_T; ++py) {
 #pragma unroll
+  for (int r = 0; r < C3F_TY / 2; ++r) {
+    const int py = grp * (C3F_TY / 2) + r;
+#pragma unroll 2
     for (int px = 0; px < C3_T; ++px) {
-      float acc = bv;
+      float2 a0 = make_float2(bv.x, 0.f), a1 = make_float2(bv.y, 0.f);
 #pragma unroll
       for (int ky = 0; ky < 4; ++ky) {
-        const float* row = &patch[2 * py + ky][2 * px * 3];
+        // the 12 floats of this tap row start 24*px bytes into a 16-byte aligned row: six 8-byte broadcast loads
+        const float2* row = reinterpret_cast<const float2*>(&patch[2 * py + ky][2 * px * 3]);
 #pragma unroll
-        for (int j = 0; j < 12; ++j) acc = fmaf(row[j], wr[ky * 12 + j], acc);
+        for (int j = 0; j < 6; ++j) {
+          const float2 xv = row[j];
+          a0 = ffma2(xv, w2[0][ky * 6 + j], a0);
+          a1 = ffma2(xv, w2[1][ky * 6 + j], a1);
+        }
       }
       const long long pix = ((long long)b * Ho + oy0 + py) * Wo + ox0 + px;
-      y[pix * ldy + co] = __float2bfloat16(fmaxf(acc, 0.f));
+      *reinterpret_cast<uint32_t*>(y + pix * ldy + co) = pack_bf16x2(fmaxf(a0.x + a0.y, 0.f), fmaxf(a1.x + a1.y, 0.f));
     }
   }
   trace.end();
@@ -331,20 +365,21 @@ __global__ void __launch_bounds__(128) conv_c3_fprop_kernel(const float* __restr
 
 int conv4s2_c3_fprop(const float* x, const float* w, const float* bias, __nv_bfloat16* y, int ldy, int B, int H,
                      int W, int Cout, cudaStream_t st) {
-  if ((H / 2) % C3_T || (W / 2) % C3_T || Cout % 128) {
-    set_error("conv4s2_c3_fprop: unsupported shape H=%d W=%d Cout=%d", H, W, Cout);
+  if ((H / 2) % C3_T || (W / 2) % C3_T || Cout % 128 || ldy % 2) {
+    set_error("conv4s2_c3_fprop: unsupported shape H=%d W=%d Cout=%d ldy=%d", H, W, Cout, ldy);
     return 1;
   }
-  dim3 grid(B * (H / 2 / C3_T) * (W / 2 / C3_T), Cout / 128);
+  dim3 grid(B * (H / 2 / C3F_TY) * (W / 2 / C3_T), Cout / 128);
   launch_k(conv_c3_fprop_kernel, dim3(grid), dim3(128), 0, st, x, w, bias, y, ldy, B, H, W, Cout);
   GCT2_CHECK_LAUNCH("conv_c3_fprop_kernel");
   return 0;
 }
 
 // dW[ky,kx,c,co] = sum_pix x[pix@tap, c] * dz[pix, co];  db[co] = sum_pix dz[pix, co]
-// 256 threads: thread = (output channel, half of the tile's rows).  A block walks several tiles, the two halves are
-// combined through shared memory and only then added to dw/db: 49 atomics per channel per BLOCK.
-__global__ void __launch_bounds__(256) conv_c3_wgrad_kernel(const float* __restrict__ x,
+// 256 threads = 64 channel pairs x 4 row groups of an 8 x 8 tile; the thread's 2 x 48 sums live in 48 packed register
+// pairs (FFMA2 with the gradient broadcast to both lanes).  The four row groups are combined with shared-memory atomics
+// (conflict-free: consecutive threads, consecutive addresses) and the block adds each value to dw / db once.
+__global__ void __launch_bounds__(256, 2) conv_c3_wgrad_kernel(const float* __restrict__ x,
                                                             const __nv_bfloat16* __restrict__ dz, int lddz,
                                                             float* __restrict__ dw, float* __restrict__ db, int B,
                                                             int H, int W, int Cout, int numTiles) {
@@ -356,58 +391,66 @@ __global__ void __launch_bounds__(256) conv_c3_wgrad_kernel(const float* __restr
   __shared__ float comb[49][128];
   const int Ho = H / 2, Wo = W / 2;
   const int tilesX = Wo / C3_T, tilesY = Ho / C3_T;
-  const int lane_c = threadIdx.x & 127, half = threadIdx.x >> 7;
-  const int co = blockIdx.y * 128 + lane_c;
-  float acc[48];
+  const int cp = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int co = blockIdx.y * 128 + 2 * cp;
+  for (int i = threadIdx.x; i < 49 * 128; i += blockDim.x) (&comb[0][0])[i] = 0.f;
+  float2 acc[2][24];
 #pragma unroll
-  for (int k = 0; k < 48; ++k) acc[k] = 0.f;
-  float accb = 0.f;
+  for (int j = 0; j < 24; ++j) acc[0][j] = acc[1][j] = make_float2(0.f, 0.f);
+  float2 accb = make_float2(0.f, 0.f);
   for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
     const int b = tile / (tilesX * tilesY);
     const int oy0 = ((tile / tilesX) % tilesY) * C3_T, ox0 = (tile % tilesX) * C3_T;
     __syncthreads();
-    c3_load_patch(patch, x, b, oy0, ox0, H, W);
+    c3_load_patch<C3_T>(patch, x, b, oy0, ox0, H, W);
     __syncthreads();
-    for (int py = half * (C3_T / 2); py < (half + 1) * (C3_T / 2); ++py) {
-      float g[C3_T];
 #pragma unroll
-      for (int px = 0; px < C3_T; ++px)  // the row's 8 gradients are requested together
-        g[px] = __bfloat162float(dz[(((long long)b * Ho + oy0 + py) * Wo + ox0 + px) * lddz + co]);
+    for (int r = 0; r < C3_T / 4; ++r) {
+      const int py = grp * (C3_T / 4) + r;
+      uint32_t g[C3_T];
 #pragma unroll
+      for (int px = 0; px < C3_T; ++px)  // the row's 8 gradient pairs are requested together
+        g[px] = __ldg(reinterpret_cast<const uint32_t*>(dz + (((long long)b * Ho + oy0 + py) * Wo + ox0 + px) * lddz + co));
+#pragma unroll 2
       for (int px = 0; px < C3_T; ++px) {
-        accb += g[px];
+        const float g0 = bf16_lo(g[px]), g1 = bf16_hi(g[px]);
+        accb.x += g0;
+        accb.y += g1;
+        const float2 g00 = make_float2(g0, g0), g11 = make_float2(g1, g1);
 #pragma unroll
         for (int ky = 0; ky < 4; ++ky) {
-          // the 12 floats of this tap row start 24*px bytes into a 16-byte aligned row: six 8-byte broadcast loads
           const float2* row = reinterpret_cast<const float2*>(&patch[2 * py + ky][2 * px * 3]);
 #pragma unroll
           for (int j = 0; j < 6; ++j) {
             const float2 xv = row[j];
-            acc[ky * 12 + 2 * j] = fmaf(xv.x, g[px], acc[ky * 12 + 2 * j]);
-            acc[ky * 12 + 2 * j + 1] = fmaf(xv.y, g[px], acc[ky * 12 + 2 * j + 1]);
+            acc[0][ky * 6 + j] = ffma2(xv, g00, acc[0][ky * 6 + j]);
+            acc[1][ky * 6 + j] = ffma2(xv, g11, acc[1][ky * 6 + j]);
           }
         }
       }
     }
   }
-  if (half == 1) {
-#pragma unroll
-    for (int k = 0; k < 48; ++k) comb[k][lane_c] = acc[k];
-    comb[48][lane_c] = accb;
-  }
   __syncthreads();
-  if (half == 0) {
 #pragma unroll
-    for (int k = 0; k < 48; ++k) atomicAdd(dw + k * Cout + co, acc[k] + comb[k][lane_c]);
-    if (db != nullptr) atomicAdd(db + co, accb + comb[48][lane_c]);
+  for (int j = 0; j < 24; ++j) {
+    atomicAdd(&comb[2 * j][2 * cp], acc[0][j].x);
+    atomicAdd(&comb[2 * j][2 * cp + 1], acc[1][j].x);
+    atomicAdd(&comb[2 * j + 1][2 * cp], acc[0][j].y);
+    atomicAdd(&comb[2 * j + 1][2 * cp + 1], acc[1][j].y);
   }
+  atomicAdd(&comb[48][2 * cp], accb.x);
+  atomicAdd(&comb[48][2 * cp + 1], accb.y);
+  __syncthreads();
+  const int cbase = blockIdx.y * 128;
+  for (int i = threadIdx.x; i < 48 * 128; i += blockDim.x) atomicAdd(dw + (i >> 7) * Cout + cbase + (i & 127), (&comb[0][0])[i]);
+  if (db != nullptr && threadIdx.x < 128) atomicAdd(db + cbase + threadIdx.x, comb[48][threadIdx.x]);
   trace.end();
 }
 
 int conv4s2_c3_wgrad(const float* x, const __nv_bfloat16* dz, int lddz, float* dw, float* db, int B, int H, int W,
                      int Cout, int zero, cudaStream_t st) {
-  if ((H / 2) % C3_T || (W / 2) % C3_T || Cout % 128) {
-    set_error("conv4s2_c3_wgrad: unsupported shape H=%d W=%d Cout=%d", H, W, Cout);
+  if ((H / 2) % C3_T || (W / 2) % C3_T || Cout % 128 || lddz % 2) {
+    set_error("conv4s2_c3_wgrad: unsupported shape H=%d W=%d Cout=%d lddz=%d", H, W, Cout, lddz);
     return 1;
   }
   if (zero) {
@@ -419,9 +462,8 @@ int conv4s2_c3_wgrad(const float* x, const __nv_bfloat16* dz, int lddz, float* d
     }
   }
   const int numTiles = B * (H / 2 / C3_T) * (W / 2 / C3_T);
-  // Two blocks per SM (16 warps hide the shared-memory latency of the FMA loop); beyond that a block walks several
-  // tiles, because the atomics per block (49 x 128) are the cost that does not shrink with the tile count.  Measured
-  // at batch 1: 74 blocks x 3.5 tiles = 47 us, 256 blocks x 1 tile (debug key 15 to vary) -- see profiles/.
+  // One tile per block up to two blocks per SM; beyond that a block walks several tiles, because the global atomics
+  // per block (49 x 128) are the cost that does not shrink with the tile count (debug key 15 varies the cap).
   int gx = g_c3w_blocks > 0 ? g_c3w_blocks : 2 * g_ew_sms;
   if (gx > numTiles) gx = numTiles;
   dim3 grid(gx, Cout / 128);
@@ -593,7 +635,7 @@ int dense_mse(const __nv_bfloat16* u0, int ldu, const float* noised, const float
     }
   }
   long long want = (pixels * (Cu / 8) + 255) / 256;  // one 16-byte vector per thread per iteration
-  int blocks = (int)(want < (long long)g_ew_sms * 2 ? want : (long long)g_ew_sms * 2);
+  int blocks = (int)(want < (long long)g_ew_sms * g_dense_bps ? want : (long long)g_ew_sms * g_dense_bps);
   if (blocks < 1) blocks = 1;
   if (Cu == 64)
     launch_k(dense_mse_kernel<8>, dim3(blocks), dim3(256), 0, st, u0, ldu, noised, x, wd, bd, pred, loss, du0, lddu, dwd, dbd, pixels, invN,

@@ -200,6 +200,46 @@ __device__ __forceinline__ void tma_load_5d_pair(void* dst, const CUtensorMap* m
       : "memory");
 }
 
+// ----------------------------------------------------------------------------- distributed shared memory (split-K in a cluster)
+// Address of the same shared-memory offset in CTA `rank` of the cluster.
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+// arrive on a (possibly remote) barrier given by its shared::cluster address; release at cluster scope: the caller's
+// earlier shared-memory writes are visible to whoever acquires the barrier's phase
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster_acquire(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > (1u << 24)) {
+      printf("gct2: cluster split-K watchdog block %d thread %d\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t cluster_addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(cluster_addr)
+               : "memory");
+  return v;
+}
+
 // ----------------------------------------------------------------------------- step trace (test hook)
 // When enabled (gct2_debug_set(11, 1)) the first and the last block of every launch append
 // {kernel id, blockIdx | gridDim << 32, t_entry, t_exit} (%globaltimer ns) to a device buffer: a whole-step timeline

@@ -218,7 +218,7 @@ class UNetEngine:
         #: gradient buckets (backward order: up0 .. up{n-1}, down{n-1} ..) are updated by `adam_sms` SM-exclusive CTAs
         #: while the conv launches keep to the other SMs (gct2_set_sm_budget); the remaining buckets, complete only when
         #: backward is over, use the whole chip.  0 = the optimiser always uses the whole chip (takes turns with the convs).
-        self.adam_sms = int(os.environ.get("GCT2_ADAM_SMS", "48"))
+        self.adam_sms = int(os.environ.get("GCT2_ADAM_SMS", "0"))
         self.adam_wide_buckets = int(os.environ.get("GCT2_ADAM_WIDE", "5"))
         self._side = torch.cuda.Stream(device=self.device)
         self._side_adam = torch.cuda.Stream(device=self.device)
@@ -230,12 +230,13 @@ class UNetEngine:
         from . import _lib
         lib = _lib.init(self.device.index or 0)
         if dp is not None and dp.world > 1:
-            # The in-launch split-K finish makes the CTAs of a conv launch wait for one another, which is only safe
-            # while every other kernel on the GPU terminates on its own.  An NCCL kernel waits for its peer GPU and
-            # must itself be fully resident: a half-placed conv launch and a half-placed NCCL kernel can then hold all
-            # 148 SMs between them forever (seen as a hang of the captured 2-GPU step).  Data-parallel steps finish
-            # split-K with the separate finishing kernel instead.
-            lib.gct2_debug_set(12, 1)
+            # The L2 form of the in-launch split-K finish makes the CTAs of a conv launch wait for one another, which is
+            # only safe while every other kernel on the GPU terminates on its own.  An NCCL kernel waits for its peer GPU
+            # and must itself be fully resident: a half-placed conv launch and a half-placed NCCL kernel can then hold
+            # all 148 SMs between them forever (seen as a hang of the captured 2-GPU step in round 1).  Data-parallel
+            # steps therefore finish split-K inside a thread-block cluster (co-scheduled by the hardware, so waiting
+            # inside it is always safe) or with the separate finishing kernel.
+            lib.gct2_debug_set(26, 1)
 
         # ---- parameters, flat in Keras order
         self.specs = variable_specs(cfg)

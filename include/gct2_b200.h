@@ -52,7 +52,10 @@ long long gct2_launch_count(void);
  * cap of the down0 weight-gradient kernel (0 = 2 blocks per SM), key 16 = which point of the TMA producer's start-up
  * timeline stamp [7] records, key 19 = CTA pairs (cta_group::2): 0 heuristic, 1 wherever legal, 2 never, key 20 =
  * split-K rendezvous watchdog in polls of ~40 ns (0 = none; default 2^28), key 21 != 0 = never fetch weights before the
- * programmatic dependency resolves, key 22 = gct2_set_sm_budget, key 23 = gct2_set_adam_sms. */
+ * programmatic dependency resolves, key 22 = gct2_set_sm_budget, key 23 = gct2_set_adam_sms, key 24 = blocks per SM of
+ * the Dense+MSE kernel, key 25 = split-K inside a thread-block cluster (partials through distributed shared memory): 0 =
+ * when the cost model picks it, 1 = never, 2 = whenever legal, key 26 != 0 = never use the L2 rendezvous form of the
+ * in-launch split-K finish (data-parallel steps: it needs all CTAs of a launch resident at once). */
 void gct2_debug_set(int key, int value);
 /* Test hook: after gct2_debug_set(7, 1) every tensor-core conv launch records, per CTA, 8 %globaltimer stamps (ns):
  * [0] entry, [1] prologue done, [2] first operands landed, [3] MMAs of the first tile issued, [4] first accumulator
@@ -60,7 +63,8 @@ void gct2_debug_set(int key, int value);
  * recent launch (up to max_ctas CTAs) to `host`; returns the number of CTAs. */
 int gct2_debug_timeline(unsigned long long* host, int max_ctas);
 /* Test hook: the plan of the most recent tensor-core conv launch: out8 = {BN, split-K factor, CTA pairs (0/1), split-K
- * finished inside the launch (0/1), grid, ring slots, ring rounds per work item, weights fetched early (0/1)}. */
+ * finish (0 = none / separate kernel, 1 = in-launch L2 rendezvous, 2 = thread-block cluster through distributed shared
+ * memory), grid, ring slots, ring rounds per work item, weights fetched early (0/1)}. */
 void gct2_debug_last_plan(int* out8);
 /* CTAs (= SMs) a tensor-core conv launch may occupy; 0 = all.  Data-parallel callers leave room for the NCCL kernels
  * that run beside backward, so that a conv launch never queues a second wave behind them. */
@@ -98,10 +102,12 @@ int gct2_conv4s2_c3_wgrad(const float* x, const uint16_t* dz, int lddz, float* d
  * ws: fp32 split-K scratch (contents irrelevant on entry and exit).  Split-K is used only when `splits` partial
  * outputs (splits * B*(H/2)*(W/2)*Cout floats) fit in ws_bytes; partials are summed in a fixed order, so results are
  * bit-reproducible.  ws may be NULL (no split-K).  The same holds for every ws argument below.
- * Concurrency: when every work item has its own resident CTA, split-K is finished inside the launch (the CTAs of a
- * tile wait for each other at counters of the launch's own), so a fprop/dgrad launch needs all of its CTAs resident:
- * do not run two of them concurrently on different streams of one device unless gct2_set_sm_budget leaves room for
- * both; wgrad calls never wait and may overlap anything.  flags: GCT2_WEIGHTS_STABLE or 0. */
+ * Split-K is finished inside the launch: preferably by a thread-block cluster per tile (its CTAs hold the K slices and
+ * exchange partials through distributed shared memory; co-scheduled by the hardware, safe beside anything), otherwise,
+ * when every work item has its own resident CTA, by a rendezvous at counters of the launch's own over fp32 slabs in
+ * `ws` -- that form needs all CTAs of the launch resident at once: do not run two such launches concurrently on
+ * different streams of one device unless gct2_set_sm_budget leaves room for both (gct2_debug_set(26, 1) switches it
+ * off); wgrad calls never wait and may overlap anything.  flags: GCT2_WEIGHTS_STABLE or 0. */
 int gct2_conv4s2_fprop(const uint16_t* x, int ldx, const uint16_t* w, const float* bias, uint16_t* y, int ldy,
                        int B, int H, int W, int Cin, int Cout, float* ws, size_t ws_bytes, int flags, void* stream);
 /* Backward-data of DownShuffle: dx[b,iy,ix,ci] (+)= sum dy[b,oy,ox,co]*w[ky,kx,ci,co], then ReLU-masked by the

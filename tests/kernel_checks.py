@@ -497,22 +497,27 @@ EW_CASES = [
 ]
 
 
-def forced(fn, BN=0, splits=0, pair=0, nofuse=0, budget=0, **kw):
+def forced(fn, BN=0, splits=0, pair=0, nofuse=0, budget=0, finish=None, **kw):
     """Runs a conv check with the tile width / split-K factor / CTA-pair mode pinned (test hooks gct2_debug_set keys 3,
     4, 19, 12 and gct2_set_sm_budget) so that every template instantiation and every split-K finishing path is exercised
     regardless of the heuristics; then asks the library which plan the launch actually used (gct2_debug_last_plan) --
     a case that asked for CTA pairs / a fused finish and silently got something else fails."""
     from gan_class_transfer2_b200 import _lib, ops
     lib = _lib.init(0)
-    for key, val in ((3, BN), (4, splits), (19, pair), (12, nofuse), (22, budget)):
+    # how split-K is finished: "cluster" = the splits are one thread-block cluster (partials through distributed shared
+    # memory), "l2" = in-launch rendezvous over fp32 slabs in global memory, "kernel" = separate finishing kernel
+    cs = {None: 0, "l2": 1, "cluster": 2, "kernel": 0}[finish]
+    if finish == "kernel":
+        nofuse = 1
+    for key, val in ((3, BN), (4, splits), (19, pair), (12, nofuse), (22, budget), (25, cs)):
         lib.gct2_debug_set(key, val)
     try:
         m = fn(**kw)
         plan = ops.last_plan()
     finally:
-        for key in (3, 4, 19, 12, 22):
+        for key in (3, 4, 19, 12, 22, 25):
             lib.gct2_debug_set(key, 0)
-    m["name"] += (f" [BN={BN or 'auto'} splits={splits or 'auto'} pair={pair}{' finish-kernel' if nofuse else ''}"
+    m["name"] += (f" [BN={BN or 'auto'} splits={splits or 'auto'} pair={pair} finish={finish or ('kernel' if nofuse else 'auto')}"
                   f"{f' budget={budget}' if budget else ''} -> {plan}]")
     want = {}
     if BN:
@@ -525,6 +530,10 @@ def forced(fn, BN=0, splits=0, pair=0, nofuse=0, budget=0, **kw):
         want["pair"] = 0
     if nofuse:
         want["fused"] = 0
+    if finish == "l2":
+        want["fused"] = 1
+    if finish == "cluster":
+        want["fused"] = 2
     if budget:
         assert plan["grid"] <= budget, (plan, budget)
     wrong = {k: (plan[k], v) for k, v in want.items() if plan[k] != v}
@@ -538,15 +547,33 @@ def forced(fn, BN=0, splits=0, pair=0, nofuse=0, budget=0, **kw):
 # (check, shape kwargs, forced plan)
 FORCED_CASES = [
     (check_conv_fprop, dict(B=2, H=16, Cin=128, Cout=256), dict(BN=64, splits=1)),
-    (check_conv_fprop, dict(B=2, H=16, Cin=128, Cout=256), dict(BN=128, splits=4)),
-    (check_conv_fprop, dict(B=2, H=16, Cin=128, Cout=256), dict(BN=256, splits=16)),
-    (check_convT_fprop, dict(B=2, H=8, Cin=128, Cout=256), dict(BN=64, splits=2)),
+    (check_conv_fprop, dict(B=2, H=16, Cin=128, Cout=256), dict(BN=128, splits=4, finish="l2")),
+    (check_conv_fprop, dict(B=2, H=16, Cin=128, Cout=256), dict(BN=256, splits=16, finish="l2")),
+    (check_convT_fprop, dict(B=2, H=8, Cin=128, Cout=256), dict(BN=64, splits=2, finish="l2")),
     (check_convT_fprop, dict(B=2, H=8, Cin=128, Cout=256), dict(BN=128, splits=1)),
-    (check_convT_fprop, dict(B=2, H=8, Cin=128, Cout=256), dict(BN=256, splits=8)),
-    (check_conv_dgrad, dict(B=2, H=16, Cin=256, Cout=128, add_old=True), dict(BN=256, splits=4)),
+    (check_convT_fprop, dict(B=2, H=8, Cin=128, Cout=256), dict(BN=256, splits=8, finish="l2")),
+    (check_conv_dgrad, dict(B=2, H=16, Cin=256, Cout=128, add_old=True), dict(BN=256, splits=4, finish="l2")),
     (check_conv_dgrad, dict(B=2, H=16, Cin=256, Cout=128, add_old=True), dict(BN=128, splits=1)),
-    (check_convT_dgrad, dict(B=2, H=8, Cin=256, Cout=128), dict(BN=256, splits=2)),
-    (check_convT_dgrad, dict(B=2, H=8, Cin=256, Cout=128), dict(BN=64, splits=32)),
+    (check_convT_dgrad, dict(B=2, H=8, Cin=256, Cout=128), dict(BN=256, splits=2, finish="l2")),
+    (check_convT_dgrad, dict(B=2, H=8, Cin=256, Cout=128), dict(BN=64, splits=32, finish="l2")),
+    # split-K inside a thread-block cluster (partials through distributed shared memory): every tile width x mode x
+    # epilogue, cluster sizes 2 / 4 / 8, a ragged batch, more clusters than the chip holds at once (waves), early weights
+    (check_conv_fprop, dict(B=2, H=16, Cin=128, Cout=256), dict(BN=64, splits=2, finish="cluster")),
+    (check_conv_fprop, dict(B=2, H=16, Cin=128, Cout=256), dict(BN=128, splits=4, finish="cluster")),
+    (check_conv_fprop, dict(B=2, H=16, Cin=128, Cout=256), dict(BN=256, splits=8, finish="cluster")),
+    (check_convT_fprop, dict(B=2, H=8, Cin=128, Cout=256), dict(BN=64, splits=8, finish="cluster")),
+    (check_convT_fprop, dict(B=2, H=8, Cin=128, Cout=256), dict(BN=128, splits=2, finish="cluster")),
+    (check_convT_fprop, dict(B=2, H=8, Cin=128, Cout=256), dict(BN=256, splits=4, finish="cluster")),
+    (check_conv_dgrad, dict(B=2, H=16, Cin=256, Cout=128, add_old=True), dict(BN=256, splits=4, finish="cluster")),
+    (check_conv_dgrad, dict(B=2, H=16, Cin=256, Cout=128, add_old=False), dict(BN=64, splits=2, finish="cluster")),
+    (check_convT_dgrad, dict(B=2, H=8, Cin=256, Cout=128), dict(BN=128, splits=8, finish="cluster")),
+    (check_convT_dgrad, dict(B=2, H=8, Cin=256, Cout=128, mask_channels=64), dict(BN=64, splits=4, finish="cluster")),
+    (check_conv_fprop, dict(B=3, H=8, Cin=256, Cout=128), dict(BN=64, splits=8, finish="cluster")),             # ragged
+    (check_convT_dgrad, dict(B=3, H=4, Cin=128, Cout=256, mask_channels=64), dict(BN=128, splits=4, finish="cluster")),
+    (check_conv_fprop, dict(B=16, H=32, Cin=128, Cout=256), dict(BN=64, splits=4, finish="cluster")),           # 512 CTAs: waves
+    (check_convT_fprop, dict(B=8, H=16, Cin=128, Cout=128), dict(BN=64, splits=2, finish="cluster")),               # 256 CTAs
+    (check_conv_fprop, dict(B=2, H=16, Cin=128, Cout=256, weights_stable=True), dict(BN=64, splits=4, finish="cluster")),
+    (check_convT_fprop, dict(B=2, H=8, Cin=192, Cout=64), dict(BN=64, splits=4, finish="cluster")),             # 3 chunks per split
     (check_conv_wgrad, dict(B=4, H=32, Cin=128, Cout=256), dict(BN=64, splits=8)),
     (check_conv_wgrad, dict(B=4, H=32, Cin=128, Cout=256), dict(BN=128, splits=1)),
     (check_conv_wgrad, dict(B=4, H=32, Cin=128, Cout=256), dict(BN=256, splits=2)),
@@ -555,16 +582,16 @@ FORCED_CASES = [
     # odd number of k-chunks per work item: the last ring round of a two-chunk slot is half full (BN <= 128)
     (check_conv_wgrad, dict(B=3, H=16, Cin=128, Cout=64), dict(BN=64, splits=1)),       # 3 pixel chunks
     (check_convT_wgrad, dict(B=1, H=4, Cin=128, Cout=128), dict(BN=128, splits=1)),     # 1 chunk, a quarter full
-    (check_conv_fprop, dict(B=1, H=16, Cin=64, Cout=128), dict(BN=128, splits=16)),     # 1 chunk per split
-    (check_convT_fprop, dict(B=2, H=8, Cin=192, Cout=64), dict(BN=64, splits=4)),       # 3 chunks per split
+    (check_conv_fprop, dict(B=1, H=16, Cin=64, Cout=128), dict(BN=128, splits=16, finish="l2")),     # 1 chunk per split
+    (check_convT_fprop, dict(B=2, H=8, Cin=192, Cout=64), dict(BN=64, splits=4, finish="l2")),       # 3 chunks per split
     # split-K finished by the separate kernel (the fallback when a CTA owns more than one work item)
     (check_conv_fprop, dict(B=2, H=16, Cin=128, Cout=256), dict(BN=128, splits=4, nofuse=1)),
     (check_convT_fprop, dict(B=2, H=8, Cin=128, Cout=256), dict(BN=256, splits=8, nofuse=1)),
     (check_conv_dgrad, dict(B=2, H=16, Cin=256, Cout=128, add_old=True), dict(BN=256, splits=4, nofuse=1)),
     (check_convT_dgrad, dict(B=2, H=8, Cin=256, Cout=128), dict(BN=64, splits=32, nofuse=1)),
     # split-K with a ragged batch: rows of the tile beyond the batch are neither stored nor finished
-    (check_conv_fprop, dict(B=3, H=8, Cin=256, Cout=128), dict(BN=64, splits=16)),
-    (check_convT_dgrad, dict(B=3, H=4, Cin=128, Cout=256, mask_channels=64), dict(BN=128, splits=8)),
+    (check_conv_fprop, dict(B=3, H=8, Cin=256, Cout=128), dict(BN=64, splits=16, finish="l2")),
+    (check_convT_dgrad, dict(B=3, H=4, Cin=128, Cout=256, mask_channels=64), dict(BN=128, splits=8, finish="l2")),
     # persistent CTAs: more work items than the SM budget (several tiles per CTA, TMEM double buffering, ring wrap)
     (check_conv_fprop, dict(B=16, H=64, Cin=64, Cout=128), dict(BN=64, splits=1, budget=24)),
     (check_convT_fprop, dict(B=16, H=16, Cin=64, Cout=64), dict(BN=64, splits=1, budget=20)),
@@ -572,11 +599,11 @@ FORCED_CASES = [
     (check_conv_wgrad, dict(B=4, H=32, Cin=128, Cout=256), dict(BN=128, splits=2, budget=10)),
     # weights fetched before the programmatic dependency resolves (GCT2_WEIGHTS_STABLE)
     (check_conv_fprop, dict(B=2, H=16, Cin=128, Cout=256, weights_stable=True), dict(BN=64, splits=1)),
-    (check_conv_fprop, dict(B=2, H=16, Cin=128, Cout=256, weights_stable=True), dict(BN=128, splits=16)),
+    (check_conv_fprop, dict(B=2, H=16, Cin=128, Cout=256, weights_stable=True), dict(BN=128, splits=16, finish="l2")),
     (check_convT_fprop, dict(B=2, H=8, Cin=128, Cout=256, weights_stable=True), dict(BN=256, splits=1)),
     (check_convT_fprop, dict(B=16, H=16, Cin=64, Cout=64, weights_stable=True), dict(BN=64, splits=1, budget=20)),
-    (check_conv_dgrad, dict(B=2, H=16, Cin=256, Cout=128, add_old=True, weights_stable=True), dict(BN=128, splits=2)),
-    (check_convT_dgrad, dict(B=2, H=8, Cin=256, Cout=128, weights_stable=True), dict(BN=64, splits=4)),
+    (check_conv_dgrad, dict(B=2, H=16, Cin=256, Cout=128, add_old=True, weights_stable=True), dict(BN=128, splits=2, finish="l2")),
+    (check_convT_dgrad, dict(B=2, H=8, Cin=256, Cout=128, weights_stable=True), dict(BN=64, splits=4, finish="l2")),
 ]
 
 # CTA pairs (tcgen05 cta_group::2): all six PAIR instantiations ({S, P, W} x BN {128, 256}), each with the direct

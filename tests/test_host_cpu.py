@@ -69,6 +69,29 @@ def test_unsupported_structures_are_rejected():
         E.NetConfig(size=64, octaves=2, pixel_size=96).validate()
 
 
+def test_disabled_skip_wirings_are_rejected_by_the_fused_engine():
+    """residual=True / concat=False (train.py:26-27,106-121) change the network's wiring; the fused engine implements the
+    reference's default only and must say so instead of silently running the concat network."""
+    for flag, val in (("concat", False), ("residual", True)):
+        old = getattr(T, flag)
+        setattr(T, flag, val)
+        try:
+            with pytest.raises(NotImplementedError):
+                T.Denoiser().net_config(256)
+        finally:
+            setattr(T, flag, old)
+
+
+def test_compile_hands_the_optimizer_to_the_denoiser():
+    d = T.Denoiser()
+    tr = T.Trainer(d)
+    tr.compile(T.Adam(T.WarmUp(1e-3, 7), beta_1=0.8), T.identity)
+    cfg = d.net_config(256)
+    assert (cfg.base_lr, cfg.warm_up, cfg.beta1) == (1e-3, 7, 0.8)
+    with pytest.raises(NotImplementedError):
+        tr.compile(object(), T.identity)
+
+
 def test_layers_refuse_cpu_tensors():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         T.DownShuffle(64)(torch.zeros(1, 8, 8, 64))
