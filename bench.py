@@ -185,6 +185,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch-per-gpu", type=int, default=1)
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling (BASELINE config 3): a fixed global batch split over the ranks")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-ops", default="", help="write the instrumented step's per-launch (op, us) list here")
@@ -209,12 +211,20 @@ def main():
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        # the collectives run beside backward: cap their CTAs and keep the conv launches off those SMs (engine.DataParallel)
+        os.environ.setdefault("NCCL_MAX_CTAS", "16")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         T.data_parallel = DataParallel(shard_optimizer=os.environ.get("GCT2_DP_SHARD", "1") != "0")
     _lib.init(local)
 
     B = args.batch_per_gpu
+    scaling = "weak"
+    if args.global_batch:
+        if args.global_batch % world:
+            raise SystemExit(f"--global-batch {args.global_batch} is not divisible by {world} ranks")
+        B = args.global_batch // world
+        scaling = "strong"
     T.use_cuda_graph = not args.no_graph
     denoiser = T.Denoiser()
     trainer = T.Trainer(denoiser)
@@ -258,6 +268,67 @@ def main():
     ms_total = max_over_ranks(s.elapsed_time(e))
     ms_per_step = ms_total / args.steps
     value = B * world * args.steps / (ms_total * 1e-3)
+
+    # ---- data parallel: correctness bit and communication breakdown
+    comm = None
+    if dist is not None:
+        # every rank must hold bit-identical bf16 weights after the timed loop (summed gradients are identical everywhere)
+        mx, mn = eng.w16.clone(), eng.w16.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        replicas_equal = bool(torch.equal(mx, mn))
+        del mx, mn
+
+        def timed(fn, n):
+            for _ in range(3):
+                fn()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn()
+            b.record()
+            barrier()
+            return max_over_ranks(a.elapsed_time(b)) / n
+
+        # (a) the same step without its collectives (wrong numbers, right compute): what the GPU alone needs
+        saved = eng._save_state()
+        graphs = eng._graph
+        eng._graph, T.data_parallel.dry_run = None, True
+        compute_ms = timed(lambda: eng.run_step(draw=True), max(10, args.steps // 4))
+        eng.release_graphs()
+        eng._graph, T.data_parallel.dry_run = graphs, False
+        eng._restore_state(saved)
+        # (b) the step's collectives alone, back to back: per bucket reduce-scatter (+ all-gather of the bf16 weights)
+        from gan_class_transfer2_b200.engine import optimizer_shard
+        dp = T.data_parallel
+
+        def comm_only():
+            for start, end, _ in eng._buckets:
+                cut = optimizer_shard(start, end, eng.small, dp.world, dp.rank) if dp.shard_optimizer else None
+                if cut is not None:
+                    lo, _, own, own_hi = cut
+                    gsrc = eng.g16 if eng.g16 is not None else eng.g
+                    dist.reduce_scatter_tensor(gsrc[own:own_hi], gsrc[lo:end])
+                    dist.all_gather_into_tensor(eng.w16[lo:end], eng.w16[own:own_hi])
+                    if start >= eng.small:
+                        continue
+                    end = eng.small
+                dist.all_reduce(eng.g[start:end])
+
+        saved = eng._save_state()
+        comm_ms = timed(comm_only, max(10, args.steps // 4))
+        eng._restore_state(saved)
+        exposed = max(0.0, ms_per_step - compute_ms)
+        grad_bytes = (2 if eng.g16 is not None else 4) * eng.P
+        comm = {"comm_exposed_ms": exposed, "comm_overlapped_ms": max(0.0, comm_ms - exposed), "comm_alone_ms": comm_ms,
+                "compute_only_ms": compute_ms, "replicas_bit_equal": replicas_equal,
+                "bytes_per_step": {"reduce_scatter": grad_bytes, "all_gather_bf16": 2 * eng.P},
+                "grad_dtype": dp.grad_dtype, "shard_optimizer": dp.shard_optimizer, "nccl_max_ctas": dp.nccl_ctas,
+                "how": "compute_only = the captured step with its collectives left out; comm_alone = the step's "
+                       "collectives back to back; exposed = step - compute_only; overlapped = comm_alone - exposed"}
+        if not replicas_equal:
+            raise SystemExit("data-parallel ranks hold different bf16 weights after the timed loop")
 
     # ---- e2e: public API, pinned host batch in, loss out, every step
     for _ in range(3):
@@ -383,7 +454,7 @@ def main():
         r = cpu_reference(B, 4, 1, budget_s=25.0)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(B, world),
             "e2e": {"value": B * world * args.steps / (ms_e2e * 1e-3), "unit": "images/s",
                     "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4,
@@ -394,7 +465,7 @@ def main():
                                  "/128-1 on the device (SURVEY 8 f2)"},
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
             "cuda_graph": not args.no_graph, "clocks": clocks, "roofline": roofline, "roofline_adam": roofline_adam,
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "comm": comm,
             "final_loss": final_loss}
     print(json.dumps(line), flush=True)
     teardown()

@@ -45,6 +45,10 @@ _PROTOS = {
     "gct2_debug_last_plan": (None, [_P]),
     "gct2_set_sm_budget": (None, [c_int]),
     "gct2_set_adam_sms": (None, [c_int]),
+    "gct2_set_policy": (None, [c_int]),
+    "gct2_get_policy": (c_int, []),
+    "gct2_loss_scale_check": (c_int, [_P, c_longlong, _P, _P]),
+    "gct2_loss_scale_update": (c_int, [_P, c_int, _P]),
     "gct2_debug_trace": (c_int, [_P, c_int]),
     "gct2_noise_images": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "gct2_conv4s2_c3_fprop": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
@@ -62,11 +66,12 @@ _PROTOS = {
     "gct2_bias_grad": (c_int, [_P, c_int, c_longlong, c_int, _P, _P]),
     "gct2_bias_grad_multi": (c_int, [c_int, _P, _P, _P, _P, _P, c_int, _P]),
     "gct2_dense_mse": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, c_longlong, c_int, c_float,
-                               c_int, c_int, _P]),
+                               c_int, c_int, _P, _P]),
     "gct2_adam_keras": (c_int, [_P, _P, _P, _P, _P, c_longlong, _P, _P, c_float, c_int, c_float, c_float, c_float,
                                 c_float, _P]),
     "gct2_adam_prepare": (c_int, [_P, _P, c_float, c_int, c_float, c_float, _P]),
-    "gct2_adam_apply": (c_int, [_P, _P, _P, _P, _P, c_longlong, _P, c_float, c_float, c_float, c_float, _P, _P]),
+    "gct2_adam_apply": (c_int, [_P, _P, _P, _P, _P, c_longlong, _P, c_float, c_float, c_float, c_float, _P, _P, _P]),
+    "gct2_adam_apply_g16": (c_int, [_P, _P, _P, _P, _P, c_longlong, _P, c_float, c_float, c_float, c_float, _P, _P]),
     "gct2_step_begin": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, ctypes.c_ulonglong, _P, _P, c_float, c_int, c_float,
                                 c_float, _P, c_longlong, _P, _P]),
     "gct2_step_begin_u8": (c_int, [_P, _P, _P, c_int, _P, _P, _P, c_int, c_int, c_int, ctypes.c_ulonglong, _P, _P, c_float,

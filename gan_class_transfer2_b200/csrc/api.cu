@@ -11,7 +11,7 @@
 using namespace gct2;
 
 namespace {
-int g_force_bn = 0, g_force_splits = 0, g_sms = 0;
+int g_force_bn = 0, g_force_splits = 0, g_sms = 0, g_policy_f16 = 0;
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline const __nv_bfloat16* CB(const uint16_t* p) { return reinterpret_cast<const __nv_bfloat16*>(p); }
 inline __nv_bfloat16* MB(uint16_t* p) { return reinterpret_cast<__nv_bfloat16*>(p); }
@@ -37,6 +37,7 @@ ConvArgs blank(int mode, int B, int Hlo, int Wlo) {
   a.Wlo = Wlo;
   a.forceBN = g_force_bn;
   a.forceSplits = g_force_splits;
+  a.f16 = g_policy_f16;
   return a;
 }
 }  // namespace
@@ -65,6 +66,13 @@ int gct2_debug_timeline(unsigned long long* host, int max_ctas) { return debug_r
 void gct2_debug_last_plan(int* out8) { debug_last_plan(out8); }
 void gct2_set_sm_budget(int sms) { conv_set_sm_budget(sms); }
 void gct2_set_adam_sms(int sms) { elementwise_set_adam_sms(sms); }
+void gct2_set_policy(int fp16) {
+  g_policy_f16 = fp16 ? 1 : 0;
+  elementwise_set_f16(g_policy_f16);
+}
+int gct2_get_policy(void) { return g_policy_f16; }
+int gct2_loss_scale_check(const float* g, long long n, float* ls, void* stream) { return loss_scale_check(g, n, ls, S(stream)); }
+int gct2_loss_scale_update(float* ls, int growth_steps, void* stream) { return loss_scale_update(ls, growth_steps, S(stream)); }
 
 void gct2_debug_set(int key, int value) {
   if (key == 3)
@@ -176,9 +184,10 @@ int gct2_bias_grad_multi(int n, const uint16_t* const* dz, const int* ld, const 
 
 int gct2_dense_mse(const uint16_t* u0, int ldu, const float* noised, const float* x, const float* wd,
                    const float* bd, float* pred, float* loss, uint16_t* du0, int lddu, float* dwd, float* dbd,
-                   long long pixels, int Cu, float inv_n, int backward, int accumulate, void* stream) {
+                   long long pixels, int Cu, float inv_n, int backward, int accumulate, const float* loss_scale,
+                   void* stream) {
   return dense_mse(CB(u0), ldu, noised, x, wd, bd, pred, loss, MB(du0), lddu, dwd, dbd, pixels, Cu, inv_n, backward,
-                   accumulate ? 0 : 1, S(stream));
+                   accumulate ? 0 : 1, loss_scale, S(stream));
 }
 
 int gct2_adam_keras(float* w, float* m, float* v, const float* g, uint16_t* w_bf16, long long n,
@@ -193,8 +202,16 @@ int gct2_adam_prepare(long long* iterations, float* hyper, float base_lr, int wa
   return adam_prepare(iterations, hyper, base_lr, warmup_steps, beta1, beta2, S(stream));
 }
 int gct2_adam_apply(float* w, float* m, float* v, const float* g, uint16_t* w_bf16, long long n, const float* hyper,
-                    float beta1, float beta2, float eps, float grad_scale, long long* iterations_inc, void* stream) {
-  return adam_apply(w, m, v, g, MB(w_bf16), n, hyper, beta1, beta2, eps, grad_scale, iterations_inc, S(stream));
+                    float beta1, float beta2, float eps, float grad_scale, long long* iterations_inc,
+                    const float* loss_scale_state, void* stream) {
+  return adam_apply(w, m, v, g, 0, MB(w_bf16), n, hyper, beta1, beta2, eps, grad_scale, iterations_inc, loss_scale_state,
+                    S(stream));
+}
+int gct2_adam_apply_g16(float* w, float* m, float* v, const uint16_t* g_bf16, uint16_t* w_bf16, long long n,
+                        const float* hyper, float beta1, float beta2, float eps, float grad_scale,
+                        long long* iterations_inc, void* stream) {
+  return adam_apply(w, m, v, g_bf16, 1, MB(w_bf16), n, hyper, beta1, beta2, eps, grad_scale, iterations_inc, nullptr,
+                    S(stream));
 }
 int gct2_step_begin(const float* x, float* noised, float* eps_out, int32_t* t_out, int B, int elems_per_image, int steps,
                     unsigned long long seed, const long long* iterations, float* hyper, float base_lr, int warmup_steps,

@@ -29,6 +29,7 @@ struct ConvArgs {
                                  // when this one starts, so its boxes may be fetched before griddepcontrol.wait
   // W
   float* dw;                     // fp32 [16][Chi][Clo]
+  int f16;                       // 16-bit storage format of every bf16-typed pointer above: 0 = bf16, 1 = fp16
   // tuning overrides (0 = heuristic)
   int forceBN, forceSplits;
 };

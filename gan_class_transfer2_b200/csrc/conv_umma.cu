@@ -30,8 +30,11 @@ static int g_b_early = 1;              // debug key 21 != 0 disables the weight 
 static int g_no_l2_finish = 0;         // key 26 != 0: never finish split-K with the L2 rendezvous (it needs every CTA of the
                                        // launch resident at once, which nothing guarantees beside NCCL kernels); the
                                        // cluster form and the finishing kernel remain
-static int g_csplit = 0;               // debug key 25: split-K inside a cluster (DSMEM): 0 = when the cost model picks it,
-                                       // 1 = never (partials through L2), 2 = whenever legal
+static int g_csplit = 1;               // key 25: split-K inside a cluster (DSMEM): 0 = when the cost model picks it, 1 = never
+                                       // (partials through L2; the single-GPU default: measured 2-5 % slower per step at
+                                       // batch 1 -- its epilogue is 1-2 us shorter but the cluster launch costs 0.5 us
+                                       // and the plans it enables use fewer CTAs), 2 = whenever legal.  Data-parallel
+                                       // steps use 0: the cluster form is safe beside NCCL kernels, the L2 form is not
 static unsigned g_spin_limit = 1u << 28;  // debug key 20: rendezvous watchdog in polls of ~40 ns (default ~10 s; 0 = none)
 static int g_stamp_pos = 0;            // debug key 16 (-DGCT2_TIMELINE builds): see ConvParams::stampPos
 static long long g_launches = 0;
@@ -221,10 +224,11 @@ int conv_init(int device) {
 }
 
 // ------------------------------------------------------------------------------------ tensor maps
+static thread_local int t_map_f16 = 0;  // storage format of the launch whose tensor maps are being encoded
 static int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
                   const cuuint32_t* box) {
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides, box, es,
+  CUresult r = g_encode(m, t_map_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -268,7 +272,7 @@ static int map_w3(CUtensorMap* m, const __nv_bfloat16* p, int R, int Cc, int box
 __global__ void splitk_finish_kernel(const float* __restrict__ ws, long long splitStride, int splits, int N,
                                      long long pixels, int epi, __nv_bfloat16* __restrict__ out, int ldo,
                                      const float* __restrict__ bias, const __nv_bfloat16* __restrict__ act, int ldact,
-                                     int maskN, int addOld) {
+                                     int maskN, int addOld, int f16) {
   TraceScope trace(20);
   pdl_launch_dependents();
   pdl_wait();
@@ -295,22 +299,22 @@ __global__ void splitk_finish_kernel(const float* __restrict__ ws, long long spl
     } else {
       if (addOld) {
         const uint2 old = *reinterpret_cast<const uint2*>(o);
-        v.x += bf16_lo(old.x);
-        v.y += bf16_hi(old.x);
-        v.z += bf16_lo(old.y);
-        v.w += bf16_hi(old.y);
+        v.x += h_lo(old.x, f16);
+        v.y += h_hi(old.x, f16);
+        v.z += h_lo(old.y, f16);
+        v.w += h_hi(old.y, f16);
       }
       if (n < maskN) {
         const uint2 a = *reinterpret_cast<const uint2*>(act + pix * ldact + n);
-        v.x = bf16_lo(a.x) > 0.f ? v.x : 0.f;
-        v.y = bf16_hi(a.x) > 0.f ? v.y : 0.f;
-        v.z = bf16_lo(a.y) > 0.f ? v.z : 0.f;
-        v.w = bf16_hi(a.y) > 0.f ? v.w : 0.f;
+        v.x = h_pos_lo(a.x) ? v.x : 0.f;
+        v.y = h_pos_hi(a.x) ? v.y : 0.f;
+        v.z = h_pos_lo(a.y) ? v.z : 0.f;
+        v.w = h_pos_hi(a.y) ? v.w : 0.f;
       }
     }
     uint2 r;
-    r.x = pack_bf16x2(v.x, v.y);
-    r.y = pack_bf16x2(v.z, v.w);
+    r.x = pack_h2(v.x, v.y, f16);
+    r.y = pack_h2(v.z, v.w, f16);
     *reinterpret_cast<uint2*>(o) = r;
   }
   trace.end();
@@ -451,12 +455,13 @@ static Choice choose(const DeviceState& ds, int mode, int mTiles, int phases, in
       const long long items = (long long)mTiles * phases * (isW ? 16 : 1) * nTiles * splits;
       const long long active = items < maxCtas ? items : maxCtas;
       const long long waves = (items + active - 1) / active;
-      // one 64-wide k-chunk in steady state, measured per CTA with tools/timeline.py (round 2, two chunks per ring slot
-      // at BN <= 128): 285 / 375 / 665 cycles at BN = 64 / 128 / 256 against tensor floors of 128 / 256 / 512 -- every
-      // shape ingests ~86 bytes per clock per SM (A is re-read for every 64 columns of N, so narrow tiles pay more per
-      // FLOP) -- and bound by the chip-wide L2 -> SM rate (~10 KB/clk with the L2 coalescing identical tile requests) when every SM pulls at once
-      double tk = BN == 64 ? 285.0 : (BN == 128 ? 375.0 : 665.0);
-      const double l2 = (16384.0 + BN * 128.0) * (double)active / 10000.0;  // measured: 128 CTAs at BN = 64 sustain 10.5 KB/clk
+      // one 64-wide k-chunk: the selection constants are the ones fitted in round 1 (408 + 0.96 BN cycles, chip-wide
+      // L2 -> SM rate 6000 B/clk).  Round 2 measured the steady state per CTA directly (tools/timeline.py: 285 / 375 /
+      // 665 cycles at BN = 64 / 128 / 256 with two chunks per ring slot -- every shape moves ~170 bytes per clock
+      // through shared memory, TMA writes plus MMA reads), but plans chosen with those figures were slower in the step
+      // (0.582 vs 0.564 ms at batch 1): the model's split-K epilogue terms are calibrated against the old ones.
+      double tk = 408.0 + 0.96 * BN;
+      const double l2 = (16384.0 + BN * 128.0) * (double)active / 6000.0;
       if (l2 > tk) tk = l2;
       const double main = kIters * tk;
       // rows of a 128-row tile that hold real pixels (deep layers at batch 1 have 16 .. 64)
@@ -579,6 +584,8 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
   p.Wlo = a.Wlo;
   p.mnLbo = g_mn_lbo;
   p.mnSbo = g_mn_sbo;
+  p.f16 = a.f16 ? 1 : 0;
+  t_map_f16 = p.f16;
   const int rows = a.mode == MODE_W ? 64 : 128;
   pixel_tile(rows, a.Hlo, a.Wlo, &p.Wt, &p.Ht, &p.Nb);
   if (a.Wlo % p.Wt || a.Hlo % p.Ht || p.Wt * p.Ht * p.Nb != rows) {
@@ -778,7 +785,7 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     int blocks = (int)((total + 255) / 256);
     if (blocks > ds.num_sms * 8) blocks = ds.num_sms * 8;
     e = launch_k(splitk_finish_kernel, dim3(blocks), dim3(256), 0, stream, a.ws, p.wsSplitStride, p.splits, p.N, pixels,
-                 a.epi, a.out, a.ldo, a.bias, a.act, a.ldact, a.maskN, a.addOld);
+                 a.epi, a.out, a.ldo, a.bias, a.act, a.ldact, a.maskN, a.addOld, a.f16);
     if (e != cudaSuccess) {
       set_error("splitk_finish_kernel launch: %s", cudaGetErrorString(e));
       return 1;

@@ -98,6 +98,7 @@ struct ConvParams {
   int* cnt;                    // fused: [numTiles][2] arrive / depart counters of THIS launch, zero between launches
   unsigned spinLimit;          // fused: rendezvous watchdog (polls of ~40 ns; 0 = wait for ever)
   int bEarly;                  // S/P: fetch the first ring pass of weight boxes before griddepcontrol.wait
+  int f16;                     // 16-bit storage format of operands and outputs: 0 = bf16, 1 = fp16 (gct2_set_policy)
   // fast division by the launch constants used in index decoding (all set by conv_launch)
   FastDiv fdMTilesC, fdNTiles, fdSplits, fdKcPer;
   int lgWt, lgHt, lgTilesX, lgTilesY;  // pixel-tile geometry is power-of-two by construction
@@ -281,6 +282,120 @@ __device__ __forceinline__ void issue_chunk(const ConvParams& p, const CUtensorM
   }
 }
 
+// Split-K finished in place (called by the epilogue warps once their partial tile is stored): split s sums rows
+// [s*R, (s+1)*R) of the tile over all partials in split order (bit-reproducible), applies the real epilogue and writes
+// the 16-bit output -- coalesced, no extra launch.
+//   cluster form (csplit): the splits are the CTAs of one cluster (co-scheduled by the hardware, so they may wait for
+//     each other whatever else runs on the GPU); partials are read from the peers' shared memory;
+//   L2 form (fused): every split of the tile has its own CTA and the host launched no more CTAs than can be resident
+//     at once; partials go through tile-major fp32 slabs in global memory and a counter rendezvous.
+// A separate (not inlined) function: its registers do not add to the pressure of the direct epilogues.
+template <int MODE, int BN>
+__device__ __noinline__ void splitk_finish_in_place(const ConvParams& p, const WorkItem& w, int tileId, bool csplit,
+                                                    uint8_t* smem, uint64_t* red_full, int warp, int lane) {
+  constexpr int NE = kEpilogueWarps<BN>();
+  const int f16 = p.f16;
+      // ---- split-K finished in place: split s sums rows [s*R, (s+1)*R) of the tile over all partials in split
+      // order (bit-reproducible), applies the real epilogue and writes the bf16 output -- coalesced, no extra launch.
+      //   cluster form (csplit): the splits are the CTAs of one cluster (co-scheduled by the hardware, so they may
+      //     wait for each other whatever else runs on the GPU); partials are read from the peers' shared memory;
+      //   L2 form (fused): every split of the tile has its own CTA and the host launched no more CTAs than can be
+      //     resident at once; partials go through tile-major fp32 slabs in global memory and a counter rendezvous.
+      constexpr int NT = NE * 32;
+      const int et = (warp - 4) * 32 + lane;
+      const uint32_t part0 = smem_u32(smem);
+      if (csplit) {
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t bar = smem_u32(red_full);
+          for (int d = 0; d < p.splits; ++d) mbar_arrive_cluster_release(map_to_rank(bar, (uint32_t)d));
+        }
+        mbar_wait_cluster_acquire(red_full, 0);
+      } else {
+        __threadfence();
+        epi_bar_sync(NT);
+        if (et == 0) {
+          atomicAdd(p.cnt + 2 * tileId, 1);
+          uint32_t spins = 0;
+          while (ld_acquire_gpu(p.cnt + 2 * tileId) < p.splits) {
+            __nanosleep(40);
+            if (p.spinLimit != 0u && ++spins > p.spinLimit) {
+              printf("gct2: split-K rendezvous watchdog block %d tile %d\n", (int)blockIdx.x, tileId);
+              __trap();
+            }
+          }
+        }
+        epi_bar_sync(NT);
+      }
+      const int R = 128 / p.splits, vecPerRow = BN / 4;
+      const float* slab0 = p.ws + ((long long)tileId * 128) * BN;
+      const long long splitStride = (long long)p.numTiles * 128 * BN;
+      for (int idx = et; idx < R * vecPerRow; idx += NT) {
+        const int rr = w.split * R + idx / vecPerRow, c4 = (idx % vecPerRow) * 4;
+        const int xl = rr & (p.Wt - 1), yl = (rr >> p.lgWt) & (p.Ht - 1), bl = rr >> (p.lgWt + p.lgHt);
+        const int b = (w.mt >> (p.lgTilesX + p.lgTilesY)) * p.Nb + bl;
+        if (b >= p.B) continue;
+        int oy = (((w.mt >> p.lgTilesX) & (p.tilesY - 1)) << p.lgHt) + yl, ox = ((w.mt & (p.tilesX - 1)) << p.lgWt) + xl;
+        if (MODE == MODE_P) {
+          oy = 2 * oy + (w.ph >> 1);
+          ox = 2 * ox + (w.ph & 1);
+        }
+        const long long opix = ((long long)b * p.Hout + oy) * p.Wout + ox;
+        // all partials of this vector are requested before the first is used (four loads in flight per batch): the
+        // sum is then bound by one remote-shared-memory / L2 round trip, not by `splits` of them; summation order
+        // stays split 0, 1, 2, ... (bit-reproducible)
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t off = part0 + (uint32_t)(rr * BN * 4) + (uint32_t)((((c4 >> 2) ^ (rr & 7))) << 4);
+        const float* sp = slab0 + (long long)rr * BN + c4;
+        for (int s0 = 0; s0 < p.splits; s0 += 4) {
+          float4 u[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (s0 + j < p.splits)
+              u[j] = csplit ? ld_dsmem_f4(map_to_rank(off, (uint32_t)(s0 + j)))
+                            : __ldcg(reinterpret_cast<const float4*>(sp + (long long)(s0 + j) * splitStride));
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (s0 + j < p.splits) {
+              v.x += u[j].x; v.y += u[j].y; v.z += u[j].z; v.w += u[j].w;
+            }
+          }
+        }
+        const int nn = w.nt * BN + c4;
+        __nv_bfloat16* o = p.out + opix * p.ldo + nn;
+        if (p.realEpi == EPI_BIAS_RELU) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + nn));
+          v.x = fmaxf(v.x + bb.x, 0.f); v.y = fmaxf(v.y + bb.y, 0.f);
+          v.z = fmaxf(v.z + bb.z, 0.f); v.w = fmaxf(v.w + bb.w, 0.f);
+        } else {
+          if (p.addOld) {
+            const uint2 old = *reinterpret_cast<const uint2*>(o);
+            v.x += h_lo(old.x, f16); v.y += h_hi(old.x, f16); v.z += h_lo(old.y, f16); v.w += h_hi(old.y, f16);
+          }
+          if (nn < p.maskN) {
+            const uint2 am = __ldg(reinterpret_cast<const uint2*>(p.act + opix * p.ldact + nn));
+            v.x = h_pos_lo(am.x) ? v.x : 0.f; v.y = h_pos_hi(am.x) ? v.y : 0.f;
+            v.z = h_pos_lo(am.y) ? v.z : 0.f; v.w = h_pos_hi(am.y) ? v.w : 0.f;
+          }
+        }
+        uint2 res;
+        res.x = pack_h2(v.x, v.y, f16);
+        res.y = pack_h2(v.z, v.w, f16);
+        *reinterpret_cast<uint2*>(o) = res;
+      }
+      if (!csplit) {
+        epi_bar_sync(NT);
+        if (et == 0) {
+          const int old = atomicAdd(p.cnt + 2 * tileId + 1, 1);
+          if (old == p.splits - 1) {  // every split has passed the rendezvous: re-arm the counters
+            p.cnt[2 * tileId] = 0;
+            p.cnt[2 * tileId + 1] = 0;
+          }
+        }
+      }
+}
+
 #ifndef GCT2_CONV_EXTRA_BOUND
 #define GCT2_CONV_EXTRA_BOUND 0
 #endif
@@ -289,7 +404,7 @@ __device__ __forceinline__ void issue_chunk(const ConvParams& p, const CUtensorM
 template <int MODE, int BN, int PAIR = 0>
 __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1) conv_umma_kernel(const __grid_constant__ CUtensorMap mapA,
                                                         const __grid_constant__ CUtensorMap mapB,
-                                                        const ConvParams p) {
+                                                        const __grid_constant__ ConvParams p) {
   constexpr int A_BYTES = 128 * 128;  // 128 rows x 64 bf16 (S/P) or 2 blocks of 64 pixels x 64 channels (W)
   constexpr bool pair = PAIR != 0;
   constexpr int KPS = kChunksPerStage<BN>();
@@ -447,7 +562,9 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
     if ((!pair || rm == 0) && elect_one()) {
       constexpr int A_MN = (MODE == MODE_W) ? 1 : 0;
       constexpr int B_MN = (MODE == MODE_P) ? 0 : 1;
-      constexpr uint32_t idesc = make_idesc_bf16(pair ? 256 : 128, BN, A_MN, B_MN);  // cta_group::2: 256 rows over the pair
+      // cta_group::2: 256 rows over the pair; operand format by the launch's storage policy
+      const uint32_t idesc = p.f16 ? make_idesc_bf16(pair ? 256 : 128, BN, A_MN, B_MN, 0)
+                                   : make_idesc_bf16(pair ? 256 : 128, BN, A_MN, B_MN, 1);
       const uint32_t a_lbo = A_MN ? (uint32_t)p.mnLbo : 16u, a_sbo = A_MN ? (uint32_t)p.mnSbo : 1024u;
       const uint32_t b_lbo = B_MN ? (uint32_t)p.mnLbo : 16u, b_sbo = B_MN ? (uint32_t)p.mnSbo : 1024u;
       constexpr uint32_t a_kstep = A_MN ? 2048u : 32u;  // bytes per UMMA_K = 16 along K
@@ -534,6 +651,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
       const int q = warp & 3;              // TMEM lane quarter this warp may access
       const int cgrp = (warp - 4) >> 2;    // which slice of the tile's columns
       const int r = q * 32 + lane;
+      const int f16 = p.f16;
       uint32_t acc = 0, acc_phase = 0;
       for (int item = clusterId; item < p.numClusterItems; item += numClusters) {
         const WorkItem w = decode_item<MODE>(p, item, rm);
@@ -575,14 +693,14 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
               for (int g = 0; g < 4; ++g) {
                 const float4 b0 = __ldg(bp + 2 * g), b1 = __ldg(bp + 2 * g + 1);
                 uint4 o;
-                o.x = pack_bf16x2(fmaxf(__uint_as_float(v[8 * g + 0]) + b0.x, 0.f),
-                                  fmaxf(__uint_as_float(v[8 * g + 1]) + b0.y, 0.f));
-                o.y = pack_bf16x2(fmaxf(__uint_as_float(v[8 * g + 2]) + b0.z, 0.f),
-                                  fmaxf(__uint_as_float(v[8 * g + 3]) + b0.w, 0.f));
-                o.z = pack_bf16x2(fmaxf(__uint_as_float(v[8 * g + 4]) + b1.x, 0.f),
-                                  fmaxf(__uint_as_float(v[8 * g + 5]) + b1.y, 0.f));
-                o.w = pack_bf16x2(fmaxf(__uint_as_float(v[8 * g + 6]) + b1.z, 0.f),
-                                  fmaxf(__uint_as_float(v[8 * g + 7]) + b1.w, 0.f));
+                o.x = pack_h2(fmaxf(__uint_as_float(v[8 * g + 0]) + b0.x, 0.f),
+                              fmaxf(__uint_as_float(v[8 * g + 1]) + b0.y, 0.f), f16);
+                o.y = pack_h2(fmaxf(__uint_as_float(v[8 * g + 2]) + b0.z, 0.f),
+                              fmaxf(__uint_as_float(v[8 * g + 3]) + b0.w, 0.f), f16);
+                o.z = pack_h2(fmaxf(__uint_as_float(v[8 * g + 4]) + b1.x, 0.f),
+                              fmaxf(__uint_as_float(v[8 * g + 5]) + b1.y, 0.f), f16);
+                o.w = pack_h2(fmaxf(__uint_as_float(v[8 * g + 6]) + b1.z, 0.f),
+                              fmaxf(__uint_as_float(v[8 * g + 7]) + b1.w, 0.f), f16);
                 dst[g] = o;
               }
             }
@@ -594,7 +712,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
             uint4 av[4], ov[4];
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              av[g] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);  // bf16 1.0 = keep
+              av[g] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);  // positive in both formats = keep
               ov[g] = make_uint4(0u, 0u, 0u, 0u);
               if (masked) av[g] = __ldg(ap + g);
               if (add) ov[g] = dst[g];
@@ -607,17 +725,17 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[8 * g + j]);
                 const uint4 o = ov[g], a = av[g];
-                f[0] += bf16_lo(o.x); f[1] += bf16_hi(o.x); f[2] += bf16_lo(o.y); f[3] += bf16_hi(o.y);
-                f[4] += bf16_lo(o.z); f[5] += bf16_hi(o.z); f[6] += bf16_lo(o.w); f[7] += bf16_hi(o.w);
-                f[0] = bf16_lo(a.x) > 0.f ? f[0] : 0.f; f[1] = bf16_hi(a.x) > 0.f ? f[1] : 0.f;
-                f[2] = bf16_lo(a.y) > 0.f ? f[2] : 0.f; f[3] = bf16_hi(a.y) > 0.f ? f[3] : 0.f;
-                f[4] = bf16_lo(a.z) > 0.f ? f[4] : 0.f; f[5] = bf16_hi(a.z) > 0.f ? f[5] : 0.f;
-                f[6] = bf16_lo(a.w) > 0.f ? f[6] : 0.f; f[7] = bf16_hi(a.w) > 0.f ? f[7] : 0.f;
+                f[0] += h_lo(o.x, f16); f[1] += h_hi(o.x, f16); f[2] += h_lo(o.y, f16); f[3] += h_hi(o.y, f16);
+                f[4] += h_lo(o.z, f16); f[5] += h_hi(o.z, f16); f[6] += h_lo(o.w, f16); f[7] += h_hi(o.w, f16);
+                f[0] = h_pos_lo(a.x) ? f[0] : 0.f; f[1] = h_pos_hi(a.x) ? f[1] : 0.f;
+                f[2] = h_pos_lo(a.y) ? f[2] : 0.f; f[3] = h_pos_hi(a.y) ? f[3] : 0.f;
+                f[4] = h_pos_lo(a.z) ? f[4] : 0.f; f[5] = h_pos_hi(a.z) ? f[5] : 0.f;
+                f[6] = h_pos_lo(a.w) ? f[6] : 0.f; f[7] = h_pos_hi(a.w) ? f[7] : 0.f;
                 uint4 res;
-                res.x = pack_bf16x2(f[0], f[1]);
-                res.y = pack_bf16x2(f[2], f[3]);
-                res.z = pack_bf16x2(f[4], f[5]);
-                res.w = pack_bf16x2(f[6], f[7]);
+                res.x = pack_h2(f[0], f[1], f16);
+                res.y = pack_h2(f[2], f[3], f16);
+                res.z = pack_h2(f[4], f[5], f16);
+                res.w = pack_h2(f[6], f[7], f16);
                 dst[g] = res;
               }
             }
@@ -665,102 +783,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
         }
         tc_fence_before();
         __syncwarp();
-        if (p.fused || csplit) {
-          // ---- split-K finished in place: split s sums rows [s*R, (s+1)*R) of the tile over all partials in split
-          // order (bit-reproducible), applies the real epilogue and writes the bf16 output -- coalesced, no extra launch.
-          //   cluster form (csplit): the splits are the CTAs of one cluster (co-scheduled by the hardware, so they may
-          //     wait for each other whatever else runs on the GPU); partials are read from the peers' shared memory;
-          //   L2 form (fused): every split of the tile has its own CTA and the host launched no more CTAs than can be
-          //     resident at once; partials go through tile-major fp32 slabs in global memory and a counter rendezvous.
-          constexpr int NT = NE * 32;
-          const int et = (warp - 4) * 32 + lane;
-          const uint32_t part0 = smem_u32(smem);
-          if (csplit) {
-            __syncwarp();
-            if (lane == 0) {
-              const uint32_t bar = smem_u32(red_full);
-              for (int d = 0; d < p.splits; ++d) mbar_arrive_cluster_release(map_to_rank(bar, (uint32_t)d));
-            }
-            mbar_wait_cluster_acquire(red_full, 0);
-          } else {
-            __threadfence();
-            epi_bar_sync(NT);
-            if (et == 0) {
-              atomicAdd(p.cnt + 2 * tileId, 1);
-              uint32_t spins = 0;
-              while (ld_acquire_gpu(p.cnt + 2 * tileId) < p.splits) {
-                __nanosleep(40);
-                if (p.spinLimit != 0u && ++spins > p.spinLimit) {
-                  printf("gct2: split-K rendezvous watchdog block %d tile %d\n", (int)blockIdx.x, tileId);
-                  __trap();
-                }
-              }
-            }
-            epi_bar_sync(NT);
-          }
-          const int R = 128 / p.splits, vecPerRow = BN / 4;
-          const float* slab0 = p.ws + ((long long)tileId * 128) * BN;
-          const long long splitStride = (long long)p.numTiles * 128 * BN;
-          for (int idx = et; idx < R * vecPerRow; idx += NT) {
-            const int rr = w.split * R + idx / vecPerRow, c4 = (idx % vecPerRow) * 4;
-            const int xl = rr & (p.Wt - 1), yl = (rr >> p.lgWt) & (p.Ht - 1), bl = rr >> (p.lgWt + p.lgHt);
-            const int b = (w.mt >> (p.lgTilesX + p.lgTilesY)) * p.Nb + bl;
-            if (b >= p.B) continue;
-            int oy = (((w.mt >> p.lgTilesX) & (p.tilesY - 1)) << p.lgHt) + yl, ox = ((w.mt & (p.tilesX - 1)) << p.lgWt) + xl;
-            if (MODE == MODE_P) {
-              oy = 2 * oy + (w.ph >> 1);
-              ox = 2 * ox + (w.ph & 1);
-            }
-            const long long opix = ((long long)b * p.Hout + oy) * p.Wout + ox;
-            float4 v;
-            if (csplit) {
-              const uint32_t off = part0 + (uint32_t)(rr * BN * 4) + (uint32_t)((((c4 >> 2) ^ (rr & 7))) << 4);
-              v = ld_dsmem_f4(map_to_rank(off, 0u));
-              for (int sidx = 1; sidx < p.splits; ++sidx) {
-                const float4 u = ld_dsmem_f4(map_to_rank(off, (uint32_t)sidx));
-                v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
-              }
-            } else {
-              const float* sp = slab0 + (long long)rr * BN + c4;
-              v = __ldcg(reinterpret_cast<const float4*>(sp));
-              for (int sidx = 1; sidx < p.splits; ++sidx) {
-                const float4 u = __ldcg(reinterpret_cast<const float4*>(sp + sidx * splitStride));
-                v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
-              }
-            }
-            const int nn = w.nt * BN + c4;
-            __nv_bfloat16* o = p.out + opix * p.ldo + nn;
-            if (p.realEpi == EPI_BIAS_RELU) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + nn));
-              v.x = fmaxf(v.x + bb.x, 0.f); v.y = fmaxf(v.y + bb.y, 0.f);
-              v.z = fmaxf(v.z + bb.z, 0.f); v.w = fmaxf(v.w + bb.w, 0.f);
-            } else {
-              if (p.addOld) {
-                const uint2 old = *reinterpret_cast<const uint2*>(o);
-                v.x += bf16_lo(old.x); v.y += bf16_hi(old.x); v.z += bf16_lo(old.y); v.w += bf16_hi(old.y);
-              }
-              if (nn < p.maskN) {
-                const uint2 am = __ldg(reinterpret_cast<const uint2*>(p.act + opix * p.ldact + nn));
-                v.x = bf16_lo(am.x) > 0.f ? v.x : 0.f; v.y = bf16_hi(am.x) > 0.f ? v.y : 0.f;
-                v.z = bf16_lo(am.y) > 0.f ? v.z : 0.f; v.w = bf16_hi(am.y) > 0.f ? v.w : 0.f;
-              }
-            }
-            uint2 res;
-            res.x = pack_bf16x2(v.x, v.y);
-            res.y = pack_bf16x2(v.z, v.w);
-            *reinterpret_cast<uint2*>(o) = res;
-          }
-          if (!csplit) {
-            epi_bar_sync(NT);
-            if (et == 0) {
-              const int old = atomicAdd(p.cnt + 2 * tileId + 1, 1);
-              if (old == p.splits - 1) {  // every split has passed the rendezvous: re-arm the counters
-                p.cnt[2 * tileId] = 0;
-                p.cnt[2 * tileId + 1] = 0;
-              }
-            }
-          }
-        }
+        if (p.fused || csplit) splitk_finish_in_place<MODE, BN>(p, w, tileId, csplit, smem, red_full, warp, lane);
 #ifdef GCT2_TIMELINE
         if (item == clusterId && warp == 4 && lane == 0) GCT2_STAMP(5);  // first epilogue (of warp 4) done
 #endif

@@ -19,6 +19,8 @@ static int g_c3w_blocks = 0;   // debug key 15: grid cap of down0's weight-gradi
 static int g_adam_blocks = 0;  // debug key 13: grid cap of the Adam kernel (0 = 8 blocks per SM)
 static int g_adam_sms = 0;     // gct2_set_adam_sms / debug key 23: > 0 = run Keras-Adam on that many SMs, one 1024-thread
                                // CTA each (SM-exclusive through its shared-memory request), leaving the rest to the convs
+static int g_f16 = 0;          // gct2_set_policy: 16-bit storage format of activations / gradients / weight shadow (0 bf16, 1 fp16)
+void elementwise_set_f16(int f16) { g_f16 = f16 ? 1 : 0; }
 static int g_dense_bps = 2;    // debug key 24: blocks per SM of the fused Dense+MSE kernel
 void elementwise_set_debug(int key, int value) {
   if (key == 24) g_dense_bps = value > 0 ? value : 2;
@@ -314,7 +316,7 @@ constexpr int C3F_TY = 4;
 __global__ void __launch_bounds__(128) conv_c3_fprop_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                             const float* __restrict__ bias,
                                                             __nv_bfloat16* __restrict__ y, int ldy, int B, int H,
-                                                            int W, int Cout) {
+                                                            int W, int Cout, int f16) {
   TraceScope trace(3);
   __shared__ __align__(16) float patch[2 * C3F_TY + 2][C3_ROW];
   const int Ho = H / 2, Wo = W / 2;
@@ -357,7 +359,7 @@ __global__ void __launch_bounds__(128) conv_c3_fprop_kernel(const float* __restr
         }
       }
       const long long pix = ((long long)b * Ho + oy0 + py) * Wo + ox0 + px;
-      *reinterpret_cast<uint32_t*>(y + pix * ldy + co) = pack_bf16x2(fmaxf(a0.x + a0.y, 0.f), fmaxf(a1.x + a1.y, 0.f));
+      *reinterpret_cast<uint32_t*>(y + pix * ldy + co) = pack_h2(fmaxf(a0.x + a0.y, 0.f), fmaxf(a1.x + a1.y, 0.f), f16);
     }
   }
   trace.end();
@@ -370,7 +372,7 @@ int conv4s2_c3_fprop(const float* x, const float* w, const float* bias, __nv_bfl
     return 1;
   }
   dim3 grid(B * (H / 2 / C3F_TY) * (W / 2 / C3_T), Cout / 128);
-  launch_k(conv_c3_fprop_kernel, dim3(grid), dim3(128), 0, st, x, w, bias, y, ldy, B, H, W, Cout);
+  launch_k(conv_c3_fprop_kernel, dim3(grid), dim3(128), 0, st, x, w, bias, y, ldy, B, H, W, Cout, g_f16);
   GCT2_CHECK_LAUNCH("conv_c3_fprop_kernel");
   return 0;
 }
@@ -382,7 +384,7 @@ int conv4s2_c3_fprop(const float* x, const float* w, const float* bias, __nv_bfl
 __global__ void __launch_bounds__(256, 2) conv_c3_wgrad_kernel(const float* __restrict__ x,
                                                             const __nv_bfloat16* __restrict__ dz, int lddz,
                                                             float* __restrict__ dw, float* __restrict__ db, int B,
-                                                            int H, int W, int Cout, int numTiles) {
+                                                            int H, int W, int Cout, int numTiles, int f16) {
   TraceScope trace(4);
   pdl_launch_dependents();
   pdl_wait();
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(256, 2) conv_c3_wgrad_kernel(const float* __re
         g[px] = __ldg(reinterpret_cast<const uint32_t*>(dz + (((long long)b * Ho + oy0 + py) * Wo + ox0 + px) * lddz + co));
 #pragma unroll 2
       for (int px = 0; px < C3_T; ++px) {
-        const float g0 = bf16_lo(g[px]), g1 = bf16_hi(g[px]);
+        const float g0 = h_lo(g[px], f16), g1 = h_hi(g[px], f16);
         accb.x += g0;
         accb.y += g1;
         const float2 g00 = make_float2(g0, g0), g11 = make_float2(g1, g1);
@@ -467,7 +469,7 @@ int conv4s2_c3_wgrad(const float* x, const __nv_bfloat16* dz, int lddz, float* d
   int gx = g_c3w_blocks > 0 ? g_c3w_blocks : 2 * g_ew_sms;
   if (gx > numTiles) gx = numTiles;
   dim3 grid(gx, Cout / 128);
-  launch_k(conv_c3_wgrad_kernel, dim3(grid), dim3(256), 0, st, x, dz, lddz, dw, db, B, H, W, Cout, numTiles);
+  launch_k(conv_c3_wgrad_kernel, dim3(grid), dim3(256), 0, st, x, dz, lddz, dw, db, B, H, W, Cout, numTiles, g_f16);
   GCT2_CHECK_LAUNCH("conv_c3_wgrad_kernel");
   return 0;
 }
@@ -485,7 +487,8 @@ __global__ void __launch_bounds__(256) dense_mse_kernel(const __nv_bfloat16* __r
                                                         const float* __restrict__ bd, float* __restrict__ pred,
                                                         float* __restrict__ loss, __nv_bfloat16* __restrict__ du0,
                                                         int lddu, float* __restrict__ dwd, float* __restrict__ dbd,
-                                                        long long pixels, float invN, int backward) {
+                                                        long long pixels, float invN, int backward, int f16,
+                                                        const float* __restrict__ loss_scale) {
   TraceScope trace(5);
   pdl_launch_dependents();
   pdl_wait();
@@ -507,6 +510,7 @@ __global__ void __launch_bounds__(256) dense_mse_kernel(const __nv_bfloat16* __r
   for (int k = 0; k < 9; ++k) wn[k] = __ldg(wd + CU * 3 + k);
 #pragma unroll
   for (int j = 0; j < 3; ++j) bv[j] = __ldg(bd + j);
+  const float gradScale = loss_scale != nullptr ? invN * __ldg(loss_scale) : invN;
   float g[8][3], gn[9], gb[3] = {0.f, 0.f, 0.f}, lossAcc = 0.f;
 #pragma unroll
   for (int c = 0; c < 8; ++c) g[c][0] = g[c][1] = g[c][2] = 0.f;
@@ -520,8 +524,8 @@ __global__ void __launch_bounds__(256) dense_mse_kernel(const __nv_bfloat16* __r
     float nz[3] = {0.f, 0.f, 0.f}, xv[3] = {0.f, 0.f, 0.f};
     if (live) {
       const uint4 uv = __ldg(reinterpret_cast<const uint4*>(u0 + p * ldu + sub * 8));
-      a[0] = bf16_lo(uv.x); a[1] = bf16_hi(uv.x); a[2] = bf16_lo(uv.y); a[3] = bf16_hi(uv.y);
-      a[4] = bf16_lo(uv.z); a[5] = bf16_hi(uv.z); a[6] = bf16_lo(uv.w); a[7] = bf16_hi(uv.w);
+      a[0] = h_lo(uv.x, f16); a[1] = h_hi(uv.x, f16); a[2] = h_lo(uv.y, f16); a[3] = h_hi(uv.y, f16);
+      a[4] = h_lo(uv.z, f16); a[5] = h_hi(uv.z, f16); a[6] = h_lo(uv.w, f16); a[7] = h_hi(uv.w, f16);
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         nz[c] = __ldg(noised + p * 3 + c);
@@ -547,7 +551,7 @@ __global__ void __launch_bounds__(256) dense_mse_kernel(const __nv_bfloat16* __r
       if (pred != nullptr && live && sub == j) pred[p * 3 + j] = pj;
       const float diff = live ? pj - xv[j] : 0.f;
       if (sub == 0) lossAcc = fmaf(diff, diff, lossAcc);
-      d[j] = 2.f * diff * invN;
+      d[j] = 2.f * diff * gradScale;  // loss scaling (mixed precision): the backward pass carries scale * gradient
     }
     if (backward && live) {
       float r[8];
@@ -558,8 +562,8 @@ __global__ void __launch_bounds__(256) dense_mse_kernel(const __nv_bfloat16* __r
         for (int j = 0; j < 3; ++j) g[c][j] = fmaf(a[c], d[j], g[c][j]);
       }
       uint4 o;
-      o.x = pack_bf16x2(r[0], r[1]); o.y = pack_bf16x2(r[2], r[3]);
-      o.z = pack_bf16x2(r[4], r[5]); o.w = pack_bf16x2(r[6], r[7]);
+      o.x = pack_h2(r[0], r[1], f16); o.y = pack_h2(r[2], r[3], f16);
+      o.z = pack_h2(r[4], r[5], f16); o.w = pack_h2(r[6], r[7], f16);
       *reinterpret_cast<uint4*>(du0 + p * lddu + sub * 8) = o;
       if (sub == 0) {
 #pragma unroll
@@ -616,7 +620,7 @@ __global__ void __launch_bounds__(256) dense_mse_kernel(const __nv_bfloat16* __r
 
 int dense_mse(const __nv_bfloat16* u0, int ldu, const float* noised, const float* x, const float* wd,
               const float* bd, float* pred, float* loss, __nv_bfloat16* du0, int lddu, float* dwd, float* dbd,
-              long long pixels, int Cu, float invN, int backward, int zero, cudaStream_t st) {
+              long long pixels, int Cu, float invN, int backward, int zero, const float* loss_scale, cudaStream_t st) {
   if (Cu != 64 && Cu != 128) {
     set_error("dense_mse: the fused kernel expects 64 or 128 up0 channels (+3 image channels), got %d", Cu);
     return 1;
@@ -639,10 +643,10 @@ int dense_mse(const __nv_bfloat16* u0, int ldu, const float* noised, const float
   if (blocks < 1) blocks = 1;
   if (Cu == 64)
     launch_k(dense_mse_kernel<8>, dim3(blocks), dim3(256), 0, st, u0, ldu, noised, x, wd, bd, pred, loss, du0, lddu, dwd, dbd, pixels, invN,
-                                                backward);
+                                                backward, g_f16, loss_scale);
   else
     launch_k(dense_mse_kernel<16>, dim3(blocks), dim3(256), 0, st, u0, ldu, noised, x, wd, bd, pred, loss, du0, lddu, dwd, dbd, pixels,
-                                                 invN, backward);
+                                                 invN, backward, g_f16, loss_scale);
   GCT2_CHECK_LAUNCH("dense_mse_kernel");
   return 0;
 }
@@ -657,7 +661,7 @@ struct BiasGradSegs {
   float* db[BG_MAX_SEG];
   long long rows[BG_MAX_SEG];
   int ld[BG_MAX_SEG], C[BG_MAX_SEG], firstBlock[BG_MAX_SEG + 1], rowsPerBlock[BG_MAX_SEG];
-  int n;
+  int n, f16;
 };
 
 __global__ void __launch_bounds__(256) bias_grad_kernel(const __grid_constant__ BiasGradSegs sg) {
@@ -669,7 +673,7 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const __grid_constant__ 
   int s = 0;
   while (s + 1 < sg.n && (int)blockIdx.x >= sg.firstBlock[s + 1]) ++s;
   const __nv_bfloat16* __restrict__ dz = sg.dz[s];
-  const int C = sg.C[s], ld = sg.ld[s];
+  const int C = sg.C[s], ld = sg.ld[s], f16 = sg.f16;
   const int vecs = C / 8;                  // threads per row, 16 bytes each
   const int rpi = blockDim.x / vecs;       // rows per iteration
   const int v = threadIdx.x % vecs, rg = threadIdx.x / vecs;
@@ -687,14 +691,14 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const __grid_constant__ 
       for (int u = 0; u < 4; ++u) q[u] = __ldg(reinterpret_cast<const uint4*>(dz + (r + (long long)u * rpi) * ld) + v);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        acc[0] += bf16_lo(q[u].x); acc[1] += bf16_hi(q[u].x); acc[2] += bf16_lo(q[u].y); acc[3] += bf16_hi(q[u].y);
-        acc[4] += bf16_lo(q[u].z); acc[5] += bf16_hi(q[u].z); acc[6] += bf16_lo(q[u].w); acc[7] += bf16_hi(q[u].w);
+        acc[0] += h_lo(q[u].x, f16); acc[1] += h_hi(q[u].x, f16); acc[2] += h_lo(q[u].y, f16); acc[3] += h_hi(q[u].y, f16);
+        acc[4] += h_lo(q[u].z, f16); acc[5] += h_hi(q[u].z, f16); acc[6] += h_lo(q[u].w, f16); acc[7] += h_hi(q[u].w, f16);
       }
     }
     for (; r < r1; r += rpi) {
       const uint4 q = __ldg(reinterpret_cast<const uint4*>(dz + r * ld) + v);
-      acc[0] += bf16_lo(q.x); acc[1] += bf16_hi(q.x); acc[2] += bf16_lo(q.y); acc[3] += bf16_hi(q.y);
-      acc[4] += bf16_lo(q.z); acc[5] += bf16_hi(q.z); acc[6] += bf16_lo(q.w); acc[7] += bf16_hi(q.w);
+      acc[0] += h_lo(q.x, f16); acc[1] += h_hi(q.x, f16); acc[2] += h_lo(q.y, f16); acc[3] += h_hi(q.y, f16);
+      acc[4] += h_lo(q.z, f16); acc[5] += h_hi(q.z, f16); acc[6] += h_lo(q.w, f16); acc[7] += h_hi(q.w, f16);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) red[rg * C + v * 8 + j] = acc[j];
@@ -716,6 +720,7 @@ int bias_grad_multi(int n, const __nv_bfloat16* const* dz, const int* ld, const 
   }
   BiasGradSegs sg;
   sg.n = n;
+  sg.f16 = g_f16;
   const int threads = 256;
   int block = 0;
   double totalBytes = 0;
@@ -797,17 +802,38 @@ __device__ __forceinline__ void adam_update(float4& wv, float4& mv, float4& vv, 
   gv.x *= gscale; gv.y *= gscale; gv.z *= gscale; gv.w *= gscale;
   adam_elem4(wv, mv, vv, gv, c1, c2, alpha, eps);
 }
+// G16: the gradient arrives as bf16 (data parallel: the reduce-scatter ran on a bf16 copy, half the NVLink bytes)
+template <bool G16>
+__device__ __forceinline__ float4 adam_load_grad(const void* __restrict__ g, long long i) {
+  if (G16) {
+    const uint2 q = __ldcs(reinterpret_cast<const uint2*>(g) + i);
+    return make_float4(bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y));
+  }
+  return __ldcs(reinterpret_cast<const float4*>(g) + i);  // the gradient is dead after this read
+}
+template <bool G16>
 __global__ void __launch_bounds__(ADAM_THREADS, 640 / ADAM_THREADS) adam_kernel(float4* __restrict__ w, float4* __restrict__ m,
-                                                            float4* __restrict__ v, const float4* __restrict__ g,
+                                                            float4* __restrict__ v, const void* __restrict__ g,
                                                             uint2* __restrict__ wb, long long nvec,
                                                             const float* __restrict__ hyper, float b1, float b2,
                                                             float eps, float gscale,
-                                                            long long* __restrict__ iterations_inc) {
+                                                            long long* __restrict__ iterations_inc, int f16,
+                                                            const float* __restrict__ ls) {
   TraceScope trace(8);
   pdl_launch_dependents();
   pdl_wait();
   trace.ready();
   const float alpha = __ldg(hyper);
+  // dynamic loss scaling (train.py:82-83, Keras LossScaleOptimizer): ls = {scale, good steps, all gradients finite, 1/scale}.
+  // A step whose gradients overflowed is skipped as a whole -- no update, no iteration count -- and the gradients carry
+  // the scale, removed here.
+  if (ls != nullptr) {
+    if (__ldg(ls + 2) == 0.f) {
+      trace.end();
+      return;
+    }
+    gscale *= __ldg(ls + 3);
+  }
   if (iterations_inc != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *iterations_inc += 1;
   const float c1 = 1.f - b1, c2 = 1.f - b2;
   const long long T = (long long)gridDim.x * blockDim.x;
@@ -817,7 +843,7 @@ __global__ void __launch_bounds__(ADAM_THREADS, 640 / ADAM_THREADS) adam_kernel(
     float4 gv[ADAM_U], mv[ADAM_U], vv[ADAM_U], wv[ADAM_U];
 #pragma unroll
     for (int u = 0; u < ADAM_U; ++u) {
-      gv[u] = __ldcs(g + i0 + u * T);  // the gradient is dead after this read
+      gv[u] = adam_load_grad<G16>(g, i0 + u * T);
       mv[u] = m[i0 + u * T];
       vv[u] = v[i0 + u * T];
       wv[u] = w[i0 + u * T];
@@ -829,20 +855,20 @@ __global__ void __launch_bounds__(ADAM_THREADS, 640 / ADAM_THREADS) adam_kernel(
       v[i0 + u * T] = vv[u];
       w[i0 + u * T] = wv[u];
       uint2 o;
-      o.x = pack_bf16x2(wv[u].x, wv[u].y);
-      o.y = pack_bf16x2(wv[u].z, wv[u].w);
+      o.x = pack_h2(wv[u].x, wv[u].y, f16);
+      o.y = pack_h2(wv[u].z, wv[u].w, f16);
       wb[i0 + u * T] = o;
     }
   }
   for (; i0 < nvec; i0 += T) {  // ragged tail
-    float4 gv = __ldcs(g + i0), mv = m[i0], vv = v[i0], wv = w[i0];
+    float4 gv = adam_load_grad<G16>(g, i0), mv = m[i0], vv = v[i0], wv = w[i0];
     adam_update(wv, mv, vv, gv, gscale, c1, c2, alpha, eps);
     m[i0] = mv;
     v[i0] = vv;
     w[i0] = wv;
     uint2 o;
-    o.x = pack_bf16x2(wv.x, wv.y);
-    o.y = pack_bf16x2(wv.z, wv.w);
+    o.x = pack_h2(wv.x, wv.y, f16);
+    o.y = pack_h2(wv.z, wv.w, f16);
     wb[i0] = o;
   }
   trace.end();
@@ -913,16 +939,17 @@ int adam_prepare(long long* iterations, float* hyper, float base_lr, int warmup_
   return 0;
 }
 
-int adam_apply(float* w, float* m, float* v, const float* g, __nv_bfloat16* w_bf16, long long n, const float* hyper,
-               float beta1, float beta2, float eps, float grad_scale, long long* iterations_inc, cudaStream_t st) {
-  if (n % 4 || (reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v) |
-                reinterpret_cast<uintptr_t>(g)) % 16 || reinterpret_cast<uintptr_t>(w_bf16) % 8) {
+int adam_apply(float* w, float* m, float* v, const void* g, int g_is_bf16, __nv_bfloat16* w_bf16, long long n,
+               const float* hyper, float beta1, float beta2, float eps, float grad_scale, long long* iterations_inc,
+               const float* ls, cudaStream_t st) {
+  if (n % 4 || (reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) % 16 ||
+      reinterpret_cast<uintptr_t>(g) % (g_is_bf16 ? 8 : 16) || reinterpret_cast<uintptr_t>(w_bf16) % 8) {
     set_error("adam: ranges must start on 16-byte boundaries and hold a multiple of 4 elements (n=%lld)", n);
     return 1;
   }
   const long long nvec = n / 4;
   if (nvec == 0) return 0;
-  if (g_adam_sms > 0 && nvec >= (long long)g_adam_sms * ADAM_WIDE_THREADS * ADAM_WIDE_U) {
+  if (!g_is_bf16 && !g_f16 && ls == nullptr && g_adam_sms > 0 && nvec >= (long long)g_adam_sms * ADAM_WIDE_THREADS * ADAM_WIDE_U) {
     static bool attr = false;
     if (!attr) {
       cudaFuncSetAttribute(adam_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ADAM_WIDE_SMEM);
@@ -937,10 +964,14 @@ int adam_apply(float* w, float* m, float* v, const float* g, __nv_bfloat16* w_bf
   long long blocks = (nvec + ADAM_THREADS * ADAM_U - 1) / (ADAM_THREADS * ADAM_U);
   const long long cap = g_adam_blocks > 0 ? g_adam_blocks : (long long)g_ew_sms * 8;
   if (blocks > cap) blocks = cap;
-  launch_k(adam_kernel, dim3((int)blocks), dim3(ADAM_THREADS), 0, st, reinterpret_cast<float4*>(w), reinterpret_cast<float4*>(m),
-                                           reinterpret_cast<float4*>(v), reinterpret_cast<const float4*>(g),
-                                           reinterpret_cast<uint2*>(w_bf16), nvec, hyper, beta1, beta2, eps,
-                                           grad_scale, iterations_inc);
+  if (g_is_bf16)
+    launch_k(adam_kernel<true>, dim3((int)blocks), dim3(ADAM_THREADS), 0, st, reinterpret_cast<float4*>(w),
+             reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), g, reinterpret_cast<uint2*>(w_bf16), nvec, hyper,
+             beta1, beta2, eps, grad_scale, iterations_inc, g_f16, ls);
+  else
+    launch_k(adam_kernel<false>, dim3((int)blocks), dim3(ADAM_THREADS), 0, st, reinterpret_cast<float4*>(w),
+             reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), g, reinterpret_cast<uint2*>(w_bf16), nvec, hyper,
+             beta1, beta2, eps, grad_scale, iterations_inc, g_f16, ls);
   GCT2_CHECK_LAUNCH("adam_kernel");
   return 0;
 }
@@ -949,11 +980,11 @@ int adam_keras(float* w, float* m, float* v, const float* g, __nv_bfloat16* w_bf
                long long* iterations, float* hyper, float base_lr, int warmup_steps, float beta1, float beta2,
                float eps, float grad_scale, cudaStream_t st) {
   if (adam_prepare(iterations, hyper, base_lr, warmup_steps, beta1, beta2, st)) return 1;
-  return adam_apply(w, m, v, g, w_bf16, n, hyper, beta1, beta2, eps, grad_scale, nullptr, st);
+  return adam_apply(w, m, v, g, 0, w_bf16, n, hyper, beta1, beta2, eps, grad_scale, nullptr, nullptr, st);
 }
 
 // ------------------------------------------------------------------------------------ fp32 -> bf16 shadow
-__global__ void cast_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, long long nvec) {
+__global__ void cast_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, long long nvec, int f16) {
   TraceScope trace(9);
   pdl_launch_dependents();
   pdl_wait();
@@ -962,8 +993,8 @@ __global__ void cast_bf16_kernel(const float4* __restrict__ src, uint2* __restri
        i += (long long)gridDim.x * blockDim.x) {
     const float4 s = __ldg(src + i);
     uint2 o;
-    o.x = pack_bf16x2(s.x, s.y);
-    o.y = pack_bf16x2(s.z, s.w);
+    o.x = pack_h2(s.x, s.y, f16);
+    o.y = pack_h2(s.z, s.w, f16);
     dst[i] = o;
   }
   trace.end();
@@ -979,8 +1010,68 @@ int cast_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t st
   if (blocks > g_ew_sms * 8) blocks = g_ew_sms * 8;
   if (blocks < 1) blocks = 1;
   launch_k(cast_bf16_kernel, dim3((int)blocks), dim3(256), 0, st, reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(dst),
-                                                nvec);
+                                                nvec, g_f16);
   GCT2_CHECK_LAUNCH("cast_bf16_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ dynamic loss scaling (f3)
+// train.py:82-83 wraps the optimiser in tf.keras.mixed_precision.LossScaleOptimizer (dynamic): the loss is multiplied by
+// `scale` before backward, the gradients divided by it before the update; a step with a non-finite gradient is skipped
+// and halves the scale, `growth` consecutive good steps double it.  State on the device: ls = {scale, good steps,
+// finite flag, 1/scale}.
+__global__ void __launch_bounds__(256) loss_scale_check_kernel(const float4* __restrict__ g, long long nvec, float* __restrict__ ls) {
+  TraceScope trace(11);
+  pdl_launch_dependents();
+  pdl_wait();
+  trace.ready();
+  bool bad = false;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(g + i);
+    // x - x is 0 for every finite x and NaN for inf / NaN
+    const float t = (v.x - v.x) + (v.y - v.y) + (v.z - v.z) + (v.w - v.w);
+    bad |= !(t == 0.f);
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) ls[2] = 0.f;
+  trace.end();
+}
+__global__ void loss_scale_update_kernel(float* __restrict__ ls, int growth) {
+  TraceScope trace(12);
+  pdl_launch_dependents();
+  pdl_wait();
+  trace.ready();
+  float scale = ls[0], good = ls[1];
+  if (ls[2] != 0.f) {
+    good += 1.f;
+    if (good >= (float)growth) {
+      if (scale * 2.f < 3.0e38f) scale *= 2.f;
+      good = 0.f;
+    }
+  } else {
+    scale = fmaxf(scale * 0.5f, 1.f);
+    good = 0.f;
+  }
+  ls[0] = scale;
+  ls[1] = good;
+  ls[2] = 1.f;  // armed for the next step
+  ls[3] = 1.f / scale;
+  trace.end();
+}
+int loss_scale_check(const float* g, long long n, float* ls, cudaStream_t st) {
+  if (n % 4 || reinterpret_cast<uintptr_t>(g) % 16) {
+    set_error("loss_scale_check: the gradient range must be 16-byte aligned and a multiple of 4 elements");
+    return 1;
+  }
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > g_ew_sms * 8) blocks = g_ew_sms * 8;
+  if (blocks < 1) blocks = 1;
+  launch_k(loss_scale_check_kernel, dim3((int)blocks), dim3(256), 0, st, reinterpret_cast<const float4*>(g), n / 4, ls);
+  GCT2_CHECK_LAUNCH("loss_scale_check_kernel");
+  return 0;
+}
+int loss_scale_update(float* ls, int growth_steps, cudaStream_t st) {
+  launch_k(loss_scale_update_kernel, dim3(1), dim3(1), 0, st, ls, growth_steps);
+  GCT2_CHECK_LAUNCH("loss_scale_update_kernel");
   return 0;
 }
 

@@ -361,11 +361,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= 2ull << 61;
   return d;
 }
-// Instruction descriptor, kind::f16 with bf16 inputs and fp32 accumulation.
-//   c_format[4,6)=1 (f32)  a_format[7,10)=1 (bf16)  b_format[10,13)=1 (bf16)
+// Instruction descriptor, kind::f16 with bf16 (fmt = 1) or fp16 (fmt = 0) inputs and fp32 accumulation.
+//   c_format[4,6)=1 (f32)  a_format[7,10)  b_format[10,13)  (0 = f16, 1 = bf16)
 //   a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major)   n>>3 at [17,23)   m>>4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, int a_mn_major, int b_mn_major, int fmt = 1) {
+  return (1u << 4) | (static_cast<uint32_t>(fmt) << 7) | (static_cast<uint32_t>(fmt) << 10) |
+         (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
 }
@@ -401,5 +402,31 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+
+// ----------------------------------------------------------------------------- the two 16-bit storage formats
+// The library stores activations, their gradients and the weights' shadow copy in bf16 (default) or, under the
+// reference's mixed-precision policy (train.py:34,43-45: Keras 'mixed_float16'), in fp16.  `f16` is uniform per launch.
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float f16_lo(uint32_t v) {
+  float f;
+  asm("{ .reg .b16 h; cvt.u16.u32 h, %1; cvt.f32.f16 %0, h; }" : "=f"(f) : "r"(v & 0xFFFFu));
+  return f;
+}
+__device__ __forceinline__ float f16_hi(uint32_t v) {
+  float f;
+  asm("{ .reg .b16 h; cvt.u16.u32 h, %1; cvt.f32.f16 %0, h; }" : "=f"(f) : "r"(v >> 16));
+  return f;
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi, int f16) { return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }
+__device__ __forceinline__ float h_lo(uint32_t v, int f16) { return f16 ? f16_lo(v) : bf16_lo(v); }
+__device__ __forceinline__ float h_hi(uint32_t v, int f16) { return f16 ? f16_hi(v) : bf16_hi(v); }
+// value > 0, read off the bits: sign clear and magnitude non-zero -- the same test in both formats (post-ReLU
+// activations are never negative or NaN)
+__device__ __forceinline__ bool h_pos_lo(uint32_t v) { return (v & 0x8000u) == 0u && (v & 0x7FFFu) != 0u; }
+__device__ __forceinline__ bool h_pos_hi(uint32_t v) { return (v & 0x80000000u) == 0u && (v & 0x7FFF0000u) != 0u; }
 
 }  // namespace gct2

@@ -44,6 +44,13 @@ class NetConfig:
     #: explicit per-octave filter counts (what a layer tree built by hand carries); default = train.py's formulas
     down_filters: Optional[Tuple[int, ...]] = None
     up_filters: Optional[Tuple[int, ...]] = None
+    #: train.py:34,43-45,82-83: Keras 'mixed_float16' policy + dynamic LossScaleOptimizer.  True: activations, their
+    #: gradients and the weights' shadow copy are fp16 (tensor cores on fp16 operands, fp32 accumulation), the loss is
+    #: multiplied by a dynamic scale before backward, steps with non-finite gradients are skipped.  False (the
+    #: reference's default): this implementation's bf16 storage, which needs no loss scaling.
+    mixed_precision: bool = False
+    loss_scale_init: float = 2.0 ** 15      # Keras LossScaleOptimizer defaults
+    loss_scale_growth: int = 2000
 
     def down_c(self, i: int) -> int:  # train.py:181
         if self.down_filters is not None:
@@ -179,18 +186,59 @@ def shard_batch(global_batch: int, world: int, rank: int) -> Tuple[int, int]:
 class DataParallel:
     """Data-parallel context: the batch shards over ranks, gradient buckets are summed with NCCL."""
 
-    def __init__(self, group=None, bucket_bytes: int = 48 << 20, shard_optimizer: bool = True):
+    def __init__(self, group=None, bucket_bytes: int = 48 << 20, shard_optimizer: bool = True,
+                 grad_dtype: Optional[str] = None, nccl_ctas: Optional[int] = None):
+        import os
         import torch.distributed as dist
         self.dist = dist
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.bucket_bytes = bucket_bytes
+        #: "bf16": the gradient reduce-scatter of the sharded optimiser runs on a bf16 copy of each bucket (half the
+        #: NVLink bytes; the fp32 gradients already carry bf16 operand noise) and Keras-Adam reads the summed bf16 values;
+        #: "fp32": the fp32 gradients themselves are reduced.  The replicated paths always reduce fp32.
+        self.grad_dtype = grad_dtype or os.environ.get("GCT2_DP_GRAD", "bf16")
+        if self.grad_dtype not in ("bf16", "fp32"):
+            raise ValueError("grad_dtype must be 'bf16' or 'fp32'")
+        #: SMs left to the NCCL kernels that run beside backward (NCCL_MAX_CTAS caps them): the tensor-core launches of
+        #: backward keep to the other SMs (gct2_set_sm_budget) instead of queueing a second wave behind a collective
+        self.nccl_ctas = nccl_ctas if nccl_ctas is not None else int(os.environ.get("NCCL_MAX_CTAS", "0") or 0)
+        #: measurement aid (bench.py's communication breakdown): when True the step is enqueued WITHOUT its collectives
+        #: (wrong numbers, right compute time); read when a step is enqueued / captured
+        self.dry_run = False
         #: SURVEY.md 8(e) "optimisation": per bucket, reduce-scatter the fp32 gradients, run Keras-Adam on this rank's
         #: 1/N slice only, all-gather the bf16 weights the tensor-core kernels read.  0.75x the bytes of an fp32
         #: all-reduce on the wire and 1/N of the optimiser's HBM traffic per GPU.  The fp32 masters of the other ranks'
         #: slices go stale until UNetEngine.gather_master_weights() (called by weights()).
         self.shard_optimizer = shard_optimizer
+
+
+class _NoWork:
+    def wait(self):
+        pass
+
+
+class _Collectives:
+    """The three collectives of the data-parallel step; DataParallel.dry_run turns them into no-ops."""
+
+    def __init__(self, dp: DataParallel):
+        self.dp = dp
+
+    def reduce_scatter(self, out, inp):
+        if self.dp.dry_run:
+            return _NoWork()
+        return self.dp.dist.reduce_scatter_tensor(out, inp, group=self.dp.group, async_op=True)
+
+    def all_gather(self, out, inp):
+        if self.dp.dry_run:
+            return _NoWork()
+        return self.dp.dist.all_gather_into_tensor(out, inp, group=self.dp.group, async_op=True)
+
+    def all_reduce(self, t):
+        if self.dp.dry_run:
+            return _NoWork()
+        return self.dp.dist.all_reduce(t, group=self.dp.group, async_op=True)
 
 
 class UNetEngine:
@@ -201,6 +249,9 @@ class UNetEngine:
         self.B = batch
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.dp = dp
+        self.half = torch.float16 if cfg.mixed_precision else torch.bfloat16  # the 16-bit storage format (ops.HALF)
+        if cfg.mixed_precision and dp is not None and dp.world > 1:
+            raise NotImplementedError("mixed_precision (fp16 + dynamic loss scaling) is implemented for single-GPU steps")
         self.use_graph = use_graph
         self.rng_seed = 0x5DEECE66D + 7919 * (dp.rank if dp else 0)  # every rank draws its own noise
         import os
@@ -237,6 +288,7 @@ class UNetEngine:
             # steps therefore finish split-K inside a thread-block cluster (co-scheduled by the hardware, so waiting
             # inside it is always safe) or with the separate finishing kernel.
             lib.gct2_debug_set(26, 1)
+            lib.gct2_debug_set(25, 0)
 
         # ---- parameters, flat in Keras order
         self.specs = variable_specs(cfg)
@@ -250,19 +302,27 @@ class UNetEngine:
             o = share_params_with
             if o.specs != self.specs:
                 raise ValueError("engines sharing parameters must have the same variable list")
+            if o.cfg.mixed_precision != cfg.mixed_precision:
+                raise ValueError("engines sharing parameters must use the same precision policy")
             self.w, self.m, self.v, self.g, self.w16 = o.w, o.m, o.v, o.g, o.w16
-            self.iterations, self.hyper = o.iterations, o.hyper
+            self.iterations, self.hyper, self.ls, self._it_scratch = o.iterations, o.hyper, o.ls, o._it_scratch
         else:
             self.w = torch.zeros(self.P, **f32)
             self.m = torch.zeros(self.P, **f32)
             self.v = torch.zeros(self.P, **f32)
             self.g = torch.zeros(self.P, **f32)
-            self.w16 = torch.zeros(self.P, dtype=torch.bfloat16, device=dev)
+            self.w16 = torch.zeros(self.P, dtype=self.half, device=dev)
             self.iterations = torch.zeros(1, dtype=torch.int64, device=dev)
             self.hyper = torch.zeros(2, **f32)
+            # dynamic loss scaling state {scale, good steps, finite flag, 1/scale} (mixed precision only)
+            self.ls = torch.tensor([cfg.loss_scale_init, 0.0, 1.0, 1.0 / cfg.loss_scale_init], **f32)
+            self._it_scratch = torch.zeros(1, dtype=torch.int64, device=dev)
+        # bf16 copy of the gradient buckets for the data-parallel reduce-scatter (DataParallel.grad_dtype)
+        self.g16 = (torch.zeros(self.P, dtype=torch.bfloat16, device=dev)
+                    if (dp is not None and dp.world > 1 and dp.shard_optimizer and dp.grad_dtype == "bf16") else None)
 
         # ---- activations and their gradients
-        bf = dict(dtype=torch.bfloat16, device=dev)
+        bf = dict(dtype=self.half, device=dev)
         self.x = torch.zeros(B, S, S, 3, **f32)
         self.x_u8 = torch.zeros(B, S, S, 3, dtype=torch.uint8, device=dev)   # decode_file's bytes (train.py:285-293)
         self.flip = torch.zeros(B, dtype=torch.uint8, device=dev)           # per-image left-right flip flags
@@ -309,6 +369,7 @@ class UNetEngine:
             self.m.zero_()
             self.v.zero_()
             self.iterations.zero_()
+            self.ls.copy_(torch.tensor([self.cfg.loss_scale_init, 0.0, 1.0, 1.0 / self.cfg.loss_scale_init]))
         self._graph = None
         # the bf16 kernels must be at rest before a step may fetch them ahead of its dependencies (weights_stable)
         torch.cuda.current_stream().synchronize()
@@ -340,7 +401,9 @@ class UNetEngine:
         return {name: self.view(self.w, name).detach().clone() for name, _ in self.specs}
 
     def grads(self) -> Dict[str, torch.Tensor]:
-        return {name: self.view(self.g, name).detach().clone() for name, _ in self.specs}
+        """The gradients of the last backward pass (mixed precision: with the loss scale removed)."""
+        unscale = float(self.ls[3]) if self.cfg.mixed_precision else 1.0
+        return {name: self.view(self.g, name).detach().clone() * unscale for name, _ in self.specs}
 
     # ------------------------------------------------------------------------------------------ buffer wiring
     def down_in(self, i: int) -> torch.Tensor:
@@ -379,7 +442,8 @@ class UNetEngine:
         ops.dense_mse(self.u0, self.noised, self.x, self.view(self.w, "dense/kernel"), self.view(self.w, "dense/bias"),
                       self.loss, inv_n, pred=self.pred if want_pred else None,
                       du0=self.gu0 if backward else None, dwd=self.view(self.g, "dense/kernel") if backward else None,
-                      dbd=self.view(self.g, "dense/bias") if backward else None, accumulate=True)
+                      dbd=self.view(self.g, "dense/bias") if backward else None, accumulate=True,
+                      loss_scale=self.ls if (backward and self.cfg.mixed_precision) else None)
 
     def _backward(self, apply_adam: bool, inc_iterations: bool = False) -> None:
         """Three chains that share the GPU (at batch 1 no layer fills 148 SMs on its own):
@@ -394,12 +458,16 @@ class UNetEngine:
         sw = self._side if self.overlap_wgrad else main
         sa = self._side_adam if self.overlap_adam else main
         dp = self.dp if (self.dp and self.dp.world > 1) else None
+        coll = _Collectives(dp) if dp else None
         pending = []
         from . import _lib
         num_sms = _lib.load().gct2_num_sms()
         # [wide buckets left, conv SM budget active]
         side = [self.adam_wide_buckets if (apply_adam and dp is None and sa is not main and 0 < self.adam_sms < num_sms)
                 else 0, False]
+        if dp is not None and 0 < dp.nccl_ctas < num_sms:
+            ops.set_sm_budget(num_sms - dp.nccl_ctas)  # the collectives of backward keep their SMs
+            side[1] = True
 
         def on_side(fn):
             if sw is main:
@@ -423,10 +491,13 @@ class UNetEngine:
                         chunk = own_hi - own
                         if sw is not main and trigger == "down0/kernel":
                             sw.wait_stream(main)
+                        gsrc = self.g
                         with torch.cuda.stream(sw):
+                            if self.g16 is not None:
+                                ops.cast_bf16(self.g[lo:end], self.g16[lo:end])
+                                gsrc = self.g16
                             # in place: my slice of the bucket receives the sum of everybody's slice
-                            rs = dp.dist.reduce_scatter_tensor(self.g[own:own + chunk], self.g[lo:end], group=dp.group,
-                                                               async_op=True)
+                            rs = coll.reduce_scatter(gsrc[own:own + chunk], gsrc[lo:end])
                         if sa is not main:
                             sa.wait_stream(main)
                             if sw is not main:
@@ -436,11 +507,10 @@ class UNetEngine:
                         with torch.cuda.stream(sa):
                             rs.wait()
                             ops.adam_apply(self.w[own:own + chunk], self.m[own:own + chunk], self.v[own:own + chunk],
-                                           self.g[own:own + chunk], self.w16[own:own + chunk], self.hyper, cfg.beta1,
+                                           gsrc[own:own + chunk], self.w16[own:own + chunk], self.hyper, cfg.beta1,
                                            cfg.beta2, cfg.epsilon, 1.0)
                             # every rank's freshly written bf16 slice to everybody (in place)
-                            pending.append(dp.dist.all_gather_into_tensor(self.w16[lo:end], self.w16[own:own + chunk],
-                                                                          group=dp.group, async_op=True))
+                            pending.append(coll.all_gather(self.w16[lo:end], self.w16[own:own + chunk]))
                         self._sharded_ranges.add((lo, end))
                         if start >= self.small:
                             continue
@@ -449,7 +519,7 @@ class UNetEngine:
                     if sw is not main and trigger == "down0/kernel":
                         sw.wait_stream(main)  # the small region is produced on the main stream
                     with torch.cuda.stream(sw):
-                        work = dp.dist.all_reduce(self.g[start:end], group=dp.group, async_op=True)
+                        work = coll.all_reduce(self.g[start:end])
                 if not apply_adam:
                     if work is not None:
                         pending.append(work)
@@ -502,8 +572,10 @@ class UNetEngine:
             main.wait_stream(sa)
         for work in pending:
             work.wait()
+        if side[1]:
+            ops.set_sm_budget(0)
         if dp:
-            dp.dist.all_reduce(self.loss, group=dp.group)
+            coll.all_reduce(self.loss).wait()
 
     def _zero_small_grads(self) -> None:
         """One memset for everything the HBM-bound kernels accumulate atomically (param_offsets' head region) + loss."""
@@ -527,10 +599,23 @@ class UNetEngine:
                            self.rng_seed, cfg.steps, cfg.base_lr, cfg.warm_up, cfg.beta1, cfg.beta2, t_out=self.t_int)
         else:
             self._zero_small_grads()
-            ops.adam_prepare(self.iterations, self.hyper, cfg.base_lr, cfg.warm_up, cfg.beta1, cfg.beta2)
+            if cfg.mixed_precision:
+                # the iteration counter advances only when the update is applied (below): alpha from a scratch copy
+                self._it_scratch.copy_(self.iterations)
+                ops.adam_prepare(self._it_scratch, self.hyper, cfg.base_lr, cfg.warm_up, cfg.beta1, cfg.beta2)
+            else:
+                ops.adam_prepare(self.iterations, self.hyper, cfg.base_lr, cfg.warm_up, cfg.beta1, cfg.beta2)
             ops.noise_images(self.x, self.eps, self.t_int, self.noised, cfg.steps)
         self._forward(want_pred=False, backward=True, inv_n=inv_n)
-        self._backward(apply_adam=True, inc_iterations=draw or u8)
+        if cfg.mixed_precision:
+            # train.py:82-83 LossScaleOptimizer: the update can only start once EVERY gradient is known to be finite
+            self._backward(apply_adam=False)
+            ops.loss_scale_check(self.g, self.ls)
+            ops.adam_apply(self.w, self.m, self.v, self.g, self.w16, self.hyper, cfg.beta1, cfg.beta2, cfg.epsilon, 1.0,
+                           iterations_inc=self.iterations, loss_scale_state=self.ls)
+            ops.loss_scale_update(self.ls, cfg.loss_scale_growth)
+        else:
+            self._backward(apply_adam=True, inc_iterations=draw or u8)
 
     def train_step_u8(self, img: torch.Tensor, flip: Optional[torch.Tensor] = None) -> torch.Tensor:
         """One training step on the batch as it leaves the reference's decode_file before the cast
@@ -566,10 +651,10 @@ class UNetEngine:
         return self.loss
 
     def _save_state(self):
-        return [t.clone() for t in (self.w, self.m, self.v, self.w16, self.iterations)]
+        return [t.clone() for t in (self.w, self.m, self.v, self.w16, self.iterations, self.ls)]
 
     def _restore_state(self, saved) -> None:
-        for dst, src in zip((self.w, self.m, self.v, self.w16, self.iterations), saved):
+        for dst, src in zip((self.w, self.m, self.v, self.w16, self.iterations, self.ls), saved):
             dst.copy_(src)
         torch.cuda.current_stream().synchronize()  # see load_weights
 

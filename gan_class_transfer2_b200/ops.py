@@ -79,8 +79,25 @@ def _lib_for(t: torch.Tensor):
     return _lib.init(t.device.index if t.device.index is not None else torch.cuda.current_device())
 
 
+#: the two 16-bit storage formats: bf16 (default) and fp16 (the reference's mixed_float16 policy, train.py:34,43-45)
+HALF = (torch.bfloat16, torch.float16)
+_policy_now = [None]
+
+
+def _policy(t: torch.Tensor) -> None:
+    """gct2_set_policy from the dtype of a 16-bit tensor handed to an op (host-side state, read at launch)."""
+    f16 = t.dtype == torch.float16
+    if _policy_now[0] != f16:
+        _lib.load().gct2_set_policy(int(f16))
+        _policy_now[0] = f16
+
+
 def _nhwc(t: torch.Tensor, dtype) -> int:
-    """Checks a [B,H,W,C] (possibly channel-sliced) view and returns its pixel stride in elements."""
+    """Checks a [B,H,W,C] (possibly channel-sliced) view and returns its pixel stride in elements.  dtype
+    torch.bfloat16 stands for "the 16-bit storage format": fp16 tensors are accepted too and select the fp16 policy."""
+    if dtype == torch.bfloat16 and t.dtype in HALF:
+        _policy(t)
+        dtype = t.dtype
     if t.dtype != dtype or t.dim() != 4 or t.stride(3) != 1:
         raise _lib.Gct2Error(f"expected an NHWC {dtype} tensor with unit channel stride, got {t.dtype} {tuple(t.shape)} "
                              f"strides {t.stride()}")
@@ -223,13 +240,14 @@ class BiasGradPlan:
 def bias_grad_multi(plan: BiasGradPlan, accumulate: bool = False):
     """BiasAddGrad of every conv layer in one launch: db_i[c] = sum over pixels of dz_i[..., c]."""
     lib = _lib_for(plan.keep[0][0])
+    _policy(plan.keep[0][0])
     check(lib.gct2_bias_grad_multi(plan.n, plan.dz, plan.ld, plan.rows, plan.C, plan.db, int(accumulate),
                                    current_stream()))
 
 
 @_timed
 def dense_mse(u0, noised, x, wd, bd, loss, inv_n: float, pred=None, du0=None, dwd=None, dbd=None,
-              accumulate: bool = False):
+              accumulate: bool = False, loss_scale=None):
     """Dense(3) on concat([u0, noised]) (train.py:198-202) fused with the MSE (train.py:262-272) and, when du0 is
     given, their backward."""
     lib = _lib_for(u0)
@@ -237,7 +255,8 @@ def dense_mse(u0, noised, x, wd, bd, loss, inv_n: float, pred=None, du0=None, dw
     pixels = u0.shape[0] * u0.shape[1] * u0.shape[2]
     check(lib.gct2_dense_mse(ptr(u0), _nhwc(u0, torch.bfloat16), ptr(noised), ptr(x), ptr(wd), ptr(bd), ptr(pred),
                              ptr(loss), ptr(du0), _nhwc(du0, torch.bfloat16) if backward else 0, ptr(dwd), ptr(dbd),
-                             pixels, u0.shape[3], inv_n, int(backward), int(accumulate), current_stream()))
+                             pixels, u0.shape[3], inv_n, int(backward), int(accumulate), ptr(loss_scale),
+                             current_stream()))
     return loss
 
 
@@ -246,6 +265,7 @@ def adam_keras(w, m, v, g, w_bf16, iterations, hyper, base_lr: float, warmup_ste
                beta2: float = 0.999, eps: float = 1e-7, grad_scale: float = 1.0):
     """tf.keras.optimizers.Adam(WarmUp(base_lr, warmup_steps)) on flat fp32 buffers (train.py:50-65,75)."""
     lib = _lib_for(w)
+    _policy(w_bf16)
     check(lib.gct2_adam_keras(ptr(w), ptr(m), ptr(v), ptr(g), ptr(w_bf16), w.numel(), ptr(iterations), ptr(hyper),
                               base_lr, warmup_steps, beta1, beta2, eps, grad_scale, current_stream()))
 
@@ -259,13 +279,18 @@ def adam_prepare(iterations, hyper, base_lr: float, warmup_steps: int, beta1: fl
 
 @_timed
 def adam_apply(w, m, v, g, w_bf16, hyper, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-7,
-               grad_scale: float = 1.0, iterations_inc=None):
+               grad_scale: float = 1.0, iterations_inc=None, loss_scale_state=None):
     """Keras-Adam update of one contiguous range of the flat buffers (views starting on 16-byte boundaries).
     iterations_inc: the optimiser's iteration counter, incremented by this launch (pass it on the step's last range
     when the step was opened with step_begin)."""
     lib = _lib_for(w)
-    check(lib.gct2_adam_apply(ptr(w), ptr(m), ptr(v), ptr(g), ptr(w_bf16), w.numel(), ptr(hyper), beta1, beta2, eps,
-                              grad_scale, ptr(iterations_inc), current_stream()))
+    _policy(w_bf16)
+    if g.dtype == torch.bfloat16:  # summed data-parallel gradients
+        check(lib.gct2_adam_apply_g16(ptr(w), ptr(m), ptr(v), ptr(g), ptr(w_bf16), w.numel(), ptr(hyper), beta1, beta2, eps,
+                                      grad_scale, ptr(iterations_inc), current_stream()))
+    else:
+        check(lib.gct2_adam_apply(ptr(w), ptr(m), ptr(v), ptr(g), ptr(w_bf16), w.numel(), ptr(hyper), beta1, beta2, eps,
+                                  grad_scale, ptr(iterations_inc), ptr(loss_scale_state), current_stream()))
 
 
 @_timed
@@ -307,6 +332,22 @@ def sample_update(pred, fake, x_theta, eps_theta, t: int, t_next: int, steps: in
 
 @_timed
 def cast_bf16(src, dst):
+    """fp32 -> the 16-bit storage format of dst (bf16 or fp16)."""
     lib = _lib_for(src)
+    _policy(dst)
     check(lib.gct2_cast_bf16(ptr(src), ptr(dst), src.numel(), current_stream()))
     return dst
+
+
+@_timed
+def loss_scale_check(g, ls):
+    """Clears ls[2] when any gradient is inf / NaN (tf.keras.mixed_precision.LossScaleOptimizer, train.py:82-83)."""
+    lib = _lib_for(g)
+    check(lib.gct2_loss_scale_check(ptr(g), g.numel(), ptr(ls), current_stream()))
+
+
+@_timed
+def loss_scale_update(ls, growth_steps: int = 2000):
+    """Dynamic loss-scale bookkeeping after the (possibly skipped) update; re-arms the finite flag."""
+    lib = _lib_for(ls)
+    check(lib.gct2_loss_scale_update(ptr(ls), int(growth_steps), current_stream()))

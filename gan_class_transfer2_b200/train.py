@@ -37,7 +37,10 @@ predict_scaled_epsilon = False
 prediction_weighting = False
 ordinary_differential_equation = False
 
-mixed_precision = False  # the reference's fp16 policy; this implementation computes in bf16 with fp32 masters
+#: train.py:34.  False (the reference's default, fp32 there): bf16 operands / fp32 accumulation and masters here.
+#: True: the reference's own reduced-precision mode (Keras 'mixed_float16' policy, train.py:43-45, and the dynamic
+#: LossScaleOptimizer, train.py:82-83): fp16 operands and activations, loss scaling with skipped steps on overflow.
+mixed_precision = False
 
 warm_up = 2_000
 test_step = 25
@@ -78,8 +81,22 @@ class Adam:
         return float(lr), 0
 
 
+class LossScaleOptimizer:
+    """tf.keras.mixed_precision.LossScaleOptimizer as train.py:82-83 uses it (dynamic scaling, Keras defaults): wraps the
+    inner optimiser; the scaling itself runs on the device (gct2_loss_scale_check / _update, engine.NetConfig)."""
+
+    def __init__(self, inner_optimizer, dynamic=True, initial_scale=2.0 ** 15, dynamic_growth_steps=2000):
+        if not dynamic:
+            raise NotImplementedError("train.py:83 uses the default dynamic loss scale")
+        self.inner_optimizer = inner_optimizer
+        self.initial_scale = float(initial_scale)
+        self.dynamic_growth_steps = int(dynamic_growth_steps)
+
+
 optimizer = Adam(WarmUp(2e-5, warm_up))
 regularizer = None
+if mixed_precision:  # train.py:82-83
+    optimizer = LossScaleOptimizer(optimizer)
 
 
 def alpha_dash(t):
@@ -115,10 +132,15 @@ def _shape_of(x):
     return tuple(x.shape)
 
 
+def preferred_type():
+    """train.py:38: the 16-bit storage format of the active policy."""
+    return torch.float16 if mixed_precision else torch.bfloat16
+
+
 def _check_act(x: torch.Tensor) -> torch.Tensor:
     if not x.is_cuda:
         raise RuntimeError("this layer runs on the B200 only: pass a CUDA tensor (no CPU fallback)")
-    return x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
+    return x if x.dtype == preferred_type() else x.to(preferred_type())
 
 
 class Sequential(Layer):
@@ -173,8 +195,8 @@ class _ConvLayer(Layer):
             self.bias = torch.zeros(self.filters, device="cuda")
 
     def _shadow(self):
-        if self._k16 is None or self._k16.shape != self.kernel.shape:
-            self._k16 = torch.empty_like(self.kernel, dtype=torch.bfloat16)
+        if self._k16 is None or self._k16.shape != self.kernel.shape or self._k16.dtype != preferred_type():
+            self._k16 = torch.empty_like(self.kernel, dtype=preferred_type())
         ops.cast_bf16(self.kernel.reshape(-1), self._k16.reshape(-1))
         return self._k16
 
@@ -191,7 +213,7 @@ class UpShuffle(_ConvLayer):
     def call(self, input):
         x = _check_act(input)
         B, H, W, _ = x.shape
-        y = torch.empty(B, 2 * H, 2 * W, self.filters, dtype=torch.bfloat16, device=x.device)
+        y = torch.empty(B, 2 * H, 2 * W, self.filters, dtype=preferred_type(), device=x.device)
         return ops.convT4s2_fprop(x, self._shadow(), self.bias, y, self._workspace(4 * y.numel(), x.device))
 
 
@@ -200,7 +222,7 @@ class DownShuffle(_ConvLayer):
 
     def call(self, input):
         B, H, W, C = input.shape
-        y = torch.empty(B, H // 2, W // 2, self.filters, dtype=torch.bfloat16, device=input.device)
+        y = torch.empty(B, H // 2, W // 2, self.filters, dtype=preferred_type(), device=input.device)
         if C == 3:
             if not input.is_cuda:
                 raise RuntimeError("this layer runs on the B200 only: pass a CUDA tensor (no CPU fallback)")
@@ -367,20 +389,27 @@ class Denoiser(Model):
     def net_config(self, image_size: int) -> NetConfig:
         downs, ups, _ = self._walk()
         opt = self._optimizer if self._optimizer is not None else optimizer
+        extra = {}
+        if isinstance(opt, LossScaleOptimizer):
+            extra = dict(loss_scale_init=opt.initial_scale, loss_scale_growth=opt.dynamic_growth_steps)
+            opt = opt.inner_optimizer
         base_lr, warm = opt.schedule()
         return NetConfig(size=image_size, pixel_size=pixel_size, max_size=max_size, octaves=len(downs), steps=steps,
                          warm_up=warm, base_lr=base_lr, beta1=opt.beta_1, beta2=opt.beta_2,
                          epsilon=opt.epsilon, down_filters=tuple(d.filters for d in downs),
-                         up_filters=tuple(u.filters for u in ups))
+                         up_filters=tuple(u.filters for u in ups), mixed_precision=bool(mixed_precision), **extra)
 
     def use_optimizer(self, opt: "Adam") -> None:
         """The optimiser the engines are built with (Trainer.compile hands over the one it was given, train.py:511-514)."""
-        if not isinstance(opt, Adam):
-            raise NotImplementedError("only tf.keras.optimizers.Adam (train.py:75) is implemented on the device")
+        inner = opt.inner_optimizer if isinstance(opt, LossScaleOptimizer) else opt
+        if not isinstance(inner, Adam):
+            raise NotImplementedError("only tf.keras.optimizers.Adam (train.py:75), optionally inside a LossScaleOptimizer "
+                                      "(train.py:83), is implemented on the device")
         if self._engines:
             cur = self._optimizer if self._optimizer is not None else optimizer
-            same = (cur.schedule() == opt.schedule() and (cur.beta_1, cur.beta_2, cur.epsilon) ==
-                    (opt.beta_1, opt.beta_2, opt.epsilon))
+            cur = cur.inner_optimizer if isinstance(cur, LossScaleOptimizer) else cur
+            same = (cur.schedule() == inner.schedule() and (cur.beta_1, cur.beta_2, cur.epsilon) ==
+                    (inner.beta_1, inner.beta_2, inner.epsilon))
             if not same:
                 raise RuntimeError("the training engine has already been built with another optimiser; compile() before "
                                    "the first step")

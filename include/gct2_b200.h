@@ -54,7 +54,7 @@ long long gct2_launch_count(void);
  * split-K rendezvous watchdog in polls of ~40 ns (0 = none; default 2^28), key 21 != 0 = never fetch weights before the
  * programmatic dependency resolves, key 22 = gct2_set_sm_budget, key 23 = gct2_set_adam_sms, key 24 = blocks per SM of
  * the Dense+MSE kernel, key 25 = split-K inside a thread-block cluster (partials through distributed shared memory): 0 =
- * when the cost model picks it, 1 = never, 2 = whenever legal, key 26 != 0 = never use the L2 rendezvous form of the
+ * when the cost model picks it, 1 = never (the default), 2 = whenever legal, key 26 != 0 = never use the L2 rendezvous form of the
  * in-launch split-K finish (data-parallel steps: it needs all CTAs of a launch resident at once). */
 void gct2_debug_set(int key, int value);
 /* Test hook: after gct2_debug_set(7, 1) every tensor-core conv launch records, per CTA, 8 %globaltimer stamps (ns):
@@ -74,6 +74,21 @@ void gct2_set_sm_budget(int sms);
  * of backward on disjoint SMs (measured: ~98 GB/s of optimiser traffic per SM up to 48 SMs, 5.8 TB/s from 64).  Both
  * forms compute bit-identical results. */
 void gct2_set_adam_sms(int sms);
+/* train.py:34,43-45 -- the reference's precision switch (`mixed_precision`, Keras policy 'mixed_float16').  fp16 != 0:
+ * every 16-bit tensor of the following launches (activations, their gradients, the weights' shadow copy; the pointers
+ * typed uint16_t below) is IEEE fp16 and the tensor cores run kind::f16 on fp16 operands; 0 (default): bf16.  Master
+ * weights, gradients of the variables, optimiser state, loss and accumulation stay fp32 in both.  Host-side state, read
+ * when a launch is enqueued. */
+void gct2_set_policy(int fp16);
+int gct2_get_policy(void);
+/* train.py:82-83 -- tf.keras.mixed_precision.LossScaleOptimizer (dynamic).  State `ls` = device float[4]: {scale, good
+ * steps, all-gradients-finite flag, 1/scale}; initialise to {2^15, 0, 1, 2^-15}.  gct2_dense_mse(loss_scale = ls)
+ * multiplies the gradient of the loss by the scale; gct2_loss_scale_check clears the flag when any of g[0..n) is inf or
+ * NaN; gct2_adam_apply(loss_scale_state = ls) skips the whole update (and the iteration count) when the flag is clear
+ * and otherwise divides the gradients by the scale; gct2_loss_scale_update halves the scale after a skipped step,
+ * doubles it after `growth_steps` consecutive good ones (Keras default 2000) and re-arms the flag. */
+int gct2_loss_scale_check(const float* g, long long n, float* ls, void* stream);
+int gct2_loss_scale_update(float* ls, int growth_steps, void* stream);
 /* Test hook: after gct2_debug_set(11, 1) the first and last block of EVERY launch of this library append
  * {kernel id, blockIdx | gridDim << 32, entry ns, exit ns}; this call synchronises, copies up to max_records records
  * (4 x u64 each) to `host`, clears the buffer and returns the count.  Kernel ids: 1 noise, 2 step_begin, 3/4 down0
@@ -148,10 +163,12 @@ int gct2_bias_grad_multi(int n, const uint16_t* const* dz, const int* ld, const 
  * pred (nullable) fp32 [pixels,3]; loss: one fp32, overwritten with sum((pred-x)^2)*inv_n; inv_n = 1/(global
  * element count) so data-parallel ranks produce partial means.  When backward != 0 also writes
  * du0 = (u0>0) * (dpred . wd^T) (bf16, stride lddu), dwd fp32 [Cu+3,3], dbd fp32 [3], dpred = 2(pred-x)*inv_n.
- * Cu is 64 or 128.  accumulate == 0: loss, dwd, dbd are overwritten; != 0: added into (the caller zeroed them). */
+ * Cu is 64 or 128.  accumulate == 0: loss, dwd, dbd are overwritten; != 0: added into (the caller zeroed them).
+ * loss_scale: NULL, or the device state of gct2_loss_scale_* (dpred is multiplied by loss_scale[0]; the loss is not). */
 int gct2_dense_mse(const uint16_t* u0, int ldu, const float* noised, const float* x, const float* wd,
                    const float* bd, float* pred, float* loss, uint16_t* du0, int lddu, float* dwd, float* dbd,
-                   long long pixels, int Cu, float inv_n, int backward, int accumulate, void* stream);
+                   long long pixels, int Cu, float inv_n, int backward, int accumulate, const float* loss_scale,
+                   void* stream);
 
 /* train.py:50-65,75 -- tf.keras.optimizers.Adam(WarmUp(base_lr, warmup_steps)), Keras formula (epsilon added to
  * the un-bias-corrected sqrt(v)).  All n parameters live in flat fp32 buffers; w_bf16 receives the shadow copy.
@@ -163,11 +180,18 @@ int gct2_adam_keras(float* w, float* m, float* v, const float* g, uint16_t* w_bf
 /* The same optimiser in two parts, so that the update of a contiguous range of variables can start as soon as that
  * range's gradients are complete (overlapping the rest of backward): gct2_adam_prepare once per step (computes
  * alpha/lr of this step into hyper[0..1], increments *iterations), then gct2_adam_apply per range
- * (iterations_inc: NULL, or a counter to increment by one -- used together with gct2_step_begin). */
+ * (iterations_inc: NULL, or a counter to increment by one -- used together with gct2_step_begin; loss_scale_state: NULL,
+ * or the device state of gct2_loss_scale_*). */
 int gct2_adam_prepare(long long* iterations, float* hyper, float base_lr, int warmup_steps, float beta1, float beta2,
                       void* stream);
 int gct2_adam_apply(float* w, float* m, float* v, const float* g, uint16_t* w_bf16, long long n, const float* hyper,
-                    float beta1, float beta2, float eps, float grad_scale, long long* iterations_inc, void* stream);
+                    float beta1, float beta2, float eps, float grad_scale, long long* iterations_inc,
+                    const float* loss_scale_state, void* stream);
+/* The same update with the gradient given as bf16 (data parallel: the gradient reduce-scatter runs on a bf16 copy of
+ * the bucket -- half the NVLink bytes -- and the optimiser of this rank's slice reads the summed bf16 values). */
+int gct2_adam_apply_g16(float* w, float* m, float* v, const uint16_t* g_bf16, uint16_t* w_bf16, long long n,
+                        const float* hyper, float beta1, float beta2, float eps, float grad_scale,
+                        long long* iterations_inc, void* stream);
 /* Everything a step needs before its first convolution, in one launch (train.py:224-234 plus optimiser bookkeeping):
  * draws t_int ~ U{1..steps} per image and eps ~ N(0,1) per element on the device (Philox4x32-10 keyed by `seed`, offset by
  * *iterations so every step differs; the reference draws with TF's unseeded generators), writes

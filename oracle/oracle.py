@@ -216,6 +216,31 @@ class _RoundBF16(torch.autograd.Function):
         return g.to(torch.bfloat16).to(torch.float32)
 
 
+class _RoundF16(torch.autograd.Function):
+    """The same for IEEE fp16 -- the storage format under the reference's mixed_float16 policy (train.py:43-45).
+    Values beyond 65504 become inf and gradients below 6e-8 become 0, exactly as in fp16 storage: that is what the
+    dynamic loss scale (train.py:82-83) exists for."""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t.to(torch.float16).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.float16).to(torch.float32)
+
+
+def _rounding(emulate_bf16):
+    """emulate_bf16: False / None (the reference's fp32 arithmetic), True / 'bf16', or 'f16'."""
+    if emulate_bf16 in (False, None):
+        return lambda t: t
+    if emulate_bf16 in (True, "bf16"):
+        return _RoundBF16.apply
+    if emulate_bf16 == "f16":
+        return _RoundF16.apply
+    raise ValueError(f"unknown emulation {emulate_bf16!r}")
+
+
 def denoiser_forward(weights: Dict[str, torch.Tensor], x_nhwc: torch.Tensor, cfg: Config = DEFAULT,
                      taps: Optional[Dict[str, torch.Tensor]] = None, emulate_bf16: bool = False) -> torch.Tensor:
     """Denoiser.call (train.py:206-215): `t` is ignored by the reference; Block is identity at block_depth=0.
@@ -227,7 +252,7 @@ def denoiser_forward(weights: Dict[str, torch.Tensor], x_nhwc: torch.Tensor, cfg
     where the CUDA path stores bf16 (tensor-core kernels' weights, every layer output and its gradient), which turns
     the loose fp32-vs-bf16 comparison into a tight one for the tests; it is not the reference's arithmetic.
     """
-    rnd = _RoundBF16.apply if emulate_bf16 else (lambda t: t)
+    rnd = _rounding(emulate_bf16)
 
     def residual(i: int, h):
         kd = weights[f"down{i}/kernel"] if i == 0 else rnd(weights[f"down{i}/kernel"])  # down0 runs in fp32
@@ -275,9 +300,13 @@ def identity(y_true, y_pred):
 
 
 def loss_and_grads(weights, x, t_int, eps, cfg: Config = DEFAULT, want_taps: bool = False,
-                   global_elems: Optional[int] = None, emulate_bf16: bool = False):
+                   global_elems: Optional[int] = None, emulate_bf16=False, loss_scale: Optional[float] = None):
     """One forward+backward (what Keras train_step's GradientTape does, train.py:516): returns
-    (loss, {name: grad}, taps) where taps also carries d(loss)/d(layer output) under 'd<name>' when requested."""
+    (loss, {name: grad}, taps) where taps also carries d(loss)/d(layer output) under 'd<name>' when requested.
+
+    loss_scale (train.py:82-83, LossScaleOptimizer.get_scaled_loss / get_unscaled_gradients): the backward pass runs on
+    loss * scale -- so every rounding of the emulated 16-bit storage sees the scaled gradient -- and the returned
+    gradients (and 'd<name>' taps) have the scale divided out again; non-finite values stay non-finite."""
     ws = {k: v.detach().clone().requires_grad_(True) for k, v in weights.items()}
     taps: Optional[Dict[str, torch.Tensor]] = {} if want_taps else None
     loss = identity(None, trainer_loss(ws, x, t_int, eps, cfg, taps, global_elems, emulate_bf16))
@@ -285,14 +314,15 @@ def loss_and_grads(weights, x, t_int, eps, cfg: Config = DEFAULT, want_taps: boo
         for v in taps.values():
             if v.requires_grad:
                 v.retain_grad()
-    loss.backward()
-    grads = {k: v.grad.detach() for k, v in ws.items()}
+    scale = 1.0 if loss_scale is None else float(loss_scale)
+    (loss * scale).backward()
+    grads = {k: v.grad.detach() / scale for k, v in ws.items()}
     out_taps: Dict[str, torch.Tensor] = {}
     if want_taps:
         for k, v in taps.items():
             out_taps[k] = v.detach()
             if v.grad is not None:
-                out_taps["d" + k] = v.grad.detach()
+                out_taps["d" + k] = v.grad.detach() / scale
     return loss.detach(), grads, out_taps
 
 
@@ -317,18 +347,55 @@ def keras_adam_update(w, m, v, g, iteration: int, cfg: Config = DEFAULT):
     return alpha
 
 
-class OracleTrainer:
-    """Stateful restatement of `trainer.fit`'s per-step work (train.py:511-523): loss, grads, Adam."""
+class DynamicLossScale:
+    """tf.keras.mixed_precision.LossScaleOptimizer's dynamic loss scale (train.py:82-83; Keras defaults initial_scale =
+    2**15, dynamic_growth_steps = 2000): a step whose gradients are not all finite is skipped and halves the scale
+    (never below 1); `growth_steps` consecutive finite steps double it."""
 
-    def __init__(self, cfg: Config = DEFAULT, weights: Optional[Dict[str, torch.Tensor]] = None, seed: int = 0):
+    def __init__(self, initial_scale: float = 2.0 ** 15, growth_steps: int = 2000):
+        self.scale = float(initial_scale)
+        self.growth_steps = int(growth_steps)
+        self.good_steps = 0
+
+    def update(self, finite: bool) -> bool:
+        """Book-keeping after one step; returns whether the optimiser update is applied."""
+        if finite:
+            self.good_steps += 1
+            if self.good_steps >= self.growth_steps:
+                self.scale *= 2.0
+                self.good_steps = 0
+            return True
+        self.scale = max(self.scale / 2.0, 1.0)
+        self.good_steps = 0
+        return False
+
+
+class OracleTrainer:
+    """Stateful restatement of `trainer.fit`'s per-step work (train.py:511-523): loss, grads, Adam.
+
+    mixed_precision=True adds what train.py:34,43-45,82-83 switch on: fp16 storage (emulated by rounding where the
+    CUDA path stores 16-bit values) and the dynamic LossScaleOptimizer -- skipped steps leave the variables, the Adam
+    moments and the iteration count untouched."""
+
+    def __init__(self, cfg: Config = DEFAULT, weights: Optional[Dict[str, torch.Tensor]] = None, seed: int = 0,
+                 mixed_precision: bool = False, initial_scale: float = 2.0 ** 15, growth_steps: int = 2000):
         self.cfg = cfg
         self.weights = {k: v.clone() for k, v in (weights or glorot_init(cfg, seed)).items()}
         self.m = {k: torch.zeros_like(v) for k, v in self.weights.items()}
         self.v = {k: torch.zeros_like(v) for k, v in self.weights.items()}
         self.iterations = 0
+        self.mixed_precision = mixed_precision
+        self.loss_scale = DynamicLossScale(initial_scale, growth_steps) if mixed_precision else None
 
     def train_step(self, x, t_int, eps) -> float:
-        loss, grads, _ = loss_and_grads(self.weights, x, t_int, eps, self.cfg)
+        if not self.mixed_precision:
+            loss, grads, _ = loss_and_grads(self.weights, x, t_int, eps, self.cfg)
+        else:
+            loss, grads, _ = loss_and_grads(self.weights, x, t_int, eps, self.cfg, emulate_bf16="f16",
+                                            loss_scale=self.loss_scale.scale)
+            finite = all(bool(torch.isfinite(g).all()) for g in grads.values())
+            if not self.loss_scale.update(finite):
+                return float(loss)
         for k in self.weights:
             keras_adam_update(self.weights[k], self.m[k], self.v[k], grads[k], self.iterations, self.cfg)
         self.iterations += 1

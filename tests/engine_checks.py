@@ -44,11 +44,11 @@ def tol_emu_grad(cfg: O.Config, layer: str) -> float:
     return 0.02 + 0.02 * level_of(layer)
 
 
-def make_engine(cfg: O.Config, batch: int, seed: int = 0, use_graph: bool = False):
+def make_engine(cfg: O.Config, batch: int, seed: int = 0, use_graph: bool = False, **net_kw):
     from gan_class_transfer2_b200.engine import NetConfig, UNetEngine
     ncfg = NetConfig(size=cfg.size, pixel_size=cfg.pixel_size, max_size=cfg.max_size, octaves=cfg.octaves,
                      steps=cfg.steps, warm_up=cfg.warm_up, base_lr=cfg.base_lr, beta1=cfg.beta1, beta2=cfg.beta2,
-                     epsilon=cfg.epsilon)
+                     epsilon=cfg.epsilon, **net_kw)
     eng = UNetEngine(ncfg, batch, use_graph=use_graph)
     weights = O.glorot_init(cfg, seed)
     eng.load_weights(weights)
@@ -68,17 +68,23 @@ def engine_taps(eng) -> Dict[str, torch.Tensor]:
     return taps
 
 
-def step_parity(cfg: O.Config, batch: int, seed: int = 0) -> Dict[str, Dict[str, float]]:
-    """One forward+backward of the engine vs the oracle (both flavours). Returns {quantity: {"emu": err, "f32": err}}."""
-    eng, weights = make_engine(cfg, batch, seed)
+def step_parity(cfg: O.Config, batch: int, seed: int = 0, mixed_precision: bool = False) -> Dict[str, Dict[str, float]]:
+    """One forward+backward of the engine vs the oracle (both flavours). Returns {quantity: {"emu": err, "f32": err}}.
+    mixed_precision: the reference's fp16 policy with the loss scaled by 2^15 (train.py:34,43-45,82-83); the engine's
+    stored activation gradients carry the scale and are compared after dividing it out."""
+    eng, weights = make_engine(cfg, batch, seed, mixed_precision=mixed_precision)
     x, t, e = O.synthetic_batch(cfg, batch, seed + 1)
     loss = eng.loss_and_grads(x.cuda(), t.cuda(), e.cuda())
     torch.cuda.synchronize()
     got_taps = engine_taps(eng)
+    scale = float(eng.ls[0]) if mixed_precision else None
+    if mixed_precision:
+        got_taps = {k: (v.float() / scale if k.startswith(("ddown", "dup")) else v) for k, v in got_taps.items()}
     got_grads = eng.grads()
     out: Dict[str, Dict[str, float]] = {}
-    for flavour, emulate in (("emu", True), ("f32", False)):
-        rl, rg, rt = O.loss_and_grads(weights, x, t, e, cfg, want_taps=True, emulate_bf16=emulate)
+    for flavour, emulate in (("emu", "f16" if mixed_precision else True), ("f32", False)):
+        rl, rg, rt = O.loss_and_grads(weights, x, t, e, cfg, want_taps=True, emulate_bf16=emulate,
+                                      loss_scale=scale if emulate else None)
         out.setdefault("loss", {})[flavour] = abs(float(loss) - float(rl)) / abs(float(rl))
         for name, ref in rt.items():
             if name == "dpred" or name not in got_taps:
@@ -91,9 +97,9 @@ def step_parity(cfg: O.Config, batch: int, seed: int = 0) -> Dict[str, Dict[str,
     return out
 
 
-def check_step_parity(cfg: O.Config, batch: int, seed: int = 0):
+def check_step_parity(cfg: O.Config, batch: int, seed: int = 0, mixed_precision: bool = False):
     """Returns (results, failures) with the tolerances stated in this module's docstring."""
-    res = step_parity(cfg, batch, seed)
+    res = step_parity(cfg, batch, seed, mixed_precision)
     bad = []
     for name, errs in res.items():
         if name == "loss":

@@ -16,6 +16,24 @@ from oracle import oracle as O
 
 BF16_TOL = 4e-3
 F32_TOL = 3e-4
+#: the 16-bit storage format the checks run in: bf16 (default) or fp16 (the reference's mixed_float16 policy, train.py:34,
+#: 43-45); see half_format()
+HALF = torch.bfloat16
+
+
+class half_format:
+    """with half_format(torch.float16): ...  -- runs the checks with fp16 tensors (the library follows the tensors' dtype)."""
+
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        global HALF
+        self.old, HALF = HALF, self.dtype
+
+    def __exit__(self, *exc):
+        global HALF
+        HALF = self.old
 
 
 def _dev():
@@ -23,7 +41,7 @@ def _dev():
 
 
 def _bf(t):
-    return t.to(torch.bfloat16)
+    return t.to(HALF)
 
 
 def _metrics(name, got, ref, tol):
@@ -47,7 +65,7 @@ def _ops():
 
 def _slice_buf(B, H, W, C, pad_front, pad_back, dev, fill=None):
     """A [B,H,W,C] bf16 view living inside a wider NHWC buffer (exercises pixel strides / concat slices)."""
-    full = torch.full((B, H, W, pad_front + C + pad_back), 7.0 if fill is None else fill, dtype=torch.bfloat16,
+    full = torch.full((B, H, W, pad_front + C + pad_back), 7.0 if fill is None else fill, dtype=HALF,
                       device=dev)
     return full, full[..., pad_front:pad_front + C]
 
@@ -411,7 +429,7 @@ def check_dense_mse(B=2, H=32, Cu=64, seed=10):
     dev = _dev()
     _, u0v = _slice_buf(B, H, H, Cu, 0, 64, dev)
     u0v.copy_(u0)
-    du0 = torch.full((B, H, H, Cu), 7.0, dtype=torch.bfloat16, device=dev)
+    du0 = torch.full((B, H, H, Cu), 7.0, dtype=HALF, device=dev)
     predg = torch.empty(B, H, H, 3, device=dev)
     lossg = torch.full((1,), 5.0, device=dev)
     dwd = torch.full((Cu + 3, 3), 3.0, device=dev)
@@ -438,7 +456,7 @@ def check_adam(n=4096 + 128, steps=3, seed=11):
     wo, m, v = w.clone(), torch.zeros(n), torch.zeros(n)
     dev = _dev()
     wg, mg, vg = w.clone().to(dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
-    wb = torch.zeros(n, dtype=torch.bfloat16, device=dev)
+    wb = torch.zeros(n, dtype=HALF, device=dev)
     it = torch.zeros(1, dtype=torch.int64, device=dev)
     hyper = torch.zeros(2, device=dev)
     for s in range(steps):
@@ -506,7 +524,7 @@ def forced(fn, BN=0, splits=0, pair=0, nofuse=0, budget=0, finish=None, **kw):
     lib = _lib.init(0)
     # how split-K is finished: "cluster" = the splits are one thread-block cluster (partials through distributed shared
     # memory), "l2" = in-launch rendezvous over fp32 slabs in global memory, "kernel" = separate finishing kernel
-    cs = {None: 0, "l2": 1, "cluster": 2, "kernel": 0}[finish]
+    cs = {None: 1, "l2": 1, "cluster": 2, "kernel": 1}[finish]
     if finish == "kernel":
         nofuse = 1
     for key, val in ((3, BN), (4, splits), (19, pair), (12, nofuse), (22, budget), (25, cs)):
@@ -515,8 +533,9 @@ def forced(fn, BN=0, splits=0, pair=0, nofuse=0, budget=0, finish=None, **kw):
         m = fn(**kw)
         plan = ops.last_plan()
     finally:
-        for key in (3, 4, 19, 12, 22, 25):
+        for key in (3, 4, 19, 12, 22):
             lib.gct2_debug_set(key, 0)
+        lib.gct2_debug_set(25, 1)  # the library's default
     m["name"] += (f" [BN={BN or 'auto'} splits={splits or 'auto'} pair={pair} finish={finish or ('kernel' if nofuse else 'auto')}"
                   f"{f' budget={budget}' if budget else ''} -> {plan}]")
     want = {}

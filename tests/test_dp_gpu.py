@@ -17,7 +17,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out, use_graph):
+def _worker(rank, world, port, out, use_graph, grad_dtype):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -29,7 +29,8 @@ def _worker(rank, world, port, out, use_graph):
         cfg = O.TINY
         ncfg = NetConfig(size=cfg.size, pixel_size=cfg.pixel_size, max_size=cfg.max_size, octaves=cfg.octaves)
         per = 2
-        eng = UNetEngine(ncfg, per, dp=DataParallel(bucket_bytes=1 << 20), use_graph=use_graph)
+        eng = UNetEngine(ncfg, per, dp=DataParallel(bucket_bytes=1 << 20, grad_dtype=grad_dtype, nccl_ctas=16),
+                         use_graph=use_graph)
         eng.load_weights(O.glorot_init(cfg, 0))
         x, t, e = O.synthetic_batch(cfg, per * world, 1)
         lo, hi = shard_batch(per * world, world, rank)
@@ -59,14 +60,15 @@ def _worker(rank, world, port, out, use_graph):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("grad_dtype", ["bf16", "fp32"])
 @pytest.mark.parametrize("use_graph", [False, True], ids=["eager", "cuda_graph"])
-def test_two_gpu_data_parallel_step_matches_oracle(tmp_path, use_graph):
+def test_two_gpu_data_parallel_step_matches_oracle(tmp_path, use_graph, grad_dtype):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
     import torch.multiprocessing as mp
     from tests import engine_checks as E
     out = str(tmp_path / "dp.pt")
-    mp.spawn(_worker, args=(2, _free_port(), out, use_graph), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), out, use_graph, grad_dtype), nprocs=2, join=True)
     got = torch.load(out)
     cfg = O.TINY
     weights = O.glorot_init(cfg, 0)

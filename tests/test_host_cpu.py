@@ -92,6 +92,23 @@ def test_compile_hands_the_optimizer_to_the_denoiser():
         tr.compile(object(), T.identity)
 
 
+def test_mixed_precision_switch_reaches_the_engine_config():
+    """train.py:34,43-45,82-83: `mixed_precision = True` selects fp16 storage and the LossScaleOptimizer's parameters."""
+    old = T.mixed_precision
+    T.mixed_precision = True
+    try:
+        d = T.Denoiser()
+        tr = T.Trainer(d)
+        tr.compile(T.LossScaleOptimizer(T.Adam(T.WarmUp(2e-5, 2000)), initial_scale=2.0 ** 12, dynamic_growth_steps=7),
+                   T.identity)
+        cfg = d.net_config(256)
+        assert cfg.mixed_precision and cfg.loss_scale_init == 2.0 ** 12 and cfg.loss_scale_growth == 7
+        assert (cfg.base_lr, cfg.warm_up) == (2e-5, 2000) and T.preferred_type() == torch.float16
+    finally:
+        T.mixed_precision = old
+    assert not T.Denoiser().net_config(256).mixed_precision and T.preferred_type() == torch.bfloat16
+
+
 def test_layers_refuse_cpu_tensors():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         T.DownShuffle(64)(torch.zeros(1, 8, 8, 64))

@@ -219,3 +219,36 @@ def test_sample_loop_algebra():
     fake3 = a ** 0.5 * xt2 + (1 - a) ** 0.5 * et2
     assert torch.allclose(a ** 0.5 * xt + (1 - a) ** 0.5 * et, fake3, atol=1e-5)
     assert a2 > a  # the schedule decays with t (train.py:85-93)
+
+
+def test_dynamic_loss_scale_follows_keras_rules():
+    """tf.keras.mixed_precision.LossScaleOptimizer (train.py:82-83), dynamic: halve (never below 1) and skip on a
+    non-finite step, double after `growth_steps` finite steps in a row, counter reset by either event."""
+    ls = O.DynamicLossScale(8.0, growth_steps=2)
+    assert ls.update(True) and (ls.scale, ls.good_steps) == (8.0, 1)
+    assert ls.update(True) and (ls.scale, ls.good_steps) == (16.0, 0)
+    assert not ls.update(False) and (ls.scale, ls.good_steps) == (8.0, 0)
+    assert ls.update(True) and not ls.update(False) and (ls.scale, ls.good_steps) == (4.0, 0)
+    for _ in range(5):
+        ls.update(False)
+    assert ls.scale == 1.0
+
+
+def test_mixed_precision_trainer_skips_overflowing_steps():
+    """OracleTrainer(mixed_precision=True): with fp16 storage emulated, a scale of 2^40 overflows the scaled gradient of
+    the loss -> the step is skipped (variables, moments, iteration count untouched) and the scale halves; with 2^15 the
+    step is applied and matches the fp32 trainer closely (that is what the loss scale is for)."""
+    cfg = O.Config(size=16, pixel_size=64, max_size=64, octaves=2)
+    w = O.glorot_init(cfg, 0)
+    x, t, e = O.synthetic_batch(cfg, 2, 1)
+    tr = O.OracleTrainer(cfg, weights=w, mixed_precision=True, initial_scale=2.0 ** 40)
+    tr.train_step(x, t, e)
+    assert tr.iterations == 0 and tr.loss_scale.scale == 2.0 ** 39
+    assert all(torch.equal(tr.weights[k], w[k]) for k in w) and all(float(v.abs().max()) == 0 for v in tr.m.values())
+    a, b = O.OracleTrainer(cfg, weights=w, mixed_precision=True), O.OracleTrainer(cfg, weights=w)
+    la, lb = a.train_step(x, t, e), b.train_step(x, t, e)
+    assert a.iterations == 1 and abs(la - lb) <= 1e-3 * lb
+    for k in w:
+        if k.endswith("kernel"):
+            da, db = a.weights[k] - w[k], b.weights[k] - w[k]
+            assert float((da - db).norm() / db.norm()) < 0.2, k   # Adam's first step is sign-like: most signs agree

@@ -24,9 +24,9 @@ sys.path.insert(0, ROOT)
 # the production library carries no stamps in its main loops: use the -DGCT2_TIMELINE build (make -C csrc timeline)
 _TL = os.path.join(ROOT, "gan_class_transfer2_b200", "libgct2_b200_timeline.so")
 if "GCT2_LIB" not in os.environ:
-    if not os.path.exists(_TL):
-        import subprocess
-        subprocess.run(["make", "-C", os.path.join(ROOT, "gan_class_transfer2_b200", "csrc"), "timeline"], check=True)
+    import subprocess
+    subprocess.run(["make", "-C", os.path.join(ROOT, "gan_class_transfer2_b200", "csrc"), "timeline"], check=True,
+                   capture_output=True)  # no-op when the library is newer than the sources
     os.environ["GCT2_LIB"] = _TL
 
 from gan_class_transfer2_b200 import _lib, ops  # noqa: E402
@@ -44,6 +44,9 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--only", default="")
     ap.add_argument("--debug", action="append", default=[])
+    ap.add_argument("--cfg", action="append", default=[],
+                    help='several plans in one process: "3=64 4=8 25=2" (space-separated gct2_debug_set key=value)')
+    ap.add_argument("--passes", default="fprop,dgrad,wgrad")
     ap.add_argument("--weights-stable", action="store_true", help="pass GCT2_WEIGHTS_STABLE (early weight fetch)")
     ap.add_argument("--cold-weights", action="store_true",
                     help="flush L2 before the measured launch, then re-touch the activations only: the state a layer "
@@ -57,6 +60,18 @@ def main():
     lib.gct2_debug_set(7, 1)
     lib.gct2_debug_set(2, 1)
     B = a.batch
+    for cfg in (a.cfg or [""]):
+        keys = [tuple(int(t) for t in kv.split("=")) for kv in cfg.split()]
+        for k, v in keys:
+            lib.gct2_debug_set(k, v)
+        if a.cfg:
+            print(json.dumps({"cfg": cfg}), flush=True)
+        run(a, lib, dev, B)
+        for k, v in keys:
+            lib.gct2_debug_set(k, 0)
+
+
+def run(a, lib, dev, B):
     g = torch.Generator(device=dev).manual_seed(0)
     for name, kind, Hin, Cin, Cout in layer_table(256, 128, 512, 6):
         if Cin == 3 or (a.only and a.only not in name):
@@ -80,6 +95,8 @@ def main():
                       "dgrad": lambda: ops.convT4s2_dgrad(dy, w, dx, x, Cin, ws, a.weights_stable),
                       "wgrad": lambda: ops.convT4s2_wgrad(x, dy, dw, ws)}
         for pname, fn in passes.items():
+            if pname not in a.passes.split(","):
+                continue
             lib.gct2_debug_set(2, 0)
             for _ in range(3):
                 fn()
