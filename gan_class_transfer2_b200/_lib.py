@@ -66,7 +66,7 @@ _PROTOS = {
     "gct2_bias_grad": (c_int, [_P, c_int, c_longlong, c_int, _P, _P]),
     "gct2_bias_grad_multi": (c_int, [c_int, _P, _P, _P, _P, _P, c_int, _P]),
     "gct2_dense_mse": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, c_longlong, c_int, c_float,
-                               c_int, c_int, _P, _P]),
+                               c_int, c_int, _P, _P, _P, c_longlong, c_int, c_int, _P]),
     "gct2_adam_keras": (c_int, [_P, _P, _P, _P, _P, c_longlong, _P, _P, c_float, c_int, c_float, c_float, c_float,
                                 c_float, _P]),
     "gct2_adam_prepare": (c_int, [_P, _P, c_float, c_int, c_float, c_float, _P]),
@@ -76,7 +76,9 @@ _PROTOS = {
                                 c_float, _P, c_longlong, _P, _P]),
     "gct2_step_begin_u8": (c_int, [_P, _P, _P, c_int, _P, _P, _P, c_int, c_int, c_int, ctypes.c_ulonglong, _P, _P, c_float,
                                    c_int, c_float, c_float, _P, c_longlong, _P, _P]),
-    "gct2_sample_update": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_longlong, _P]),
+    "gct2_sample_update": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_longlong, c_int, _P]),
+    "gct2_latent_edits": (c_int, [_P, _P, _P, c_int, c_int, _P]),
+    "gct2_rmse": (c_int, [_P, _P, c_longlong, _P, _P]),
     "gct2_cast_bf16": (c_int, [_P, _P, c_longlong, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOS)

@@ -185,9 +185,10 @@ int gct2_bias_grad_multi(int n, const uint16_t* const* dz, const int* ld, const 
 int gct2_dense_mse(const uint16_t* u0, int ldu, const float* noised, const float* x, const float* wd,
                    const float* bd, float* pred, float* loss, uint16_t* du0, int lddu, float* dwd, float* dbd,
                    long long pixels, int Cu, float inv_n, int backward, int accumulate, const float* loss_scale,
+                   const float* eps, const int32_t* t_int, long long pixels_per_image, int target_mode, int steps,
                    void* stream) {
   return dense_mse(CB(u0), ldu, noised, x, wd, bd, pred, loss, MB(du0), lddu, dwd, dbd, pixels, Cu, inv_n, backward,
-                   accumulate ? 0 : 1, loss_scale, S(stream));
+                   accumulate ? 0 : 1, loss_scale, eps, t_int, pixels_per_image, target_mode, steps, S(stream));
 }
 
 int gct2_adam_keras(float* w, float* m, float* v, const float* g, uint16_t* w_bf16, long long n,
@@ -232,9 +233,13 @@ int gct2_step_begin_u8(const uint8_t* img, const uint8_t* flip, float* x_out, in
 }
 
 int gct2_sample_update(const float* pred, float* fake, float* x_theta, float* eps_theta, int t, int t_next, int steps,
-                       long long n, void* stream) {
-  return sample_update(pred, fake, x_theta, eps_theta, t, t_next, steps, n, S(stream));
+                       long long n, int target_mode, void* stream) {
+  return sample_update(pred, fake, x_theta, eps_theta, t, t_next, steps, n, target_mode, S(stream));
 }
+int gct2_latent_edits(const float* eps_theta, const float* dictionary, float* out, int size, int entries, void* stream) {
+  return latent_edits(eps_theta, dictionary, out, size, entries, S(stream));
+}
+int gct2_rmse(const float* a, const float* b, long long n, float* out, void* stream) { return rmse(a, b, n, out, S(stream)); }
 
 int gct2_cast_bf16(const float* src, uint16_t* dst, long long n, void* stream) {
   return cast_bf16(src, MB(dst), n, S(stream));

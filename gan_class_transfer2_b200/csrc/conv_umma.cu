@@ -455,12 +455,14 @@ static Choice choose(const DeviceState& ds, int mode, int mTiles, int phases, in
       const long long items = (long long)mTiles * phases * (isW ? 16 : 1) * nTiles * splits;
       const long long active = items < maxCtas ? items : maxCtas;
       const long long waves = (items + active - 1) / active;
-      // one 64-wide k-chunk: the selection constants are the ones fitted in round 1 (408 + 0.96 BN cycles, chip-wide
-      // L2 -> SM rate 6000 B/clk).  Round 2 measured the steady state per CTA directly (tools/timeline.py: 285 / 375 /
-      // 665 cycles at BN = 64 / 128 / 256 with two chunks per ring slot -- every shape moves ~170 bytes per clock
-      // through shared memory, TMA writes plus MMA reads), but plans chosen with those figures were slower in the step
-      // (0.582 vs 0.564 ms at batch 1): the model's split-K epilogue terms are calibrated against the old ones.
-      double tk = 408.0 + 0.96 * BN;
+      // one 64-wide k-chunk: issue-bound at small grids.  Selection constants: 290 cycles with two chunks per ring slot
+      // (BN <= 128), 408 + 0.96 BN with one (BN = 256), never below the tensor pipe's ~2.1 BN, and the chip-wide L2 -> SM
+      // rate (6000 B/clk) when every SM pulls at once.  Round 2 also measured the steady state per CTA directly
+      // (tools/timeline.py: 285 / 375 / 665 cycles at BN = 64 / 128 / 256 -- every shape moves ~170 bytes per clock through
+      // shared memory, TMA writes plus MMA reads), but plans chosen with those figures were slower in the step (0.582 vs
+      // 0.564 ms at batch 1): the split-K epilogue terms below are calibrated against the constants kept here.
+      double tk = kps_for(BN) == 2 ? 290.0 : 408.0 + 0.96 * BN;
+      if (tk < 2.1 * BN) tk = 2.1 * BN;
       const double l2 = (16384.0 + BN * 128.0) * (double)active / 6000.0;
       if (l2 > tk) tk = l2;
       const double main = kIters * tk;

@@ -290,11 +290,21 @@ __device__ __forceinline__ void issue_chunk(const ConvParams& p, const CUtensorM
 //   L2 form (fused): every split of the tile has its own CTA and the host launched no more CTAs than can be resident
 //     at once; partials go through tile-major fp32 slabs in global memory and a counter rendezvous.
 // A separate (not inlined) function: its registers do not add to the pressure of the direct epilogues.
+#ifdef GCT2_INLINE_FINISH
+#define GCT2_FINISH_ATTR __forceinline__
+#else
+#define GCT2_FINISH_ATTR __noinline__
+#endif
+#ifdef GCT2_NO_F16
+#define GCT2_F16_OF(p) 0
+#else
+#define GCT2_F16_OF(p) ((p).f16)
+#endif
 template <int MODE, int BN>
-__device__ __noinline__ void splitk_finish_in_place(const ConvParams& p, const WorkItem& w, int tileId, bool csplit,
+__device__ GCT2_FINISH_ATTR void splitk_finish_in_place(const ConvParams& p, const WorkItem& w, int tileId, bool csplit,
                                                     uint8_t* smem, uint64_t* red_full, int warp, int lane) {
   constexpr int NE = kEpilogueWarps<BN>();
-  const int f16 = p.f16;
+  const int f16 = GCT2_F16_OF(p);
       // ---- split-K finished in place: split s sums rows [s*R, (s+1)*R) of the tile over all partials in split
       // order (bit-reproducible), applies the real epilogue and writes the bf16 output -- coalesced, no extra launch.
       //   cluster form (csplit): the splits are the CTAs of one cluster (co-scheduled by the hardware, so they may
@@ -563,7 +573,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
       constexpr int A_MN = (MODE == MODE_W) ? 1 : 0;
       constexpr int B_MN = (MODE == MODE_P) ? 0 : 1;
       // cta_group::2: 256 rows over the pair; operand format by the launch's storage policy
-      const uint32_t idesc = p.f16 ? make_idesc_bf16(pair ? 256 : 128, BN, A_MN, B_MN, 0)
+      const uint32_t idesc = GCT2_F16_OF(p) ? make_idesc_bf16(pair ? 256 : 128, BN, A_MN, B_MN, 0)
                                    : make_idesc_bf16(pair ? 256 : 128, BN, A_MN, B_MN, 1);
       const uint32_t a_lbo = A_MN ? (uint32_t)p.mnLbo : 16u, a_sbo = A_MN ? (uint32_t)p.mnSbo : 1024u;
       const uint32_t b_lbo = B_MN ? (uint32_t)p.mnLbo : 16u, b_sbo = B_MN ? (uint32_t)p.mnSbo : 1024u;
@@ -651,7 +661,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
       const int q = warp & 3;              // TMEM lane quarter this warp may access
       const int cgrp = (warp - 4) >> 2;    // which slice of the tile's columns
       const int r = q * 32 + lane;
-      const int f16 = p.f16;
+      const int f16 = GCT2_F16_OF(p);
       uint32_t acc = 0, acc_phase = 0;
       for (int item = clusterId; item < p.numClusterItems; item += numClusters) {
         const WorkItem w = decode_item<MODE>(p, item, rm);

@@ -98,8 +98,13 @@ __device__ __forceinline__ float abar_of(int t, int steps) {
   const float om = 1.f - (float)t / (float)(steps + 1);
   return om * om * 0.25f;
 }
+__device__ __forceinline__ float abar_of_f(float t, int steps) {
+  const float om = 1.f - t / (float)(steps + 1);
+  return om * om * 0.25f;
+}
 __global__ void sample_update_kernel(const float4* __restrict__ pred, float4* __restrict__ fake, float4* __restrict__ x_theta,
-                                     float4* __restrict__ eps_theta, int t, int t_next, int steps, long long nvec) {
+                                     float4* __restrict__ eps_theta, int t, int t_next, int steps, long long nvec,
+                                     int mode) {
   TraceScope trace(10);
   pdl_launch_dependents();
   pdl_wait();
@@ -111,9 +116,30 @@ __global__ void sample_update_kernel(const float4* __restrict__ pred, float4* __
        i += (long long)gridDim.x * blockDim.x) {
     float4 xt, et;
     if (pred != nullptr) {
-      xt = __ldg(pred + i);
+      const float4 pr = __ldg(pred + i);
       const float4 f = fake[i];
-      et = make_float4((f.x - sa * xt.x) / sb, (f.y - sa * xt.y) / sb, (f.z - sa * xt.z) / sb, (f.w - sa * xt.w) / sb);
+      if (mode & 8) {
+        // ordinary_differential_equation (train.py:382-391, 452-461): x_theta from the predicted previous step;
+        // epsilon_theta is left untouched by the reference
+        const float a1 = abar_of(t - 1, steps), sa1 = sqrtf(a1), sb1 = sqrtf(1.f - a1);
+        const float den = sa1 * sb - sa * sb1;
+        xt = make_float4((pr.x * sb - f.x * sb1) / den, (pr.y * sb - f.y * sb1) / den, (pr.z * sb - f.z * sb1) / den,
+                         (pr.w * sb - f.w * sb1) / den);
+        et = eps_theta[i];
+      } else if (mode == 0) {  // predict_x (train.py:394-398, 464-468)
+        xt = pr;
+        et = make_float4((f.x - sa * xt.x) / sb, (f.y - sa * xt.y) / sb, (f.z - sa * xt.z) / sb, (f.w - sa * xt.w) / sb);
+      } else {  // the network predicts (scaled) epsilon (train.py:400-413, 470-479)
+        float4 sc4;
+        if (mode & 2) {
+          et = make_float4(pr.x / sb, pr.y / sb, pr.z / sb, pr.w / sb);
+          sc4 = pr;
+        } else {
+          et = pr;
+          sc4 = make_float4(pr.x * sb, pr.y * sb, pr.z * sb, pr.w * sb);
+        }
+        xt = make_float4((f.x - sc4.x) / sa, (f.y - sc4.y) / sa, (f.z - sc4.z) / sa, (f.w - sc4.w) / sa);
+      }
       x_theta[i] = xt;
       eps_theta[i] = et;
     } else {
@@ -128,7 +154,7 @@ __global__ void sample_update_kernel(const float4* __restrict__ pred, float4* __
 }
 
 int sample_update(const float* pred, float* fake, float* x_theta, float* eps_theta, int t, int t_next, int steps,
-                  long long n, cudaStream_t st) {
+                  long long n, int mode, cudaStream_t st) {
   if (n % 4 || steps < 1 || (pred != nullptr && (t < 1 || t > steps))) {
     set_error("sample_update: n must be a multiple of 4 and 1 <= t <= steps (n=%lld t=%d steps=%d)", n, t, steps);
     return 1;
@@ -139,7 +165,7 @@ int sample_update(const float* pred, float* fake, float* x_theta, float* eps_the
   if (blocks < 1) blocks = 1;
   launch_k(sample_update_kernel, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const float4*>(pred),
            reinterpret_cast<float4*>(fake), reinterpret_cast<float4*>(x_theta), reinterpret_cast<float4*>(eps_theta), t,
-           t_next, steps, nvec);
+           t_next, steps, nvec, mode);
   GCT2_CHECK_LAUNCH("sample_update_kernel");
   return 0;
 }
@@ -488,7 +514,9 @@ __global__ void __launch_bounds__(256) dense_mse_kernel(const __nv_bfloat16* __r
                                                         float* __restrict__ loss, __nv_bfloat16* __restrict__ du0,
                                                         int lddu, float* __restrict__ dwd, float* __restrict__ dbd,
                                                         long long pixels, float invN, int backward, int f16,
-                                                        const float* __restrict__ loss_scale) {
+                                                        const float* __restrict__ loss_scale,
+                                                        const float* __restrict__ eps, const int* __restrict__ t_int,
+                                                        long long ppi, int mode, int steps) {
   TraceScope trace(5);
   pdl_launch_dependents();
   pdl_wait();
@@ -522,6 +550,24 @@ __global__ void __launch_bounds__(256) dense_mse_kernel(const __nv_bfloat16* __r
     const bool live = p < pixels;
     float a[8];
     float nz[3] = {0.f, 0.f, 0.f}, xv[3] = {0.f, 0.f, 0.f};
+    // train.py:238-252: target = ca*x + cb*eps, compared with sc*prediction (predict_x, the default: ca = sc = 1, cb = 0)
+    float ca = 1.f, cb = 0.f, sc = 1.f;
+    if (mode != 0 && live) {
+      const float t = (float)__ldg(t_int + (int)(p / ppi));
+      const float ab = abar_of_f(t, steps), sb = sqrtf(1.f - ab);
+      if (mode & 8) {  // ordinary_differential_equation: the noised image of step t - 1
+        const float a1 = abar_of_f(t - 1.f, steps);
+        ca = sqrtf(a1);
+        cb = sqrtf(1.f - a1);
+      } else {
+        ca = 0.f;
+        cb = (mode & 2) ? sb : 1.f;        // predict_scaled_epsilon
+        if (mode & 4) {                    // prediction_weighting
+          cb *= sb;
+          sc = sb;
+        }
+      }
+    }
     if (live) {
       const uint4 uv = __ldg(reinterpret_cast<const uint4*>(u0 + p * ldu + sub * 8));
       a[0] = h_lo(uv.x, f16); a[1] = h_hi(uv.x, f16); a[2] = h_lo(uv.y, f16); a[3] = h_hi(uv.y, f16);
@@ -529,7 +575,8 @@ __global__ void __launch_bounds__(256) dense_mse_kernel(const __nv_bfloat16* __r
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         nz[c] = __ldg(noised + p * 3 + c);
-        xv[c] = __ldg(x + p * 3 + c);
+        xv[c] = ca * __ldg(x + p * 3 + c);
+        if (cb != 0.f) xv[c] = fmaf(cb, __ldg(eps + p * 3 + c), xv[c]);
       }
     } else {
 #pragma unroll
@@ -549,9 +596,9 @@ __global__ void __launch_bounds__(256) dense_mse_kernel(const __nv_bfloat16* __r
     for (int j = 0; j < 3; ++j) {
       const float pj = s[j] + nz[0] * wn[j] + nz[1] * wn[3 + j] + nz[2] * wn[6 + j] + bv[j];
       if (pred != nullptr && live && sub == j) pred[p * 3 + j] = pj;
-      const float diff = live ? pj - xv[j] : 0.f;
+      const float diff = live ? sc * pj - xv[j] : 0.f;
       if (sub == 0) lossAcc = fmaf(diff, diff, lossAcc);
-      d[j] = 2.f * diff * gradScale;  // loss scaling (mixed precision): the backward pass carries scale * gradient
+      d[j] = 2.f * diff * sc * gradScale;  // loss scaling (mixed precision): the backward pass carries scale * gradient
     }
     if (backward && live) {
       float r[8];
@@ -620,7 +667,13 @@ __global__ void __launch_bounds__(256) dense_mse_kernel(const __nv_bfloat16* __r
 
 int dense_mse(const __nv_bfloat16* u0, int ldu, const float* noised, const float* x, const float* wd,
               const float* bd, float* pred, float* loss, __nv_bfloat16* du0, int lddu, float* dwd, float* dbd,
-              long long pixels, int Cu, float invN, int backward, int zero, const float* loss_scale, cudaStream_t st) {
+              long long pixels, int Cu, float invN, int backward, int zero, const float* loss_scale, const float* eps,
+              const int* t_int, long long pixels_per_image, int target_mode, int steps, cudaStream_t st) {
+  if (target_mode != 0 && (t_int == nullptr || pixels_per_image < 1 || steps < 1 || ((target_mode & 7) && eps == nullptr) ||
+                           ((target_mode & 8) && eps == nullptr))) {
+    set_error("dense_mse: target mode %d needs t_int, eps, pixels_per_image and steps", target_mode);
+    return 1;
+  }
   if (Cu != 64 && Cu != 128) {
     set_error("dense_mse: the fused kernel expects 64 or 128 up0 channels (+3 image channels), got %d", Cu);
     return 1;
@@ -643,10 +696,10 @@ int dense_mse(const __nv_bfloat16* u0, int ldu, const float* noised, const float
   if (blocks < 1) blocks = 1;
   if (Cu == 64)
     launch_k(dense_mse_kernel<8>, dim3(blocks), dim3(256), 0, st, u0, ldu, noised, x, wd, bd, pred, loss, du0, lddu, dwd, dbd, pixels, invN,
-                                                backward, g_f16, loss_scale);
+                                                backward, g_f16, loss_scale, eps, t_int, pixels_per_image, target_mode, steps);
   else
     launch_k(dense_mse_kernel<16>, dim3(blocks), dim3(256), 0, st, u0, ldu, noised, x, wd, bd, pred, loss, du0, lddu, dwd, dbd, pixels,
-                                                 invN, backward, g_f16, loss_scale);
+                                                 invN, backward, g_f16, loss_scale, eps, t_int, pixels_per_image, target_mode, steps);
   GCT2_CHECK_LAUNCH("dense_mse_kernel");
   return 0;
 }
@@ -1072,6 +1125,99 @@ int loss_scale_check(const float* g, long long n, float* ls, cudaStream_t st) {
 int loss_scale_update(float* ls, int growth_steps, cudaStream_t st) {
   launch_k(loss_scale_update_kernel, dim3(1), dim3(1), 0, st, ls, growth_steps);
   GCT2_CHECK_LAUNCH("loss_scale_update_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ log_sample's latent edits (f1)
+// train.py:418-432: from the inverted latent epsilon_theta [S,S,3] the four latents that are decoded again --
+//   out[0] = epsilon_theta, out[1] = pixelated (4x4 average, nearest up-sampling), out[2] = shifted by one pixel along
+//   both axes (tf.roll, wrapping), out[3] = quantised: per pixel the nearest (squared distance, first minimum) of the K
+//   entries of dictionary [S,S,K,3].  One thread per pixel.
+__global__ void __launch_bounds__(256) latent_edits_kernel(const float* __restrict__ e, const float* __restrict__ dict,
+                                                           float* __restrict__ out, int S, int K) {
+  TraceScope trace(13);
+  pdl_launch_dependents();
+  pdl_wait();
+  trace.ready();
+  const long long n = (long long)S * S;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(p / S), x = (int)(p - (long long)y * S);
+    const float v0 = __ldg(e + p * 3), v1 = __ldg(e + p * 3 + 1), v2 = __ldg(e + p * 3 + 2);
+    float* o = out + p * 3;
+    o[0] = v0; o[1] = v1; o[2] = v2;
+    // pixelated: mean of the 4x4 block, summed in row-major order (the order of a pooling window)
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    const int by = y & ~3, bx = x & ~3;
+    for (int dy = 0; dy < 4; ++dy)
+      for (int dx = 0; dx < 4; ++dx) {
+        const float* q = e + ((long long)(by + dy) * S + bx + dx) * 3;
+        s0 += __ldg(q); s1 += __ldg(q + 1); s2 += __ldg(q + 2);
+      }
+    o += n * 3;
+    o[0] = s0 * 0.0625f; o[1] = s1 * 0.0625f; o[2] = s2 * 0.0625f;
+    // shifted: out[y][x] = e[y-1][x-1] with wrap-around
+    const float* q = e + ((long long)((y + S - 1) % S) * S + (x + S - 1) % S) * 3;
+    o += n * 3;
+    o[0] = __ldg(q); o[1] = __ldg(q + 1); o[2] = __ldg(q + 2);
+    // quantised
+    const float* d = dict + p * K * 3;
+    int best = 0;
+    float bestErr = 3.4e38f;
+    for (int k = 0; k < K; ++k) {
+      const float a0 = v0 - __ldg(d + k * 3), a1 = v1 - __ldg(d + k * 3 + 1), a2 = v2 - __ldg(d + k * 3 + 2);
+      const float err = a0 * a0 + a1 * a1 + a2 * a2;
+      if (err < bestErr) {
+        bestErr = err;
+        best = k;
+      }
+    }
+    o += n * 3;
+    o[0] = __ldg(d + best * 3); o[1] = __ldg(d + best * 3 + 1); o[2] = __ldg(d + best * 3 + 2);
+  }
+  trace.end();
+}
+int latent_edits(const float* eps_theta, const float* dictionary, float* out, int S, int K, cudaStream_t st) {
+  if (S < 4 || S % 4 || K < 1) {
+    set_error("latent_edits: the image side must be a multiple of 4 and the dictionary non-empty (S=%d K=%d)", S, K);
+    return 1;
+  }
+  int blocks = (int)(((long long)S * S + 255) / 256);
+  if (blocks > g_ew_sms * 8) blocks = g_ew_sms * 8;
+  launch_k(latent_edits_kernel, dim3(blocks), dim3(256), 0, st, eps_theta, dictionary, out, S, K);
+  GCT2_CHECK_LAUNCH("latent_edits_kernel");
+  return 0;
+}
+
+// train.py:357-361 'example loss': out[0] = sqrt(mean((a - b)^2)) over n elements; one block (n is one image).
+__global__ void __launch_bounds__(1024) rmse_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
+                                                    float* __restrict__ out) {
+  TraceScope trace(14);
+  pdl_launch_dependents();
+  pdl_wait();
+  trace.ready();
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float d = __ldg(a + i) - __ldg(b + i);
+    acc = fmaf(d, d, acc);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) out[0] = sqrtf(v / (float)n);
+  }
+  trace.end();
+}
+int rmse(const float* a, const float* b, long long n, float* out, cudaStream_t st) {
+  if (n < 1) {
+    set_error("rmse: empty input");
+    return 1;
+  }
+  launch_k(rmse_kernel, dim3(1), dim3(1024), 0, st, a, b, n, out);
+  GCT2_CHECK_LAUNCH("rmse_kernel");
   return 0;
 }
 

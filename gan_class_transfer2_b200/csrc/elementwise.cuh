@@ -16,7 +16,10 @@ int conv4s2_c3_wgrad(const float* x, const __nv_bfloat16* dz, int lddz, float* d
                      int Cout, int zero, cudaStream_t st);
 int dense_mse(const __nv_bfloat16* u0, int ldu, const float* noised, const float* x, const float* wd,
               const float* bd, float* pred, float* loss, __nv_bfloat16* du0, int lddu, float* dwd, float* dbd,
-              long long pixels, int Cu, float invN, int backward, int zero, const float* loss_scale, cudaStream_t st);
+              long long pixels, int Cu, float invN, int backward, int zero, const float* loss_scale, const float* eps,
+              const int* t_int, long long pixels_per_image, int target_mode, int steps, cudaStream_t st);
+int latent_edits(const float* eps_theta, const float* dictionary, float* out, int S, int K, cudaStream_t st);
+int rmse(const float* a, const float* b, long long n, float* out, cudaStream_t st);
 int bias_grad_multi(int n, const __nv_bfloat16* const* dz, const int* ld, const long long* rows, const int* C,
                     float* const* db, int zero, cudaStream_t st);
 int bias_grad(const __nv_bfloat16* dz, int ld, long long rows, int C, float* db, cudaStream_t st);
@@ -32,7 +35,7 @@ int loss_scale_check(const float* g, long long n, float* ls, cudaStream_t st);
 int loss_scale_update(float* ls, int growth_steps, cudaStream_t st);
 void elementwise_set_f16(int f16);
 int sample_update(const float* pred, float* fake, float* x_theta, float* eps_theta, int t, int t_next, int steps,
-                  long long n, cudaStream_t st);
+                  long long n, int mode, cudaStream_t st);
 int step_begin(const float* x, const uint8_t* x_u8, const uint8_t* flip, float* x_out, int W, float* noised,
                float* eps_out, int* t_out, int B, int elemsPerImage, int steps,
                unsigned long long seed, const long long* iterations, float* hyper, float base_lr, int warmup_steps,

@@ -51,6 +51,9 @@ class NetConfig:
     mixed_precision: bool = False
     loss_scale_init: float = 2.0 ** 15      # Keras LossScaleOptimizer defaults
     loss_scale_growth: int = 2000
+    #: train.py:29-32 (predict_x / predict_scaled_epsilon / prediction_weighting / ordinary_differential_equation) as
+    #: ops.target_mode bits: what the loss compares (train.py:238-252) and what log_sample derives from a prediction
+    target_mode: int = 0
 
     def down_c(self, i: int) -> int:  # train.py:181
         if self.down_filters is not None:
@@ -443,7 +446,8 @@ class UNetEngine:
                       self.loss, inv_n, pred=self.pred if want_pred else None,
                       du0=self.gu0 if backward else None, dwd=self.view(self.g, "dense/kernel") if backward else None,
                       dbd=self.view(self.g, "dense/bias") if backward else None, accumulate=True,
-                      loss_scale=self.ls if (backward and self.cfg.mixed_precision) else None)
+                      loss_scale=self.ls if (backward and self.cfg.mixed_precision) else None,
+                      eps=self.eps, t_int=self.t_int, mode=cfg.target_mode, steps=cfg.steps)
 
     def _backward(self, apply_adam: bool, inc_iterations: bool = False) -> None:
         """Three chains that share the GPU (at batch 1 no layer fills 148 SMs on its own):
@@ -568,7 +572,9 @@ class UNetEngine:
         bucket_done("down0/kernel")
         if sw is not main:
             main.wait_stream(sw)
-        if sa is not main:
+        if sa is not main and apply_adam:
+            # (only when this call forked work onto the optimiser stream: joining a stream that holds nothing of this
+            # step would tie a captured graph to uncaptured work)
             main.wait_stream(sa)
         for work in pending:
             work.wait()
@@ -590,13 +596,14 @@ class UNetEngine:
             # the batch as decode_file's uint8 bytes: decode (+ flip) happens inside the prologue launch
             ops.step_begin_u8(self.x_u8, self.flip, self.x, self.noised, self.iterations, self.hyper,
                               self.g[:self.small], self.loss, self.rng_seed, cfg.steps, cfg.base_lr, cfg.warm_up,
-                              cfg.beta1, cfg.beta2, t_out=self.t_int)
+                              cfg.beta1, cfg.beta2, t_out=self.t_int, eps_out=self.eps if cfg.target_mode else None)
         elif draw:
             # train.py:224-234 in one launch: t_int ~ U{1..steps} and epsilon ~ N(0,1) drawn on the device (Philox,
             # offset by the optimiser iteration), noising, zeroing of the atomically-accumulated gradients + loss, and
             # this step's Adam alpha; the iteration counter is advanced by the step's last Adam launch
             ops.step_begin(self.x, self.noised, self.iterations, self.hyper, self.g[:self.small], self.loss,
-                           self.rng_seed, cfg.steps, cfg.base_lr, cfg.warm_up, cfg.beta1, cfg.beta2, t_out=self.t_int)
+                           self.rng_seed, cfg.steps, cfg.base_lr, cfg.warm_up, cfg.beta1, cfg.beta2, t_out=self.t_int,
+                           eps_out=self.eps if cfg.target_mode else None)  # targets other than x need the drawn noise
         else:
             self._zero_small_grads()
             if cfg.mixed_precision:
@@ -751,11 +758,12 @@ class UNetEngine:
 
         def body():
             steps = self.cfg.steps
-            ops.sample_update(None, self.noised, self.xt, self.et, t_values[0], t_values[0], steps)  # first mix
+            mode = self.cfg.target_mode
+            ops.sample_update(None, self.noised, self.xt, self.et, t_values[0], t_values[0], steps, mode)  # first mix
             for k, t in enumerate(t_values):
                 self._forward(want_pred=True, backward=False, inv_n=1.0)
                 ops.sample_update(self.pred, self.noised, self.xt, self.et, t,
-                                  t_values[k + 1] if k + 1 < len(t_values) else 0, steps)
+                                  t_values[k + 1] if k + 1 < len(t_values) else 0, steps, mode)
 
         if not self.use_graph:
             body()

@@ -245,9 +245,22 @@ def bias_grad_multi(plan: BiasGradPlan, accumulate: bool = False):
                                    current_stream()))
 
 
+TARGET_X, TARGET_EPSILON, TARGET_SCALED, TARGET_WEIGHTED, TARGET_ODE = 0, 1, 2, 4, 8
+
+
+def target_mode(predict_x: bool = True, predict_scaled_epsilon: bool = False, prediction_weighting: bool = False,
+                ordinary_differential_equation: bool = False) -> int:
+    """train.py:29-32 -> the GCT2_TARGET_* bits (train.py:238-252: ODE takes precedence, then predict_x)."""
+    if ordinary_differential_equation:
+        return TARGET_ODE
+    if predict_x:
+        return TARGET_X
+    return TARGET_EPSILON | (TARGET_SCALED if predict_scaled_epsilon else 0) | (TARGET_WEIGHTED if prediction_weighting else 0)
+
+
 @_timed
 def dense_mse(u0, noised, x, wd, bd, loss, inv_n: float, pred=None, du0=None, dwd=None, dbd=None,
-              accumulate: bool = False, loss_scale=None):
+              accumulate: bool = False, loss_scale=None, eps=None, t_int=None, mode: int = 0, steps: int = 200):
     """Dense(3) on concat([u0, noised]) (train.py:198-202) fused with the MSE (train.py:262-272) and, when du0 is
     given, their backward."""
     lib = _lib_for(u0)
@@ -256,7 +269,7 @@ def dense_mse(u0, noised, x, wd, bd, loss, inv_n: float, pred=None, du0=None, dw
     check(lib.gct2_dense_mse(ptr(u0), _nhwc(u0, torch.bfloat16), ptr(noised), ptr(x), ptr(wd), ptr(bd), ptr(pred),
                              ptr(loss), ptr(du0), _nhwc(du0, torch.bfloat16) if backward else 0, ptr(dwd), ptr(dbd),
                              pixels, u0.shape[3], inv_n, int(backward), int(accumulate), ptr(loss_scale),
-                             current_stream()))
+                             ptr(eps), ptr(t_int), u0.shape[1] * u0.shape[2], int(mode), int(steps), current_stream()))
     return loss
 
 
@@ -322,12 +335,12 @@ def step_begin_u8(img, flip, x_out, noised, iterations, hyper, gsmall, loss, see
 
 
 @_timed
-def sample_update(pred, fake, x_theta, eps_theta, t: int, t_next: int, steps: int = 200):
+def sample_update(pred, fake, x_theta, eps_theta, t: int, t_next: int, steps: int = 200, mode: int = 0):
     """log_sample's per-step arithmetic (train.py:365-398, 441-468, predict_x branch): x_theta / eps_theta from the
     prediction at step t, and the next Denoiser input (fake, in place) for step t_next.  pred=None: first mix only."""
     lib = _lib_for(fake)
     check(lib.gct2_sample_update(ptr(pred), ptr(fake), ptr(x_theta), ptr(eps_theta), t, t_next, steps, fake.numel(),
-                                 current_stream()))
+                                 int(mode), current_stream()))
 
 
 @_timed
@@ -351,3 +364,24 @@ def loss_scale_update(ls, growth_steps: int = 2000):
     """Dynamic loss-scale bookkeeping after the (possibly skipped) update; re-arms the finite flag."""
     lib = _lib_for(ls)
     check(lib.gct2_loss_scale_update(ptr(ls), int(growth_steps), current_stream()))
+
+
+@_timed
+def latent_edits(eps_theta, dictionary, out):
+    """train.py:418-432: [epsilon_theta, pixelated, shifted, quantised] from the inverted latent [1,S,S,3] and the
+    dictionary [S,S,K,3]; out fp32 [4,S,S,3]."""
+    lib = _lib_for(eps_theta)
+    S = eps_theta.shape[-2]
+    if tuple(dictionary.shape[:2]) != (S, S) or dictionary.shape[3] != 3 or out.shape[0] != 4 or not out.is_contiguous():
+        raise ValueError("latent_edits expects eps_theta [1,S,S,3], dictionary [S,S,K,3] and a contiguous out [4,S,S,3]")
+    check(lib.gct2_latent_edits(ptr(eps_theta.contiguous()), ptr(dictionary.contiguous()), ptr(out), S, dictionary.shape[2],
+                                current_stream()))
+    return out
+
+
+@_timed
+def rmse(a, b, out):
+    """train.py:357-361 'example loss': out[0] = sqrt(mean((a - b)**2))."""
+    lib = _lib_for(a)
+    check(lib.gct2_rmse(ptr(a.contiguous()), ptr(b.contiguous()), a.numel(), ptr(out), current_stream()))
+    return out

@@ -397,7 +397,9 @@ class Denoiser(Model):
         return NetConfig(size=image_size, pixel_size=pixel_size, max_size=max_size, octaves=len(downs), steps=steps,
                          warm_up=warm, base_lr=base_lr, beta1=opt.beta_1, beta2=opt.beta_2,
                          epsilon=opt.epsilon, down_filters=tuple(d.filters for d in downs),
-                         up_filters=tuple(u.filters for u in ups), mixed_precision=bool(mixed_precision), **extra)
+                         up_filters=tuple(u.filters for u in ups), mixed_precision=bool(mixed_precision),
+                         target_mode=ops.target_mode(predict_x, predict_scaled_epsilon, prediction_weighting,
+                                                     ordinary_differential_equation), **extra)
 
     def use_optimizer(self, opt: "Adam") -> None:
         """The optimiser the engines are built with (Trainer.compile hands over the one it was given, train.py:511-514)."""
@@ -432,12 +434,11 @@ class Denoiser(Model):
         return self._engines[key]
 
     def sample(self, x_theta, epsilon_theta, t_values):
-        """The diffusion loops of log_sample (train.py:365-398: `reversed(range(steps, 0, -1))`, batch 1;
-        train.py:441-468: `range(steps, 0, -1)`, batch 6) for the reference's default target (predict_x):
-        every iteration mixes `fake`, calls the denoiser and re-derives (x_theta, epsilon_theta).  Returns the final
-        pair as fp32 NHWC device tensors.  One CUDA graph per (batch, schedule)."""
-        if not (predict_x and not ordinary_differential_equation):
-            raise NotImplementedError("only the reference's default target (predict_x=True) is accelerated")
+        """The diffusion loops of log_sample (train.py:365-413: `reversed(range(steps, 0, -1))`, batch 1;
+        train.py:439-479: `range(steps, 0, -1)`, batch 6) for the objective the module's switches select (predict_x by
+        default; predicted / scaled noise and the ODE form as in train.py:382-413): every iteration mixes `fake`, calls
+        the denoiser and re-derives (x_theta, epsilon_theta).  Returns the final pair as fp32 NHWC device tensors.  One
+        CUDA graph per (batch, schedule)."""
         B, H, W, C = x_theta.shape
         if C != 3 or H != W or tuple(epsilon_theta.shape) != tuple(x_theta.shape):
             raise ValueError("sample expects two square NHWC tensors [B,S,S,3] of equal shape")
@@ -504,8 +505,6 @@ class Trainer(Model):
         B, H, W, C = x.shape
         if C != 3 or H != W:
             raise ValueError("Trainer expects square NHWC images with 3 channels")
-        if not (predict_x and not ordinary_differential_equation):
-            raise NotImplementedError("only the reference's default target (predict_x=True, train.py:243-244) is accelerated")
         return self.denoiser.engine(B, H)
 
     def call(self, x, t_int=None, epsilon=None):
@@ -541,6 +540,73 @@ class Trainer(Model):
         loss = loss.clone()
         # identity (train.py:171-173) is the mean of an already-scalar loss: skip the extra launch
         return {"loss": loss if self.compiled_loss is identity else self.compiled_loss(None, loss)}
+
+
+# ------------------------------------------------------------------------------------------------ log_sample
+#: train.py:305-311: the fixed evaluation tensors.  The reference reads `example_image` from disk at import; here the
+#: caller assigns them (fp32 device tensors): example_image [1,S,S,3] in [-1,1), example [1,2,S,S,3] ~ N(0,1),
+#: dictionary [S,S,2**bits_per_pixel,3] ~ N(0,1).  None -> log_sample draws synthetic ones once.
+example_image: Optional[torch.Tensor] = None
+example: Optional[torch.Tensor] = None
+dictionary: Optional[torch.Tensor] = None
+bits_per_pixel = 3
+
+
+def log_sample(epochs, logs, denoiser=None):
+    """train.py:323-496 without the TensorBoard writer: returns what the reference logs -- {'example loss': float,
+    'denoised', 'step_1', 'step_0.25', 'step_0.5', 'step_0.75', 'fake': images (x*0.5+0.5)} -- computed on the device:
+      :325-361  one denoising of the example at test_step and its RMSE (gct2_rmse);
+      :365-413  the forward (inversion) loop t = 1..steps at batch 1 (Denoiser.sample: one CUDA graph);
+      :418-432  the latent edits (gct2_latent_edits) + the two fixed noise samples -> batch 6;
+      :439-496  the backward loop t = steps..1 at batch 6, with x_theta snapshots at t = steps, 3/4, 1/2, 1/4 steps."""
+    global example_image, example, dictionary
+    den = denoiser if denoiser is not None else __getattr__("denoiser")
+    S = size
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if example_image is None or example is None or dictionary is None:
+        g = torch.Generator().manual_seed(1234)
+        example_image = (torch.randint(0, 256, (1, S, S, 3), generator=g).float() / 128 - 1).to(dev)
+        example = torch.randn(1, 2, S, S, 3, generator=g).to(dev)
+        dictionary = torch.randn(S, S, 2 ** bits_per_pixel, 3, generator=g).to(dev)
+    out: Dict[str, object] = {}
+    # ---- :325-361
+    f = alpha_dash(float(test_step))
+    if ordinary_differential_equation:
+        f = alpha_dash(steps / 2) ** 0.5
+    noised = example_image * f ** 0.5 + example[0, :1] * (1 - f) ** 0.5
+    pred = den((noised, None))
+    if ordinary_differential_equation:
+        h, h1 = alpha_dash(steps / 2), alpha_dash(steps / 2 - 1)
+        denoised = (pred * (1 - h) ** 0.5 - noised * (1 - h1) ** 0.5) / (h1 ** 0.5 * (1 - h) ** 0.5 - h ** 0.5 * (1 - h1) ** 0.5)
+    elif predict_x:
+        denoised = pred
+    else:
+        p = pred if predict_scaled_epsilon else pred * (1 - f) ** 0.5
+        denoised = (noised - p) / f ** 0.5
+    loss_t = torch.zeros(1, device=dev)
+    ops.rmse(example_image, denoised, loss_t)
+    out["denoised"] = denoised * 0.5 + 0.5
+    # ---- :365-413 forward diffusion (inversion): x_theta = epsilon_theta = the example, t ascending
+    _, eps_theta = den.sample(example_image, example_image, list(range(1, steps + 1)))
+    # ---- :418-434
+    edits = torch.empty(4, S, S, 3, device=dev)
+    ops.latent_edits(eps_theta, dictionary, edits)
+    fake = torch.cat([example[0], edits], 0)   # [6,S,S,3]
+    # ---- :439-496 backward diffusion at batch 6, snapshots of x_theta
+    marks = {steps: "step_1", 3 * steps // 4: "step_0.75", 2 * steps // 4: "step_0.5", steps // 4: "step_0.25"}
+    x_theta, e_theta = fake, fake
+    sched = list(range(steps, 0, -1))
+    cuts = sorted({sched.index(t) + 1 for t in marks if t in sched} | {len(sched)})
+    start = 0
+    for cut in cuts:   # one captured graph per segment; a snapshot is taken right after the step it belongs to
+        x_theta, e_theta = den.sample(x_theta, e_theta, sched[start:cut])
+        t_done = sched[cut - 1]
+        if t_done in marks:
+            out[marks[t_done]] = x_theta * 0.5 + 0.5
+        start = cut
+    out["fake"] = x_theta * 0.5 + 0.5
+    out["example loss"] = float(loss_t)
+    return out
 
 
 _singletons: Dict[str, object] = {}

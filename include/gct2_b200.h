@@ -35,6 +35,13 @@ extern "C" {
  * before the programmatic dependency on the previous launch of `stream` resolves.  Without the flag every load waits. */
 #define GCT2_WEIGHTS_STABLE 1
 
+/* Objective switches of train.py:29-32 as understood by gct2_dense_mse / gct2_sample_update (`target_mode`). */
+#define GCT2_TARGET_X 0        /* predict_x = True (the reference's default)                          train.py:243-244 */
+#define GCT2_TARGET_EPSILON 1  /* predict_x = False: the network predicts the noise                  train.py:245-246 */
+#define GCT2_TARGET_SCALED 2   /* | predict_scaled_epsilon                                            train.py:247-248 */
+#define GCT2_TARGET_WEIGHTED 4 /* | prediction_weighting                                              train.py:250-252 */
+#define GCT2_TARGET_ODE 8      /* ordinary_differential_equation (takes precedence)                   train.py:238-242 */
+
 int gct2_abi_version(void);
 const char* gct2_last_error(void);
 /* Selects the device, resolves the driver entry points, raises the kernels' shared-memory limits.
@@ -164,10 +171,16 @@ int gct2_bias_grad_multi(int n, const uint16_t* const* dz, const int* ld, const 
  * element count) so data-parallel ranks produce partial means.  When backward != 0 also writes
  * du0 = (u0>0) * (dpred . wd^T) (bf16, stride lddu), dwd fp32 [Cu+3,3], dbd fp32 [3], dpred = 2(pred-x)*inv_n.
  * Cu is 64 or 128.  accumulate == 0: loss, dwd, dbd are overwritten; != 0: added into (the caller zeroed them).
- * loss_scale: NULL, or the device state of gct2_loss_scale_* (dpred is multiplied by loss_scale[0]; the loss is not). */
+ * loss_scale: NULL, or the device state of gct2_loss_scale_* (dpred is multiplied by loss_scale[0]; the loss is not).
+ * target_mode selects what the loss compares (train.py:238-252): 0 = predict_x (target = x; eps, t_int unused, may be
+ * NULL); otherwise the network predicts the noise -- GCT2_TARGET_EPSILON, optionally | GCT2_TARGET_SCALED (target
+ * eps*sqrt(1-abar(t))) | GCT2_TARGET_WEIGHTED (target and prediction both times sqrt(1-abar(t))) -- or
+ * GCT2_TARGET_ODE (target = the noised image of step t-1).  eps fp32 [pixels,3] and t_int int32 [images] are the draws
+ * of the noising step; pixels_per_image maps a pixel to its image. */
 int gct2_dense_mse(const uint16_t* u0, int ldu, const float* noised, const float* x, const float* wd,
                    const float* bd, float* pred, float* loss, uint16_t* du0, int lddu, float* dwd, float* dbd,
                    long long pixels, int Cu, float inv_n, int backward, int accumulate, const float* loss_scale,
+                   const float* eps, const int32_t* t_int, long long pixels_per_image, int target_mode, int steps,
                    void* stream);
 
 /* train.py:50-65,75 -- tf.keras.optimizers.Adam(WarmUp(base_lr, warmup_steps)), Keras formula (epsilon added to
@@ -214,9 +227,17 @@ int gct2_step_begin_u8(const uint8_t* img, const uint8_t* flip, float* x_out, in
  * Denoiser calls in one launch.  After the call at step t:  x_theta = pred;  eps_theta = (fake - sqrt(abar(t)) x_theta)
  * / sqrt(1 - abar(t));  then, if 1 <= t_next <= steps, the next call's input  fake = sqrt(abar(t_next)) x_theta +
  * sqrt(1 - abar(t_next)) eps_theta  (in place).  pred == NULL: only the mix, from the given x_theta / eps_theta (the
- * loop's first iteration).  All tensors fp32 with n elements. */
+ * loop's first iteration).  All tensors fp32 with n elements.  target_mode as for gct2_dense_mse: with GCT2_TARGET_EPSILON
+ * (| _SCALED) the prediction is the (scaled) noise and x_theta = (fake - scaled noise) / sqrt(abar(t)) (train.py:400-413);
+ * with GCT2_TARGET_ODE x_theta follows train.py:382-391 and eps_theta is left unchanged. */
 int gct2_sample_update(const float* pred, float* fake, float* x_theta, float* eps_theta, int t, int t_next, int steps,
-                       long long n, void* stream);
+                       long long n, int target_mode, void* stream);
+/* train.py:418-432 -- the latent edits between log_sample's two loops, one launch: from epsilon_theta fp32 [size,size,3]
+ * and dictionary fp32 [size,size,entries,3] writes out fp32 [4,size,size,3] = {epsilon_theta, pixelated (avg_pool2d 4 +
+ * nearest UpSampling2D 4), shifted (tf.roll by 1 along both axes), quantised (nearest dictionary entry per pixel)}. */
+int gct2_latent_edits(const float* eps_theta, const float* dictionary, float* out, int size, int entries, void* stream);
+/* train.py:357-361 -- log_sample's 'example loss': out[0] = sqrt(mean((a - b)^2)) over n fp32 elements. */
+int gct2_rmse(const float* a, const float* b, long long n, float* out, void* stream);
 /* fp32 -> bf16 (round to nearest even); builds the first shadow copy of the weights. */
 int gct2_cast_bf16(const float* src, uint16_t* dst, long long n, void* stream);
 

@@ -48,6 +48,12 @@ class Config:
     beta1: float = 0.9
     beta2: float = 0.999
     epsilon: float = 1e-7
+    # train.py:29-32: what the network predicts / what the loss compares (all at the reference's defaults)
+    predict_x: bool = True
+    predict_scaled_epsilon: bool = False
+    prediction_weighting: bool = False
+    ordinary_differential_equation: bool = False
+    test_step: int = 25   # train.py:95
 
     def down_filters(self, i: int) -> int:  # train.py:181
         return min(self.pixel_size * 2 ** i, self.max_size)
@@ -171,10 +177,62 @@ def sample_loop(weights, x_theta: torch.Tensor, eps_theta: torch.Tensor, t_value
         a = alpha_dash(float(t), cfg.steps)
         fake = a ** 0.5 * x_theta + (1 - a) ** 0.5 * eps_theta
         pred = denoiser_forward(weights, fake, cfg, emulate_bf16=emulate_bf16)
-        x_theta = pred
-        eps_theta = (fake - a ** 0.5 * x_theta) / (1 - a) ** 0.5
+        x_theta, eps_theta = sample_update(pred, fake, x_theta, eps_theta, t, cfg)
         trace.append(x_theta)
     return x_theta, eps_theta, trace
+
+
+def sample_update(pred, fake, x_theta, eps_theta, t, cfg: "Config"):
+    """What log_sample derives from one prediction (train.py:382-413 and :452-479, the same arithmetic in both loops)."""
+    a = alpha_dash(float(t), cfg.steps)
+    if cfg.ordinary_differential_equation:        # :382-391 / :452-461 -- epsilon_theta is left as it was
+        a1 = alpha_dash(float(t - 1), cfg.steps)
+        x_theta = (pred * (1 - a) ** 0.5 - fake * (1 - a1) ** 0.5) / (a1 ** 0.5 * (1 - a) ** 0.5 - a ** 0.5 * (1 - a1) ** 0.5)
+        return x_theta, eps_theta
+    if cfg.predict_x:                             # :394-398 / :464-468
+        x_theta = pred
+        return x_theta, (fake - a ** 0.5 * x_theta) / (1 - a) ** 0.5
+    if cfg.predict_scaled_epsilon:                # :401-405 / :471-473
+        eps_theta, scaled = pred / (1 - a) ** 0.5, pred
+    else:                                         # :406-410 / :474-476
+        eps_theta, scaled = pred, pred * (1 - a) ** 0.5
+    return (fake - scaled) / a ** 0.5, eps_theta  # :411-413 / :477-479
+
+
+def latent_edits(eps_theta: torch.Tensor, dictionary: torch.Tensor) -> torch.Tensor:
+    """train.py:418-432: the four latents log_sample decodes again -- epsilon_theta itself, pixelated (4x4 average pooling
+    + nearest up-sampling), shifted (tf.roll by one along both spatial axes) and quantised (per pixel the nearest of the
+    2**bits_per_pixel entries of `dictionary` [S,S,K,3] in squared distance).  eps_theta [1,S,S,3] -> [4,S,S,3]."""
+    e = eps_theta
+    pooled = F.avg_pool2d(_nchw(e), 4, 4)
+    pixelated = _nhwc(pooled.repeat_interleave(4, dim=2).repeat_interleave(4, dim=3))
+    shifted = torch.roll(torch.roll(e, 1, 1), 1, 2)
+    err = ((e[..., None, :] - dictionary[None]) ** 2).sum(-1)          # [1,S,S,K]
+    idx = err.argmin(-1)                                               # first minimum, like tf.argmin
+    quantised = torch.gather(dictionary[None], 3, idx[..., None, None].expand(-1, -1, -1, 1, 3)).squeeze(3)
+    return torch.cat([e, pixelated, shifted, quantised], 0)
+
+
+def example_denoise(weights, example_image, noise, cfg: "Config" = None, emulate_bf16=False):
+    """train.py:325-361: one denoising of the fixed example at test_step and the scalar log_sample reports as
+    'example loss': sqrt(mean((example - denoised)**2)).  example_image, noise: [1,S,S,3].  NOTE the reference's
+    quirk, restated as written: image_factor = alpha_dash(test_step) and the mix uses image_factor**0.5 and
+    (1 - image_factor)**0.5 (:325-332)."""
+    cfg = DEFAULT if cfg is None else cfg
+    f = alpha_dash(float(cfg.test_step), cfg.steps)
+    if cfg.ordinary_differential_equation:
+        f = alpha_dash(cfg.steps / 2, cfg.steps) ** 0.5          # :326-328
+    noised = example_image * f ** 0.5 + noise * (1 - f) ** 0.5
+    pred = denoiser_forward(weights, noised, cfg, emulate_bf16=emulate_bf16)
+    if cfg.ordinary_differential_equation:                        # :338-347
+        h, h1 = alpha_dash(cfg.steps / 2, cfg.steps), alpha_dash(cfg.steps / 2 - 1, cfg.steps)
+        denoised = (pred * (1 - h) ** 0.5 - noised * (1 - h1) ** 0.5) / (h1 ** 0.5 * (1 - h) ** 0.5 - h ** 0.5 * (1 - h1) ** 0.5)
+    elif cfg.predict_x:
+        denoised = pred
+    else:                                                         # :350-355
+        p = pred if cfg.predict_scaled_epsilon else pred * (1 - f) ** 0.5
+        denoised = (noised - p) / f ** 0.5
+    return denoised, float(((example_image - denoised) ** 2).mean() ** 0.5)
 
 
 # --------------------------------------------------------------------------------------------- layers
@@ -279,16 +337,36 @@ def noise_images(x, t_int, eps, cfg: Config = DEFAULT):
     return x * a ** 0.5 + eps * (1 - a) ** 0.5
 
 
+def loss_target(x, t_int, eps, pred, cfg: Config = DEFAULT):
+    """train.py:238-252: the regression target (and the re-weighted prediction) for the four objective switches."""
+    t = t_int.to(x.dtype)[:, None, None, None]
+    if cfg.ordinary_differential_equation:                     # :238-242 the noised image of step t-1
+        a1 = alpha_dash(t - 1, cfg.steps)
+        return x * a1 ** 0.5 + eps * (1 - a1) ** 0.5, pred
+    if cfg.predict_x:                                          # :243-244 (the reference's default)
+        return x, pred
+    target = eps                                               # :245-246
+    s = (1 - alpha_dash(t, cfg.steps)) ** 0.5
+    if cfg.predict_scaled_epsilon:                             # :247-248
+        target = target * s
+    if cfg.prediction_weighting:                               # :250-252
+        target = target * s
+        pred = pred * s
+    return target, pred
+
+
 def trainer_loss(weights, x, t_int, eps, cfg: Config = DEFAULT, taps=None, global_elems: Optional[int] = None,
                  emulate_bf16: bool = False):
-    """Trainer.call with predict_x=True (train.py:223-236,243-244,262-263,272) -> scalar mean squared error.
+    """Trainer.call (train.py:223-272) -> scalar mean squared error between the target selected by the objective
+    switches (train.py:238-252; default predict_x: the clean image) and the prediction.
 
     global_elems overrides the mean's denominator (data-parallel shards of one global batch)."""
     noised = noise_images(x, t_int, eps, cfg)
     if taps is not None:
         taps["noised"] = noised
     pred = denoiser_forward(weights, noised, cfg, taps, emulate_bf16)
-    sq = (x.to(torch.float32) - pred.to(torch.float32)) ** 2
+    target, pred = loss_target(x, t_int, eps, pred, cfg)
+    sq = (target.to(torch.float32) - pred.to(torch.float32)) ** 2
     if global_elems is None:
         return sq.mean()
     return sq.sum() / global_elems

@@ -45,7 +45,10 @@ def tol_emu_grad(cfg: O.Config, layer: str) -> float:
 
 
 def make_engine(cfg: O.Config, batch: int, seed: int = 0, use_graph: bool = False, **net_kw):
+    from gan_class_transfer2_b200 import ops
     from gan_class_transfer2_b200.engine import NetConfig, UNetEngine
+    net_kw.setdefault("target_mode", ops.target_mode(cfg.predict_x, cfg.predict_scaled_epsilon, cfg.prediction_weighting,
+                                                     cfg.ordinary_differential_equation))
     ncfg = NetConfig(size=cfg.size, pixel_size=cfg.pixel_size, max_size=cfg.max_size, octaves=cfg.octaves,
                      steps=cfg.steps, warm_up=cfg.warm_up, base_lr=cfg.base_lr, beta1=cfg.beta1, beta2=cfg.beta2,
                      epsilon=cfg.epsilon, **net_kw)

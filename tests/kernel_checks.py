@@ -311,6 +311,64 @@ def check_step_begin_u8(B=3, H=32, seed=15):
     return worst
 
 
+def check_sample_update_modes(B=2, H=16, seed=17, target=None):
+    """gct2_sample_update for the objective switches of train.py:29-32 against oracle.sample_update (train.py:382-413)."""
+    import dataclasses
+    ops = _ops()
+    cfg = dataclasses.replace(O.Config(size=H), **(target or {}))
+    mode = ops.target_mode(cfg.predict_x, cfg.predict_scaled_epsilon, cfg.prediction_weighting,
+                           cfg.ordinary_differential_equation)
+    g = torch.Generator().manual_seed(seed)
+    dev = _dev()
+    shape = (B, H, H, 3)
+    x0, e0, pred = _rand(shape, g), _rand(shape, g), _rand(shape, g)
+    t, tn = 37, 36
+    a, an = O.alpha_dash(float(t), cfg.steps), O.alpha_dash(float(tn), cfg.steps)
+    fake_ref = a ** 0.5 * x0 + (1 - a) ** 0.5 * e0
+    x_ref, e_ref = O.sample_update(pred, fake_ref, x0, e0, t, cfg)
+    fake = torch.zeros(shape, device=dev)
+    xt, et = x0.to(dev), e0.to(dev)
+    ops.sample_update(None, fake, xt, et, t, t, cfg.steps, mode)
+    ops.sample_update(pred.to(dev), fake, xt, et, t, tn, cfg.steps, mode)
+    torch.cuda.synchronize()
+    ms = [_metrics("x_theta", xt, x_ref, 5e-6), _metrics("eps_theta", et, e_ref, 5e-6),
+          _metrics("next fake", fake, an ** 0.5 * x_ref + (1 - an) ** 0.5 * e_ref, 5e-6)]
+    worst = dict(max(ms, key=lambda q: q["err"] / q["tol"]))
+    worst["name"] = f"sample_update mode {mode} (worst: {worst['name']})"
+    return worst
+
+
+def check_latent_edits(S=32, K=8, seed=18):
+    """gct2_latent_edits against oracle.latent_edits (train.py:418-432): the copies, the roll and the dictionary gather
+    must be exact, the 4x4 average within fp32 summation order."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(seed)
+    e = _rand((1, S, S, 3), g)
+    d = _rand((S, S, K, 3), g)
+    ref = O.latent_edits(e, d)
+    dev = _dev()
+    out = torch.full((4, S, S, 3), 9.0, device=dev)
+    ops.latent_edits(e.to(dev), d.to(dev), out)
+    torch.cuda.synchronize()
+    got = out.cpu()
+    m = _metrics(f"latent_edits S{S} K{K} pixelated", got[1], ref[1], 1e-6)
+    if not (torch.equal(got[0], ref[0]) and torch.equal(got[2], ref[2]) and torch.equal(got[3], ref[3])):
+        m["err"] = float("inf")
+        m["detail"] = "copy / roll / quantised planes differ"
+    return m
+
+
+def check_rmse(n=3 * 64 * 64, seed=19):
+    ops = _ops()
+    g = torch.Generator().manual_seed(seed)
+    a, b = _rand((n,), g), _rand((n,), g)
+    dev = _dev()
+    out = torch.zeros(1, device=dev)
+    ops.rmse(a.to(dev), b.to(dev), out)
+    torch.cuda.synchronize()
+    return _metrics(f"rmse n{n}", out, (((a - b) ** 2).mean() ** 0.5).reshape(1), 2e-6)
+
+
 def check_sample_update(B=2, H=16, seed=16):
     """gct2_sample_update against the loop arithmetic of train.py:369-372 / :394-397 (fp32 elementwise)."""
     ops = _ops()
@@ -413,17 +471,25 @@ def check_bias_grad_multi(seed=12):
     return worst
 
 
-def check_dense_mse(B=2, H=32, Cu=64, seed=10):
+def check_dense_mse(B=2, H=32, Cu=64, seed=10, target=None):
+    """target: None (predict_x) or the objective switches of train.py:29-32 as a dict for oracle.Config."""
+    import dataclasses
     ops = _ops()
     g = torch.Generator().manual_seed(seed)
     u0 = _bf(_rand((B, H, H, Cu), g).clamp_min(0))
     noised = _rand((B, H, H, 3), g)
     x = _rand((B, H, H, 3), g)
+    eps = _rand((B, H, H, 3), g)
+    t_int = torch.randint(1, 201, (B,), generator=g, dtype=torch.int32)
+    ocfg = dataclasses.replace(O.Config(size=H), **(target or {}))
+    mode = ops.target_mode(ocfg.predict_x, ocfg.predict_scaled_epsilon, ocfg.prediction_weighting,
+                           ocfg.ordinary_differential_equation)
     wd = _rand((Cu + 3, 3), g, 0.2).requires_grad_(True)
     bd = _rand((3,), g, 0.1).requires_grad_(True)
     u0r = u0.float().requires_grad_(True)
     pred = O.dense(torch.cat([u0r, noised], -1), wd, bd)
-    loss = ((x - pred) ** 2).mean()
+    tgt, wpred = O.loss_target(x, t_int, eps, pred, ocfg)
+    loss = ((tgt - wpred) ** 2).mean()
     loss.backward()
     du0_ref = u0r.grad * (u0.float() > 0)
     dev = _dev()
@@ -435,14 +501,15 @@ def check_dense_mse(B=2, H=32, Cu=64, seed=10):
     dwd = torch.full((Cu + 3, 3), 3.0, device=dev)
     dbd = torch.full((3,), 3.0, device=dev)
     ops.dense_mse(u0v, noised.to(dev), x.to(dev), wd.detach().to(dev), bd.detach().to(dev), lossg,
-                  1.0 / (B * H * H * 3), pred=predg, du0=du0, dwd=dwd, dbd=dbd)
+                  1.0 / (B * H * H * 3), pred=predg, du0=du0, dwd=dwd, dbd=dbd, eps=eps.to(dev), t_int=t_int.to(dev),
+                  mode=mode, steps=ocfg.steps)
     torch.cuda.synchronize()
     ms = [_metrics("dense pred", predg, pred, 2e-5), _metrics("mse loss", lossg, loss.reshape(1), 2e-5),
           _metrics("dense du0", du0, du0_ref, BF16_TOL), _metrics("dense dW", dwd, wd.grad, F32_TOL),
           _metrics("dense db", dbd, bd.grad, F32_TOL)]
     worst = max(ms, key=lambda m: m["err"] / m["tol"])
     worst = dict(worst)
-    worst["name"] = f"dense_mse B{B} H{H} (worst: {worst['name']})"
+    worst["name"] = f"dense_mse B{B} H{H} mode {mode} (worst: {worst['name']})"
     return worst
 
 
@@ -512,6 +579,20 @@ EW_CASES = [
     (check_dense_mse, dict(B=1, H=16, Cu=128)),
     (check_dense_mse, dict(B=3, H=5, Cu=64)),
     (check_adam, {}),
+    # the objective switches of train.py:29-32 (loss targets, train.py:238-252)
+    (check_dense_mse, dict(target=dict(predict_x=False))),
+    (check_dense_mse, dict(target=dict(predict_x=False, predict_scaled_epsilon=True))),
+    (check_dense_mse, dict(target=dict(predict_x=False, prediction_weighting=True))),
+    (check_dense_mse, dict(target=dict(predict_x=False, predict_scaled_epsilon=True, prediction_weighting=True), B=3, H=8)),
+    (check_dense_mse, dict(target=dict(ordinary_differential_equation=True))),
+    (check_sample_update_modes, dict(target=dict(predict_x=False))),
+    (check_sample_update_modes, dict(target=dict(predict_x=False, predict_scaled_epsilon=True))),
+    (check_sample_update_modes, dict(target=dict(ordinary_differential_equation=True))),
+    (check_sample_update_modes, {}),
+    # the rest of log_sample (train.py:325-361, 418-432)
+    (check_latent_edits, {}),
+    (check_latent_edits, dict(S=64, K=3)),
+    (check_rmse, {}),
 ]
 
 
