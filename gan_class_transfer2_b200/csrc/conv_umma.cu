@@ -151,9 +151,9 @@ void conv_set_debug(int key, int value) {
   }
 }
 
-template <int MODE, int BN, int PAIR = 0>
+template <int MODE, int BN, int PAIR = 0, int CS = 0>
 static int set_attr() {
-  cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<MODE, BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<MODE, BN, PAIR, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        227 * 1024);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(conv_umma_kernel<%d,%d,%d>): %s", MODE, BN, PAIR, cudaGetErrorString(e));
@@ -211,6 +211,8 @@ int conv_init(int device) {
   rc |= set_attr<MODE_W, 64>() | set_attr<MODE_W, 128>() | set_attr<MODE_W, 256>();
   rc |= set_attr<MODE_S, 128, 1>() | set_attr<MODE_S, 256, 1>() | set_attr<MODE_P, 128, 1>() | set_attr<MODE_P, 256, 1>();
   rc |= set_attr<MODE_W, 128, 1>() | set_attr<MODE_W, 256, 1>();
+  rc |= set_attr<MODE_S, 64, 0, 1>() | set_attr<MODE_S, 128, 0, 1>() | set_attr<MODE_S, 256, 0, 1>();
+  rc |= set_attr<MODE_P, 64, 0, 1>() | set_attr<MODE_P, 128, 0, 1>() | set_attr<MODE_P, 256, 0, 1>();
   if (rc) return 1;
   query_all_pairs(ds);
   if (cudaMalloc(&ds.cnt, (size_t)CNT_RING_INTS * sizeof(int)) != cudaSuccess ||
@@ -400,7 +402,7 @@ static void query_clusters(DeviceState& ds) {
     cfg.attrs = at;
     cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, conv_umma_kernel<MODE, BN, 0>, &cfg) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveClusters(&n, conv_umma_kernel<MODE, BN, 0, 1>, &cfg) != cudaSuccess) {
       cudaGetLastError();
       n = 0;
     }
@@ -520,10 +522,10 @@ static Choice choose(const DeviceState& ds, int mode, int mTiles, int phases, in
   return best;
 }
 
-template <int MODE, int BN, int PAIR = 0>
+template <int MODE, int BN, int PAIR = 0, int CS = 0>
 static cudaError_t launch_one(int grid, size_t smem, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b,
                               const ConvParams& p) {
-  const int clusterSize = PAIR ? 2 : (p.csplit ? p.splits : 1);
+  const int clusterSize = PAIR ? 2 : (CS ? p.splits : 1);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kConvThreads<BN>());
@@ -544,7 +546,7 @@ static cudaError_t launch_one(int grid, size_t smem, cudaStream_t st, const CUte
     at[cfg.numAttrs].val.programmaticStreamSerializationAllowed = 1;
     ++cfg.numAttrs;
   }
-  return cudaLaunchKernelEx(&cfg, conv_umma_kernel<MODE, BN, PAIR>, a, b, p);
+  return cudaLaunchKernelEx(&cfg, conv_umma_kernel<MODE, BN, PAIR, CS>, a, b, p);
 }
 
 template <int MODE>
@@ -553,6 +555,17 @@ static cudaError_t launch_bn(int BN, int grid, size_t smem, cudaStream_t st, con
   if (p.cm == 2) {
     if (BN < 128) return cudaErrorInvalidValue;
     return BN == 128 ? launch_one<MODE, 128, 1>(grid, smem, st, a, b, p) : launch_one<MODE, 256, 1>(grid, smem, st, a, b, p);
+  }
+  if (p.csplit) {
+    if constexpr (MODE == MODE_W) {
+      return cudaErrorInvalidValue;
+    } else {
+      switch (BN) {
+        case 64: return launch_one<MODE, 64, 0, 1>(grid, smem, st, a, b, p);
+        case 128: return launch_one<MODE, 128, 0, 1>(grid, smem, st, a, b, p);
+        default: return launch_one<MODE, 256, 0, 1>(grid, smem, st, a, b, p);
+      }
+    }
   }
   switch (BN) {
     case 64: return launch_one<MODE, 64>(grid, smem, st, a, b, p);

@@ -289,20 +289,18 @@ __device__ __forceinline__ void issue_chunk(const ConvParams& p, const CUtensorM
 //     each other whatever else runs on the GPU); partials are read from the peers' shared memory;
 //   L2 form (fused): every split of the tile has its own CTA and the host launched no more CTAs than can be resident
 //     at once; partials go through tile-major fp32 slabs in global memory and a counter rendezvous.
-// A separate (not inlined) function: its registers do not add to the pressure of the direct epilogues.
-#ifdef GCT2_INLINE_FINISH
+// (inlined: as a separate function it cost 11 us per step at batch 1 -- call overhead on the critical path of every
+// split-K launch)
 #define GCT2_FINISH_ATTR __forceinline__
-#else
-#define GCT2_FINISH_ATTR __noinline__
-#endif
 #ifdef GCT2_NO_F16
 #define GCT2_F16_OF(p) 0
 #else
 #define GCT2_F16_OF(p) ((p).f16)
 #endif
-template <int MODE, int BN>
-__device__ GCT2_FINISH_ATTR void splitk_finish_in_place(const ConvParams& p, const WorkItem& w, int tileId, bool csplit,
+template <int MODE, int BN, int CS>
+__device__ GCT2_FINISH_ATTR void splitk_finish_in_place(const ConvParams& p, const WorkItem& w, int tileId,
                                                     uint8_t* smem, uint64_t* red_full, int warp, int lane) {
+  constexpr bool csplit = CS != 0;
   constexpr int NE = kEpilogueWarps<BN>();
   const int f16 = GCT2_F16_OF(p);
       // ---- split-K finished in place: split s sums rows [s*R, (s+1)*R) of the tile over all partials in split
@@ -351,25 +349,29 @@ __device__ GCT2_FINISH_ATTR void splitk_finish_in_place(const ConvParams& p, con
           ox = 2 * ox + (w.ph & 1);
         }
         const long long opix = ((long long)b * p.Hout + oy) * p.Wout + ox;
-        // all partials of this vector are requested before the first is used (four loads in flight per batch): the
-        // sum is then bound by one remote-shared-memory / L2 round trip, not by `splits` of them; summation order
-        // stays split 0, 1, 2, ... (bit-reproducible)
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        const uint32_t off = part0 + (uint32_t)(rr * BN * 4) + (uint32_t)((((c4 >> 2) ^ (rr & 7))) << 4);
-        const float* sp = slab0 + (long long)rr * BN + c4;
-        for (int s0 = 0; s0 < p.splits; s0 += 4) {
-          float4 u[4];
+        float4 v;
+        if (csplit) {
+          // four remote loads in flight per batch: the sum is bound by one distributed-shared-memory round trip per
+          // batch, not per split; summation order stays split 0, 1, 2, ... (bit-reproducible)
+          v = make_float4(0.f, 0.f, 0.f, 0.f);
+          const uint32_t off = part0 + (uint32_t)(rr * BN * 4) + (uint32_t)((((c4 >> 2) ^ (rr & 7))) << 4);
+          for (int s0 = 0; s0 < p.splits; s0 += 4) {
+            float4 u[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (s0 + j < p.splits)
-              u[j] = csplit ? ld_dsmem_f4(map_to_rank(off, (uint32_t)(s0 + j)))
-                            : __ldcg(reinterpret_cast<const float4*>(sp + (long long)(s0 + j) * splitStride));
+            for (int j = 0; j < 4; ++j)
+              if (s0 + j < p.splits) u[j] = ld_dsmem_f4(map_to_rank(off, (uint32_t)(s0 + j)));
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (s0 + j < p.splits) {
+                v.x += u[j].x; v.y += u[j].y; v.z += u[j].z; v.w += u[j].w;
+              }
           }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (s0 + j < p.splits) {
-              v.x += u[j].x; v.y += u[j].y; v.z += u[j].z; v.w += u[j].w;
-            }
+        } else {
+          const float* sp = slab0 + (long long)rr * BN + c4;
+          v = __ldcg(reinterpret_cast<const float4*>(sp));
+          for (int sidx = 1; sidx < p.splits; ++sidx) {
+            const float4 u = __ldcg(reinterpret_cast<const float4*>(sp + sidx * splitStride));
+            v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
           }
         }
         const int nn = w.nt * BN + c4;
@@ -411,7 +413,10 @@ __device__ GCT2_FINISH_ATTR void splitk_finish_in_place(const ConvParams& p, con
 #endif
 // PAIR = 1: the cta_group::2 variant (a separate instantiation: a kernel that contains cta_group::2 instructions can
 // only be launched as a cluster of an even number of CTAs).
-template <int MODE, int BN, int PAIR = 0>
+// CS = 1: the variant whose split-K is finished inside a thread-block cluster (DSMEM).  A separate instantiation so that
+// the default kernels do not carry its code: with it compiled in, every launch of the step was slower (0.582 vs 0.564 ms
+// per step at batch 1 with the path unused -- the kernels grow past what the instruction cache holds at start-up).
+template <int MODE, int BN, int PAIR = 0, int CS = 0>
 __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1) conv_umma_kernel(const __grid_constant__ CUtensorMap mapA,
                                                         const __grid_constant__ CUtensorMap mapB,
                                                         const __grid_constant__ ConvParams p) {
@@ -440,7 +445,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
   const unsigned long long t_entry = (p.dbg != nullptr && threadIdx.x == 0) ? globaltimer_ns() : 0ull;
 #endif
 
-  const bool csplit = !pair && MODE != MODE_W && p.csplit != 0;
+  constexpr bool csplit = CS != 0 && !pair && MODE != MODE_W;
   const int rm = (pair || csplit) ? (int)cluster_ctarank() : 0;
   const int clusterId = pair ? (int)(blockIdx.x >> 1) : (csplit ? fd_div(p.fdSplits, (int)blockIdx.x) : (int)blockIdx.x);
   const int numClusters = pair ? (int)(gridDim.x >> 1) : (csplit ? fd_div(p.fdSplits, (int)gridDim.x) : (int)gridDim.x);
@@ -459,7 +464,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
       // pair: the leader's accumulator buffer is free once the epilogues of BOTH CTAs have drained theirs
       mbar_init(&tempty[i], (pair ? 2 : 1) * kEpilogueWarps<BN>());
     }
-    mbar_init(red_full, (uint32_t)(p.splits * kEpilogueWarps<BN>()));  // one arrival per epilogue warp of every peer
+    if (csplit) mbar_init(red_full, (uint32_t)(p.splits * kEpilogueWarps<BN>()));  // one arrival per epilogue warp of every peer
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -793,7 +798,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
         }
         tc_fence_before();
         __syncwarp();
-        if (p.fused || csplit) splitk_finish_in_place<MODE, BN>(p, w, tileId, csplit, smem, red_full, warp, lane);
+        if (p.fused || csplit) splitk_finish_in_place<MODE, BN, csplit ? 1 : 0>(p, w, tileId, smem, red_full, warp, lane);
 #ifdef GCT2_TIMELINE
         if (item == clusterId && warp == 4 && lane == 0) GCT2_STAMP(5);  // first epilogue (of warp 4) done
 #endif

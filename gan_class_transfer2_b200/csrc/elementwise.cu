@@ -855,6 +855,10 @@ __device__ __forceinline__ void adam_update(float4& wv, float4& mv, float4& vv, 
   gv.x *= gscale; gv.y *= gscale; gv.z *= gscale; gv.w *= gscale;
   adam_elem4(wv, mv, vv, gv, c1, c2, alpha, eps);
 }
+__device__ __forceinline__ float4 round_f16x4(float4 v) {
+  const uint32_t a = pack_f16x2(v.x, v.y), b = pack_f16x2(v.z, v.w);
+  return make_float4(f16_lo(a), f16_hi(a), f16_lo(b), f16_hi(b));
+}
 // G16: the gradient arrives as bf16 (data parallel: the reduce-scatter ran on a bf16 copy, half the NVLink bytes)
 template <bool G16>
 __device__ __forceinline__ float4 adam_load_grad(const void* __restrict__ g, long long i) {
@@ -887,6 +891,8 @@ __global__ void __launch_bounds__(ADAM_THREADS, 640 / ADAM_THREADS) adam_kernel(
     }
     gscale *= __ldg(ls + 3);
   }
+  // mixed precision: the reference's weight gradients are fp16 tensors (cast to fp32 before the unscaling): same rounding
+  const bool roundG = ls != nullptr && f16 != 0;
   if (iterations_inc != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *iterations_inc += 1;
   const float c1 = 1.f - b1, c2 = 1.f - b2;
   const long long T = (long long)gridDim.x * blockDim.x;
@@ -903,6 +909,7 @@ __global__ void __launch_bounds__(ADAM_THREADS, 640 / ADAM_THREADS) adam_kernel(
     }
 #pragma unroll
     for (int u = 0; u < ADAM_U; ++u) {
+      if (roundG) gv[u] = round_f16x4(gv[u]);
       adam_update(wv[u], mv[u], vv[u], gv[u], gscale, c1, c2, alpha, eps);
       m[i0 + u * T] = mv[u];
       v[i0 + u * T] = vv[u];
@@ -915,6 +922,7 @@ __global__ void __launch_bounds__(ADAM_THREADS, 640 / ADAM_THREADS) adam_kernel(
   }
   for (; i0 < nvec; i0 += T) {  // ragged tail
     float4 gv = adam_load_grad<G16>(g, i0), mv = m[i0], vv = v[i0], wv = w[i0];
+    if (roundG) gv = round_f16x4(gv);
     adam_update(wv, mv, vv, gv, gscale, c1, c2, alpha, eps);
     m[i0] = mv;
     v[i0] = vv;
@@ -1073,7 +1081,11 @@ int cast_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t st
 // `scale` before backward, the gradients divided by it before the update; a step with a non-finite gradient is skipped
 // and halves the scale, `growth` consecutive good steps double it.  State on the device: ls = {scale, good steps,
 // finite flag, 1/scale}.
-__global__ void __launch_bounds__(256) loss_scale_check_kernel(const float4* __restrict__ g, long long nvec, float* __restrict__ ls) {
+// `limit`: the largest finite value of the gradients' storage format in the reference -- under Keras' mixed_float16 policy
+// the weight gradients leave the fp16 convolutions as fp16 tensors, so a scaled gradient beyond 65504 IS an overflow there
+// (this implementation accumulates them in fp32 and applies the same limit to skip the same steps).
+__global__ void __launch_bounds__(256) loss_scale_check_kernel(const float4* __restrict__ g, long long nvec, float* __restrict__ ls,
+                                                               float limit) {
   TraceScope trace(11);
   pdl_launch_dependents();
   pdl_wait();
@@ -1081,9 +1093,8 @@ __global__ void __launch_bounds__(256) loss_scale_check_kernel(const float4* __r
   bool bad = false;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = __ldg(g + i);
-    // x - x is 0 for every finite x and NaN for inf / NaN
-    const float t = (v.x - v.x) + (v.y - v.y) + (v.z - v.z) + (v.w - v.w);
-    bad |= !(t == 0.f);
+    // |x| <= limit is false for NaN, inf and everything the 16-bit format cannot hold
+    bad |= !(fabsf(v.x) <= limit && fabsf(v.y) <= limit && fabsf(v.z) <= limit && fabsf(v.w) <= limit);
   }
   if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) ls[2] = 0.f;
   trace.end();
@@ -1118,7 +1129,8 @@ int loss_scale_check(const float* g, long long n, float* ls, cudaStream_t st) {
   long long blocks = (n / 4 + 255) / 256;
   if (blocks > g_ew_sms * 8) blocks = g_ew_sms * 8;
   if (blocks < 1) blocks = 1;
-  launch_k(loss_scale_check_kernel, dim3((int)blocks), dim3(256), 0, st, reinterpret_cast<const float4*>(g), n / 4, ls);
+  launch_k(loss_scale_check_kernel, dim3((int)blocks), dim3(256), 0, st, reinterpret_cast<const float4*>(g), n / 4, ls,
+           g_f16 ? 65504.0f : 3.3895314e38f /* bf16 max */);
   GCT2_CHECK_LAUNCH("loss_scale_check_kernel");
   return 0;
 }
