@@ -295,10 +295,12 @@ def main():
         saved = eng._save_state()
         graphs = eng._graph
         eng._graph, T.data_parallel.dry_run = None, True
-        compute_ms = timed(lambda: eng.run_step(draw=True), max(10, args.steps // 4))
-        eng.release_graphs()
-        eng._graph, T.data_parallel.dry_run = graphs, False
-        eng._restore_state(saved)
+        try:
+            compute_ms = timed(lambda: eng.run_step(draw=True), max(10, args.steps // 4))
+        finally:
+            eng.release_graphs()
+            eng._graph, T.data_parallel.dry_run = graphs, False
+            eng._restore_state(saved)
         # (b) the step's collectives alone, back to back: per bucket reduce-scatter (+ all-gather of the bf16 weights)
         from gan_class_transfer2_b200.engine import optimizer_shard
         dp = T.data_parallel

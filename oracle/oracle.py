@@ -394,7 +394,12 @@ def loss_and_grads(weights, x, t_int, eps, cfg: Config = DEFAULT, want_taps: boo
                 v.retain_grad()
     scale = 1.0 if loss_scale is None else float(loss_scale)
     (loss * scale).backward()
-    grads = {k: v.grad.detach() / scale for k, v in ws.items()}
+    if emulate_bf16 == "f16":
+        # under Keras' mixed_float16 policy every layer computes in fp16, so EVERY variable's gradient leaves its op as
+        # an fp16 tensor (cast to fp32 afterwards): values beyond 65504 are inf -- the overflow LossScaleOptimizer detects
+        grads = {k: v.grad.detach().to(torch.float16).to(torch.float32) / scale for k, v in ws.items()}
+    else:
+        grads = {k: v.grad.detach() / scale for k, v in ws.items()}
     out_taps: Dict[str, torch.Tensor] = {}
     if want_taps:
         for k, v in taps.items():

@@ -2,9 +2,9 @@
 
 Two comparisons per quantity:
   * "emu": against the oracle with bf16 rounding injected exactly where the CUDA path stores bf16: activations
-    <= 6e-3 rel-L2, gradients <= 2 % + 2 % per U-Net level (tol_emu_grad);
+    <= 6e-3 rel-L2, gradients <= 1.5 % + 1.9 % per U-Net level (tol_emu_grad);
   * "f32": against the oracle in the reference's own fp32 arithmetic (the tolerance north_star asks to be *stated*):
-    activations <= 1e-2 rel-L2, loss <= 1e-3 relative, gradients <= 6 % + 3 % per level (tol_f32_grad): bf16
+    activations <= 1e-2 rel-L2, loss <= 1e-3 relative, gradients <= 6 % + 2.2 % per level (tol_f32_grad; 10-25 % above the floor rounding alone sets): bf16
     rounding compounds through the ReLU masks of up to 12 layers; SURVEY.md Appendix D measured the same growth.
   Indexing / fusion bugs show up as O(1) errors; the per-kernel checks (tests/kernel_checks.py) are the tight ones.
 """
@@ -27,21 +27,30 @@ def level_of(layer: str) -> int:
     return int(layer.lstrip("downup").split("/")[0])
 
 
-def tol_f32_grad(cfg: O.Config, layer: str) -> float:
-    """Stated bf16-vs-fp32 tolerance (rel-L2) for the gradients of `layer`: 6 % at level 0 plus 3 % per U-Net level
-    (measured on B200: 4 % at level 0 growing to 15 % at level 5; SURVEY.md App. D saw the same in emulation).  The
-    Dense layer sits directly under the fp32 loss: 0.5 %."""
+def tol_f32_grad(cfg: O.Config, layer: str, mixed_precision: bool = False) -> float:
+    """Stated 16-bit-vs-fp32 tolerance (rel-L2) for the gradients of `layer` (weight gradients and activation
+    gradients): bf16 storage 6 % + 2.2 % per U-Net level, fp16 storage (the reference's mixed_float16 policy, three more
+    mantissa bits) 2.5 % + 1.2 % per level.  These sit 10-25 % above what rounding to the storage format ALONE does to
+    the gradients (tests/test_oracle.py::test_stated_gradient_tolerances_bracket_the_inherent_bf16_error; measured on
+    B200, default model, bf16: 4.1 / 7.2 / 9.0 / 10.6 / 13.3 / 14.8 % for the activation gradients of levels 0..5,
+    profiles/r2_parity_tables.jsonl) -- the CUDA path adds nothing measurable to that floor.  The Dense layer sits
+    directly under the fp32 loss: 0.5 %."""
     if layer.startswith("dense") or layer == "pred":
         return 5e-3
-    return 0.06 + 0.03 * level_of(layer)
+    if mixed_precision:
+        return 0.025 + 0.012 * level_of(layer)
+    return 0.06 + 0.022 * level_of(layer)
 
 
-def tol_emu_grad(cfg: O.Config, layer: str) -> float:
-    """Tolerance against the bf16-emulating oracle: the roundings sit at the same places but fp32 summation order
-    differs, which flips bf16 roundings and ReLU masks downstream: 2 % + 2 % per level (measured 1 % .. 8 %)."""
+def tol_emu_grad(cfg: O.Config, layer: str, mixed_precision: bool = False) -> float:
+    """Tolerance against the oracle that rounds to the storage format at the same points: what remains is fp32
+    summation order, which flips roundings and ReLU masks downstream: bf16 1.5 % + 1.9 % per level (measured 0.2 % ..
+    10 % at level 6), fp16 1 % + 1 % per level (measured up to 4.1 %)."""
     if layer.startswith("dense") or layer == "pred":
         return 1e-3
-    return 0.02 + 0.02 * level_of(layer)
+    if mixed_precision:
+        return 0.01 + 0.01 * level_of(layer)
+    return 0.015 + 0.019 * level_of(layer)
 
 
 def make_engine(cfg: O.Config, batch: int, seed: int = 0, use_graph: bool = False, **net_kw):
@@ -108,11 +117,11 @@ def check_step_parity(cfg: O.Config, batch: int, seed: int = 0, mixed_precision:
         if name == "loss":
             lim = {"emu": 1e-3, "f32": 1e-3}
         elif name.startswith(("act/ddown", "act/dup")):
-            lim = {"emu": tol_emu_grad(cfg, name[5:]), "f32": tol_f32_grad(cfg, name[5:])}
+            lim = {"emu": tol_emu_grad(cfg, name[5:], mixed_precision), "f32": tol_f32_grad(cfg, name[5:], mixed_precision)}
         elif name.startswith("act/"):
             lim = {"emu": 6e-3, "f32": 1e-2}
         else:
-            lim = {"emu": tol_emu_grad(cfg, name[5:]), "f32": tol_f32_grad(cfg, name[5:])}
+            lim = {"emu": tol_emu_grad(cfg, name[5:], mixed_precision), "f32": tol_f32_grad(cfg, name[5:], mixed_precision)}
         for flavour, err in errs.items():
             if not err <= lim[flavour]:
                 bad.append((name, flavour, err, lim[flavour]))

@@ -123,9 +123,10 @@ def test_loss_scale_kernels_follow_keras_dynamics():
         ops.loss_scale_check(gd, ls)
         ops.adam_apply(w, m, v, gd, wb, hyper, iterations_inc=it, loss_scale_state=ls)
         ops.loss_scale_update(ls, 2)
+        scale_used = ref.scale
         applied = ref.update(step not in poison)
-        if applied:
-            O.keras_adam_update(wo, mo, vo, grad, it_ref, cfg)
+        if applied:  # the scaled gradient is an fp16 tensor in the reference (cast to fp32, then unscaled)
+            O.keras_adam_update(wo, mo, vo, scaled.to(torch.float16).float() / scale_used, it_ref, cfg)
             it_ref += 1
         torch.cuda.synchronize()
         assert int(it) == it_ref, (step, int(it), it_ref)

@@ -27,7 +27,7 @@ def main():
         lim = {}
         if name.startswith("grad/") or name.startswith(("act/ddown", "act/dup")):
             key = name[5:]
-            lim = {"emu": E.tol_emu_grad(cfg, key), "f32": E.tol_f32_grad(cfg, key)}
+            lim = {"emu": E.tol_emu_grad(cfg, key, a.mixed_precision), "f32": E.tol_f32_grad(cfg, key, a.mixed_precision)}
         print(json.dumps({"config": a.config, "batch": a.batch, "mp": a.mixed_precision, "quantity": name,
                           **{k: round(v, 5) for k, v in errs.items()},
                           **{"tol_" + k: v for k, v in lim.items()}}), flush=True)
