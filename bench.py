@@ -214,7 +214,11 @@ def main():
         # the collectives run beside backward: cap their CTAs and keep the conv launches off those SMs (engine.DataParallel)
         os.environ.setdefault("NCCL_MAX_CTAS", "16")
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        opts = None
+        if os.environ.get("GCT2_NCCL_PRIORITY", "1") != "0":
+            # the collectives' CTAs go first whenever an SM frees up: they are few, and everything waits for them
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
         T.data_parallel = DataParallel(shard_optimizer=os.environ.get("GCT2_DP_SHARD", "1") != "0")
     _lib.init(local)
 
@@ -306,8 +310,22 @@ def main():
         dp = T.data_parallel
 
         def comm_only():
+            used_p2p = False
             for start, end, _ in eng._buckets:
                 cut = optimizer_shard(start, end, eng.small, dp.world, dp.rank) if dp.shard_optimizer else None
+                if cut is not None and eng._p2p is not None and (cut[3] - cut[2]) % 8 == 0 and cut[2] % 8 == 0:
+                    # the fused kernel IS the exchange: cross-rank barrier + gradient sum / Adam / weight broadcast
+                    lo, _, own, own_hi = cut
+                    pp = eng._p2p
+                    pp["hg"].barrier(channel=0)
+                    ops.adam_apply_p2p(eng.w[own:own_hi], eng.m[own:own_hi], eng.v[own:own_hi], pp["g_ptrs"], pp["w_ptrs"],
+                                       dp.world, own, eng.hyper, eng.cfg.beta1, eng.cfg.beta2, eng.cfg.epsilon, 1.0, True,
+                                       pp["g_mc"], pp["w_mc"])
+                    used_p2p = True
+                    if start >= eng.small:
+                        continue
+                    end = eng.small
+                    cut = None
                 if cut is not None:
                     lo, _, own, own_hi = cut
                     gsrc = eng.g16 if eng.g16 is not None else eng.g
@@ -317,6 +335,8 @@ def main():
                         continue
                     end = eng.small
                 dist.all_reduce(eng.g[start:end])
+            if used_p2p:
+                eng._p2p["hw"].barrier(channel=1)
 
         saved = eng._save_state()
         comm_ms = timed(comm_only, max(10, args.steps // 4))
@@ -327,6 +347,7 @@ def main():
                 "compute_only_ms": compute_ms, "replicas_bit_equal": replicas_equal,
                 "bytes_per_step": {"reduce_scatter": grad_bytes, "all_gather_bf16": 2 * eng.P},
                 "grad_dtype": dp.grad_dtype, "shard_optimizer": dp.shard_optimizer, "nccl_max_ctas": dp.nccl_ctas,
+                "transport": ("p2p+multimem" if eng._p2p["g_mc"] else "p2p") if eng._p2p is not None else "nccl",
                 "how": "compute_only = the captured step with its collectives left out; comm_alone = the step's "
                        "collectives back to back; exposed = step - compute_only; overlapped = comm_alone - exposed"}
         if not replicas_equal:

@@ -214,6 +214,13 @@ int gct2_adam_apply_g16(float* w, float* m, float* v, const uint16_t* g_bf16, ui
   return adam_apply(w, m, v, g_bf16, 1, MB(w_bf16), n, hyper, beta1, beta2, eps, grad_scale, iterations_inc, nullptr,
                     S(stream));
 }
+int gct2_adam_apply_p2p(float* w, float* m, float* v, const uint16_t* const* g_bf16_ptrs, uint16_t* const* w16_ptrs,
+                        const uint16_t* g_multicast, uint16_t* w16_multicast, int world, long long elem_offset, long long n,
+                        const float* hyper, float beta1, float beta2, float eps, float grad_scale, int write_all,
+                        void* stream) {
+  return adam_apply_p2p(w, m, v, g_bf16_ptrs, w16_ptrs, g_multicast, w16_multicast, world, elem_offset, n, hyper, beta1,
+                        beta2, eps, grad_scale, write_all, S(stream));
+}
 int gct2_step_begin(const float* x, float* noised, float* eps_out, int32_t* t_out, int B, int elems_per_image, int steps,
                     unsigned long long seed, const long long* iterations, float* hyper, float base_lr, int warmup_steps,
                     float beta1, float beta2, float* gsmall, long long nsmall, float* loss, void* stream) {

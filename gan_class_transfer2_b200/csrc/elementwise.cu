@@ -993,6 +993,129 @@ __global__ void __launch_bounds__(ADAM_WIDE_THREADS, 1) adam_wide_kernel(float4*
   trace.end();
 }
 
+// ------------------------------------------------------------------------------------ data parallel: gradient exchange +
+// Keras-Adam + weight broadcast in ONE kernel over NVLink peer memory (no NCCL kernel, no SM reserved for a collective)
+// Every rank owns 1/N of each gradient bucket.  For its slice the kernel
+//   1. reads the bf16 gradients of ALL ranks -- P2P loads from the peers' buffers (torch symmetric memory maps them into
+//      this process) or, with NVLS multicast, ONE multimem.ld_reduce per vector that the NVSwitch sums on the way --
+//      and accumulates them in fp32 in rank order;
+//   2. applies Keras-Adam to its fp32 masters (same adam_elem arithmetic as adam_kernel);
+//   3. writes the new bf16 weights straight into the shadow buffer of EVERY rank (P2P stores / one multimem.st).
+// That is reduce-scatter + sharded optimiser + all-gather without a collective library: the NVLink transfers are the
+// kernel's own loads and stores and overlap its arithmetic element by element.  The caller brackets it with two
+// cross-rank barriers (engine.py): all gradients of the bucket complete before, all weight writes landed after.
+struct P2PPtrs {
+  const uint16_t* g[8];   // per rank: base of its bf16 gradient buffer (symmetric: same layout everywhere)
+  uint16_t* w16[8];       // per rank: base of its bf16 / fp16 weight shadow
+  const uint16_t* g_mc;   // multicast address of the gradient buffer (nullptr: per-peer loads)
+  uint16_t* w16_mc;       // multicast address of the shadow buffer (nullptr: per-peer stores)
+  int world;
+};
+__device__ __forceinline__ uint4 ld_sys_u4(const void* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_sys_u4(void* p, uint4 v) {
+  asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// NVLS: the switch adds the bf16 pairs of all ranks (fp32 accumulation inside the switch) and returns the sums
+__device__ __forceinline__ uint4 multimem_ld_reduce_bf16x8(const void* mc) {
+  uint4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st_u4(void* mc, uint4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(__uint_as_float(v.x)),
+               "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+               : "memory");
+}
+__global__ void __launch_bounds__(256) adam_p2p_kernel(float4* __restrict__ w, float4* __restrict__ m, float4* __restrict__ v,
+                                                       const __grid_constant__ P2PPtrs pp, long long elemOff, long long n8,
+                                                       const float* __restrict__ hyper, float b1, float b2, float eps,
+                                                       float gscale, int f16, int writeAll) {
+  TraceScope trace(15);
+  pdl_launch_dependents();
+  pdl_wait();
+  trace.ready();
+  const float alpha = __ldg(hyper);
+  const float c1 = 1.f - b1, c2 = 1.f - b2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = elemOff + 8 * i;  // first of my eight elements in the flat buffers
+    float gs[8];
+    if (pp.g_mc != nullptr) {
+      const uint4 q = multimem_ld_reduce_bf16x8(pp.g_mc + e);
+      gs[0] = bf16_lo(q.x); gs[1] = bf16_hi(q.x); gs[2] = bf16_lo(q.y); gs[3] = bf16_hi(q.y);
+      gs[4] = bf16_lo(q.z); gs[5] = bf16_hi(q.z); gs[6] = bf16_lo(q.w); gs[7] = bf16_hi(q.w);
+    } else {
+      uint4 q[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (r < pp.world) q[r] = ld_sys_u4(pp.g[r] + e);  // all peers' vectors in flight together
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gs[j] = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (r < pp.world) {  // rank order: the sum does not depend on which rank computes it
+          gs[0] += bf16_lo(q[r].x); gs[1] += bf16_hi(q[r].x); gs[2] += bf16_lo(q[r].y); gs[3] += bf16_hi(q[r].y);
+          gs[4] += bf16_lo(q[r].z); gs[5] += bf16_hi(q[r].z); gs[6] += bf16_lo(q[r].w); gs[7] += bf16_hi(q[r].w);
+        }
+    }
+    float4 w0 = w[2 * i], w1 = w[2 * i + 1], m0 = m[2 * i], m1 = m[2 * i + 1], v0 = v[2 * i], v1 = v[2 * i + 1];
+    adam_update(w0, m0, v0, make_float4(gs[0], gs[1], gs[2], gs[3]), gscale, c1, c2, alpha, eps);
+    adam_update(w1, m1, v1, make_float4(gs[4], gs[5], gs[6], gs[7]), gscale, c1, c2, alpha, eps);
+    w[2 * i] = w0; w[2 * i + 1] = w1;
+    m[2 * i] = m0; m[2 * i + 1] = m1;
+    v[2 * i] = v0; v[2 * i + 1] = v1;
+    uint4 o;
+    o.x = pack_h2(w0.x, w0.y, f16); o.y = pack_h2(w0.z, w0.w, f16);
+    o.z = pack_h2(w1.x, w1.y, f16); o.w = pack_h2(w1.z, w1.w, f16);
+    if (!writeAll) {
+      // replicated range (every rank updates the same values itself): only my own shadow
+      *reinterpret_cast<uint4*>(pp.w16[0] + e) = o;
+    } else if (pp.w16_mc != nullptr) {
+      multimem_st_u4(pp.w16_mc + e, o);
+    } else {
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (r < pp.world) st_sys_u4(pp.w16[r] + e, o);
+    }
+  }
+  trace.end();
+}
+
+int adam_apply_p2p(float* w, float* m, float* v, const uint16_t* const* g_ptrs, uint16_t* const* w16_ptrs,
+                   const uint16_t* g_mc, uint16_t* w16_mc, int world, long long elem_offset, long long n,
+                   const float* hyper, float beta1, float beta2, float eps, float grad_scale, int write_all,
+                   cudaStream_t st) {
+  if (world < 1 || world > 8 || n % 8 || elem_offset % 8 ||
+      (reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) % 16) {
+    set_error("adam_apply_p2p: 1..8 ranks, ranges of whole 8-element vectors on 16-byte boundaries (world=%d n=%lld off=%lld)",
+              world, n, elem_offset);
+    return 1;
+  }
+  if (n == 0) return 0;
+  P2PPtrs pp;
+  for (int r = 0; r < 8; ++r) {
+    pp.g[r] = r < world ? g_ptrs[r] : nullptr;
+    pp.w16[r] = r < world ? w16_ptrs[r] : nullptr;
+  }
+  pp.g_mc = g_mc;
+  pp.w16_mc = w16_mc;
+  pp.world = world;
+  const long long n8 = n / 8;
+  long long blocks = (n8 + 255) / 256;
+  const long long cap = g_adam_blocks > 0 ? g_adam_blocks : (long long)g_ew_sms * 4;
+  if (blocks > cap) blocks = cap;
+  launch_k(adam_p2p_kernel, dim3((int)blocks), dim3(256), 0, st, reinterpret_cast<float4*>(w), reinterpret_cast<float4*>(m),
+           reinterpret_cast<float4*>(v), pp, elem_offset, n8, hyper, beta1, beta2, eps, grad_scale, g_f16, write_all);
+  GCT2_CHECK_LAUNCH("adam_p2p_kernel");
+  return 0;
+}
+
 int adam_prepare(long long* iterations, float* hyper, float base_lr, int warmup_steps, float beta1, float beta2,
                  cudaStream_t st) {
   launch_k(adam_prepare_kernel, dim3(1), dim3(1), 0, st, iterations, hyper, base_lr, warmup_steps, beta1, beta2);

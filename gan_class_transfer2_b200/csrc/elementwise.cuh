@@ -31,6 +31,10 @@ int adam_prepare(long long* iterations, float* hyper, float base_lr, int warmup_
 int adam_apply(float* w, float* m, float* v, const void* g, int g_is_bf16, __nv_bfloat16* w_bf16, long long n,
                const float* hyper, float beta1, float beta2, float eps, float grad_scale, long long* iterations_inc,
                const float* ls, cudaStream_t st);
+int adam_apply_p2p(float* w, float* m, float* v, const uint16_t* const* g_ptrs, uint16_t* const* w16_ptrs,
+                   const uint16_t* g_mc, uint16_t* w16_mc, int world, long long elem_offset, long long n,
+                   const float* hyper, float beta1, float beta2, float eps, float grad_scale, int write_all,
+                   cudaStream_t st);
 int loss_scale_check(const float* g, long long n, float* ls, cudaStream_t st);
 int loss_scale_update(float* ls, int growth_steps, cudaStream_t st);
 void elementwise_set_f16(int f16);

@@ -189,9 +189,11 @@ def shard_batch(global_batch: int, world: int, rank: int) -> Tuple[int, int]:
 class DataParallel:
     """Data-parallel context: the batch shards over ranks, gradient buckets are summed with NCCL."""
 
-    def __init__(self, group=None, bucket_bytes: int = 48 << 20, shard_optimizer: bool = True,
-                 grad_dtype: Optional[str] = None, nccl_ctas: Optional[int] = None):
+    def __init__(self, group=None, bucket_bytes: Optional[int] = None, shard_optimizer: bool = True,
+                 grad_dtype: Optional[str] = None, nccl_ctas: Optional[int] = None, transport: Optional[str] = None):
         import os
+        if bucket_bytes is None:
+            bucket_bytes = int(float(os.environ.get("GCT2_DP_BUCKET_MB", "48")) * (1 << 20))
         import torch.distributed as dist
         self.dist = dist
         self.group = group
@@ -207,6 +209,17 @@ class DataParallel:
         #: SMs left to the NCCL kernels that run beside backward (NCCL_MAX_CTAS caps them): the tensor-core launches of
         #: backward keep to the other SMs (gct2_set_sm_budget) instead of queueing a second wave behind a collective
         self.nccl_ctas = nccl_ctas if nccl_ctas is not None else int(os.environ.get("NCCL_MAX_CTAS", "0") or 0)
+        #: how the remaining SMs are shared during backward: "split" = the dgrad chain (main stream) and the wgrad chain
+        #: (side stream) get half each, so that together with the NCCL kernels nothing ever queues behind anything;
+        #: "shared" = each chain may use all of them (the chains then take turns and a collective waits for a gap)
+        self.sm_sharing = os.environ.get("GCT2_DP_SM", "shared")
+        #: how gradients and weights cross the GPUs: "p2p" = ONE kernel per bucket does the gradient sum, Keras-Adam and the
+        #: weight broadcast with its own loads and stores over NVLink peer memory (symmetric-memory buffers; with NVLS the
+        #: sum is a multimem.ld_reduce inside the switch and the broadcast a multimem.st) -- no NCCL kernel, no SMs set
+        #: aside for a collective; "nccl" = reduce-scatter / all-gather calls.  "p2p" falls back to "nccl" when the
+        #: buffers cannot be mapped.
+        self.transport = transport or os.environ.get("GCT2_DP_TRANSPORT", "p2p")
+        self.multicast = os.environ.get("GCT2_DP_MULTICAST", "1") != "0"
         #: measurement aid (bench.py's communication breakdown): when True the step is enqueued WITHOUT its collectives
         #: (wrong numbers, right compute time); read when a step is enqueued / captured
         self.dry_run = False
@@ -323,6 +336,10 @@ class UNetEngine:
         # bf16 copy of the gradient buckets for the data-parallel reduce-scatter (DataParallel.grad_dtype)
         self.g16 = (torch.zeros(self.P, dtype=torch.bfloat16, device=dev)
                     if (dp is not None and dp.world > 1 and dp.shard_optimizer and dp.grad_dtype == "bf16") else None)
+        self._p2p = None
+        if (dp is not None and dp.world > 1 and dp.shard_optimizer and dp.transport == "p2p" and share_params_with is None
+                and dp.world <= 8):
+            self._p2p = self._map_peer_buffers()
 
         # ---- activations and their gradients
         bf = dict(dtype=self.half, device=dev)
@@ -355,6 +372,34 @@ class UNetEngine:
         layers = [f"down{i}" for i in range(n)] + [f"up{i}" for i in range(n)]
         self._bias_plan = ops.BiasGradPlan([self.gdown_out(i) for i in range(n)] + [self.gup_out(i) for i in range(n)],
                                            [self.view(self.g, f"{l}/bias") for l in layers])
+
+    def _map_peer_buffers(self):
+        """Re-homes the bf16 gradient copy and the 16-bit weight shadow in symmetric memory (every rank's buffer mapped
+        into every process, plus NVLS multicast addresses where the fabric offers them).  Returns None -- and the step
+        falls back to NCCL -- when that is not possible."""
+        dp = self.dp
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            group = dp.group if dp.group is not None else dp.dist.group.WORLD
+            g16 = symm_mem.empty(self.P, dtype=torch.bfloat16, device=self.device)
+            w16 = symm_mem.empty(self.P, dtype=self.half, device=self.device)
+            hg = symm_mem.rendezvous(g16, group)
+            hw = symm_mem.rendezvous(w16, group)
+            g16.zero_()
+            w16.copy_(self.w16)
+            g_mc = int(getattr(hg, "multicast_ptr", 0) or 0) if dp.multicast else 0
+            w_mc = int(getattr(hw, "multicast_ptr", 0) or 0) if dp.multicast else 0
+            if not (g_mc and w_mc):
+                g_mc = w_mc = 0
+            self.g16, self.w16 = g16, w16
+            torch.cuda.synchronize(self.device)
+            hw.barrier(channel=0)
+            return dict(hg=hg, hw=hw, g_ptrs=[int(p) for p in hg.buffer_ptrs], w_ptrs=[int(p) for p in hw.buffer_ptrs],
+                        g_mc=g_mc, w_mc=w_mc)
+        except Exception as exc:  # noqa: BLE001 -- any failure here means "no peer mapping": use the collectives
+            import warnings
+            warnings.warn(f"gct2: peer-memory transport unavailable ({type(exc).__name__}: {exc}); using NCCL collectives")
+            return None
 
     # ------------------------------------------------------------------------------------------ parameter access
     def view(self, buf: torch.Tensor, name: str) -> torch.Tensor:
@@ -469,9 +514,17 @@ class UNetEngine:
         # [wide buckets left, conv SM budget active]
         side = [self.adam_wide_buckets if (apply_adam and dp is None and sa is not main and 0 < self.adam_sms < num_sms)
                 else 0, False]
-        if dp is not None and 0 < dp.nccl_ctas < num_sms:
+        chain_caps = False
+        p2p_used = [False]
+        if dp is not None and 0 < dp.nccl_ctas < num_sms and self._p2p is None:
             ops.set_sm_budget(num_sms - dp.nccl_ctas)  # the collectives of backward keep their SMs
             side[1] = True
+            if dp.sm_sharing == "split" and sw is not main:
+                half = (num_sms - dp.nccl_ctas) // 2
+                lib_ = _lib.load()
+                lib_.gct2_debug_set(9, half)   # wgrad launches (side stream)
+                lib_.gct2_debug_set(10, half)  # dgrad launches (main stream)
+                chain_caps = True
 
         def on_side(fn):
             if sw is main:
@@ -495,6 +548,36 @@ class UNetEngine:
                         chunk = own_hi - own
                         if sw is not main and trigger == "down0/kernel":
                             sw.wait_stream(main)
+                        if self._p2p is not None and chunk % 8 == 0 and own % 8 == 0:
+                            # fused: cast -> barrier -> ONE kernel (gradient sum over NVLink, Keras-Adam on my slice, weight
+                            # broadcast into every rank's shadow); see gct2_adam_apply_p2p
+                            pp = self._p2p
+                            with torch.cuda.stream(sw):
+                                ops.cast_bf16(self.g[lo:end], self.g16[lo:end])
+                            if sa is not main:
+                                sa.wait_stream(main)   # ... including the dgrad that still reads this bucket's weights
+                                if sw is not main:
+                                    sa.wait_stream(sw)
+                            elif sw is not main:
+                                main.wait_stream(sw)
+                            with torch.cuda.stream(sa):
+                                if dp.dry_run:
+                                    ops.adam_apply(self.w[own:own + chunk], self.m[own:own + chunk], self.v[own:own + chunk],
+                                                   self.g16[own:own + chunk], self.w16[own:own + chunk], self.hyper,
+                                                   cfg.beta1, cfg.beta2, cfg.epsilon, 1.0)
+                                else:
+                                    pp["hg"].barrier(channel=0)   # every rank's gradients of this bucket are in place
+                                    ops.adam_apply_p2p(self.w[own:own + chunk], self.m[own:own + chunk],
+                                                       self.v[own:own + chunk], pp["g_ptrs"], pp["w_ptrs"], dp.world, own,
+                                                       self.hyper, cfg.beta1, cfg.beta2, cfg.epsilon, 1.0, True,
+                                                       pp["g_mc"], pp["w_mc"])
+                            self._sharded_ranges.add((lo, end))
+                            p2p_used[0] = True
+                            if start >= self.small:
+                                continue
+                            end = self.small  # the head region below stays replicated
+                            cut = None
+                    if cut is not None:
                         gsrc = self.g
                         with torch.cuda.stream(sw):
                             if self.g16 is not None:
@@ -578,8 +661,15 @@ class UNetEngine:
             main.wait_stream(sa)
         for work in pending:
             work.wait()
+        if p2p_used[0] and not dp.dry_run:
+            # every rank has finished its fused kernels: all weight writes into my shadow have landed, and nobody still
+            # reads my gradient copy (the next step may overwrite it)
+            self._p2p["hw"].barrier(channel=1)
         if side[1]:
             ops.set_sm_budget(0)
+        if chain_caps:
+            _lib.load().gct2_debug_set(9, 0)
+            _lib.load().gct2_debug_set(10, 0)
         if dp:
             coll.all_reduce(self.loss).wait()
 

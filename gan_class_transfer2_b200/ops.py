@@ -385,3 +385,18 @@ def rmse(a, b, out):
     lib = _lib_for(a)
     check(lib.gct2_rmse(ptr(a.contiguous()), ptr(b.contiguous()), a.numel(), ptr(out), current_stream()))
     return out
+
+
+@_timed
+def adam_apply_p2p(w, m, v, g_ptrs, w16_ptrs, world: int, elem_offset: int, hyper, beta1: float = 0.9, beta2: float = 0.999,
+                   eps: float = 1e-7, grad_scale: float = 1.0, write_all: bool = True, g_mc: int = 0, w16_mc: int = 0):
+    """Data parallel, fused: gradient exchange + Keras-Adam + weight broadcast of this rank's slice over NVLink peer memory
+    (gct2_adam_apply_p2p).  w, m, v: this rank's fp32 masters of the slice; g_ptrs / w16_ptrs: per-rank BASE device
+    pointers (ints) of the bf16 gradient buffers and the 16-bit weight shadows; elem_offset: where the slice starts in
+    them; g_mc / w16_mc: NVLS multicast addresses or 0."""
+    import ctypes
+    lib = _lib_for(w)
+    ga = (ctypes.c_void_p * world)(*g_ptrs[:world])
+    wa = (ctypes.c_void_p * world)(*w16_ptrs[:world])
+    check(lib.gct2_adam_apply_p2p(ptr(w), ptr(m), ptr(v), ga, wa, g_mc or None, w16_mc or None, world, int(elem_offset),
+                                  w.numel(), ptr(hyper), beta1, beta2, eps, grad_scale, int(write_all), current_stream()))

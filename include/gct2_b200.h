@@ -205,6 +205,20 @@ int gct2_adam_apply(float* w, float* m, float* v, const float* g, uint16_t* w_bf
 int gct2_adam_apply_g16(float* w, float* m, float* v, const uint16_t* g_bf16, uint16_t* w_bf16, long long n,
                         const float* hyper, float beta1, float beta2, float eps, float grad_scale,
                         long long* iterations_inc, void* stream);
+/* Data parallel, the fused form: gradient exchange + Keras-Adam + weight broadcast of one rank's slice of a
+ * gradient bucket in ONE kernel over NVLink peer memory -- no collective library on the path.  g_bf16_ptrs / w16_ptrs are
+ * HOST arrays of `world` device pointers: the BASE of every rank's bf16 gradient buffer and of every rank's 16-bit weight
+ * shadow, all mapped into this process (CUDA IPC / a symmetric-memory allocator; index = rank, this rank included).  The slice
+ * is elements [elem_offset, elem_offset + n) of those flat buffers; w, m, v point at THIS rank's fp32 masters of the
+ * slice.  For every element the kernel sums the bf16 gradients of all ranks in fp32 (rank order), applies the update,
+ * and writes the new 16-bit weight into every rank's shadow (write_all != 0) or only into w16_ptrs[0] (write_all == 0:
+ * a range every rank updates redundantly).  g_multicast / w16_multicast: NULL, or the NVLS multicast addresses of the two
+ * buffers -- then the sum is one multimem.ld_reduce (added inside the NVSwitch) and the broadcast one multimem.st.
+ * The caller orders it across ranks: all ranks' gradients of the slice complete before, all writes landed after. */
+int gct2_adam_apply_p2p(float* w, float* m, float* v, const uint16_t* const* g_bf16_ptrs, uint16_t* const* w16_ptrs,
+                        const uint16_t* g_multicast, uint16_t* w16_multicast, int world, long long elem_offset, long long n,
+                        const float* hyper, float beta1, float beta2, float eps, float grad_scale, int write_all,
+                        void* stream);
 /* Everything a step needs before its first convolution, in one launch (train.py:224-234 plus optimiser bookkeeping):
  * draws t_int ~ U{1..steps} per image and eps ~ N(0,1) per element on the device (Philox4x32-10 keyed by `seed`, offset by
  * *iterations so every step differs; the reference draws with TF's unseeded generators), writes

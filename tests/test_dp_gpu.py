@@ -17,7 +17,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out, use_graph, grad_dtype):
+def _worker(rank, world, port, out, use_graph, grad_dtype, transport):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -29,7 +29,7 @@ def _worker(rank, world, port, out, use_graph, grad_dtype):
         cfg = O.TINY
         ncfg = NetConfig(size=cfg.size, pixel_size=cfg.pixel_size, max_size=cfg.max_size, octaves=cfg.octaves)
         per = 2
-        eng = UNetEngine(ncfg, per, dp=DataParallel(bucket_bytes=1 << 20, grad_dtype=grad_dtype, nccl_ctas=16),
+        eng = UNetEngine(ncfg, per, dp=DataParallel(bucket_bytes=1 << 20, grad_dtype=grad_dtype, nccl_ctas=16, transport=transport),
                          use_graph=use_graph)
         eng.load_weights(O.glorot_init(cfg, 0))
         x, t, e = O.synthetic_batch(cfg, per * world, 1)
@@ -52,6 +52,8 @@ def _worker(rank, world, port, out, use_graph, grad_dtype):
         dist.all_gather(gathered, w)
         if rank == 0:
             torch.save({"loss": float(loss), "grads": grads, "losses": losses, "stale_raises": stale_raises,
+                        "transport": "p2p" if eng._p2p is not None else "nccl",
+                        "multicast": bool(eng._p2p and eng._p2p["g_mc"]),
                         "replicas_equal": all(torch.equal(gathered[0], g) for g in gathered),
                         "weights": {k: v.cpu() for k, v in eng.weights().items()}}, out)
     finally:
@@ -60,16 +62,19 @@ def _worker(rank, world, port, out, use_graph, grad_dtype):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("grad_dtype", ["bf16", "fp32"])
+@pytest.mark.parametrize("grad_dtype,transport", [("bf16", "p2p"), ("bf16", "nccl"), ("fp32", "nccl")])
 @pytest.mark.parametrize("use_graph", [False, True], ids=["eager", "cuda_graph"])
-def test_two_gpu_data_parallel_step_matches_oracle(tmp_path, use_graph, grad_dtype):
+def test_two_gpu_data_parallel_step_matches_oracle(tmp_path, use_graph, grad_dtype, transport):
+    """transport "p2p": gradient sum + Keras-Adam + weight broadcast fused in one kernel over NVLink peer memory
+    (gct2_adam_apply_p2p, multimem when the fabric offers it); "nccl": reduce-scatter / all-gather collectives."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
     import torch.multiprocessing as mp
     from tests import engine_checks as E
     out = str(tmp_path / "dp.pt")
-    mp.spawn(_worker, args=(2, _free_port(), out, use_graph, grad_dtype), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), out, use_graph, grad_dtype, transport), nprocs=2, join=True)
     got = torch.load(out)
+    print("transport used:", got["transport"], "multicast:", got["multicast"])
     cfg = O.TINY
     weights = O.glorot_init(cfg, 0)
     x, t, e = O.synthetic_batch(cfg, 4, 1)
