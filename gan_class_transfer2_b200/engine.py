@@ -219,7 +219,12 @@ class DataParallel:
         #: aside for a collective; "nccl" = reduce-scatter / all-gather calls.  "p2p" falls back to "nccl" when the
         #: buffers cannot be mapped.
         self.transport = transport or os.environ.get("GCT2_DP_TRANSPORT", "p2p")
-        self.multicast = os.environ.get("GCT2_DP_MULTICAST", "1") != "0"
+        #: NVLS multicast addresses (multimem.ld_reduce / multimem.st) for the fused kernel's sum and broadcast.  Measured on
+        #: 2 / 4 / 8 B200s at 1 image per GPU (profiles/r2_scaling_transports.jsonl): 2964 / 6238 / 12604 images/s with
+        #: them, 3090 / 6215 / 11521 with plain peer loads and stores -- the switch-side reduction pays from four GPUs on,
+        #: between two GPUs a peer load is cheaper than a round trip through the switch's reduction unit
+        mc = os.environ.get("GCT2_DP_MULTICAST", "")
+        self.multicast = (self.world > 2) if mc == "" else (mc != "0")
         #: measurement aid (bench.py's communication breakdown): when True the step is enqueued WITHOUT its collectives
         #: (wrong numbers, right compute time); read when a step is enqueued / captured
         self.dry_run = False
