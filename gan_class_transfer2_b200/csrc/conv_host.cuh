@@ -8,7 +8,7 @@
 namespace gct2 {
 
 struct ConvArgs {
-  int mode;                      // MODE_S / MODE_P / MODE_W
+  int mode;                      // MODE_S / MODE_P / MODE_W / MODE_CF / MODE_CD / MODE_CW
   int B, Hlo, Wlo;               // lo-res spatial extent; the hi-res side is (2*Hlo, 2*Wlo)
   const __nv_bfloat16* hi;       // hi-res operand (S: A gather; W: G), base already offset to its first channel
   int ldHi, Chi;                 // pixel stride (elements) and number of channels used
@@ -29,6 +29,8 @@ struct ConvArgs {
                                  // when this one starts, so its boxes may be fetched before griddepcontrol.wait
   // W
   float* dw;                     // fp32 [16][Chi][Clo]
+  int ks;                        // stride-1 modes (MODE_CF / MODE_CD / MODE_CW): kernel side, 3 or 1; the single-resolution
+                                 // activation operand goes in `lo` (CF: x, CD: dy, CW: dy) and CW's gathered x in `hi`
   int f16;                       // 16-bit storage format of every bf16-typed pointer above: 0 = bf16, 1 = fp16
   // tuning overrides (0 = heuristic)
   int forceBN, forceSplits;

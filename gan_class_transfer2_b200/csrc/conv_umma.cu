@@ -213,6 +213,9 @@ int conv_init(int device) {
   rc |= set_attr<MODE_W, 128, 1>() | set_attr<MODE_W, 256, 1>();
   rc |= set_attr<MODE_S, 64, 0, 1>() | set_attr<MODE_S, 128, 0, 1>() | set_attr<MODE_S, 256, 0, 1>();
   rc |= set_attr<MODE_P, 64, 0, 1>() | set_attr<MODE_P, 128, 0, 1>() | set_attr<MODE_P, 256, 0, 1>();
+  rc |= set_attr<MODE_CF, 64>() | set_attr<MODE_CF, 128>() | set_attr<MODE_CF, 256>();
+  rc |= set_attr<MODE_CD, 64>() | set_attr<MODE_CD, 128>() | set_attr<MODE_CD, 256>();
+  rc |= set_attr<MODE_CW, 64>() | set_attr<MODE_CW, 128>() | set_attr<MODE_CW, 256>();
   if (rc) return 1;
   query_all_pairs(ds);
   if (cudaMalloc(&ds.cnt, (size_t)CNT_RING_INTS * sizeof(int)) != cudaSuccess ||
@@ -261,9 +264,9 @@ static int map_lo4(CUtensorMap* m, const __nv_bfloat16* p, int ld, int C, int B,
   cuuint32_t box[4] = {64, (cuuint32_t)Wt, (cuuint32_t)Ht, (cuuint32_t)Nb};
   return encode(m, p, 4, dims, st, box);
 }
-// kernel [16][R][Cc] viewed as (Cc, R, 16).
-static int map_w3(CUtensorMap* m, const __nv_bfloat16* p, int R, int Cc, int boxRows) {
-  cuuint64_t dims[3] = {(cuuint64_t)Cc, (cuuint64_t)R, 16};
+// kernel [taps][R][Cc] viewed as (Cc, R, taps).
+static int map_w3(CUtensorMap* m, const __nv_bfloat16* p, int R, int Cc, int boxRows, int taps = 16) {
+  cuuint64_t dims[3] = {(cuuint64_t)Cc, (cuuint64_t)R, (cuuint64_t)taps};
   cuuint64_t st[2] = {(cuuint64_t)Cc * 2, (cuuint64_t)R * Cc * 2};
   cuuint32_t box[3] = {64, (cuuint32_t)boxRows, 1};
   return encode(m, p, 3, dims, st, box);
@@ -436,7 +439,8 @@ static int cta_budget(const DeviceState& ds, int mode, bool dgradEpi) {
 //     extra launch (finishing kernel) -- with cheap k-steps it pays only when a layer has very few tiles;
 //   * epilogues scale with the tile's real rows: deep layers at batch 1 fill 16-64 of a tile's 128 rows.
 static Choice choose(const DeviceState& ds, int mode, int mTiles, int phases, int N, int kTotal, long long outElems,
-                     bool dgradEpi, int forceBN, int forceSplits, size_t slabBytes, size_t wsBytes) {
+                     bool dgradEpi, int forceBN, int forceSplits, size_t slabBytes, size_t wsBytes, int wTaps = 16,
+                     bool allowCluster = true) {
   Choice best{0, 1};
   double bestCost = 1e30;
   const int bns[3] = {256, 128, 64};
@@ -454,7 +458,7 @@ static Choice choose(const DeviceState& ds, int mode, int mTiles, int phases, in
       const size_t tileSlab = isW ? 0 : (size_t)mTiles * phases * 128 * N * sizeof(float);
       if (splits > 1 && (slabBytes > tileSlab ? slabBytes : tileSlab) * splits > wsBytes) break;
       const int kIters = kTotal / splits;
-      const long long items = (long long)mTiles * phases * (isW ? 16 : 1) * nTiles * splits;
+      const long long items = (long long)mTiles * phases * (isW ? wTaps : 1) * nTiles * splits;
       const long long active = items < maxCtas ? items : maxCtas;
       const long long waves = (items + active - 1) / active;
       // one 64-wide k-chunk: issue-bound at small grids.  Selection constants: 290 cycles with two chunks per ring slot
@@ -482,7 +486,7 @@ static Choice choose(const DeviceState& ds, int mode, int mTiles, int phases, in
         // every peer through DSMEM; no global traffic, no residency requirement beyond the cluster itself
         int lg = 0;
         while ((1 << lg) < splits) ++lg;
-        const int clusters = (splits <= 8 && g_csplit != 1 && g_fuse_finish) ? ds.max_clusters[mode][bn_index(BN)][lg] : 0;
+        const int clusters = (allowCluster && splits <= 8 && g_csplit != 1 && g_fuse_finish) ? ds.max_clusters[mode][bn_index(BN)][lg] : 0;
         if (clusters > 0) {
           const double epiC = 2500.0 + 20.0 * BN;
           const bool fits = g_sm_budget == 0 || items <= maxCtas;
@@ -553,11 +557,15 @@ template <int MODE>
 static cudaError_t launch_bn(int BN, int grid, size_t smem, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b,
                              const ConvParams& p) {
   if (p.cm == 2) {
-    if (BN < 128) return cudaErrorInvalidValue;
-    return BN == 128 ? launch_one<MODE, 128, 1>(grid, smem, st, a, b, p) : launch_one<MODE, 256, 1>(grid, smem, st, a, b, p);
+    if constexpr (mode_is_s1(MODE)) {
+      return cudaErrorInvalidValue;  // the stride-1 maps have no cta_group::2 instantiations
+    } else {
+      if (BN < 128) return cudaErrorInvalidValue;
+      return BN == 128 ? launch_one<MODE, 128, 1>(grid, smem, st, a, b, p) : launch_one<MODE, 256, 1>(grid, smem, st, a, b, p);
+    }
   }
   if (p.csplit) {
-    if constexpr (MODE == MODE_W) {
+    if constexpr (mode_is_w(MODE) || mode_is_s1(MODE)) {
       return cudaErrorInvalidValue;
     } else {
       switch (BN) {
@@ -601,7 +609,14 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
   p.mnSbo = g_mn_sbo;
   p.f16 = a.f16 ? 1 : 0;
   t_map_f16 = p.f16;
-  const int rows = a.mode == MODE_W ? 64 : 128;
+  const bool s1 = mode_is_s1(a.mode);
+  if (s1 && a.ks != 1 && a.ks != 3) {
+    set_error("stride-1 conv: kernel side must be 1 or 3 (got %d)", a.ks);
+    return 1;
+  }
+  const int s1Taps = s1 ? a.ks * a.ks : 0;
+  p.ks = a.ks;
+  const int rows = mode_is_w(a.mode) ? 64 : 128;
   pixel_tile(rows, a.Hlo, a.Wlo, &p.Wt, &p.Ht, &p.Nb);
   if (a.Wlo % p.Wt || a.Hlo % p.Ht || p.Wt * p.Ht * p.Nb != rows) {
     set_error("unsupported spatial extent %dx%d (tile %dx%dx%d)", a.Hlo, a.Wlo, p.Nb, p.Ht, p.Wt);
@@ -615,22 +630,27 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
   int BN = 0;
   p.cm = 1;
 
-  if (a.mode == MODE_S || a.mode == MODE_P) {
+  if (!mode_is_w(a.mode)) {
+    // weight-side roles: S and CF contract over the kernel's rows (HWIO: R = Cin) and produce its columns; P and CD the
+    // other way round
+    const bool rowsAreK = a.mode == MODE_S || a.mode == MODE_CF;
     const int Ck = a.mode == MODE_S ? a.Chi : a.Clo;
-    const int N = a.mode == MODE_S ? a.Cc : a.R;
-    const int wk = a.mode == MODE_S ? a.R : a.Cc;
+    const int N = rowsAreK ? a.Cc : a.R;
+    const int wk = rowsAreK ? a.R : a.Cc;
     if (Ck % 64 || N % 64 || wk != Ck) {
       set_error("conv: channel counts must be multiples of 64 and match the kernel (Ck=%d N=%d kernel %dx%d)", Ck, N,
                 a.R, a.Cc);
       return 1;
     }
-    const int taps = a.mode == MODE_S ? 16 : 4;
-    const int phases = a.mode == MODE_S ? 1 : 4;
+    const int taps = s1 ? s1Taps : (a.mode == MODE_S ? 16 : 4);
+    const int phases = a.mode == MODE_P ? 4 : 1;
     p.kcPer = Ck / 64;
     const int kTotal = taps * p.kcPer;
-    const size_t slab = (size_t)a.B * (a.mode == MODE_S ? 1 : 4) * a.Hlo * a.Wlo * N * sizeof(float);
-    Choice c = choose(ds, a.mode, pixTiles, phases, N, kTotal, (long long)(slab / sizeof(float)), a.epi == EPI_DGRAD,
-                      a.forceBN, a.forceSplits, slab, a.ws ? a.wsBytes : 0);
+    const size_t slab = (size_t)a.B * phases * a.Hlo * a.Wlo * N * sizeof(float);
+    // the cost model knows two shapes of main loop: MN-major weights (S) and K-major weights (P)
+    const int modelMode = rowsAreK ? MODE_S : MODE_P;
+    Choice c = choose(ds, modelMode, pixTiles, phases, N, kTotal, (long long)(slab / sizeof(float)), a.epi == EPI_DGRAD,
+                      a.forceBN, a.forceSplits, slab, a.ws ? a.wsBytes : 0, 16, !s1);
     if (c.BN == 0) {
       set_error("conv: no tile shape for N=%d", N);
       return 1;
@@ -639,7 +659,7 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     // (measured: +4 % step throughput at 8 images/GPU, +6 % at 32, -1 % at batch 1 where a CTA owns one tile and
     // the cluster launch costs more than the shared B tile saves -- hence only for launches of more than one wave)
     const long long itemsPlain = (long long)pixTiles * (N / c.BN) * phases * c.splits;
-    if ((g_pair == 1 || (g_pair == 0 && itemsPlain > maxCtas)) && c.BN >= 128 && pixTiles % 2 == 0 &&
+    if (!s1 && (g_pair == 1 || (g_pair == 0 && itemsPlain > maxCtas)) && c.BN >= 128 && pixTiles % 2 == 0 &&
         ds.max_pairs[a.mode][bn_index(c.BN)] > 0) {
       c.pair = 1;
       c.csplit = 0;  // a cluster is either a cta_group::2 pair or the K slices of one tile
@@ -652,8 +672,8 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     p.numItems = pixTiles * p.nTiles * phases * c.splits;
     p.cm = c.pair ? 2 : 1;
     p.N = N;
-    p.Hout = a.mode == MODE_S ? a.Hlo : 2 * a.Hlo;
-    p.Wout = a.mode == MODE_S ? a.Wlo : 2 * a.Wlo;
+    p.Hout = a.mode == MODE_P ? 2 * a.Hlo : a.Hlo;
+    p.Wout = a.mode == MODE_P ? 2 * a.Wlo : a.Wlo;
     p.out = a.out;
     p.ldo = a.ldo;
     p.bias = a.bias;
@@ -689,6 +709,9 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
       p.ldG = a.ldHi;
       if (map_hi5(&mapA, a.hi, a.ldHi, a.Chi, a.B, 2 * a.Hlo, 2 * a.Wlo, p.Wt, p.Ht, p.Nb)) return 1;
       if (map_w3(&mapB, a.w, a.R, a.Cc, 64)) return 1;
+    } else if (s1) {
+      if (map_lo4(&mapA, a.lo, a.ldLo, a.Clo, a.B, a.Hlo, a.Wlo, p.Wt, p.Ht, p.Nb)) return 1;
+      if (map_w3(&mapB, a.w, a.R, a.Cc, a.mode == MODE_CF ? 64 : BN, taps)) return 1;
     } else {
       if (map_lo4(&mapA, a.lo, a.ldLo, a.Clo, a.B, a.Hlo, a.Wlo, p.Wt, p.Ht, p.Nb)) return 1;
       if (map_w3(&mapB, a.w, a.R, a.Cc, c.pair ? BN / 2 : BN)) return 1;
@@ -703,15 +726,16 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
       return 1;
     }
     const int chunks = pixTiles;
-    const size_t slab = (size_t)16 * a.Chi * a.Clo * sizeof(float);
+    const int wTaps = s1 ? s1Taps : 16;
+    const size_t slab = (size_t)wTaps * a.Chi * a.Clo * sizeof(float);
     Choice c = choose(ds, MODE_W, Mch / 128, 1, Nch, chunks, (long long)(slab / sizeof(float)), false, a.forceBN,
-                      a.forceSplits, slab, a.ws ? a.wsBytes : 0);
+                      a.forceSplits, slab, a.ws ? a.wsBytes : 0, wTaps);
     if (c.BN == 0) {
       set_error("wgrad: no tile shape for N=%d", Nch);
       return 1;
     }
-    const long long itemsPlainW = (long long)16 * (Mch / 128) * (Nch / c.BN) * c.splits;
-    if ((g_pair == 1 || (g_pair == 0 && itemsPlainW > maxCtas)) && c.BN >= 128 && (Mch / 128) % 2 == 0 &&
+    const long long itemsPlainW = (long long)wTaps * (Mch / 128) * (Nch / c.BN) * c.splits;
+    if (!s1 && (g_pair == 1 || (g_pair == 0 && itemsPlainW > maxCtas)) && c.BN >= 128 && (Mch / 128) % 2 == 0 &&
         ds.max_pairs[MODE_W][bn_index(c.BN)] > 0)
       c.pair = 1;
     BN = c.BN;
@@ -719,7 +743,7 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     p.nTiles = Nch / BN;
     p.splits = c.splits;
     p.kIters = chunks / c.splits;
-    p.numItems = 16 * p.mTiles * p.nTiles * c.splits;
+    p.numItems = wTaps * p.mTiles * p.nTiles * c.splits;
     p.cm = c.pair ? 2 : 1;
     p.N = Nch;
     p.ldG = a.ldHi;
@@ -730,13 +754,17 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     p.colStride = p.gIsA ? 1 : a.Clo;
     p.atomic = c.splits > 1;
     CUtensorMap mg, mp;
-    if (map_hi5(&mg, a.hi, a.ldHi, a.Chi, a.B, 2 * a.Hlo, 2 * a.Wlo, p.Wt, p.Ht, p.Nb)) return 1;
+    if (s1) {  // the gathered operand is the layer's input at the same extent as dy
+      if (map_lo4(&mg, a.hi, a.ldHi, a.Chi, a.B, a.Hlo, a.Wlo, p.Wt, p.Ht, p.Nb)) return 1;
+    } else if (map_hi5(&mg, a.hi, a.ldHi, a.Chi, a.B, 2 * a.Hlo, 2 * a.Wlo, p.Wt, p.Ht, p.Nb)) {
+      return 1;
+    }
     if (map_lo4(&mp, a.lo, a.ldLo, a.Clo, a.B, a.Hlo, a.Wlo, p.Wt, p.Ht, p.Nb)) return 1;
     mapA = p.gIsA ? mg : mp;
     mapB = p.gIsA ? mp : mg;
     if (p.atomic) {
       p.ws = a.ws;
-      p.wsSplitStride = (long long)16 * a.Chi * a.Clo;
+      p.wsSplitStride = (long long)wTaps * a.Chi * a.Clo;
     }
   }
 
@@ -787,14 +815,20 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     e = launch_bn<MODE_S>(BN, grid, smem, stream, mapA, mapB, p);
   else if (a.mode == MODE_P)
     e = launch_bn<MODE_P>(BN, grid, smem, stream, mapA, mapB, p);
-  else
+  else if (a.mode == MODE_W)
     e = launch_bn<MODE_W>(BN, grid, smem, stream, mapA, mapB, p);
+  else if (a.mode == MODE_CF)
+    e = launch_bn<MODE_CF>(BN, grid, smem, stream, mapA, mapB, p);
+  else if (a.mode == MODE_CD)
+    e = launch_bn<MODE_CD>(BN, grid, smem, stream, mapA, mapB, p);
+  else
+    e = launch_bn<MODE_CW>(BN, grid, smem, stream, mapA, mapB, p);
   if (e != cudaSuccess) {
     set_error("conv_umma_kernel launch: %s", cudaGetErrorString(e));
     return 1;
   }
   count_launch();
-  if (a.mode != MODE_W && p.splits > 1 && !p.fused && !p.csplit) {
+  if (!mode_is_w(a.mode) && p.splits > 1 && !p.fused && !p.csplit) {
     const long long pixels = (long long)a.B * p.Hout * p.Wout;
     const long long total = pixels * (p.N / 4);
     int blocks = (int)((total + 255) / 256);
@@ -807,8 +841,8 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     }
     count_launch();
   }
-  if (a.mode == MODE_W && p.splits > 1) {
-    const long long nvec = (long long)4 * a.Chi * a.Clo;  // 16 taps * Chi * Clo / 4
+  if (mode_is_w(a.mode) && p.splits > 1) {
+    const long long nvec = (long long)(s1 ? s1Taps : 16) * a.Chi * a.Clo / 4;
     int blocks = (int)((nvec + 255) / 256);
     if (blocks > ds.num_sms * 8) blocks = ds.num_sms * 8;
     e = launch_k(wgrad_reduce_kernel, dim3(blocks), dim3(256), 0, stream, reinterpret_cast<const float4*>(a.ws),

@@ -13,6 +13,13 @@
 //   MODE_W  weight gradient  dW[tap][g][p] = sum_pix G_hi[pix @ tap, g] * P_lo[pix, p]
 //           both operands MN-major (pixels are the contraction dim and are the slow smem axis).
 //
+// Stride-1 index maps (reference: train.py:131-139, Block's ks x ks / stride-1 Conv2D with ks = 3; the dormant
+// block_depth > 0 branch).  Input and output have the same extent; a tap is a whole-tile shift:
+//   MODE_CF fprop            out[pix, n] = sum_{tap(ks*ks), k} X[pix + (tap - ks/2), k] * Wt[tap][k][n]     (B MN-major, HWIO)
+//   MODE_CD dgrad            dx[pix, n]  = sum_{tap, k} dY[pix - (tap - ks/2), k] * Wt[tap][n][k]           (B K-major,  HWIO)
+//   MODE_CW weight gradient  dW[tap][g][p] = sum_pix X[pix + (tap - ks/2), g] * dY[pix, p]
+//           A of CF / CD and the X operand of CW: 4-D TMA box shifted by the tap, zero fill at the border (SAME padding).
+//
 // Warp roles: warps 0, 2, 3 = TMA producers (ring rounds round-robin; warp 2 also allocates TMEM), warp 1 = MMA
 // issuer, warps 4.. = epilogue (8 warps for BN = 64, 16 otherwise; TMEM -> registers -> global).  Accumulators are
 // double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the main loop of tile i+1.
@@ -38,7 +45,9 @@
 
 namespace gct2 {
 
-enum : int { MODE_S = 0, MODE_P = 1, MODE_W = 2 };
+enum : int { MODE_S = 0, MODE_P = 1, MODE_W = 2, MODE_CF = 3, MODE_CD = 4, MODE_CW = 5 };
+__host__ __device__ constexpr bool mode_is_w(int m) { return m == MODE_W || m == MODE_CW; }
+__host__ __device__ constexpr bool mode_is_s1(int m) { return m >= MODE_CF; }
 enum : int { EPI_BIAS_RELU = 0, EPI_DGRAD = 1, EPI_WS_SLAB = 2, EPI_WGRAD = 3 };
 
 __device__ __forceinline__ void epi_bar_sync(int nthreads) {  // named barrier 1: epilogue warps only
@@ -99,6 +108,7 @@ struct ConvParams {
   unsigned spinLimit;          // fused: rendezvous watchdog (polls of ~40 ns; 0 = wait for ever)
   int bEarly;                  // S/P: fetch the first ring pass of weight boxes before griddepcontrol.wait
   int f16;                     // 16-bit storage format of operands and outputs: 0 = bf16, 1 = fp16 (gct2_set_policy)
+  int ks;                      // stride-1 modes: kernel side (3, or 1 for a per-pixel projection); taps = ks * ks
   // fast division by the launch constants used in index decoding (all set by conv_launch)
   FastDiv fdMTilesC, fdNTiles, fdSplits, fdKcPer;
   int lgWt, lgHt, lgTilesX, lgTilesY;  // pixel-tile geometry is power-of-two by construction
@@ -142,7 +152,7 @@ __device__ __forceinline__ WorkItem decode_item(const ConvParams& p, int item, i
   }
   w.mt = fd_mod(p.fdMTilesC, item) * p.cm + rm;
   int r = fd_div(p.fdMTilesC, item);
-  if (MODE == MODE_W) {
+  if (mode_is_w(MODE)) {
     w.nt = fd_mod(p.fdNTiles, r);
     r = fd_div(p.fdNTiles, r);
     w.split = fd_mod(p.fdSplits, r);
@@ -241,6 +251,36 @@ __device__ __forceinline__ void issue_chunk(const ConvParams& p, const CUtensorM
         tma_load_3d_pair(sb, mapB, bar, kc * 64, w.nt * BN + rm * (BN / 2), ky * 4 + kx);
       else
         tma_load_3d(sb, mapB, bar, kc * 64, w.nt * BN, ky * 4 + kx);
+    }
+  } else if (MODE == MODE_CF || MODE == MODE_CD) {
+    const int tap = fd_div(p.fdKcPer, kit), kc = kit - tap * p.kcPer;
+    const int ky = p.ks == 3 ? (tap * 11) >> 5 : 0, kx = tap - ky * p.ks, off = p.ks >> 1;
+    const int sx = MODE == MODE_CF ? kx - off : off - kx, sy = MODE == MODE_CF ? ky - off : off - ky;
+    if (doA) tma_load_4d(sa, mapA, bar, kc * 64, x0 + sx, y0 + sy, b0);
+    if (doB) {
+      if (MODE == MODE_CF) {
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j) tma_load_3d(sb + j * BLK, mapB, bar, w.nt * BN + j * 64, kc * 64, tap);
+      } else {
+        tma_load_3d(sb, mapB, bar, kc * 64, w.nt * BN, tap);
+      }
+    }
+  } else if (MODE == MODE_CW) {
+    const int cx = (kit & (p.tilesX - 1)) << p.lgWt;
+    const int cy = ((kit >> p.lgTilesX) & (p.tilesY - 1)) << p.lgHt;
+    const int cb = (kit >> (p.lgTilesX + p.lgTilesY)) * p.Nb;
+    const int ky = p.ks == 3 ? (w.ph * 11) >> 5 : 0, kx = w.ph - ky * p.ks, off = p.ks >> 1;
+    if (p.gIsA) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) tma_load_4d(sa + j * BLK, mapA, bar, w.mt * 128 + j * 64, cx + kx - off, cy + ky - off, cb);
+#pragma unroll
+      for (int j = 0; j < BN / 64; ++j) tma_load_4d(sb + j * BLK, mapB, bar, w.nt * BN + j * 64, cx, cy, cb);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) tma_load_4d(sa + j * BLK, mapA, bar, w.mt * 128 + j * 64, cx, cy, cb);
+#pragma unroll
+      for (int j = 0; j < BN / 64; ++j)
+        tma_load_4d(sb + j * BLK, mapB, bar, w.nt * BN + j * 64, cx + kx - off, cy + ky - off, cb);
     }
   } else {
     // pixel chunk -> (batch tile, y tile, x tile); both operands are activations: always loaded together
@@ -445,7 +485,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
   const unsigned long long t_entry = (p.dbg != nullptr && threadIdx.x == 0) ? globaltimer_ns() : 0ull;
 #endif
 
-  constexpr bool csplit = CS != 0 && !pair && MODE != MODE_W;
+  constexpr bool csplit = CS != 0 && !pair && !mode_is_w(MODE);
   const int rm = (pair || csplit) ? (int)cluster_ctarank() : 0;
   const int clusterId = pair ? (int)(blockIdx.x >> 1) : (csplit ? fd_div(p.fdSplits, (int)blockIdx.x) : (int)blockIdx.x);
   const int numClusters = pair ? (int)(gridDim.x >> 1) : (csplit ? fd_div(p.fdSplits, (int)gridDim.x) : (int)gridDim.x);
@@ -500,7 +540,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
   const int lastCh = p.kIters - (p.rounds - 1) * KPS;  // chunks of an item's last round (1 or KPS)
 
   // ---- weights of the first ring pass, before the dependency resolves (they are not produced by the previous launch)
-  const bool early = MODE != MODE_W && p.bEarly != 0;
+  const bool early = !mode_is_w(MODE) && p.bEarly != 0;
   if (early && producer && clusterId < p.numClusterItems) {
     const WorkItem w = decode_item<MODE>(p, clusterId, rm);
     const int firstPass = p.rounds < S ? p.rounds : S;
@@ -543,7 +583,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
       for (int item = clusterId; item < p.numClusterItems; item += numClusters, gbase += (uint32_t)p.rounds) {
         const WorkItem w = decode_item<MODE>(p, item, rm);
         int x0 = 0, y0 = 0, b0 = 0;
-        if (MODE != MODE_W) {
+        if (!mode_is_w(MODE)) {
           x0 = (w.mt & (p.tilesX - 1)) << p.lgWt;
           y0 = ((w.mt >> p.lgTilesX) & (p.tilesY - 1)) << p.lgHt;
           b0 = (w.mt >> (p.lgTilesX + p.lgTilesY)) * p.Nb;
@@ -575,8 +615,8 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (pair: the leader CTA only)
     if ((!pair || rm == 0) && elect_one()) {
-      constexpr int A_MN = (MODE == MODE_W) ? 1 : 0;
-      constexpr int B_MN = (MODE == MODE_P) ? 0 : 1;
+      constexpr int A_MN = mode_is_w(MODE) ? 1 : 0;
+      constexpr int B_MN = (MODE == MODE_P || MODE == MODE_CD) ? 0 : 1;
       // cta_group::2: 256 rows over the pair; operand format by the launch's storage policy
       const uint32_t idesc = GCT2_F16_OF(p) ? make_idesc_bf16(pair ? 256 : 128, BN, A_MN, B_MN, 0)
                                    : make_idesc_bf16(pair ? 256 : 128, BN, A_MN, B_MN, 1);
@@ -675,7 +715,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
         // row -> output location
         bool valid = true;
         long long pix = 0;
-        if (MODE != MODE_W) {
+        if (!mode_is_w(MODE)) {
           const int xl = r & (p.Wt - 1), yl = (r >> p.lgWt) & (p.Ht - 1), bl = r >> (p.lgWt + p.lgHt);
           const int x = ((w.mt & (p.tilesX - 1)) << p.lgWt) + xl;
           const int y = (((w.mt >> p.lgTilesX) & (p.tilesY - 1)) << p.lgHt) + yl;

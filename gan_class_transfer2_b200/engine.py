@@ -186,6 +186,24 @@ def shard_batch(global_batch: int, world: int, rank: int) -> Tuple[int, int]:
     return rank * per, (rank + 1) * per
 
 
+def plan_table_key(cfg: NetConfig, batch: int, sms: int) -> str:
+    """Which tuned table applies: the network's shape, the per-GPU batch, the storage policy and the SM count."""
+    ch = ",".join(f"{cfg.down_c(i)}:{cfg.up_c(i)}" for i in range(cfg.octaves))
+    return f"size{cfg.size}_oct{cfg.octaves}_ch{ch}_b{batch}_{'f16' if cfg.mixed_precision else 'bf16'}_sm{sms}"
+
+
+def load_tuned_plans(cfg: NetConfig, batch: int, sms: int) -> Dict[str, Tuple[int, int]]:
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tuned_plans.json")
+    if not os.path.exists(path):
+        return {}
+    with open(path) as f:
+        tables = json.load(f)
+    table = tables.get(plan_table_key(cfg, batch, sms), {}).get("plans", {})
+    return {k: (int(v[0]), int(v[1])) for k, v in table.items()}
+
+
 class DataParallel:
     """Data-parallel context: the batch shards over ranks, gradient buckets are summed with NCCL."""
 
@@ -301,6 +319,12 @@ class UNetEngine:
         dev, n, S, B = self.device, cfg.octaves, cfg.size, batch
         from . import _lib
         lib = _lib.init(self.device.index or 0)
+        self._lib = lib
+        #: per-launch plan overrides {"<layer>/<pass>": (BN, splits)}; tuned_plans.json holds tables measured in the step
+        #: (tools/tune_plans.py) for single-GPU configurations, GCT2_TUNED=0 ignores them
+        self.plans: Dict[str, Tuple[int, int]] = {}
+        if os.environ.get("GCT2_TUNED", "1") != "0" and not (dp is not None and dp.world > 1):
+            self.plans = load_tuned_plans(cfg, batch, _lib.load().gct2_num_sms())
         if dp is not None and dp.world > 1:
             # The L2 form of the in-launch split-K finish makes the CTAs of a conv launch wait for one another, which is
             # only safe while every other kernel on the GPU terminates on its own.  An NCCL kernel waits for its peer GPU
@@ -481,17 +505,64 @@ class UNetEngine:
     def gup_out(self, i: int) -> torch.Tensor:
         return self.gu0 if i == 0 else self.gcat[i][..., :self.cfg.up_c(i)]
 
+    # ------------------------------------------------------------------------------------------ tensor-core passes
+    def plan_keys(self) -> List[str]:
+        """The tensor-core launches of one step in step order: "<layer>/<fprop|dgrad|wgrad>" (down0 runs on CUDA cores)."""
+        n = self.cfg.octaves
+        keys = [f"down{i}/fprop" for i in range(1, n)] + [f"up{i}/fprop" for i in reversed(range(n))]
+        for i in range(n):
+            keys += [f"up{i}/wgrad", f"up{i}/dgrad"]
+        for i in reversed(range(1, n)):
+            keys += [f"down{i}/wgrad", f"down{i}/dgrad"]
+        return keys
+
+    def _conv_pass(self, key: str) -> None:
+        """One tensor-core launch of the step on the current stream.  `self.plans[key] = (BN, splits)` (tile width and
+        split-K factor; 0 = the library's cost model decides) overrides the plan: the table is measured *in the step*
+        by tools/tune_plans.py, where launches compete for SMs with the two other chains -- something a per-launch cost
+        model cannot see."""
+        cfg, n = self.cfg, self.cfg.octaves
+        layer, kind = key.split("/")
+        i = int(layer[4:] if layer.startswith("down") else layer[2:])
+        bn, splits = self.plans.get(key, (0, 0))
+        if bn or splits:
+            self._lib.gct2_debug_set(3, int(bn))
+            self._lib.gct2_debug_set(4, int(splits))
+        try:
+            if layer.startswith("down"):
+                if kind == "fprop":
+                    ops.conv4s2_fprop(self.down_in(i), self.view(self.w16, f"down{i}/kernel"),
+                                      self.view(self.w, f"down{i}/bias"), self.down_out(i), self.ws, self.weights_stable)
+                elif kind == "wgrad":
+                    ops.conv4s2_wgrad(self.down_in(i), self.gdown_out(i), self.view(self.g, f"down{i}/kernel"), self.ws_w)
+                else:
+                    # total gradient of down_{i-1}'s output = skip-path part (stored raw by up_{i-1}'s dgrad) + this
+                    ops.conv4s2_dgrad(self.gdown_out(i), self.view(self.w16, f"down{i}/kernel"),
+                                      self.gcat[i][..., cfg.up_c(i):], self.down_in(i), True, self.ws, self.weights_stable)
+            else:
+                if kind == "fprop":
+                    ops.convT4s2_fprop(self.up_in_buf(i), self.view(self.w16, f"up{i}/kernel"),
+                                       self.view(self.w, f"up{i}/bias"), self.up_out(i), self.ws, self.weights_stable)
+                elif kind == "wgrad":
+                    ops.convT4s2_wgrad(self.up_in_buf(i), self.gup_out(i), self.view(self.g, f"up{i}/kernel"), self.ws_w)
+                else:
+                    mask = cfg.down_c(i) if i == n - 1 else cfg.up_c(i + 1)
+                    ops.convT4s2_dgrad(self.gup_out(i), self.view(self.w16, f"up{i}/kernel"), self.gup_in_buf(i),
+                                       self.up_in_buf(i), mask, self.ws, self.weights_stable)
+        finally:
+            if bn or splits:
+                self._lib.gct2_debug_set(3, 0)
+                self._lib.gct2_debug_set(4, 0)
+
     # ------------------------------------------------------------------------------------------ forward / backward
     def _forward(self, want_pred: bool, backward: bool, inv_n: float) -> None:
         cfg, n = self.cfg, self.cfg.octaves
         ops.conv4s2_c3_fprop(self.noised, self.view(self.w, "down0/kernel"), self.view(self.w, "down0/bias"),
                              self.down_out(0))
         for i in range(1, n):
-            ops.conv4s2_fprop(self.down_in(i), self.view(self.w16, f"down{i}/kernel"),
-                              self.view(self.w, f"down{i}/bias"), self.down_out(i), self.ws, self.weights_stable)
+            self._conv_pass(f"down{i}/fprop")
         for i in reversed(range(n)):
-            ops.convT4s2_fprop(self.up_in_buf(i), self.view(self.w16, f"up{i}/kernel"),
-                               self.view(self.w, f"up{i}/bias"), self.up_out(i), self.ws, self.weights_stable)
+            self._conv_pass(f"up{i}/fprop")
         ops.dense_mse(self.u0, self.noised, self.x, self.view(self.w, "dense/kernel"), self.view(self.w, "dense/bias"),
                       self.loss, inv_n, pred=self.pred if want_pred else None,
                       du0=self.gu0 if backward else None, dwd=self.view(self.g, "dense/kernel") if backward else None,
@@ -639,18 +710,12 @@ class UNetEngine:
                         side[1] = True
 
         for i in range(n):  # up0 .. up{n-1}
-            on_side(lambda: ops.convT4s2_wgrad(self.up_in_buf(i), self.gup_out(i), self.view(self.g, f"up{i}/kernel"),
-                                               self.ws_w))
-            mask = cfg.down_c(i) if i == n - 1 else cfg.up_c(i + 1)
-            ops.convT4s2_dgrad(self.gup_out(i), self.view(self.w16, f"up{i}/kernel"), self.gup_in_buf(i),
-                               self.up_in_buf(i), mask, self.ws, self.weights_stable)
+            on_side(lambda: self._conv_pass(f"up{i}/wgrad"))
+            self._conv_pass(f"up{i}/dgrad")
             bucket_done(f"up{i}/kernel")
         for i in reversed(range(1, n)):  # down{n-1} .. down1
-            on_side(lambda: ops.conv4s2_wgrad(self.down_in(i), self.gdown_out(i), self.view(self.g, f"down{i}/kernel"),
-                                              self.ws_w))
-            # total gradient of down_{i-1}'s output = skip-path part (already stored raw by up_{i-1}'s dgrad) + this
-            ops.conv4s2_dgrad(self.gdown_out(i), self.view(self.w16, f"down{i}/kernel"), self.gcat[i][..., cfg.up_c(i):],
-                              self.down_in(i), True, self.ws, self.weights_stable)
+            on_side(lambda: self._conv_pass(f"down{i}/wgrad"))
+            self._conv_pass(f"down{i}/dgrad")
             bucket_done(f"down{i}/kernel")
         ops.conv4s2_c3_wgrad(self.noised, self.gdown_out(0), self.view(self.g, "down0/kernel"), None, accumulate=True)
         # every conv layer's BiasAddGrad in one launch: the pre-activation gradients all still sit in their buffers
@@ -792,22 +857,8 @@ class UNetEngine:
         11 wgrads, in step order -- back to back on the current stream and nothing else, over whatever the buffers
         hold.  Same plans, same programmatic dependent launch chaining as inside the step; the optimiser, the
         CUDA-core kernels and the side streams are left out so that the time is the family's alone."""
-        cfg, n = self.cfg, self.cfg.octaves
-        for i in range(1, n):
-            ops.conv4s2_fprop(self.down_in(i), self.view(self.w16, f"down{i}/kernel"),
-                              self.view(self.w, f"down{i}/bias"), self.down_out(i), self.ws, self.weights_stable)
-        for i in reversed(range(n)):
-            ops.convT4s2_fprop(self.up_in_buf(i), self.view(self.w16, f"up{i}/kernel"),
-                               self.view(self.w, f"up{i}/bias"), self.up_out(i), self.ws, self.weights_stable)
-        for i in range(n):
-            ops.convT4s2_wgrad(self.up_in_buf(i), self.gup_out(i), self.view(self.g, f"up{i}/kernel"), self.ws_w)
-            mask = cfg.down_c(i) if i == n - 1 else cfg.up_c(i + 1)
-            ops.convT4s2_dgrad(self.gup_out(i), self.view(self.w16, f"up{i}/kernel"), self.gup_in_buf(i),
-                               self.up_in_buf(i), mask, self.ws, self.weights_stable)
-        for i in reversed(range(1, n)):
-            ops.conv4s2_wgrad(self.down_in(i), self.gdown_out(i), self.view(self.g, f"down{i}/kernel"), self.ws_w)
-            ops.conv4s2_dgrad(self.gdown_out(i), self.view(self.w16, f"down{i}/kernel"), self.gcat[i][..., cfg.up_c(i):],
-                              self.down_in(i), True, self.ws, self.weights_stable)
+        for key in self.plan_keys():
+            self._conv_pass(key)
 
     def release_graphs(self) -> None:
         """Drops the captured step graphs.  Data-parallel callers do this before ``destroy_process_group``: NCCL keeps a
