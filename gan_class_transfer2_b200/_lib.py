@@ -63,6 +63,13 @@ _PROTOS = {
     "gct2_convT4s2_dgrad": (c_int, [_P, c_int, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                     _P, c_size_t, c_int, _P]),
     "gct2_convT4s2_wgrad": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "gct2_conv3s1_fprop": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_size_t,
+                                   c_int, _P]),
+    "gct2_conv3s1_dgrad": (c_int, [_P, c_int, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                   c_int, _P, c_size_t, c_int, _P]),
+    "gct2_conv3s1_wgrad": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "gct2_conv3s1_c3_fprop": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "gct2_conv3s1_c3_wgrad": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "gct2_bias_grad": (c_int, [_P, c_int, c_longlong, c_int, _P, _P]),
     "gct2_bias_grad_multi": (c_int, [c_int, _P, _P, _P, _P, _P, c_int, _P]),
     "gct2_dense_mse": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, c_longlong, c_int, c_float,

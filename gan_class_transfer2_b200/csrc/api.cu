@@ -173,6 +173,57 @@ int gct2_convT4s2_wgrad(const uint16_t* x, int ldx, const uint16_t* dy, int lddy
   return conv_launch(a, S(stream));
 }
 
+int gct2_conv3s1_fprop(const uint16_t* x, int ldx, const uint16_t* w, const float* bias, uint16_t* y, int ldy, int B,
+                       int H, int W, int Cin, int Cout, int ks, float* ws, size_t ws_bytes, int flags, void* stream) {
+  if (check_conv("gct2_conv3s1_fprop", B, H, W, Cin, Cout)) return 1;
+  ConvArgs a = blank(MODE_CF, B, H, W);
+  a.ks = ks;
+  a.lo = CB(x); a.ldLo = ldx; a.Clo = Cin;
+  a.w = CB(w); a.R = Cin; a.Cc = Cout;
+  a.epi = EPI_BIAS_RELU; a.out = MB(y); a.ldo = ldy; a.bias = bias;
+  a.ws = ws; a.wsBytes = ws_bytes; a.flags = (flags & GCT2_WEIGHTS_STABLE) ? CONV_WEIGHTS_STABLE : 0;
+  return conv_launch(a, S(stream));
+}
+
+int gct2_conv3s1_dgrad(const uint16_t* dy, int lddy, const uint16_t* w, uint16_t* dx, int lddx, const uint16_t* act,
+                       int ldact, int mask_channels, int add_old, int B, int H, int W, int Cin, int Cout, int ks,
+                       float* ws, size_t ws_bytes, int flags, void* stream) {
+  if (check_conv("gct2_conv3s1_dgrad", B, H, W, Cin, Cout)) return 1;
+  if (mask_channels % 32 || mask_channels < 0 || mask_channels > Cin) {
+    set_error("gct2_conv3s1_dgrad: mask_channels must be a multiple of 32 in [0, Cin] (got %d)", mask_channels);
+    return 1;
+  }
+  ConvArgs a = blank(MODE_CD, B, H, W);
+  a.ks = ks;
+  a.lo = CB(dy); a.ldLo = lddy; a.Clo = Cout;
+  a.w = CB(w); a.R = Cin; a.Cc = Cout;
+  a.epi = EPI_DGRAD; a.out = MB(dx); a.ldo = lddx; a.act = CB(act); a.ldact = ldact; a.maskN = mask_channels;
+  a.addOld = add_old ? 1 : 0;
+  a.ws = ws; a.wsBytes = ws_bytes; a.flags = (flags & GCT2_WEIGHTS_STABLE) ? CONV_WEIGHTS_STABLE : 0;
+  return conv_launch(a, S(stream));
+}
+
+int gct2_conv3s1_wgrad(const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, int B, int H, int W,
+                       int Cin, int Cout, int ks, float* ws, size_t ws_bytes, void* stream) {
+  if (check_conv("gct2_conv3s1_wgrad", B, H, W, Cin, Cout)) return 1;
+  ConvArgs a = blank(MODE_CW, B, H, W);
+  a.ks = ks;
+  a.hi = CB(x); a.ldHi = ldx; a.Chi = Cin;
+  a.lo = CB(dy); a.ldLo = lddy; a.Clo = Cout;
+  a.dw = dw;
+  a.ws = ws; a.wsBytes = ws_bytes;
+  return conv_launch(a, S(stream));
+}
+
+int gct2_conv3s1_c3_fprop(const float* x, const float* w, const float* bias, uint16_t* y, int ldy, int B, int H,
+                          int W, int Cout, void* stream) {
+  return conv3s1_c3_fprop(x, w, bias, MB(y), ldy, B, H, W, Cout, S(stream));
+}
+int gct2_conv3s1_c3_wgrad(const float* x, const uint16_t* dz, int lddz, float* dw, int B, int H, int W, int Cout,
+                          int accumulate, void* stream) {
+  return conv3s1_c3_wgrad(x, CB(dz), lddz, dw, B, H, W, Cout, accumulate ? 0 : 1, S(stream));
+}
+
 int gct2_bias_grad(const uint16_t* dz, int ld, long long rows, int C, float* db, void* stream) {
   return bias_grad(CB(dz), ld, rows, C, db, S(stream));
 }

@@ -500,6 +500,172 @@ int conv4s2_c3_wgrad(const float* x, const __nv_bfloat16* dz, int lddz, float* d
   return 0;
 }
 
+// ------------------------------------------------------------------------------------ 3x3 / stride-1 conv on the image
+// train.py:131-139 with block_depth > 0: the first Conv2D of the outermost Block (train.py:192) reads the 3-channel
+// image (K = 27): CUDA-core direct convolution.  A thread owns one pixel x 8 output channels; the kernel (27 x Cout fp32)
+// and the bias sit in shared memory, the 27 inputs of a pixel are broadcast loads shared by the threads of that pixel.
+__global__ void __launch_bounds__(256) conv3s1_c3_fprop_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                               const float* __restrict__ bias,
+                                                               __nv_bfloat16* __restrict__ y, int ldy, int B, int H,
+                                                               int W, int Cout, int f16) {
+  TraceScope trace(30);
+  extern __shared__ __align__(16) float c3s1_smem[];
+  float* ws = c3s1_smem;             // [27][Cout]
+  float* bs = c3s1_smem + 27 * Cout;  // [Cout]
+  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) ws[i] = __ldg(w + i);
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) bs[i] = __ldg(bias + i);
+  pdl_launch_dependents();
+  pdl_wait();
+  trace.ready();
+  __syncthreads();
+  const int groups = Cout / 8, ppb = blockDim.x / groups;
+  const int grp = threadIdx.x % groups, pl = threadIdx.x / groups;
+  const long long pixels = (long long)B * H * W;
+  if (pl < ppb) {
+    for (long long p = (long long)blockIdx.x * ppb + pl; p < pixels; p += (long long)gridDim.x * ppb) {
+      const int xx = (int)(p % W), yy = (int)((p / W) % H);
+      const long long b = p / ((long long)W * H);
+      float acc[8];
+      const float4 b0 = *reinterpret_cast<const float4*>(bs + grp * 8), b1 = *reinterpret_cast<const float4*>(bs + grp * 8 + 4);
+      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = yy + ky - 1;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ix = xx + kx - 1;
+          const bool in = iy >= 0 && iy < H && ix >= 0 && ix < W;
+          const float* xp = x + ((b * H + iy) * W + ix) * 3;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float v = in ? __ldg(xp + c) : 0.f;
+            const float* wr = ws + ((ky * 3 + kx) * 3 + c) * Cout + grp * 8;
+            const float4 w0 = *reinterpret_cast<const float4*>(wr), w1 = *reinterpret_cast<const float4*>(wr + 4);
+            acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]);
+            acc[3] = fmaf(v, w0.w, acc[3]); acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
+            acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+          }
+        }
+      }
+      uint4 o;
+      o.x = pack_h2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), f16);
+      o.y = pack_h2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f), f16);
+      o.z = pack_h2(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f), f16);
+      o.w = pack_h2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f), f16);
+      *reinterpret_cast<uint4*>(y + p * ldy + grp * 8) = o;
+    }
+  }
+  trace.end();
+}
+
+int conv3s1_c3_fprop(const float* x, const float* w, const float* bias, __nv_bfloat16* y, int ldy, int B, int H,
+                     int W, int Cout, cudaStream_t st) {
+  if (Cout % 8 || Cout < 8 || Cout > 1024 || ldy % 8 || B < 1 || H < 1 || W < 1) {
+    set_error("conv3s1_c3_fprop: unsupported shape B=%d H=%d W=%d Cout=%d ldy=%d", B, H, W, Cout, ldy);
+    return 1;
+  }
+  const size_t smem = (size_t)28 * Cout * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(conv3s1_c3_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("conv3s1_c3_fprop: %s", cudaGetErrorString(e));
+      return 1;
+    }
+  }
+  const int groups = Cout / 8, ppb = 256 / groups;
+  if (ppb < 1) {
+    set_error("conv3s1_c3_fprop: Cout=%d needs more than one block per pixel", Cout);
+    return 1;
+  }
+  const long long pixels = (long long)B * H * W;
+  long long blocks = (pixels + ppb - 1) / ppb;
+  if (blocks > (long long)g_ew_sms * 8) blocks = (long long)g_ew_sms * 8;
+  launch_k(conv3s1_c3_fprop_kernel, dim3((int)blocks), dim3(256), smem, st, x, w, bias, y, ldy, B, H, W, Cout, g_f16);
+  GCT2_CHECK_LAUNCH("conv3s1_c3_fprop_kernel");
+  return 0;
+}
+
+// wgrad: dw[ky,kx,c,co] += sum_pix x[pix + (ky-1, kx-1), c] * dz[pix, co].  A thread owns one output channel and a
+// stride of the block's pixels with its 27 sums in registers (the pixel's 27 inputs are the same address for all
+// threads of a warp: broadcast loads); lanes are combined in shared memory, one global atomic per value per block.
+__global__ void __launch_bounds__(256) conv3s1_c3_wgrad_kernel(const float* __restrict__ x,
+                                                               const __nv_bfloat16* __restrict__ dz, int lddz,
+                                                               float* __restrict__ dw, int B, int H, int W, int Cout,
+                                                               int chBlock, long long pixPerBlock, int f16) {
+  TraceScope trace(31);
+  extern __shared__ __align__(16) float c3s1w_smem[];  // [27][chBlock]
+  for (int i = threadIdx.x; i < 27 * chBlock; i += blockDim.x) c3s1w_smem[i] = 0.f;
+  pdl_launch_dependents();
+  pdl_wait();
+  trace.ready();
+  __syncthreads();
+  const int lanes = blockDim.x / chBlock;
+  const int cl = threadIdx.x % chBlock, lane = threadIdx.x / chBlock;
+  const int co = blockIdx.y * chBlock + cl;
+  const long long pixels = (long long)B * H * W;
+  const long long p0 = (long long)blockIdx.x * pixPerBlock;
+  const long long p1 = p0 + pixPerBlock < pixels ? p0 + pixPerBlock : pixels;
+  float acc[27];
+#pragma unroll
+  for (int k = 0; k < 27; ++k) acc[k] = 0.f;
+  if (lane < lanes) {
+    const unsigned short* dzs = reinterpret_cast<const unsigned short*>(dz);
+    for (long long p = p0 + lane; p < p1; p += lanes) {
+      const unsigned short raw = __ldg(dzs + p * lddz + co);
+      const float g = h_lo((uint32_t)raw, f16);
+      const int xx = (int)(p % W), yy = (int)((p / W) % H);
+      const long long b = p / ((long long)W * H);
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = yy + ky - 1;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ix = xx + kx - 1;
+          const bool in = iy >= 0 && iy < H && ix >= 0 && ix < W;
+          const float* xp = x + ((b * H + iy) * W + ix) * 3;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float v = in ? __ldg(xp + c) : 0.f;
+            acc[(ky * 3 + kx) * 3 + c] = fmaf(v, g, acc[(ky * 3 + kx) * 3 + c]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 27; ++k) atomicAdd(&c3s1w_smem[k * chBlock + cl], acc[k]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 27 * chBlock; i += blockDim.x)
+    atomicAdd(dw + (long long)(i / chBlock) * Cout + blockIdx.y * chBlock + (i % chBlock), c3s1w_smem[i]);
+  trace.end();
+}
+
+int conv3s1_c3_wgrad(const float* x, const __nv_bfloat16* dz, int lddz, float* dw, int B, int H, int W, int Cout,
+                     int zero, cudaStream_t st) {
+  int chBlock = Cout < 256 ? Cout : 256;
+  if (Cout < 8 || 256 % chBlock || Cout % chBlock || B < 1 || H < 1 || W < 1) {
+    set_error("conv3s1_c3_wgrad: Cout must be a power of two >= 8 or a multiple of 256 (got %d)", Cout);
+    return 1;
+  }
+  if (zero) {
+    cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)27 * Cout * sizeof(float), st);
+    if (e != cudaSuccess) {
+      set_error("conv3s1_c3_wgrad memset: %s", cudaGetErrorString(e));
+      return 1;
+    }
+  }
+  const long long pixels = (long long)B * H * W;
+  long long gx = 2LL * g_ew_sms;
+  if (gx > (pixels + 63) / 64) gx = (pixels + 63) / 64;
+  if (gx < 1) gx = 1;
+  const long long ppb = (pixels + gx - 1) / gx;
+  gx = (pixels + ppb - 1) / ppb;
+  launch_k(conv3s1_c3_wgrad_kernel, dim3((int)gx, Cout / chBlock), dim3(256), (size_t)27 * chBlock * sizeof(float), st, x, dz,
+           lddz, dw, B, H, W, Cout, chBlock, ppb, g_f16);
+  GCT2_CHECK_LAUNCH("conv3s1_c3_wgrad_kernel");
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------ Dense(3) + MSE (a6,a7)
 // LPP lanes share one pixel (lane `sub` owns 8 of the Cu = 8*LPP up0 channels: one 16-byte load / store), so a warp
 // walks 32/LPP pixels per iteration; the 3 image channels are handled by every lane of the group (broadcast loads).
@@ -534,8 +700,9 @@ __global__ void __launch_bounds__(256) dense_mse_kernel(const __nv_bfloat16* __r
   for (int c = 0; c < 8; ++c)
 #pragma unroll
     for (int j = 0; j < 3; ++j) w[c][j] = __ldg(wd + (sub * 8 + c) * 3 + j);
+  const bool img = noised != nullptr;  // false: Dense(3) on the CU 16-bit channels only (wd is [CU,3])
 #pragma unroll
-  for (int k = 0; k < 9; ++k) wn[k] = __ldg(wd + CU * 3 + k);
+  for (int k = 0; k < 9; ++k) wn[k] = img ? __ldg(wd + CU * 3 + k) : 0.f;
 #pragma unroll
   for (int j = 0; j < 3; ++j) bv[j] = __ldg(bd + j);
   const float gradScale = loss_scale != nullptr ? invN * __ldg(loss_scale) : invN;
@@ -574,7 +741,7 @@ __global__ void __launch_bounds__(256) dense_mse_kernel(const __nv_bfloat16* __r
       a[4] = h_lo(uv.z, f16); a[5] = h_hi(uv.z, f16); a[6] = h_lo(uv.w, f16); a[7] = h_hi(uv.w, f16);
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        nz[c] = __ldg(noised + p * 3 + c);
+        if (img) nz[c] = __ldg(noised + p * 3 + c);
         xv[c] = ca * __ldg(x + p * 3 + c);
         if (cb != 0.f) xv[c] = fmaf(cb, __ldg(eps + p * 3 + c), xv[c]);
       }
@@ -656,9 +823,11 @@ __global__ void __launch_bounds__(256) dense_mse_kernel(const __nv_bfloat16* __r
     if (i == CU * 3 + 12)
       atomicAdd(loss, v * invN);
     else if (backward) {
-      if (i < CU * 3 + 9)
+      if (i < CU * 3)
         atomicAdd(dwd + i, v);
-      else
+      else if (i < CU * 3 + 9) {
+        if (img) atomicAdd(dwd + i, v);
+      } else
         atomicAdd(dbd + (i - CU * 3 - 9), v);
     }
   }
@@ -684,7 +853,7 @@ int dense_mse(const __nv_bfloat16* u0, int ldu, const float* noised, const float
   }
   if (zero) {
     cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), st);
-    if (backward && e == cudaSuccess) e = cudaMemsetAsync(dwd, 0, (size_t)(Cu + 3) * 3 * sizeof(float), st);
+    if (backward && e == cudaSuccess) e = cudaMemsetAsync(dwd, 0, (size_t)(Cu + (noised ? 3 : 0)) * 3 * sizeof(float), st);
     if (backward && e == cudaSuccess) e = cudaMemsetAsync(dbd, 0, 3 * sizeof(float), st);
     if (e != cudaSuccess) {
       set_error("dense_mse memset: %s", cudaGetErrorString(e));

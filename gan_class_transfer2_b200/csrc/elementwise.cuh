@@ -14,6 +14,10 @@ int conv4s2_c3_fprop(const float* x, const float* w, const float* bias, __nv_bfl
                      int W, int Cout, cudaStream_t st);
 int conv4s2_c3_wgrad(const float* x, const __nv_bfloat16* dz, int lddz, float* dw, float* db, int B, int H, int W,
                      int Cout, int zero, cudaStream_t st);
+int conv3s1_c3_fprop(const float* x, const float* w, const float* bias, __nv_bfloat16* y, int ldy, int B, int H,
+                     int W, int Cout, cudaStream_t st);
+int conv3s1_c3_wgrad(const float* x, const __nv_bfloat16* dz, int lddz, float* dw, int B, int H, int W, int Cout,
+                     int zero, cudaStream_t st);
 int dense_mse(const __nv_bfloat16* u0, int ldu, const float* noised, const float* x, const float* wd,
               const float* bd, float* pred, float* loss, __nv_bfloat16* du0, int lddu, float* dwd, float* dbd,
               long long pixels, int Cu, float invN, int backward, int zero, const float* loss_scale, const float* eps,

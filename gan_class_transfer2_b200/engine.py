@@ -54,6 +54,36 @@ class NetConfig:
     #: train.py:29-32 (predict_x / predict_scaled_epsilon / prediction_weighting / ordinary_differential_equation) as
     #: ops.target_mode bits: what the loss compares (train.py:238-252) and what log_sample derives from a prediction
     target_mode: int = 0
+    #: train.py:20,131-139: Block = block_depth x Conv2D(filters, 3, 1, 'same', relu); 0 (the reference's default) makes
+    #: every Block an identity.  > 0 is run by block_engine.BlockUNetEngine
+    block_depth: int = 0
+    #: train.py:27,113-119: Residual concatenates [module(x), x]; False = module(x) alone (no skip connections)
+    concat: bool = True
+    #: filters of the innermost Block (train.py:179); None = min(pixel_size * 2**octaves, max_size)
+    mid_filters: Optional[int] = None
+    #: filters of the two outermost Blocks (train.py:192,194); None = pixel_size
+    outer_filters: Optional[int] = None
+
+    @property
+    def fused_default(self) -> bool:
+        """The wiring the tuned UNetEngine implements (the reference's defaults)."""
+        return self.block_depth == 0 and self.concat
+
+    def mid_c(self) -> int:  # train.py:179
+        return self.mid_filters if self.mid_filters is not None else min(self.pixel_size * 2 ** self.octaves, self.max_size)
+
+    def outer_c(self) -> int:  # train.py:192,194
+        return self.outer_filters if self.outer_filters is not None else self.pixel_size
+
+    def level_in(self, i: int) -> int:
+        """Channels entering Residual level i (the tensor the skip connection carries)."""
+        if i == 0:
+            return self.outer_c() if self.block_depth else 3
+        return self.down_c(i - 1)
+
+    def res_out(self, i: int) -> int:
+        """Channels leaving Residual level i (train.py:113-121)."""
+        return self.up_c(i) + (self.level_in(i) if self.concat else 0)
 
     def down_c(self, i: int) -> int:  # train.py:181
         if self.down_filters is not None:
@@ -66,7 +96,11 @@ class NetConfig:
         return min(self.pixel_size * 2 ** i // 2, self.max_size)
 
     def up_in(self, i: int) -> int:
-        return self.down_c(i) if i == self.octaves - 1 else self.up_c(i + 1) + self.down_c(i)
+        """Input channels of UpShuffle i: behind a Block (block_depth > 0) the Block's filters, otherwise whatever the
+        inner Residual (or, innermost, the DownShuffle) delivers."""
+        if self.block_depth:
+            return self.down_c(i)
+        return self.down_c(i) if i == self.octaves - 1 else self.res_out(i + 1)
 
     def validate(self) -> None:
         n = self.octaves
@@ -77,28 +111,47 @@ class NetConfig:
         for i in range(n):
             if self.down_c(i) % 64 or self.up_c(i) % 64:
                 raise ValueError("channel counts must be multiples of 64 (tensor-core tile granularity)")
-        if self.down_c(0) % 128:
+        if self.block_depth < 0:
+            raise ValueError("block_depth must be >= 0")
+        if self.block_depth == 0 and self.down_c(0) % 128:
             raise ValueError("down0 filters must be a multiple of 128")
-        if self.up_c(0) not in (64, 128):
-            raise ValueError("the fused Dense(3)+MSE kernel supports 64 or 128 up0 channels")
+        dense_in = self.outer_c() if self.block_depth else self.up_c(0)
+        if dense_in not in (64, 128):
+            raise ValueError("the fused Dense(3)+MSE kernel supports 64 or 128 16-bit input channels")
         # weight gradients put one side's channels on the 128-row M axis of the tensor-core tile
-        pairs = [(self.down_c(i - 1), self.down_c(i)) for i in range(1, n)] + [(self.up_in(i), self.up_c(i)) for i in range(n)]
+        pairs = [(s[2], s[3]) for name, s in variable_specs(self) if name.endswith("kernel") and len(s) == 4 and s[2] != 3]
         for a, b in pairs:
+            if a % 64 or b % 64:
+                raise ValueError("channel counts must be multiples of 64 (tensor-core tile granularity)")
             if a % 128 and b % 128:
                 raise ValueError(f"a conv layer with {a} -> {b} channels has no side that is a multiple of 128 "
                                  "(needed by the weight-gradient kernel)")
 
 
 def variable_specs(cfg: NetConfig) -> List[Tuple[str, Tuple[int, ...]]]:
-    """Keras variable order and layouts of trainer.trainable_variables (train.py:175-204)."""
+    """Variable list of trainer.trainable_variables (train.py:175-204) in construction order, Keras
+    layouts: Conv2D [k,k,Cin,Cout], Conv2DTranspose [4,4,Cout,Cin], Dense [Cin,3].  With block_depth > 0 every Block of
+    the recursion contributes block_depth 3x3 convolutions: block_in (train.py:192), block_down{i} (:185), block_mid
+    (:179), block_up{i} (:187), block_out (:194)."""
     specs: List[Tuple[str, Tuple[int, ...]]] = []
-    cin = 3
-    for i in range(cfg.octaves):
+    n, d = cfg.octaves, cfg.block_depth
+
+    def block(prefix: str, cin: int, filters: int) -> int:
+        for k in range(d):
+            specs.extend([(f"{prefix}/conv{k}/kernel", (3, 3, cin, filters)), (f"{prefix}/conv{k}/bias", (filters,))])
+            cin = filters
+        return cin
+
+    cin = block("block_in", 3, cfg.outer_c())
+    for i in range(n):
         specs += [(f"down{i}/kernel", (4, 4, cin, cfg.down_c(i))), (f"down{i}/bias", (cfg.down_c(i),))]
-        cin = cfg.down_c(i)
-    for i in reversed(range(cfg.octaves)):
-        specs += [(f"up{i}/kernel", (4, 4, cfg.up_c(i), cfg.up_in(i))), (f"up{i}/bias", (cfg.up_c(i),))]
-    specs += [("dense/kernel", (cfg.up_c(0) + 3, 3)), ("dense/bias", (3,))]
+        cin = block(f"block_down{i}", cfg.down_c(i), cfg.down_c(i))
+    cin = block("block_mid", cin, cfg.mid_c())
+    for i in reversed(range(n)):
+        c = block(f"block_up{i}", cin if i == n - 1 else cfg.res_out(i + 1), cfg.down_c(i))
+        specs += [(f"up{i}/kernel", (4, 4, cfg.up_c(i), c)), (f"up{i}/bias", (cfg.up_c(i),))]
+    c = block("block_out", cfg.res_out(0), cfg.outer_c())
+    specs += [("dense/kernel", (c, 3)), ("dense/bias", (3,))]
     return specs
 
 
@@ -112,7 +165,9 @@ def glorot_uniform(shape, generator) -> torch.Tensor:
 def small_names(cfg: NetConfig) -> List[str]:
     """Variables whose gradients are accumulated with atomics by HBM-bound kernels (down0's kernel, every bias, the
     Dense layer): they live together at the head of the flat buffers so that one memset zeroes their gradients."""
-    names = ["down0/kernel"] + [n for n, _ in variable_specs(cfg) if n.endswith("bias") and not n.startswith("dense")]
+    specs = variable_specs(cfg)
+    image_kernels = [n for n, s in specs if n.endswith("kernel") and len(s) == 4 and s[2] == 3]  # CUDA-core convs on the image
+    names = image_kernels + [n for n, _ in specs if n.endswith("bias") and not n.startswith("dense")]
     return names + ["dense/kernel", "dense/bias"]
 
 

@@ -210,6 +210,60 @@ def convT4s2_wgrad(x, dy, dw, ws: Optional[Workspace] = None):
 
 
 @_timed
+def conv3s1_fprop(x, w, bias, y, ws: Workspace, weights_stable: bool = False):
+    """Block's Conv2D(filters, ks, 1, 'same', relu) (train.py:131-139; ks = 3): y = relu(conv2d(x, w, s=1, SAME) + b).
+    w 16-bit [ks,ks,Cin,Cout] (ks = 3 or 1)."""
+    lib = _lib_for(x)
+    B, H, W, Cin = x.shape
+    check(lib.gct2_conv3s1_fprop(ptr(x), _nhwc(x, torch.bfloat16), ptr(w), ptr(bias), ptr(y), _nhwc(y, torch.bfloat16),
+                                 B, H, W, Cin, y.shape[3], w.shape[0], ptr(ws.buf), ws.nbytes, int(weights_stable),
+                                 current_stream()))
+    return y
+
+
+@_timed
+def conv3s1_dgrad(dy, w, dx, act, mask_channels: int, add_old: bool, ws: Workspace, weights_stable: bool = False):
+    """Backward-data of the stride-1 conv: dx = mask(conv2d_backprop_input(dy, w) (+ dx)); channels [0, mask_channels)
+    of dx are ReLU-masked by act, the rest stored raw (a concat buffer's skip slice)."""
+    lib = _lib_for(dy)
+    B, H, W, Cin = dx.shape
+    check(lib.gct2_conv3s1_dgrad(ptr(dy), _nhwc(dy, torch.bfloat16), ptr(w), ptr(dx), _nhwc(dx, torch.bfloat16),
+                                 ptr(act), _nhwc(act, torch.bfloat16), int(mask_channels), int(add_old), B, H, W, Cin,
+                                 dy.shape[3], w.shape[0], ptr(ws.buf), ws.nbytes, int(weights_stable), current_stream()))
+    return dx
+
+
+@_timed
+def conv3s1_wgrad(x, dy, dw, ws: Optional[Workspace] = None):
+    """dw fp32 [ks,ks,Cin,Cout] = conv2d_backprop_filter(x, dy) of the stride-1 conv."""
+    lib = _lib_for(x)
+    B, H, W, Cin = x.shape
+    check(lib.gct2_conv3s1_wgrad(ptr(x), _nhwc(x, torch.bfloat16), ptr(dy), _nhwc(dy, torch.bfloat16), ptr(dw), B, H, W,
+                                 Cin, dy.shape[3], dw.shape[0], ptr(ws.buf) if ws else 0, ws.nbytes if ws else 0,
+                                 current_stream()))
+    return dw
+
+
+@_timed
+def conv3s1_c3_fprop(x, w, bias, y):
+    """The first conv of the outermost Block (block_depth > 0) on the fp32 3-channel image. w fp32 [3,3,3,Cout]."""
+    lib = _lib_for(x)
+    B, H, W, _ = x.shape
+    check(lib.gct2_conv3s1_c3_fprop(ptr(x), ptr(w), ptr(bias), ptr(y), _nhwc(y, torch.bfloat16), B, H, W, y.shape[3],
+                                    current_stream()))
+    return y
+
+
+@_timed
+def conv3s1_c3_wgrad(x, dz, dw, accumulate: bool = False):
+    lib = _lib_for(x)
+    B, H, W, _ = x.shape
+    check(lib.gct2_conv3s1_c3_wgrad(ptr(x), ptr(dz), _nhwc(dz, torch.bfloat16), ptr(dw), B, H, W, dz.shape[3],
+                                    int(accumulate), current_stream()))
+    return dw
+
+
+@_timed
 def bias_grad(dz, db):
     lib = _lib_for(dz)
     ld = _nhwc(dz, torch.bfloat16)
@@ -262,7 +316,7 @@ def target_mode(predict_x: bool = True, predict_scaled_epsilon: bool = False, pr
 def dense_mse(u0, noised, x, wd, bd, loss, inv_n: float, pred=None, du0=None, dwd=None, dbd=None,
               accumulate: bool = False, loss_scale=None, eps=None, t_int=None, mode: int = 0, steps: int = 200):
     """Dense(3) on concat([u0, noised]) (train.py:198-202) fused with the MSE (train.py:262-272) and, when du0 is
-    given, their backward."""
+    given, their backward.  noised=None: the layer reads u0's channels only (behind a Block, or without the skip)."""
     lib = _lib_for(u0)
     backward = du0 is not None
     pixels = u0.shape[0] * u0.shape[1] * u0.shape[2]

@@ -158,6 +158,33 @@ int gct2_convT4s2_dgrad(const uint16_t* dy, int lddy, const uint16_t* w, uint16_
 int gct2_convT4s2_wgrad(const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, int B, int H, int W,
                         int Cin, int Cout, float* ws, size_t ws_bytes, void* stream);
 
+/* train.py:131-139 Block's Conv2D(filters, 3, 1, 'same', relu) -- the dormant block_depth > 0 branch --
+ * on the same tcgen05 implicit-GEMM template as the 4x4 / stride-2 family: a filter tap is a whole-tile shift of one
+ * 4-D TMA box (zero fill at the border = SAME padding).  ks is the kernel side: 3, or 1 for a per-pixel projection
+ * (the Dense(input_channels) of train.py:106-112 is the 1x1 case).  Cin % 64 == 0, Cout % 64 == 0.
+ *   fprop: y = relu(conv2d(x, w[ks,ks,Cin,Cout], s=1, SAME) + b); x, y 16-bit [B,H,W,*] with pixel strides ldx / ldy.
+ *   dgrad: dx = mask(conv2d_backprop_input(dy, w) (+ dx when add_old)): columns [0, mask_channels) are zeroed where the
+ *          saved activation `act` (co-located with dx, stride ldact) is not positive, the rest is stored raw (the skip
+ *          slice of a concat buffer, completed later by the DownShuffle dgrad that also reads it).
+ *   wgrad: dw[ks,ks,Cin,Cout] fp32 = conv2d_backprop_filter(x, dy); overwritten.  One side's channel count must be a
+ *          multiple of 128.
+ * ws / flags as for gct2_conv4s2_fprop. */
+int gct2_conv3s1_fprop(const uint16_t* x, int ldx, const uint16_t* w, const float* bias, uint16_t* y, int ldy, int B,
+                       int H, int W, int Cin, int Cout, int ks, float* ws, size_t ws_bytes, int flags, void* stream);
+int gct2_conv3s1_dgrad(const uint16_t* dy, int lddy, const uint16_t* w, uint16_t* dx, int lddx, const uint16_t* act,
+                       int ldact, int mask_channels, int add_old, int B, int H, int W, int Cin, int Cout, int ks,
+                       float* ws, size_t ws_bytes, int flags, void* stream);
+int gct2_conv3s1_wgrad(const uint16_t* x, int ldx, const uint16_t* dy, int lddy, float* dw, int B, int H, int W,
+                       int Cin, int Cout, int ks, float* ws, size_t ws_bytes, void* stream);
+/* The first convolution of the outermost Block (train.py:192 with block_depth > 0) reads the 3-channel image:
+ * y = relu(conv2d(x, w[3,3,3,Cout], s=1, SAME) + b), x fp32 [B,H,W,3], y 16-bit stride ldy; and its weight gradient
+ * dw fp32 [3,3,3,Cout] from dz (16-bit, already ReLU-masked).  CUDA-core direct convolutions (K = 27).  Cout % 8 == 0.
+ * accumulate == 0: dw is overwritten; != 0: added into (the caller zeroed it). */
+int gct2_conv3s1_c3_fprop(const float* x, const float* w, const float* bias, uint16_t* y, int ldy, int B, int H,
+                          int W, int Cout, void* stream);
+int gct2_conv3s1_c3_wgrad(const float* x, const uint16_t* dz, int lddz, float* dw, int B, int H, int W, int Cout,
+                          int accumulate, void* stream);
+
 /* BiasAddGrad of every conv layer: db[c] = sum over rows of dz[row*ld + c]; dz bf16, db fp32 (overwritten). */
 int gct2_bias_grad(const uint16_t* dz, int ld, long long rows, int C, float* db, void* stream);
 /* The same for n <= 16 tensors in ONE launch (all conv layers of a step).  dz, ld, rows, C, db are HOST arrays of
@@ -171,6 +198,8 @@ int gct2_bias_grad_multi(int n, const uint16_t* const* dz, const int* ld, const 
  * element count) so data-parallel ranks produce partial means.  When backward != 0 also writes
  * du0 = (u0>0) * (dpred . wd^T) (bf16, stride lddu), dwd fp32 [Cu+3,3], dbd fp32 [3], dpred = 2(pred-x)*inv_n.
  * Cu is 64 or 128.  accumulate == 0: loss, dwd, dbd are overwritten; != 0: added into (the caller zeroed them).
+ * noised == NULL: the layer reads the Cu 16-bit channels only (wd, dwd fp32 [Cu,3]) -- Dense(3) behind a Block
+ * (block_depth > 0) or without the concat skip (concat = False), where no image channels reach it.
  * loss_scale: NULL, or the device state of gct2_loss_scale_* (dpred is multiplied by loss_scale[0]; the loss is not).
  * target_mode selects what the loss compares (train.py:238-252): 0 = predict_x (target = x; eps, t_int unused, may be
  * NULL); otherwise the network predicts the noise -- GCT2_TARGET_EPSILON, optionally | GCT2_TARGET_SCALED (target

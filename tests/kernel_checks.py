@@ -70,6 +70,144 @@ def _slice_buf(B, H, W, C, pad_front, pad_back, dev, fill=None):
     return full, full[..., pad_front:pad_front + C]
 
 
+# ---------------------------------------------------------------------------------------------- stride-1 conv (Block)
+def _s1_ref(x, w, ks):
+    """Keras Conv2D(filters, ks, 1, 'same') without bias / activation, NHWC in, NHWC out (train.py:131-139)."""
+    return F.conv2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), None, stride=1, padding=ks // 2).permute(0, 2, 3, 1)
+
+
+def check_conv3_fprop(B, H, Cin, Cout, ks=3, seed=20, pad=64, weights_stable=False):
+    ops = _ops()
+    g = torch.Generator().manual_seed(seed)
+    x = _bf(_rand((B, H, H, Cin), g))
+    w = _bf(_rand((ks, ks, Cin, Cout), g, 1.0 / math.sqrt(ks * ks * Cin)))
+    b = _rand((Cout,), g, 0.1)
+    ref = torch.relu(_s1_ref(x.float(), w.float(), ks) + b)
+    dev = _dev()
+    _, xv = _slice_buf(B, H, H, Cin, pad, 0, dev)
+    xv.copy_(x)
+    yfull, yv = _slice_buf(B, H, H, Cout, 0, pad, dev)
+    ws = ops.Workspace(64 << 20, dev)
+    ops.conv3s1_fprop(xv, w.to(dev), b.to(dev), yv, ws, weights_stable)
+    torch.cuda.synchronize()
+    m = _metrics(f"conv3s1_fprop ks{ks} B{B} H{H} {Cin}->{Cout}", yv, ref, BF16_TOL)
+    m["pad_intact"] = bool((yfull[..., Cout:] == 7.0).all().item()) if pad else True
+    return m
+
+
+def check_conv3_dgrad(B, H, Cin, Cout, ks=3, mask_channels=None, add_old=False, seed=21, pad=64, weights_stable=False):
+    ops = _ops()
+    g = torch.Generator().manual_seed(seed)
+    mask_channels = Cin if mask_channels is None else mask_channels
+    dy = _bf(_rand((B, H, H, Cout), g))
+    w = _bf(_rand((ks, ks, Cin, Cout), g, 1.0 / math.sqrt(ks * ks * Cin)))
+    act = _bf(_rand((B, H, H, Cin), g).clamp_min(0))
+    old = _bf(_rand((B, H, H, Cin), g))
+    xr = torch.zeros(B, H, H, Cin, requires_grad=True)
+    _s1_ref(xr, w.float(), ks).backward(dy.float())
+    ref = xr.grad
+    if add_old:
+        ref = ref + old.float()
+    keep = act.float() > 0
+    keep[..., mask_channels:] = True
+    ref = ref * keep
+    dev = _dev()
+    _, dyv = _slice_buf(B, H, H, Cout, 0, pad, dev)
+    dyv.copy_(dy)
+    dxfull, dxv = _slice_buf(B, H, H, Cin, pad, 0, dev)
+    dxv.copy_(old)
+    _, actv = _slice_buf(B, H, H, Cin, pad, 0, dev)
+    actv.copy_(act)
+    ws = ops.Workspace(64 << 20, dev)
+    ops.conv3s1_dgrad(dyv, w.to(dev), dxv, actv, mask_channels, add_old, ws, weights_stable)
+    torch.cuda.synchronize()
+    m = _metrics(f"conv3s1_dgrad ks{ks} B{B} H{H} {Cin}<-{Cout} mask{mask_channels} add{int(add_old)}", dxv, ref, BF16_TOL)
+    m["pad_intact"] = bool((dxfull[..., :pad] == 7.0).all().item()) if pad else True
+    return m
+
+
+def check_conv3_wgrad(B, H, Cin, Cout, ks=3, seed=22, pad=64):
+    ops = _ops()
+    g = torch.Generator().manual_seed(seed)
+    x = _bf(_rand((B, H, H, Cin), g))
+    dy = _bf(_rand((B, H, H, Cout), g))
+    wr = torch.zeros(ks, ks, Cin, Cout, requires_grad=True)
+    _s1_ref(x.float(), wr, ks).backward(dy.float())
+    dev = _dev()
+    _, xv = _slice_buf(B, H, H, Cin, pad, 0, dev)
+    xv.copy_(x)
+    _, dyv = _slice_buf(B, H, H, Cout, 0, pad, dev)
+    dyv.copy_(dy)
+    dw = torch.full((ks, ks, Cin, Cout), 3.0, device=dev)
+    ws = ops.Workspace(64 << 20, dev)
+    ops.conv3s1_wgrad(xv, dyv, dw, ws)
+    torch.cuda.synchronize()
+    return _metrics(f"conv3s1_wgrad ks{ks} B{B} H{H} {Cin}x{Cout}", dw, wr.grad, F32_TOL * 2)
+
+
+def check_conv3_c3(B=2, H=32, Cout=128, seed=23):
+    """The 3-channel 3x3 / stride-1 conv of the outermost Block: forward and weight gradient."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(seed)
+    x = _rand((B, H, H, 3), g)
+    w = _rand((3, 3, 3, Cout), g, 0.2)
+    b = _rand((Cout,), g, 0.1)
+    dz = _bf(_rand((B, H, H, Cout), g))
+    wr = w.clone().requires_grad_(True)
+    pre = _s1_ref(x, wr, 3) + b
+    pre.backward(dz.float())
+    dev = _dev()
+    yfull, yv = _slice_buf(B, H, H, Cout, 64, 0, dev)
+    ops.conv3s1_c3_fprop(x.to(dev), w.to(dev), b.to(dev), yv)
+    _, dzv = _slice_buf(B, H, H, Cout, 0, 64, dev)
+    dzv.copy_(dz)
+    dw = torch.full((3, 3, 3, Cout), 3.0, device=dev)
+    ops.conv3s1_c3_wgrad(x.to(dev), dzv, dw)
+    dw2 = torch.full((3, 3, 3, Cout), 0.5, device=dev)
+    ops.conv3s1_c3_wgrad(x.to(dev), dzv, dw2, accumulate=True)
+    torch.cuda.synchronize()
+    ms = [_metrics(f"conv3s1_c3_fprop B{B} H{H} 3->{Cout}", yv, torch.relu(pre.detach()), BF16_TOL),
+          _metrics("conv3s1_c3_wgrad", dw, wr.grad, F32_TOL),
+          _metrics("conv3s1_c3_wgrad accumulate", dw2, wr.grad + 0.5, F32_TOL)]
+    worst = dict(max(ms, key=lambda m: m["err"] / m["tol"]))
+    worst["name"] = f"conv3s1_c3 B{B} H{H} Cout{Cout} (worst: {worst['name']})"
+    worst["pad_intact"] = bool((yfull[..., :64] == 7.0).all().item())
+    return worst
+
+
+def check_dense_mse_noimage(B=2, H=32, Cu=128, seed=24):
+    """Dense(3) + MSE on the 16-bit channels only (behind a Block / without the concat skip)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(seed)
+    u0 = _bf(_rand((B, H, H, Cu), g).clamp_min(0))
+    x = _rand((B, H, H, 3), g)
+    wd = _rand((Cu, 3), g, 0.2).requires_grad_(True)
+    bd = _rand((3,), g, 0.1).requires_grad_(True)
+    u0r = u0.float().requires_grad_(True)
+    pred = O.dense(u0r, wd, bd)
+    loss = ((x - pred) ** 2).mean()
+    loss.backward()
+    du0_ref = u0r.grad * (u0.float() > 0)
+    dev = _dev()
+    _, u0v = _slice_buf(B, H, H, Cu, 0, 64, dev)
+    u0v.copy_(u0)
+    du0 = torch.full((B, H, H, Cu), 7.0, dtype=HALF, device=dev)
+    predg = torch.empty(B, H, H, 3, device=dev)
+    lossg = torch.full((1,), 5.0, device=dev)
+    dwd = torch.full((Cu + 3, 3), 3.0, device=dev)   # three guard rows: the kernel must not touch them
+    dbd = torch.full((3,), 3.0, device=dev)
+    ops.dense_mse(u0v, None, x.to(dev), wd.detach().to(dev), bd.detach().to(dev), lossg, 1.0 / (B * H * H * 3),
+                  pred=predg, du0=du0, dwd=dwd, dbd=dbd)
+    torch.cuda.synchronize()
+    ms = [_metrics("dense pred", predg, pred, 2e-5), _metrics("mse loss", lossg, loss.reshape(1), 2e-5),
+          _metrics("dense du0", du0, du0_ref, BF16_TOL), _metrics("dense dW", dwd[:Cu], wd.grad, F32_TOL),
+          _metrics("dense db", dbd, bd.grad, F32_TOL)]
+    worst = dict(max(ms, key=lambda m: m["err"] / m["tol"]))
+    worst["name"] = f"dense_mse without image channels B{B} H{H} Cu{Cu} (worst: {worst['name']})"
+    worst["pad_intact"] = bool((dwd[Cu:] == 3.0).all().item())
+    return worst
+
+
 # ---------------------------------------------------------------------------------------------- conv (down)
 def check_conv_fprop(B, H, Cin, Cout, seed=0, pad=64, weights_stable=False):
     ops = _ops()
@@ -751,6 +889,42 @@ PAIR_CASES = [
     (check_convT_wgrad, dict(B=2, H=16, Cin=256, Cout=256), dict(BN=128, splits=1, pair=1)),
     (check_convT_wgrad, dict(B=2, H=16, Cin=256, Cout=256), dict(BN=256, splits=2, pair=1)),
     (check_convT_wgrad, dict(B=3, H=8, Cin=512, Cout=256), dict(BN=256, splits=1, pair=1)),             # 3 chunks, 4 M tiles
+]
+
+
+# stride-1 index maps (train.py:131-139): every tile width, split-K through L2 / the finishing kernel, 1x1, ragged batch,
+# extents from 4x4 (tile spans several images) to 64x64 (several tiles per image), a concat-style partial mask
+S1_CASES = [
+    (check_conv3_fprop, dict(B=2, H=16, Cin=128, Cout=256), dict(BN=64, splits=1)),
+    (check_conv3_fprop, dict(B=2, H=16, Cin=128, Cout=256), dict(BN=128, splits=2, finish="l2")),
+    (check_conv3_fprop, dict(B=2, H=16, Cin=128, Cout=256), dict(BN=256, splits=1)),
+    (check_conv3_fprop, dict(B=3, H=8, Cin=256, Cout=128), dict(BN=128, splits=4, finish="kernel")),
+    (check_conv3_fprop, dict(B=3, H=4, Cin=512, Cout=512), dict()),
+    (check_conv3_fprop, dict(B=1, H=64, Cin=192, Cout=128), dict()),
+    (check_conv3_fprop, dict(B=2, H=32, Cin=64, Cout=64, weights_stable=True), dict()),
+    (check_conv3_fprop, dict(B=2, H=16, Cin=128, Cout=64, ks=1), dict()),
+    (check_conv3_dgrad, dict(B=2, H=16, Cin=256, Cout=128), dict(BN=64, splits=1)),
+    (check_conv3_dgrad, dict(B=2, H=16, Cin=256, Cout=128, add_old=True), dict(BN=128, splits=2, finish="l2")),
+    (check_conv3_dgrad, dict(B=2, H=16, Cin=256, Cout=128, mask_channels=128), dict(BN=256, splits=1)),
+    (check_conv3_dgrad, dict(B=3, H=8, Cin=128, Cout=256, add_old=True), dict(BN=128, splits=4, finish="kernel")),
+    (check_conv3_dgrad, dict(B=3, H=4, Cin=512, Cout=512), dict()),
+    (check_conv3_dgrad, dict(B=1, H=64, Cin=192, Cout=128, mask_channels=64), dict()),
+    (check_conv3_dgrad, dict(B=2, H=16, Cin=64, Cout=128, ks=1, weights_stable=True), dict()),
+    (check_conv3_wgrad, dict(B=2, H=16, Cin=128, Cout=256), dict(BN=64, splits=1)),
+    (check_conv3_wgrad, dict(B=2, H=16, Cin=128, Cout=256), dict(BN=128, splits=2)),
+    (check_conv3_wgrad, dict(B=2, H=16, Cin=256, Cout=256), dict(BN=256, splits=1)),
+    (check_conv3_wgrad, dict(B=3, H=8, Cin=64, Cout=128), dict()),
+    (check_conv3_wgrad, dict(B=3, H=4, Cin=512, Cout=512), dict()),
+    (check_conv3_wgrad, dict(B=1, H=64, Cin=192, Cout=128), dict()),
+    (check_conv3_wgrad, dict(B=2, H=16, Cin=128, Cout=64, ks=1), dict()),
+]
+
+S1_EW_CASES = [
+    (check_conv3_c3, {}),
+    (check_conv3_c3, dict(B=1, H=16, Cout=64)),
+    (check_conv3_c3, dict(B=3, H=8, Cout=512)),
+    (check_dense_mse_noimage, {}),
+    (check_dense_mse_noimage, dict(B=1, H=16, Cu=64)),
 ]
 
 

@@ -53,6 +53,34 @@ def test_cta_pair_kernels_match_oracle(case):
     assert m.get("pad_intact", True), m
 
 
+# ---- stride-1 convs of Block (train.py:131-139, block_depth > 0)
+@pytest.mark.parametrize("case", K.S1_CASES, ids=_fid)
+def test_stride1_conv_family_matches_oracle(case):
+    fn, kw, force = case
+    m = K.forced(fn, **force, **kw)
+    assert m["err"] <= m["tol"], m
+    assert m.get("pad_intact", True), m
+
+
+@pytest.mark.parametrize("case", K.S1_EW_CASES, ids=_id)
+def test_block_cuda_core_kernels_match_oracle(case):
+    fn, kw = case
+    m = fn(**kw)
+    assert m["err"] <= m["tol"], m
+    assert m.get("pad_intact", True), m
+
+
+def test_stride1_conv_family_fp16_storage():
+    with K.half_format(torch.float16):
+        for fn, kw in ((K.check_conv3_fprop, dict(B=2, H=16, Cin=128, Cout=256)),
+                       (K.check_conv3_dgrad, dict(B=2, H=16, Cin=256, Cout=128, add_old=True)),
+                       (K.check_conv3_wgrad, dict(B=2, H=16, Cin=128, Cout=256)), (K.check_conv3_c3, {}),
+                       (K.check_dense_mse_noimage, {})):
+            m = fn(**kw)
+            assert m["err"] <= m["tol"], m
+            assert m.get("pad_intact", True), m
+
+
 # ---- fp16 storage (train.py:34,43-45: the reference's own reduced-precision mode)
 F16_CASES = [
     (K.check_conv_fprop, dict(B=2, H=16, Cin=128, Cout=256), dict(BN=64, splits=1)),
