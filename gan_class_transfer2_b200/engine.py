@@ -339,6 +339,9 @@ class UNetEngine:
     def __init__(self, cfg: NetConfig, batch: int, device=None, dp: Optional[DataParallel] = None,
                  use_graph: bool = False, share_params_with: Optional["UNetEngine"] = None):
         cfg.validate()
+        if type(self) is UNetEngine and not cfg.fused_default:
+            raise NotImplementedError("UNetEngine implements the reference's default wiring (block_depth = 0, concat = True); "
+                                      "use engine.make_engine / block_engine.BlockUNetEngine for the dormant switches")
         self.cfg = cfg
         self.B = batch
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -357,7 +360,9 @@ class UNetEngine:
         #: dependency -- so no launch that writes them can still be running when a conv launch of the main stream starts
         #: its prologue.  With the optimiser on the main stream (test hook GCT2_OVERLAP=none|wgrad) an Adam launch could
         #: still be draining under programmatic dependent launch, and the flag stays off.
-        self.weights_stable = self.overlap_adam and os.environ.get("GCT2_WEIGHTS_EARLY", "1") != "0"
+        #: Off under mixed precision as well: there the whole update is one launch on the main stream after backward.
+        self.weights_stable = (self.overlap_adam and not cfg.mixed_precision
+                               and os.environ.get("GCT2_WEIGHTS_EARLY", "1") != "0")
         #: Keras-Adam beside backward on disjoint SMs (single GPU): the optimiser is HBM-bound and draws ~98 GB/s per SM,
         #: the tensor-core launches of backward need no HBM bandwidth to speak of -- so the first `adam_wide_buckets`
         #: gradient buckets (backward order: up0 .. up{n-1}, down{n-1} ..) are updated by `adam_sms` SM-exclusive CTAs
@@ -435,6 +440,15 @@ class UNetEngine:
         self.noised = torch.zeros(B, S, S, 3, **f32)
         self.pred = torch.zeros(B, S, S, 3, **f32)
         self.loss = torch.zeros(1, **f32)
+        self.global_batch = B * (dp.world if dp else 1)
+        self._alloc_activations()
+
+    def _alloc_activations(self) -> None:
+        """Activation / gradient buffers of the default wiring (see the module docstring) and everything sized by them."""
+        import os
+        cfg, dev, dp = self.cfg, self.device, self.dp
+        n, S, B = cfg.octaves, cfg.size, self.B
+        bf = dict(dtype=self.half, device=dev)
         self.cat: Dict[int, torch.Tensor] = {}
         self.gcat: Dict[int, torch.Tensor] = {}
         for j in range(1, n):
@@ -449,7 +463,6 @@ class UNetEngine:
         # split-K scratch: one for the main stream (fprop / dgrad partial outputs), one for the side stream (wgrad)
         self.ws = ops.Workspace(max(4 * 4 * biggest, 64 << 20), dev)
         self.ws_w = ops.Workspace(64 << 20, dev)
-        self.global_batch = B * (dp.world if dp else 1)
         # gradient buckets: all-reduce granularity (data parallel) and the granularity at which Adam chases backward
         local_bucket = int(float(os.environ.get("GCT2_BUCKET_MB", "8")) * (1 << 20))  # Adam granularity (8 MB: per layer)
         self._buckets = grad_buckets(cfg, dp.bucket_bytes if dp else local_bucket)
@@ -995,3 +1008,12 @@ class UNetEngine:
         self.loss.zero_()
         self._forward(want_pred=True, backward=False, inv_n=1.0)
         return self.pred
+
+
+def make_engine(cfg: NetConfig, batch: int, **kw) -> UNetEngine:
+    """The engine for a configuration: the tuned UNetEngine for the reference's default wiring, BlockUNetEngine for the
+    dormant switches (block_depth > 0, concat = False)."""
+    if cfg.fused_default:
+        return UNetEngine(cfg, batch, **kw)
+    from .block_engine import BlockUNetEngine
+    return BlockUNetEngine(cfg, batch, **kw)

@@ -17,7 +17,7 @@ from typing import Callable, Dict, Iterable, List, Optional, Sequence
 import torch
 
 from . import ops
-from .engine import DataParallel, NetConfig, UNetEngine, glorot_uniform
+from .engine import DataParallel, NetConfig, UNetEngine, glorot_uniform, make_engine
 
 # ------------------------------------------------------------------------------------------------ train.py:17-36
 size = 256
@@ -173,6 +173,7 @@ class _ConvLayer(Layer):
     """Common part of the two stride-2 4x4 layers: lazily created glorot-uniform kernel in the Keras layout, zero bias
     (train.py:149,162), bf16 shadow for the tensor cores."""
     transposed = False
+    ksize = 4
 
     def __init__(self, filters):
         super().__init__()
@@ -189,7 +190,8 @@ class _ConvLayer(Layer):
 
     def build(self, input_shape):
         cin = input_shape[-1]
-        shape = (4, 4, self.filters, cin) if self.transposed else (4, 4, cin, self.filters)
+        k = self.ksize
+        shape = (k, k, self.filters, cin) if self.transposed else (k, k, cin, self.filters)
         if self.kernel is None:
             self.kernel = glorot_uniform(shape, _next_init_generator()).cuda()
             self.bias = torch.zeros(self.filters, device="cuda")
@@ -231,22 +233,37 @@ class DownShuffle(_ConvLayer):
                                  self._workspace(4 * y.numel(), input.device))
 
 
+class Conv3x3(_ConvLayer):
+    """train.py:132-137: Conv2D(filters, 3, 1, 'same', glorot_uniform, relu) -- the layer a Block stacks."""
+    ksize = 3
+
+    def call(self, input):
+        B, H, W, C = input.shape
+        y = torch.empty(B, H, W, self.filters, dtype=preferred_type(), device=input.device)
+        if C == 3:
+            return ops.conv3s1_c3_fprop(input.float().contiguous(), self.kernel, self.bias, y)
+        return ops.conv3s1_fprop(_check_act(input), self._shadow(), self.bias, y, self._workspace(4 * y.numel(), input.device))
+
+
 class Block(Layer):
     """train.py:123-143: block_depth x Conv2D(filters, 3, 1, 'same', relu).  block_depth is 0 in the reference
-    (train.py:20), which makes this an empty Sequential: identity, no variables."""
+    (train.py:20), which makes this an empty Sequential: identity, no variables.  The depth is read when the Block is
+    constructed (inside a Denoiser the engine runs the convolutions; standalone the layers run one launch each)."""
 
     def __init__(self, filters):
         super().__init__()
         self.filters = filters
+        self.depth = int(block_depth)
+        self.module = Sequential([Conv3x3(filters) for _ in range(self.depth)])
 
     def build(self, input_shape):
-        if block_depth != 0:
-            raise NotImplementedError("block_depth > 0 (3x3 stride-1 convolutions) is outside the accelerated path; "
-                                      "the reference default is block_depth = 0 (train.py:20)")
-        self.module = Sequential([])
+        pass  # the convolutions build themselves at first use (their input channels are inferred, train.py:139)
 
     def call(self, input):
         return self.module(input)
+
+    def sublayers(self):
+        return [self.module]
 
 
 class Residual(Layer):
@@ -364,9 +381,9 @@ class Denoiser(Model):
     def _walk(self):
         """Pattern-matches the layer tree against the one shape the fused engine implements and returns
         (down layers outer->inner, up layers outer->inner, dense)."""
-        if residual or not concat:
-            raise NotImplementedError("the fused engine implements the reference's default skip wiring only "
-                                      "(residual=False, concat=True, train.py:26-27,113-119)")
+        if residual:
+            raise NotImplementedError("residual=True (the Dense projection branch, train.py:106-112) is not implemented; "
+                                      "the reference default is residual=False")
         outer = self.middle.layers
         if not (len(outer) == 4 and isinstance(outer[0], Block) and isinstance(outer[1], Residual)
                 and isinstance(outer[2], Block) and isinstance(outer[3], Dense) and outer[3].units == 3):
@@ -386,6 +403,18 @@ class Denoiser(Model):
             raise NotImplementedError("the innermost module must be a Block (train.py:179)")
         return downs, ups, outer[3]
 
+    def _blocks(self) -> Dict[str, Block]:
+        """Every Block of the recursion by the variable prefix the engine uses for it."""
+        outer = self.middle.layers
+        blocks = {"block_in": outer[0], "block_out": outer[2]}
+        node, i = outer[1], 0
+        while isinstance(node, Residual):
+            seq = node.module.layers
+            blocks[f"block_down{i}"], blocks[f"block_up{i}"] = seq[1], seq[3]
+            node, i = seq[2], i + 1
+        blocks["block_mid"] = node
+        return blocks
+
     def net_config(self, image_size: int) -> NetConfig:
         downs, ups, _ = self._walk()
         opt = self._optimizer if self._optimizer is not None else optimizer
@@ -394,6 +423,19 @@ class Denoiser(Model):
             extra = dict(loss_scale_init=opt.initial_scale, loss_scale_growth=opt.dynamic_growth_steps)
             opt = opt.inner_optimizer
         base_lr, warm = opt.schedule()
+        blocks = self._blocks()
+        depths = {b.depth for b in blocks.values()}
+        if len(depths) != 1:
+            raise NotImplementedError("all Blocks of a Denoiser must have the same depth (train.py:20 is one global)")
+        depth = depths.pop()
+        if depth:
+            for i, d in enumerate(downs):
+                if blocks[f"block_down{i}"].filters != d.filters or blocks[f"block_up{i}"].filters != d.filters:
+                    raise NotImplementedError("the Blocks of a level must have the level's DownShuffle filters (train.py:184-187)")
+            if blocks["block_in"].filters != blocks["block_out"].filters:
+                raise NotImplementedError("the two outermost Blocks must have equal filters (train.py:192,194)")
+            extra.update(block_depth=depth, mid_filters=blocks["block_mid"].filters, outer_filters=blocks["block_in"].filters)
+        extra.update(concat=bool(concat))
         return NetConfig(size=image_size, pixel_size=pixel_size, max_size=max_size, octaves=len(downs), steps=steps,
                          warm_up=warm, base_lr=base_lr, beta1=opt.beta_1, beta2=opt.beta_2,
                          epsilon=opt.epsilon, down_filters=tuple(d.filters for d in downs),
@@ -421,8 +463,8 @@ class Denoiser(Model):
         key = (batch, image_size)
         if key not in self._engines:
             first = next(iter(self._engines.values()), None)
-            eng = UNetEngine(self.net_config(image_size), batch, dp=data_parallel, use_graph=use_cuda_graph,
-                             share_params_with=first)
+            eng = make_engine(self.net_config(image_size), batch, dp=data_parallel, use_graph=use_cuda_graph,
+                              share_params_with=first)
             if first is None:
                 if self._pending_weights is not None:
                     eng.load_weights(self._pending_weights)
@@ -456,6 +498,11 @@ class Denoiser(Model):
             layer.built = True
         dense.kernel, dense.bias = eng.view(eng.w, "dense/kernel"), eng.view(eng.w, "dense/bias")
         dense.built = True
+        for prefix, block in self._blocks().items():
+            for k, conv in enumerate(block.module.layers):
+                conv.kernel, conv.bias = eng.view(eng.w, f"{prefix}/conv{k}/kernel"), eng.view(eng.w, f"{prefix}/conv{k}/bias")
+                conv.built = True
+            block.built = True
 
     # -- Keras-like surface ------------------------------------------------------------------------------------
     def set_seed(self, seed: int) -> None:

@@ -54,6 +54,24 @@ class Config:
     prediction_weighting: bool = False
     ordinary_differential_equation: bool = False
     test_step: int = 25   # train.py:95
+    # train.py:26-27: how Residual joins its module and its input (reference: residual=False, concat=True)
+    residual: bool = False
+    concat: bool = True
+
+    def mid_filters(self) -> int:  # train.py:179
+        return min(self.pixel_size * 2 ** self.octaves, self.max_size)
+
+    def level_in(self, i: int) -> int:
+        """Channels of the tensor entering Residual level i."""
+        if i == 0:
+            return self.pixel_size if self.block_depth else 3
+        return self.down_filters(i - 1)
+
+    def res_out(self, i: int) -> int:
+        """Channels leaving Residual level i (train.py:110-121)."""
+        if self.residual:
+            return self.level_in(i)
+        return self.up_filters(i) + (self.level_in(i) if self.concat else 0)
 
     def down_filters(self, i: int) -> int:  # train.py:181
         return min(self.pixel_size * 2 ** i, self.max_size)
@@ -92,29 +110,40 @@ class WarmUp:
 
 # --------------------------------------------------------------------------------------------- variables
 def variable_specs(cfg: Config = DEFAULT) -> List[Tuple[str, Tuple[int, ...]]]:
-    """Keras variable order and layouts: down0..down{n-1}, up{n-1}..up0, dense; kernel then bias.
+    """Variable list in construction order (train.py:175-204), Keras layouts: Conv2D.kernel
+    [k,k,Cin,Cout]; Conv2DTranspose.kernel [4,4,Cout,Cin]; Dense.kernel [Cin,Cout]; kernel then bias.
 
-    Conv2D.kernel [4,4,Cin,Cout]; Conv2DTranspose.kernel [4,4,Cout,Cin]; Dense.kernel [Cin,3].
-    """
+    Reference defaults (block_depth=0, residual=False, concat=True): down0..down{n-1}, up{n-1}..up0, dense.  A Block
+    (train.py:123-143) adds block_depth Conv2D(filters, 3, 1, 'same') layers: block_in (:192), block_down{i} (:185),
+    block_mid (:179), block_up{i} (:187), block_out (:194).  residual=True adds res{i}/dense/kernel, the bias-free
+    Dense(input_channels) of train.py:106-108."""
     specs: List[Tuple[str, Tuple[int, ...]]] = []
-    cin = 3
-    skip_c = []  # channels of the tensor entering Residual_i (the skip)
-    for i in range(cfg.octaves):
+    n, d = cfg.octaves, cfg.block_depth
+
+    def block(prefix, cin, filters):
+        for k in range(d):
+            specs.append((f"{prefix}/conv{k}/kernel", (3, 3, cin, filters)))
+            specs.append((f"{prefix}/conv{k}/bias", (filters,)))
+            cin = filters
+        return cin
+
+    cin = block("block_in", 3, cfg.pixel_size)
+    for i in range(n):
         co = cfg.down_filters(i)
         specs.append((f"down{i}/kernel", (4, 4, cin, co)))
         specs.append((f"down{i}/bias", (co,)))
-        skip_c.append(cin)
-        cin = co
-    # innermost: up_{n-1} consumes down_{n-1}'s output; up_i (i < n-1) consumes concat[up_{i+1}, down_i]
-    for i in reversed(range(cfg.octaves)):
-        if i == cfg.octaves - 1:
-            ci = cfg.down_filters(i)
-        else:
-            ci = cfg.up_filters(i + 1) + cfg.down_filters(i)
+        cin = block(f"block_down{i}", co, co)
+    cin = block("block_mid", cin, cfg.mid_filters())
+    # innermost: up_{n-1} consumes the innermost Block's output; up_i (i < n-1) what Residual_{i+1} returns
+    for i in reversed(range(n)):
+        ci = block(f"block_up{i}", cin if i == n - 1 else cfg.res_out(i + 1), cfg.down_filters(i))
         co = cfg.up_filters(i)
         specs.append((f"up{i}/kernel", (4, 4, co, ci)))
         specs.append((f"up{i}/bias", (co,)))
-    specs.append(("dense/kernel", (cfg.up_filters(0) + 3, 3)))
+        if cfg.residual:
+            specs.append((f"res{i}/dense/kernel", (co, cfg.level_in(i))))
+    c = block("block_out", cfg.res_out(0), cfg.pixel_size)
+    specs.append(("dense/kernel", (c, 3)))
     specs.append(("dense/bias", (3,)))
     return specs
 
@@ -257,6 +286,12 @@ def up_shuffle(x_nhwc, kernel_hwoi, bias):
     return _nhwc(F.relu(F.conv_transpose2d(_nchw(x_nhwc), w, bias, stride=2, padding=1)))
 
 
+def conv3x3(x_nhwc, kernel_hwio, bias):
+    """train.py:132-137: relu(Conv2D(filters, 3, 1, 'same')(x)); SAME for k3/s1 is pad (1,1)."""
+    w = kernel_hwio.permute(3, 2, 0, 1)
+    return _nhwc(F.relu(F.conv2d(_nchw(x_nhwc), w, bias, stride=1, padding=1)))
+
+
 def dense(x_nhwc, kernel, bias):
     """train.py:198-202: Keras Dense contracts the last axis only; no activation."""
     return x_nhwc @ kernel + bias
@@ -300,8 +335,10 @@ def _rounding(emulate_bf16):
 
 
 def denoiser_forward(weights: Dict[str, torch.Tensor], x_nhwc: torch.Tensor, cfg: Config = DEFAULT,
-                     taps: Optional[Dict[str, torch.Tensor]] = None, emulate_bf16: bool = False) -> torch.Tensor:
-    """Denoiser.call (train.py:206-215): `t` is ignored by the reference; Block is identity at block_depth=0.
+                     taps: Optional[Dict[str, torch.Tensor]] = None, emulate_bf16: bool = False,
+                     force: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+    """Denoiser.call (train.py:206-215): `t` is ignored by the reference; Block is identity at block_depth=0 (the
+    reference's default) and a stack of 3x3 convolutions otherwise.
 
     Residual_i(h) = concat([Up_i(Residual_{i+1}(Down_i(h))), h], -1) with the module output FIRST (train.py:113-119).
     `taps`, when given, collects every layer output (post-ReLU) by name.
@@ -309,22 +346,61 @@ def denoiser_forward(weights: Dict[str, torch.Tensor], x_nhwc: torch.Tensor, cfg
     emulate_bf16=False is the reference's arithmetic (fp32).  emulate_bf16=True additionally rounds to bf16 exactly
     where the CUDA path stores bf16 (tensor-core kernels' weights, every layer output and its gradient), which turns
     the loose fp32-vs-bf16 comparison into a tight one for the tests; it is not the reference's arithmetic.
+
+    `force` (teacher forcing, a test aid): {layer name: tensor} -- the named layers' outputs are REPLACED by the given
+    values (gradients still flow through the layer as computed), so that a backward pass can be compared with another
+    implementation's on exactly the same activations and ReLU masks instead of through the mask flips that accumulated
+    forward rounding causes.
     """
-    rnd = _rounding(emulate_bf16)
+    rnd0 = _rounding(emulate_bf16)
+    current = [None]
+
+    def rnd(t):
+        """Rounding of a layer output; under teacher forcing the output then takes the forced value."""
+        t = rnd0(t)
+        name, current[0] = current[0], None
+        if force is not None and name is not None and name in force:
+            t = t + (force[name].to(t.dtype) - t).detach()
+        return t
+
+    def named(name):
+        current[0] = name
+
+    def kern(name, cin):
+        # the CUDA path runs the convolutions that read the 3-channel image on CUDA cores with the fp32 kernel
+        return weights[name] if cin == 3 else rnd0(weights[name])
+
+    def block(prefix: str, h):
+        """train.py:123-143: block_depth x Conv2D(filters, 3, 1, 'same', relu)."""
+        for k in range(cfg.block_depth):
+            name = f"{prefix}/conv{k}"
+            named(name)
+            h = rnd(conv3x3(h, kern(f"{name}/kernel", h.shape[-1]), weights[f"{name}/bias"]))
+            if taps is not None:
+                taps[name] = h
+        return h
 
     def residual(i: int, h):
-        kd = weights[f"down{i}/kernel"] if i == 0 else rnd(weights[f"down{i}/kernel"])  # down0 runs in fp32
-        d = rnd(down_shuffle(h, kd, weights[f"down{i}/bias"]))
+        """train.py:97-121 around Sequential[DownShuffle, Block, middle, Block, UpShuffle] (train.py:182-190)."""
+        named(f"down{i}")
+        d = rnd(down_shuffle(h, kern(f"down{i}/kernel", h.shape[-1]), weights[f"down{i}/bias"]))
         if taps is not None:
             taps[f"down{i}"] = d
-        inner = residual(i + 1, d) if i + 1 < cfg.octaves else d
-        u = rnd(up_shuffle(inner, rnd(weights[f"up{i}/kernel"]), weights[f"up{i}/bias"]))
+        d = block(f"block_down{i}", d)
+        inner = residual(i + 1, d) if i + 1 < cfg.octaves else block("block_mid", d)
+        inner = block(f"block_up{i}", inner)
+        named(f"up{i}")
+        u = rnd(up_shuffle(inner, rnd0(weights[f"up{i}/kernel"]), weights[f"up{i}/bias"]))
         if taps is not None:
             taps[f"up{i}"] = u
-        return torch.cat([u, h], dim=-1)
+        if cfg.residual:                    # :110-111 input + Dense(input_channels, use_bias=False)(module(input))
+            return h + u @ weights[f"res{i}/dense/kernel"]
+        if cfg.concat:                      # :112-119 module output FIRST
+            return torch.cat([u, h], dim=-1)
+        return u                            # :120-121
 
-    cat0 = residual(0, x_nhwc)
-    pred = dense(cat0, weights["dense/kernel"], weights["dense/bias"])
+    top = block("block_out", residual(0, block("block_in", x_nhwc)))
+    pred = dense(top, weights["dense/kernel"], weights["dense/bias"])
     if taps is not None:
         taps["pred"] = pred
     return pred
@@ -356,7 +432,7 @@ def loss_target(x, t_int, eps, pred, cfg: Config = DEFAULT):
 
 
 def trainer_loss(weights, x, t_int, eps, cfg: Config = DEFAULT, taps=None, global_elems: Optional[int] = None,
-                 emulate_bf16: bool = False):
+                 emulate_bf16: bool = False, force=None):
     """Trainer.call (train.py:223-272) -> scalar mean squared error between the target selected by the objective
     switches (train.py:238-252; default predict_x: the clean image) and the prediction.
 
@@ -364,7 +440,7 @@ def trainer_loss(weights, x, t_int, eps, cfg: Config = DEFAULT, taps=None, globa
     noised = noise_images(x, t_int, eps, cfg)
     if taps is not None:
         taps["noised"] = noised
-    pred = denoiser_forward(weights, noised, cfg, taps, emulate_bf16)
+    pred = denoiser_forward(weights, noised, cfg, taps, emulate_bf16, force)
     target, pred = loss_target(x, t_int, eps, pred, cfg)
     sq = (target.to(torch.float32) - pred.to(torch.float32)) ** 2
     if global_elems is None:
@@ -378,7 +454,7 @@ def identity(y_true, y_pred):
 
 
 def loss_and_grads(weights, x, t_int, eps, cfg: Config = DEFAULT, want_taps: bool = False,
-                   global_elems: Optional[int] = None, emulate_bf16=False, loss_scale: Optional[float] = None):
+                   global_elems: Optional[int] = None, emulate_bf16=False, loss_scale: Optional[float] = None, force=None):
     """One forward+backward (what Keras train_step's GradientTape does, train.py:516): returns
     (loss, {name: grad}, taps) where taps also carries d(loss)/d(layer output) under 'd<name>' when requested.
 
@@ -387,7 +463,7 @@ def loss_and_grads(weights, x, t_int, eps, cfg: Config = DEFAULT, want_taps: boo
     gradients (and 'd<name>' taps) have the scale divided out again; non-finite values stay non-finite."""
     ws = {k: v.detach().clone().requires_grad_(True) for k, v in weights.items()}
     taps: Optional[Dict[str, torch.Tensor]] = {} if want_taps else None
-    loss = identity(None, trainer_loss(ws, x, t_int, eps, cfg, taps, global_elems, emulate_bf16))
+    loss = identity(None, trainer_loss(ws, x, t_int, eps, cfg, taps, global_elems, emulate_bf16, force))
     if want_taps:
         for v in taps.values():
             if v.requires_grad:
@@ -491,25 +567,33 @@ def bf16_round(t: torch.Tensor) -> torch.Tensor:
 
 
 def flops_per_image(cfg: Config = DEFAULT) -> Dict[str, float]:
-    """FLOP convention of SURVEY.md 8(a): conv 2*Ho*Wo*16*Cin*Cout, convT 2*Hin*Win*16*Cin*Cout, dense 2*H*W*Cin*Cout."""
+    """FLOP convention of SURVEY.md 8(a): conv 2*Ho*Wo*k*k*Cin*Cout, convT 2*Hin*Win*16*Cin*Cout, dense 2*H*W*Cin*Cout."""
     fwd = 0.0
-    down0 = 0.0
-    h = cfg.size
+    no_dgrad = 0.0  # layers reading the image have no data gradient
+    n = cfg.octaves
+
+    def extent(name: str) -> int:
+        """Output extent of a Conv2D / input extent of a Conv2DTranspose / extent of a Dense."""
+        head = name.split("/")[0]
+        if head in ("block_in", "block_out", "dense"):
+            return cfg.size
+        if head == "block_mid":
+            return cfg.size >> n
+        digits = int("".join(ch for ch in head if ch.isdigit()))
+        if head.startswith("res"):
+            return cfg.size >> digits
+        return cfg.size >> (digits + 1)
+
     for name, shape in variable_specs(cfg):
         if not name.endswith("kernel"):
             continue
-        if name.startswith("down"):
-            i = int(name[4:name.index("/")])
-            ho = cfg.size // 2 ** (i + 1)
-            f = 2.0 * ho * ho * 16 * shape[2] * shape[3]
-            if i == 0:
-                down0 = f
-        elif name.startswith("up"):
-            i = int(name[2:name.index("/")])
-            hin = cfg.size // 2 ** (i + 1)
-            f = 2.0 * hin * hin * 16 * shape[2] * shape[3]
+        h = extent(name)
+        if len(shape) == 4:
+            f = 2.0 * h * h * shape[0] * shape[1] * shape[2] * shape[3]
+            if shape[2] == 3 and not name.startswith("up"):
+                no_dgrad += f
         else:
             f = 2.0 * h * h * shape[0] * shape[1]
         fwd += f
-    bwd = 2 * fwd - down0
+    bwd = 2 * fwd - no_dgrad
     return {"fwd": fwd, "bwd": bwd, "step": fwd + bwd}

@@ -69,17 +69,42 @@ def test_unsupported_structures_are_rejected():
         E.NetConfig(size=64, octaves=2, pixel_size=96).validate()
 
 
-def test_disabled_skip_wirings_are_rejected_by_the_fused_engine():
-    """residual=True / concat=False (train.py:26-27,106-121) change the network's wiring; the fused engine implements the
-    reference's default only and must say so instead of silently running the concat network."""
-    for flag, val in (("concat", False), ("residual", True)):
-        old = getattr(T, flag)
-        setattr(T, flag, val)
-        try:
+def test_wiring_switches_reach_the_engine_config():
+    """train.py:20,26-27: block_depth and concat change what Denoiser.__init__ builds; both are run by the layer-list
+    engine (block_engine.BlockUNetEngine) and must arrive in the engine's configuration with the oracle's variable list.
+    residual=True (train.py:106-112) is not implemented and must say so instead of silently running another network."""
+    import dataclasses
+    saved = {k: getattr(T, k) for k in ("concat", "residual", "block_depth", "octaves", "max_size")}
+    try:
+        T.octaves, T.max_size = 4, 256
+        for kw in (dict(block_depth=1), dict(block_depth=2, concat=False), dict(concat=False)):
+            T.block_depth, T.concat = kw.get("block_depth", 0), kw.get("concat", True)
+            cfg = T.Denoiser().net_config(64)
+            assert (cfg.block_depth, cfg.concat) == (T.block_depth, T.concat) and not cfg.fused_default
+            cfg.validate()
+            ocfg = dataclasses.replace(O.TINY, **kw)
+            assert E.variable_specs(cfg) == O.variable_specs(ocfg)
+            assert sum(cnt for _, cnt in E.param_offsets(cfg)[0].values()) == O.param_count(ocfg)
             with pytest.raises(NotImplementedError):
-                T.Denoiser().net_config(256)
-        finally:
-            setattr(T, flag, old)
+                E.UNetEngine(cfg, 1)  # the tuned engine is for the default wiring only
+        T.block_depth, T.concat, T.residual = 0, True, True
+        with pytest.raises(NotImplementedError):
+            T.Denoiser().net_config(64)
+    finally:
+        for k, v in saved.items():
+            setattr(T, k, v)
+    assert T.Denoiser().net_config(256).fused_default
+
+
+def test_small_region_holds_everything_accumulated_with_atomics():
+    cfg = E.NetConfig(size=64, pixel_size=128, max_size=256, octaves=4, block_depth=2)
+    names = E.small_names(cfg)
+    assert names[0] == "block_in/conv0/kernel" and "down0/kernel" not in names  # down0 reads 128 channels here
+    assert all(n.endswith("bias") or n.startswith("dense") or n == names[0] for n in names)
+    offs, total = E.param_offsets(cfg)
+    small = E.small_region(cfg)
+    assert all((off < small) == (name in names) for name, (off, _) in offs.items())
+    assert small % 64 == 0 and total % 4 == 0
 
 
 def test_compile_hands_the_optimizer_to_the_denoiser():

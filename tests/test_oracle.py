@@ -279,3 +279,75 @@ def test_stated_gradient_tolerances_bracket_the_inherent_bf16_error():
             if E.level_of(k) >= 2:
                 worst_ratio = max(worst_ratio, tol / inherent)
     assert worst_ratio < 4.0, worst_ratio
+
+
+# ---- dormant switches of train.py:20,26-27 (block_depth, residual, concat) as restated by the oracle
+def test_block_conv_is_same_padded_3x3_correlation():
+    """Block's Conv2D(filters, 3, 1, 'same', relu) (train.py:131-139) against the definition written out with shifts:
+    out[y, x] = relu(b + sum_{ky,kx} in[y + ky - 1, x + kx - 1] @ W[ky, kx]), zeros outside the image."""
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 5, 6, 3, generator=g)
+    w = torch.randn(3, 3, 3, 4, generator=g)
+    b = torch.randn(4, generator=g)
+    ref = torch.zeros(2, 5, 6, 4) + b
+    xp = torch.nn.functional.pad(x, (0, 0, 1, 1, 1, 1))
+    for ky in range(3):
+        for kx in range(3):
+            ref = ref + xp[:, ky:ky + 5, kx:kx + 6, :] @ w[ky, kx]
+    assert torch.allclose(O.conv3x3(x, w, b), torch.relu(ref), atol=1e-5)
+
+
+def test_wiring_variants_shapes_and_counts():
+    import dataclasses
+    base = O.Config(size=32, pixel_size=8, max_size=16, octaves=2)
+    x = torch.zeros(1, 32, 32, 3)
+    # 2 octaves: 4 conv layers + Dense = 10 variables; 7 Blocks (in, down0, down1, mid, up1, up0, out); 2 projections
+    for kw, n_vars in ((dict(block_depth=1), 10 + 2 * 7), (dict(block_depth=2, concat=False), 10 + 4 * 7),
+                       (dict(residual=True), 10 + 2), (dict(concat=False), 10)):
+        cfg = dataclasses.replace(base, **kw)
+        specs = O.variable_specs(cfg)
+        assert len(specs) == n_vars, (kw, len(specs))
+        w = O.glorot_init(cfg, 0)
+        taps = {}
+        pred = O.denoiser_forward(w, x, cfg, taps)
+        assert pred.shape == (1, 32, 32, 3)
+        for i in range(cfg.octaves):
+            assert taps[f"down{i}"].shape[-1] == cfg.down_filters(i) and taps[f"up{i}"].shape[-1] == cfg.up_filters(i)
+        # every kernel's input-channel count is what the walk produces (a mismatch would have raised inside conv2d)
+        assert O.param_count(cfg) == sum(v.numel() for v in w.values())
+    # the residual branch (train.py:110-111) keeps the channel count of its input: 3 at the outermost level
+    cfg = dataclasses.replace(base, residual=True)
+    assert dict(O.variable_specs(cfg))["res0/dense/kernel"] == (cfg.up_filters(0), 3)
+    assert dict(O.variable_specs(cfg))["dense/kernel"] == (3, 3)
+    # block_depth = 0 and concat = True are the published 41 691 660 parameters
+    assert O.param_count(O.DEFAULT) == 41_691_660
+
+
+def test_finite_difference_gradients_with_blocks():
+    import dataclasses
+    cfg = O.Config(size=16, pixel_size=4, max_size=16, octaves=2, block_depth=1)
+    for cfg in (cfg, dataclasses.replace(cfg, concat=False), dataclasses.replace(cfg, residual=True)):
+        w = {k: v.double() for k, v in O.glorot_init(cfg, 3).items()}
+        for k in w:
+            if k.endswith("bias"):
+                w[k] = w[k] + 0.05
+        x, t, e = O.synthetic_batch(cfg, 2, 4)
+        x, e = x.double(), e.double()
+
+        def loss_fn(ws):
+            return ((x - O.denoiser_forward(ws, O.noise_images(x, t, e, cfg), cfg)) ** 2).mean()
+
+        ws = {k: v.clone().requires_grad_(True) for k, v in w.items()}
+        loss_fn(ws).backward()
+        g = torch.Generator().manual_seed(5)
+        names = ["block_in/conv0/kernel", "block_down1/conv0/kernel", "block_mid/conv0/bias", "block_up0/conv0/kernel",
+                 "block_out/conv0/kernel", "down0/kernel", "up1/kernel"] + (["res1/dense/kernel"] if cfg.residual else [])
+        for name in names:
+            d = torch.randn(w[name].shape, generator=g, dtype=torch.float64)
+            h = 1e-6
+            wp, wm = dict(w), dict(w)
+            wp[name] = w[name] + h * d
+            wm[name] = w[name] - h * d
+            fd = (loss_fn(wp) - loss_fn(wm)) / (2 * h)
+            an = (ws[name].grad * d).sum()
+            assert abs(fd - an) <= 1e-5 * max(1.0, abs(an)), (name, float(fd), float(an))

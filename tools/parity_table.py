@@ -1,7 +1,10 @@
 """Prints the whole-step parity table (CUDA engine vs the CPU oracle, both flavours) for a configuration: the measured
 relative L2 errors behind the tolerances stated in tests/engine_checks.py.
 
-    python tools/parity_table.py --config default --batch 1 [--mixed-precision]
+    python tools/parity_table.py --config default --batch 1 [--mixed-precision] [--block-depth D] [--no-concat] [--forced]
+
+--forced prints the teacher-forced table instead (tests/engine_checks.py:teacher_forced_parity): the backward pass
+against the oracle running on the engine's own activations.
 """
 import argparse
 import json
@@ -18,17 +21,28 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--mixed-precision", action="store_true")
+    ap.add_argument("--block-depth", type=int, default=0)
+    ap.add_argument("--no-concat", action="store_true")
+    ap.add_argument("--forced", action="store_true")
     a = ap.parse_args()
+    import dataclasses
     from oracle import oracle as O
     from tests import engine_checks as E
     cfg = {"default": O.DEFAULT, "tiny": O.TINY, "wide": O.WIDE}[a.config]
+    cfg = dataclasses.replace(cfg, block_depth=a.block_depth, concat=not a.no_concat)
+    tag = {"config": a.config, "batch": a.batch, "mp": a.mixed_precision, "block_depth": a.block_depth, "concat": cfg.concat}
+    if a.forced:
+        res, _ = E.teacher_forced_parity(cfg, a.batch, a.seed)
+        for name, err in res.items():
+            print(json.dumps({**tag, "forced": True, "quantity": name, "err": round(err, 6), "tol": E.TOL_FORCED}), flush=True)
+        return
     res = E.step_parity(cfg, a.batch, a.seed, a.mixed_precision)
     for name, errs in res.items():
         lim = {}
-        if name.startswith("grad/") or name.startswith(("act/ddown", "act/dup")):
+        if name.startswith("grad/") or name.startswith(("act/ddown", "act/dup", "act/dblock")):
             key = name[5:]
             lim = {"emu": E.tol_emu_grad(cfg, key, a.mixed_precision), "f32": E.tol_f32_grad(cfg, key, a.mixed_precision)}
-        print(json.dumps({"config": a.config, "batch": a.batch, "mp": a.mixed_precision, "quantity": name,
+        print(json.dumps({**tag, "quantity": name,
                           **{k: round(v, 5) for k, v in errs.items()},
                           **{"tol_" + k: v for k, v in lim.items()}}), flush=True)
 
