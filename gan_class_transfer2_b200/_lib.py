@@ -65,6 +65,8 @@ _PROTOS = {
     "gct2_convT4s2_wgrad": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "gct2_conv3s1_fprop": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_size_t,
                                    c_int, _P]),
+    "gct2_conv3s1_fprop_add": (c_int, [_P, c_int, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                       _P]),
     "gct2_conv3s1_dgrad": (c_int, [_P, c_int, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_int, _P, c_size_t, c_int, _P]),
     "gct2_conv3s1_wgrad": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
@@ -74,6 +76,8 @@ _PROTOS = {
     "gct2_bias_grad_multi": (c_int, [c_int, _P, _P, _P, _P, _P, c_int, _P]),
     "gct2_dense_mse": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, c_longlong, c_int, c_float,
                                c_int, c_int, _P, _P, _P, c_longlong, c_int, c_int, _P]),
+    "gct2_res0_compose": (c_int, [_P, _P, _P, c_int, _P]),
+    "gct2_res0_decompose": (c_int, [_P, _P, _P, _P, _P, c_int, _P]),
     "gct2_adam_keras": (c_int, [_P, _P, _P, _P, _P, c_longlong, _P, _P, c_float, c_int, c_float, c_float, c_float,
                                 c_float, _P]),
     "gct2_adam_prepare": (c_int, [_P, _P, c_float, c_int, c_float, c_float, _P]),

@@ -1,7 +1,9 @@
 """Step engine for the reference's dormant wiring switches.
 
-``train.py:20`` ``block_depth`` and ``train.py:27`` ``concat`` change what ``Denoiser.__init__`` (train.py:175-204)
-builds: with ``block_depth = d > 0`` every ``Block`` of the recursion is a stack of d ``Conv2D(filters, 3, 1, 'same',
+``train.py:20`` ``block_depth``, ``train.py:26`` ``residual`` and ``train.py:27`` ``concat`` change what
+``Denoiser.__init__`` (train.py:175-204) builds: with ``residual = True`` a ``Residual`` returns ``input +
+Dense(input_channels, use_bias=False)(module(input))`` (train.py:106-111; a 1x1 case of the stride-1 map with the add fused
+into its epilogue, and at the image level -- 3 channels -- folded into the Dense(3) kernel); with ``block_depth = d > 0`` every ``Block`` of the recursion is a stack of d ``Conv2D(filters, 3, 1, 'same',
 relu)`` (train.py:131-139) -- one on the image, one behind every DownShuffle, one in the middle, one in front of
 every UpShuffle, one in front of Dense(3) --, and with ``concat = False`` a ``Residual`` is just its module (no skip).
 
@@ -37,7 +39,7 @@ from .engine import NetConfig, UNetEngine
 
 @dataclasses.dataclass
 class _Layer:
-    kind: str                       # "image3" | "s1" | "down" | "down_image" | "up"
+    kind: str                       # "image3" | "s1" | "down" | "down_image" | "up" | "proj"
     name: str                       # variable prefix ("<name>/kernel", "<name>/bias")
     x: torch.Tensor                 # input view (fp32 image for the two image kinds)
     y: torch.Tensor                 # output view (post-ReLU)
@@ -45,6 +47,7 @@ class _Layer:
     gx: Optional[torch.Tensor]      # where the input's gradient goes (None: the input is the image)
     mask: int = 0                   # leading channels of gx that are ReLU-masked by x (the rest is a raw skip part)
     add_old: bool = False           # gx already holds the other consumer's part
+    res: Optional[torch.Tensor] = None  # "proj": the Residual's input, added in the epilogue (train.py:110-111)
 
 
 class BlockUNetEngine(UNetEngine):
@@ -70,23 +73,24 @@ class BlockUNetEngine(UNetEngine):
             self._bufs += [a, g]
             return a, g
 
+        joined = cfg.concat and not cfg.residual  # the skip travels as a channel slice of the level's buffer
         # one buffer per Residual level: [up_j output | skip] (train.py:113-119), or the up output alone
         self.cat, self.gcat = {}, {}
         for j in range(n):
-            if j == 0 and d == 0:
-                C = cfg.up_c(0)  # the image is not 16-bit data: Dense reads it separately (only reached with concat off)
+            if (j == 0 and d == 0) or not joined:
+                C = cfg.up_c(j)  # (at the image level the skip is not 16-bit data: Dense reads the image separately)
             else:
                 C = cfg.res_out(j)
             self.cat[j], self.gcat[j] = pair(C, S >> j)
 
         def skip_view(j: int):
             """Where the tensor entering level j lives (and its gradient)."""
-            if cfg.concat and not (j == 0 and d == 0):
+            if joined and not (j == 0 and d == 0):
                 return self.cat[j][..., cfg.up_c(j):], self.gcat[j][..., cfg.up_c(j):]
             return pair(cfg.level_in(j), S >> j)
 
-        def add(kind, name, x, gx, y, gy, mask=None, add_old=False):
-            self.layers.append(_Layer(kind, name, x, y, gy, gx, x.shape[3] if mask is None else mask, add_old))
+        def add(kind, name, x, gx, y, gy, mask=None, add_old=False, res=None):
+            self.layers.append(_Layer(kind, name, x, y, gy, gx, x.shape[3] if mask is None else mask, add_old, res))
 
         def block(prefix, x, gx, filters, H, last=None, first_mask=None):
             """d stride-1 convs; the last one writes into `last` (a view pair) when given.  Returns the output pair."""
@@ -107,12 +111,14 @@ class BlockUNetEngine(UNetEngine):
             if h.dtype == torch.float32:
                 add("down_image", f"down{i}", h, None, dy, gdy)
             else:
-                # with the skip connection h has a second consumer whose raw part is already in gh
-                add("down", f"down{i}", h, gh, dy, gdy, add_old=cfg.concat)
+                # with a skip (concat) or identity (residual) path h has a second consumer whose raw part is already in gh
+                add("down", f"down{i}", h, gh, dy, gdy, add_old=cfg.concat or cfg.residual)
             hy, ghy = block(f"block_down{i}", dy, gdy, cfg.down_c(i), H, last=nxt)
             if i + 1 < n:
                 inner, ginner = level(i + 1, hy, ghy)
-                inner_mask = cfg.up_c(i + 1) if cfg.concat else None  # the skip part of cat[i+1] is stored raw
+                # what the consumer of level i+1's output may ReLU-mask: the up part of a concat buffer (its skip part is
+                # stored raw), nothing of a residual sum (not a ReLU output), everything otherwise
+                inner_mask = 0 if cfg.residual else (cfg.up_c(i + 1) if cfg.concat else None)
             else:
                 inner, ginner = block("block_mid", hy, ghy, cfg.mid_c(), H)
                 inner_mask = None
@@ -123,6 +129,15 @@ class BlockUNetEngine(UNetEngine):
                 u, gu = inner, ginner
             out, gout = self.cat[i][..., :cfg.up_c(i)], self.gcat[i][..., :cfg.up_c(i)]
             add("up", f"up{i}", u, gu, out, gout, mask=inner_mask)
+            if cfg.residual:
+                if h.dtype == torch.float32:
+                    return out, gout  # image level: the projection onto 3 channels is folded into Dense(3) (_forward)
+                # r = h + Dense(C, use_bias=False)(up_i output).  The gradient of r IS the identity path's part of h's
+                # gradient: r's gradient buffer is h's, and down_i's dgrad completes it in place (add_old)
+                r = torch.zeros_like(h)
+                self._bufs.append(r)
+                add("proj", f"res{i}/dense", out, gout, r, gh, res=h)
+                return r, gh
             return self.cat[i], self.gcat[i]
 
         if d:
@@ -131,21 +146,36 @@ class BlockUNetEngine(UNetEngine):
             h0, gh0 = self.noised, None
         top, gtop = level(0, h0, gh0)
         if d:
-            top, gtop = block("block_out", top, gtop, cfg.outer_c(), S, first_mask=cfg.up_c(0) if cfg.concat else None)
+            top_mask = 0 if cfg.residual else (cfg.up_c(0) if cfg.concat else None)
+            top, gtop = block("block_out", top, gtop, cfg.outer_c(), S, first_mask=top_mask)
         self.dense_in, self.gdense_in = top, gtop
         biggest = max(t.numel() for t in self._bufs)
         self.ws = ops.Workspace(max(4 * 4 * biggest, 64 << 20), dev)
         self.ws_w = self.ws  # one stream: the weight gradients share the scratch
         self._buckets = []
         # BiasAddGrad of every layer: gct2_bias_grad_multi takes up to 16 tensors per launch
+        biased = [l for l in self.layers if l.kind != "proj"]
         self._bias_plans = [ops.BiasGradPlan([l.gy for l in chunk], [self.view(self.g, f"{l.name}/bias") for l in chunk])
-                            for chunk in (self.layers[i:i + 16] for i in range(0, len(self.layers), 16))]
+                            for chunk in (biased[i:i + 16] for i in range(0, len(biased), 16))]
+        self._res0 = cfg.residual and d == 0
+        if self._res0:
+            U = cfg.up_c(0)
+            self._weff = torch.zeros(U + 3, 3, dtype=torch.float32, device=dev)
+            self._dweff = torch.zeros(U + 3, 3, dtype=torch.float32, device=dev)
 
     # ------------------------------------------------------------------------------------------ the step's two halves
     def plan_keys(self) -> List[str]:
         return []  # the plan table of tools/tune_plans.py belongs to the default wiring
 
+    def _proj_kernel(self, l: _Layer, buf: torch.Tensor) -> torch.Tensor:
+        """Dense kernel [Cin, Cout] of a residual projection as the [1,1,Cin,Cout] kernel of the stride-1 map."""
+        k = self.view(buf, f"{l.name}/kernel")
+        return k.view(1, 1, *k.shape)
+
     def _fprop(self, l: _Layer) -> None:
+        if l.kind == "proj":
+            ops.conv3s1_fprop_add(l.x, self._proj_kernel(l, self.w16), l.res, l.y, self.weights_stable)
+            return
         bias = self.view(self.w, f"{l.name}/bias")
         if l.kind == "image3":
             ops.conv3s1_c3_fprop(l.x, self.view(self.w, f"{l.name}/kernel"), bias, l.y)
@@ -163,18 +193,36 @@ class BlockUNetEngine(UNetEngine):
         for l in self.layers:
             self._fprop(l)
         # the default wiring (runnable here as a cross-check of the tuned engine) hands Dense the image channels too
-        image = self.noised if (cfg.block_depth == 0 and cfg.concat) else None
-        ops.dense_mse(self.dense_in, image, self.x, self.view(self.w, "dense/kernel"), self.view(self.w, "dense/bias"),
+        image = self.noised if (cfg.block_depth == 0 and cfg.concat and not cfg.residual) else None
+        wd, dwd = self.view(self.w, "dense/kernel"), self.view(self.g, "dense/kernel")
+        if self._res0:
+            # image-level residual: pred = (noised + up0 . Wp) . Wd + bd through the effective kernel [Wp Wd ; Wd]
+            image = self.noised
+            wd = ops.res0_compose(self.view(self.w, "res0/dense/kernel"), wd, self._weff)
+            dwd = self._dweff
+            if backward:
+                self._dweff.zero_()
+        ops.dense_mse(self.dense_in, image, self.x, wd, self.view(self.w, "dense/bias"),
                       self.loss, inv_n, pred=self.pred if want_pred else None,
                       du0=self.gdense_in if backward else None,
-                      dwd=self.view(self.g, "dense/kernel") if backward else None,
+                      dwd=dwd if backward else None,
                       dbd=self.view(self.g, "dense/bias") if backward else None, accumulate=True,
                       loss_scale=self.ls if (backward and cfg.mixed_precision) else None,
                       eps=self.eps, t_int=self.t_int, mode=cfg.target_mode, steps=cfg.steps)
+        if self._res0 and backward:
+            ops.res0_decompose(self._dweff, self.view(self.w, "res0/dense/kernel"), self.view(self.w, "dense/kernel"),
+                               self.view(self.g, "res0/dense/kernel"), self.view(self.g, "dense/kernel"))
 
     def _backward(self, apply_adam: bool, inc_iterations: bool = False) -> None:
         cfg = self.cfg
         for l in reversed(self.layers):
+            if l.kind == "proj":
+                # d(up_i output) = relu'(.) (g_r . Wp^T); dWp = up_i output^T . g_r; the identity path needs no work: g_r
+                # already sits in the buffer down_i's dgrad completes
+                ops.conv3s1_wgrad(l.x, l.gy, self._proj_kernel(l, self.g), self.ws_w)
+                ops.conv3s1_dgrad(l.gy, self._proj_kernel(l, self.w16), l.gx, l.x, l.mask, False, self.ws,
+                                  self.weights_stable)
+                continue
             dw = self.view(self.g, f"{l.name}/kernel")
             w16 = self.view(self.w16, f"{l.name}/kernel")
             if l.kind == "image3":

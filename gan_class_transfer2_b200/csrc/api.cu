@@ -185,6 +185,25 @@ int gct2_conv3s1_fprop(const uint16_t* x, int ldx, const uint16_t* w, const floa
   return conv_launch(a, S(stream));
 }
 
+int gct2_conv3s1_fprop_add(const uint16_t* x, int ldx, const uint16_t* w, const uint16_t* res, int ldres, uint16_t* y,
+                           int ldy, int B, int H, int W, int Cin, int Cout, int ks, int flags, void* stream) {
+  if (check_conv("gct2_conv3s1_fprop_add", B, H, W, Cin, Cout)) return 1;
+  if (res == nullptr) {
+    set_error("gct2_conv3s1_fprop_add: res must not be NULL");
+    return 1;
+  }
+  ConvArgs a = blank(MODE_CF, B, H, W);
+  a.ks = ks;
+  a.lo = CB(x); a.ldLo = ldx; a.Clo = Cin;
+  a.w = CB(w); a.R = Cin; a.Cc = Cout;
+  // the data-gradient epilogue with nothing masked and the add operand taken from `res`: y = acc + res
+  a.epi = EPI_DGRAD; a.out = MB(y); a.ldo = ldy; a.act = CB(res); a.ldact = ldres; a.maskN = 0; a.addOld = 1;
+  a.addSrc = CB(res); a.ldAdd = ldres;
+  a.forceSplits = 1;
+  a.flags = (flags & GCT2_WEIGHTS_STABLE) ? CONV_WEIGHTS_STABLE : 0;
+  return conv_launch(a, S(stream));
+}
+
 int gct2_conv3s1_dgrad(const uint16_t* dy, int lddy, const uint16_t* w, uint16_t* dx, int lddx, const uint16_t* act,
                        int ldact, int mask_channels, int add_old, int B, int H, int W, int Cin, int Cout, int ks,
                        float* ws, size_t ws_bytes, int flags, void* stream) {
@@ -240,6 +259,13 @@ int gct2_dense_mse(const uint16_t* u0, int ldu, const float* noised, const float
                    void* stream) {
   return dense_mse(CB(u0), ldu, noised, x, wd, bd, pred, loss, MB(du0), lddu, dwd, dbd, pixels, Cu, inv_n, backward,
                    accumulate ? 0 : 1, loss_scale, eps, t_int, pixels_per_image, target_mode, steps, S(stream));
+}
+
+int gct2_res0_compose(const float* wp, const float* wd, float* weff, int U, void* stream) {
+  return res0_compose(wp, wd, weff, U, S(stream));
+}
+int gct2_res0_decompose(const float* dweff, const float* wp, const float* wd, float* dwp, float* dwd, int U, void* stream) {
+  return res0_decompose(dweff, wp, wd, dwp, dwd, U, S(stream));
 }
 
 int gct2_adam_keras(float* w, float* m, float* v, const float* g, uint16_t* w_bf16, long long n,

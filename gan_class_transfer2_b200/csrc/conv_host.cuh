@@ -23,6 +23,8 @@ struct ConvArgs {
   const float* bias;
   const __nv_bfloat16* act;
   int ldact, maskN, addOld;
+  const __nv_bfloat16* addSrc;   // stride-1 modes: tensor added instead of out's old contents (needs addOld, no split-K)
+  int ldAdd;
   float* ws;                     // fp32 split-K workspace (contents irrelevant on entry and on exit)
   size_t wsBytes;
   int flags;                     // CONV_WEIGHTS_STABLE: `w` is not being written by any launch that may still be running

@@ -681,6 +681,12 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     p.ldact = a.ldact;
     p.maskN = a.maskN;
     p.addOld = a.addOld;
+    p.addSrc = s1 ? a.addSrc : nullptr;
+    p.ldAdd = a.ldAdd;
+    if (p.addSrc != nullptr && (c.splits != 1 || a.epi != EPI_DGRAD || !a.addOld)) {
+      set_error("conv: the separate add operand needs the add epilogue without split-K");
+      return 1;
+    }
     p.epi = a.epi;
     p.bEarly = (g_b_early && (a.flags & CONV_WEIGHTS_STABLE)) ? 1 : 0;
     if (c.splits > 1) {

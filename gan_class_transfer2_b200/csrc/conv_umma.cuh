@@ -125,6 +125,8 @@ struct ConvParams {
   int ldact;
   int maskN;                   // EPI_DGRAD: columns [0,maskN) are ReLU-masked
   int addOld;                  // EPI_DGRAD: add the value already stored in out (skip-path gradient)
+  const __nv_bfloat16* addSrc; // stride-1 modes, EPI_DGRAD without split-K: add THIS tensor (pixel stride ldAdd) instead of
+  int ldAdd;                   // out's old contents -- the `input + Dense(module(input))` of train.py:110-111
   float* ws;                   // EPI_WS_SLAB: fp32 [splits][outPixels][N]; EPI_WGRAD split-K: fp32 [splits][16*Chi*Clo]
   long long wsSplitStride;     // elements between consecutive split slabs
   float* dw;                   // EPI_WGRAD: fp32 [16][...]
@@ -763,6 +765,10 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
             // the saved activation and the skip gradient are requested while the TMEM load is in flight
             uint4* dst = reinterpret_cast<uint4*>(p.out + pix * p.ldo + n);
             const uint4* ap = reinterpret_cast<const uint4*>(p.act + pix * p.ldact + n);
+            const uint4* addp = dst;
+            if constexpr (mode_is_s1(MODE)) {
+              if (p.addSrc != nullptr) addp = reinterpret_cast<const uint4*>(p.addSrc + pix * p.ldAdd + n);
+            }
             const bool masked = valid && n < p.maskN, add = valid && p.addOld;
             uint4 av[4], ov[4];
 #pragma unroll
@@ -770,7 +776,7 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
               av[g] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);  // positive in both formats = keep
               ov[g] = make_uint4(0u, 0u, 0u, 0u);
               if (masked) av[g] = __ldg(ap + g);
-              if (add) ov[g] = dst[g];
+              if (add) ov[g] = addp[g];
             }
             tmem_ld_wait();
             if (valid) {

@@ -873,6 +873,66 @@ int dense_mse(const __nv_bfloat16* u0, int ldu, const float* noised, const float
   return 0;
 }
 
+// ------------------------------------------------------------------------------------ residual = True at the image level
+// train.py:106-112 with residual = True and block_depth = 0: the outermost Residual returns
+//   r = noised + up0 . Wp          (Dense(3, use_bias=False) on up0's U channels, train.py:107-111)
+// and Dense(3) follows (train.py:198-202): pred = r . Wd + bd = up0 . (Wp Wd) + noised . Wd + bd -- the fused
+// Dense(3)+MSE kernel with the effective kernel Weff = [Wp Wd ; Wd] ([U+3, 3]).  Its outputs map back linearly:
+//   dWp = dWeff[:U] . Wd^T ,  dWd = Wp^T . dWeff[:U] + dWeff[U:] ;  du0 = relu'(up0) (dpred . Weff[:U]^T) is already right.
+// Both maps are U x 3 x 3 multiply-adds: one small block each.
+__global__ void res0_compose_kernel(const float* __restrict__ wp, const float* __restrict__ wd, float* __restrict__ weff, int U) {
+  TraceScope trace(32);
+  pdl_launch_dependents();
+  pdl_wait();
+  trace.ready();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (U + 3) * 3; i += gridDim.x * blockDim.x) {
+    const int r = i / 3, j = i - 3 * r;
+    float v;
+    if (r < U)
+      v = wp[r * 3] * wd[j] + wp[r * 3 + 1] * wd[3 + j] + wp[r * 3 + 2] * wd[6 + j];
+    else
+      v = wd[(r - U) * 3 + j];
+    weff[i] = v;
+  }
+  trace.end();
+}
+__global__ void res0_decompose_kernel(const float* __restrict__ dweff, const float* __restrict__ wp,
+                                      const float* __restrict__ wd, float* __restrict__ dwp, float* __restrict__ dwd, int U) {
+  TraceScope trace(33);
+  pdl_launch_dependents();
+  pdl_wait();
+  trace.ready();
+  for (int i = threadIdx.x; i < U * 3; i += blockDim.x) {
+    const int r = i / 3, k = i - 3 * r;
+    dwp[i] = dweff[r * 3] * wd[k * 3] + dweff[r * 3 + 1] * wd[k * 3 + 1] + dweff[r * 3 + 2] * wd[k * 3 + 2];
+  }
+  if (threadIdx.x < 9) {
+    const int k = threadIdx.x / 3, j = threadIdx.x - 3 * k;
+    float v = dweff[(U + k) * 3 + j];
+    for (int r = 0; r < U; ++r) v = fmaf(wp[r * 3 + k], dweff[r * 3 + j], v);
+    dwd[threadIdx.x] = v;
+  }
+  trace.end();
+}
+int res0_compose(const float* wp, const float* wd, float* weff, int U, cudaStream_t st) {
+  if (U < 1) {
+    set_error("res0_compose: U must be positive");
+    return 1;
+  }
+  launch_k(res0_compose_kernel, dim3(1), dim3(256), 0, st, wp, wd, weff, U);
+  GCT2_CHECK_LAUNCH("res0_compose_kernel");
+  return 0;
+}
+int res0_decompose(const float* dweff, const float* wp, const float* wd, float* dwp, float* dwd, int U, cudaStream_t st) {
+  if (U < 1) {
+    set_error("res0_decompose: U must be positive");
+    return 1;
+  }
+  launch_k(res0_decompose_kernel, dim3(1), dim3(256), 0, st, dweff, wp, wd, dwp, dwd, U);
+  GCT2_CHECK_LAUNCH("res0_decompose_kernel");
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------ bias gradients
 // db[c] = sum_rows dz[row, c] for up to BG_MAX_SEG tensors in ONE launch (every conv layer's BiasAddGrad).  A block
 // owns a row range of one segment; thread = channel pair, blockDim.x/pairs row groups; shared-memory reduce, one

@@ -18,6 +18,8 @@ int conv3s1_c3_fprop(const float* x, const float* w, const float* bias, __nv_bfl
                      int W, int Cout, cudaStream_t st);
 int conv3s1_c3_wgrad(const float* x, const __nv_bfloat16* dz, int lddz, float* dw, int B, int H, int W, int Cout,
                      int zero, cudaStream_t st);
+int res0_compose(const float* wp, const float* wd, float* weff, int U, cudaStream_t st);
+int res0_decompose(const float* dweff, const float* wp, const float* wd, float* dwp, float* dwd, int U, cudaStream_t st);
 int dense_mse(const __nv_bfloat16* u0, int ldu, const float* noised, const float* x, const float* wd,
               const float* bd, float* pred, float* loss, __nv_bfloat16* du0, int lddu, float* dwd, float* dbd,
               long long pixels, int Cu, float invN, int backward, int zero, const float* loss_scale, const float* eps,

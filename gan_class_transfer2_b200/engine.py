@@ -59,6 +59,9 @@ class NetConfig:
     block_depth: int = 0
     #: train.py:27,113-119: Residual concatenates [module(x), x]; False = module(x) alone (no skip connections)
     concat: bool = True
+    #: train.py:26,106-112: Residual returns input + Dense(input_channels, use_bias=False)(module(input)) (and ignores
+    #: `concat`)
+    residual: bool = False
     #: filters of the innermost Block (train.py:179); None = min(pixel_size * 2**octaves, max_size)
     mid_filters: Optional[int] = None
     #: filters of the two outermost Blocks (train.py:192,194); None = pixel_size
@@ -67,7 +70,7 @@ class NetConfig:
     @property
     def fused_default(self) -> bool:
         """The wiring the tuned UNetEngine implements (the reference's defaults)."""
-        return self.block_depth == 0 and self.concat
+        return self.block_depth == 0 and self.concat and not self.residual
 
     def mid_c(self) -> int:  # train.py:179
         return self.mid_filters if self.mid_filters is not None else min(self.pixel_size * 2 ** self.octaves, self.max_size)
@@ -82,7 +85,9 @@ class NetConfig:
         return self.down_c(i - 1)
 
     def res_out(self, i: int) -> int:
-        """Channels leaving Residual level i (train.py:113-121)."""
+        """Channels leaving Residual level i (train.py:110-121)."""
+        if self.residual:
+            return self.level_in(i)
         return self.up_c(i) + (self.level_in(i) if self.concat else 0)
 
     def down_c(self, i: int) -> int:  # train.py:181
@@ -120,6 +125,7 @@ class NetConfig:
             raise ValueError("the fused Dense(3)+MSE kernel supports 64 or 128 16-bit input channels")
         # weight gradients put one side's channels on the 128-row M axis of the tensor-core tile
         pairs = [(s[2], s[3]) for name, s in variable_specs(self) if name.endswith("kernel") and len(s) == 4 and s[2] != 3]
+        pairs += [s for name, s in variable_specs(self) if name.startswith("res") and s[1] != 3]
         for a, b in pairs:
             if a % 64 or b % 64:
                 raise ValueError("channel counts must be multiples of 64 (tensor-core tile granularity)")
@@ -150,6 +156,8 @@ def variable_specs(cfg: NetConfig) -> List[Tuple[str, Tuple[int, ...]]]:
     for i in reversed(range(n)):
         c = block(f"block_up{i}", cin if i == n - 1 else cfg.res_out(i + 1), cfg.down_c(i))
         specs += [(f"up{i}/kernel", (4, 4, cfg.up_c(i), c)), (f"up{i}/bias", (cfg.up_c(i),))]
+        if cfg.residual:  # train.py:107: Dense(input_shape[-1], use_bias=False)
+            specs.append((f"res{i}/dense/kernel", (cfg.up_c(i), cfg.level_in(i))))
     c = block("block_out", cfg.res_out(0), cfg.outer_c())
     specs += [("dense/kernel", (c, 3)), ("dense/bias", (3,))]
     return specs
@@ -168,6 +176,8 @@ def small_names(cfg: NetConfig) -> List[str]:
     specs = variable_specs(cfg)
     image_kernels = [n for n, s in specs if n.endswith("kernel") and len(s) == 4 and s[2] == 3]  # CUDA-core convs on the image
     names = image_kernels + [n for n, _ in specs if n.endswith("bias") and not n.startswith("dense")]
+    if cfg.residual and cfg.block_depth == 0:
+        names.append("res0/dense/kernel")  # [U,3]: updated with the Dense(3) it is folded into (gct2_res0_compose)
     return names + ["dense/kernel", "dense/bias"]
 
 
@@ -1012,7 +1022,7 @@ class UNetEngine:
 
 def make_engine(cfg: NetConfig, batch: int, **kw) -> UNetEngine:
     """The engine for a configuration: the tuned UNetEngine for the reference's default wiring, BlockUNetEngine for the
-    dormant switches (block_depth > 0, concat = False)."""
+    dormant switches (block_depth > 0, concat = False, residual = True)."""
     if cfg.fused_default:
         return UNetEngine(cfg, batch, **kw)
     from .block_engine import BlockUNetEngine

@@ -222,6 +222,18 @@ def conv3s1_fprop(x, w, bias, y, ws: Workspace, weights_stable: bool = False):
 
 
 @_timed
+def conv3s1_fprop_add(x, w, res, y, weights_stable: bool = False):
+    """train.py:110-111 (residual = True): y = res + Dense(C, use_bias=False)(x) -- the 1x1 case of the stride-1 map with
+    the add fused into the epilogue.  w 16-bit [1,1,Cin,Cout] (a Dense kernel [Cin,Cout] viewed as a 1x1 conv)."""
+    lib = _lib_for(x)
+    B, H, W, Cin = x.shape
+    check(lib.gct2_conv3s1_fprop_add(ptr(x), _nhwc(x, torch.bfloat16), ptr(w), ptr(res), _nhwc(res, torch.bfloat16), ptr(y),
+                                     _nhwc(y, torch.bfloat16), B, H, W, Cin, y.shape[3], w.shape[0], int(weights_stable),
+                                     current_stream()))
+    return y
+
+
+@_timed
 def conv3s1_dgrad(dy, w, dx, act, mask_channels: int, add_old: bool, ws: Workspace, weights_stable: bool = False):
     """Backward-data of the stride-1 conv: dx = mask(conv2d_backprop_input(dy, w) (+ dx)); channels [0, mask_channels)
     of dx are ReLU-masked by act, the rest stored raw (a concat buffer's skip slice)."""
@@ -325,6 +337,21 @@ def dense_mse(u0, noised, x, wd, bd, loss, inv_n: float, pred=None, du0=None, dw
                              pixels, u0.shape[3], inv_n, int(backward), int(accumulate), ptr(loss_scale),
                              ptr(eps), ptr(t_int), u0.shape[1] * u0.shape[2], int(mode), int(steps), current_stream()))
     return loss
+
+
+@_timed
+def res0_compose(wp, wd, weff):
+    """weff [U+3,3] = [wp . wd ; wd]: the image-level residual projection folded into Dense(3) (see gct2_res0_compose)."""
+    lib = _lib_for(wp)
+    check(lib.gct2_res0_compose(ptr(wp), ptr(wd), ptr(weff), wp.shape[0], current_stream()))
+    return weff
+
+
+@_timed
+def res0_decompose(dweff, wp, wd, dwp, dwd):
+    """dwp = dweff[:U] . wd^T, dwd = wp^T . dweff[:U] + dweff[U:] (see gct2_res0_decompose)."""
+    lib = _lib_for(wp)
+    check(lib.gct2_res0_decompose(ptr(dweff), ptr(wp), ptr(wd), ptr(dwp), ptr(dwd), wp.shape[0], current_stream()))
 
 
 @_timed

@@ -276,11 +276,18 @@ class Residual(Layer):
         self.highway = highway
 
     def build(self, input_shape):
-        if residual:
-            raise NotImplementedError("residual=True (Dense projection branch, train.py:106-112) is outside the "
-                                      "accelerated path; the reference default is residual=False")
+        if residual:  # train.py:106-108
+            self.dense = Dense(input_shape[-1], use_bias=False)
 
     def call(self, input):
+        if residual:  # train.py:110-111 (standalone use; inside a Denoiser the engine fuses the add into the projection)
+            out = self.module(input)
+            if not self.dense.built:
+                self.dense.build(tuple(out.shape))
+                self.dense.built = True
+            k = self.dense.kernel.to(out.dtype)
+            y = torch.empty(*out.shape[:3], k.shape[1], dtype=out.dtype, device=out.device)
+            return ops.conv3s1_fprop_add(out, k.view(1, 1, *k.shape), _check_act(input), y)
         if concat:
             out = self.module(input)
             return torch.cat([out, self.highway(input).to(out.dtype)], -1)
@@ -293,16 +300,17 @@ class Residual(Layer):
 class Dense(Layer):
     """tf.keras.layers.Dense as train.py:198-202 uses it: contraction of the last axis, bias, no activation."""
 
-    def __init__(self, units):
+    def __init__(self, units, use_bias=True):
         super().__init__()
         self.units = units
+        self.use_bias = use_bias
         self.kernel: Optional[torch.Tensor] = None
         self.bias: Optional[torch.Tensor] = None
 
     def build(self, input_shape):
         if self.kernel is None:
             self.kernel = glorot_uniform((input_shape[-1], self.units), _next_init_generator()).cuda()
-            self.bias = torch.zeros(self.units, device="cuda")
+            self.bias = torch.zeros(self.units, device="cuda") if self.use_bias else None
 
 
 def identity(y_true, y_pred):
@@ -381,9 +389,6 @@ class Denoiser(Model):
     def _walk(self):
         """Pattern-matches the layer tree against the one shape the fused engine implements and returns
         (down layers outer->inner, up layers outer->inner, dense)."""
-        if residual:
-            raise NotImplementedError("residual=True (the Dense projection branch, train.py:106-112) is not implemented; "
-                                      "the reference default is residual=False")
         outer = self.middle.layers
         if not (len(outer) == 4 and isinstance(outer[0], Block) and isinstance(outer[1], Residual)
                 and isinstance(outer[2], Block) and isinstance(outer[3], Dense) and outer[3].units == 3):
@@ -435,7 +440,7 @@ class Denoiser(Model):
             if blocks["block_in"].filters != blocks["block_out"].filters:
                 raise NotImplementedError("the two outermost Blocks must have equal filters (train.py:192,194)")
             extra.update(block_depth=depth, mid_filters=blocks["block_mid"].filters, outer_filters=blocks["block_in"].filters)
-        extra.update(concat=bool(concat))
+        extra.update(concat=bool(concat), residual=bool(residual))
         return NetConfig(size=image_size, pixel_size=pixel_size, max_size=max_size, octaves=len(downs), steps=steps,
                          warm_up=warm, base_lr=base_lr, beta1=opt.beta_1, beta2=opt.beta_2,
                          epsilon=opt.epsilon, down_filters=tuple(d.filters for d in downs),
@@ -498,6 +503,13 @@ class Denoiser(Model):
             layer.built = True
         dense.kernel, dense.bias = eng.view(eng.w, "dense/kernel"), eng.view(eng.w, "dense/bias")
         dense.built = True
+        node, i = self.middle.layers[1], 0
+        while isinstance(node, Residual):  # train.py:106-108: the projections of residual = True
+            if eng.cfg.residual:
+                node.dense = Dense(eng.cfg.level_in(i), use_bias=False)
+                node.dense.kernel, node.dense.built = eng.view(eng.w, f"res{i}/dense/kernel"), True
+            node.built = True
+            node, i = node.module.layers[2], i + 1
         for prefix, block in self._blocks().items():
             for k, conv in enumerate(block.module.layers):
                 conv.kernel, conv.bias = eng.view(eng.w, f"{prefix}/conv{k}/kernel"), eng.view(eng.w, f"{prefix}/conv{k}/bias")

@@ -171,6 +171,11 @@ int gct2_convT4s2_wgrad(const uint16_t* x, int ldx, const uint16_t* dy, int lddy
  * ws / flags as for gct2_conv4s2_fprop. */
 int gct2_conv3s1_fprop(const uint16_t* x, int ldx, const uint16_t* w, const float* bias, uint16_t* y, int ldy, int B,
                        int H, int W, int Cin, int Cout, int ks, float* ws, size_t ws_bytes, int flags, void* stream);
+/* train.py:106-112 Residual with residual = True: y = res + Dense(Cout, use_bias=False)(x), i.e. the ks = 1 case of the
+ * stride-1 map without bias and activation and with the layer's input `res` (16-bit [B,H,W,Cout], stride ldres) added in
+ * the epilogue.  Backward: gct2_conv3s1_dgrad / _wgrad with ks = 1 (the identity path's gradient is the incoming one). */
+int gct2_conv3s1_fprop_add(const uint16_t* x, int ldx, const uint16_t* w, const uint16_t* res, int ldres, uint16_t* y,
+                           int ldy, int B, int H, int W, int Cin, int Cout, int ks, int flags, void* stream);
 int gct2_conv3s1_dgrad(const uint16_t* dy, int lddy, const uint16_t* w, uint16_t* dx, int lddx, const uint16_t* act,
                        int ldact, int mask_channels, int add_old, int B, int H, int W, int Cin, int Cout, int ks,
                        float* ws, size_t ws_bytes, int flags, void* stream);
@@ -211,6 +216,14 @@ int gct2_dense_mse(const uint16_t* u0, int ldu, const float* noised, const float
                    long long pixels, int Cu, float inv_n, int backward, int accumulate, const float* loss_scale,
                    const float* eps, const int32_t* t_int, long long pixels_per_image, int target_mode, int steps,
                    void* stream);
+
+/* train.py:106-112 with residual = True at the image level (block_depth = 0): the outermost Residual returns
+ * r = noised + up0 . wp (Dense(3, use_bias=False), wp fp32 [U,3]) and Dense(3) (wd fp32 [3,3], train.py:198-202) follows, so
+ * pred = up0 . (wp wd) + noised . wd + bd: gct2_dense_mse with the effective kernel weff = [wp wd ; wd] (fp32 [U+3,3]) that
+ * gct2_res0_compose writes.  gct2_res0_decompose maps gct2_dense_mse's dwd output (dweff, fp32 [U+3,3]) back:
+ * dwp = dweff[:U] . wd^T, dwd = wp^T . dweff[:U] + dweff[U:] (both overwritten). */
+int gct2_res0_compose(const float* wp, const float* wd, float* weff, int U, void* stream);
+int gct2_res0_decompose(const float* dweff, const float* wp, const float* wd, float* dwp, float* dwd, int U, void* stream);
 
 /* train.py:50-65,75 -- tf.keras.optimizers.Adam(WarmUp(base_lr, warmup_steps)), Keras formula (epsilon added to
  * the un-bias-corrected sqrt(v)).  All n parameters live in flat fp32 buffers; w_bf16 receives the shadow copy.

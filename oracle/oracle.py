@@ -394,7 +394,14 @@ def denoiser_forward(weights: Dict[str, torch.Tensor], x_nhwc: torch.Tensor, cfg
         if taps is not None:
             taps[f"up{i}"] = u
         if cfg.residual:                    # :110-111 input + Dense(input_channels, use_bias=False)(module(input))
-            return h + u @ weights[f"res{i}/dense/kernel"]
+            wres = weights[f"res{i}/dense/kernel"]
+            if h.shape[-1] == 3:            # (CUDA path: folded into Dense(3) in fp32, the sum is never stored)
+                return h + u @ wres
+            named(f"res{i}/dense")
+            r = rnd(h + u @ rnd0(wres))
+            if taps is not None:
+                taps[f"res{i}/dense"] = r
+            return r
         if cfg.concat:                      # :112-119 module output FIRST
             return torch.cat([u, h], dim=-1)
         return u                            # :120-121

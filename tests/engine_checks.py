@@ -39,7 +39,10 @@ def depth_factor(cfg: O.Config) -> float:
     model, activation gradients of level 0 against the same-rounding oracle: 1.2 % / 3.3 % / 6.9 % at block_depth 0 / 1 /
     2).  Stated: the default wiring's tolerances x (1 + block_depth)^1.5.  The tight statement about the backward pass
     of these networks is teacher_forced_parity, which removes the mask flips from the comparison."""
-    return (1.0 + cfg.block_depth) ** 1.5
+    f = (1.0 + cfg.block_depth) ** 1.5
+    # residual = True: the outer levels' gradients come through the projections of the residual sums instead of straight
+    # from the concat's skip slice: measured 2.6 % instead of 1.2 % at level 0 (same-rounding oracle), equal further down
+    return f * (1.8 if cfg.residual else 1.0)
 
 
 def no_skip_tol(cfg: O.Config, layer: str, flavour: str):
@@ -86,8 +89,7 @@ def make_engine(cfg: O.Config, batch: int, seed: int = 0, use_graph: bool = Fals
     from gan_class_transfer2_b200 import ops
     from gan_class_transfer2_b200 import engine as EN
     from gan_class_transfer2_b200.engine import NetConfig
-    if cfg.residual:
-        raise NotImplementedError("residual=True is restated by the oracle only")
+    net_kw.setdefault("residual", cfg.residual)
     net_kw.setdefault("block_depth", cfg.block_depth)
     net_kw.setdefault("concat", cfg.concat)
     net_kw.setdefault("target_mode", ops.target_mode(cfg.predict_x, cfg.predict_scaled_epsilon, cfg.prediction_weighting,
@@ -113,7 +115,8 @@ def engine_taps(eng) -> Dict[str, torch.Tensor]:
     if hasattr(eng, "layers"):  # the layer-list engine: every layer by the oracle's tap name
         for l in eng.layers:
             taps[l.name] = l.y
-            taps["d" + l.name] = l.gy
+            if l.kind != "proj":  # (a residual sum's gradient buffer is completed in place into its input's gradient)
+                taps["d" + l.name] = l.gy
         return taps
     for i in range(n):
         taps[f"down{i}"] = eng.down_out(i)

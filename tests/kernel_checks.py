@@ -145,6 +145,62 @@ def check_conv3_wgrad(B, H, Cin, Cout, ks=3, seed=22, pad=64):
     return _metrics(f"conv3s1_wgrad ks{ks} B{B} H{H} {Cin}x{Cout}", dw, wr.grad, F32_TOL * 2)
 
 
+def check_proj_add(B, H, Cin, Cout, seed=25, pad=64):
+    """train.py:110-111: y = res + Dense(Cout, use_bias=False)(x), the 1x1 map with the add in the epilogue."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(seed)
+    x = _bf(_rand((B, H, H, Cin), g))
+    res = _bf(_rand((B, H, H, Cout), g))
+    w = _bf(_rand((Cin, Cout), g, 1.0 / math.sqrt(Cin)))
+    ref = res.float() + x.float() @ w.float()
+    dev = _dev()
+    _, xv = _slice_buf(B, H, H, Cin, pad, 0, dev)
+    xv.copy_(x)
+    _, rv = _slice_buf(B, H, H, Cout, 0, pad, dev)
+    rv.copy_(res)
+    yfull, yv = _slice_buf(B, H, H, Cout, 0, pad, dev)
+    ops.conv3s1_fprop_add(xv, w.to(dev).view(1, 1, Cin, Cout), rv, yv)
+    torch.cuda.synchronize()
+    m = _metrics(f"conv3s1_fprop_add B{B} H{H} {Cin}->{Cout}", yv, ref, BF16_TOL)
+    m["pad_intact"] = bool((yfull[..., Cout:] == 7.0).all().item())
+    return m
+
+
+def check_res0_fold(U=64, B=2, H=16, seed=26):
+    """The image-level residual folded into Dense(3): pred, loss and all four gradients (dWp, dWd, dbd, du0) of
+    pred = (noised + u0 . Wp) . Wd + bd through gct2_res0_compose -> gct2_dense_mse -> gct2_res0_decompose."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(seed)
+    u0 = _bf(_rand((B, H, H, U), g).clamp_min(0))
+    noised, x = _rand((B, H, H, 3), g), _rand((B, H, H, 3), g)
+    wp = _rand((U, 3), g, 0.2).requires_grad_(True)
+    wd = _rand((3, 3), g, 0.5).requires_grad_(True)
+    bd = _rand((3,), g, 0.1).requires_grad_(True)
+    u0r = u0.float().requires_grad_(True)
+    pred = (noised + u0r @ wp) @ wd + bd
+    loss = ((x - pred) ** 2).mean()
+    loss.backward()
+    dev = _dev()
+    u0v = u0.to(dev)
+    weff = torch.zeros(U + 3, 3, device=dev)
+    dweff = torch.zeros(U + 3, 3, device=dev)
+    du0 = torch.full((B, H, H, U), 7.0, dtype=HALF, device=dev)
+    predg, lossg, dbd = torch.empty(B, H, H, 3, device=dev), torch.zeros(1, device=dev), torch.zeros(3, device=dev)
+    dwp, dwd = torch.full((U, 3), 3.0, device=dev), torch.full((3, 3), 3.0, device=dev)
+    wpd, wdd = wp.detach().to(dev), wd.detach().to(dev)
+    ops.res0_compose(wpd, wdd, weff)
+    ops.dense_mse(u0v, noised.to(dev), x.to(dev), weff, bd.detach().to(dev), lossg, 1.0 / (B * H * H * 3), pred=predg,
+                  du0=du0, dwd=dweff, dbd=dbd, accumulate=True)
+    ops.res0_decompose(dweff, wpd, wdd, dwp, dwd)
+    torch.cuda.synchronize()
+    ms = [_metrics("pred", predg, pred, 2e-5), _metrics("loss", lossg, loss.reshape(1), 2e-5),
+          _metrics("du0", du0, u0r.grad * (u0.float() > 0), BF16_TOL), _metrics("dWp", dwp, wp.grad, F32_TOL),
+          _metrics("dWd", dwd, wd.grad, F32_TOL), _metrics("dbd", dbd, bd.grad, F32_TOL)]
+    worst = dict(max(ms, key=lambda m: m["err"] / m["tol"]))
+    worst["name"] = f"image-level residual folded into Dense(3) U{U} (worst: {worst['name']})"
+    return worst
+
+
 def check_conv3_c3(B=2, H=32, Cout=128, seed=23):
     """The 3-channel 3x3 / stride-1 conv of the outermost Block: forward and weight gradient."""
     ops = _ops()
@@ -920,6 +976,11 @@ S1_CASES = [
 ]
 
 S1_EW_CASES = [
+    (check_proj_add, dict(B=2, H=16, Cin=64, Cout=128)),
+    (check_proj_add, dict(B=3, H=4, Cin=256, Cout=256)),
+    (check_proj_add, dict(B=1, H=64, Cin=128, Cout=64)),
+    (check_res0_fold, {}),
+    (check_res0_fold, dict(U=128, B=1)),
     (check_conv3_c3, {}),
     (check_conv3_c3, dict(B=1, H=16, Cout=64)),
     (check_conv3_c3, dict(B=3, H=8, Cout=512)),

@@ -71,25 +71,24 @@ def test_unsupported_structures_are_rejected():
 
 def test_wiring_switches_reach_the_engine_config():
     """train.py:20,26-27: block_depth and concat change what Denoiser.__init__ builds; both are run by the layer-list
-    engine (block_engine.BlockUNetEngine) and must arrive in the engine's configuration with the oracle's variable list.
-    residual=True (train.py:106-112) is not implemented and must say so instead of silently running another network."""
+    engine (block_engine.BlockUNetEngine) and must arrive in the engine's configuration with the oracle's variable list,
+    and so does residual=True (train.py:106-112: the bias-free Dense projection added to the Residual's input)."""
     import dataclasses
     saved = {k: getattr(T, k) for k in ("concat", "residual", "block_depth", "octaves", "max_size")}
     try:
         T.octaves, T.max_size = 4, 256
-        for kw in (dict(block_depth=1), dict(block_depth=2, concat=False), dict(concat=False)):
-            T.block_depth, T.concat = kw.get("block_depth", 0), kw.get("concat", True)
+        for kw in (dict(block_depth=1), dict(block_depth=2, concat=False), dict(concat=False), dict(residual=True),
+                   dict(residual=True, block_depth=1)):
+            T.block_depth, T.concat, T.residual = kw.get("block_depth", 0), kw.get("concat", True), kw.get("residual", False)
             cfg = T.Denoiser().net_config(64)
-            assert (cfg.block_depth, cfg.concat) == (T.block_depth, T.concat) and not cfg.fused_default
+            assert (cfg.block_depth, cfg.concat, cfg.residual) == (T.block_depth, T.concat, T.residual)
+            assert not cfg.fused_default
             cfg.validate()
             ocfg = dataclasses.replace(O.TINY, **kw)
             assert E.variable_specs(cfg) == O.variable_specs(ocfg)
             assert sum(cnt for _, cnt in E.param_offsets(cfg)[0].values()) == O.param_count(ocfg)
             with pytest.raises(NotImplementedError):
                 E.UNetEngine(cfg, 1)  # the tuned engine is for the default wiring only
-        T.block_depth, T.concat, T.residual = 0, True, True
-        with pytest.raises(NotImplementedError):
-            T.Denoiser().net_config(64)
     finally:
         for k, v in saved.items():
             setattr(T, k, v)
