@@ -380,7 +380,25 @@ __device__ GCT2_FINISH_ATTR void splitk_finish_in_place(const ConvParams& p, con
       const int R = 128 / p.splits, vecPerRow = BN / 4;
       const float* slab0 = p.ws + ((long long)tileId * 128) * BN;
       const long long splitStride = (long long)p.numTiles * 128 * BN;
-      for (int idx = et; idx < R * vecPerRow; idx += NT) {
+      const int items = R * vecPerRow;
+      if (!csplit) {
+        // L2 form, pass 1: ALL partials of this CTA's rows are requested at once, global -> shared memory without
+        // passing through registers (cp.async into the operand ring, idle now: the CTA's only work item has retired its
+        // MMAs).  The sum below then costs one L2 round trip whatever the split factor; loading the partials one after
+        // the other was most of a 6-9 us epilogue at 16 / 32 splits (the 4x4 and 8x8 layers at batch 1).  Layout
+        // [split][item]: a warp's 16-byte reads are consecutive.  Every thread reads back only what it requested itself.
+        for (int idx = et; idx < items; idx += NT) {
+          const int rr = w.split * R + idx / vecPerRow, c4 = (idx % vecPerRow) * 4;
+          const int bl = rr >> (p.lgWt + p.lgHt);
+          if ((w.mt >> (p.lgTilesX + p.lgTilesY)) * p.Nb + bl >= p.B) continue;
+          const float* sp = slab0 + (long long)rr * BN + c4;
+          const uint32_t dst = part0 + (uint32_t)idx * 16u;
+          for (int sidx = 0; sidx < p.splits; ++sidx)
+            cp_async_cg16(dst + (uint32_t)(sidx * items) * 16u, sp + (long long)sidx * splitStride);
+        }
+        cp_async_wait_all();
+      }
+      for (int idx = et; idx < items; idx += NT) {
         const int rr = w.split * R + idx / vecPerRow, c4 = (idx % vecPerRow) * 4;
         const int xl = rr & (p.Wt - 1), yl = (rr >> p.lgWt) & (p.Ht - 1), bl = rr >> (p.lgWt + p.lgHt);
         const int b = (w.mt >> (p.lgTilesX + p.lgTilesY)) * p.Nb + bl;
@@ -409,10 +427,11 @@ __device__ GCT2_FINISH_ATTR void splitk_finish_in_place(const ConvParams& p, con
               }
           }
         } else {
-          const float* sp = slab0 + (long long)rr * BN + c4;
-          v = __ldcg(reinterpret_cast<const float4*>(sp));
+          // pass 2: summation order split 0, 1, 2, ... -- bit-identical to the finishing kernel
+          const uint32_t src = part0 + (uint32_t)idx * 16u;
+          v = ld_smem_f4(src);
           for (int sidx = 1; sidx < p.splits; ++sidx) {
-            const float4 u = __ldcg(reinterpret_cast<const float4*>(sp + sidx * splitStride));
+            const float4 u = ld_smem_f4(src + (uint32_t)(sidx * items) * 16u);
             v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
           }
         }
@@ -844,7 +863,9 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
         }
         tc_fence_before();
         __syncwarp();
-        if (p.fused || csplit) splitk_finish_in_place<MODE, BN, csplit ? 1 : 0>(p, w, tileId, smem, red_full, warp, lane);
+        if constexpr (!mode_is_w(MODE)) {  // (weight gradients never finish in place: keep the code out of their kernels)
+          if (p.fused || csplit) splitk_finish_in_place<MODE, BN, csplit ? 1 : 0>(p, w, tileId, smem, red_full, warp, lane);
+        }
 #ifdef GCT2_TIMELINE
         if (item == clusterId && warp == 4 && lane == 0) GCT2_STAMP(5);  // first epilogue (of warp 4) done
 #endif

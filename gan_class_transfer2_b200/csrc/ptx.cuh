@@ -231,6 +231,19 @@ __device__ __forceinline__ void mbar_wait_cluster_acquire(uint64_t* bar, uint32_
     }
   }
 }
+// 16 bytes global -> shared without passing through registers (LDGSTS, L2-coherent like ld.global.cg): any number of
+// them may be in flight per thread; cp_async_wait_all() makes the issuing thread's copies visible to itself.
+__device__ __forceinline__ void cp_async_cg16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ float4 ld_smem_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t cluster_addr) {
   float4 v;
   asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"

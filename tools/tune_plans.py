@@ -30,10 +30,12 @@ def main():
     ap.add_argument("--min-gain", type=float, default=0.004)
     ap.add_argument("--write", action="store_true")
     ap.add_argument("--budget-s", type=float, default=600.0)
+    ap.add_argument("--reach", type=int, default=1, help="split factors tried: the incumbent's times 2^-reach .. 2^reach")
+    ap.add_argument("--fresh", action="store_true", help="start from the cost model's plans, not from the stored table")
     a = ap.parse_args()
     os.environ["GCT2_TUNED"] = "0"
     from gan_class_transfer2_b200 import _lib, ops
-    from gan_class_transfer2_b200.engine import NetConfig, UNetEngine, plan_table_key
+    from gan_class_transfer2_b200.engine import NetConfig, UNetEngine, plan_table_key, load_tuned_plans
     import time
     lib = _lib.init(0)
     cfg = NetConfig()
@@ -83,6 +85,8 @@ def main():
     eng.plans = {}
     t_model = measure({})
     cur = dict(base_plans)
+    if not a.fresh:
+        cur.update({k: v for k, v in load_tuned_plans(cfg, a.batch, lib.gct2_num_sms()).items() if valid(k, v)})
     t_cur = measure(cur)
     print(json.dumps({"event": "start", "ms_model": round(t_model, 4), "ms_explicit": round(t_cur, 4), "plans": base_plans}),
           flush=True)
@@ -95,7 +99,7 @@ def main():
             bn0, sp0 = cur[key]
             cands = []
             for bn in (64, 128, 256):
-                for sp in sorted({max(1, sp0 // 2), sp0, sp0 * 2}):
+                for sp in sorted({max(1, sp0 >> r) for r in range(a.reach + 1)} | {sp0 << r for r in range(a.reach + 1)}):
                     if (bn, sp) != (bn0, sp0):
                         cands.append((bn, sp))
             t_cur = measure(cur, reps=2)
