@@ -21,7 +21,7 @@
 //           A of CF / CD and the X operand of CW: 4-D TMA box shifted by the tap, zero fill at the border (SAME padding).
 //
 // Warp roles: warps 0, 2, 3 = TMA producers (ring rounds round-robin; warp 2 also allocates TMEM), warp 1 = MMA
-// issuer, warps 4.. = epilogue (8 warps for BN = 64, 16 otherwise; TMEM -> registers -> global).  Accumulators are
+// issuer, warps 4.. = epilogue (8 warps; TMEM -> registers -> global).  Accumulators are
 // double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the main loop of tile i+1.
 //
 // Ring: a slot holds KPS k-chunks of 64 (KPS = 2 for BN <= 128, 1 for BN = 256), i.e. one full/empty barrier round trip
@@ -182,10 +182,16 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 #define GCT2_STAMP(slot) do { } while (0)
 #endif
 
-// Epilogue warps per tile width: 8 (two 32-column slices) for BN = 64, 16 (four slices) for BN = 128 / 256.
+// Epilogue warps per tile width.  Round 1 gave the BN = 128 / 256 instantiations 16 of them (640 threads, so 96 registers
+// per thread and spills in every such kernel); measured in round 2 (profiles/r2_epilogue_warps_ab.jsonl): 8 warps with 128
+// registers and no spills are faster at every batch size (0.5435 -> 0.5382 ms at batch 1, +1.9 % at 8 images, +0.8 % at 32)
+// -- the epilogue of tile i overlaps the main loop of tile i + 1 anyway, and at batch 1 the split-K wait dominates it.
+#ifndef GCT2_EPI_WARPS_WIDE
+#define GCT2_EPI_WARPS_WIDE 8  // A/B hook (make variant)
+#endif
 template <int BN>
 __host__ __device__ constexpr int kEpilogueWarps() {
-  return BN == 64 ? 8 : 16;
+  return BN == 64 ? 8 : GCT2_EPI_WARPS_WIDE;
 }
 template <int BN>
 __host__ __device__ constexpr int kConvThreads() {
@@ -470,7 +476,7 @@ __device__ GCT2_FINISH_ATTR void splitk_finish_in_place(const ConvParams& p, con
 }
 
 #ifndef GCT2_CONV_EXTRA_BOUND
-#define GCT2_CONV_EXTRA_BOUND 0
+#define GCT2_CONV_EXTRA_BOUND 128  // launch bound 512 for 384-thread CTAs: at most 128 registers per thread
 #endif
 // PAIR = 1: the cta_group::2 variant (a separate instantiation: a kernel that contains cta_group::2 instructions can
 // only be launched as a cluster of an even number of CTAs).

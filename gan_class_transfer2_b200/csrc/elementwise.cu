@@ -1077,6 +1077,9 @@ __global__ void adam_prepare_kernel(long long* __restrict__ iterations, float* _
 #ifndef GCT2_ADAM_THREADS
 #define GCT2_ADAM_THREADS 256
 #endif
+#ifndef GCT2_ADAM_MINB
+#define GCT2_ADAM_MINB (640 / GCT2_ADAM_THREADS)  // A/B hook: resident blocks per SM the register budget is sized for
+#endif
 constexpr int ADAM_U = GCT2_ADAM_U;
 constexpr int ADAM_THREADS = GCT2_ADAM_THREADS;
 __device__ __forceinline__ void adam_update(float4& wv, float4& mv, float4& vv, float4 gv, float gscale, float c1,
@@ -1098,7 +1101,7 @@ __device__ __forceinline__ float4 adam_load_grad(const void* __restrict__ g, lon
   return __ldcs(reinterpret_cast<const float4*>(g) + i);  // the gradient is dead after this read
 }
 template <bool G16>
-__global__ void __launch_bounds__(ADAM_THREADS, 640 / ADAM_THREADS) adam_kernel(float4* __restrict__ w, float4* __restrict__ m,
+__global__ void __launch_bounds__(ADAM_THREADS, GCT2_ADAM_MINB) adam_kernel(float4* __restrict__ w, float4* __restrict__ m,
                                                             float4* __restrict__ v, const void* __restrict__ g,
                                                             uint2* __restrict__ wb, long long nvec,
                                                             const float* __restrict__ hyper, float b1, float b2,
