@@ -2,6 +2,7 @@
  * TensorFlow / Keras *definitions* of the ops train.py calls -- not from any library's convolution:
  *
  *   Conv2D(filters, 4, 2, 'same') + bias + relu            train.py:158-169  (DownShuffle)
+ *   Conv2D(filters, 3, 1, 'same') + bias + relu            train.py:131-139  (Block, block_depth > 0; same loop, k = 3, s = 1)
  *   Conv2DTranspose(filters, 4, 2, 'same') + bias + relu   train.py:145-156  (UpShuffle)
  *   Dense(3) on the last axis                              train.py:198-202
  *   mean squared difference                                train.py:272

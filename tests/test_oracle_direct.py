@@ -126,3 +126,64 @@ def test_whole_forward_pass_matches_with_the_wiring_restated(lib):
     out = np.empty((2, 16, 16, 3), np.float32)
     lib.gct2_direct_dense(_p(h), _p(_np(w["dense/kernel"])), _p(_np(w["dense/bias"])), _p(out), 2 * 256, h.shape[-1], 3)
     np.testing.assert_allclose(out, ref, rtol=2e-4, atol=2e-5)
+
+
+# ---- the dormant switches (train.py:20,26-27) against the direct C ops
+def conv3(lib, x, w, b, relu=True):
+    """Conv2D(filters, 3, 1, 'same') through the generic direct loop (SAME padding from TensorFlow's rule: 1 before)."""
+    B, H, W, Cin = x.shape
+    y = np.empty((B, H, W, w.shape[3]), np.float32)
+    lib.gct2_direct_conv2d_same(_p(x), _p(w), _p(b), _p(y), B, H, W, Cin, w.shape[3], 3, 1, int(relu))
+    return y
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 8, 5, 7), (1, 4, 4, 3, 4), (1, 5, 9, 2, 3)])
+def test_block_convolution_matches_the_direct_definition(lib, shape):
+    B, H, W, Ci, Co = shape
+    g = torch.Generator().manual_seed(H * 10 + Ci)
+    x = torch.randn(B, H, W, Ci, generator=g)
+    w, b = torch.randn(3, 3, Ci, Co, generator=g) * 0.3, torch.randn(Co, generator=g)
+    np.testing.assert_allclose(conv3(lib, _np(x), _np(w), _np(b)), _np(O.conv3x3(x, w, b)), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("kw", [dict(block_depth=1), dict(block_depth=2, concat=False), dict(residual=True),
+                                dict(residual=True, block_depth=1)],
+                         ids=["depth1", "depth2-no-concat", "residual", "residual-depth1"])
+def test_whole_forward_pass_of_the_dormant_wirings(lib, kw):
+    """train.py:175-204 with block_depth > 0 / residual = True / concat = False, the recursion restated here over the direct
+    C ops: Sequential[Block, Residual(Sequential[DownShuffle, Block, inner, Block, UpShuffle]), Block, Dense(3)], a Block =
+    block_depth 3x3 convolutions, a Residual = input + Dense_nobias(module(input)) | concat([module(input), input]) |
+    module(input) -- must reproduce oracle.denoiser_forward."""
+    import dataclasses
+    cfg = dataclasses.replace(O.Config(size=16, pixel_size=8, max_size=16, octaves=2), **kw)
+    w = O.glorot_init(cfg, 3)
+    g = torch.Generator().manual_seed(8)
+    for k in list(w):
+        if k.endswith("bias"):
+            w[k] = torch.randn(w[k].shape, generator=g) * 0.1
+    x = torch.rand(2, 16, 16, 3, generator=g) * 2 - 1
+    ref = _np(O.denoiser_forward(w, x, cfg))
+
+    def block(prefix, h):
+        for k in range(cfg.block_depth):
+            h = conv3(lib, h, _np(w[f"{prefix}/conv{k}/kernel"]), _np(w[f"{prefix}/conv{k}/bias"]))
+        return h
+
+    def residual(i, h):
+        d = block(f"block_down{i}", conv(lib, h, _np(w[f"down{i}/kernel"]), _np(w[f"down{i}/bias"])))
+        inner = residual(i + 1, d) if i + 1 < cfg.octaves else block("block_mid", d)
+        u = convT(lib, block(f"block_up{i}", inner), _np(w[f"up{i}/kernel"]), _np(w[f"up{i}/bias"]))
+        if cfg.residual:
+            kern = _np(w[f"res{i}/dense/kernel"])
+            proj = np.empty(h.shape, np.float32)
+            zero = np.zeros(kern.shape[1], np.float32)
+            lib.gct2_direct_dense(_p(u), _p(kern), _p(zero), _p(proj), u.size // u.shape[-1], u.shape[-1], kern.shape[1])
+            return np.ascontiguousarray(h + proj)
+        if cfg.concat:
+            return np.ascontiguousarray(np.concatenate([u, h], axis=-1))
+        return u
+
+    top = block("block_out", residual(0, block("block_in", _np(x))))
+    out = np.empty((2, 16, 16, 3), np.float32)
+    lib.gct2_direct_dense(_p(top), _p(_np(w["dense/kernel"])), _p(_np(w["dense/bias"])), _p(out), 2 * 256, top.shape[-1], 3)
+    np.testing.assert_allclose(out, ref, rtol=3e-4, atol=3e-5)
