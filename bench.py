@@ -309,6 +309,8 @@ def main():
         from gan_class_transfer2_b200.engine import optimizer_shard
         dp = T.data_parallel
 
+        head_p2p = [False]
+
         def comm_only():
             used_p2p = False
             for start, end, _ in eng._buckets:
@@ -324,6 +326,13 @@ def main():
                     used_p2p = True
                     if start >= eng.small:
                         continue
+                    if pp.get("head_p2p"):
+                        # the head region and the loss: staging copies + one peer-load sum, no NCCL call
+                        pp["head"][:eng.small].copy_(eng.g[:eng.small], non_blocking=True)
+                        pp["head"][eng.small:eng.small + 1].copy_(eng.loss, non_blocking=True)
+                        ops.sum_peers_f32(pp["head_ptrs"], dp.world, eng.g[:eng.small], eng.loss)
+                        head_p2p[0] = True
+                        continue
                     end = eng.small
                     cut = None
                 if cut is not None:
@@ -337,6 +346,8 @@ def main():
                 dist.all_reduce(eng.g[start:end])
             if used_p2p:
                 eng._p2p["hw"].barrier(channel=1)
+            if not head_p2p[0]:
+                dist.all_reduce(eng.loss)  # the reported loss (global mean)
 
         saved = eng._save_state()
         comm_ms = timed(comm_only, max(10, args.steps // 4))
@@ -348,6 +359,7 @@ def main():
                 "bytes_per_step": {"reduce_scatter": grad_bytes, "all_gather_bf16": 2 * eng.P},
                 "grad_dtype": dp.grad_dtype, "shard_optimizer": dp.shard_optimizer, "nccl_max_ctas": dp.nccl_ctas,
                 "transport": ("p2p+multimem" if eng._p2p["g_mc"] else "p2p") if eng._p2p is not None else "nccl",
+                "head_and_loss": "peer loads" if (eng._p2p is not None and eng._p2p.get("head_p2p")) else "nccl all-reduce",
                 "how": "compute_only = the captured step with its collectives left out; comm_alone = the step's "
                        "collectives back to back; exposed = step - compute_only; overlapped = comm_alone - exposed"}
         if not replicas_equal:

@@ -85,6 +85,7 @@ _PROTOS = {
     "gct2_adam_apply_g16": (c_int, [_P, _P, _P, _P, _P, c_longlong, _P, c_float, c_float, c_float, c_float, _P, _P]),
     "gct2_adam_apply_p2p": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_longlong, c_longlong, _P, c_float, c_float, c_float,
                                     c_float, c_int, _P]),
+    "gct2_sum_peers_f32": (c_int, [_P, c_int, _P, c_longlong, _P, c_longlong, _P]),
     "gct2_step_begin": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, ctypes.c_ulonglong, _P, _P, c_float, c_int, c_float,
                                 c_float, _P, c_longlong, _P, _P]),
     "gct2_step_begin_u8": (c_int, [_P, _P, _P, c_int, _P, _P, _P, c_int, c_int, c_int, ctypes.c_ulonglong, _P, _P, c_float,

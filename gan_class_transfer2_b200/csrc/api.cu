@@ -298,6 +298,10 @@ int gct2_adam_apply_p2p(float* w, float* m, float* v, const uint16_t* const* g_b
   return adam_apply_p2p(w, m, v, g_bf16_ptrs, w16_ptrs, g_multicast, w16_multicast, world, elem_offset, n, hyper, beta1,
                         beta2, eps, grad_scale, write_all, S(stream));
 }
+int gct2_sum_peers_f32(const float* const* src_ptrs, int world, float* out_a, long long n_a, float* out_b, long long n_b,
+                       void* stream) {
+  return sum_peers_f32(src_ptrs, world, out_a, n_a, out_b, n_b, S(stream));
+}
 int gct2_step_begin(const float* x, float* noised, float* eps_out, int32_t* t_out, int B, int elems_per_image, int steps,
                     unsigned long long seed, const long long* iterations, float* hyper, float base_lr, int warmup_steps,
                     float beta1, float beta2, float* gsmall, long long nsmall, float* loss, void* stream) {

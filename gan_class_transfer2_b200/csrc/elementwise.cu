@@ -1348,6 +1348,52 @@ int adam_apply_p2p(float* w, float* m, float* v, const uint16_t* const* g_ptrs, 
   return 0;
 }
 
+// The replicated head region (down0's kernel, biases, Dense: a few thousand fp32 gradients) and the scalar loss, summed
+// over all ranks without a collective library: every rank reads every rank's copy (in symmetric memory) and adds them in
+// rank order -- the same sum bit for bit on every rank, so the redundant Keras-Adam updates stay identical.  Replaces two
+// small NCCL all-reduces (~15-30 us of launch latency each) at the very end of the step, where nothing can hide them.
+struct PeerF32 {
+  const float* src[8];
+  int world;
+};
+__global__ void __launch_bounds__(256) sum_peers_f32_kernel(const __grid_constant__ PeerF32 pp, float* __restrict__ out_a,
+                                                            long long n_a, float* __restrict__ out_b, long long n_b) {
+  TraceScope trace(16);
+  pdl_launch_dependents();
+  pdl_wait();
+  trace.ready();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_a + n_b; i += (long long)gridDim.x * blockDim.x) {
+    float v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < pp.world) asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v[r]) : "l"(pp.src[r] + i) : "memory");
+    float sum = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < pp.world) sum += v[r];
+    if (i < n_a)
+      out_a[i] = sum;
+    else
+      out_b[i - n_a] = sum;
+  }
+  trace.end();
+}
+int sum_peers_f32(const float* const* src_ptrs, int world, float* out_a, long long n_a, float* out_b, long long n_b,
+                  cudaStream_t st) {
+  if (world < 1 || world > 8 || n_a < 0 || n_b < 0 || n_a + n_b == 0) {
+    set_error("sum_peers_f32: 1..8 ranks and a non-empty range (world=%d n=%lld+%lld)", world, n_a, n_b);
+    return 1;
+  }
+  PeerF32 pp;
+  for (int r = 0; r < 8; ++r) pp.src[r] = r < world ? src_ptrs[r] : nullptr;
+  pp.world = world;
+  long long blocks = (n_a + n_b + 255) / 256;
+  if (blocks > g_ew_sms * 2) blocks = g_ew_sms * 2;
+  launch_k(sum_peers_f32_kernel, dim3((int)blocks), dim3(256), 0, st, pp, out_a, n_a, out_b, n_b);
+  GCT2_CHECK_LAUNCH("sum_peers_f32_kernel");
+  return 0;
+}
+
 int adam_prepare(long long* iterations, float* hyper, float base_lr, int warmup_steps, float beta1, float beta2,
                  cudaStream_t st) {
   launch_k(adam_prepare_kernel, dim3(1), dim3(1), 0, st, iterations, hyper, base_lr, warmup_steps, beta1, beta2);

@@ -41,6 +41,8 @@ int adam_apply_p2p(float* w, float* m, float* v, const uint16_t* const* g_ptrs, 
                    const uint16_t* g_mc, uint16_t* w16_mc, int world, long long elem_offset, long long n,
                    const float* hyper, float beta1, float beta2, float eps, float grad_scale, int write_all,
                    cudaStream_t st);
+int sum_peers_f32(const float* const* src_ptrs, int world, float* out_a, long long n_a, float* out_b, long long n_b,
+                  cudaStream_t st);
 int loss_scale_check(const float* g, long long n, float* ls, cudaStream_t st);
 int loss_scale_update(float* ls, int growth_steps, cudaStream_t st);
 void elementwise_set_f16(int f16);

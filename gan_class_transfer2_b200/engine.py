@@ -442,7 +442,6 @@ class UNetEngine:
         if (dp is not None and dp.world > 1 and dp.shard_optimizer and dp.transport == "p2p" and share_params_with is None
                 and dp.world <= 8):
             self._p2p = self._map_peer_buffers()
-
         # ---- activations and their gradients
         bf = dict(dtype=self.half, device=dev)
         self.x = torch.zeros(B, S, S, 3, **f32)
@@ -455,6 +454,21 @@ class UNetEngine:
         self.loss = torch.zeros(1, **f32)
         self.global_batch = B * (dp.world if dp else 1)
         self._alloc_activations()
+        #: With the peer-memory transport no NCCL kernel runs beside a conv launch (the head region's all-reduce and the
+        #: loss all-reduce start only after the last dgrad; what does run beside backward -- the gradient cast, the
+        #: signal-pad barrier's single small CTA, the fused exchange kernel -- either terminates on its own or leaves room
+        #: for a conv CTA on its SM), so the L2 rendezvous form of the split-K finish and the single-GPU plan table are
+        #: usable again.  GCT2_DP_L2_FINISH=1 turns that on (an A/B switch until it has been measured on 8 GPUs).
+        all_fused = self._p2p is not None and all(
+            (cut := optimizer_shard(st, en, self.small, dp.world, dp.rank)) is not None
+            and (cut[3] - cut[2]) % 8 == 0 and cut[2] % 8 == 0 for st, en, _ in self._buckets if en > self.small)
+        self.dp_l2_finish = all_fused and os.environ.get("GCT2_DP_L2_FINISH", "0") == "1"
+        if self.dp_l2_finish:
+            lib.gct2_debug_set(26, 0)
+            lib.gct2_debug_set(25, 1)
+            if os.environ.get("GCT2_TUNED", "1") != "0":
+                self.plans = load_tuned_plans(cfg, batch, _lib.load().gct2_num_sms())
+
 
     def _alloc_activations(self) -> None:
         """Activation / gradient buffers of the default wiring (see the module docstring) and everything sized by them."""
@@ -497,6 +511,10 @@ class UNetEngine:
             hw = symm_mem.rendezvous(w16, group)
             g16.zero_()
             w16.copy_(self.w16)
+            # fp32 staging of the replicated head region's gradients + the loss (summed by peer loads, no NCCL call)
+            head = symm_mem.empty(self.small + 4, dtype=torch.float32, device=self.device)
+            hh = symm_mem.rendezvous(head, group)
+            head.zero_()
             g_mc = int(getattr(hg, "multicast_ptr", 0) or 0) if dp.multicast else 0
             w_mc = int(getattr(hw, "multicast_ptr", 0) or 0) if dp.multicast else 0
             if not (g_mc and w_mc):
@@ -505,7 +523,8 @@ class UNetEngine:
             torch.cuda.synchronize(self.device)
             hw.barrier(channel=0)
             return dict(hg=hg, hw=hw, g_ptrs=[int(p) for p in hg.buffer_ptrs], w_ptrs=[int(p) for p in hw.buffer_ptrs],
-                        g_mc=g_mc, w_mc=w_mc)
+                        g_mc=g_mc, w_mc=w_mc, head=head, hh=hh, head_ptrs=[int(p) for p in hh.buffer_ptrs],
+                        head_p2p=os.environ.get("GCT2_DP_HEAD", "p2p") == "p2p")
         except Exception as exc:  # noqa: BLE001 -- any failure here means "no peer mapping": use the collectives
             import warnings
             warnings.warn(f"gct2: peer-memory transport unavailable ({type(exc).__name__}: {exc}); using NCCL collectives")
@@ -673,6 +692,7 @@ class UNetEngine:
                 else 0, False]
         chain_caps = False
         p2p_used = [False]
+        head_done = [False]  # head region + loss already summed over the ranks by peer loads
         if dp is not None and 0 < dp.nccl_ctas < num_sms and self._p2p is None:
             ops.set_sm_budget(num_sms - dp.nccl_ctas)  # the collectives of backward keep their SMs
             side[1] = True
@@ -709,8 +729,14 @@ class UNetEngine:
                             # fused: cast -> barrier -> ONE kernel (gradient sum over NVLink, Keras-Adam on my slice, weight
                             # broadcast into every rank's shadow); see gct2_adam_apply_p2p
                             pp = self._p2p
+                            # the last bucket carries the replicated head region below it: its gradients and the loss go
+                            # through the same barrier and are summed by peer loads right after the fused kernel
+                            head_now = start < self.small and pp["head_p2p"]
                             with torch.cuda.stream(sw):
                                 ops.cast_bf16(self.g[lo:end], self.g16[lo:end])
+                                if head_now and not dp.dry_run:
+                                    pp["head"][:self.small].copy_(self.g[:self.small], non_blocking=True)
+                                    pp["head"][self.small:self.small + 1].copy_(self.loss, non_blocking=True)
                             if sa is not main:
                                 sa.wait_stream(main)   # ... including the dgrad that still reads this bucket's weights
                                 if sw is not main:
@@ -731,6 +757,16 @@ class UNetEngine:
                             self._sharded_ranges.add((lo, end))
                             p2p_used[0] = True
                             if start >= self.small:
+                                continue
+                            if head_now:
+                                with torch.cuda.stream(sa):
+                                    if not dp.dry_run:
+                                        ops.sum_peers_f32(pp["head_ptrs"], dp.world, self.g[:self.small], self.loss)
+                                    ops.adam_apply(self.w[:self.small], self.m[:self.small], self.v[:self.small],
+                                                   self.g[:self.small], self.w16[:self.small], self.hyper, cfg.beta1,
+                                                   cfg.beta2, cfg.epsilon, 1.0,
+                                                   iterations_inc=self.iterations if inc_iterations else None)
+                                head_done[0] = True
                                 continue
                             end = self.small  # the head region below stays replicated
                             cut = None
@@ -821,7 +857,7 @@ class UNetEngine:
         if chain_caps:
             _lib.load().gct2_debug_set(9, 0)
             _lib.load().gct2_debug_set(10, 0)
-        if dp:
+        if dp and not head_done[0]:
             coll.all_reduce(self.loss).wait()
 
     def _zero_small_grads(self) -> None:

@@ -481,3 +481,13 @@ def adam_apply_p2p(w, m, v, g_ptrs, w16_ptrs, world: int, elem_offset: int, hype
     wa = (ctypes.c_void_p * world)(*w16_ptrs[:world])
     check(lib.gct2_adam_apply_p2p(ptr(w), ptr(m), ptr(v), ga, wa, g_mc or None, w16_mc or None, world, int(elem_offset),
                                   w.numel(), ptr(hyper), beta1, beta2, eps, grad_scale, int(write_all), current_stream()))
+
+
+@_timed
+def sum_peers_f32(src_ptrs, world: int, out_a, out_b):
+    """out_a / out_b (fp32, consecutive in every rank's staging buffer) = the sum over ranks of the buffers at src_ptrs
+    (per-rank base device pointers, ints), added in rank order (gct2_sum_peers_f32)."""
+    import ctypes
+    lib = _lib_for(out_a)
+    sa = (ctypes.c_void_p * world)(*src_ptrs[:world])
+    check(lib.gct2_sum_peers_f32(sa, world, ptr(out_a), out_a.numel(), ptr(out_b), out_b.numel(), current_stream()))

@@ -261,6 +261,12 @@ int gct2_adam_apply_p2p(float* w, float* m, float* v, const uint16_t* const* g_b
                         const uint16_t* g_multicast, uint16_t* w16_multicast, int world, long long elem_offset, long long n,
                         const float* hyper, float beta1, float beta2, float eps, float grad_scale, int write_all,
                         void* stream);
+/* Data parallel: the small replicated region (down0's kernel, biases, Dense) and the scalar loss summed over all ranks by
+ * peer loads -- out_a[i] = sum_r src_ptrs[r][i] for i < n_a, out_b[i - n_a] likewise for the next n_b elements, ranks added in
+ * index order (the same bits on every rank).  src_ptrs: HOST array of `world` device pointers to every rank's fp32 staging
+ * buffer (symmetric memory, this rank included).  The caller orders it across ranks like gct2_adam_apply_p2p. */
+int gct2_sum_peers_f32(const float* const* src_ptrs, int world, float* out_a, long long n_a, float* out_b, long long n_b,
+                       void* stream);
 /* Everything a step needs before its first convolution, in one launch (train.py:224-234 plus optimiser bookkeeping):
  * draws t_int ~ U{1..steps} per image and eps ~ N(0,1) per element on the device (Philox4x32-10 keyed by `seed`, offset by
  * *iterations so every step differs; the reference draws with TF's unseeded generators), writes

@@ -1,7 +1,7 @@
 """Prints the whole-step parity table (CUDA engine vs the CPU oracle, both flavours) for a configuration: the measured
 relative L2 errors behind the tolerances stated in tests/engine_checks.py.
 
-    python tools/parity_table.py --config default --batch 1 [--mixed-precision] [--block-depth D] [--no-concat] [--forced]
+    python tools/parity_table.py --config default --batch 1 [--mixed-precision] [--block-depth D] [--no-concat] [--residual] [--forced]
 
 --forced prints the teacher-forced table instead (tests/engine_checks.py:teacher_forced_parity): the backward pass
 against the oracle running on the engine's own activations.
@@ -23,14 +23,16 @@ def main():
     ap.add_argument("--mixed-precision", action="store_true")
     ap.add_argument("--block-depth", type=int, default=0)
     ap.add_argument("--no-concat", action="store_true")
+    ap.add_argument("--residual", action="store_true")
     ap.add_argument("--forced", action="store_true")
     a = ap.parse_args()
     import dataclasses
     from oracle import oracle as O
     from tests import engine_checks as E
     cfg = {"default": O.DEFAULT, "tiny": O.TINY, "wide": O.WIDE}[a.config]
-    cfg = dataclasses.replace(cfg, block_depth=a.block_depth, concat=not a.no_concat)
-    tag = {"config": a.config, "batch": a.batch, "mp": a.mixed_precision, "block_depth": a.block_depth, "concat": cfg.concat}
+    cfg = dataclasses.replace(cfg, block_depth=a.block_depth, concat=not a.no_concat, residual=a.residual)
+    tag = {"config": a.config, "batch": a.batch, "mp": a.mixed_precision, "block_depth": a.block_depth, "concat": cfg.concat,
+           "residual": cfg.residual}
     if a.forced:
         res, _ = E.teacher_forced_parity(cfg, a.batch, a.seed)
         for name, err in res.items():
