@@ -197,7 +197,7 @@ def loss_curve_parity(cfg: O.Config, batch: int, steps: int, seed: int = 0, use_
 
 #: teacher_forced_parity: what is left when both sides run backward on the SAME activations is the rounding of the
 #: stored 16-bit gradients (2^-9 per layer, random-walking over the layers of the chain) and fp32 summation order
-TOL_FORCED = 0.03
+TOL_FORCED = 0.02  # measured on B200: 0.4 - 0.95 % over every configuration of profiles/r2_parity_forced_activations.jsonl
 
 
 def teacher_forced_parity(cfg: O.Config, batch: int, seed: int = 0, layer_list: bool = False):

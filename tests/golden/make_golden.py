@@ -1,10 +1,11 @@
-"""Generates tests/golden/tiny_step.npz from the oracle (run once; re-run only when the oracle is deliberately changed).
+"""Generates tests/golden/tiny_step.npz (and tiny_step_depth1.npz / tiny_step_residual.npz: train.py:20,26 flipped) from the
+oracle (run once; re-run only when the oracle is deliberately changed).
 
 The reference itself cannot produce vectors here: it needs TensorFlow (not installed, no network), a GPU at
 train.py:40 and the author's dataset at train.py:305,315.  These vectors therefore pin the oracle against drift
 and give the CUDA path a committed fixture; they do not pin the oracle to TensorFlow ("parity unpinned").
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [depth1 residual]      # no argument: all three
 """
 import os
 import sys
@@ -17,8 +18,13 @@ sys.path.insert(0, ROOT)
 from oracle import oracle as O  # noqa: E402
 
 
-def main():
-    cfg = O.TINY
+VARIANTS = {"": {}, "depth1": dict(block_depth=1), "residual": dict(residual=True)}
+
+
+def make(name: str, kw: dict):
+    """One fixture: tiny_step.npz (train.py's default wiring) or tiny_step_<variant>.npz (a dormant switch flipped)."""
+    import dataclasses
+    cfg = dataclasses.replace(O.TINY, **kw)
     tr = O.OracleTrainer(cfg, seed=0)
     x, t, e = O.synthetic_batch(cfg, 2, 1)
     loss, grads, taps = O.loss_and_grads(tr.weights, x, t, e, cfg, want_taps=True)
@@ -49,8 +55,15 @@ def main():
         out["anorm/" + k] = np.float32(taps[k].norm())
     out["losses3"] = np.array([tr.train_step(*O.synthetic_batch(cfg, 2, 100 + s)) for s in range(3)], dtype=np.float32)
     out["w_after3/dense/kernel"] = tr.weights["dense/kernel"].numpy()
-    np.savez(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tiny_step.npz"), **out)
-    print({k: (v.tolist() if v.size < 4 else v.shape) for k, v in out.items()})
+    fname = "tiny_step.npz" if not name else f"tiny_step_{name}.npz"
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), fname), **out)
+    print(fname, {k: (v.tolist() if v.size < 4 else v.shape) for k, v in out.items() if not k.startswith(("gidx", "gval", "gnorm"))})
+
+
+def main():
+    which = sys.argv[1:] or list(VARIANTS)
+    for name in which:
+        make(name, VARIANTS[name])
 
 
 if __name__ == "__main__":

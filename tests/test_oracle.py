@@ -169,10 +169,14 @@ def test_data_parallel_shards_reproduce_the_global_gradient():
         assert torch.allclose(parts[0][1][k] + parts[1][1][k], grads[k], rtol=1e-4, atol=1e-8), k
 
 
-def test_golden_vectors_tiny_step():
-    """Drift check: the oracle reproduces the vectors it generated when it was pinned (make_golden.py)."""
-    gold = np.load(GOLDEN)
-    cfg = O.TINY
+@pytest.mark.parametrize("variant,kw", [("", {}), ("_depth1", dict(block_depth=1)), ("_residual", dict(residual=True))],
+                         ids=["default", "depth1", "residual"])
+def test_golden_vectors_tiny_step(variant, kw):
+    """Drift check: the oracle reproduces the vectors it generated when it was pinned (make_golden.py) -- for train.py's
+    default wiring and with block_depth = 1 / residual = True (train.py:20,26)."""
+    import dataclasses
+    gold = np.load(GOLDEN.replace("tiny_step.npz", f"tiny_step{variant}.npz"))
+    cfg = dataclasses.replace(O.TINY, **kw)
     tr = O.OracleTrainer(cfg, seed=0)
     x, t, e = O.synthetic_batch(cfg, 2, 1)
     loss, grads, taps = O.loss_and_grads(tr.weights, x, t, e, cfg, want_taps=True)
