@@ -442,8 +442,7 @@ class UNetEngine:
         if (dp is not None and dp.world > 1 and dp.shard_optimizer and dp.transport == "p2p" and share_params_with is None
                 and dp.world <= 8):
             self._p2p = self._map_peer_buffers()
-        # ---- activations and their gradients
-        bf = dict(dtype=self.half, device=dev)
+        # ---- the step's inputs and outputs (activations and their gradients: _alloc_activations)
         self.x = torch.zeros(B, S, S, 3, **f32)
         self.x_u8 = torch.zeros(B, S, S, 3, dtype=torch.uint8, device=dev)   # decode_file's bytes (train.py:285-293)
         self.flip = torch.zeros(B, dtype=torch.uint8, device=dev)           # per-image left-right flip flags

@@ -1,5 +1,6 @@
 """CPU: host-side logic of the drop-in surface (no kernels are launched)."""
 import math
+import os
 
 import pytest
 import torch
@@ -214,3 +215,47 @@ def test_fast_division_magic_numbers():
         for n in ns:
             if 0 <= n < (1 << 31):
                 assert div(f, n) == n // d, (d, n)
+
+
+def test_plan_table_is_keyed_by_shape_batch_policy_and_sm_count(tmp_path, monkeypatch):
+    """tuned_plans.json (tools/tune_plans.py): a table applies to exactly the configuration it was measured on."""
+    import json
+    cfg = E.NetConfig()
+    key = E.plan_table_key(cfg, 1, 148)
+    assert key != E.plan_table_key(cfg, 8, 148) and key != E.plan_table_key(cfg, 1, 132)
+    assert key != E.plan_table_key(E.NetConfig(mixed_precision=True), 1, 148)
+    assert key != E.plan_table_key(E.NetConfig(size=64, max_size=256, octaves=4), 1, 148)
+    shipped = E.load_tuned_plans(cfg, 1, 148)
+    assert shipped and all(len(v) == 2 and v[0] in (64, 128, 256) and v[1] >= 1 for v in shipped.values())
+    layers = {f"down{i}" for i in range(1, 6)} | {f"up{i}" for i in range(6)}
+    assert all(k.split("/")[0] in layers and k.split("/")[1] in ("fprop", "dgrad", "wgrad") for k in shipped)
+    assert E.load_tuned_plans(cfg, 3, 148) == {}  # no table for this batch: the cost model decides
+
+
+def test_ncu_summary_reads_both_csv_shapes(tmp_path):
+    """tools/ncu_summary.py: the --metrics log (one row per launch and metric) and the raw page (one row per launch)."""
+    import subprocess
+    import sys
+    long_csv = tmp_path / "long.csv"
+    long_csv.write_text(
+        '==PROF== Connected\n'
+        '"ID","Process ID","Process Name","Host Name","Kernel Name","Context","Stream","Block Size","Grid Size","Device","CC",'
+        '"Section Name","Metric Name","Metric Unit","Metric Value"\n'
+        + "".join(f'"{i}","1","python","h","void gct2::conv_umma_kernel<0, 64, 0, 0>(CUtensorMap_st)","1","7","(384, 1, 1)",'
+                  f'"(128, 1, 1)","0","10.0","s","{m}","{u}","{v}"\n'
+                  for i in range(2) for m, u, v in (("gpu__time_duration.sum", "ns", "12000"), ("dram__bytes_read.sum", "Mbyte", "5"),
+                                                    ("dram__bytes_write.sum", "Kbyte", "250"))))
+    out = tmp_path / "o.csv"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run([sys.executable, os.path.join(root, "tools", "ncu_summary.py"), "--raw", str(long_csv), "--out", str(out)],
+                   check=True, capture_output=True)
+    rows = out.read_text().strip().split("\n")
+    assert rows[0].startswith("kernel,time_us,grid,block") and len(rows) == 3
+    cells = rows[1].split('",')[1].split(",")
+    assert cells[0] == "12.000" and cells[1] == "128.000" and cells[2] == "384.000" and cells[3] == "5.000" and cells[4] == "0.250"
+    wide = tmp_path / "wide.csv"
+    wide.write_text('"ID","Kernel Name","Block Size","SM_A.Sec.gpu__time_duration.sum","FBSP.Sec.dram__bytes_read.sum"\n'
+                    '"","","","us","byte"\n"0","k<1>(int)","(384, 1, 1)","7.5","1000000"\n')
+    subprocess.run([sys.executable, os.path.join(root, "tools", "ncu_summary.py"), "--raw", str(wide), "--out", str(out)],
+                   check=True, capture_output=True)
+    assert out.read_text().strip().split("\n")[1] == '"k<1>",7.500,1.000'
