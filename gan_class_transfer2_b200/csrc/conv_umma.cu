@@ -27,6 +27,7 @@ static int g_fuse_finish = 1;          // debug key 12 != 0 disables the in-kern
 static int g_cap_w = 0, g_cap_sp = 0;  // debug keys 9 / 10: CTA budget of wgrad / dgrad launches (0 = all SMs)
 static int g_sm_budget = 0;            // key 22 / gct2_set_sm_budget: CTAs any conv launch may occupy (0 = all SMs)
 static int g_b_early = 1;              // debug key 21 != 0 disables the weight fetch before griddepcontrol.wait
+static int g_tap_fuse = 1;             // debug key 27 != 0 disables the four-tap weight-gradient items of 64-channel layers
 static int g_no_l2_finish = 0;         // key 26 != 0: never finish split-K with the L2 rendezvous (it needs every CTA of the
                                        // launch resident at once, which nothing guarantees beside NCCL kernels); the
                                        // cluster form and the finishing kernel remain
@@ -135,6 +136,7 @@ void conv_set_debug(int key, int value) {
   if (key == 19) g_pair = value;
   if (key == 20) g_spin_limit = (unsigned)value;
   if (key == 21) g_b_early = value ? 0 : 1;
+  if (key == 27) g_tap_fuse = value ? 0 : 1;
   if (key == 22) conv_set_sm_budget(value);
   if (key == 25) g_csplit = value;
   if (key == 26) g_no_l2_finish = value;
@@ -734,22 +736,28 @@ int conv_launch(const ConvArgs& a, cudaStream_t stream) {
     const int chunks = pixTiles;
     const int wTaps = s1 ? s1Taps : 16;
     const size_t slab = (size_t)wTaps * a.Chi * a.Clo * sizeof(float);
-    Choice c = choose(ds, MODE_W, Mch / 128, 1, Nch, chunks, (long long)(slab / sizeof(float)), false, a.forceBN,
-                      a.forceSplits, slab, a.ws ? a.wsBytes : 0, wTaps);
+    // A 64-channel gathered N side (up0: 64 output channels) would run on 128 x 64 tiles, the shape that spends most
+    // shared-memory traffic per FLOP (ncu, 32 images: 36-43 % tensor-pipe active).  The un-shifted operand is the same for
+    // every filter tap, so one work item takes FOUR taps: a 256-wide tile whose 64-column blocks are the gathered operand
+    // at taps 4 ph .. 4 ph + 3 -- one A load per four B loads, the BN = 256 main loop.
+    const bool tapFuse = g_tap_fuse && !s1 && !p.gIsA && Nch == 64 && (a.forceBN == 0 || a.forceBN == 256);
+    Choice c = choose(ds, MODE_W, Mch / 128, 1, tapFuse ? 256 : Nch, chunks, (long long)(slab / sizeof(float)), false,
+                      tapFuse ? 256 : a.forceBN, a.forceSplits, slab, a.ws ? a.wsBytes : 0, tapFuse ? 4 : wTaps);
     if (c.BN == 0) {
       set_error("wgrad: no tile shape for N=%d", Nch);
       return 1;
     }
     const long long itemsPlainW = (long long)wTaps * (Mch / 128) * (Nch / c.BN) * c.splits;
-    if (!s1 && (g_pair == 1 || (g_pair == 0 && itemsPlainW > maxCtas)) && c.BN >= 128 && (Mch / 128) % 2 == 0 &&
+    if (!s1 && !tapFuse && (g_pair == 1 || (g_pair == 0 && itemsPlainW > maxCtas)) && c.BN >= 128 && (Mch / 128) % 2 == 0 &&
         ds.max_pairs[MODE_W][bn_index(c.BN)] > 0)
       c.pair = 1;
     BN = c.BN;
     p.mTiles = Mch / 128;
-    p.nTiles = Nch / BN;
+    p.nTiles = tapFuse ? 1 : Nch / BN;
+    p.tapFuse = tapFuse ? 4 : 0;
     p.splits = c.splits;
     p.kIters = chunks / c.splits;
-    p.numItems = wTaps * p.mTiles * p.nTiles * c.splits;
+    p.numItems = (tapFuse ? wTaps / 4 : wTaps) * p.mTiles * p.nTiles * c.splits;
     p.cm = c.pair ? 2 : 1;
     p.N = Nch;
     p.ldG = a.ldHi;

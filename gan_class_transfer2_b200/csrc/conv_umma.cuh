@@ -109,6 +109,9 @@ struct ConvParams {
   int bEarly;                  // S/P: fetch the first ring pass of weight boxes before griddepcontrol.wait
   int f16;                     // 16-bit storage format of operands and outputs: 0 = bf16, 1 = fp16 (gct2_set_policy)
   int ks;                      // stride-1 modes: kernel side (3, or 1 for a per-pixel projection); taps = ks * ks
+  int tapFuse;                 // MODE_W with a 64-channel gathered N side (up0): 4 = one work item computes FOUR filter taps --
+                               // the un-shifted A tile is loaded once, the four 64-column blocks of a 256-wide B tile are the
+                               // gathered operand at four different taps, and the epilogue scatters the blocks to their taps
   // fast division by the launch constants used in index decoding (all set by conv_launch)
   FastDiv fdMTilesC, fdNTiles, fdSplits, fdKcPer;
   int lgWt, lgHt, lgTilesX, lgTilesY;  // pixel-tile geometry is power-of-two by construction
@@ -323,9 +326,20 @@ __device__ __forceinline__ void issue_chunk(const ConvParams& p, const CUtensorM
     } else {
 #pragma unroll
       for (int j = 0; j < 2; ++j) tma_load_4d(sa + j * BLK, mapA, bar, w.mt * 128 + j * 64, cx, cy, cb);
+      if (BN == 256 && p.tapFuse) {
+        // four taps share the A tile: block j of the B tile is the gathered operand's 64 channels at tap 4 * ph + j
 #pragma unroll
-      for (int j = 0; j < BN / 64; ++j)
-        tma_load_5d(sb + j * BLK, mapB, bar, px * p.ldG + w.nt * BN + j * 64, cx + hx, py, cy + hy, cb);
+        for (int j = 0; j < BN / 64; ++j) {
+          const int kx2 = j, ky2 = w.ph;  // tap = 4 * ph + j  ->  (ky, kx) = (ph, j)
+          const int py2 = (ky2 + 1) & 1, px2 = (kx2 + 1) & 1;
+          const int hy2 = ((ky2 + 1) >> 1) - 1, hx2 = ((kx2 + 1) >> 1) - 1;
+          tma_load_5d(sb + j * BLK, mapB, bar, px2 * p.ldG, cx + hx2, py2, cy + hy2, cb);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j)
+          tma_load_5d(sb + j * BLK, mapB, bar, px * p.ldG + w.nt * BN + j * 64, cx + hx, py, cy + hy, cb);
+      }
     }
   }
 }
@@ -852,9 +866,12 @@ __global__ void __launch_bounds__(kConvThreads<BN>() + GCT2_CONV_EXTRA_BOUND, 1)
             }
           } else {  // EPI_WGRAD: row = M-side channel, columns = N-side channels
             tmem_ld_wait();
+            // (tap-fused items: the tile's 64-column block n / 64 belongs to tap 4 * ph + n / 64)
+            const int tapOf = (BN == 256 && p.tapFuse) ? w.ph * 4 + (n >> 6) : w.ph;
+            const int colOf = (BN == 256 && p.tapFuse) ? (n & 63) : n;
             float* base = (p.atomic ? p.ws + (long long)w.split * p.wsSplitStride : p.dw) +
-                          (long long)w.ph * p.tapStride + (long long)(w.mt * 128 + r) * p.rowStride +
-                          (long long)n * p.colStride;
+                          (long long)tapOf * p.tapStride + (long long)(w.mt * 128 + r) * p.rowStride +
+                          (long long)colOf * p.colStride;
             if (p.colStride == 1) {
               float4* d4 = reinterpret_cast<float4*>(base);
 #pragma unroll

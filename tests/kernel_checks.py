@@ -875,6 +875,12 @@ FORCED_CASES = [
     (check_convT_wgrad, dict(B=4, H=16, Cin=256, Cout=64), dict(BN=64, splits=4)),
     (check_convT_wgrad, dict(B=4, H=16, Cin=256, Cout=128), dict(BN=256, splits=16)),
     # odd number of k-chunks per work item: the last ring round of a two-chunk slot is half full (BN <= 128)
+    # four filter taps per work item when the gathered N side has 64 channels (up0's weight gradient): a 256-wide tile whose
+    # 64-column blocks are four taps; forcing BN = 64 above keeps the one-tap path covered
+    (check_convT_wgrad, dict(B=4, H=16, Cin=256, Cout=64), dict(BN=256, splits=4)),
+    (check_convT_wgrad, dict(B=2, H=32, Cin=256, Cout=64), dict(BN=256, splits=1)),
+    (check_convT_wgrad, dict(B=1, H=128, Cin=256, Cout=64), dict(BN=256, splits=16)),   # up0 itself at batch 1
+    (check_conv_wgrad, dict(B=3, H=16, Cin=64, Cout=128), dict(BN=256, splits=1)),      # 3 pixel chunks
     (check_conv_wgrad, dict(B=3, H=16, Cin=128, Cout=64), dict(BN=64, splits=1)),       # 3 pixel chunks
     (check_convT_wgrad, dict(B=1, H=4, Cin=128, Cout=128), dict(BN=128, splits=1)),     # 1 chunk, a quarter full
     (check_conv_fprop, dict(B=1, H=16, Cin=64, Cout=128), dict(BN=128, splits=16, finish="l2")),     # 1 chunk per split
