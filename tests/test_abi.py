@@ -73,3 +73,33 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
     assert "UTMALDG" in sass
     assert "LDTM" in sass
     assert "HMMA." not in sass.replace("UTCHMMA", "")
+
+
+def test_every_conv_instantiation_is_a_tensor_core_kernel_within_its_register_budget():
+    """profiles/sass_summary.txt is generated from the shipped library (tools/sass_summary.py): all 30 instantiations of
+    conv_umma_kernel -- the 4x4 / stride-2 maps, their cta_group::2 and cluster split-K variants and the stride-1 maps of
+    Block / Residual (modes 3-5) -- issue UTCHMMA and UTMALDG, read their accumulators with LDTM, and contain no HMMA; the
+    S / P maps stage split-K partials with LDGSTS."""
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "sass_summary.py")], capture_output=True, text=True).stdout
+    rows = [l for l in out.split("\n") if l.startswith("conv_umma_kernel<")]
+    if not rows:
+        pytest.skip("cuobjdump produced no SASS")
+    inst = {}
+    for l in rows:
+        name = l.split(">")[0] + ">"
+        inst[name] = dict(kv.split("=") for kv in l[len(name):].split() if "=" in kv)
+    modes = {int(re.match(r"conv_umma_kernel<(\d)", n).group(1)) for n in inst}
+    assert modes == {0, 1, 2, 3, 4, 5} and len(inst) == 30, sorted(inst)
+    for name, ops in inst.items():
+        assert int(ops.get("UTCHMMA", 0)) > 0 and int(ops.get("UTMALDG", 0)) > 0 and int(ops.get("LDTM", 0)) > 0, name
+        assert "HMMA" not in ops, name
+    log = os.path.join(root, "gan_class_transfer2_b200", "csrc", "conv_umma.ptxas.log")
+    if not os.path.exists(log):
+        return  # (a build artefact of csrc/Makefile: absent when the library was built some other way)
+    with open(log) as f:
+        regs = [int(m) for m in re.findall(r"Used (\d+) registers", f.read())]
+    assert regs and max(r for r in regs if r > 60) <= 128  # 384 threads x 128 registers: three quarters of an SM's file
