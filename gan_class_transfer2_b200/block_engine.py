@@ -29,7 +29,7 @@ reader's part stored raw first and is completed (+=, mask) by the DownShuffle's 
 from __future__ import annotations
 
 import dataclasses
-from typing import List, Optional
+from typing import Callable, List, Optional
 
 import torch
 
@@ -50,6 +50,96 @@ class _Layer:
     res: Optional[torch.Tensor] = None  # "proj": the Residual's input, added in the epilogue (train.py:110-111)
 
 
+def build_layer_list(cfg: NetConfig, image, pair: Callable, alloc_like: Callable):
+    """The layer list of a configuration, by the recursion of the reference's constructor (train.py:175-204).
+
+    Works on anything buffer-shaped: `image` stands for the fp32 noised image, `pair(C, H)` returns a new 16-bit
+    activation buffer [B,H,H,C] and its gradient twin, `alloc_like(buf)` one more buffer of buf's geometry; buffers are
+    sliced as buf[..., a:b] and asked for .shape and .dtype.  The engine passes CUDA tensors, the CPU tests symbolic
+    buffers (tests/test_block_wiring.py checks the forward and backward data flow of every switch combination).
+    Returns (layers, cat, gcat, dense_in, gdense_in)."""
+    n, d, S = cfg.octaves, cfg.block_depth, cfg.size
+    layers: List[_Layer] = []
+    joined = cfg.concat and not cfg.residual  # the skip travels as a channel slice of the level's buffer
+    # one buffer per Residual level: [up_j output | skip] (train.py:113-119), or the up output alone
+    cat, gcat = {}, {}
+    for j in range(n):
+        if (j == 0 and d == 0) or not joined:
+            C = cfg.up_c(j)  # (at the image level the skip is not 16-bit data: Dense reads the image separately)
+        else:
+            C = cfg.res_out(j)
+        cat[j], gcat[j] = pair(C, S >> j)
+
+    def is_image(t) -> bool:
+        return t.dtype == torch.float32
+
+    def skip_view(j: int):
+        """Where the tensor entering level j lives (and its gradient)."""
+        if joined and not (j == 0 and d == 0):
+            return cat[j][..., cfg.up_c(j):], gcat[j][..., cfg.up_c(j):]
+        return pair(cfg.level_in(j), S >> j)
+
+    def add(kind, name, x, gx, y, gy, mask=None, add_old=False, res=None):
+        layers.append(_Layer(kind, name, x, y, gy, gx, x.shape[3] if mask is None else mask, add_old, res))
+
+    def block(prefix, x, gx, filters, H, last=None, first_mask=None):
+        """d stride-1 convs; the last one writes into `last` (a view pair) when given.  Returns the output pair."""
+        for k in range(d):
+            y, gy = last if (k == d - 1 and last is not None) else pair(filters, H)
+            if is_image(x):
+                add("image3", f"{prefix}/conv{k}", x, None, y, gy)
+            else:
+                add("s1", f"{prefix}/conv{k}", x, gx, y, gy, mask=first_mask if k == 0 else None)
+            x, gx = y, gy
+        return x, gx
+
+    def level(i: int, h, gh):
+        """Residual level i on the tensor h (train.py:180-190); returns the level's output pair."""
+        H = S >> (i + 1)
+        nxt = skip_view(i + 1) if i + 1 < n else pair(cfg.down_c(i), H)
+        dy, gdy = nxt if d == 0 else pair(cfg.down_c(i), H)
+        if is_image(h):
+            add("down_image", f"down{i}", h, None, dy, gdy)
+        else:
+            # with a skip (concat) or identity (residual) path h has a second consumer whose raw part is already in gh
+            add("down", f"down{i}", h, gh, dy, gdy, add_old=cfg.concat or cfg.residual)
+        hy, ghy = block(f"block_down{i}", dy, gdy, cfg.down_c(i), H, last=nxt)
+        if i + 1 < n:
+            inner, ginner = level(i + 1, hy, ghy)
+            # what the consumer of level i+1's output may ReLU-mask: the up part of a concat buffer (its skip part is
+            # stored raw), nothing of a residual sum (not a ReLU output), everything otherwise
+            inner_mask = 0 if cfg.residual else (cfg.up_c(i + 1) if cfg.concat else None)
+        else:
+            inner, ginner = block("block_mid", hy, ghy, cfg.mid_c(), H)
+            inner_mask = None
+        if d:
+            u, gu = block(f"block_up{i}", inner, ginner, cfg.down_c(i), H, first_mask=inner_mask)
+            inner_mask = None
+        else:
+            u, gu = inner, ginner
+        out, gout = cat[i][..., :cfg.up_c(i)], gcat[i][..., :cfg.up_c(i)]
+        add("up", f"up{i}", u, gu, out, gout, mask=inner_mask)
+        if cfg.residual:
+            if is_image(h):
+                return out, gout  # image level: the projection onto 3 channels is folded into Dense(3) (_forward)
+            # r = h + Dense(C, use_bias=False)(up_i output).  The gradient of r IS the identity path's part of h's
+            # gradient: r's gradient buffer is h's, and down_i's dgrad completes it in place (add_old)
+            r = alloc_like(h)
+            add("proj", f"res{i}/dense", out, gout, r, gh, res=h)
+            return r, gh
+        return cat[i], gcat[i]
+
+    if d:
+        h0, gh0 = block("block_in", image, None, cfg.outer_c(), S, last=skip_view(0))
+    else:
+        h0, gh0 = image, None
+    top, gtop = level(0, h0, gh0)
+    if d:
+        top_mask = 0 if cfg.residual else (cfg.up_c(0) if cfg.concat else None)
+        top, gtop = block("block_out", top, gtop, cfg.outer_c(), S, first_mask=top_mask)
+    return layers, cat, gcat, top, gtop
+
+
 class BlockUNetEngine(UNetEngine):
     def __init__(self, cfg: NetConfig, batch: int, device=None, dp=None, use_graph: bool = False,
                  share_params_with: Optional[UNetEngine] = None):
@@ -62,10 +152,8 @@ class BlockUNetEngine(UNetEngine):
 
     # ------------------------------------------------------------------------------------------ buffers + layer list
     def _alloc_activations(self) -> None:
-        cfg, dev, B, S = self.cfg, self.device, self.B, self.cfg.size
-        n, d = cfg.octaves, cfg.block_depth
+        cfg, dev, B = self.cfg, self.device, self.B
         self._bufs: List[torch.Tensor] = []
-        self.layers: List[_Layer] = []
 
         def pair(C: int, H: int):
             a = torch.zeros(B, H, H, C, dtype=self.half, device=dev)
@@ -73,82 +161,12 @@ class BlockUNetEngine(UNetEngine):
             self._bufs += [a, g]
             return a, g
 
-        joined = cfg.concat and not cfg.residual  # the skip travels as a channel slice of the level's buffer
-        # one buffer per Residual level: [up_j output | skip] (train.py:113-119), or the up output alone
-        self.cat, self.gcat = {}, {}
-        for j in range(n):
-            if (j == 0 and d == 0) or not joined:
-                C = cfg.up_c(j)  # (at the image level the skip is not 16-bit data: Dense reads the image separately)
-            else:
-                C = cfg.res_out(j)
-            self.cat[j], self.gcat[j] = pair(C, S >> j)
+        def alloc_like(t):
+            r = torch.zeros_like(t)
+            self._bufs.append(r)
+            return r
 
-        def skip_view(j: int):
-            """Where the tensor entering level j lives (and its gradient)."""
-            if joined and not (j == 0 and d == 0):
-                return self.cat[j][..., cfg.up_c(j):], self.gcat[j][..., cfg.up_c(j):]
-            return pair(cfg.level_in(j), S >> j)
-
-        def add(kind, name, x, gx, y, gy, mask=None, add_old=False, res=None):
-            self.layers.append(_Layer(kind, name, x, y, gy, gx, x.shape[3] if mask is None else mask, add_old, res))
-
-        def block(prefix, x, gx, filters, H, last=None, first_mask=None):
-            """d stride-1 convs; the last one writes into `last` (a view pair) when given.  Returns the output pair."""
-            for k in range(d):
-                y, gy = last if (k == d - 1 and last is not None) else pair(filters, H)
-                if x.dtype == torch.float32:
-                    add("image3", f"{prefix}/conv{k}", x, None, y, gy)
-                else:
-                    add("s1", f"{prefix}/conv{k}", x, gx, y, gy, mask=first_mask if k == 0 else None)
-                x, gx = y, gy
-            return x, gx
-
-        def level(i: int, h, gh):
-            """Residual level i on the tensor h (train.py:180-190); returns the level's output pair."""
-            H = S >> (i + 1)
-            nxt = skip_view(i + 1) if i + 1 < n else pair(cfg.down_c(i), H)
-            dy, gdy = nxt if d == 0 else pair(cfg.down_c(i), H)
-            if h.dtype == torch.float32:
-                add("down_image", f"down{i}", h, None, dy, gdy)
-            else:
-                # with a skip (concat) or identity (residual) path h has a second consumer whose raw part is already in gh
-                add("down", f"down{i}", h, gh, dy, gdy, add_old=cfg.concat or cfg.residual)
-            hy, ghy = block(f"block_down{i}", dy, gdy, cfg.down_c(i), H, last=nxt)
-            if i + 1 < n:
-                inner, ginner = level(i + 1, hy, ghy)
-                # what the consumer of level i+1's output may ReLU-mask: the up part of a concat buffer (its skip part is
-                # stored raw), nothing of a residual sum (not a ReLU output), everything otherwise
-                inner_mask = 0 if cfg.residual else (cfg.up_c(i + 1) if cfg.concat else None)
-            else:
-                inner, ginner = block("block_mid", hy, ghy, cfg.mid_c(), H)
-                inner_mask = None
-            if d:
-                u, gu = block(f"block_up{i}", inner, ginner, cfg.down_c(i), H, first_mask=inner_mask)
-                inner_mask = None
-            else:
-                u, gu = inner, ginner
-            out, gout = self.cat[i][..., :cfg.up_c(i)], self.gcat[i][..., :cfg.up_c(i)]
-            add("up", f"up{i}", u, gu, out, gout, mask=inner_mask)
-            if cfg.residual:
-                if h.dtype == torch.float32:
-                    return out, gout  # image level: the projection onto 3 channels is folded into Dense(3) (_forward)
-                # r = h + Dense(C, use_bias=False)(up_i output).  The gradient of r IS the identity path's part of h's
-                # gradient: r's gradient buffer is h's, and down_i's dgrad completes it in place (add_old)
-                r = torch.zeros_like(h)
-                self._bufs.append(r)
-                add("proj", f"res{i}/dense", out, gout, r, gh, res=h)
-                return r, gh
-            return self.cat[i], self.gcat[i]
-
-        if d:
-            h0, gh0 = block("block_in", self.noised, None, cfg.outer_c(), S, last=skip_view(0))
-        else:
-            h0, gh0 = self.noised, None
-        top, gtop = level(0, h0, gh0)
-        if d:
-            top_mask = 0 if cfg.residual else (cfg.up_c(0) if cfg.concat else None)
-            top, gtop = block("block_out", top, gtop, cfg.outer_c(), S, first_mask=top_mask)
-        self.dense_in, self.gdense_in = top, gtop
+        self.layers, self.cat, self.gcat, self.dense_in, self.gdense_in = build_layer_list(cfg, self.noised, pair, alloc_like)
         biggest = max(t.numel() for t in self._bufs)
         self.ws = ops.Workspace(max(4 * 4 * biggest, 64 << 20), dev)
         self.ws_w = self.ws  # one stream: the weight gradients share the scratch
@@ -157,7 +175,7 @@ class BlockUNetEngine(UNetEngine):
         biased = [l for l in self.layers if l.kind != "proj"]
         self._bias_plans = [ops.BiasGradPlan([l.gy for l in chunk], [self.view(self.g, f"{l.name}/bias") for l in chunk])
                             for chunk in (biased[i:i + 16] for i in range(0, len(biased), 16))]
-        self._res0 = cfg.residual and d == 0
+        self._res0 = cfg.residual and cfg.block_depth == 0
         if self._res0:
             U = cfg.up_c(0)
             self._weff = torch.zeros(U + 3, 3, dtype=torch.float32, device=dev)
